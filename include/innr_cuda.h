@@ -1,0 +1,187 @@
+/*
+ * innr_cuda.h -- C-ABI of libinnr_cuda.so: the B200 (sm_100a) device path for innr's batch
+ * similarity-search hot path. This is the drop-in boundary a Rust shim crate (`innr-cuda`, see
+ * INTEGRATION.md) binds with `extern "C"`; every entry point cites the reference interface
+ * (/root/reference, innr 0.6.3) it stands behind.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. Host buffers are caller-owned; the library copies at upload and
+ *    never retains a host pointer. `_dev` entry points take device pointers (and a CUDA stream as
+ *    `void*`) so that a host runtime which already owns device memory (torch, a sharded driver) can call
+ *    the same kernels without a host round trip.
+ *  - Every function returns an `int` status (INNR_OK == 0). No C++ exception crosses the boundary.
+ *    The reference panics (assert_eq!) on length/dimension mismatches; the shim asserts before the FFI
+ *    call so that panic messages stay identical, and the library answers INNR_EINVAL for the same
+ *    conditions. `innr_cuda_last_error()` returns a thread-local message.
+ *  - There is no CPU fallback: without a CUDA device every compute entry returns INNR_ECUDA.
+ *  - Results follow the reference bit for bit on the scan paths: f32 scores of
+ *    batch_dot/l2/cosine/norms and batch_knn* (sequential unfused f32 sum over d), Hamming distances,
+ *    u8 asymmetric scores (32 virtual FMA chains), and every returned index (ties -> lower index).
+ *    MaxSim is within 1e-5 relative (condition-aware) of the reference.
+ *  - Indices: `index_base` is added to local row numbers so a row-sharded corpus reports global
+ *    indices; global indices must be < 2^32 - 1 (the reference truncates ids to u32 at
+ *    src/batch.rs:403).
+ *  - Thread safety: a corpus handle is immutable after upload. Calls are serialised per device by an
+ *    internal mutex (one stream + one workspace per device).
+ */
+#ifndef INNR_CUDA_H
+#define INNR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INNR_OK 0
+#define INNR_EINVAL 1       /* dimension / length mismatch, bad argument (reference: panic) */
+#define INNR_ECUDA 2        /* CUDA runtime failure or no device */
+#define INNR_ENOMEM 3       /* device or host allocation failed */
+#define INNR_EUNSUPPORTED 4 /* shape outside what the kernels cover (message says which) */
+
+/* metric selector for the f32 PDX scans */
+#define INNR_METRIC_DOT 0    /* batch_dot / batch_knn_dot        src/batch.rs:270, :742 */
+#define INNR_METRIC_COSINE 1 /* batch_cosine / batch_knn_cosine  src/batch.rs:690, :777 */
+#define INNR_METRIC_L2 2     /* batch_l2_squared / batch_knn     src/batch.rs:236, :385 */
+
+typedef struct innr_cuda_corpus innr_cuda_corpus; /* opaque, device-resident shard */
+
+/* ---- library / device ---------------------------------------------------------------------- */
+int innr_cuda_device_count(int* out_count);
+/* Binds the calling thread's subsequent calls to `device` and creates its stream/workspace. */
+int innr_cuda_init(int device);
+int innr_cuda_shutdown(void);
+const char* innr_cuda_last_error(void);
+/* Display string of the new `Backend::Cuda` variant (src/backend.rs:18-41: `#[non_exhaustive]` enum,
+ * Display strings are a stability contract) -> "cuda". */
+const char* innr_cuda_backend_name(void);
+/* Device-side analogue of backend::dense_backend(len) (src/backend.rs:46): for a device-resident corpus
+ * every length answers 1 (= Backend::Cuda); kept as a function so the shim mirrors the predicate shape. */
+int innr_cuda_dense_backend(size_t len, int* out_is_cuda);
+/* number of kernels the library has launched so far (bench.py's gpu_launches counter) */
+int innr_cuda_launch_count(uint64_t* out_count);
+
+/* ---- f32 VerticalBatch (PDX) corpus: src/batch.rs:88-220 ------------------------------------- */
+/* host_pdx: the buffer VerticalBatch::data() returns (src/batch.rs:212): data[d*n + i]. */
+int innr_cuda_upload_f32_pdx(const float* host_pdx, size_t n, size_t d, uint64_t index_base,
+                             innr_cuda_corpus** out);
+/* host_rows: row-major n x d (VerticalBatch::from_flat input, src/batch.rs:167); transposed on device. */
+int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64_t index_base,
+                              innr_cuda_corpus** out);
+/* Non-owning view over device memory already in PDX layout with row pitch `ld` floats
+ * (ld >= n, ld % 4 == 0, base 16-byte aligned): dev_pdx[dd*ld + i]. */
+int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t ld, uint64_t index_base,
+                               innr_cuda_corpus** out);
+/* Synthetic corpus generated on the device:
+ * generator 0 = G-hash: row r, dim j -> splitmix64(salt + r*d + j) (uniform [-1,1), 24-bit);
+ * generator 1 = G-ref : row r = generate_embedding(d, seed = salt + r) (examples/batch_demo.rs:233-242).
+ * Rows are [first_row, first_row + n). */
+int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
+                               uint64_t index_base, innr_cuda_corpus** out);
+int innr_cuda_free(innr_cuda_corpus* c);
+/* kind: 0 f32 pdx, 1 binary codes, 2 u8 codes, 3 token matrix */
+int innr_cuda_corpus_info(const innr_cuda_corpus* c, int* kind, size_t* n, size_t* d, size_t* ld,
+                          uint64_t* index_base, size_t* device_bytes);
+/* copies vector i (local index) back to the host: VerticalBatch::extract_vector, src/batch.rs:217 */
+int innr_cuda_extract_vector(const innr_cuda_corpus* c, size_t i, float* out_host);
+
+/* ---- full score vectors: batch_dot / batch_l2_squared / batch_norms / batch_cosine --------------- */
+/* query: host, query_len must equal d (src/batch.rs:251, :285). out_host: n floats. */
+int innr_cuda_batch_dot(const innr_cuda_corpus* c, const float* query, size_t query_len, float* out_host);
+int innr_cuda_batch_l2_squared(const innr_cuda_corpus* c, const float* query, size_t query_len,
+                               float* out_host);
+int innr_cuda_batch_norms(const innr_cuda_corpus* c, float* out_host);
+/* norms: caller-supplied, norms_len must equal n (src/batch.rs:711) */
+int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t query_len,
+                           const float* norms, size_t norms_len, float* out_host);
+
+/* ---- kNN with fused top-k: batch_knn / batch_knn_dot / batch_knn_cosine -------------------------- */
+/* queries: host, n_queries x d row-major. Writes min(k, n) results per query at stride k into out_idx /
+ * out_score (row-major n_queries x k) and the per-query count into *out_count. n == 0 or k == 0 -> count 0.
+ * Order: dot/cosine descending, L2 ascending; ties -> lower index (stable sort, src/batch.rs:756-758). */
+int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                        size_t query_len, size_t k, uint64_t* out_idx, float* out_score, size_t* out_count);
+/* Device-pointer form used for row-sharded corpora: writes the shard's local top-k as sorted 64-bit
+ * composite keys (n_queries x k, padded with 0xFFFF...F) into dev_keys on `stream`. Keys from all shards
+ * are exchanged by the caller (one allgather) and merged with innr_cuda_merge_keys_dev. */
+int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const float* dev_queries,
+                                 size_t n_queries, size_t k, uint64_t* dev_keys, void* stream);
+/* dev_keys_in: n_lists x n_queries x k sorted key lists. Writes the merged top-k per query as keys
+ * (dev_keys_out, may be NULL) and decoded (dev_idx u64, dev_score f32; either may be NULL).
+ * metric selects the key decoding (descending for dot/cosine, ascending for L2). */
+int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k,
+                             int metric, uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score,
+                             void* stream);
+
+/* ---- TopK (src/topk.rs:47-187) as one fused selection ------------------------------------------- */
+/* Equivalent to inserting (id = i, distances[i]) for i = 0..n-1 and calling into_sorted(): the k smallest
+ * by (total_cmp(distance), id). Exact ties at the boundary: see DESIGN.md (row T). */
+int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, uint32_t* out_id,
+                                  float* out_distance, size_t* out_count);
+
+/* ---- packed binary codes: src/binary.rs:37-165 -------------------------------------------------- */
+/* words: host, n x ceil(dim_bits/64) u64 (PackedBinary::data(), LSB-first). Padding bits of the last word
+ * are masked on upload (PackedBinary::new, src/binary.rs:59-66). */
+int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, uint64_t index_base,
+                            innr_cuda_corpus** out);
+/* generator: word w of code r = splitmix64(salt + r*words + w) */
+int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t dim_bits,
+                              uint64_t index_base, innr_cuda_corpus** out);
+/* binary_hamming (src/binary.rs:154) of the query against every code: out_host n x u32. query_dim_bits
+ * must equal the corpus dimension (src/binary.rs:155-159). */
+int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                          uint32_t* out_host);
+/* caller composition examples/binary_demo.rs:174-180: all distances, stable sort_by_key, take(k). */
+int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
+                           size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,
+                           size_t* out_count);
+int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* dev_query_words,
+                                    size_t n_queries, size_t k, uint64_t* dev_keys, void* stream);
+/* encode_binary (src/binary.rs:133-141): bit i = values[i] > threshold; out_words ceil(n/64) u64 */
+int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words);
+
+/* ---- scalar-quantised u8 codes: src/scalar.rs:44-393 --------------------------------------------- */
+/* rows: host, n x d bytes (each QuantizedU8::data() packed contiguously by the shim). */
+int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, float offset,
+                        uint64_t index_base, innr_cuda_corpus** out);
+/* G-hash f32 rows (salt + r*d + j) quantised on the device with quantize_u8's formula (src/scalar.rs:212-225) */
+int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
+                          uint64_t index_base, innr_cuda_corpus** out);
+/* quantize_u8 (src/scalar.rs:212-225) of a host f32 buffer */
+int innr_cuda_quantize_u8(const float* values, size_t n, float alpha, float offset, uint8_t* out_codes);
+/* mixed_dot_u8_f32 (src/scalar.rs:314) of the query against every row: out_host n floats */
+int innr_cuda_mixed_dot_u8_all(const innr_cuda_corpus* c, const float* query, size_t query_len,
+                               float* out_host);
+/* asymmetric_dot_u8 (src/scalar.rs:261-300) of the query against every row */
+int innr_cuda_asymmetric_dot_u8_all(const innr_cuda_corpus* c, const float* query, size_t query_len,
+                                    float* out_host);
+/* batch_knn_u8 (src/scalar.rs:370-393): descending, ties -> lower index */
+int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size_t n_queries,
+                           size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
+                           size_t* out_count);
+int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_queries, size_t n_queries,
+                                    size_t k, uint64_t* dev_keys, void* stream);
+
+/* ---- ColBERT MaxSim over a document set: src/maxsim.rs:96-194 ------------------------------------ */
+/* tokens: host, total_tokens x dim row-major; doc j owns rows [doc_offsets[j], doc_offsets[j+1]). */
+int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, size_t n_docs, size_t dim,
+                            uint64_t index_base, innr_cuda_corpus** out);
+/* G-hash token rows (salt + row*dim + j), every doc `tokens_per_doc` tokens; docs [first_doc, first_doc+n_docs) */
+int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, size_t tokens_per_doc,
+                              size_t dim, uint64_t index_base, innr_cuda_corpus** out);
+/* maxsim (cosine_flag 0) / maxsim_cosine (1) of the query token set against every doc:
+ * out_scores_host n_docs floats. Empty query or empty doc -> 0.0 (src/maxsim.rs:97-99). q_dim must equal dim. */
+int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_q, size_t q_dim,
+                     int cosine_flag, float* out_scores_host);
+int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_q, int cosine_flag,
+                         float* dev_scores, void* stream);
+
+/* ---- timing hook for bench.py: average device time (ms) of the last call's dominant kernel, measured with
+ *      CUDA events on the launching stream ---------------------------------------------------------- */
+int innr_cuda_last_kernel_ms(float* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INNR_CUDA_H */

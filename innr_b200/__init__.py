@@ -1,0 +1,17 @@
+"""innr_b200 -- B200-native (sm_100a) device path for innr's batch similarity-search hot path.
+
+The product is libinnr_cuda.so (hand-written CUDA behind the C-ABI in include/innr_cuda.h). This package is the
+host-side mirror of the reference's API for that path (same names, arguments and error behaviour as
+innr::batch / innr::binary / innr::scalar / innr::maxsim / innr::backend) so the parity tests read like the
+reference's own tests. No CPU fallback: without the shared library or a CUDA device, calls raise.
+"""
+from ._lib import InnrCudaError, backend_name, build, init, last_kernel_ms, launch_count, lib  # noqa: F401
+from .backend import Backend, dense_backend  # noqa: F401
+from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, batch_dot, batch_knn,  # noqa: F401
+                    batch_knn_cosine, batch_knn_dot, batch_knn_many, batch_l2_squared, batch_norms)
+from .binary import (BinaryCorpus, PackedBinary, binary_hamming, encode_binary, hamming_all,  # noqa: F401
+                     hamming_topk, hamming_topk_many)
+from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_cosine  # noqa: F401
+from .scalar import (QuantizationParams, QuantizedU8, U8Corpus, asymmetric_dot_u8, asymmetric_dot_u8_all,  # noqa: F401
+                     batch_knn_u8, batch_knn_u8_many, mixed_dot_u8_all, mixed_dot_u8_f32, quantize_u8)
+from .topk import topk_from_distances  # noqa: F401

@@ -1,0 +1,1011 @@
+// api.cu -- the C-ABI of libinnr_cuda.so (include/innr_cuda.h): handles, per-device stream + workspace,
+// host<->device staging, argument checks that mirror the reference's panics. No torch, no CPU fallback.
+#include "../../include/innr_cuda.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace innr;
+
+struct innr_cuda_corpus {
+  int kind = 0;  // 0 f32 pdx, 1 binary, 2 u8, 3 tokens
+  int device = 0;
+  bool owns = true;
+  void* dev = nullptr;
+  size_t bytes = 0;
+  size_t n = 0, d = 0, ld = 0;
+  uint64_t index_base = 0;
+  // binary
+  size_t words = 0, chunks = 0, dim_bits = 0;
+  // u8
+  float alpha = 1.0f, offset = 0.0f;
+  // tokens
+  uint64_t* dev_offsets = nullptr;
+  size_t total_tokens = 0, uniform_tokens = 0;
+};
+
+namespace {
+
+constexpr int MAX_DEVICES = 16;
+constexpr size_t MAX_FUSED_K = 128;
+
+struct Buf {  // growable device or pinned-host scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) {
+      if (pinned) cudaFreeHost(p); else cudaFree(p);
+      p = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+    cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) {
+      if (pinned) cudaFreeHost(p); else cudaFree(p);
+    }
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct DeviceCtx {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Workspace ws;
+  Buf d_query, d_keys, d_scores, d_aux, h_pin;
+  float last_ms = 0.0f;
+};
+
+std::mutex g_mu;
+DeviceCtx g_ctx[MAX_DEVICES];
+uint64_t g_launches = 0;
+thread_local int t_device = -1;
+thread_local std::string t_err;
+
+int fail(int code, const std::string& msg) {
+  t_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  cudaGetLastError();  // clear sticky-less error state
+  return fail(e == cudaErrorMemoryAllocation ? INNR_ENOMEM : INNR_ECUDA,
+              std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                   \
+  do {                                             \
+    cudaError_t e__ = (call);                      \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+int ensure_ctx(int device, DeviceCtx** out) {
+  if (device < 0 || device >= MAX_DEVICES) return fail(INNR_EINVAL, "device index out of range");
+  DeviceCtx& c = g_ctx[device];
+  if (!c.ready) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      cudaGetLastError();
+      return fail(INNR_ECUDA, "no CUDA device available (libinnr_cuda has no CPU fallback)");
+    }
+    if (device >= count) return fail(INNR_EINVAL, "device index >= device count");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c.device = device;
+    c.ws.num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c.ev0));
+    CU(cudaEventCreate(&c.ev1));
+    // per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
+    c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32;
+    CU(cudaMalloc(&c.ws.partials, c.ws.partials_cap * sizeof(uint64_t)));
+    CU(cudaMalloc(&c.ws.ticket, sizeof(unsigned)));
+    CU(cudaMemset(c.ws.ticket, 0, sizeof(unsigned)));
+    c.h_pin.pinned = true;
+    c.ready = true;
+  } else {
+    CU(cudaSetDevice(device));
+  }
+  *out = &c;
+  return INNR_OK;
+}
+
+int current_ctx(DeviceCtx** out) {
+  if (t_device < 0) t_device = 0;
+  return ensure_ctx(t_device, out);
+}
+
+int ctx_for(const innr_cuda_corpus* c, DeviceCtx** out) { return ensure_ctx(c->device, out); }
+
+size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+int check_index_range(size_t n, uint64_t index_base) {
+  if (index_base + n >= 0xFFFFFFFFull) return fail(INNR_EUNSUPPORTED, "global indices must be < 2^32 - 1");
+  return INNR_OK;
+}
+
+struct Timed {  // records the device time of the kernels launched in its scope
+  DeviceCtx& c;
+  explicit Timed(DeviceCtx& ctx) : c(ctx) { cudaEventRecord(c.ev0, c.stream); }
+  void stop() { cudaEventRecord(c.ev1, c.stream); }
+  void finish() { cudaEventElapsedTime(&c.last_ms, c.ev0, c.ev1); }
+};
+
+// decode sorted composite keys on the host
+void decode_keys_f32(const uint64_t* keys, size_t count, bool descending, uint64_t* out_idx, float* out_score) {
+  for (size_t j = 0; j < count; ++j) {
+    uint32_t hi = (uint32_t)(keys[j] >> 32);
+    if (descending) hi = ~hi;
+    uint32_t bits = order_bits_to_f32_bits(hi);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    out_idx[j] = keys[j] & 0xFFFFFFFFull;
+    out_score[j] = f;
+  }
+}
+
+int new_corpus(int kind, int device, innr_cuda_corpus** out) {
+  *out = new (std::nothrow) innr_cuda_corpus();
+  if (!*out) return fail(INNR_ENOMEM, "host allocation failed");
+  (*out)->kind = kind;
+  (*out)->device = device;
+  return INNR_OK;
+}
+
+PdxView pdx_view(const innr_cuda_corpus* c) {
+  return PdxView{(const float*)c->dev, c->n, c->d, c->ld, (uint32_t)c->index_base};
+}
+BinView bin_view(const innr_cuda_corpus* c) {
+  return BinView{(const uint4*)c->dev, c->n, c->ld, c->words, c->chunks, c->dim_bits, (uint32_t)c->index_base};
+}
+U8View u8_view(const innr_cuda_corpus* c) {
+  return U8View{(const uint4*)c->dev, c->n, c->d, c->ld, c->chunks, c->alpha, c->offset, (uint32_t)c->index_base};
+}
+TokView tok_view(const innr_cuda_corpus* c) {
+  return TokView{(const float*)c->dev, c->dev_offsets, c->n, c->d, c->total_tokens, c->uniform_tokens};
+}
+
+// Shared tail of every host-facing top-k call: keys device -> pinned -> decode.
+template <class Decode>
+int fetch_keys(DeviceCtx& ctx, size_t nq, size_t kk, Timed& tm, Decode decode) {
+  CU(ctx.h_pin.reserve(nq * kk * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx.h_pin.p, ctx.d_keys.p, nq * kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.stream));
+  CU(cudaStreamSynchronize(ctx.stream));
+  tm.finish();
+  decode((const uint64_t*)ctx.h_pin.p);
+  return INNR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int innr_cuda_device_count(int* out_count) {
+  if (!out_count) return fail(INNR_EINVAL, "null out_count");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    count = 0;
+  }
+  *out_count = count;
+  return INNR_OK;
+}
+
+int innr_cuda_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* c;
+  int rc = ensure_ctx(device, &c);
+  if (rc == INNR_OK) t_device = device;
+  return rc;
+}
+
+int innr_cuda_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int i = 0; i < MAX_DEVICES; ++i) {
+    DeviceCtx& c = g_ctx[i];
+    if (!c.ready) continue;
+    cudaSetDevice(i);
+    cudaStreamSynchronize(c.stream);
+    c.d_query.release(); c.d_keys.release(); c.d_scores.release(); c.d_aux.release(); c.h_pin.release();
+    cudaFree(c.ws.partials);
+    cudaFree(c.ws.ticket);
+    cudaEventDestroy(c.ev0);
+    cudaEventDestroy(c.ev1);
+    cudaStreamDestroy(c.stream);
+    c = DeviceCtx();
+  }
+  return INNR_OK;
+}
+
+const char* innr_cuda_last_error(void) { return t_err.c_str(); }
+const char* innr_cuda_backend_name(void) { return "cuda"; }
+int innr_cuda_dense_backend(size_t len, int* out_is_cuda) {
+  (void)len;
+  if (!out_is_cuda) return fail(INNR_EINVAL, "null out");
+  *out_is_cuda = 1;
+  return INNR_OK;
+}
+int innr_cuda_launch_count(uint64_t* out_count) {
+  if (!out_count) return fail(INNR_EINVAL, "null out");
+  *out_count = g_launches;
+  return INNR_OK;
+}
+int innr_cuda_last_kernel_ms(float* out_ms) {
+  if (!out_ms) return fail(INNR_EINVAL, "null out");
+  DeviceCtx* c;
+  int rc = current_ctx(&c);
+  if (rc) return rc;
+  *out_ms = c->last_ms;
+  return INNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ f32 PDX corpus
+static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, innr_cuda_corpus** out) {
+  int rc = check_index_range(n, index_base);
+  if (rc) return rc;
+  rc = new_corpus(0, ctx.device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n;
+  c->d = d;
+  c->ld = round_up(n, 64);
+  c->index_base = index_base;
+  c->bytes = c->ld * d * sizeof(float);
+  if (c->bytes) {
+    cudaError_t e = cudaMalloc(&c->dev, c->bytes);
+    if (e != cudaSuccess) {
+      delete c;
+      *out = nullptr;
+      return cuda_fail(e, "cudaMalloc(corpus)");
+    }
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_upload_f32_pdx(const float* host_pdx, size_t n, size_t d, uint64_t index_base,
+                             innr_cuda_corpus** out) {
+  if (!out || (!host_pdx && n * d)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_pdx(*ctx, n, d, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(cudaMemsetAsync(c->dev, 0, c->bytes, ctx->stream));
+    CU(cudaMemcpy2DAsync(c->dev, c->ld * sizeof(float), host_pdx, n * sizeof(float), n * sizeof(float), d,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64_t index_base,
+                              innr_cuda_corpus** out) {
+  if (!out || (!host_rows && n * d)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_pdx(*ctx, n, d, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, n * d * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(stage, host_rows, n * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = launch_transpose_rows_to_pdx((const float*)stage, n, d, (float*)c->dev, c->ld, ctx->stream, &g_launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "upload_f32_rows");
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t ld, uint64_t index_base,
+                               innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  if (ld < n || (ld % 4) != 0 || ((uintptr_t)dev_pdx % 16) != 0)
+    return fail(INNR_EINVAL, "wrap_f32_pdx_dev: need ld >= n, ld % 4 == 0, 16-byte aligned base");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = check_index_range(n, index_base);
+  if (rc) return rc;
+  rc = new_corpus(0, ctx->device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->owns = false;
+  c->dev = (void*)dev_pdx;
+  c->n = n;
+  c->d = d;
+  c->ld = ld;
+  c->index_base = index_base;
+  c->bytes = ld * d * sizeof(float);
+  return INNR_OK;
+}
+
+int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
+                               uint64_t index_base, innr_cuda_corpus** out) {
+  if (!out || (generator != 0 && generator != 1)) return fail(INNR_EINVAL, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_pdx(*ctx, n, d, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_generate_f32_pdx(generator, salt, first_row, n, d, (float*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_free(innr_cuda_corpus* c) {
+  if (!c) return INNR_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  cudaSetDevice(c->device);
+  if (c->owns && c->dev) cudaFree(c->dev);
+  if (c->dev_offsets) cudaFree(c->dev_offsets);
+  delete c;
+  return INNR_OK;
+}
+
+int innr_cuda_corpus_info(const innr_cuda_corpus* c, int* kind, size_t* n, size_t* d, size_t* ld,
+                          uint64_t* index_base, size_t* device_bytes) {
+  if (!c) return fail(INNR_EINVAL, "null corpus");
+  if (kind) *kind = c->kind;
+  if (n) *n = c->n;
+  if (d) *d = c->kind == 1 ? c->dim_bits : c->d;
+  if (ld) *ld = c->ld;
+  if (index_base) *index_base = c->index_base;
+  if (device_bytes) *device_bytes = c->bytes;
+  return INNR_OK;
+}
+
+int innr_cuda_extract_vector(const innr_cuda_corpus* c, size_t i, float* out_host) {
+  if (!c || c->kind != 0 || !out_host) return fail(INNR_EINVAL, "extract_vector: need an f32 corpus");
+  if (i >= c->n) return fail(INNR_EINVAL, "extract_vector: index out of bounds");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  if (c->d == 0) return INNR_OK;
+  CU(cudaMemcpy2DAsync(out_host, sizeof(float), (const float*)c->dev + i, c->ld * sizeof(float), sizeof(float),
+                       c->d, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return INNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ full score vectors
+static int pdx_scores(const innr_cuda_corpus* c, int mode, const float* query, size_t query_len,
+                      const float* norms, size_t norms_len, float* out_host) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (mode == PDX_COSINE_NORMS && norms_len != c->n)
+    return fail(INNR_EINVAL, "batch_cosine: norms.len() != batch.num_vectors");     // src/batch.rs:711
+  if (mode != PDX_NORMS && query_len != c->d)
+    return fail(INNR_EINVAL, "query.len() != batch.dimension");                       // src/batch.rs:251,285
+  if (c->n == 0) return INNR_OK;
+  if (!out_host || (mode != PDX_NORMS && !query && c->d)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+  if (mode != PDX_NORMS && c->d)
+    CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (mode == PDX_COSINE_NORMS) {
+    CU(ctx->d_aux.reserve(c->n * sizeof(float)));
+    CU(cudaMemcpyAsync(ctx->d_aux.p, norms, c->n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  Timed tm(*ctx);
+  CU(launch_pdx_scores(pdx_view(c), mode, (const float*)ctx->d_query.p, (const float*)ctx->d_aux.p,
+                       (float*)ctx->d_scores.p, ctx->ws, ctx->stream, &g_launches));
+  tm.stop();
+  CU(cudaMemcpyAsync(out_host, ctx->d_scores.p, c->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+int innr_cuda_batch_dot(const innr_cuda_corpus* c, const float* query, size_t query_len, float* out_host) {
+  return pdx_scores(c, PDX_DOT, query, query_len, nullptr, 0, out_host);
+}
+int innr_cuda_batch_l2_squared(const innr_cuda_corpus* c, const float* query, size_t query_len, float* out_host) {
+  return pdx_scores(c, PDX_L2, query, query_len, nullptr, 0, out_host);
+}
+int innr_cuda_batch_norms(const innr_cuda_corpus* c, float* out_host) {
+  return pdx_scores(c, PDX_NORMS, nullptr, 0, nullptr, 0, out_host);
+}
+int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t query_len, const float* norms,
+                           size_t norms_len, float* out_host) {
+  return pdx_scores(c, PDX_COSINE_NORMS, query, query_len, norms, norms_len, out_host);
+}
+
+// ------------------------------------------------------------------------------------------ kNN
+static int metric_to_mode(int metric, int* mode) {
+  switch (metric) {
+    case INNR_METRIC_DOT: *mode = PDX_DOT; return INNR_OK;
+    case INNR_METRIC_COSINE: *mode = PDX_COSINE_FUSED; return INNR_OK;
+    case INNR_METRIC_L2: *mode = PDX_L2; return INNR_OK;
+  }
+  return fail(INNR_EINVAL, "unknown metric");
+}
+
+int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                        size_t query_len, size_t k, uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:386,743,778
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;                           // src/batch.rs:388-393
+  if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < c->n ? k : c->n;                                               // k.min(num_vectors)
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((n_queries * c->d + 4) * sizeof(float)));
+  CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
+  if (c->d)
+    CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_pdx_knn(pdx_view(c), mode, (const float*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p,
+                    ctx->ws, ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
+    for (size_t q = 0; q < n_queries; ++q)
+      decode_keys_f32(keys + q * kk, kk, metric != INNR_METRIC_L2, out_idx + q * k, out_score + q * k);
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const float* dev_queries,
+                                 size_t n_queries, size_t k, uint64_t* dev_keys, void* stream) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  if (k == 0 || n_queries == 0) return INNR_OK;
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->n == 0) {
+    CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
+    return INNR_OK;
+  }
+  CU(launch_pdx_knn(pdx_view(c), mode, dev_queries, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
+  return INNR_OK;
+}
+
+int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,
+                             uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, void* stream) {
+  if (k == 0 || n_queries == 0 || n_lists == 0) return INNR_OK;
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  CU(launch_merge_keys(dev_keys_in, n_lists, n_queries, k, metric != INNR_METRIC_L2, dev_keys_out, dev_idx, dev_score,
+                       (cudaStream_t)stream, &g_launches));
+  return INNR_OK;
+}
+
+int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, uint32_t* out_id, float* out_distance,
+                                  size_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (n == 0 || k == 0) return INNR_OK;
+  if (!distances || !out_id || !out_distance) return fail(INNR_EINVAL, "null argument");
+  int rc = check_index_range(n, 0);
+  if (rc) return rc;
+  const size_t kk = k < n ? k : n;
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  rc = current_ctx(&ctx);
+  if (rc) return rc;
+  CU(ctx->d_scores.reserve(n * sizeof(float)));
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx->d_scores.p, distances, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_topk_from_distances((const float*)ctx->d_scores.p, n, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                                ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) {
+    std::vector<uint64_t> idx(kk);
+    decode_keys_f32(keys, kk, false, idx.data(), out_distance);
+    for (size_t j = 0; j < kk; ++j) out_id[j] = (uint32_t)idx[j];
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ binary codes
+static int alloc_binary(DeviceCtx& ctx, size_t n, size_t dim_bits, uint64_t index_base, innr_cuda_corpus** out) {
+  int rc = check_index_range(n, index_base);
+  if (rc) return rc;
+  rc = new_corpus(1, ctx.device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n;
+  c->dim_bits = dim_bits;
+  c->words = (dim_bits + 63) / 64;
+  c->chunks = (c->words + 1) / 2;
+  c->d = dim_bits;
+  c->ld = round_up(n, 16);
+  c->index_base = index_base;
+  c->bytes = c->chunks * c->ld * sizeof(uint4);
+  if (c->bytes) {
+    cudaError_t e = cudaMalloc(&c->dev, c->bytes);
+    if (e != cudaSuccess) {
+      delete c;
+      *out = nullptr;
+      return cuda_fail(e, "cudaMalloc(binary corpus)");
+    }
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, uint64_t index_base,
+                            innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_binary(*ctx, n, dim_bits, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    if (!words) return fail(INNR_EINVAL, "null words");
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, n * c->words * sizeof(uint64_t)));
+    cudaError_t e = cudaMemcpyAsync(stage, words, n * c->words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = launch_binary_pack((const uint64_t*)stage, n, c->words, dim_bits, (uint4*)c->dev, c->ld, ctx->stream, &g_launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "upload_binary");
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t dim_bits, uint64_t index_base,
+                              innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_binary(*ctx, n, dim_bits, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_generate_binary(salt, first_row, n, c->words, dim_bits, (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+// copies nq query codes (row-major words) to the device, padded to 2*chunks words each and masked
+static int stage_binary_queries(DeviceCtx& ctx, const innr_cuda_corpus* c, const uint64_t* query_words, size_t nq) {
+  const size_t qw = 2 * c->chunks;
+  CU(ctx.h_pin.reserve(nq * qw * sizeof(uint64_t)));
+  uint64_t* h = (uint64_t*)ctx.h_pin.p;
+  const size_t rem = c->dim_bits % 64;
+  for (size_t q = 0; q < nq; ++q)
+    for (size_t w = 0; w < qw; ++w) {
+      uint64_t x = w < c->words ? query_words[q * c->words + w] : 0;
+      if (w + 1 == c->words && rem) x &= (1ull << rem) - 1;  // PackedBinary::new masks padding
+      h[q * qw + w] = x;
+    }
+  CU(ctx.d_query.reserve(nq * qw * sizeof(uint64_t) + 16));
+  CU(cudaMemcpyAsync(ctx.d_query.p, h, nq * qw * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx.stream));
+  return INNR_OK;
+}
+
+int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                          uint32_t* out_host) {
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (query_dim_bits != c->dim_bits)
+    return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");             // src/binary.rs:155-159
+  if (c->n == 0) return INNR_OK;
+  if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  if (c->words == 0) {
+    std::memset(out_host, 0, c->n * sizeof(uint32_t));
+    return INNR_OK;
+  }
+  rc = stage_binary_queries(*ctx, c, query_words, 1);
+  if (rc) return rc;
+  CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
+  Timed tm(*ctx);
+  CU(launch_hamming_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (uint32_t*)ctx->d_scores.p, ctx->stream,
+                        &g_launches));
+  tm.stop();
+  CU(cudaMemcpyAsync(out_host, ctx->d_scores.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
+                           size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,
+                           size_t* out_count) {
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;
+  if (!out_idx || !out_dist || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < c->n ? k : c->n;
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  if (c->words == 0) {  // zero-dimensional codes: every distance is 0 -> first kk indices
+    for (size_t q = 0; q < n_queries; ++q)
+      for (size_t j = 0; j < kk; ++j) {
+        out_idx[q * k + j] = c->index_base + j;
+        out_dist[q * k + j] = 0;
+      }
+    if (out_count) *out_count = kk;
+    return INNR_OK;
+  }
+  rc = stage_binary_queries(*ctx, c, query_words, n_queries);
+  if (rc) return rc;
+  CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
+  Timed tm(*ctx);
+  CU(launch_hamming_topk(bin_view(c), (const uint64_t*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p,
+                         ctx->ws, ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
+    for (size_t q = 0; q < n_queries; ++q)
+      for (size_t j = 0; j < kk; ++j) {
+        out_idx[q * k + j] = keys[q * kk + j] & 0xFFFFFFFFull;
+        out_dist[q * k + j] = (uint32_t)(keys[q * kk + j] >> 32);
+      }
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* dev_query_words, size_t n_queries,
+                                    size_t k, uint64_t* dev_keys, void* stream) {
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (k == 0 || n_queries == 0) return INNR_OK;
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->n == 0 || c->words == 0) {
+    CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
+    return INNR_OK;
+  }
+  CU(launch_hamming_topk(bin_view(c), dev_query_words, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
+  return INNR_OK;
+}
+
+int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words) {
+  if (n == 0) return INNR_OK;
+  if (!values || !out_words) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  const size_t nw = (n + 63) / 64;
+  CU(ctx->d_scores.reserve(n * sizeof(float)));
+  CU(ctx->d_aux.reserve(nw * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx->d_scores.p, values, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_encode_binary((const float*)ctx->d_scores.p, n, threshold, (uint64_t*)ctx->d_aux.p, ctx->stream, &g_launches));
+  CU(cudaMemcpyAsync(out_words, ctx->d_aux.p, nw * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return INNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ u8 codes
+static int alloc_u8(DeviceCtx& ctx, size_t n, size_t d, float alpha, float offset, uint64_t index_base,
+                    innr_cuda_corpus** out) {
+  int rc = check_index_range(n, index_base);
+  if (rc) return rc;
+  rc = new_corpus(2, ctx.device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n;
+  c->d = d;
+  c->chunks = (d + 15) / 16;
+  c->ld = round_up(n, 16);
+  c->alpha = alpha;
+  c->offset = offset;
+  c->index_base = index_base;
+  c->bytes = c->chunks * c->ld * sizeof(uint4);
+  if (c->bytes) {
+    cudaError_t e = cudaMalloc(&c->dev, c->bytes);
+    if (e != cudaSuccess) {
+      delete c;
+      *out = nullptr;
+      return cuda_fail(e, "cudaMalloc(u8 corpus)");
+    }
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, float offset, uint64_t index_base,
+                        innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_u8(*ctx, n, d, alpha, offset, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    if (!rows) return fail(INNR_EINVAL, "null rows");
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, n * d));
+    cudaError_t e = cudaMemcpyAsync(stage, rows, n * d, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_u8_pack((const uint8_t*)stage, n, d, (uint4*)c->dev, c->ld, ctx->stream, &g_launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "upload_u8");
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
+                          uint64_t index_base, innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_u8(*ctx, n, d, alpha, offset, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_generate_u8(salt, first_row, n, d, alpha, offset, (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_quantize_u8(const float* values, size_t n, float alpha, float offset, uint8_t* out_codes) {
+  if (n == 0) return INNR_OK;
+  if (!values || !out_codes) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  CU(ctx->d_scores.reserve(n * sizeof(float)));
+  CU(ctx->d_aux.reserve(n));
+  CU(cudaMemcpyAsync(ctx->d_scores.p, values, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_quantize_u8((const float*)ctx->d_scores.p, n, alpha, offset, (uint8_t*)ctx->d_aux.p, ctx->stream, &g_launches));
+  CU(cudaMemcpyAsync(out_codes, ctx->d_aux.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return INNR_OK;
+}
+
+static int u8_scores(const innr_cuda_corpus* c, int mode, const float* query, size_t query_len, float* out_host,
+                     const char* mismatch_msg) {
+  if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
+  if (query_len != c->d) return fail(INNR_EINVAL, mismatch_msg);
+  if (c->n == 0) return INNR_OK;
+  if (!out_host || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(c->n * sizeof(float)));
+  if (c->d) CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (c->d == 0) {
+    // mixed dot of empty vectors is 0.0; asymmetric adds offset * 0.0
+    for (size_t i = 0; i < c->n; ++i) out_host[i] = 0.0f;
+    return INNR_OK;
+  }
+  Timed tm(*ctx);
+  CU(launch_u8_scores(u8_view(c), mode, (const float*)ctx->d_query.p, (float*)ctx->d_scores.p, ctx->stream, &g_launches));
+  tm.stop();
+  CU(cudaMemcpyAsync(out_host, ctx->d_scores.p, c->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+int innr_cuda_mixed_dot_u8_all(const innr_cuda_corpus* c, const float* query, size_t query_len, float* out_host) {
+  return u8_scores(c, 0, query, query_len, out_host, "mixed_dot_u8_f32: slice length mismatch");
+}
+int innr_cuda_asymmetric_dot_u8_all(const innr_cuda_corpus* c, const float* query, size_t query_len, float* out_host) {
+  return u8_scores(c, 1, query, query_len, out_host, "asymmetric_dot_u8: dimension mismatch");
+}
+
+int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size_t n_queries, size_t query_len,
+                           size_t k, uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;  // src/scalar.rs:376-378 (before any length check)
+  if (query_len != c->d) return fail(INNR_EINVAL, "asymmetric_dot_u8_precomputed: dimension mismatch");
+  if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < c->n ? k : c->n;
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((n_queries * c->d + 4) * sizeof(float)));
+  CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_u8_knn(u8_view(c), (const float*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                   ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
+    for (size_t q = 0; q < n_queries; ++q) decode_keys_f32(keys + q * kk, kk, true, out_idx + q * k, out_score + q * k);
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_queries, size_t n_queries, size_t k,
+                                    uint64_t* dev_keys, void* stream) {
+  if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
+  if (k == 0 || n_queries == 0) return INNR_OK;
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (c->n == 0 || c->d == 0) {
+    CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
+    return INNR_OK;
+  }
+  CU(launch_u8_knn(u8_view(c), dev_queries, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
+  return INNR_OK;
+}
+
+// ------------------------------------------------------------------------------------------ MaxSim
+int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, size_t n_docs, size_t dim,
+                            uint64_t index_base, innr_cuda_corpus** out) {
+  if (!out || (n_docs && !doc_offsets)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  size_t total = n_docs ? (size_t)doc_offsets[n_docs] : 0;
+  if (n_docs && doc_offsets[0] != 0) return fail(INNR_EINVAL, "doc_offsets[0] must be 0");
+  for (size_t j = 0; j < n_docs; ++j)
+    if (doc_offsets[j + 1] < doc_offsets[j]) return fail(INNR_EINVAL, "doc_offsets must be non-decreasing");
+  if (total * dim && !tokens) return fail(INNR_EINVAL, "null tokens");
+  rc = new_corpus(3, ctx->device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n_docs;
+  c->d = dim;
+  c->index_base = index_base;
+  c->total_tokens = total;
+  c->bytes = total * dim * sizeof(float);
+  if (c->bytes) {
+    CU(cudaMalloc(&c->dev, c->bytes));
+    CU(cudaMemcpyAsync(c->dev, tokens, c->bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (n_docs) {
+    CU(cudaMalloc(&c->dev_offsets, (n_docs + 1) * sizeof(uint64_t)));
+    CU(cudaMemcpyAsync(c->dev_offsets, doc_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return INNR_OK;
+}
+
+int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, size_t tokens_per_doc, size_t dim,
+                              uint64_t index_base, innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = new_corpus(3, ctx->device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n_docs;
+  c->d = dim;
+  c->index_base = index_base;
+  c->total_tokens = n_docs * tokens_per_doc;
+  c->uniform_tokens = tokens_per_doc;
+  c->bytes = c->total_tokens * dim * sizeof(float);
+  if (c->bytes) {
+    CU(cudaMalloc(&c->dev, c->bytes));
+    CU(launch_generate_tokens(salt, first_doc * tokens_per_doc, c->total_tokens, dim, (float*)c->dev, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+static int maxsim_common(const innr_cuda_corpus* c, DeviceCtx* ctx, const float* dev_q, size_t n_q, int cosine,
+                         float* dev_scores, cudaStream_t s) {
+  if (n_q == 0 || c->total_tokens == 0 || c->d == 0) {
+    // empty query or all-empty docs -> 0.0 (src/maxsim.rs:97-99); zero-dim tokens dot to 0.0 as well
+    if (c->n) CU(cudaMemsetAsync(dev_scores, 0, c->n * sizeof(float), s));
+    return INNR_OK;
+  }
+  cudaError_t e = launch_maxsim(tok_view(c), dev_q, n_q, cosine, dev_scores, s, &g_launches);
+  if (e == cudaErrorInvalidValue) return fail(INNR_EUNSUPPORTED, "maxsim: dim / n_q exceed the shared-memory tile");
+  if (e != cudaSuccess) return cuda_fail(e, "launch_maxsim");
+  (void)ctx;
+  return INNR_OK;
+}
+
+int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_q, size_t q_dim, int cosine_flag,
+                     float* out_scores_host) {
+  if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
+  if (n_q && c->total_tokens && q_dim != c->d) return fail(INNR_EINVAL, "dimension mismatch (doc)");  // src/maxsim.rs:107-110
+  if (c->n == 0) return INNR_OK;
+  if (!out_scores_host || (n_q * q_dim && !q_tokens)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((n_q * c->d + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(c->n * sizeof(float)));
+  if (n_q * c->d && c->total_tokens)
+    CU(cudaMemcpyAsync(ctx->d_query.p, q_tokens, n_q * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  rc = maxsim_common(c, ctx, (const float*)ctx->d_query.p, n_q, cosine_flag, (float*)ctx->d_scores.p, ctx->stream);
+  if (rc) return rc;
+  tm.stop();
+  CU(cudaMemcpyAsync(out_scores_host, ctx->d_scores.p, c->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_q, int cosine_flag,
+                         float* dev_scores, void* stream) {
+  if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
+  if (c->n == 0) return INNR_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  return maxsim_common(c, ctx, dev_q_tokens, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
+}
+
+}  // extern "C"

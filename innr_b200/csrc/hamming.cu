@@ -1,0 +1,243 @@
+// hamming.cu -- HBM-bound popcount scan over packed binary codes with fused top-k.
+//
+// Replaces (reference, innr 0.6.3):
+//   binary_hamming            src/binary.rs:154-165   (sum of (a ^ b).count_ones() over u64 words)
+//   PackedBinary::new masking src/binary.rs:59-66
+//   encode_binary             src/binary.rs:133-141   (bit = v > threshold, LSB-first)
+//   caller's top-k            examples/binary_demo.rs:174-180 (all distances, stable sort_by_key, take k)
+//
+// Device layout ("PDX for codes"): 128-bit chunks, chunk-major: codes[c * ld + i] holds words 2c, 2c+1 of
+// code i. One thread owns one code; consecutive threads read consecutive 16-byte chunks, so every warp load is
+// 512 contiguous bytes and no cross-lane reduction is needed. Integer arithmetic: results are exact.
+// Key = (distance << 32) | global index: ascending distance, ties -> lower index == stable sort_by_key.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace innr {
+
+namespace {
+
+constexpr int HAM_THREADS = 256;
+
+__device__ __forceinline__ unsigned popc_u4(uint4 a, uint4 b) {
+  return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+}
+
+// CHUNKS_CT > 0: compile-time chunk count (fully unrolled, all loads in flight); 0: runtime loop
+template <int CHUNKS_CT>
+__device__ __forceinline__ unsigned code_distance(const uint4* __restrict__ p, size_t ld, unsigned chunks,
+                                                  const uint4* __restrict__ sq) {
+  unsigned dist = 0;
+  if (CHUNKS_CT > 0) {
+    uint4 v[CHUNKS_CT > 0 ? CHUNKS_CT : 1];
+#pragma unroll
+    for (int c = 0; c < CHUNKS_CT; ++c) v[c] = ldg_stream_u4(p + (size_t)c * ld);
+#pragma unroll
+    for (int c = 0; c < CHUNKS_CT; ++c) dist += popc_u4(v[c], sq[c]);
+  } else {
+    unsigned c = 0;
+    for (; c + 4 <= chunks; c += 4) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg_stream_u4(p + (size_t)(c + u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dist += popc_u4(v[u], sq[c + u]);
+    }
+    for (; c < chunks; ++c) dist += popc_u4(ldg_stream_u4(p + (size_t)c * ld), sq[c]);
+  }
+  return dist;
+}
+
+struct HamArgs {
+  const uint4* data;
+  unsigned long long ld;
+  unsigned n, chunks, n_tiles, index_base;
+  const uint64_t* query_words;  // device: 2*chunks words (zero padded)
+  int k;
+  uint64_t* partials;
+  uint64_t* out_keys;
+  unsigned* ticket;
+  uint32_t* dist_out;
+};
+
+template <int CHUNKS_CT, int R, bool TOPK>
+__global__ void __launch_bounds__(HAM_THREADS) hamming_kernel(const HamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sq = reinterpret_cast<uint4*>(smem_raw);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(sq + a.chunks);
+  const int lane = threadIdx.x & 31;
+  for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
+    uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
+    sq[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+  }
+  __syncthreads();
+
+  WarpList<R> lists[1];
+  uint64_t thrs[1];
+  lists[0].init();
+  thrs[0] = KEY_SENTINEL;
+
+  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const unsigned i = tile * HAM_THREADS + threadIdx.x;
+    const bool valid = i < a.n;
+    unsigned dist = 0;
+    if (valid) dist = code_distance<CHUNKS_CT>(a.data + i, a.ld, a.chunks, sq);
+    if (TOPK) lists[0].offer(make_key_u32(dist, a.index_base + i), valid, thrs[0], a.k, lane);
+    else if (valid) a.dist_out[i] = dist;
+  }
+  if (TOPK) block_finish<R, 1>(lists, thrs, 1, a.k, smem_keys, a.partials, a.out_keys, a.ticket);
+}
+
+// row-major words [n][words] -> chunk-major uint4, masking padding bits (PackedBinary::new)
+__global__ void binary_pack_kernel(const uint64_t* __restrict__ words_rm, unsigned n, unsigned words,
+                                   unsigned dim_bits, uint4* __restrict__ codes, size_t ld, unsigned chunks) {
+  const size_t total = (size_t)chunks * ld;
+  const unsigned rem = dim_bits % 64;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const unsigned c = (unsigned)(t / ld);
+    const size_t i = t % ld;
+    uint64_t w[2] = {0, 0};
+    if (i < n) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned wi = 2 * c + h;
+        if (wi < words) {
+          uint64_t x = words_rm[i * words + wi];
+          if (wi == words - 1 && rem != 0) x &= (1ull << rem) - 1;
+          w[h] = x;
+        }
+      }
+    }
+    codes[t] = make_uint4((unsigned)w[0], (unsigned)(w[0] >> 32), (unsigned)w[1], (unsigned)(w[1] >> 32));
+  }
+}
+
+__global__ void generate_binary_kernel(uint64_t salt, uint64_t first_row, unsigned n, unsigned words,
+                                       unsigned dim_bits, uint4* __restrict__ codes, size_t ld, unsigned chunks) {
+  const size_t total = (size_t)chunks * ld;
+  const unsigned rem = dim_bits % 64;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const unsigned c = (unsigned)(t / ld);
+    const size_t i = t % ld;
+    uint64_t w[2] = {0, 0};
+    if (i < n) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        unsigned wi = 2 * c + h;
+        if (wi < words) {
+          uint64_t x = splitmix64(salt + (first_row + i) * words + wi);
+          if (wi == words - 1 && rem != 0) x &= (1ull << rem) - 1;
+          w[h] = x;
+        }
+      }
+    }
+    codes[t] = make_uint4((unsigned)w[0], (unsigned)(w[0] >> 32), (unsigned)w[1], (unsigned)(w[1] >> 32));
+  }
+}
+
+// encode_binary: one warp per output u64 word (two ballots)
+__global__ void encode_binary_kernel(const float* __restrict__ values, size_t n, float threshold,
+                                     uint64_t* __restrict__ words, size_t n_words) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t w = warp; w < n_words; w += n_warps) {
+    size_t i0 = w * 64 + lane, i1 = i0 + 32;
+    unsigned lo = __ballot_sync(FULL_MASK, i0 < n && values[i0] > threshold);
+    unsigned hi = __ballot_sync(FULL_MASK, i1 < n && values[i1] > threshold);
+    if (lane == 0) words[w] = ((uint64_t)hi << 32) | lo;
+  }
+}
+
+template <int CHUNKS_CT, int R, bool TOPK>
+cudaError_t launch_ham(const HamArgs& a, size_t smem, int num_sms, cudaStream_t s) {
+  auto kern = hamming_kernel<CHUNKS_CT, R, TOPK>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HAM_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  unsigned grid = TOPK ? (unsigned)occ * (unsigned)num_sms : a.n_tiles;
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid == 0) grid = 1;
+  kern<<<grid, HAM_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_binary_pack(const uint64_t* dev_words_rowmajor, size_t n, size_t words, size_t dim_bits,
+                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+  if (n == 0 || words == 0) return cudaSuccess;
+  unsigned chunks = (unsigned)((words + 1) / 2);
+  binary_pack_kernel<<<148 * 8, 256, 0, s>>>(dev_words_rowmajor, (unsigned)n, (unsigned)words, (unsigned)dim_bits,
+                                             dev_codes, ld, chunks);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t words, size_t dim_bits,
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+  if (n == 0 || words == 0) return cudaSuccess;
+  unsigned chunks = (unsigned)((words + 1) / 2);
+  generate_binary_kernel<<<148 * 16, 256, 0, s>>>(salt, first_row, (unsigned)n, (unsigned)words, (unsigned)dim_bits,
+                                                  dev_codes, ld, chunks);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
+                                 cudaStream_t s, uint64_t* launches) {
+  size_t n_words = (n + 63) / 64;
+  if (n_words == 0) return cudaSuccess;
+  unsigned grid = (unsigned)((n_words * 32 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  encode_binary_kernel<<<grid, 256, 0, s>>>(dev_values, n, threshold, dev_words, n_words);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+static HamArgs make_args(const BinView& v, const uint64_t* q) {
+  HamArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.n = (unsigned)v.n;
+  a.chunks = (unsigned)v.chunks;
+  a.n_tiles = (unsigned)((v.n + HAM_THREADS - 1) / HAM_THREADS);
+  a.index_base = v.index_base;
+  a.query_words = q;
+  return a;
+}
+
+cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
+                               cudaStream_t s, uint64_t* launches) {
+  if (v.n == 0) return cudaSuccess;
+  HamArgs a = make_args(v, dev_query_words);
+  a.dist_out = dev_out;
+  size_t smem = v.chunks * sizeof(uint4);
+  cudaError_t e = (v.chunks == 8) ? launch_ham<8, 1, false>(a, smem, 148, s) : launch_ham<0, 1, false>(a, smem, 148, s);
+  if (e == cudaSuccess) ++*launches;
+  return e;
+}
+
+cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  if (k > 128) return cudaErrorInvalidValue;
+  for (size_t q = 0; q < nq; ++q) {
+    HamArgs a = make_args(v, dev_query_words + q * 2 * v.chunks);
+    a.k = (int)k;
+    a.partials = ws.partials;
+    a.ticket = ws.ticket;
+    a.out_keys = dev_keys + q * k;
+    size_t smem = v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
+    cudaError_t e;
+    if (v.chunks == 8)
+      e = (k <= 32) ? launch_ham<8, 1, true>(a, smem, ws.num_sms, s) : launch_ham<8, 4, true>(a, smem, ws.num_sms, s);
+    else
+      e = (k <= 32) ? launch_ham<0, 1, true>(a, smem, ws.num_sms, s) : launch_ham<0, 4, true>(a, smem, ws.num_sms, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace innr

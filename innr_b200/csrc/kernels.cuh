@@ -1,0 +1,100 @@
+// kernels.cuh -- launcher prototypes shared between the kernel translation units and the C-ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace innr {
+
+// modes of the f32 PDX scan (scan_f32.cu)
+enum PdxMode : int {
+  PDX_DOT = 0,          // batch_dot_into            src/batch.rs:284-297
+  PDX_COSINE_FUSED = 1, // batch_norms + batch_cosine in ONE pass (knn)  src/batch.rs:672-686, 705-728
+  PDX_L2 = 2,           // batch_l2_squared_into     src/batch.rs:250-266
+  PDX_NORMS = 3,        // batch_norms_into          src/batch.rs:672-686
+  PDX_COSINE_NORMS = 4, // batch_cosine_into with caller-supplied norms  src/batch.rs:705-728
+};
+
+struct Workspace {
+  uint64_t* partials = nullptr;  // per-CTA top-k lists
+  size_t partials_cap = 0;       // in u64
+  unsigned* ticket = nullptr;    // last-CTA-done counter (self-resetting)
+  int num_sms = 0;
+};
+
+struct PdxView {
+  const float* data;  // data[dd * ld + i]
+  size_t n, d, ld;
+  uint32_t index_base;
+};
+
+// kNN: queries on device (nq x d row-major); writes nq x k sorted keys (sentinel padded) into dev_keys.
+// Returns cudaSuccess or the launch error; `launches` is incremented per kernel launched.
+cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
+                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+// full score vectors: out[q * ld + i] (device). dev_norms only for PDX_COSINE_NORMS.
+cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
+                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches);
+// merge n_lists x nq x k sorted key lists -> nq x k; optional decode (idx u64, f32 score bits by `descending`)
+cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
+                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
+                              uint64_t* launches);
+// keys from a plain f32 array (TopK analogue): ascending, id = i
+cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
+                                       Workspace& ws, cudaStream_t s, uint64_t* launches);
+
+// layout / generator kernels (layout.cu)
+cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,
+                                         cudaStream_t s, uint64_t* launches);
+cudaError_t launch_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
+                                    float* dev_pdx, size_t ld, cudaStream_t s, uint64_t* launches);
+
+// binary codes (hamming.cu): chunk-major layout codes[c * ld + i] (uint4 = 128 bits), chunks = ceil(words/2)
+struct BinView {
+  const uint4* data;
+  size_t n, ld, words, chunks, dim_bits;
+  uint32_t index_base;
+};
+cudaError_t launch_binary_pack(const uint64_t* dev_words_rowmajor, size_t n, size_t words, size_t dim_bits,
+                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t words, size_t dim_bits,
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
+                               cudaStream_t s, uint64_t* launches);
+cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
+                                 cudaStream_t s, uint64_t* launches);
+
+// u8 codes (u8.cu): chunk-major layout codes[c * ld + i] (uint4 = 16 dims), chunks = ceil(d/16)
+struct U8View {
+  const uint4* data;
+  size_t n, d, ld, chunks;
+  float alpha, offset;
+  uint32_t index_base;
+};
+cudaError_t launch_u8_pack(const uint8_t* dev_rows, size_t n, size_t d, uint4* dev_codes, size_t ld,
+                           cudaStream_t s, uint64_t* launches);
+cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
+                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, float offset, uint8_t* dev_out,
+                               cudaStream_t s, uint64_t* launches);
+// mode 0: raw mixed dot, 1: asymmetric score
+cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
+                             cudaStream_t s, uint64_t* launches);
+cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
+                          Workspace& ws, cudaStream_t s, uint64_t* launches);
+
+// MaxSim (maxsim.cu)
+struct TokView {
+  const float* tokens;          // total_tokens x dim row-major
+  const uint64_t* doc_offsets;  // n_docs + 1 (device)
+  size_t n_docs, dim, total_tokens;
+  size_t uniform_tokens;        // > 0 when every doc has exactly this many tokens
+};
+cudaError_t launch_generate_tokens(uint64_t salt, uint64_t first_row, size_t n_rows, size_t dim, float* dev_tokens,
+                                   cudaStream_t s, uint64_t* launches);
+cudaError_t launch_maxsim(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
+                          cudaStream_t s, uint64_t* launches);
+
+}  // namespace innr

@@ -1,0 +1,402 @@
+// scan_f32.cu -- HBM-bound scan of a device-resident VerticalBatch (PDX layout) with fused exact top-k.
+//
+// Replaces (reference, innr 0.6.3):
+//   batch_dot_into          src/batch.rs:284-297      batch_l2_squared_into  src/batch.rs:250-266
+//   batch_norms_into        src/batch.rs:672-686      batch_cosine_into      src/batch.rs:705-728
+//   batch_knn (L2 + TopK)   src/batch.rs:385-411      batch_knn_dot          src/batch.rs:742-764
+//   batch_knn_cosine        src/batch.rs:777-800      TopK::insert           src/topk.rs:96-121
+//
+// Bit-exactness: the reference's batch loops are `acc[i] += q[d] * v[d][i]` with d
+// ascending and NO fused multiply-add, so one thread owning vector i and computing
+// __fadd_rn(acc, __fmul_rn(q, v)) for d = 0..D-1 reproduces every score bit for bit. The PDX layout makes that
+// mapping perfectly coalesced: a thread owns 4 consecutive vectors (one 128-bit load per dimension row), a warp
+// reads 512 contiguous bytes per row, a CTA tile covers TILE = 4 * blockDim vectors.
+//
+// batch_knn_cosine recomputes all corpus norms on every call (src/batch.rs:788); here sum(v*v) is accumulated
+// in the same pass over the same registers (same sequential order => same bits) at zero extra HBM bytes.
+//
+// Selection never materialises N scores: scores become 64-bit composite keys (common.cuh) and flow into a
+// per-warp register list, a CTA merge and a last-CTA merge -- one launch per query group.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace innr {
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int VPT = 4;                        // vectors per thread (one float4)
+constexpr int TILE = SCAN_THREADS * VPT;      // vectors per CTA tile
+constexpr float NORM_EPS = 1e-9f;             // crate::NORM_EPSILON, src/lib.rs:178
+
+struct PdxArgs {
+  const float* data;
+  unsigned long long ld;
+  unsigned n, d, ld4;     // ld4 = ld (u32 copy for bounds checks; ld < 2^32)
+  unsigned n_tiles;
+  unsigned index_base;
+  const float* queries;   // nq_valid x d (device)
+  int nq_valid;
+  int k;
+  uint64_t* partials;
+  uint64_t* out_keys;
+  unsigned* ticket;
+  float* scores_out;      // scores mode: out[q * ld + i]
+  const float* norms_in;  // PDX_COSINE_NORMS
+};
+
+template <int MODE>
+__device__ __forceinline__ void accumulate(float q, float v, float& acc) {
+  if (MODE == PDX_L2) {
+    float diff = __fsub_rn(q, v);                 // let diff = q_d - v_d;
+    acc = __fadd_rn(acc, __fmul_rn(diff, diff));  // *dist += diff * diff;
+  } else {
+    acc = __fadd_rn(acc, __fmul_rn(q, v));        // *prod += q_d * v_d;
+  }
+}
+
+template <int MODE, int QB, int R, bool KNN>
+__global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a) {
+  constexpr bool NEED_SS = (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS);
+  constexpr bool NEED_DOT = (MODE != PDX_NORMS);
+  constexpr int U = (QB == 1) ? 8 : 4;  // dimension rows in flight per thread
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // [d][QB] interleaved queries (padded so the d-loop can read whole float4 groups), then qnorm[QB], then keys
+  const unsigned d_pad = (a.d + U - 1) / U * U;
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  float* s_qn = sq + (size_t)d_pad * QB;
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(s_qn + ((QB + 3) & ~3));
+
+  const int lane = threadIdx.x & 31;
+
+  if (NEED_DOT) {
+    for (unsigned idx = threadIdx.x; idx < d_pad * QB; idx += blockDim.x) {
+      unsigned dd = idx / QB, q = idx % QB;
+      sq[idx] = (dd < a.d && (int)q < a.nq_valid) ? a.queries[(size_t)q * a.d + dd] : 0.0f;
+    }
+    if ((MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS) && threadIdx.x < QB) {
+      // query_norm = query.iter().map(|x| x * x).sum::<f32>().sqrt()   (src/batch.rs:714) -- sequential
+      float ss = 0.0f;
+      if ((int)threadIdx.x < a.nq_valid) {
+        const float* qp = a.queries + (size_t)threadIdx.x * a.d;
+        for (unsigned dd = 0; dd < a.d; ++dd) {
+          float x = qp[dd];
+          ss = __fadd_rn(ss, __fmul_rn(x, x));
+        }
+      }
+      s_qn[threadIdx.x] = __fsqrt_rn(ss);
+    }
+  }
+  __syncthreads();
+
+  WarpList<R> lists[QB];
+  uint64_t thrs[QB];
+  if (KNN) {
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      lists[q].init();
+      thrs[q] = KEY_SENTINEL;
+    }
+  }
+
+  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const unsigned i0 = tile * TILE + threadIdx.x * VPT;
+    const bool active = i0 < a.ld4;  // ld is a multiple of 4: the whole float4 is in bounds
+    float acc[QB][VPT];
+    float ss[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      ss[j] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < QB; ++q) acc[q][j] = 0.0f;
+    }
+    if (active) {
+      const float* p = a.data + i0;
+      unsigned dd = 0;
+      for (; dd + U <= a.d; dd += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(p + (size_t)u * a.ld);
+        p += (size_t)U * a.ld;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float vv[VPT] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          if (NEED_SS) {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) ss[j] = __fadd_rn(ss[j], __fmul_rn(vv[j], vv[j]));
+          }
+          if (NEED_DOT) {
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+              const float qv = sq[(size_t)(dd + u) * QB + q];
+#pragma unroll
+              for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
+            }
+          }
+        }
+      }
+      for (; dd < a.d; ++dd) {  // D % U tail
+        float4 v = ldg_stream_f4(p);
+        p += a.ld;
+        const float vv[VPT] = {v.x, v.y, v.z, v.w};
+        if (NEED_SS) {
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) ss[j] = __fadd_rn(ss[j], __fmul_rn(vv[j], vv[j]));
+        }
+        if (NEED_DOT) {
+#pragma unroll
+          for (int q = 0; q < QB; ++q) {
+            const float qv = sq[(size_t)dd * QB + q];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
+          }
+        }
+      }
+    }
+
+    // epilogue: scores (and keys)
+    float nrm[VPT];
+    if (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) nrm[j] = __fsqrt_rn(ss[j]);  // *norm = norm.sqrt()  (src/batch.rs:683-685)
+    }
+    if (MODE == PDX_COSINE_NORMS) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) nrm[j] = (active && i0 + j < a.n) ? a.norms_in[i0 + j] : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      float s[VPT];
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        if (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS) {
+          const float qn = s_qn[q];
+          // src/batch.rs:716-727: qn < eps -> 0 for all; norm > eps ? dot / (qn * norm) : 0
+          float c = 0.0f;
+          if (!(qn < NORM_EPS) && nrm[j] > NORM_EPS) c = __fdiv_rn(acc[q][j], __fmul_rn(qn, nrm[j]));
+          s[j] = c;
+        } else if (MODE == PDX_NORMS) {
+          s[j] = nrm[j];
+        } else {
+          s[j] = acc[q][j];
+        }
+      }
+      if (KNN) {
+        if (q < a.nq_valid) {
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            const unsigned i = i0 + j;
+            const uint64_t key = (MODE == PDX_L2) ? make_key_asc(s[j], a.index_base + i)
+                                                  : make_key_desc(s[j], a.index_base + i);
+            lists[q].offer(key, active && i < a.n, thrs[q], a.k, lane);
+          }
+        }
+      } else if (active && q < a.nq_valid) {
+        *reinterpret_cast<float4*>(a.scores_out + (size_t)q * a.ld + i0) = make_float4(s[0], s[1], s[2], s[3]);
+      }
+    }
+  }
+
+  if (KNN) block_finish<R, QB>(lists, thrs, a.nq_valid, a.k, smem_keys, a.partials, a.out_keys, a.ticket);
+}
+
+template <int MODE, int QB, int R, bool KNN>
+cudaError_t launch_one(const PdxArgs& a, size_t smem, int max_ctas_per_sm_hint, int num_sms, cudaStream_t s) {
+  auto kern = pdx_scan_kernel<MODE, QB, R, KNN>;
+  static int occ = 0;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  if (occ == 0 || smem > 16 * 1024) {
+    int o = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, SCAN_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (o < 1) return cudaErrorInvalidConfiguration;
+    occ = o;
+  }
+  (void)max_ctas_per_sm_hint;
+  unsigned grid = (unsigned)occ * (unsigned)num_sms;
+  if (!KNN) grid = a.n_tiles;  // no cross-tile state: one CTA per tile, hardware scheduler balances
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  if (grid == 0) grid = 1;
+  kern<<<grid, SCAN_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+size_t scan_smem_bytes(size_t d, int qb, int k, bool knn) {
+  const int U = (qb == 1) ? 8 : 4;
+  size_t d_pad = (d + U - 1) / U * U;
+  size_t b = d_pad * qb * sizeof(float) + ((qb + 3) & ~3) * sizeof(float);
+  if (knn) b += (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t);
+  return b;
+}
+
+}  // namespace
+
+unsigned pdx_max_grid(int num_sms) { return (unsigned)num_sms * 8u; }
+
+cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
+                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  PdxArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.ld4 = (unsigned)v.ld;
+  a.n = (unsigned)v.n;
+  a.d = (unsigned)v.d;
+  a.n_tiles = (unsigned)((v.ld + TILE - 1) / TILE);
+  a.index_base = v.index_base;
+  a.k = (int)k;
+  a.partials = ws.partials;
+  a.ticket = ws.ticket;
+  const bool big_k = k > 32;
+  // query blocking: 8 queries share one pass over the corpus when their lists fit in registers
+  const int QBMAX = big_k ? 1 : 8;
+  size_t done = 0;
+  while (done < nq) {
+    int qb = (nq - done >= 2 && QBMAX == 8) ? 8 : 1;
+    size_t smem = scan_smem_bytes(v.d, qb, (int)k, true);
+    if (smem > 200 * 1024 && qb == 8) {
+      qb = 1;
+      smem = scan_smem_bytes(v.d, 1, (int)k, true);
+    }
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    int nqv = (int)((nq - done) < (size_t)qb ? (nq - done) : (size_t)qb);
+    a.queries = dev_queries + done * v.d;
+    a.nq_valid = nqv;
+    a.out_keys = dev_keys + done * k;
+    cudaError_t e;
+#define INNR_DISPATCH(MODE)                                                                          \
+  if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, 0, ws.num_sms, s);                          \
+  else if (!big_k) e = launch_one<MODE, 1, 1, true>(a, smem, 0, ws.num_sms, s);                      \
+  else e = launch_one<MODE, 1, 4, true>(a, smem, 0, ws.num_sms, s);
+    if (mode == PDX_DOT) { INNR_DISPATCH(PDX_DOT) }
+    else if (mode == PDX_L2) { INNR_DISPATCH(PDX_L2) }
+    else if (mode == PDX_COSINE_FUSED) { INNR_DISPATCH(PDX_COSINE_FUSED) }
+    else return cudaErrorInvalidValue;
+#undef INNR_DISPATCH
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    done += nqv;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
+                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  PdxArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.ld4 = (unsigned)v.ld;
+  a.n = (unsigned)v.n;
+  a.d = (unsigned)v.d;
+  a.n_tiles = (unsigned)((v.ld + TILE - 1) / TILE);
+  a.index_base = v.index_base;
+  a.queries = dev_query;
+  a.nq_valid = 1;
+  a.scores_out = dev_out;
+  a.norms_in = dev_norms;
+  size_t smem = scan_smem_bytes(v.d, 1, 0, false);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  switch (mode) {
+    case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
+    case PDX_L2: e = launch_one<PDX_L2, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
+    case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
+    case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e == cudaSuccess) ++*launches;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// merge of key lists (K10: after the allgather of per-shard top-k) and the TopK analogue
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int R>
+__global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int n_lists, int nq, int k,
+                                                        int descending, uint64_t* keys_out, uint64_t* idx_out,
+                                                        float* score_out) {
+  const int q = blockIdx.x, lane = threadIdx.x;
+  WarpList<R> list;
+  list.init();
+  uint64_t thr = KEY_SENTINEL;
+  warp_merge_lists<R, true>(list, thr, in + (size_t)q * k, 0, 1, n_lists, (size_t)nq * k, k, lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int p = r * 32 + lane;
+    if (p < k) {
+      uint64_t key = list.v[r];
+      if (keys_out) keys_out[(size_t)q * k + p] = key;
+      if (idx_out) idx_out[(size_t)q * k + p] = key & 0xFFFFFFFFull;
+      if (score_out) {
+        uint32_t hi = (uint32_t)(key >> 32);
+        if (descending) hi = ~hi;
+        score_out[(size_t)q * k + p] = __uint_as_float(order_bits_to_f32_bits(hi));
+      }
+    }
+  }
+}
+
+template <int R>
+__global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const float* dist, unsigned n, int k,
+                                                                     uint64_t* partials, uint64_t* out_keys,
+                                                                     unsigned* ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  WarpList<R> lists[1];
+  uint64_t thrs[1];
+  lists[0].init();
+  thrs[0] = KEY_SENTINEL;
+  // grid-stride over whole warps so every lane reaches the ballots together
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned n_round = (n + 31u) / 32u * 32u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool valid = i < n;
+    const float dv = valid ? dist[i] : 0.0f;
+    lists[0].offer(make_key_asc(dv, i), valid, thrs[0], k, lane);
+  }
+  block_finish<R, 1>(lists, thrs, 1, k, smem_keys, partials, out_keys, ticket);
+}
+
+}  // namespace
+
+cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
+                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
+                              uint64_t* launches) {
+  if (k > 128) return cudaErrorInvalidValue;
+  if (k <= 32)
+    merge_keys_kernel<1><<<(unsigned)nq, 32, 0, s>>>(dev_in, (int)n_lists, (int)nq, (int)k, descending,
+                                                      dev_keys_out, dev_idx, dev_score);
+  else
+    merge_keys_kernel<4><<<(unsigned)nq, 32, 0, s>>>(dev_in, (int)n_lists, (int)nq, (int)k, descending,
+                                                      dev_keys_out, dev_idx, dev_score);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
+                                       Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  if (k > 128) return cudaErrorInvalidValue;
+  unsigned grid = (unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS);
+  unsigned cap = (unsigned)ws.num_sms * 4u;
+  if (grid > cap) grid = cap;
+  if (grid == 0) grid = 1;
+  size_t smem = (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t);
+  if (k <= 32)
+    topk_distances_kernel<1><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
+                                                              dev_keys, ws.ticket);
+  else
+    topk_distances_kernel<4><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
+                                                              dev_keys, ws.ticket);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace innr

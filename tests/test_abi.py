@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: libinnr_cuda.so loads, exports every symbol include/innr_cuda.h
+declares (and nothing is bound that the header lacks), and the product fails loudly without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import innr_b200
+from innr_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "innr_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(innr_cuda_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    if not os.path.exists(L.SO_PATH):
+        innr_b200.build()
+    lib = ctypes.CDLL(L.SO_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/innr_cuda.h but not exported"
+
+
+def test_python_binding_covers_the_header():
+    declared = set(_header_symbols())
+    bound = set(L.SIGNATURES) | set(L.STRING_GETTERS)
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    L.lib()  # binds argtypes for every symbol
+
+
+def test_backend_string_and_enum():
+    assert innr_b200.backend_name() == "cuda"                       # new Backend::Cuda Display string
+    assert str(innr_b200.Backend.Avx512) == "avx512" and str(innr_b200.Backend.Portable) == "portable"  # src/backend.rs:114-120
+    assert str(innr_b200.Backend.Cuda) == "cuda"
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    b = innr_b200.VerticalBatch.from_rows([[1.0, 2.0], [3.0, 4.0]])   # host-side layout only
+    assert b.get(1, 0) == 2.0
+    with pytest.raises(innr_b200.InnrCudaError, match="no CPU fallback"):
+        innr_b200.batch_dot([1.0, 1.0], b)
+    with pytest.raises(innr_b200.InnrCudaError):
+        innr_b200.encode_binary([1.0, -1.0], 0.0)
+    with pytest.raises(innr_b200.InnrCudaError):
+        innr_b200.quantize_u8([0.5], innr_b200.QuantizationParams.from_range(0.0, 1.0))
+
+
+def test_host_side_types_match_reference_contracts():
+    pb = innr_b200.PackedBinary([0xFFFFFFFFFFFFFFFF], 8)              # src/binary.rs:59-66 padding mask
+    assert int(pb.data[0]) == 0xFF
+    with pytest.raises(AssertionError):
+        innr_b200.PackedBinary([0, 0], 8)
+    p = innr_b200.QuantizationParams.from_range(1.0, 1.0)             # alpha <= 0 -> 1.0 (src/scalar.rs:54-60)
+    assert p.alpha == 1.0 and p.offset == 1.0
+    with pytest.raises(AssertionError):
+        innr_b200.QuantizedU8([1, 2, 3], 2)
+    vb = innr_b200.VerticalBatch.from_rows([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])
+    assert list(vb.dimension_slice(1)) == [2.0, 5.0] and list(vb.data) == [1.0, 4.0, 2.0, 5.0, 3.0, 6.0]
+    with pytest.raises(AssertionError):
+        innr_b200.VerticalBatch.from_rows([[1.0], [1.0, 2.0]])

@@ -1,0 +1,284 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north_star): integer / byte / index work bit-exact; f32 scan scores bit-exact (sequential unfused sums are
+reproduced on the device); MaxSim within 1e-5 relative, condition-aware (|got - ref| <= 1e-5 * sum_i max_j sum_k
+|q_ik d_jk| -- the bound the reference's own property tests use, tests/property_tests.rs:56-64).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import innr_b200
+    innr_b200.init(0)
+    return innr_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def rand_rows(n, d, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((n, d)) * scale).astype(np.float32)
+
+
+def assert_knn_equal(got, want, ties_as_sets=False):
+    assert np.array_equal(bits(got.scores), bits(want.scores)), (got.scores, want.scores)
+    if not ties_as_sets:
+        assert got.indices == want.indices
+        return
+    # SURVEY.md 8a row T (L2/TopK path): exact-tie groups compare as sets
+    s = np.asarray(want.scores)
+    for v in np.unique(bits(s)):
+        sel = bits(s) == v
+        g = sorted(np.asarray(got.indices)[sel].tolist())
+        w = sorted(np.asarray(want.indices)[sel].tolist())
+        if sel.sum() == 1 or g == w:
+            assert g == w
+    assert len(set(got.indices)) == len(got.indices)
+
+
+SHAPES = [(1, 1), (5, 3), (63, 7), (1000, 128), (4097, 100), (1024, 8), (20000, 768), (3000, 1)]
+
+
+@pytest.mark.parametrize("n,d", SHAPES)
+def test_scores_bit_exact(ib, oracle, n, d):
+    rows = rand_rows(n, d, n * 31 + d)
+    q = rand_rows(1, d, 7)[0]
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    assert np.array_equal(gb.data, ob.data)
+    for fn in ("batch_dot", "batch_l2_squared"):
+        assert np.array_equal(bits(getattr(ib, fn)(q, gb)), bits(getattr(oracle, fn)(q, ob))), fn
+    gn, on = ib.batch_norms(gb), oracle.batch_norms(ob)
+    assert np.array_equal(bits(gn), bits(on))
+    assert np.array_equal(bits(ib.batch_cosine(q, gb, gn)), bits(oracle.batch_cosine(q, ob, on)))
+    # caller-supplied (arbitrary) norms, incl. zero / tiny / negative entries
+    weird = on.copy()
+    weird[:: max(1, n // 7)] = 0.0
+    weird[1:: max(2, n // 5)] = 1e-10
+    assert np.array_equal(bits(ib.batch_cosine(q, gb, weird)), bits(oracle.batch_cosine(q, ob, weird)))
+
+
+@pytest.mark.parametrize("n,d", SHAPES)
+@pytest.mark.parametrize("k", [1, 10, 33, 128])
+def test_knn_bit_exact(ib, oracle, n, d, k):
+    rows = rand_rows(n, d, n * 17 + d + k)
+    q = rand_rows(1, d, 11)[0]
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    assert_knn_equal(ib.batch_knn_dot(q, gb, k), oracle.batch_knn_dot(q, ob, k))
+    assert_knn_equal(ib.batch_knn_cosine(q, gb, k), oracle.batch_knn_cosine(q, ob, k))
+    assert_knn_equal(ib.batch_knn(q, gb, k), oracle.batch_knn(q, ob, k), ties_as_sets=True)
+
+
+def test_knn_ties_lower_index_first(ib, oracle):
+    # heavy exact ties: integer-valued rows, many duplicates
+    rng = np.random.default_rng(5)
+    rows = rng.integers(-2, 3, size=(5000, 16)).astype(np.float32)
+    q = rng.integers(-2, 3, size=16).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), 5000, 16), oracle.VerticalBatch.from_flat(rows.reshape(-1), 5000, 16)
+    for k in (1, 10, 100):
+        assert_knn_equal(ib.batch_knn_dot(q, gb, k), oracle.batch_knn_dot(q, ob, k))
+        assert_knn_equal(ib.batch_knn_cosine(q, gb, k), oracle.batch_knn_cosine(q, ob, k))
+        assert_knn_equal(ib.batch_knn(q, gb, k), oracle.batch_knn(q, ob, k), ties_as_sets=True)
+
+
+def test_knn_special_values(ib, oracle):
+    # NaN / inf / -0.0 ordering follows f32::total_cmp (SURVEY.md 8b edge contracts)
+    rows = rand_rows(300, 4, 3)
+    rows[5, 0] = np.nan
+    rows[9, 1] = np.inf
+    rows[17, 2] = -np.inf
+    rows[30] = 0.0
+    rows[31] = -0.0
+    q = np.array([1.0, -2.0, 0.5, 0.0], np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), 300, 4), oracle.VerticalBatch.from_flat(rows.reshape(-1), 300, 4)
+    for k in (3, 300):
+        if k > 128:
+            continue
+        g, w = ib.batch_knn_dot(q, gb, k), oracle.batch_knn_dot(q, ob, k)
+        assert g.indices == w.indices and np.array_equal(bits(g.scores), bits(w.scores))
+        g, w = ib.batch_knn_cosine(q, gb, k), oracle.batch_knn_cosine(q, ob, k)
+        assert g.indices == w.indices and np.array_equal(bits(g.scores), bits(w.scores))
+    zq = np.zeros(4, np.float32)  # zero query: all cosines 0.0 -> first k indices
+    g, w = ib.batch_knn_cosine(zq, gb, 10), oracle.batch_knn_cosine(zq, ob, 10)
+    assert g.indices == w.indices == list(range(10))
+
+
+def test_multi_query_equals_single(ib, oracle):
+    n, d, nq, k = 6000, 64, 19, 10
+    rows = rand_rows(n, d, 1)
+    qs = rand_rows(nq, d, 2)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for metric, single in (("dot", "batch_knn_dot"), ("cosine", "batch_knn_cosine"), ("l2", "batch_knn")):
+        idx, sc = ib.batch_knn_many(metric, qs, gb, k)
+        for j in range(nq):
+            w = getattr(oracle, single)(qs[j], ob, k)
+            assert idx[j].tolist() == w.indices, (metric, j)
+            assert np.array_equal(bits(sc[j]), bits(w.scores))
+
+
+def test_config1_batch_demo_gref(ib, oracle):
+    """BASELINE config 1: 10K x 128 G-ref lattice (examples/batch_demo.rs:159-170), 100 queries, batch_knn_dot k=10.
+    The lattice is an adversarial near-tie fixture; corpus generated on the device."""
+    n, d, nq, k = 10_000, 128, 100, 10
+    dev = ib.DeviceBatch.generate("gref", 0, 0, n, d)
+    rows = np.stack([oracle.generate_embedding(d, i) for i in range(n)])
+    for i in (0, 1, 4097, n - 1):
+        assert np.array_equal(bits(dev.extract_vector(i)), bits(rows[i]))
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    qs = np.stack([oracle.generate_embedding(d, 50_000 + j) for j in range(nq)])
+    idx, sc = ib.batch_knn_many("dot", qs, dev, k)
+    widx, wsc = oracle.batch_knn_many("dot", qs, ob, k, n_threads=8)
+    assert np.array_equal(idx, widx) and np.array_equal(bits(sc), bits(wsc))
+    assert np.array_equal(bits(ib.batch_l2_squared(qs[0], dev)), bits(oracle.batch_l2_squared(qs[0], ob)))
+
+
+def test_device_generators_match_oracle(ib, oracle):
+    n, d = 777, 48
+    dev = ib.DeviceBatch.generate("ghash", 0x5EED0000, 1000, n, d, index_base=1000)
+    want = oracle.ghash_f32(0x5EED0000, 1000 * d, n * d).reshape(n, d)
+    for i in (0, 1, 500, n - 1):
+        assert np.array_equal(bits(dev.extract_vector(i)), bits(want[i]))
+    q = oracle.ghash_f32(0x5EED0001, 0, d)
+    g = ib.batch_knn_cosine(q, dev, 10)
+    w = oracle.batch_knn_cosine(q, oracle.VerticalBatch.from_flat(want.reshape(-1), n, d), 10)
+    assert g.indices == [i + 1000 for i in w.indices]          # global indices = index_base + local
+    assert np.array_equal(bits(g.scores), bits(w.scores))
+
+
+def test_rows_upload_transposes_on_device(ib):
+    n, d = 1234, 37
+    rows = rand_rows(n, d, 9)
+    a = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    b = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d).device()
+    q = rand_rows(1, d, 10)[0]
+    assert np.array_equal(bits(ib.batch_dot(q, a)), bits(ib.batch_dot(q, b)))
+    assert np.array_equal(bits(a.extract_vector(n - 1)), bits(rows[n - 1]))
+
+
+def test_topk_from_distances_random(ib, oracle):
+    rng = np.random.default_rng(3)
+    for n, k in ((1, 1), (31, 5), (1000, 10), (100_000, 100), (5000, 128)):
+        d = rng.standard_normal(n).astype(np.float32)
+        got = ib.topk_from_distances(d, k)
+        order = np.lexsort((np.arange(n), d))[:k]
+        assert [i for i, _ in got] == order.tolist()
+        assert np.array_equal(bits([s for _, s in got]), bits(d[order]))
+
+
+# ------------------------------------------------------------------------------------------------ Hamming
+@pytest.mark.parametrize("dim", [64, 100, 128, 1000, 1024, 2048 + 17])
+def test_hamming_bit_exact(ib, oracle, dim):
+    words = (dim + 63) // 64
+    n = 5000
+    rng = np.random.default_rng(dim)
+    codes = rng.integers(0, 2**64, size=(n, words), dtype=np.uint64)
+    q = rng.integers(0, 2**64, size=words, dtype=np.uint64)
+    # dirty padding bits must be masked like PackedBinary::new does
+    corpus = ib.BinaryCorpus.from_words(codes, n, dim)
+    qpb = ib.PackedBinary(q, dim)
+    opb = [oracle.PackedBinary(c, dim) for c in codes[:50]]
+    oq = oracle.PackedBinary(q, dim)
+    allg = ib.hamming_all(qpb, corpus)
+    for i in range(50):
+        assert int(allg[i]) == oracle.binary_hamming(oq, opb[i])
+    masked = np.stack([oracle.PackedBinary(c, dim).data for c in codes])
+    for k in (1, 100, 128):
+        gi, gd = ib.hamming_topk(qpb.data, corpus, k)
+        wi, wd = oracle.hamming_topk(oq.data, masked, k)
+        assert gi.tolist() == wi.tolist() and gd.tolist() == wd.tolist()
+
+
+def test_hamming_generator_and_multi_query(ib, oracle):
+    n, dim, k = 20_000, 1024, 100
+    corpus = ib.BinaryCorpus.generate(0x5EED0002, 0, n, dim)
+    codes = oracle.ghash_u64(0x5EED0002, 0, n * 16).reshape(n, 16)
+    qs = oracle.ghash_u64(0x5EED0001, 0, 3 * 16).reshape(3, 16)
+    gi, gd = ib.hamming_topk_many(qs, corpus, k)
+    wi, wd = oracle.hamming_topk_many(qs, codes, k, n_threads=3)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+
+
+# ------------------------------------------------------------------------------------------------ u8
+@pytest.mark.parametrize("d", [1, 8, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 100, 128, 384, 777])
+def test_u8_bit_exact(ib, oracle, d):
+    n = 3000
+    rng = np.random.default_rng(d)
+    mat = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    q = (rng.standard_normal(d) * 3).astype(np.float32)
+    gp, op = ib.QuantizationParams.from_range(-1.5, 2.0), oracle.QuantizationParams.from_range(-1.5, 2.0)
+    corpus = ib.U8Corpus.from_rows(mat, gp)
+    mixed = ib.mixed_dot_u8_all(q, corpus)
+    asym = ib.asymmetric_dot_u8_all(q, corpus)
+    for i in range(0, n, 97):
+        assert np.float32(mixed[i]).tobytes() == np.float32(oracle.mixed_dot_u8_f32(q, mat[i])).tobytes(), (d, i)
+        assert np.float32(asym[i]).tobytes() == np.float32(
+            oracle.asymmetric_dot_u8(q, oracle.QuantizedU8(mat[i], d), op)).tobytes(), (d, i)
+    for k in (1, 10, 100):
+        got = ib.batch_knn_u8(q, corpus, gp, k)
+        want = oracle.batch_knn_u8(q, mat, op, k)
+        assert [i for i, _ in got] == [i for i, _ in want]
+        assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want]))
+
+
+def test_u8_generator_and_quantize(ib, oracle):
+    n, d = 4000, 384
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    vals = oracle.ghash_f32(0x5EED0000, 0, n * d)
+    assert np.array_equal(ib.quantize_u8(vals, gp).data, oracle.quantize_u8(vals, op).data)
+    corpus = ib.U8Corpus.generate(0x5EED0000, 0, n, d, gp)
+    mat = oracle.quantize_u8(vals, op).data.reshape(n, d)
+    q = oracle.ghash_f32(0x5EED0001, 0, d)
+    got = ib.batch_knn_u8(q, corpus, gp, 10)
+    want = oracle.batch_knn_u8(q, mat, op, 10)
+    assert [i for i, _ in got] == [i for i, _ in want]
+    assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want]))
+
+
+# ------------------------------------------------------------------------------------------------ MaxSim
+def _maxsim_scale(q, toks, off):
+    out = np.zeros(len(off) - 1)
+    aq = np.abs(q.astype(np.float64))
+    for j in range(len(off) - 1):
+        t = np.abs(toks[off[j]:off[j + 1]].astype(np.float64))
+        out[j] = float(np.sum(np.max(aq @ t.T, axis=1))) if t.shape[0] else 0.0
+    return out
+
+
+@pytest.mark.parametrize("nq,dim", [(1, 4), (3, 30), (32, 128), (40, 64), (32, 16), (7, 129)])
+def test_maxsim_within_tolerance(ib, oracle, nq, dim):
+    rng = np.random.default_rng(nq * 100 + dim)
+    lens = rng.integers(0, 200, size=60)
+    lens[3] = 0                                   # empty doc -> 0.0
+    lens[10] = 180
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    toks = rng.standard_normal((int(off[-1]), dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    corpus = ib.TokenCorpus.from_tokens(toks, off, dim)
+    for cos in (False, True):
+        got = ib.maxsim_corpus(q, corpus, cosine=cos)
+        want = oracle.maxsim_corpus(q, toks, off, cosine_flag=cos)
+        scale = _maxsim_scale(q, toks, off) if not cos else np.full(len(lens), float(nq))
+        assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-5 * scale + 1e-6), (
+            cos, float(np.max(np.abs(got - want))))
+        assert got[3] == 0.0
+
+
+def test_maxsim_colbert_shape_generated(ib, oracle):
+    """C3 shape at reduced doc count: 32 x 128 query tokens vs docs of 180 x 128 tokens, generated on the device."""
+    n_docs, nt, dim, nq = 500, 180, 128, 32
+    corpus = ib.TokenCorpus.generate(0x5EED0000, 0, n_docs, nt, dim)
+    toks = oracle.ghash_f32(0x5EED0000, 0, n_docs * nt * dim).reshape(n_docs * nt, dim)
+    q = oracle.ghash_f32(0x5EED0001, 0, nq * dim).reshape(nq, dim)
+    off = np.arange(0, n_docs * nt + 1, nt, dtype=np.uint64)
+    for cos in (False, True):
+        got = ib.maxsim_corpus(q, corpus, cosine=cos)
+        want = oracle.maxsim_corpus(q, toks, off, cosine_flag=cos, n_threads=8)
+        scale = _maxsim_scale(q, toks, off) if not cos else np.full(n_docs, float(nq))
+        assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-5 * scale + 1e-6)
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+        assert float(np.max(rel)) < 1e-5, float(np.max(rel))   # north_star: f32 scores within 1e-5 relative
