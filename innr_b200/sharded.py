@@ -1,0 +1,120 @@
+"""Row-sharded corpora across the GPUs of one box: one process per GPU, `torch.distributed` for the plumbing.
+
+SURVEY.md 8e: vectors are independent and top-k selection is a monoid, so each rank scans a contiguous row range
+(global index = shard base + local; contiguous ranges keep "lower global index wins" consistent across shards),
+emits its local top-k as sorted 64-bit composite keys, and ONE allgather of k keys per rank per query exchanges
+them; every rank then runs the same n_ranks*k -> k merge. No other collective is on the data path.
+
+torch is used for device buffers, streams and the allgather only; the scan and the merge are libinnr_cuda kernels
+launched on torch's current stream through the `_dev` entry points of the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous row range [lo, hi) of shard `rank` (shard s owns rows [s*N/G, (s+1)*N/G))."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+# ---- host-side key codec (same bit layout as csrc/common.cuh; used by the CPU/gloo tests and for decoding) ----
+def order_bits(scores: np.ndarray) -> np.ndarray:
+    b = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint32)
+    mask = ((b.view(np.int32) >> 31).view(np.uint32)) >> np.uint32(1)
+    return (b ^ mask) ^ np.uint32(0x80000000)
+
+
+def encode_keys(scores: np.ndarray, indices: np.ndarray, descending: bool) -> np.ndarray:
+    o = order_bits(scores)
+    if descending:
+        o = ~o
+    return (o.astype(np.uint64) << np.uint64(32)) | np.asarray(indices, dtype=np.uint64)
+
+
+def decode_keys(keys: np.ndarray, descending: bool):
+    keys = np.asarray(keys, dtype=np.uint64)
+    hi = (keys >> np.uint64(32)).astype(np.uint32)
+    if descending:
+        hi = ~hi
+    o = hi ^ np.uint32(0x80000000)
+    mask = ((o.view(np.int32) >> 31).view(np.uint32)) >> np.uint32(1)
+    return (keys & np.uint64(0xFFFFFFFF)), (o ^ mask).view(np.float32)
+
+
+def merge_keys_host(key_lists: np.ndarray, k: int) -> np.ndarray:
+    """Reference semantics of the merge (K10): the k smallest keys of the union. key_lists: (n_lists, k)."""
+    flat = np.asarray(key_lists, dtype=np.uint64).reshape(-1)
+    flat = flat[flat != np.uint64(0xFFFFFFFFFFFFFFFF)]
+    return np.sort(flat)[:k]
+
+
+class ShardedKnn:
+    """One rank's view of a row-sharded corpus. kind: 'f32' (DeviceBatch), 'u8' (U8Corpus), 'binary' (BinaryCorpus)."""
+
+    def __init__(self, shard, kind: str = "f32", metric: str = "cosine", group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.shard, self.kind, self.metric, self.group = shard, kind, metric, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._metric_id = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
+        self._bufs = {}
+
+    def _buffers(self, nq: int, k: int, device):
+        key = (nq, k)
+        if key not in self._bufs:
+            t = self.torch
+            self._bufs[key] = dict(
+                local=t.empty(nq * k, dtype=t.int64, device=device),
+                gathered=t.empty(self.world * nq * k, dtype=t.int64, device=device),
+                idx=t.empty(nq * k, dtype=t.int64, device=device),
+                score=t.empty(nq * k, dtype=t.float32 if self.kind != "binary" else t.int32, device=device),
+                keys=t.empty(nq * k, dtype=t.int64, device=device))
+        return self._bufs[key]
+
+    def knn_dev(self, dev_queries, nq: int, k: int):
+        """dev_queries: torch tensor on this rank's GPU (f32 nq x d, or int64 words for 'binary'). Returns
+        (idx int64[nq,k], score[nq,k]) tensors on the device, identical on every rank. All work is queued on
+        torch's current stream."""
+        t = self.torch
+        stream = C.c_void_p(t.cuda.current_stream().cuda_stream)
+        b = self._buffers(nq, k, dev_queries.device)
+        qp = C.c_void_p(dev_queries.data_ptr())
+        lp = C.c_void_p(b["local"].data_ptr())
+        if self.kind == "f32":
+            L.call("innr_cuda_batch_knn_keys_dev", self.shard.h, self._metric_id, qp, nq, k, lp, stream)
+        elif self.kind == "u8":
+            L.call("innr_cuda_batch_knn_u8_keys_dev", self.shard.h, qp, nq, k, lp, stream)
+        else:
+            L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+            src, n_lists = b["gathered"], self.world
+        else:
+            src, n_lists = b["local"], 1
+        if self.kind == "binary":
+            # distance is the high half of the key itself
+            L.call("innr_cuda_merge_keys_dev", C.c_void_p(src.data_ptr()), n_lists, nq, k, L.METRIC_L2,
+                   C.c_void_p(b["keys"].data_ptr()), C.c_void_p(b["idx"].data_ptr()), None, stream)
+            return b["idx"].view(nq, k), (b["keys"] >> 32).view(nq, k)
+        m = L.METRIC_L2 if (self.kind == "f32" and self.metric == "l2") else L.METRIC_DOT
+        L.call("innr_cuda_merge_keys_dev", C.c_void_p(src.data_ptr()), n_lists, nq, k, m,
+               None, C.c_void_p(b["idx"].data_ptr()), C.c_void_p(b["score"].data_ptr()), stream)
+        return b["idx"].view(nq, k), b["score"].view(nq, k)
+
+    def knn(self, queries_host: np.ndarray, k: int, pinned_stage=None):
+        """End-to-end call with HOST buffers: H2D of the queries, shard scan, allgather, merge, D2H of the result."""
+        t = self.torch
+        q = np.ascontiguousarray(queries_host)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        src = t.from_numpy(q.view(np.int64) if self.kind == "binary" else q)
+        dq = src.to(f"cuda:{t.cuda.current_device()}", non_blocking=True)
+        idx, score = self.knn_dev(dq, nq, k)
+        return idx.cpu().numpy().astype(np.uint64), score.cpu().numpy()

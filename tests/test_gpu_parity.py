@@ -21,6 +21,17 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
+def same_scores(a, b):
+    """Bit equality, except that any NaN matches any NaN: NaN sign/payload is not portable across the reference's
+    own targets (x86 propagates the operand payload and makes 0*inf a NEGATIVE NaN, aarch64 a positive default
+    NaN); the device produces the canonical 0x7FFFFFFF ("NaN scores")."""
+    a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+    if a.shape != b.shape:
+        return False
+    both_nan = np.isnan(a) & np.isnan(b)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | both_nan))
+
+
 def rand_rows(n, d, seed, scale=1.0):
     rng = np.random.default_rng(seed)
     return (rng.standard_normal((n, d)) * scale).astype(np.float32)
@@ -96,13 +107,11 @@ def test_knn_special_values(ib, oracle):
     rows[31] = -0.0
     q = np.array([1.0, -2.0, 0.5, 0.0], np.float32)
     gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), 300, 4), oracle.VerticalBatch.from_flat(rows.reshape(-1), 300, 4)
-    for k in (3, 300):
-        if k > 128:
-            continue
+    for k in (3, 100):
         g, w = ib.batch_knn_dot(q, gb, k), oracle.batch_knn_dot(q, ob, k)
-        assert g.indices == w.indices and np.array_equal(bits(g.scores), bits(w.scores))
+        assert g.indices == w.indices and same_scores(g.scores, w.scores)
         g, w = ib.batch_knn_cosine(q, gb, k), oracle.batch_knn_cosine(q, ob, k)
-        assert g.indices == w.indices and np.array_equal(bits(g.scores), bits(w.scores))
+        assert g.indices == w.indices and same_scores(g.scores, w.scores)
     zq = np.zeros(4, np.float32)  # zero query: all cosines 0.0 -> first k indices
     g, w = ib.batch_knn_cosine(zq, gb, 10), oracle.batch_knn_cosine(zq, ob, 10)
     assert g.indices == w.indices == list(range(10))
