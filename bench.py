@@ -43,6 +43,15 @@ WORKLOADS = {
 }
 
 
+def load_traffic(workload, scale, world):
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), only
+    meaningful for the exact captured configuration (scale 1.0, 1 GPU); else null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if scale != 1.0 or world != 1 or not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(workload, {}).get("bytes")
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -499,7 +508,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": w.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": load_traffic(args.workload, args.scale, world),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms},
             "clocks": clocks,
         }

@@ -27,16 +27,33 @@ namespace {
 
 constexpr int U8_THREADS = 256;
 
-__device__ __forceinline__ float byte_to_f32(unsigned word, int k) {
+// The 2^23 magic constant is kept in a register the compiler cannot see through, so that PRMT takes the byte
+// selector as its immediate operand (with a literal constant the selector is re-materialised by a MOV per byte).
+// (An asm mov is folded by ptxas too, so the value travels as a kernel argument: U8Args::magic.)
+#ifndef INNR_U8_I2F
+#define INNR_U8_I2F 0
+#endif
+__device__ __forceinline__ float byte_to_f32(unsigned word, int k, unsigned magic) {
+#if INNR_U8_I2F
+  (void)magic;
+  return __uint2float_rn((word >> (8 * k)) & 0xFFu);  // I2F.F32.U8 with a byte selector
+#else
   // bytes: [b_k, 0x00, 0x00, 0x4B] = 2^23 + b_k as f32; subtracting 2^23 is exact
-  unsigned bits = __byte_perm(word, 0x4B000000u, 0x7440u | (unsigned)k);
+  unsigned bits = __byte_perm(word, magic, 0x7440u | (unsigned)k);
   return __fsub_rn(__uint_as_float(bits), 8388608.0f);
+#endif
 }
 
-__device__ __forceinline__ void fma16(const uint4 v, const float* __restrict__ q, float* acc) {
+__device__ __forceinline__ void fma16(const uint4 v, const float* __restrict__ q, float* acc, unsigned magic) {
   const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = fmaf(q[e], byte_to_f32(w[e >> 2], e & 3), acc[e]);
+  for (int g = 0; g < 4; ++g) {
+    const float4 qv = *reinterpret_cast<const float4*>(q + 4 * g);  // 16-byte aligned by construction
+    acc[4 * g + 0] = fmaf(qv.x, byte_to_f32(w[g], 0, magic), acc[4 * g + 0]);
+    acc[4 * g + 1] = fmaf(qv.y, byte_to_f32(w[g], 1, magic), acc[4 * g + 1]);
+    acc[4 * g + 2] = fmaf(qv.z, byte_to_f32(w[g], 2, magic), acc[4 * g + 2]);
+    acc[4 * g + 3] = fmaf(qv.w, byte_to_f32(w[g], 3, magic), acc[4 * g + 3]);
+  }
 }
 
 __device__ __forceinline__ float hsum8(const float* v) {  // src/arch/x86_64.rs:982-987
@@ -47,7 +64,7 @@ __device__ __forceinline__ float hsum8(const float* v) {  // src/arch/x86_64.rs:
 
 // mixed_dot_u8_f32 of the smem query against the vector whose chunk 0 is at p
 __device__ __forceinline__ float mixed_dot(const uint4* __restrict__ p, size_t ld, unsigned d, unsigned chunks,
-                                           const float* __restrict__ sq) {
+                                           const float* __restrict__ sq, const unsigned magic) {
   if (d == 0) return 0.0f;
   if (d < 16) {  // portable path: sequential unfused sum (src/scalar.rs:353-358)
     uint4 v = ldg_stream_u4(p);
@@ -55,7 +72,7 @@ __device__ __forceinline__ float mixed_dot(const uint4* __restrict__ p, size_t l
     float s = 0.0f;
 #pragma unroll
     for (int e = 0; e < 16; ++e)
-      if ((unsigned)e < d) s = __fadd_rn(s, __fmul_rn(sq[e], byte_to_f32(w[e >> 2], e & 3)));
+      if ((unsigned)e < d) s = __fadd_rn(s, __fmul_rn(sq[e], byte_to_f32(w[e >> 2], e & 3, magic)));
     return s;
   }
   float acc[32];
@@ -68,16 +85,16 @@ __device__ __forceinline__ float mixed_dot(const uint4* __restrict__ p, size_t l
     uint4 v1 = ldg_stream_u4(p + (size_t)(2 * b + 1) * ld);
     uint4 v2 = ldg_stream_u4(p + (size_t)(2 * b + 2) * ld);
     uint4 v3 = ldg_stream_u4(p + (size_t)(2 * b + 3) * ld);
-    fma16(v0, sq + 32 * b, acc);
-    fma16(v1, sq + 32 * b + 16, acc + 16);
-    fma16(v2, sq + 32 * b + 32, acc);
-    fma16(v3, sq + 32 * b + 48, acc + 16);
+    fma16(v0, sq + 32 * b, acc, magic);
+    fma16(v1, sq + 32 * b + 16, acc + 16, magic);
+    fma16(v2, sq + 32 * b + 32, acc, magic);
+    fma16(v3, sq + 32 * b + 48, acc + 16, magic);
   }
   for (; b < chunks32; ++b) {
     uint4 v0 = ldg_stream_u4(p + (size_t)(2 * b) * ld);
     uint4 v1 = ldg_stream_u4(p + (size_t)(2 * b + 1) * ld);
-    fma16(v0, sq + 32 * b, acc);
-    fma16(v1, sq + 32 * b + 16, acc + 16);
+    fma16(v0, sq + 32 * b, acc, magic);
+    fma16(v1, sq + 32 * b + 16, acc + 16, magic);
   }
   float all[8];
 #pragma unroll
@@ -101,12 +118,12 @@ __device__ __forceinline__ float mixed_dot(const uint4* __restrict__ p, size_t l
   }
 #pragma unroll
   for (int e = 0; e < 24; ++e)  // 8-wide chunks (at most 3)
-    if ((unsigned)e < n8) rem[e & 7] = fmaf(sq[rs + e], byte_to_f32(w[e >> 2], e & 3), rem[e & 7]);
+    if ((unsigned)e < n8) rem[e & 7] = fmaf(sq[rs + e], byte_to_f32(w[e >> 2], e & 3, magic), rem[e & 7]);
   result = __fadd_rn(result, hsum8(rem));  // always added, even when empty (src/arch/x86_64.rs:1004-1009)
 #pragma unroll
   for (int e = 0; e < 31; ++e)  // scalar tail, unfused (src/arch/x86_64.rs:1013-1017)
     if ((unsigned)e >= n8 && (unsigned)e < remaining)
-      result = __fadd_rn(result, __fmul_rn(sq[rs + e], byte_to_f32(w[e >> 2], e & 3)));
+      result = __fadd_rn(result, __fmul_rn(sq[rs + e], byte_to_f32(w[e >> 2], e & 3, magic)));
   return result;
 }
 
@@ -115,6 +132,7 @@ struct U8Args {
   unsigned long long ld;
   unsigned n, d, chunks, n_tiles, index_base;
   float alpha, offset;
+  unsigned magic;      // 0x4B000000 (2^23 as f32 bits), see byte_to_f32
   const float* query;  // device, d floats
   int k, mode;         // mode (scores kernel): 0 raw mixed dot, 1 asymmetric score
   uint64_t* partials;
@@ -123,8 +141,11 @@ struct U8Args {
   float* scores_out;
 };
 
+#ifndef INNR_U8_MINB
+#define INNR_U8_MINB 3
+#endif
 template <int R, bool KNN>
-__global__ void __launch_bounds__(U8_THREADS) u8_scan_kernel(const U8Args a) {
+__global__ void __launch_bounds__(U8_THREADS, INNR_U8_MINB) u8_scan_kernel(const U8Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned d_pad = (a.d + 31) / 32 * 32 + 32;
   float* sq = reinterpret_cast<float*>(smem_raw);
@@ -151,7 +172,7 @@ __global__ void __launch_bounds__(U8_THREADS) u8_scan_kernel(const U8Args a) {
     const bool valid = i < a.n;
     float score = 0.0f;
     if (valid) {
-      float mixed = mixed_dot(a.data + i, a.ld, a.d, a.chunks, sq);
+      float mixed = mixed_dot(a.data + i, a.ld, a.d, a.chunks, sq, a.magic);
       score = (KNN || a.mode == 1) ? __fadd_rn(__fmul_rn(scale, mixed), bias) : mixed;  // src/scalar.rs:299
     }
     if (KNN) lists[0].offer(make_key_desc(score, a.index_base + i), valid, thrs[0], a.k, lane);
@@ -249,6 +270,7 @@ U8Args make_args(const U8View& v, const float* q) {
   a.index_base = v.index_base;
   a.alpha = v.alpha;
   a.offset = v.offset;
+  a.magic = 0x4B000000u;
   a.query = q;
   return a;
 }
