@@ -309,3 +309,128 @@ def test_maxsim_colbert_shape_generated(ib, oracle):
         assert np.all(np.abs(got.astype(np.float64) - want) <= 1e-5 * scale + 1e-6)
         rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
         assert float(np.max(rel)) < 1e-5, float(np.max(rel))   # north_star: f32 scores within 1e-5 relative
+
+
+# ------------------------------------------------------------------------------------------------ sharding (K10)
+def test_sharded_merge_on_one_gpu(ib, oracle):
+    """The multi-rank path emulated as one process over all ranks' data (B200_PROFILING.md: never run ranks that wait
+    on one another on one GPU): 3 contiguous row shards with index_base, local keys via *_keys_dev on torch's
+    stream, concatenated as an allgather would, merged by merge_keys_kernel."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L, sharded
+    n, d, k, nq = 9001, 40, 10, 5
+    rng = np.random.default_rng(4)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)   # heavy ties
+    qs = rng.integers(-3, 4, size=(nq, d)).astype(np.float32)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    world = 3
+    shards = []
+    for r in range(world):
+        lo, hi = sharded.shard_range(n, r, world)
+        pdx = np.ascontiguousarray(rows[lo:hi].T).reshape(-1)
+        shards.append(ib.DeviceBatch.from_pdx(pdx, hi - lo, d, index_base=lo))
+    dq = torch.from_numpy(qs).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for metric, mid, single in (("dot", L.METRIC_DOT, "batch_knn_dot"), ("cosine", L.METRIC_COSINE, "batch_knn_cosine"),
+                                ("l2", L.METRIC_L2, "batch_knn")):
+        gathered = torch.empty(world * nq * k, dtype=torch.int64, device="cuda")
+        for r, sh in enumerate(shards):
+            L.call("innr_cuda_batch_knn_keys_dev", sh.h, mid, C.c_void_p(dq.data_ptr()), nq, k,
+                   C.c_void_p(gathered[r * nq * k:].data_ptr()), stream)
+        idx = torch.empty(nq * k, dtype=torch.int64, device="cuda")
+        sc = torch.empty(nq * k, dtype=torch.float32, device="cuda")
+        L.call("innr_cuda_merge_keys_dev", C.c_void_p(gathered.data_ptr()), world, nq, k, mid, None,
+               C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()), stream)
+        torch.cuda.synchronize()
+        idx, sc = idx.cpu().numpy().reshape(nq, k), sc.cpu().numpy().reshape(nq, k)
+        for j in range(nq):
+            if metric == "l2":
+                dist_all = oracle.batch_l2_squared(qs[j], ob)
+                order = np.lexsort((np.arange(n), dist_all))[:k]
+                assert idx[j].tolist() == order.tolist() and np.array_equal(bits(sc[j]), bits(dist_all[order]))
+            else:
+                w = getattr(oracle, single)(qs[j], ob, k)
+                assert idx[j].tolist() == w.indices and np.array_equal(bits(sc[j]), bits(w.scores))
+    # ShardedKnn (world size 1 when torch.distributed is not initialised) == the plain call
+    sk = sharded.ShardedKnn(shards[0], "f32", "cosine")
+    i1, s1 = sk.knn(qs, k)
+    i2, s2 = ib.batch_knn_many("cosine", qs, shards[0], k)
+    assert np.array_equal(i1, i2) and np.array_equal(bits(s1), bits(s2))
+
+
+# ------------------------------------------------------------------------------------------------ full BASELINE sizes
+def _free_gb():
+    import torch
+    return torch.cuda.mem_get_info()[0] / 1e9
+
+
+def test_full_size_c2a_properties(ib, oracle):
+    """BASELINE C2a at full size (10M x 768, G-hash, generated on the device) through size-independent properties:
+    every returned (index, score) is re-derived bit-exactly on the CPU from the stateless generator; results are
+    sorted by (score desc, index asc); no sampled row outside the result beats the k-th score; and
+    top-k(whole) == merge(top-k(first half), top-k(second half))."""
+    from innr_b200 import synth, sharded
+    if _free_gb() < 70:
+        pytest.skip("needs ~62 GB of free HBM")
+    n, d, k = 10_000_000, 768, 10
+    whole = ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, 0, n, d)
+    q = oracle.ghash_f32(synth.SALT_QUERY, 0, d)
+    for metric, single, desc in (("cosine", "batch_knn_cosine", True), ("l2", "batch_knn", False)):
+        idx, sc = ib.batch_knn_many(metric, q, whole, k)
+        idx, sc = idx[0], sc[0]
+        rows = np.stack([oracle.ghash_f32(synth.SALT_CORPUS, int(i) * d, d) for i in idx])
+        small = oracle.VerticalBatch.from_flat(rows.reshape(-1), k, d)
+        want = oracle.batch_cosine(q, small, oracle.batch_norms(small)) if metric == "cosine" else oracle.batch_l2_squared(q, small)
+        assert np.array_equal(bits(sc), bits(want)), metric
+        keys = sharded.encode_keys(sc, idx, desc)
+        assert np.all(keys[:-1] < keys[1:])
+        rng = np.random.default_rng(1)
+        sample = rng.integers(0, n, size=3000)
+        srows = np.stack([oracle.ghash_f32(synth.SALT_CORPUS, int(i) * d, d) for i in sample])
+        sb = oracle.VerticalBatch.from_flat(srows.reshape(-1), len(sample), d)
+        ssc = oracle.batch_cosine(q, sb, oracle.batch_norms(sb)) if metric == "cosine" else oracle.batch_l2_squared(q, sb)
+        skeys = sharded.encode_keys(ssc, sample, desc)
+        inside = set(int(i) for i in idx)
+        assert all(int(i) in inside for i, kk in zip(sample, skeys) if kk < keys[-1])
+    halves = [ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, lo, n // 2, d, index_base=lo) for lo in (0, n // 2)]
+    parts = [ib.batch_knn_many("cosine", q, h, k) for h in halves]
+    merged = sharded.merge_keys_host(np.stack([sharded.encode_keys(p[1][0], p[0][0], True) for p in parts]), k)
+    idx, sc = ib.batch_knn_many("cosine", q, whole, k)
+    assert np.array_equal(merged, sharded.encode_keys(sc[0], idx[0], True))
+
+
+def test_full_size_c4_c5_properties(ib, oracle):
+    """BASELINE C4 (100M x 1024-bit, top-100) and C5 (50M x 384 u8, top-10) at full size: every returned entry is
+    re-derived bit-exactly on the CPU; order is (distance asc | score desc, index asc); a random sample holds no
+    better candidate."""
+    from innr_b200 import synth
+    if _free_gb() < 40:
+        pytest.skip("needs ~35 GB of free HBM")
+    n, k = 100_000_000, 100
+    corpus = ib.BinaryCorpus.generate(synth.SALT_CODES, 0, n, 1024)
+    qc = oracle.ghash_u64(synth.SALT_QUERY, 0, 16)
+    idx, ds = ib.hamming_topk(qc, corpus, k)
+    want = [oracle.binary_hamming(oracle.PackedBinary(qc, 1024),
+                                  oracle.PackedBinary(oracle.ghash_u64(synth.SALT_CODES, int(i) * 16, 16), 1024)) for i in idx]
+    assert ds.tolist() == want
+    keys = (ds.astype(np.uint64) << np.uint64(32)) | idx
+    assert np.all(keys[:-1] < keys[1:])
+    rng = np.random.default_rng(2)
+    sample = rng.integers(0, n, size=20000)
+    scodes = np.stack([oracle.ghash_u64(synth.SALT_CODES, int(i) * 16, 16) for i in sample])
+    sd = np.array([bin(int(x)).count("1") for x in np.bitwise_xor(scodes, qc).reshape(-1)]).reshape(-1, 16).sum(1)
+    skeys = (sd.astype(np.uint64) << np.uint64(32)) | sample.astype(np.uint64)
+    inside = set(int(i) for i in idx)
+    assert all(int(i) in inside for i, kk in zip(sample, skeys) if kk < keys[-1])
+    del corpus
+
+    n, d, k = 50_000_000, 384, 10
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    c8 = ib.U8Corpus.generate(synth.SALT_CORPUS, 0, n, d, gp)
+    q = oracle.ghash_f32(synth.SALT_QUERY, 0, d)
+    got = ib.batch_knn_u8(q, c8, gp, k)
+    for i, s in got:
+        row = oracle.quantize_u8(oracle.ghash_f32(synth.SALT_CORPUS, i * d, d), op)
+        assert np.float32(s).tobytes() == np.float32(oracle.asymmetric_dot_u8(q, row, op)).tobytes()
+    assert all((got[j][1], -got[j][0]) > (got[j + 1][1], -got[j + 1][0]) for j in range(k - 1))
