@@ -113,8 +113,9 @@ int ensure_ctx(int device, DeviceCtx** out) {
     // per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
     c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32;
     CU(cudaMalloc(&c.ws.partials, c.ws.partials_cap * sizeof(uint64_t)));
-    CU(cudaMalloc(&c.ws.ticket, sizeof(unsigned)));
-    CU(cudaMemset(c.ws.ticket, 0, sizeof(unsigned)));
+    CU(cudaMalloc(&c.ws.group_partials, (size_t)(c.ws.num_sms * 8 / 32 + 2) * 8 * 128 * sizeof(uint64_t)));
+    CU(cudaMalloc(&c.ws.tickets, 1024 * sizeof(unsigned)));
+    CU(cudaMemset(c.ws.tickets, 0, 1024 * sizeof(unsigned)));
     c.h_pin.pinned = true;
     c.ready = true;
   } else {
@@ -223,7 +224,8 @@ int innr_cuda_shutdown(void) {
     cudaStreamSynchronize(c.stream);
     c.d_query.release(); c.d_keys.release(); c.d_scores.release(); c.d_aux.release(); c.h_pin.release();
     cudaFree(c.ws.partials);
-    cudaFree(c.ws.ticket);
+    cudaFree(c.ws.group_partials);
+    cudaFree(c.ws.tickets);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
     cudaStreamDestroy(c.stream);

@@ -56,7 +56,8 @@ struct HamArgs {
   int k;
   uint64_t* partials;
   uint64_t* out_keys;
-  unsigned* ticket;
+  uint64_t* group_partials;
+  unsigned* tickets;
   uint32_t* dist_out;
 };
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(HAM_THREADS) hamming_kernel(const HamArgs a) {
     if (TOPK) lists[0].offer(make_key_u32(dist, a.index_base + i), valid, thrs[0], a.k, lane);
     else if (valid) a.dist_out[i] = dist;
   }
-  if (TOPK) block_finish<R, 1>(lists, thrs, 1, a.k, smem_keys, a.partials, a.out_keys, a.ticket);
+  if (TOPK) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
 // row-major words [n][words] -> chunk-major uint4, masking padding bits (PackedBinary::new)
@@ -156,9 +157,7 @@ cudaError_t launch_ham(const HamArgs& a, size_t smem, int num_sms, cudaStream_t 
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HAM_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorInvalidConfiguration;
-  unsigned grid = TOPK ? (unsigned)occ * (unsigned)num_sms : a.n_tiles;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (grid == 0) grid = 1;
+  unsigned grid = TOPK ? balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms) : (a.n_tiles ? a.n_tiles : 1);
   kern<<<grid, HAM_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -226,7 +225,8 @@ cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_word
     HamArgs a = make_args(v, dev_query_words + q * 2 * v.chunks);
     a.k = (int)k;
     a.partials = ws.partials;
-    a.ticket = ws.ticket;
+    a.group_partials = ws.group_partials;
+    a.tickets = ws.tickets;
     a.out_keys = dev_keys + q * k;
     size_t smem = v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
     cudaError_t e;

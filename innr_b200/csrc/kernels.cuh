@@ -16,11 +16,21 @@ enum PdxMode : int {
 };
 
 struct Workspace {
-  uint64_t* partials = nullptr;  // per-CTA top-k lists
-  size_t partials_cap = 0;       // in u64
-  unsigned* ticket = nullptr;    // last-CTA-done counter (self-resetting)
+  uint64_t* partials = nullptr;        // per-CTA top-k lists
+  size_t partials_cap = 0;             // in u64
+  uint64_t* group_partials = nullptr;  // per-group (32 CTAs) merged lists
+  unsigned* tickets = nullptr;         // [0] top level, [1+g] group g; zeroed once, self-resetting
   int num_sms = 0;
 };
+
+// Persistent grids stride tiles by gridDim: pick the largest grid <= max_ctas for which every CTA gets the same
+// number of tiles (+-0), so no CTA runs a whole extra tile while the others idle (matters for small shards).
+inline unsigned balanced_grid(unsigned n_tiles, unsigned max_ctas) {
+  if (n_tiles == 0 || max_ctas == 0) return 1;
+  if (n_tiles <= max_ctas) return n_tiles;
+  unsigned waves = (n_tiles + max_ctas - 1) / max_ctas;
+  return (n_tiles + waves - 1) / waves;
+}
 
 struct PdxView {
   const float* data;  // data[dd * ld + i]

@@ -40,7 +40,8 @@ struct PdxArgs {
   int k;
   uint64_t* partials;
   uint64_t* out_keys;
-  unsigned* ticket;
+  uint64_t* group_partials;
+  unsigned* tickets;
   float* scores_out;      // scores mode: out[q * ld + i]
   const float* norms_in;  // PDX_COSINE_NORMS
 };
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a)
     }
   }
 
-  if (KNN) block_finish<R, QB>(lists, thrs, a.nq_valid, a.k, smem_keys, a.partials, a.out_keys, a.ticket);
+  if (KNN) block_finish<R, QB>(lists, a.nq_valid, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
 template <int MODE, int QB, int R, bool KNN>
@@ -219,10 +220,8 @@ cudaError_t launch_one(const PdxArgs& a, size_t smem, int max_ctas_per_sm_hint, 
     occ = o;
   }
   (void)max_ctas_per_sm_hint;
-  unsigned grid = (unsigned)occ * (unsigned)num_sms;
-  if (!KNN) grid = a.n_tiles;  // no cross-tile state: one CTA per tile, hardware scheduler balances
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (grid == 0) grid = 1;
+  unsigned grid = balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms);
+  if (!KNN) grid = a.n_tiles ? a.n_tiles : 1;  // no cross-tile state: one CTA per tile, hardware scheduler balances
   kern<<<grid, SCAN_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -251,7 +250,8 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
   a.index_base = v.index_base;
   a.k = (int)k;
   a.partials = ws.partials;
-  a.ticket = ws.ticket;
+  a.group_partials = ws.group_partials;
+  a.tickets = ws.tickets;
   const bool big_k = k > 32;
   // query blocking: 8 queries share one pass over the corpus when their lists fit in registers
   const int QBMAX = big_k ? 1 : 8;
@@ -325,8 +325,7 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int 
   const int q = blockIdx.x, lane = threadIdx.x;
   WarpList<R> list;
   list.init();
-  uint64_t thr = KEY_SENTINEL;
-  warp_merge_lists<R, true>(list, thr, in + (size_t)q * k, 0, 1, n_lists, (size_t)nq * k, k, lane);
+  warp_merge_lists<R, true>(list, in + (size_t)q * k, 0, 1, n_lists, (size_t)nq * k, k, lane);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     int p = r * 32 + lane;
@@ -345,8 +344,8 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int 
 
 template <int R>
 __global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const float* dist, unsigned n, int k,
-                                                                     uint64_t* partials, uint64_t* out_keys,
-                                                                     unsigned* ticket) {
+                                                                     uint64_t* partials, uint64_t* group_partials,
+                                                                     uint64_t* out_keys, unsigned* tickets) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -362,7 +361,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const floa
     const float dv = valid ? dist[i] : 0.0f;
     lists[0].offer(make_key_asc(dv, i), valid, thrs[0], k, lane);
   }
-  block_finish<R, 1>(lists, thrs, 1, k, smem_keys, partials, out_keys, ticket);
+  block_finish<R, 1>(lists, 1, k, smem_keys, partials, group_partials, out_keys, tickets);
 }
 
 }  // namespace
@@ -391,10 +390,10 @@ cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k
   size_t smem = (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t);
   if (k <= 32)
     topk_distances_kernel<1><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
-                                                              dev_keys, ws.ticket);
+                                                              ws.group_partials, dev_keys, ws.tickets);
   else
     topk_distances_kernel<4><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
-                                                              dev_keys, ws.ticket);
+                                                              ws.group_partials, dev_keys, ws.tickets);
   ++*launches;
   return cudaGetLastError();
 }

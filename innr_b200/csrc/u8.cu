@@ -137,7 +137,8 @@ struct U8Args {
   int k, mode;         // mode (scores kernel): 0 raw mixed dot, 1 asymmetric score
   uint64_t* partials;
   uint64_t* out_keys;
-  unsigned* ticket;
+  uint64_t* group_partials;
+  unsigned* tickets;
   float* scores_out;
 };
 
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(U8_THREADS, INNR_U8_MINB) u8_scan_kernel(const
     if (KNN) lists[0].offer(make_key_desc(score, a.index_base + i), valid, thrs[0], a.k, lane);
     else if (valid) a.scores_out[i] = score;
   }
-  if (KNN) block_finish<R, 1>(lists, thrs, 1, a.k, smem_keys, a.partials, a.out_keys, a.ticket);
+  if (KNN) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
 __global__ void u8_pack_kernel(const uint8_t* __restrict__ rows, unsigned n, unsigned d, uint4* __restrict__ codes,
@@ -252,9 +253,7 @@ cudaError_t launch_u8(const U8Args& a, size_t smem, int num_sms, cudaStream_t s)
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, U8_THREADS, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorInvalidConfiguration;
-  unsigned grid = KNN ? (unsigned)occ * (unsigned)num_sms : a.n_tiles;
-  if (grid > a.n_tiles) grid = a.n_tiles;
-  if (grid == 0) grid = 1;
+  unsigned grid = KNN ? balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms) : (a.n_tiles ? a.n_tiles : 1);
   kern<<<grid, U8_THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -326,7 +325,8 @@ cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, 
     U8Args a = make_args(v, dev_queries + q * v.d);
     a.k = (int)k;
     a.partials = ws.partials;
-    a.ticket = ws.ticket;
+    a.group_partials = ws.group_partials;
+    a.tickets = ws.tickets;
     a.out_keys = dev_keys + q * k;
     cudaError_t e = (k <= 32) ? launch_u8<1, true>(a, smem, ws.num_sms, s) : launch_u8<4, true>(a, smem, ws.num_sms, s);
     if (e != cudaSuccess) return e;
