@@ -3,6 +3,7 @@
 #include "../../include/innr_cuda.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -28,6 +29,8 @@ struct innr_cuda_corpus {
   // tokens
   uint64_t* dev_offsets = nullptr;
   size_t total_tokens = 0, uniform_tokens = 0;
+  CUtensorMap tmap;
+  bool tmap_valid = false;
 };
 
 namespace {
@@ -177,7 +180,8 @@ U8View u8_view(const innr_cuda_corpus* c) {
   return U8View{(const uint4*)c->dev, c->n, c->d, c->ld, c->chunks, c->alpha, c->offset, (uint32_t)c->index_base};
 }
 TokView tok_view(const innr_cuda_corpus* c) {
-  return TokView{(const float*)c->dev, c->dev_offsets, c->n, c->d, c->total_tokens, c->uniform_tokens};
+  return TokView{(const float*)c->dev, c->dev_offsets, c->n, c->d, c->total_tokens, c->uniform_tokens, c->tmap,
+                 c->tmap_valid};
 }
 
 // Shared tail of every host-facing top-k call: keys device -> pinned -> decode.
@@ -928,6 +932,7 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
   if (c->bytes) {
     CU(cudaMalloc(&c->dev, c->bytes));
     CU(cudaMemcpyAsync(c->dev, tokens, c->bytes, cudaMemcpyHostToDevice, ctx->stream));
+    c->tmap_valid = make_token_tmap(&c->tmap, (const float*)c->dev, total, dim);
   }
   if (n_docs) {
     CU(cudaMalloc(&c->dev_offsets, (n_docs + 1) * sizeof(uint64_t)));
@@ -956,6 +961,7 @@ int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, 
   if (c->bytes) {
     CU(cudaMalloc(&c->dev, c->bytes));
     CU(launch_generate_tokens(salt, first_doc * tokens_per_doc, c->total_tokens, dim, (float*)c->dev, ctx->stream, &g_launches));
+    c->tmap_valid = make_token_tmap(&c->tmap, (const float*)c->dev, c->total_tokens, dim);
     CU(cudaStreamSynchronize(ctx->stream));
   }
   return INNR_OK;
@@ -968,7 +974,12 @@ static int maxsim_common(const innr_cuda_corpus* c, DeviceCtx* ctx, const float*
     if (c->n) CU(cudaMemsetAsync(dev_scores, 0, c->n * sizeof(float), s));
     return INNR_OK;
   }
-  cudaError_t e = launch_maxsim(tok_view(c), dev_q, n_q, cosine, dev_scores, s, &g_launches);
+  // tcgen05/TMEM path when the shape fits (dim 128, <= 32 query tokens); INNR_MAXSIM_V1=1 forces the CUDA-core kernel
+  static const bool force_v1 = getenv("INNR_MAXSIM_V1") != nullptr;
+  TokView tv = tok_view(c);
+  cudaError_t e = (!force_v1 && maxsim_tc_supported(tv, n_q))
+                      ? launch_maxsim_tc(tv, dev_q, n_q, cosine, dev_scores, ctx->ws.num_sms, s, &g_launches)
+                      : launch_maxsim(tv, dev_q, n_q, cosine, dev_scores, s, &g_launches);
   if (e == cudaErrorInvalidValue) return fail(INNR_EUNSUPPORTED, "maxsim: dim / n_q exceed the shared-memory tile");
   if (e != cudaSuccess) return cuda_fail(e, "launch_maxsim");
   (void)ctx;

@@ -1,0 +1,87 @@
+// umma_probe.cu -- one-tile device test of the tcgen05 path used by the MaxSim kernel:
+// D[128 x 64] = A[128 x 128] * B[64 x 128]^T, kind::tf32, A and B K-major, TMA SWIZZLE_128B panels.
+// Checks descriptor encodings, the TMEM accumulator layout and tcgen05.ld 32x32b before the real kernel uses them.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../tc_common.cuh"
+using namespace innr;
+using namespace innr::tc;
+
+constexpr int M = 128, N = 64, K = 128;
+
+__global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap tmA,
+                                             const __grid_constant__ CUtensorMap tmB, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* sA = reinterpret_cast<float*>(smem);                  // 4 panels x [128][32]
+  float* sB = reinterpret_cast<float*>(smem + 4 * 16384);      // 4 panels x [64][32]
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_full, (M + N) * K * 4);
+    for (int p = 0; p < 4; ++p) {
+      tma_load_2d(sA + p * (M * 32), &tmA, &bar_full, p * 32, 0);
+      tma_load_2d(sB + p * (N * 32), &tmB, &bar_full, p * 32, 0);
+    }
+    mbar_wait(&bar_full, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_tf32(M, N);
+    for (int kk = 0; kk < K / 8; ++kk) {
+      const uint32_t a_addr = smem_u32(sA + (kk / 4) * (M * 32)) + (kk % 4) * 32;
+      const uint32_t b_addr = smem_u32(sB + (kk / 4) * (N * 32)) + (kk % 4) * 32;
+      umma_tf32(tmem, make_smem_desc_kmajor_sw128(a_addr), make_smem_desc_kmajor_sw128(b_addr), idesc, kk > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after_sync();
+  uint32_t r[32];
+  for (int c = 0; c < N; c += 32) {
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * N + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+int main() {
+  std::vector<float> A(M * K), B(N * K);
+  srand(1);
+  for (auto& x : A) x = (float)((rand() % 33) - 16) / 8.0f;   // exactly representable in tf32
+  for (auto& x : B) x = (float)((rand() % 33) - 16) / 16.0f;
+  float *dA, *dB, *dO;
+  cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 4); cudaMalloc(&dO, M * N * 4);
+  cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dO, 0, M * N * 4);
+  CUtensorMap tmA, tmB;
+  if (!make_tmap_f32_rows(&tmA, dA, M, K, M) || !make_tmap_f32_rows(&tmB, dB, N, K, N)) { printf("tensor map failed\n"); return 2; }
+  size_t smem = 4 * 16384 + 4 * 8192 + 1024;
+  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe<<<1, 128, smem>>>(tmA, tmB, dO);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 3; }
+  std::vector<float> O(M * N);
+  cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0; int bad = 0;
+  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)A[i * K + k] * B[j * K + k];
+    double err = fabs(ref - O[i * N + j]); if (err > maxerr) maxerr = err; if (err > 1e-3) ++bad;
+  }
+  printf("umma_probe: max abs err %.3g, bad %d / %d  (O[0][0]=%f O[5][7]=%f)\n", maxerr, bad, M * N, O[0], O[5 * N + 7]);
+  return bad ? 1 : 0;
+}
