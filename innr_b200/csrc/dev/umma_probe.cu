@@ -12,7 +12,7 @@ using namespace innr::tc;
 constexpr int M = 128, N = 64, K = 128;
 
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap tmA,
-                                             const __grid_constant__ CUtensorMap tmB, float* out) {
+                                             const __grid_constant__ CUtensorMap tmB, float* out, int from_tmem) {
   extern __shared__ __align__(1024) uint8_t smem[];
   float* sA = reinterpret_cast<float*>(smem);                  // 4 panels x [128][32]
   float* sB = reinterpret_cast<float*>(smem + 4 * 16384);      // 4 panels x [64][32]
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     mbar_init(&bar_mma, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<64>(&tmem_base);
+  if (warp == 0) tmem_alloc<256>(&tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -47,15 +47,45 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
   }
   mbar_wait(&bar_mma, 0);
   tc_fence_after_sync();
+  if (from_tmem) {
+    // second pass: A staged into TMEM columns [64, 192) by the owning lanes, D2 = A(tmem) * B^T into columns [192, 256)
+    __shared__ uint64_t bar2;
+    if (threadIdx.x == 0) { mbar_init(&bar2, 1); fence_barrier_init(); }
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      uint32_t v[32];
+      const int row = threadIdx.x;
+      for (int j = 0; j < 32; ++j) {
+        const int k = c0 + j, p = k >> 5, c = (k & 31) >> 2, e = k & 3;
+        v[j] = __float_as_uint(*reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sA) + p * (M * 128) + row * 128 +
+                                                         ((c ^ (row & 7)) << 4) + (e << 2)));
+      }
+      tmem_st_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + 64 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (threadIdx.x == 0) {
+      const uint32_t idesc = make_idesc_tf32(M, N);
+      for (int kk = 0; kk < K / 8; ++kk) {
+        const uint32_t b_addr = smem_u32(sB + (kk / 4) * (N * 32)) + (kk % 4) * 32;
+        umma_tf32_ts(tmem + 192, tmem + 64 + kk * 8, make_smem_desc_kmajor_sw128(b_addr), idesc, kk > 0);
+      }
+      umma_commit(&bar2);
+    }
+    mbar_wait(&bar2, 0);
+    tc_fence_after_sync();
+  }
+  const uint32_t dcol = from_tmem ? 192 : 0;
   uint32_t r[32];
   for (int c = 0; c < N; c += 32) {
-    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + dcol + c, r);
     tmem_ld_wait();
     for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * N + c + j] = __uint_as_float(r[j]);
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tmem);
+  if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 int main() {
@@ -72,16 +102,21 @@ int main() {
   if (!make_tmap_f32_rows(&tmA, dA, M, K, M) || !make_tmap_f32_rows(&tmB, dB, N, K, N)) { printf("tensor map failed\n"); return 2; }
   size_t smem = 4 * 16384 + 4 * 8192 + 1024;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  probe<<<1, 128, smem>>>(tmA, tmB, dO);
-  cudaError_t e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 3; }
-  std::vector<float> O(M * N);
-  cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
-  double maxerr = 0; int bad = 0;
-  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
-    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)A[i * K + k] * B[j * K + k];
-    double err = fabs(ref - O[i * N + j]); if (err > maxerr) maxerr = err; if (err > 1e-3) ++bad;
+  int rc = 0;
+  for (int from_tmem = 0; from_tmem < 2; ++from_tmem) {
+    cudaMemset(dO, 0, M * N * 4);
+    probe<<<1, 128, smem>>>(tmA, tmB, dO, from_tmem);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 3; }
+    std::vector<float> O(M * N);
+    cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0; int bad = 0;
+    for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
+      double ref = 0; for (int k = 0; k < K; ++k) ref += (double)A[i * K + k] * B[j * K + k];
+      double err = fabs(ref - O[i * N + j]); if (err > maxerr) maxerr = err; if (err > 1e-3) ++bad;
+    }
+    printf("umma_probe (A from %s): max abs err %.3g, bad %d / %d  (O[0][0]=%f O[5][7]=%f)\n", from_tmem ? "TMEM" : "smem", maxerr, bad, M * N, O[0], O[5 * N + 7]);
+    rc |= bad ? 1 : 0;
   }
-  printf("umma_probe: max abs err %.3g, bad %d / %d  (O[0][0]=%f O[5][7]=%f)\n", maxerr, bad, M * N, O[0], O[5 * N + 7]);
-  return bad ? 1 : 0;
+  return rc;
 }

@@ -3,20 +3,24 @@
 // Replaces the reference's per-pair AVX-512 loops (maxsim_avx512 src/arch/x86_64.rs:119-143, cosine_avx512
 // :681-786, driven per document by examples/maxsim_colbert.rs:171-174) with one dense contraction per 128-token
 // tile:   S[128 tokens x 64] = X[128 x 128] * [Qhi ; Qlo]^T        (kind::tf32, f32 accumulate in TMEM)
-// issued twice per tile: once with X as loaded (the tensor core reads the top 19 bits = Xhi) and once with
-// Xlo = X - trunc_tf32(X) written in place over the same shared-memory stage. Adding columns j and 32+j gives
-// (Qhi+Qlo)_j . (Xhi+Xlo) -- a 4-term split whose error is ~2^-21 relative to sum|q.x| (the f32 tolerance of the
+// issued twice per tile: once with X as loaded by TMA into shared memory (the tensor core reads the top 19 bits =
+// Xhi) and once with Xlo = X - trunc_tf32(X) as the A operand in TENSOR MEMORY (written there by the converter
+// warps with tcgen05.st, so the split costs no shared-memory write and no second operand read: the kernel is
+// shared-memory-bandwidth sensitive, 4 x 64 KB per tile). Adding columns j and 32+j gives
+// (Qhi+Qlo)_j . Xhi + Qhi_j . Xlo -- the classic 3-term split whose error is ~2^-21 relative to sum|q.x| (the f32 tolerance of the
 // north_star, 1e-5, is 2^-16.6). The row-max over a document's tokens and the sum over query tokens are fused in
 // the TMEM->register epilogue; one f32 per document leaves the SM.
 //
-// Shape of the machine (one persistent CTA per SM, 320 threads, ~225 KB shared memory, 192 TMEM columns):
-//   warp 8      TMA producer: 4 x cp.async.bulk.tensor (128 rows x 128 B, SWIZZLE_128B) per tile -> 3-stage ring
-//   warp 9      MMA issuer (one thread): hi(i) then lo(i-1), 16 tcgen05.mma (M128 N64 K8) each, commits to mbarriers
-//   warps 4-7   converters: after hi(i) has been read, Xlo in place + per-token sum of squares (cosine)
+// Shape of the machine (one persistent CTA per SM, 448 threads, ~225 KB shared memory, 192 TMEM columns):
+//   warp 12     TMA producer: 4 x cp.async.bulk.tensor (128 rows x 128 B, SWIZZLE_128B) per tile -> 3-stage ring
+//   warp 13     MMA issuer (one thread): hi(i) then lo(i-1), 16 tcgen05.mma (M128 N64 K8) each, commits to mbarriers
+//   warps 4-11  converters: after hi(i) has been read, Xlo in place + per-token sum of squares (cosine)
 //   warps 0-3   epilogue: tcgen05.ld 32 lanes x 64 columns, hi+lo add, cosine scale, max over token lanes
 //               (halving butterfly; segmented scan when a document boundary falls inside the 32-token chunk),
 //               warp 0 stitches chunk summaries in token order and writes one score per document.
 // HBM-bound by design: tensor time is ~40 % of the tile's HBM time.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -27,7 +31,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 320;   // 4 epilogue + 4 converter + TMA + MMA warps
 constexpr int TILE_M = 128;                 // tokens per tile (UMMA M)
 constexpr int DIM = 128;                    // K
 constexpr int NQ = 32;                      // query tokens (padded)
@@ -39,6 +43,8 @@ constexpr int QPANEL_BYTES = UMMA_N * 128;  // 8 KB
 constexpr int QBYTES = 4 * QPANEL_BYTES;
 constexpr float EPS_SQ = 1e-9f * 1e-9f;
 constexpr int NO_DOC = 0x7FFFFFFF;
+constexpr int BB_COL0 = 192;                // TMEM columns [192, 200): ring of per-token sum of squares (8 tiles)
+constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo buffers of 128 columns
 
 struct __align__(8) Summary {  // per 32-token chunk, written by its epilogue warp, read by the stitcher (warp 0)
   float head[NQ];
@@ -47,8 +53,7 @@ struct __align__(8) Summary {  // per 32-token chunk, written by its epilogue wa
 };
 
 struct SharedTail {  // everything after the operand buffers
-  uint64_t full[STAGES], empty[STAGES], hi_done[STAGES], lo_ready[STAGES], tmem_full[STAGES], tmem_empty[STAGES];
-  float bb[STAGES][TILE_M];
+  uint64_t full[STAGES], empty[STAGES], lo_ready[2], lo_free[2], tmem_full[STAGES], tmem_empty[STAGES];
   Summary sum[4];
   uint32_t tmem_base;
   int range[4];  // doc_lo, doc_hi (+ token range as two u32 halves are kept in registers)
@@ -60,6 +65,7 @@ struct TcArgs {
   unsigned n_docs, n_q;
   const float* q;
   int cosine;
+  int debug_mode;  // 0 normal; 1 = TMA streaming only; 4 = no epilogue math (profiling aids)
   float* out;
 };
 
@@ -110,16 +116,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&st->full[s], 1);
-      mbar_init(&st->empty[s], 1);
-      mbar_init(&st->hi_done[s], 1);
-      mbar_init(&st->lo_ready[s], 128);
+      mbar_init(&st->empty[s], 129);  // hi MMAs done reading (1 commit) + 128 converter threads done reading
       mbar_init(&st->tmem_full[s], 1);
       mbar_init(&st->tmem_empty[s], 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&st->lo_ready[b], 128);
+      mbar_init(&st->lo_free[b], 1);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tm_tokens);
   }
-  if (warp == 9) tmem_alloc<256>(&st->tmem_base);
+  if (warp == 9) tmem_alloc<512>(&st->tmem_base);
   // B operand: rows 0..31 = Qhi, rows 32..63 = Qlo (cosine: rows pre-scaled by 1/||q||), K-major SW128 panels
   for (int idx = threadIdx.x; idx < NQ * DIM; idx += blockDim.x) {
     const int r = idx / DIM, k = idx % DIM;
@@ -157,61 +165,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TILE_M, UMMA_N);
       const uint32_t q_base = smem_u32(s_q);
-      auto issue = [&](int s, int t, bool accumulate_first) {
+      auto issue_hi = [&](int s) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
         const uint32_t a_base = smem_u32(s_tok + s * STAGE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < DIM / 8; ++kk) {
           const uint64_t ad = make_smem_desc_kmajor_sw128(a_base + (kk >> 2) * PANEL_BYTES + (kk & 3) * 32);
           const uint64_t bd = make_smem_desc_kmajor_sw128(q_base + (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32);
-          umma_tf32(tmem + t * UMMA_N, ad, bd, idesc, (accumulate_first || kk > 0) ? 1u : 0u);
+          umma_tf32(tmem + s * UMMA_N, ad, bd, idesc, kk > 0 ? 1u : 0u);
         }
       };
-      for (unsigned i = 0; i <= n_tiles; ++i) {
-        if (i < n_tiles) {  // hi(i): X as loaded
-          const int s = i % STAGES;
-          mbar_wait(&st->full[s], (i / STAGES) & 1);
-          mbar_wait(&st->tmem_empty[s], ((i / STAGES) & 1) ^ 1);
-          tc_fence_after_sync();
-          issue(s, s, false);
-          umma_commit(&st->hi_done[s]);
+      // A = Xlo in tensor memory (128 lanes x 128 columns); B = the Qhi rows only (N = 32): Qlo.Xlo is below
+      // 2^-22 of the product and is not worth a quarter of the tensor work (the kernel runs under the power cap).
+      const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQ);
+      auto issue_lo = [&](int t, int b) {
+#pragma unroll
+        for (int kk = 0; kk < DIM / 8; ++kk) {
+          const uint64_t bd = make_smem_desc_kmajor_sw128(q_base + (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32);
+          umma_tf32_ts(tmem + t * UMMA_N, tmem + LO_COL0 + b * DIM + kk * 8, bd, idesc_lo, 1u);
         }
-        if (i >= 1) {  // lo(i-1): the converters have replaced X by Xlo in place
-          const unsigned j = i - 1;
-          const int s = j % STAGES;
-          mbar_wait(&st->lo_ready[s], (j / STAGES) & 1);
-          tc_fence_after_sync();
-          issue(s, s, true);
-          umma_commit(&st->empty[s]);      // shared-memory stage free for the producer
-          umma_commit(&st->tmem_full[s]);  // accumulator complete for the epilogue
+      };
+      if (a.debug_mode == 1) {
+        for (unsigned i = 0; i < n_tiles; ++i) {
+          mbar_wait(&st->full[i % STAGES], (i / STAGES) & 1);
+          for (int r = 0; r < 129; ++r) mbar_arrive(&st->empty[i % STAGES]);
+        }
+      }
+      // hi(i) and lo(j) are issued in whatever order their inputs become ready (never block on one while the
+      // other could run); lo(j) always follows hi(j) because both accumulate into the same TMEM columns.
+      unsigned nh = 0, nl = 0;
+      while (a.debug_mode != 1 && nl < n_tiles) {
+        if (nl < nh) {  // lo(nl): the converters have written Xlo of tile nl to TMEM buffer nl % 2
+          const int b = nl & 1;
+          if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
+            tc_fence_after_sync();
+            issue_lo(nl % STAGES, b);
+            umma_commit(&st->tmem_full[nl % STAGES]);  // accumulator complete for the epilogue
+            umma_commit(&st->lo_free[b]);              // Xlo buffer may be overwritten
+            ++nl;
+          }
+        }
+        if (nh < n_tiles && nh < nl + STAGES) {  // hi(nh): X as loaded
+          const int s = nh % STAGES;
+          if (mbar_try_wait(&st->full[s], (nh / STAGES) & 1) &&
+              mbar_try_wait(&st->tmem_empty[s], ((nh / STAGES) & 1) ^ 1)) {
+            tc_fence_after_sync();
+            issue_hi(s);
+            umma_commit(&st->empty[s]);  // 1 of 129: the tensor core has finished reading the stage
+            ++nh;
+          }
         }
       }
     }
   } else if (warp >= 4) {
-    // =========================== converters: Xlo in place + token sum of squares ===========================
-    const int row = threadIdx.x - 128;  // one token row per thread
-    for (unsigned i = 0; i < n_tiles; ++i) {
-      const int s = i % STAGES;
+    // =========================== converters: Xlo -> TMEM, token sum of squares ===========================
+    // One token row per thread = one TMEM lane per thread (warps 4-7 own lane quadrants 0-3). A panel row (8 chunks
+    // of 16 B) is loaded at once, split, and written as 32 TMEM columns with one tcgen05.st.
+    const int row = threadIdx.x - 128;
+    for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
+      const int s = i % STAGES, b = i & 1;
       mbar_wait(&st->full[s], (i / STAGES) & 1);
-      mbar_wait(&st->hi_done[s], (i / STAGES) & 1);
-      uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
+      mbar_wait(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
+      const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * DIM;
       float ss = 0.0f;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
+        const uint8_t* pbase = base + p * PANEL_BYTES;
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(pbase + ((c ^ (row & 7)) << 4));
+        uint32_t lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float4* ptr = reinterpret_cast<float4*>(base + p * PANEL_BYTES + ((c ^ (row & 7)) << 4));
-          float4 v = *ptr;
-          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-          v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          *ptr = v;
+          if (a.cosine) {
+            ss = fmaf(v[c].x, v[c].x, ss); ss = fmaf(v[c].y, v[c].y, ss);
+            ss = fmaf(v[c].z, v[c].z, ss); ss = fmaf(v[c].w, v[c].w, ss);
+          }
+          lo[4 * c + 0] = __float_as_uint(v[c].x - __uint_as_float(__float_as_uint(v[c].x) & 0xFFFFE000u));
+          lo[4 * c + 1] = __float_as_uint(v[c].y - __uint_as_float(__float_as_uint(v[c].y) & 0xFFFFE000u));
+          lo[4 * c + 2] = __float_as_uint(v[c].z - __uint_as_float(__float_as_uint(v[c].z) & 0xFFFFE000u));
+          lo[4 * c + 3] = __float_as_uint(v[c].w - __uint_as_float(__float_as_uint(v[c].w) & 0xFFFFE000u));
         }
+        if (p == 3) mbar_arrive(&st->empty[s]);  // this thread has read its whole row: 1 of 129
+        tmem_st_32x32b_x32(tdst + 32 * p, lo);
       }
-      st->bb[s][row] = ss;
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's operand reads
-      mbar_arrive(&st->lo_ready[s]);
+      tmem_st_32x32b_x1(tmem + ((uint32_t)((warp & 3) * 32) << 16) + BB_COL0 + (i & 7), __float_as_uint(ss));
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&st->lo_ready[b]);
     }
   } else {
     // =========================== epilogue (warps 0-3 = TMEM lane quadrants 0-3) ===========================
@@ -225,7 +267,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
       if (lane == 0) a.out[doc] = v;
     };
-    for (unsigned i = 0; i < n_tiles; ++i) {
+    for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
       const int t = i % STAGES;
       const unsigned long long c0 = tok_lo + (unsigned long long)i * TILE_M + warp * 32;
       const unsigned long long g = c0 + lane;
@@ -236,10 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + t * UMMA_N;
       tmem_ld_32x32b_x32(taddr, rh);
       tmem_ld_32x32b_x32(taddr + 32, rl);
+      const uint32_t bb_bits = tmem_ld_32x32b_x1(tmem + ((uint32_t)(warp * 32) << 16) + BB_COL0 + (i & 7));
       tmem_ld_wait();
-      float bbv = st->bb[t][warp * 32 + lane];
+      float bbv = __uint_as_float(bb_bits);
       tc_fence_before_sync();
       if (lane == 0) mbar_arrive(&st->tmem_empty[t]);
+      if (a.debug_mode == 4) { if (rh[0] == 0x12345u && rl[0] == 0x54321u) a.out[0] = bbv; continue; }
       float sc[NQ];
       const float rt = a.cosine ? (bbv > EPS_SQ ? rsqrtf(bbv) : 0.0f) : 1.0f;
 #pragma unroll
@@ -253,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       if (c0 < tok_hi) {  // warp-uniform
         int doc = NO_DOC;
         if (a.uniform_tokens) {
-          if (valid) doc = (int)(g / a.uniform_tokens);
+          if (valid) doc = (int)((unsigned)g / (unsigned)a.uniform_tokens);  // tokens < 2^31
         } else {
           while (cur_doc + 1 < doc_hi && a.doc_offsets[cur_doc + 1] <= c0) ++cur_doc;  // uniform
           if (valid) {
@@ -376,7 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<256>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace
@@ -414,6 +458,8 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   a.q = dev_q;
   a.cosine = cosine;
   a.out = dev_scores;
+  static const int dbg = getenv("INNR_MAXSIM_DEBUG") ? atoi(getenv("INNR_MAXSIM_DEBUG")) : 0;
+  a.debug_mode = dbg;
   unsigned grid = (unsigned)num_sms;
   const unsigned long long tiles = (v.total_tokens + TILE_M - 1) / TILE_M;
   if (grid > tiles) grid = (unsigned)tiles;
