@@ -31,6 +31,11 @@ struct innr_cuda_corpus {
   size_t total_tokens = 0, uniform_tokens = 0;
   CUtensorMap tmap;
   bool tmap_valid = false;
+  // f32 PDX: TMA map over the corpus + lazily computed norm cache for the tensor-core filter path (knn_tc.cu)
+  CUtensorMap tm_pdx;
+  bool tm_pdx_valid = false;
+  float* dev_inv_norms = nullptr;
+  unsigned* dev_max_norm_bits = nullptr;
 };
 
 namespace {
@@ -69,7 +74,7 @@ struct DeviceCtx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   Workspace ws;
-  Buf d_query, d_keys, d_scores, d_aux, h_pin;
+  Buf d_query, d_keys, d_scores, d_aux, d_tcws, h_pin, h_counts;
   float last_ms = 0.0f;
 };
 
@@ -120,6 +125,7 @@ int ensure_ctx(int device, DeviceCtx** out) {
     CU(cudaMalloc(&c.ws.tickets, 1024 * sizeof(unsigned)));
     CU(cudaMemset(c.ws.tickets, 0, 1024 * sizeof(unsigned)));
     c.h_pin.pinned = true;
+    c.h_counts.pinned = true;
     c.ready = true;
   } else {
     CU(cudaSetDevice(device));
@@ -226,7 +232,7 @@ int innr_cuda_shutdown(void) {
     if (!c.ready) continue;
     cudaSetDevice(i);
     cudaStreamSynchronize(c.stream);
-    c.d_query.release(); c.d_keys.release(); c.d_scores.release(); c.d_aux.release(); c.h_pin.release();
+    c.d_query.release(); c.d_keys.release(); c.d_scores.release(); c.d_aux.release(); c.d_tcws.release(); c.h_pin.release(); c.h_counts.release();
     cudaFree(c.ws.partials);
     cudaFree(c.ws.group_partials);
     cudaFree(c.ws.tickets);
@@ -279,6 +285,7 @@ static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, in
       *out = nullptr;
       return cuda_fail(e, "cudaMalloc(corpus)");
     }
+    c->tm_pdx_valid = make_pdx_tmap(&c->tm_pdx, (const float*)c->dev, c->n, c->d, c->ld);
   }
   return INNR_OK;
 }
@@ -346,6 +353,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   c->ld = ld;
   c->index_base = index_base;
   c->bytes = ld * d * sizeof(float);
+  c->tm_pdx_valid = make_pdx_tmap(&c->tm_pdx, dev_pdx, n, d, ld);
   return INNR_OK;
 }
 
@@ -372,6 +380,8 @@ int innr_cuda_free(innr_cuda_corpus* c) {
   cudaSetDevice(c->device);
   if (c->owns && c->dev) cudaFree(c->dev);
   if (c->dev_offsets) cudaFree(c->dev_offsets);
+  if (c->dev_inv_norms) cudaFree(c->dev_inv_norms);
+  if (c->dev_max_norm_bits) cudaFree(c->dev_max_norm_bits);
   delete c;
   return INNR_OK;
 }
@@ -449,6 +459,34 @@ int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t
 }
 
 // ------------------------------------------------------------------------------------------ kNN
+// Queries on the device -> keys on the device. Large batches of dot / cosine queries go through the tensor-core
+// filter (knn_tc.cu: exact results, see there); everything else through the bit-exact scan with fused top-k.
+// INNR_KNN_TC=0 disables the tensor-core path.
+static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
+                        uint64_t* dev_keys, cudaStream_t s) {
+  static const bool tc_off = getenv("INNR_KNN_TC") && atoi(getenv("INNR_KNN_TC")) == 0;
+  PdxView v = pdx_view(c);
+  if (!tc_off && c->tm_pdx_valid && knn_tc_supported(v, mode, nq, k)) {
+    if (!c->dev_inv_norms) {  // exact norms once per corpus (batch_norms), then 1/norm and the max
+      CU(cudaMalloc(&c->dev_inv_norms, c->n * sizeof(float)));
+      CU(cudaMalloc(&c->dev_max_norm_bits, sizeof(unsigned)));
+      CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+      CU(launch_pdx_scores(v, PDX_NORMS, nullptr, nullptr, (float*)ctx->d_scores.p, ctx->ws, s, &g_launches));
+      CU(launch_knn_tc_inv_norms((const float*)ctx->d_scores.p, c->n, c->dev_inv_norms, c->dev_max_norm_bits, s, &g_launches));
+    }
+    CU(ctx->d_tcws.reserve(knn_tc_workspace_bytes(c->n, c->d, nq, k)));
+    CU(ctx->h_counts.reserve(nq * sizeof(unsigned)));
+    std::vector<unsigned> overflow;
+    CU(launch_pdx_knn_tc(v, c->tm_pdx, mode, dev_queries, nq, k, dev_keys, c->dev_inv_norms, c->dev_max_norm_bits,
+                         ctx->d_tcws.p, (unsigned*)ctx->h_counts.p, ctx->ws, s, &g_launches, &overflow));
+    for (unsigned q : overflow)
+      CU(launch_pdx_knn(v, mode, dev_queries + (size_t)q * c->d, 1, k, dev_keys + (size_t)q * k, ctx->ws, s, &g_launches));
+    return INNR_OK;
+  }
+  CU(launch_pdx_knn(v, mode, dev_queries, nq, k, dev_keys, ctx->ws, s, &g_launches));
+  return INNR_OK;
+}
+
 static int metric_to_mode(int metric, int* mode) {
   switch (metric) {
     case INNR_METRIC_DOT: *mode = PDX_DOT; return INNR_OK;
@@ -479,8 +517,9 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   if (c->d)
     CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   Timed tm(*ctx);
-  CU(launch_pdx_knn(pdx_view(c), mode, (const float*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p,
-                    ctx->ws, ctx->stream, &g_launches));
+  rc = knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, (const float*)ctx->d_query.p, n_queries, kk,
+                    (uint64_t*)ctx->d_keys.p, ctx->stream);
+  if (rc) return rc;
   tm.stop();
   rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
     for (size_t q = 0; q < n_queries; ++q)
@@ -508,8 +547,7 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  CU(launch_pdx_knn(pdx_view(c), mode, dev_queries, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
-  return INNR_OK;
+  return knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, dev_queries, n_queries, k < c->n ? k : c->n, dev_keys, s);
 }
 
 int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,

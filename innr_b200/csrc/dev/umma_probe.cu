@@ -11,6 +11,49 @@ using namespace innr::tc;
 
 constexpr int M = 128, N = 64, K = 128;
 
+// A given as a PDX matrix At[k][m] (MN-major for the MMA): 16 TMA boxes of [32 k][32 m], SWIZZLE_128B.
+__global__ void __launch_bounds__(128) probe_mn(const __grid_constant__ CUtensorMap tmAt,
+                                                const __grid_constant__ CUtensorMap tmB, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                                          // box (kb, mb) at (kb*4+mb)*4096
+  float* sB = reinterpret_cast<float*>(smem + 4 * 16384);
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&bar_full, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<64>(&tmem_base);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_full, (M + N) * K * 4);
+    for (int kb = 0; kb < 4; ++kb)
+      for (int mb = 0; mb < 4; ++mb) tma_load_2d(sA + (kb * 4 + mb) * 4096, &tmAt, &bar_full, mb * 32, kb * 32);
+    for (int p = 0; p < 4; ++p) tma_load_2d(sB + p * (N * 32), &tmB, &bar_full, p * 32, 0);
+    mbar_wait(&bar_full, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_tf32(M, N, true);
+    for (int kk = 0; kk < K / 8; ++kk) {
+      const uint32_t a_addr = smem_u32(sA) + (kk / 4) * 16384 + (kk % 4) * 1024;
+      const uint32_t b_addr = smem_u32(sB + (kk / 4) * (N * 32)) + (kk % 4) * 32;
+      umma_tf32(tmem, make_smem_desc_mnmajor_sw128_32b(a_addr, 4096, 512), make_smem_desc_kmajor_sw128(b_addr), idesc, kk > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after_sync();
+  uint32_t r[32];
+  for (int c = 0; c < N; c += 32) {
+    tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + c, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * N + c + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap tmA,
                                              const __grid_constant__ CUtensorMap tmB, float* out, int from_tmem) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -116,6 +159,28 @@ int main() {
       double err = fabs(ref - O[i * N + j]); if (err > maxerr) maxerr = err; if (err > 1e-3) ++bad;
     }
     printf("umma_probe (A from %s): max abs err %.3g, bad %d / %d  (O[0][0]=%f O[5][7]=%f)\n", from_tmem ? "TMEM" : "smem", maxerr, bad, M * N, O[0], O[5 * N + 7]);
+    rc |= bad ? 1 : 0;
+  }
+  {  // MN-major A
+    std::vector<float> At(K * M);
+    for (int i = 0; i < M; ++i) for (int k = 0; k < K; ++k) At[k * M + i] = A[i * K + k];
+    float* dAt; cudaMalloc(&dAt, At.size() * 4);
+    cudaMemcpy(dAt, At.data(), At.size() * 4, cudaMemcpyHostToDevice);
+    CUtensorMap tmAt;
+    if (!make_tmap_f32_rows(&tmAt, dAt, K, M, 32, 0, true)) { printf("tensor map At failed\n"); return 2; }
+    cudaFuncSetAttribute(probe_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaMemset(dO, 0, M * N * 4);
+    probe_mn<<<1, 128, smem>>>(tmAt, tmB, dO);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error (mn): %s\n", cudaGetErrorString(e)); return 3; }
+    std::vector<float> O(M * N);
+    cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0; int bad = 0;
+    for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) {
+      double ref = 0; for (int k = 0; k < K; ++k) ref += (double)A[i * K + k] * B[j * K + k];
+      double err = fabs(ref - O[i * N + j]); if (err > maxerr) maxerr = err; if (err > 1e-3) ++bad;
+    }
+    printf("umma_probe (A MN-major from PDX): max abs err %.3g, bad %d / %d  (O[0][0]=%f O[5][7]=%f)\n", maxerr, bad, M * N, O[0], O[5 * N + 7]);
     rc |= bad ? 1 : 0;
   }
   return rc;

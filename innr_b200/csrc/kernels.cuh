@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace innr {
 
 // modes of the f32 PDX scan (scan_f32.cu)
@@ -53,6 +55,19 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
 // keys from a plain f32 array (TopK analogue): ascending, id = i
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, uint64_t* launches);
+
+// tensor-core filter path for large query batches (knn_tc.cu): dot / cosine, k <= 32, exact results
+bool make_pdx_tmap(CUtensorMap* m, const float* dev_pdx, size_t n, size_t d, size_t ld);
+bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k);
+size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k);
+cudaError_t launch_knn_tc_inv_norms(const float* dev_norms, size_t n, float* dev_inv, unsigned* dev_max_bits, cudaStream_t s,
+                                    uint64_t* launches);
+// host_counts: pinned buffer of nq unsigned; overflow_queries receives the queries whose candidate list overflowed
+// (the caller re-runs them on the exact scan). Synchronises the stream once at the end.
+cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mode, const float* dev_queries, size_t nq,
+                              size_t k, uint64_t* dev_keys, const float* dev_inv_norms, const unsigned* dev_max_norm_bits,
+                              void* workspace, unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                              std::vector<unsigned>* overflow_queries);
 
 // layout / generator kernels (layout.cu)
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,

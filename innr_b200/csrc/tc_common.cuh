@@ -144,10 +144,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t smem_ad
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// MN-major operand (contiguous along M/N, e.g. a PDX corpus tile [k][vector]) stored as TMA SWIZZLE_128B boxes of
+// [k rows][32 floats]: canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units -> LBO = byte stride between
+// 32-element MN atoms (the box stride), SBO = byte stride between 8-row K atoms (1024 B inside a box).
+// For 32-bit (tf32) MN-major operands the only legal shared-memory layout is SWIZZLE_128B_BASE32B (layout type 1):
+// 128-byte rows, 32-byte chunks XOR-ed with (row % 4) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+// the K atom is 4 rows (512 B).
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                     uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 // kind::tf32, F32 accumulate, A and B K-major: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2,
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major = false) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major ? (1u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tc
@@ -169,15 +186,18 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-inline bool make_tmap_f32_rows(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// pitch_floats: row pitch of the matrix in floats (>= cols; 0 = dense)
+inline bool make_tmap_f32_rows(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                               uint64_t pitch_floats = 0, bool atom32 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint64_t gstride[1] = {(pitch_floats ? pitch_floats : cols) * sizeof(float)};
   cuuint32_t box[2] = {32, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

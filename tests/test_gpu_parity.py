@@ -434,3 +434,23 @@ def test_full_size_c4_c5_properties(ib, oracle):
         row = oracle.quantize_u8(oracle.ghash_f32(synth.SALT_CORPUS, i * d, d), op)
         assert np.float32(s).tobytes() == np.float32(oracle.asymmetric_dot_u8(q, row, op)).tobytes()
     assert all((got[j][1], -got[j][0]) > (got[j + 1][1], -got[j + 1][0]) for j in range(k - 1))
+
+
+# ------------------------------------------------------------------------------------------------ tensor-core filter path
+@pytest.mark.parametrize("n,d,nq", [(20_000, 768, 64), (50_000, 100, 40), (8_192, 32, 130), (33_000, 8, 33)])
+def test_knn_tc_filter_path_is_exact(ib, oracle, n, d, nq):
+    """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
+    result bit-identical to the reference (indices AND scores), including a zero query, a zero vector, duplicates."""
+    rows = rand_rows(n, d, n + d)
+    rows[17] = 0.0                      # zero-norm vector -> cosine 0.0
+    rows[100] = rows[200] = rows[300]   # exact duplicates -> ties -> lower index first
+    qs = rand_rows(nq, d, 99)
+    qs[3] = 0.0                         # zero-norm query -> every cosine 0.0 -> first k indices (overflow fallback)
+    qs[5] = rows[300] * 2.0             # query parallel to the duplicates
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for metric in ("cosine", "dot"):
+        for k in (1, 10, 32):
+            idx, sc = ib.batch_knn_many(metric, qs, gb, k)
+            widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
+            assert np.array_equal(idx, widx), (metric, k, np.argwhere(idx != widx)[:5])
+            assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
