@@ -59,6 +59,10 @@ const char* innr_cuda_backend_name(void);
 /* Device-side analogue of backend::dense_backend(len) (src/backend.rs:46): for a device-resident corpus
  * every length answers 1 (= Backend::Cuda); kept as a function so the shim mirrors the predicate shape. */
 int innr_cuda_dense_backend(size_t len, int* out_is_cuda);
+/* Tuning knobs (process-wide). Names: "knn_tc" (1/0: tensor-core filter path for large dot/cosine query batches),
+ * "knn_tc_min_n" (corpus size from which it is used, default 100000), "knn_tc_min_queries" (default 32),
+ * "maxsim_tc" (1/0: tcgen05 MaxSim when dim == 128 and <= 32 query tokens). Results never depend on them. */
+int innr_cuda_set_option(const char* name, double value);
 /* number of kernels the library has launched so far (bench.py's gpu_launches counter) */
 int innr_cuda_launch_count(uint64_t* out_count);
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "innr_cuda_init": [ci],
     "innr_cuda_shutdown": [],
     "innr_cuda_dense_backend": [sz, C.POINTER(ci)],
+    "innr_cuda_set_option": [C.c_char_p, C.c_double],
     "innr_cuda_launch_count": [u64p],
     "innr_cuda_last_kernel_ms": [f32p],
     "innr_cuda_upload_f32_pdx": [f32p, sz, sz, u64, handle_p],
@@ -136,6 +137,11 @@ def last_kernel_ms() -> float:
     v = C.c_float(0)
     call("innr_cuda_last_kernel_ms", C.byref(v))
     return float(v.value)
+
+
+def set_option(name: str, value: float) -> None:
+    """Tuning knobs of the library (see include/innr_cuda.h); results never depend on them."""
+    call("innr_cuda_set_option", name.encode(), float(value))
 
 
 def init(device: int = 0) -> None:

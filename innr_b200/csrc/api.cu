@@ -78,6 +78,13 @@ struct DeviceCtx {
   float last_ms = 0.0f;
 };
 
+struct Options {
+  bool knn_tc = true;
+  size_t knn_tc_min_n = 100000;
+  size_t knn_tc_min_queries = 32;
+  bool maxsim_tc = true;
+} g_opt;
+
 std::mutex g_mu;
 DeviceCtx g_ctx[MAX_DEVICES];
 uint64_t g_launches = 0;
@@ -119,11 +126,14 @@ int ensure_ctx(int device, DeviceCtx** out) {
     CU(cudaEventCreate(&c.ev0));
     CU(cudaEventCreate(&c.ev1));
     // per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
-    c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32;
+    // (the same buffers hold several query groups of one launch when the grid is small: scan_f32.cu, grid.y)
+    c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32 * 4;
     CU(cudaMalloc(&c.ws.partials, c.ws.partials_cap * sizeof(uint64_t)));
-    CU(cudaMalloc(&c.ws.group_partials, (size_t)(c.ws.num_sms * 8 / 32 + 2) * 8 * 128 * sizeof(uint64_t)));
-    CU(cudaMalloc(&c.ws.tickets, 1024 * sizeof(unsigned)));
-    CU(cudaMemset(c.ws.tickets, 0, 1024 * sizeof(unsigned)));
+    c.ws.group_cap = (size_t)(c.ws.num_sms * 8 / 32 + 2) * 8 * 128 * 4;
+    CU(cudaMalloc(&c.ws.group_partials, c.ws.group_cap * sizeof(uint64_t)));
+    c.ws.tickets_cap = 16384;
+    CU(cudaMalloc(&c.ws.tickets, c.ws.tickets_cap * sizeof(unsigned)));
+    CU(cudaMemset(c.ws.tickets, 0, c.ws.tickets_cap * sizeof(unsigned)));
     c.h_pin.pinned = true;
     c.h_counts.pinned = true;
     c.ready = true;
@@ -250,6 +260,17 @@ int innr_cuda_dense_backend(size_t len, int* out_is_cuda) {
   (void)len;
   if (!out_is_cuda) return fail(INNR_EINVAL, "null out");
   *out_is_cuda = 1;
+  return INNR_OK;
+}
+int innr_cuda_set_option(const char* name, double value) {
+  if (!name) return fail(INNR_EINVAL, "null option name");
+  std::lock_guard<std::mutex> lk(g_mu);
+  const std::string n(name);
+  if (n == "knn_tc") g_opt.knn_tc = value != 0;
+  else if (n == "knn_tc_min_n") g_opt.knn_tc_min_n = (size_t)value;
+  else if (n == "knn_tc_min_queries") g_opt.knn_tc_min_queries = (size_t)value;
+  else if (n == "maxsim_tc") g_opt.maxsim_tc = value != 0;
+  else return fail(INNR_EINVAL, "unknown option: " + n);
   return INNR_OK;
 }
 int innr_cuda_launch_count(uint64_t* out_count) {
@@ -461,12 +482,12 @@ int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t
 // ------------------------------------------------------------------------------------------ kNN
 // Queries on the device -> keys on the device. Large batches of dot / cosine queries go through the tensor-core
 // filter (knn_tc.cu: exact results, see there); everything else through the bit-exact scan with fused top-k.
-// INNR_KNN_TC=0 disables the tensor-core path.
+// innr_cuda_set_option("knn_tc", 0) disables the tensor-core path.
 static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
                         uint64_t* dev_keys, cudaStream_t s) {
-  static const bool tc_off = getenv("INNR_KNN_TC") && atoi(getenv("INNR_KNN_TC")) == 0;
   PdxView v = pdx_view(c);
-  if (!tc_off && c->tm_pdx_valid && knn_tc_supported(v, mode, nq, k)) {
+  if (g_opt.knn_tc && c->tm_pdx_valid && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries &&
+      knn_tc_supported(v, mode, nq, k)) {
     if (!c->dev_inv_norms) {  // exact norms once per corpus (batch_norms), then 1/norm and the max
       CU(cudaMalloc(&c->dev_inv_norms, c->n * sizeof(float)));
       CU(cudaMalloc(&c->dev_max_norm_bits, sizeof(unsigned)));
@@ -1012,10 +1033,9 @@ static int maxsim_common(const innr_cuda_corpus* c, DeviceCtx* ctx, const float*
     if (c->n) CU(cudaMemsetAsync(dev_scores, 0, c->n * sizeof(float), s));
     return INNR_OK;
   }
-  // tcgen05/TMEM path when the shape fits (dim 128, <= 32 query tokens); INNR_MAXSIM_V1=1 forces the CUDA-core kernel
-  static const bool force_v1 = getenv("INNR_MAXSIM_V1") != nullptr;
+  // tcgen05/TMEM path when the shape fits (dim 128, <= 32 query tokens); option "maxsim_tc" = 0 forces the CUDA-core kernel
   TokView tv = tok_view(c);
-  cudaError_t e = (!force_v1 && maxsim_tc_supported(tv, n_q))
+  cudaError_t e = (g_opt.maxsim_tc && maxsim_tc_supported(tv, n_q))
                       ? launch_maxsim_tc(tv, dev_q, n_q, cosine, dev_scores, ctx->ws.num_sms, s, &g_launches)
                       : launch_maxsim(tv, dev_q, n_q, cosine, dev_scores, s, &g_launches);
   if (e == cudaErrorInvalidValue) return fail(INNR_EUNSUPPORTED, "maxsim: dim / n_q exceed the shared-memory tile");

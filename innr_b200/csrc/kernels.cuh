@@ -22,7 +22,9 @@ struct Workspace {
   uint64_t* partials = nullptr;        // per-CTA top-k lists
   size_t partials_cap = 0;             // in u64
   uint64_t* group_partials = nullptr;  // per-group (32 CTAs) merged lists
+  size_t group_cap = 0;                // in u64
   unsigned* tickets = nullptr;         // [0] top level, [1+g] group g; zeroed once, self-resetting
+  size_t tickets_cap = 0;
   int num_sms = 0;
 };
 

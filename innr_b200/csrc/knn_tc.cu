@@ -21,6 +21,7 @@
 // (Xlo -> TMEM as the A operand of the third product), 4 epilogue warps (TMEM -> registers, threshold, append).
 // Work unit = 128 vectors x 128 queries, K loop over 32-dimension blocks through a 4-stage shared-memory ring
 // (X 16 KB + Qhi 16 KB + Qlo 16 KB per stage); 12 MMAs (M128 N128 K8) per block.
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -391,7 +392,7 @@ static KnnTcPlan make_plan(size_t n, size_t d, size_t nq, size_t k) {
 size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) { return make_plan(n, d, nq, k).total; }
 
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k) {
-  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED) && nq >= 32 && k >= 1 && k <= 32 && v.d >= 8 && v.n >= 4096 &&
+  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED) && nq >= 1 && k >= 1 && k <= 32 && v.d >= 1 && v.n >= 4096 &&
          v.n < 0x7FFFFF00ull && v.ld % 4 == 0;
 }
 
@@ -410,12 +411,19 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
   unsigned* cand = (unsigned*)(w + p.off_cand);
   uint64_t* skeys = (uint64_t*)(w + p.off_skeys);
   cudaError_t e;
+  static const bool trace = getenv("INNR_KNN_TC_TRACE") != nullptr;
+  cudaEvent_t ev[6];
+  if (trace)
+    for (auto& x : ev) cudaEventCreate(&x);
+  auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], s); };
+  mark(0);
 
   // 1. sample pass on a prefix of the corpus (exact, bit-identical scores)
   PdxView prefix = v;
   prefix.n = p.n_s;
   e = launch_pdx_knn(prefix, mode, dev_queries, nq, k, skeys, ws, s, launches);
   if (e != cudaSuccess) return e;
+  mark(1);
   // 2. operands and thresholds
   knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine,
                                                       qhi, qlo, qnorm);
@@ -427,6 +435,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
   CUtensorMap tm_qhi, tm_qlo;
   if (!make_tmap_f32_rows(&tm_qhi, qhi, p.nq_pad, p.d_pad, QT) || !make_tmap_f32_rows(&tm_qlo, qlo, p.nq_pad, p.d_pad, QT))
     return cudaErrorInvalidValue;
+  mark(2);
   // 3. tensor-core filter
   static bool attr_set = false;
   const size_t smem = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
@@ -454,6 +463,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
   ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  mark(3);
   // 4. exact rescoring + selection
   const size_t rs_smem = ((v.d + 3) & ~(size_t)3) * 4 + (size_t)(RS_THREADS / 32) * k * 8;
   knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
@@ -461,6 +471,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
   ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  mark(4);
   // 5. overflowed candidate lists -> the caller re-runs those queries on the exact scan
   if (host_counts && overflow_queries) {
     e = cudaMemcpyAsync(host_counts, cnt, nq * 4, cudaMemcpyDeviceToHost, s);
@@ -470,6 +481,15 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
     overflow_queries->clear();
     for (size_t q = 0; q < nq; ++q)
       if (host_counts[q] > a.cap) overflow_queries->push_back((unsigned)q);
+    if (trace) {
+      float t[4];
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+      unsigned long long tot = 0, mx = 0;
+      for (size_t q = 0; q < nq; ++q) { tot += host_counts[q]; if (host_counts[q] > mx) mx = host_counts[q]; }
+      fprintf(stderr, "[knn_tc] sample(n_s=%u) %.2f ms | prep %.2f | filter %.2f | rescore %.2f | candidates total %llu max %llu overflow %zu\n",
+              p.n_s, t[0], t[1], t[2], t[3], tot, mx, overflow_queries->size());
+      for (auto& x : ev) cudaEventDestroy(x);
+    }
   }
   return cudaSuccess;
 }

@@ -17,6 +17,8 @@
 //
 // Selection never materialises N scores: scores become 64-bit composite keys (common.cuh) and flow into a
 // per-warp register list, a CTA merge and a last-CTA merge -- one launch per query group.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -35,8 +37,8 @@ struct PdxArgs {
   unsigned n, d, ld4;     // ld4 = ld (u32 copy for bounds checks; ld < 2^32)
   unsigned n_tiles;
   unsigned index_base;
-  const float* queries;   // nq_valid x d (device)
-  int nq_valid;
+  const float* queries;   // nq_total x d (device); blockIdx.y selects the group of QB queries
+  int nq_valid;           // queries in this launch (all y groups together)
   int k;
   uint64_t* partials;
   uint64_t* out_keys;
@@ -57,19 +59,32 @@ __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
 }
 
 template <int MODE, int QB, int R, bool KNN>
-__global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a) {
+__global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_in) {
   constexpr bool NEED_SS = (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS);
   constexpr bool NEED_DOT = (MODE != PDX_NORMS);
   constexpr int U = (QB == 1) ? 8 : 4;  // dimension rows in flight per thread
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [d][QB] interleaved queries (padded so the d-loop can read whole float4 groups), then qnorm[QB], then keys
-  const unsigned d_pad = (a.d + U - 1) / U * U;
+  const unsigned d_pad = (a_in.d + U - 1) / U * U;
   float* sq = reinterpret_cast<float*>(smem_raw);
   float* s_qn = sq + (size_t)d_pad * QB;
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(s_qn + ((QB + 3) & ~3));
 
   const int lane = threadIdx.x & 31;
+
+  // query group of this CTA (grid.y): shifts the query, output and merge-workspace pointers
+  PdxArgs a = a_in;
+  {
+    const unsigned y = blockIdx.y;
+    const unsigned n_groups = (gridDim.x + FINISH_GROUP - 1) / FINISH_GROUP;
+    a.queries += (size_t)y * QB * a.d;
+    a.nq_valid = min(QB, a_in.nq_valid - (int)(y * QB));
+    a.out_keys += (size_t)y * QB * a.k;
+    a.partials += (size_t)y * gridDim.x * QB * a.k;
+    a.group_partials += (size_t)y * n_groups * QB * a.k;
+    a.tickets += (size_t)y * (1 + n_groups);
+  }
 
   if (NEED_DOT) {
     for (unsigned idx = threadIdx.x; idx < d_pad * QB; idx += blockDim.x) {
@@ -203,27 +218,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a)
 }
 
 template <int MODE, int QB, int R, bool KNN>
-cudaError_t launch_one(const PdxArgs& a, size_t smem, int max_ctas_per_sm_hint, int num_sms, cudaStream_t s) {
+cudaError_t launch_one(const PdxArgs& a, size_t smem, int ny, int num_sms, cudaStream_t s) {
   auto kern = pdx_scan_kernel<MODE, QB, R, KNN>;
-  static int occ = 0;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  if (occ == 0 || smem > 16 * 1024) {
-    int o = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, SCAN_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (o < 1) return cudaErrorInvalidConfiguration;
-    occ = o;
-  }
-  (void)max_ctas_per_sm_hint;
+  int occ = 0;
+  cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SCAN_THREADS, smem);
+  if (eo != cudaSuccess) return eo;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
   unsigned grid = balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms);
   if (!KNN) grid = a.n_tiles ? a.n_tiles : 1;  // no cross-tile state: one CTA per tile, hardware scheduler balances
-  kern<<<grid, SCAN_THREADS, smem, s>>>(a);
+  kern<<<dim3(grid, ny > 0 ? ny : 1), SCAN_THREADS, smem, s>>>(a);
   return cudaGetLastError();
+}
+
+// grid.x the KNN launch will use (needed to size the merge workspace per query group)
+template <int MODE, int QB, int R>
+unsigned knn_grid_x(unsigned n_tiles, size_t smem, int num_sms) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pdx_scan_kernel<MODE, QB, R, true>, SCAN_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+  return balanced_grid(n_tiles, (unsigned)occ * (unsigned)num_sms);
 }
 
 size_t scan_smem_bytes(size_t d, int qb, int k, bool knn) {
@@ -243,36 +261,51 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
-  a.ld4 = (unsigned)v.ld;
+  // columns actually scanned: n rounded up to a whole float4 (the row pitch is a multiple of 4, so the last float4 is
+  // in bounds); a prefix view (n << ld) scans only its own columns
+  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
   a.n = (unsigned)v.n;
   a.d = (unsigned)v.d;
-  a.n_tiles = (unsigned)((v.ld + TILE - 1) / TILE);
+  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
   a.index_base = v.index_base;
   a.k = (int)k;
   a.partials = ws.partials;
   a.group_partials = ws.group_partials;
   a.tickets = ws.tickets;
   const bool big_k = k > 32;
-  // query blocking: 8 queries share one pass over the corpus when their lists fit in registers
-  const int QBMAX = big_k ? 1 : 8;
+  // query blocking: 8 queries share one pass over the corpus when their lists fit in registers; several groups of 8
+  // run as grid.y of ONE launch as long as their merge workspaces fit (small corpora / many queries: C1, sample pass)
   size_t done = 0;
   while (done < nq) {
-    int qb = (nq - done >= 2 && QBMAX == 8) ? 8 : 1;
+    int qb = (nq - done >= 2 && !big_k) ? 8 : 1;
     size_t smem = scan_smem_bytes(v.d, qb, (int)k, true);
     if (smem > 200 * 1024 && qb == 8) {
       qb = 1;
       smem = scan_smem_bytes(v.d, 1, (int)k, true);
     }
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    int nqv = (int)((nq - done) < (size_t)qb ? (nq - done) : (size_t)qb);
+    int ny = 1;
+    if (qb == 8) {
+      unsigned gx = 1;
+      if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 8, 1>(a.n_tiles, smem, ws.num_sms);
+      else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 8, 1>(a.n_tiles, smem, ws.num_sms);
+      else gx = knn_grid_x<PDX_COSINE_FUSED, 8, 1>(a.n_tiles, smem, ws.num_sms);
+      const size_t n_groups = (gx + FINISH_GROUP - 1) / FINISH_GROUP;
+      size_t fit = ws.partials_cap / ((size_t)gx * 8 * k);
+      fit = std::min(fit, ws.group_cap / (n_groups * 8 * k));
+      fit = std::min(fit, ws.tickets_cap / (1 + n_groups));
+      const size_t groups_left = (nq - done + 7) / 8;
+      ny = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(fit, groups_left), 65535));
+    }
+    const size_t nq_launch = std::min<size_t>(nq - done, (size_t)ny * qb);
     a.queries = dev_queries + done * v.d;
-    a.nq_valid = nqv;
+    a.nq_valid = (int)nq_launch;
     a.out_keys = dev_keys + done * k;
     cudaError_t e;
 #define INNR_DISPATCH(MODE)                                                                          \
-  if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, 0, ws.num_sms, s);                          \
-  else if (!big_k) e = launch_one<MODE, 1, 1, true>(a, smem, 0, ws.num_sms, s);                      \
-  else e = launch_one<MODE, 1, 4, true>(a, smem, 0, ws.num_sms, s);
+  if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, ny, ws.num_sms, s);                         \
+  else if (!big_k) e = launch_one<MODE, 1, 1, true>(a, smem, 1, ws.num_sms, s);                      \
+  else e = launch_one<MODE, 1, 4, true>(a, smem, 1, ws.num_sms, s);
     if (mode == PDX_DOT) { INNR_DISPATCH(PDX_DOT) }
     else if (mode == PDX_L2) { INNR_DISPATCH(PDX_L2) }
     else if (mode == PDX_COSINE_FUSED) { INNR_DISPATCH(PDX_COSINE_FUSED) }
@@ -280,7 +313,7 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
 #undef INNR_DISPATCH
     if (e != cudaSuccess) return e;
     ++*launches;
-    done += nqv;
+    done += nq_launch;
   }
   return cudaSuccess;
 }
@@ -290,10 +323,12 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
-  a.ld4 = (unsigned)v.ld;
+  // columns actually scanned: n rounded up to a whole float4 (the row pitch is a multiple of 4, so the last float4 is
+  // in bounds); a prefix view (n << ld) scans only its own columns
+  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
   a.n = (unsigned)v.n;
   a.d = (unsigned)v.d;
-  a.n_tiles = (unsigned)((v.ld + TILE - 1) / TILE);
+  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
   a.index_base = v.index_base;
   a.queries = dev_query;
   a.nq_valid = 1;
@@ -303,10 +338,10 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e;
   switch (mode) {
-    case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
-    case PDX_L2: e = launch_one<PDX_L2, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
-    case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
-    case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false>(a, smem, 0, ws.num_sms, s); break;
+    case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
+    case PDX_L2: e = launch_one<PDX_L2, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
+    case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
+    case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     default: return cudaErrorInvalidValue;
   }
   if (e == cudaSuccess) ++*launches;

@@ -441,6 +441,8 @@ def test_full_size_c4_c5_properties(ib, oracle):
 def test_knn_tc_filter_path_is_exact(ib, oracle, n, d, nq):
     """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
     result bit-identical to the reference (indices AND scores), including a zero query, a zero vector, duplicates."""
+    ib.set_option("knn_tc_min_n", 4096)       # exercise the tensor-core path at test sizes
+    ib.set_option("knn_tc_min_queries", 32)
     rows = rand_rows(n, d, n + d)
     rows[17] = 0.0                      # zero-norm vector -> cosine 0.0
     rows[100] = rows[200] = rows[300]   # exact duplicates -> ties -> lower index first
@@ -454,3 +456,19 @@ def test_knn_tc_filter_path_is_exact(ib, oracle, n, d, nq):
             widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
             assert np.array_equal(idx, widx), (metric, k, np.argwhere(idx != widx)[:5])
             assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
+    ib.set_option("knn_tc_min_n", 100000)
+
+
+def test_knn_tc_on_the_reference_lattice(ib, oracle):
+    """The G-ref lattice has near-ties below f32 resolution: the adversarial case for a TF32 filter."""
+    ib.set_option("knn_tc_min_n", 4096)
+    n, d, nq, k = 30_000, 128, 64, 10
+    dev = ib.DeviceBatch.generate("gref", 0, 0, n, d)
+    rows = np.stack([oracle.generate_embedding(d, i) for i in range(n)])
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    qs = np.stack([oracle.generate_embedding(d, 50_000 + j) for j in range(nq)])
+    for metric in ("dot", "cosine"):
+        idx, sc = ib.batch_knn_many(metric, qs, dev, k)
+        widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
+        assert np.array_equal(idx, widx) and np.array_equal(bits(sc), bits(wsc)), metric
+    ib.set_option("knn_tc_min_n", 100000)
