@@ -60,50 +60,114 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense 16-bit tensor peak (TFLOP/s) for a kernel timed inside a long step: the sustained cuBLAS bf16 figure of
+    MEASURED_PEAKS.json (f16 and bf16 issue at the same rate), else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clocks-event (throttle) reasons sampled DURING the timed region. NVML in a thread every ~2 ms
+    (a 4 ms step needs a faster sampler than `nvidia-smi -lms 100`); nvidia-smi (the B200_PROFILING.md clocks line)
+    is the fallback when NVML cannot be loaded. Only samples taken between mark_begin() and mark_end() are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.samples, self.stop_flag, self.t = gpu_index, [], False, None
+        self.t_begin = self.t_end = None
+        self.mode, self.proc, self.max_mhz = None, None, None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+                                          "-lms", "20", "-i", str(self._nvml_index())], stdout=subprocess.PIPE, text=True)
+            self.mode = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, tuple(n for n, bit in names if mask & bit)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                mhz, self.max_mhz = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            rs = tuple(n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                       if v.lower().startswith("active"))
+            self.samples.append((time.perf_counter(), mhz, rs))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampler unavailable"]}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.t:
+            self.t.join(timeout=2)
+        lo, hi = self.t_begin or 0.0, self.t_end or float("inf")
+        inside = [s for s in self.samples if lo <= s[0] <= hi]
+        sm = [s[1] for s in inside]
+        reasons = sorted({r for s in inside for r in s[2]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons, "sampler": self.mode,
+                "window_ms": (hi - lo) * 1e3 if self.t_end else None}
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -380,7 +444,7 @@ def dtype_of(workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="knn_cosine_1q", choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=1024, help="queries per step for knn_cosine_multi")
@@ -439,6 +503,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     ev[0].record()
     for i in range(args.steps):
         kev[i][0].record()
@@ -446,6 +511,7 @@ def main():
         kev[i][1].record()
     ev[1].record()
     barrier()
+    sampler.mark_end()
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
     launches = ib.launch_count() - l0
     step_ms = [a.elapsed_time(b) for a, b in kev]
@@ -496,6 +562,21 @@ def main():
     peak, peak_src = load_peaks()
     achieved = w.kernel_bytes / (kern_ms / 1e3) / 1e9
 
+    roofline = {"bound": "hbm", "kernel": w.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": load_traffic(args.workload, args.scale, world),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms}
+    tc = ib.knn_tc_last_stats() if args.workload == "knn_cosine_multi" else None
+    if tc and tc["passes"] > 0 and tc["filter_ms"] > 0:
+        # large query batches: the dominant kernel is the tcgen05 filter (csrc/knn_tc.cu); algorithmic flops per launch =
+        # 2 * rows * d * queries of THIS rank, time = CUDA events around that launch inside the library
+        tpeak, tsrc = load_tensor_peak()
+        flops = 2.0 * w.n_local * w.d * w.nq
+        tf = flops / (tc["filter_ms"] / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "knn_tc_filter_kernel (kind::f16, exact rescoring after it)",
+                    "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None,
+                    "peak_source": tsrc, "algorithmic_flops_per_launch": flops, "kernel_ms": tc["filter_ms"],
+                    "call_ms": tc["total_ms"], "filter_passes": tc["passes"], "rescored_pairs": tc["candidates"],
+                    "exact_scan_queries": tc["exact_scan_queries"]}
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -507,10 +588,7 @@ def main():
                        "generator": "G-ref lattice" if args.workload == "batch_demo" else "G-hash (splitmix64)"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": w.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": load_traffic(args.workload, args.scale, world),
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms},
+            "roofline": roofline,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

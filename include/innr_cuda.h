@@ -63,6 +63,12 @@ int innr_cuda_dense_backend(size_t len, int* out_is_cuda);
  * "knn_tc_min_n" (corpus size from which it is used, default 100000), "knn_tc_min_queries" (default 32),
  * "maxsim_tc" (1/0: tcgen05 MaxSim when dim == 128 and <= 32 query tokens). Results never depend on them. */
 int innr_cuda_set_option(const char* name, double value);
+/* Statistics of the most recent batch_knn call that went through the tensor-core filter (csrc/knn_tc.cu): time of the
+ * whole-corpus filter pass and of the whole device-side call (CUDA events), flops issued by that pass, number of
+ * (query, vector) pairs re-scored exactly, queries answered by the exact scan instead, filter passes. Any pointer may be
+ * NULL. bench.py's tensor roofline reads this. */
+int innr_cuda_knn_tc_last_stats(float* out_filter_ms, float* out_total_ms, double* out_filter_flops,
+                                uint64_t* out_candidates, uint32_t* out_exact_scan_queries, int* out_passes);
 /* number of kernels the library has launched so far (bench.py's gpu_launches counter) */
 int innr_cuda_launch_count(uint64_t* out_count);
 

@@ -5,8 +5,8 @@ host-side mirror of the reference's API for that path (same names, arguments and
 innr::batch / innr::binary / innr::scalar / innr::maxsim / innr::backend) so the parity tests read like the
 reference's own tests. No CPU fallback: without the shared library or a CUDA device, calls raise.
 """
-from ._lib import (InnrCudaError, backend_name, build, init, last_kernel_ms, launch_count, lib,  # noqa: F401
-                   set_option)
+from ._lib import (InnrCudaError, backend_name, build, init, knn_tc_last_stats, last_kernel_ms,  # noqa: F401
+                   launch_count, lib, set_option)
 from .backend import Backend, dense_backend  # noqa: F401
 from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, batch_dot, batch_knn,  # noqa: F401
                     batch_knn_cosine, batch_knn_dot, batch_knn_many, batch_l2_squared, batch_norms)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "innr_cuda_shutdown": [],
     "innr_cuda_dense_backend": [sz, C.POINTER(ci)],
     "innr_cuda_set_option": [C.c_char_p, C.c_double],
+    "innr_cuda_knn_tc_last_stats": [f32p, f32p, C.POINTER(C.c_double), u64p, C.POINTER(C.c_uint32), C.POINTER(ci)],
     "innr_cuda_launch_count": [u64p],
     "innr_cuda_last_kernel_ms": [f32p],
     "innr_cuda_upload_f32_pdx": [f32p, sz, sz, u64, handle_p],
@@ -137,6 +138,14 @@ def last_kernel_ms() -> float:
     v = C.c_float(0)
     call("innr_cuda_last_kernel_ms", C.byref(v))
     return float(v.value)
+
+
+def knn_tc_last_stats() -> dict:
+    """Statistics of the most recent batch_knn call that used the tensor-core filter (include/innr_cuda.h)."""
+    f, t, fl, cand, ex, p = C.c_float(), C.c_float(), C.c_double(), C.c_uint64(), C.c_uint32(), C.c_int()
+    call("innr_cuda_knn_tc_last_stats", C.byref(f), C.byref(t), C.byref(fl), C.byref(cand), C.byref(ex), C.byref(p))
+    return {"filter_ms": f.value, "total_ms": t.value, "filter_flops": fl.value, "candidates": cand.value,
+            "exact_scan_queries": ex.value, "passes": p.value}
 
 
 def set_option(name: str, value: float) -> None:

@@ -31,11 +31,11 @@ struct innr_cuda_corpus {
   size_t total_tokens = 0, uniform_tokens = 0;
   CUtensorMap tmap;
   bool tmap_valid = false;
-  // f32 PDX: TMA map over the corpus + lazily computed norm cache for the tensor-core filter path (knn_tc.cu)
-  CUtensorMap tm_pdx;
-  bool tm_pdx_valid = false;
-  float* dev_inv_norms = nullptr;
-  unsigned* dev_max_norm_bits = nullptr;
+  // f32 PDX: lazily built operands of the tensor-core filter path (knn_tc.cu): exact norms, f16 unit vectors + TMA map
+  int tc_state = 0;  // 0 not built, 1 ready, -1 unusable (non-finite norms / no memory): exact scan only
+  float* dev_norms = nullptr;
+  void* dev_xh = nullptr;
+  CUtensorMap tm_xh;
 };
 
 namespace {
@@ -88,6 +88,7 @@ struct Options {
 std::mutex g_mu;
 DeviceCtx g_ctx[MAX_DEVICES];
 uint64_t g_launches = 0;
+KnnTcStats g_tc_stats;
 thread_local int t_device = -1;
 thread_local std::string t_err;
 
@@ -273,6 +274,17 @@ int innr_cuda_set_option(const char* name, double value) {
   else return fail(INNR_EINVAL, "unknown option: " + n);
   return INNR_OK;
 }
+int innr_cuda_knn_tc_last_stats(float* out_filter_ms, float* out_total_ms, double* out_filter_flops,
+                                uint64_t* out_candidates, uint32_t* out_exact_scan_queries, int* out_passes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (out_filter_ms) *out_filter_ms = g_tc_stats.filter_ms;
+  if (out_total_ms) *out_total_ms = g_tc_stats.total_ms;
+  if (out_filter_flops) *out_filter_flops = g_tc_stats.filter_flops;
+  if (out_candidates) *out_candidates = g_tc_stats.candidates;
+  if (out_exact_scan_queries) *out_exact_scan_queries = g_tc_stats.overflowed;
+  if (out_passes) *out_passes = g_tc_stats.passes;
+  return INNR_OK;
+}
 int innr_cuda_launch_count(uint64_t* out_count) {
   if (!out_count) return fail(INNR_EINVAL, "null out");
   *out_count = g_launches;
@@ -306,7 +318,6 @@ static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, in
       *out = nullptr;
       return cuda_fail(e, "cudaMalloc(corpus)");
     }
-    c->tm_pdx_valid = make_pdx_tmap(&c->tm_pdx, (const float*)c->dev, c->n, c->d, c->ld);
   }
   return INNR_OK;
 }
@@ -374,7 +385,6 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   c->ld = ld;
   c->index_base = index_base;
   c->bytes = ld * d * sizeof(float);
-  c->tm_pdx_valid = make_pdx_tmap(&c->tm_pdx, dev_pdx, n, d, ld);
   return INNR_OK;
 }
 
@@ -401,8 +411,8 @@ int innr_cuda_free(innr_cuda_corpus* c) {
   cudaSetDevice(c->device);
   if (c->owns && c->dev) cudaFree(c->dev);
   if (c->dev_offsets) cudaFree(c->dev_offsets);
-  if (c->dev_inv_norms) cudaFree(c->dev_inv_norms);
-  if (c->dev_max_norm_bits) cudaFree(c->dev_max_norm_bits);
+  if (c->dev_norms) cudaFree(c->dev_norms);
+  if (c->dev_xh) cudaFree(c->dev_xh);
   delete c;
   return INNR_OK;
 }
@@ -483,23 +493,48 @@ int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t
 // Queries on the device -> keys on the device. Large batches of dot / cosine queries go through the tensor-core
 // filter (knn_tc.cu: exact results, see there); everything else through the bit-exact scan with fused top-k.
 // innr_cuda_set_option("knn_tc", 0) disables the tensor-core path.
+// Builds the per-corpus operands of the filter path on first use; on any failure the corpus stays on the exact scan.
+static int knn_tc_prepare(innr_cuda_corpus* c, DeviceCtx* ctx, const PdxView& v, cudaStream_t s) {
+  if (c->tc_state != 0) return INNR_OK;
+  c->tc_state = -1;
+  const size_t xh_bytes = c->n * knn_tc_dpad(c->d) * 2;
+  if (cudaMalloc(&c->dev_norms, c->n * sizeof(float) + 16) != cudaSuccess ||
+      cudaMalloc(&c->dev_xh, xh_bytes) != cudaSuccess) {
+    cudaGetLastError();  // out of memory is not an error of the call: exact scan
+    if (c->dev_norms) cudaFree(c->dev_norms);
+    c->dev_norms = nullptr;
+    c->dev_xh = nullptr;
+    return INNR_OK;
+  }
+  CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+  CU(launch_pdx_scores(v, PDX_NORMS, nullptr, nullptr, (float*)ctx->d_scores.p, ctx->ws, s, &g_launches));
+  CU(cudaMemcpyAsync(c->dev_norms, ctx->d_scores.p, c->n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CU(ctx->h_counts.reserve(64));
+  unsigned* nonfinite = (unsigned*)ctx->h_counts.p;
+  CU(launch_knn_tc_build(v, c->dev_norms, c->dev_xh, (unsigned*)(c->dev_norms + c->n), &c->tm_xh, nonfinite, s, &g_launches));
+  if (*nonfinite == 0) {
+    c->tc_state = 1;
+  } else {
+    cudaFree(c->dev_xh);
+    c->dev_xh = nullptr;
+  }
+  return INNR_OK;
+}
+
 static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
                         uint64_t* dev_keys, cudaStream_t s) {
   PdxView v = pdx_view(c);
-  if (g_opt.knn_tc && c->tm_pdx_valid && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries &&
+  if (g_opt.knn_tc && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries && knn_tc_supported(v, mode, nq, k)) {
+    int rc = knn_tc_prepare(c, ctx, v, s);
+    if (rc) return rc;
+  }
+  if (g_opt.knn_tc && c->tc_state == 1 && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries &&
       knn_tc_supported(v, mode, nq, k)) {
-    if (!c->dev_inv_norms) {  // exact norms once per corpus (batch_norms), then 1/norm and the max
-      CU(cudaMalloc(&c->dev_inv_norms, c->n * sizeof(float)));
-      CU(cudaMalloc(&c->dev_max_norm_bits, sizeof(unsigned)));
-      CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
-      CU(launch_pdx_scores(v, PDX_NORMS, nullptr, nullptr, (float*)ctx->d_scores.p, ctx->ws, s, &g_launches));
-      CU(launch_knn_tc_inv_norms((const float*)ctx->d_scores.p, c->n, c->dev_inv_norms, c->dev_max_norm_bits, s, &g_launches));
-    }
     CU(ctx->d_tcws.reserve(knn_tc_workspace_bytes(c->n, c->d, nq, k)));
     CU(ctx->h_counts.reserve(nq * sizeof(unsigned)));
     std::vector<unsigned> overflow;
-    CU(launch_pdx_knn_tc(v, c->tm_pdx, mode, dev_queries, nq, k, dev_keys, c->dev_inv_norms, c->dev_max_norm_bits,
-                         ctx->d_tcws.p, (unsigned*)ctx->h_counts.p, ctx->ws, s, &g_launches, &overflow));
+    CU(launch_pdx_knn_tc(v, c->tm_xh, c->dev_norms, mode, dev_queries, nq, k, dev_keys, ctx->d_tcws.p,
+                         (unsigned*)ctx->h_counts.p, ctx->ws, s, &g_launches, &overflow, &g_tc_stats));
     for (unsigned q : overflow)
       CU(launch_pdx_knn(v, mode, dev_queries + (size_t)q * c->d, 1, k, dev_keys + (size_t)q * k, ctx->ws, s, &g_launches));
     return INNR_OK;

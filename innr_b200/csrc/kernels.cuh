@@ -59,17 +59,25 @@ cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k
                                        Workspace& ws, cudaStream_t s, uint64_t* launches);
 
 // tensor-core filter path for large query batches (knn_tc.cu): dot / cosine, k <= 32, exact results
-bool make_pdx_tmap(CUtensorMap* m, const float* dev_pdx, size_t n, size_t d, size_t ld);
+struct KnnTcStats {
+  float filter_ms = 0, total_ms = 0;   // final (whole-corpus) filter pass; whole device-side call
+  double filter_flops = 0;             // flops issued by the final filter pass (2 * rows * padded d * padded queries)
+  unsigned long long candidates = 0;   // pairs re-scored exactly
+  unsigned overflowed = 0;             // queries answered by the exact scan instead
+  int passes = 0;
+};
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k);
+size_t knn_tc_dpad(size_t d);  // row pitch (elements) of the f16 operand copy
 size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k);
-cudaError_t launch_knn_tc_inv_norms(const float* dev_norms, size_t n, float* dev_inv, unsigned* dev_max_bits, cudaStream_t s,
-                                    uint64_t* launches);
-// host_counts: pinned buffer of nq unsigned; overflow_queries receives the queries whose candidate list overflowed
+// once per corpus: dev_xh (n x knn_tc_dpad(d) f16) = unit vectors, from the PDX corpus and its exact norms
+cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* dev_xh, unsigned* dev_scratch_u32,
+                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, uint64_t* launches);
+// host_counts: pinned buffer of nq unsigned; overflow_queries receives the queries the filter could not answer
 // (the caller re-runs them on the exact scan). Synchronises the stream once at the end.
-cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mode, const float* dev_queries, size_t nq,
-                              size_t k, uint64_t* dev_keys, const float* dev_inv_norms, const unsigned* dev_max_norm_bits,
-                              void* workspace, unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
-                              std::vector<unsigned>* overflow_queries);
+cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
+                              const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys, void* workspace,
+                              unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                              std::vector<unsigned>* overflow_queries, KnnTcStats* stats);
 
 // layout / generator kernels (layout.cu)
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,

@@ -2,25 +2,33 @@
 //
 // For large query batches (BASELINE C2b: 1024 queries over 10M x 768) scoring is a dense contraction. The reference
 // (src/batch.rs:742-800) scores every (query, vector) pair in f32 and fully sorts; results must stay bit-exact with
-// it, which a TF32 contraction cannot deliver directly. So the tensor cores only *prune*:
+// it, which no tensor-core contraction delivers directly. So the tensor cores only *prune*, with a rigorous bound:
 //
-//   1. sample pass   exact top-k of every query over a prefix of the corpus (the bit-exact scan kernel of
-//                    scan_f32.cu) -> L_q = k-th best exact score = a lower bound of the true k-th best score;
-//   2. filter pass   S = X * [Qhi ; Qlo]^T on tcgen05 (3-term TF32 split, f32 accumulate in TMEM), reading the PDX
-//                    corpus directly as the MN-major A operand (TMA, SWIZZLE_128B_ATOM_32B); every pair with
-//                    S >= L_q - margin is appended to a per-query candidate list (a few hundred per query);
-//   3. rescore       candidates are re-scored with the reference's exact sequential f32 arithmetic and the top-k is
-//                    selected on the same 64-bit keys as the scan kernel -> indices and scores bit-identical to
-//                    batch_knn_dot / batch_knn_cosine. A query whose list overflows falls back to the exact scan.
+//   0. once per corpus  exact norms (the bit-exact scan) and Xh = f16(x / ||x||), row-major [n][d] (K-major operand);
+//   1. per call         Qh = f16(q / ||q||), row-major [nq][d];
+//   2. filter passes    S = Xh * Qh^T on tcgen05 (kind::f16, f32 accumulate in TMEM) ~ cosine(q, x), |S - cos| <= eps.
+//                       With r = ||x|| (dot) or [||x|| > 1e-9] (cosine), every pair has the interval
+//                       [S*r - eps*r, S*r + eps*r] around the reference's score (in units of score/||q|| for dot).
+//                       A pass over rows [0, n_i) appends (index, lower bound) of every pair whose UPPER bound reaches
+//                       the query's threshold; the k-th largest LOWER bound of the appended pairs is a valid lower
+//                       bound of the reference's k-th best score and becomes the threshold of the next, larger pass
+//                       (n_0 = 4096 rows with threshold -inf, then n/512, n/16, n). No exact sample scan is needed.
+//   3. rescore          the final candidates (~20 k per query) are re-scored with the reference's exact sequential
+//                       f32 arithmetic and selected on the same 64-bit keys as the scan kernel -> indices and scores
+//                       bit-identical to batch_knn_dot / batch_knn_cosine. A query whose final list overflows, or
+//                       whose norm is zero / non-finite, is re-run on the exact scan by the caller.
 //
-// The margin (2e-5 of ||q||*max||v||, 2e-5 absolute for cosine) is ~10x the error bound of the split
-// (2^-21 relative to sum|q_i v_i| plus f32 accumulation); tests compare against the exact path on i.i.d. data and on
-// the reference's near-tie lattice.
+// eps = 1.05e-3 + 3.5e-7*d bounds: f16 rounding of both unit vectors (2*2^-11 of sum|q'x'| <= 1, plus the subnormal
+// floor), the f32 accumulation of d exact products in the tensor core (d*2^-23, truncation), and the distance of the
+// reference's own sequential f32 score from the real-valued one (2*d*2^-24). Corpora with a non-finite norm never
+// take this path.
 //
-// Filter kernel: persistent, one CTA per SM, 320 threads: TMA producer warp, MMA issuer warp, 4 converter warps
-// (Xlo -> TMEM as the A operand of the third product), 4 epilogue warps (TMEM -> registers, threshold, append).
-// Work unit = 128 vectors x 128 queries, K loop over 32-dimension blocks through a 4-stage shared-memory ring
-// (X 16 KB + Qhi 16 KB + Qlo 16 KB per stage); 12 MMAs (M128 N128 K8) per block.
+// Filter kernel: persistent, one CTA per SM, 192 threads: 4 epilogue warps (TMEM -> registers, bound test, append),
+// TMA producer warp, MMA issuer warp. Work unit = 128 vectors x 256 queries, K loop over 64-dimension blocks through a
+// 4-stage shared-memory ring (X 16 KB + Q 32 KB per stage), 4 MMAs (M128 N256 K16) per block, two 256-column
+// accumulators in TMEM so the epilogue of one unit overlaps the MMAs of the next.
+#include <cuda_fp16.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -35,196 +43,183 @@ namespace {
 
 using namespace tc;
 
-constexpr int KT_THREADS = 320;
+constexpr int KT_THREADS = 192;
 constexpr int VT = 128;    // vectors per work unit (UMMA M)
-constexpr int QT = 128;    // queries per work unit (UMMA N)
-constexpr int KB = 32;     // dimensions per K block
+constexpr int QT = 256;    // queries per work unit (UMMA N, up to)
+constexpr int KB = 64;     // dimensions per K block (128 bytes of f16 = one swizzle row)
 constexpr int KSTAGES = 4;
-constexpr int X_BYTES = KB * VT * 4;   // 16 KB: 4 boxes of [32 dims][32 vectors]
-constexpr int Q_BYTES = QT * KB * 4;   // 16 KB: [128 queries][32 dims], K-major SW128
-constexpr int KSTAGE_BYTES = X_BYTES + 2 * Q_BYTES;
-constexpr int ACC_COL0 = 0;      // 2 accumulators x 128 columns
-constexpr int XLO_COL0 = 256;    // 2 Xlo buffers x 32 columns
-constexpr float NORM_EPS = 1e-9f;
+constexpr int X_BYTES = VT * KB * 2;   // 16 KB
+constexpr int Q_BYTES = QT * KB * 2;   // 32 KB
+constexpr int KSTAGE_BYTES = X_BYTES + Q_BYTES;
+constexpr float COS_NORM_EPS = 1e-9f;   // src/batch.rs:721-727
+constexpr float TINY_NORM = 1e-30f;     // below this a vector / query is not normalised (handled by the exact path)
+constexpr unsigned CAND_CAP = 4096;
 
 struct KtShared {
-  uint64_t full[KSTAGES], empty[KSTAGES], lo_ready[2], lo_free[2], acc_full[2], acc_empty[2];
+  uint64_t full[KSTAGES], empty[KSTAGES], acc_full[2], acc_empty[2];
   float thr[2][QT];
   uint32_t tmem_base;
 };
 
 struct KtArgs {
-  unsigned n, d, n_vtiles, n_qgroups, kblocks;
-  unsigned index_base;
+  unsigned n_rows;          // rows [0, n_rows) of the corpus are filtered by this pass
+  unsigned n_qgroups, kblocks, nq_pad;
   int cosine;
-  const float* inv_norms;   // n floats: 1/||v|| (0 when ||v|| <= eps), cosine only
-  const float* thr;         // n_qgroups*QT thresholds (+inf for padded queries)
+  float eps;
+  const float* norms;       // exact ||x|| per vector
+  const float* thr;         // nq_pad thresholds (+inf: accept nothing)
   unsigned* cand_count;     // nq_pad counters
-  unsigned* cand;           // nq_pad x cap local vector indices
-  unsigned cap;
+  unsigned* cand_idx;       // nq_pad x CAND_CAP local vector indices
+  float* cand_lb;           // nq_pad x CAND_CAP lower bounds
 };
 
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16, A = B = F16 (format 0), K-major, F32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __grid_constant__ CUtensorMap tm_x,
-                                                                       const __grid_constant__ CUtensorMap tm_qhi,
-                                                                       const __grid_constant__ CUtensorMap tm_qlo,
+                                                                       const __grid_constant__ CUtensorMap tm_q,
                                                                        const KtArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   KtShared* st = reinterpret_cast<KtShared*>(smem + KSTAGES * KSTAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // contiguous range of vector tiles for this CTA; every query group is processed for a tile before moving on, so
-  // the tile's rows are re-read from L2, not from HBM
-  const unsigned vt_lo = (unsigned)((unsigned long long)a.n_vtiles * blockIdx.x / gridDim.x);
-  const unsigned vt_hi = (unsigned)((unsigned long long)a.n_vtiles * (blockIdx.x + 1) / gridDim.x);
-  const unsigned n_units = (vt_hi - vt_lo) * a.n_qgroups;
+  // contiguous range of (vector tile, query group) units for this CTA, query group fastest: the X tile of consecutive
+  // units is the same and is re-read from L2, not from HBM
+  const unsigned n_vtiles = (a.n_rows + VT - 1) / VT;
+  const unsigned long long total_units = (unsigned long long)n_vtiles * a.n_qgroups;
+  const unsigned u_lo = (unsigned)(total_units * blockIdx.x / gridDim.x);
+  const unsigned u_hi = (unsigned)(total_units * (blockIdx.x + 1) / gridDim.x);
+  const unsigned n_units = u_hi - u_lo;
   const unsigned n_iters = n_units * a.kblocks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < KSTAGES; ++s) {
       mbar_init(&st->full[s], 1);
-      mbar_init(&st->empty[s], 129);  // MMAs done with the stage (1 commit) + 128 converter threads done reading X
+      mbar_init(&st->empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&st->lo_ready[b], 128);
-      mbar_init(&st->lo_free[b], 1);
       mbar_init(&st->acc_full[b], 1);
       mbar_init(&st->acc_empty[b], 4);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tm_x);
-    tma_prefetch_desc(&tm_qhi);
-    tma_prefetch_desc(&tm_qlo);
+    tma_prefetch_desc(&tm_q);
   }
-  if (warp == 9) tmem_alloc<512>(&st->tmem_base);
+  if (warp == 5) tmem_alloc<512>(&st->tmem_base);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = st->tmem_base;
 
-  if (warp == 8) {
+  if (warp == 4) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       for (unsigned it = 0; it < n_iters; ++it) {
-        const unsigned unit = it / a.kblocks, kb = it % a.kblocks;
-        const unsigned vt = vt_lo + unit / a.n_qgroups, qg = unit % a.n_qgroups;
+        const unsigned unit = u_lo + it / a.kblocks, kb = it % a.kblocks;
+        const unsigned vt = unit / a.n_qgroups, qg = unit % a.n_qgroups;
         const int s = it % KSTAGES;
         mbar_wait(&st->empty[s], ((it / KSTAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&st->full[s], KSTAGE_BYTES);
         uint8_t* sb = smem + s * KSTAGE_BYTES;
-        for (int mb = 0; mb < 4; ++mb) tma_load_2d(sb + mb * 4096, &tm_x, &st->full[s], (int)(vt * VT + mb * 32), (int)(kb * KB));
-        tma_load_2d(sb + X_BYTES, &tm_qhi, &st->full[s], (int)(kb * KB), (int)(qg * QT));
-        tma_load_2d(sb + X_BYTES + Q_BYTES, &tm_qlo, &st->full[s], (int)(kb * KB), (int)(qg * QT));
+        tma_load_2d(sb, &tm_x, &st->full[s], (int)(kb * KB), (int)(vt * VT));
+        tma_load_2d(sb + X_BYTES, &tm_q, &st->full[s], (int)(kb * KB), (int)(qg * QT));
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 5) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc_mn = make_idesc_tf32(VT, QT, true);   // A = X tile in shared memory, MN-major
-      const uint32_t idesc_ts = make_idesc_tf32(VT, QT, false);  // A = Xlo in tensor memory
-      auto issue_hi = [&](unsigned it) {  // Xhi.Qhi + Xhi.Qlo
-        const unsigned unit = it / a.kblocks, kb = it % a.kblocks;
+      for (unsigned it = 0; it < n_iters; ++it) {
+        const unsigned ul = it / a.kblocks, kb = it % a.kblocks;
+        const unsigned qg = (u_lo + ul) % a.n_qgroups;
+        const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
+        const uint32_t idesc = make_idesc_f16(VT, (int)qt_u);
         const int s = it % KSTAGES;
+        if (kb == 0) mbar_wait(&st->acc_empty[ul & 1], ((ul >> 1) & 1) ^ 1);
+        mbar_wait(&st->full[s], (it / KSTAGES) & 1);
+        tc_fence_after_sync();
         const uint32_t xb = smem_u32(smem + s * KSTAGE_BYTES);
-        const uint32_t acc = tmem + ACC_COL0 + (unit & 1) * QT;
+        const uint32_t acc = tmem + (ul & 1) * QT;
 #pragma unroll
-        for (int ks = 0; ks < KB / 8; ++ks) {
-          const uint64_t ad = make_smem_desc_mnmajor_sw128_32b(xb + ks * 1024, 4096, 512);
-          const uint64_t bh = make_smem_desc_kmajor_sw128(xb + X_BYTES + ks * 32);
-          const uint64_t bl = make_smem_desc_kmajor_sw128(xb + X_BYTES + Q_BYTES + ks * 32);
-          umma_tf32(acc, ad, bh, idesc_mn, (kb > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(acc, ad, bl, idesc_mn, 1u);
+        for (int ks = 0; ks < KB / 16; ++ks) {
+          const uint64_t ad = make_smem_desc_kmajor_sw128(xb + ks * 32);
+          const uint64_t bd = make_smem_desc_kmajor_sw128(xb + X_BYTES + ks * 32);
+          umma_f16(acc, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
         }
-      };
-      auto issue_lo = [&](unsigned it) {  // Xlo.Qhi
-        const unsigned unit = it / a.kblocks;
-        const int s = it % KSTAGES, b = it & 1;
-        const uint32_t xb = smem_u32(smem + s * KSTAGE_BYTES);
-        const uint32_t acc = tmem + ACC_COL0 + (unit & 1) * QT;
-#pragma unroll
-        for (int ks = 0; ks < KB / 8; ++ks) {
-          const uint64_t bh = make_smem_desc_kmajor_sw128(xb + X_BYTES + ks * 32);
-          umma_tf32_ts(acc, tmem + XLO_COL0 + b * KB + ks * 8, bh, idesc_ts, 1u);
-        }
-      };
-      unsigned nh = 0, nl = 0;
-      while (nl < n_iters) {
-        if (nl < nh) {
-          const int b = nl & 1;
-          if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
-            tc_fence_after_sync();
-            issue_lo(nl);
-            umma_commit(&st->empty[nl % KSTAGES]);  // the stage (X and Q) is no longer read by the tensor core
-            umma_commit(&st->lo_free[b]);
-            if (nl % a.kblocks == a.kblocks - 1) umma_commit(&st->acc_full[(nl / a.kblocks) & 1]);
-            ++nl;
-          }
-        }
-        if (nh < n_iters && nh < nl + KSTAGES) {
-          const int s = nh % KSTAGES;
-          const unsigned unit = nh / a.kblocks;
-          bool ok = mbar_try_wait(&st->full[s], (nh / KSTAGES) & 1);
-          if (ok && nh % a.kblocks == 0) ok = mbar_try_wait(&st->acc_empty[unit & 1], ((unit >> 1) & 1) ^ 1);
-          if (ok) {
-            tc_fence_after_sync();
-            issue_hi(nh);
-            ++nh;
-          }
-        }
+        umma_commit(&st->empty[s]);  // the stage is no longer read by the tensor core
+        if (kb == a.kblocks - 1) umma_commit(&st->acc_full[ul & 1]);
       }
-    }
-  } else if (warp >= 4) {
-    // =========================== converters: Xlo -> TMEM (A operand of the third product) ===========================
-    const int m = threadIdx.x - 128;  // vector (TMEM lane) owned by this thread
-    const int mb = m >> 5, e = m & 31;
-    for (unsigned it = 0; it < n_iters; ++it) {
-      const int s = it % KSTAGES, b = it & 1;
-      mbar_wait(&st->full[s], (it / KSTAGES) & 1);
-      mbar_wait(&st->lo_free[b], ((it >> 1) & 1) ^ 1);
-      tc_fence_after_sync();
-      const uint8_t* box = smem + s * KSTAGE_BYTES + mb * 4096;
-      uint32_t lo[32];
-#pragma unroll
-      for (int k = 0; k < KB; ++k) {
-        // SWIZZLE_128B_ATOM_32B: 32-byte chunk index XOR (row % 4)
-        const float x = *reinterpret_cast<const float*>(box + k * 128 + ((((e >> 3) ^ (k & 3)) << 5) | ((e & 7) << 2)));
-        lo[k] = __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u));
-      }
-      mbar_arrive(&st->empty[s]);
-      tmem_st_32x32b_x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + XLO_COL0 + b * KB, lo);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&st->lo_ready[b]);
     }
   } else {
-    // =========================== epilogue: threshold + append ===========================
-    for (unsigned unit = 0; unit < n_units; ++unit) {
-      const unsigned vt = vt_lo + unit / a.n_qgroups, qg = unit % a.n_qgroups;
-      const int ab = unit & 1;
+    // =========================== epilogue: bound test + append ===========================
+    for (unsigned ul = 0; ul < n_units; ++ul) {
+      const unsigned unit = u_lo + ul;
+      const unsigned vt = unit / a.n_qgroups, qg = unit % a.n_qgroups;
+      const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
+      const int ab = ul & 1;
       const unsigned v = vt * VT + warp * 32 + lane;  // local vector index of this lane
-      st->thr[ab][warp * 32 + lane] = a.thr[qg * QT + warp * 32 + lane];
-      float rn = 1.0f;
-      if (a.cosine) rn = v < a.n ? a.inv_norms[v] : 0.0f;
+      for (unsigned c = threadIdx.x; c < QT; c += 128) st->thr[ab][c] = c < qt_u ? a.thr[qg * QT + c] : INFINITY;
+      float rn = 0.0f, e = 0.0f;
+      const bool vvalid = v < a.n_rows;
+      if (vvalid) {
+        const float nv = a.norms[v];
+        if (a.cosine) {
+          rn = nv > COS_NORM_EPS ? 1.0f : 0.0f;
+          e = a.eps * rn;
+        } else {
+          rn = nv >= TINY_NORM ? nv : 0.0f;
+          e = a.eps * rn + 1e-18f;
+        }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // thresholds of this unit visible to the 4 epilogue warps
-      mbar_wait(&st->acc_full[ab], (unit >> 1) & 1);
+      mbar_wait(&st->acc_full[ab], (ul >> 1) & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + ACC_COL0 + ab * QT;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + ab * QT;
 #pragma unroll 1
-      for (int c0 = 0; c0 < QT; c0 += 32) {
+      for (unsigned c0 = 0; c0 < qt_u; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         tmem_ld_wait();
-        if (c0 + 32 == QT) {
+        if (c0 + 32 >= qt_u) {
           tc_fence_before_sync();
           if (lane == 0) mbar_arrive(&st->acc_empty[ab]);
         }
-        if (v < a.n) {
+        const float4* t4 = reinterpret_cast<const float4*>(&st->thr[ab][c0]);
+        bool any = false;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 t = t4[j4];
+          any |= fmaf(__uint_as_float(r[4 * j4 + 0]), rn, e) >= t.x;
+          any |= fmaf(__uint_as_float(r[4 * j4 + 1]), rn, e) >= t.y;
+          any |= fmaf(__uint_as_float(r[4 * j4 + 2]), rn, e) >= t.z;
+          any |= fmaf(__uint_as_float(r[4 * j4 + 3]), rn, e) >= t.w;
+        }
+        if (__any_sync(FULL_MASK, any && vvalid)) {  // rare (except in the first, dense pass): warp-aggregated appends
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float sc = __uint_as_float(r[j]) * rn;
-            if (sc >= st->thr[ab][c0 + j]) {
+            const float sr = __uint_as_float(r[j]);
+            const bool hit = vvalid && (fmaf(sr, rn, e) >= st->thr[ab][c0 + j]);
+            const unsigned m = __ballot_sync(FULL_MASK, hit);
+            if (m) {
               const unsigned q = qg * QT + c0 + j;
-              const unsigned pos = atomicAdd(&a.cand_count[q], 1u);
-              if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = v;
+              unsigned base = 0;
+              if (lane == __ffs(m) - 1) base = atomicAdd(&a.cand_count[q], (unsigned)__popc(m));
+              base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
+              const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+              if (hit && pos < CAND_CAP) {
+                a.cand_idx[(size_t)q * CAND_CAP + pos] = v;
+                a.cand_lb[(size_t)q * CAND_CAP + pos] = fmaf(sr, rn, -e);
+              }
             }
           }
         }
@@ -234,85 +229,124 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 5) tmem_dealloc<512>(tmem);
 }
 
-// ---- Qhi / Qlo operand matrices (row-major [nq_pad][d_pad]) ---------------------------------------------------------
-__global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned nq, unsigned d, unsigned nq_pad,
-                                           unsigned d_pad, int cosine, float* __restrict__ qhi, float* __restrict__ qlo,
-                                           float* __restrict__ qnorm) {
-  const unsigned row = blockIdx.x;
-  __shared__ float s_scale;
-  if (threadIdx.x == 0) {
-    float scale = 1.0f, qn = 0.0f;
-    if (row < nq) {
-      float ss = 0.0f;  // sequential f32 sum, as batch_cosine_into (src/batch.rs:714)
-      for (unsigned k = 0; k < d; ++k) ss = __fadd_rn(ss, __fmul_rn(q[(size_t)row * d + k], q[(size_t)row * d + k]));
-      qn = __fsqrt_rn(ss);
-      if (cosine) scale = qn > NORM_EPS ? 1.0f / qn : 0.0f;
+// ---- once per corpus: Xh[i][k] = f16(x[k][i] / ||x_i||) from the PDX corpus and its exact norms ----------------------
+__global__ void knn_tc_build_xh_kernel(const float* __restrict__ pdx, size_t ld, unsigned n, unsigned d, unsigned d_pad,
+                                       const float* __restrict__ norms, __half* __restrict__ xh,
+                                       unsigned* __restrict__ nonfinite) {
+  __shared__ float tile[32][33];
+  const unsigned i0 = blockIdx.x * 32;
+  const unsigned tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  float inv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const unsigned i = i0 + ty * 4 + r;
+    float nv = i < n ? norms[i] : 0.0f;
+    const bool finite = nv == nv && nv < INFINITY;
+    if (i < n && !finite && tx == 0) atomicAdd(nonfinite, 1u);
+    inv[r] = (finite && nv >= TINY_NORM) ? 1.0f / nv : 0.0f;
+  }
+  for (unsigned d0 = 0; d0 < d_pad; d0 += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned dd = d0 + ty * 4 + r, i = i0 + tx;
+      tile[ty * 4 + r][tx] = (dd < d && i < n) ? pdx[(size_t)dd * ld + i] : 0.0f;
     }
-    s_scale = scale;
-    if (row < nq_pad) qnorm[row] = qn;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const unsigned i = i0 + ty * 4 + r, dd = d0 + tx;
+      if (i < n && dd < d_pad) xh[(size_t)i * d_pad + dd] = __float2half_rn(tile[tx][ty * 4 + r] * inv[r]);
+    }
+  }
+}
+
+// ---- per call: Qh row = f16(q / ||q||); ||q|| is the sequential f32 sum of batch_cosine_into (src/batch.rs:714) ------
+__global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned nq, unsigned d, unsigned nq_pad,
+                                           unsigned d_pad, int cosine, __half* __restrict__ qh,
+                                           unsigned* __restrict__ qflag, float* __restrict__ thr,
+                                           unsigned* __restrict__ cand_count) {
+  const unsigned row = blockIdx.x;
+  __shared__ float s_inv;
+  __shared__ unsigned s_bad;
+  if (threadIdx.x == 0) {
+    float inv = 0.0f;
+    unsigned bad = 0;
+    if (row < nq) {
+      float ss = 0.0f;
+      for (unsigned k = 0; k < d; ++k) ss = __fadd_rn(ss, __fmul_rn(q[(size_t)row * d + k], q[(size_t)row * d + k]));
+      const float qn = __fsqrt_rn(ss);
+      const bool finite = qn == qn && qn < INFINITY;
+      // zero / denormal / non-finite norms, and cosine queries below the reference's 1e-9 guard (all scores 0.0):
+      // answered by the exact scan
+      bad = (!finite || qn < TINY_NORM || (cosine && qn < COS_NORM_EPS)) ? 1u : 0u;
+      inv = bad ? 0.0f : 1.0f / qn;
+    }
+    s_inv = inv;
+    s_bad = bad;
+    qflag[row] = bad;
+    thr[row] = (row < nq && !bad) ? -INFINITY : INFINITY;  // first pass: everything / nothing
+    cand_count[row] = 0;
   }
   __syncthreads();
+  const float inv = s_inv;
   for (unsigned k = threadIdx.x; k < d_pad; k += blockDim.x) {
-    float v = (row < nq && k < d) ? q[(size_t)row * d + k] * s_scale : 0.0f;
-    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    qhi[(size_t)row * d_pad + k] = hi;
-    qlo[(size_t)row * d_pad + k] = v - hi;
+    const float v = (row < nq && k < d) ? q[(size_t)row * d + k] * inv : 0.0f;
+    qh[(size_t)row * d_pad + k] = __float2half_rn(v);
   }
 }
 
-// ---- 1/||v|| and max ||v|| from the exact norms -----------------------------------------------------------------------
-__global__ void knn_tc_inv_norms_kernel(const float* __restrict__ norms, unsigned n, float* __restrict__ inv,
-                                        unsigned* __restrict__ max_bits) {
-  float mx = 0.0f;
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float nv = norms[i];
-    inv[i] = nv > NORM_EPS ? 1.0f / nv : 0.0f;
-    if (nv == nv) mx = fmaxf(mx, nv);
+// ---- between passes: threshold of the next pass = k-th largest lower bound among the appended pairs ------------------
+// one warp per query; also resets the counter for the next pass
+__global__ void knn_tc_select_kernel(unsigned nq, unsigned k, const unsigned* __restrict__ qflag,
+                                     unsigned* __restrict__ cand_count, const float* __restrict__ cand_lb,
+                                     float* __restrict__ thr) {
+  const unsigned q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  if (qflag[q]) return;  // thr stays +inf
+  unsigned cnt = cand_count[q];
+  if (cnt > CAND_CAP) cnt = CAND_CAP;  // any k stored pairs give a valid bound
+  WarpList<1> list;
+  list.init();
+  uint64_t t = KEY_SENTINEL;
+  for (unsigned c0 = 0; c0 < cnt; c0 += 32) {
+    const unsigned c = c0 + lane;
+    const bool valid = c < cnt;
+    const float lb = valid ? cand_lb[(size_t)q * CAND_CAP + c] : 0.0f;
+    list.offer(make_key_desc(lb, c), valid, t, (int)k, lane);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(max_bits, __float_as_uint(mx));  // non-negative floats order like uints
+  const uint64_t kth = list.at((int)k - 1);
+  if (lane == 0) {
+    thr[q] = (kth == KEY_SENTINEL) ? -INFINITY : __uint_as_float(order_bits_to_f32_bits(~(uint32_t)(kth >> 32)));
+    cand_count[q] = 0;
+  }
 }
 
-// ---- thresholds from the sample pass: thr_q = (k-th best exact score of the sample) - margin ----------------------------
-__global__ void knn_tc_threshold_kernel(const uint64_t* __restrict__ sample_keys, unsigned nq, unsigned nq_pad, unsigned k,
-                                        int cosine, const float* __restrict__ qnorm, const unsigned* __restrict__ max_bits,
-                                        float* __restrict__ thr) {
-  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq_pad) return;
-  float t = INFINITY;  // padded queries accept nothing
-  if (q < nq) {
-    const uint64_t key = sample_keys[(size_t)q * k + (k - 1)];
-    if (key == KEY_SENTINEL) {
-      t = -INFINITY;  // sample smaller than k: no bound
-    } else {
-      const float lb = __uint_as_float(order_bits_to_f32_bits(~(uint32_t)(key >> 32)));
-      const float scale = cosine ? 1.0f : qnorm[q] * __uint_as_float(*max_bits);
-      t = (lb == lb) ? lb - 2e-5f * scale : -INFINITY;
-    }
-  }
-  thr[q] = t;
-}
-
-// ---- exact rescoring + selection: one CTA per query ---------------------------------------------------------------------
+// ---- exact rescoring + selection: one CTA per query -------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 
 template <int R>
 __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float* __restrict__ data, size_t ld, unsigned n,
                                                                     unsigned d, unsigned index_base,
                                                                     const float* __restrict__ queries, int cosine,
-                                                                    const unsigned* __restrict__ cand_count,
-                                                                    const unsigned* __restrict__ cand, unsigned cap,
-                                                                    int k, uint64_t* __restrict__ out_keys) {
+                                                                    const unsigned* __restrict__ qflag,
+                                                                    unsigned* __restrict__ cand_count,
+                                                                    const unsigned* __restrict__ cand, int k,
+                                                                    uint64_t* __restrict__ out_keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(sq + ((d + 3) & ~3u));
   __shared__ float s_qn;
   const unsigned q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (qflag[q]) {  // not filtered: reported as overflowed so that the caller runs the exact scan for it
+    if (threadIdx.x == 0) cand_count[q] = 0xFFFFFFFFu;
+    return;
+  }
   for (unsigned i = threadIdx.x; i < d; i += blockDim.x) sq[i] = queries[(size_t)q * d + i];
   if (threadIdx.x == 0) {
     float ss = 0.0f;
@@ -322,7 +356,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
   __syncthreads();
   const float qn = s_qn;
   unsigned cnt = cand_count[q];
-  if (cnt > cap) cnt = cap;
+  if (cnt > CAND_CAP) cnt = CAND_CAP;
   WarpList<R> list;
   list.init();
   uint64_t thr = KEY_SENTINEL;
@@ -331,7 +365,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
     const bool valid = c < cnt;
     uint64_t key = KEY_SENTINEL;
     if (valid) {
-      const unsigned i = cand[(size_t)q * cap + c];
+      const unsigned i = cand[(size_t)q * CAND_CAP + c];
       const float* p = data + i;
       float acc = 0.0f, ss = 0.0f;
       for (unsigned dd = 0; dd < d; ++dd) {  // the reference's sequential unfused sums (src/batch.rs:290-296, 676-681)
@@ -342,7 +376,7 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
       float s = acc;
       if (cosine) {
         const float nrm = __fsqrt_rn(ss);
-        s = (!(qn < NORM_EPS) && nrm > NORM_EPS) ? __fdiv_rn(acc, __fmul_rn(qn, nrm)) : 0.0f;
+        s = (!(qn < COS_NORM_EPS) && nrm > COS_NORM_EPS) ? __fdiv_rn(acc, __fmul_rn(qn, nrm)) : 0.0f;
       }
       key = make_key_desc(s, index_base + i);
     }
@@ -352,91 +386,115 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
   if (warp == 0) list.store(out_keys + (size_t)q * k, k, lane);
 }
 
-}  // namespace
-
-bool make_pdx_tmap(CUtensorMap* m, const float* dev_pdx, size_t n, size_t d, size_t ld) {
-  if (n == 0 || d == 0) return false;
-  return make_tmap_f32_rows(m, dev_pdx, d, n, KB, ld, /*atom32=*/true);  // box = 32 vectors x 32 dims
+// tensor map over a row-major f16 matrix [rows][pitch] (pitch in elements, multiple of 8): box = 64 x box_rows, SW128
+bool make_tmap_f16_rows(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc || rows == 0 || cols == 0) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch * 2};
+  cuuint32_t box[2] = {KB, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-size_t knn_tc_cap() { return 4096; }
-
-// workspace layout helpers -----------------------------------------------------------------------------------------------
+// workspace layout ------------------------------------------------------------------------------------------------------
 struct KnnTcPlan {
-  unsigned nq_pad, d_pad, n_s;
-  size_t off_qhi, off_qlo, off_qnorm, off_thr, off_cnt, off_cand, off_skeys, total;
+  unsigned nq_pad, d_pad;
+  size_t off_qh, off_qflag, off_thr, off_cnt, off_idx, off_lb, total;
 };
 
-static KnnTcPlan make_plan(size_t n, size_t d, size_t nq, size_t k) {
+KnnTcPlan make_plan(size_t d, size_t nq) {
   KnnTcPlan p{};
-  p.nq_pad = (unsigned)((nq + QT - 1) / QT * QT);
-  p.d_pad = (unsigned)((d + KB - 1) / KB * KB);
-  size_t ns = n / 128;
-  if (ns < 64 * k) ns = 64 * k;
-  if (ns < 8192) ns = 8192;
-  if (ns > n) ns = n;
-  p.n_s = (unsigned)ns;
+  p.nq_pad = (unsigned)((nq + 15) / 16 * 16);
+  p.d_pad = (unsigned)knn_tc_dpad(d);
   size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-  p.off_qhi = take((size_t)p.nq_pad * p.d_pad * 4);
-  p.off_qlo = take((size_t)p.nq_pad * p.d_pad * 4);
-  p.off_qnorm = take((size_t)p.nq_pad * 4);
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 1023) / 1024 * 1024; return r; };
+  p.off_qh = take((size_t)p.nq_pad * p.d_pad * 2);
+  p.off_qflag = take((size_t)p.nq_pad * 4);
   p.off_thr = take((size_t)p.nq_pad * 4);
   p.off_cnt = take((size_t)p.nq_pad * 4);
-  p.off_cand = take((size_t)p.nq_pad * knn_tc_cap() * 4);
-  p.off_skeys = take((size_t)nq * k * 8);
+  p.off_idx = take((size_t)p.nq_pad * CAND_CAP * 4);
+  p.off_lb = take((size_t)p.nq_pad * CAND_CAP * 4);
   p.total = o;
   return p;
 }
 
-size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) { return make_plan(n, d, nq, k).total; }
+}  // namespace
+
+size_t knn_tc_dpad(size_t d) { return (d + 7) / 8 * 8; }
+
+size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) {
+  (void)n;
+  (void)k;
+  return make_plan(d, nq).total;
+}
 
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k) {
   return (mode == PDX_DOT || mode == PDX_COSINE_FUSED) && nq >= 1 && k >= 1 && k <= 32 && v.d >= 1 && v.n >= 4096 &&
-         v.n < 0x7FFFFF00ull && v.ld % 4 == 0;
+         v.n < 0x7FFFFF00ull;
 }
 
-cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mode, const float* dev_queries, size_t nq,
-                              size_t k, uint64_t* dev_keys, const float* dev_inv_norms, const unsigned* dev_max_norm_bits,
-                              void* workspace, unsigned* host_counts, Workspace& ws, cudaStream_t s,
-                              uint64_t* launches, std::vector<unsigned>* overflow_queries) {
+// Xh + its tensor map from the PDX corpus and its exact norms; *host_nonfinite = vectors with a NaN / inf norm (the
+// caller disables the path for the corpus when it is not 0). Synchronises the stream.
+cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* dev_xh, unsigned* dev_scratch_u32,
+                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, uint64_t* launches) {
+  const unsigned d_pad = (unsigned)knn_tc_dpad(v.d);
+  cudaError_t e = cudaMemsetAsync(dev_scratch_u32, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  knn_tc_build_xh_kernel<<<(unsigned)((v.n + 31) / 32), dim3(32, 8), 0, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, d_pad,
+                                                                             dev_norms, (__half*)dev_xh, dev_scratch_u32);
+  ++*launches;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(host_nonfinite, dev_scratch_u32, 4, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return e;
+  if (!make_tmap_f16_rows(tm_xh, dev_xh, v.n, d_pad, d_pad, VT)) return cudaErrorInvalidValue;
+  return cudaSuccess;
+}
+
+cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
+                              const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys, void* workspace,
+                              unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                              std::vector<unsigned>* overflow_queries, KnnTcStats* stats) {
   const int cosine = mode == PDX_COSINE_FUSED;
-  const KnnTcPlan p = make_plan(v.n, v.d, nq, k);
+  const KnnTcPlan p = make_plan(v.d, nq);
   uint8_t* w = (uint8_t*)workspace;
-  float* qhi = (float*)(w + p.off_qhi);
-  float* qlo = (float*)(w + p.off_qlo);
-  float* qnorm = (float*)(w + p.off_qnorm);
+  __half* qh = (__half*)(w + p.off_qh);
+  unsigned* qflag = (unsigned*)(w + p.off_qflag);
   float* thr = (float*)(w + p.off_thr);
   unsigned* cnt = (unsigned*)(w + p.off_cnt);
-  unsigned* cand = (unsigned*)(w + p.off_cand);
-  uint64_t* skeys = (uint64_t*)(w + p.off_skeys);
+  unsigned* cand_idx = (unsigned*)(w + p.off_idx);
+  float* cand_lb = (float*)(w + p.off_lb);
   cudaError_t e;
   static const bool trace = getenv("INNR_KNN_TC_TRACE") != nullptr;
-  cudaEvent_t ev[6];
-  if (trace)
-    for (auto& x : ev) cudaEventCreate(&x);
-  auto mark = [&](int i) { if (trace) cudaEventRecord(ev[i], s); };
-  mark(0);
+  static cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call begin, final pass begin / end, call end
+  if (!ev[0])
+    for (auto& x : ev)
+      if ((e = cudaEventCreate(&x)) != cudaSuccess) return e;
+  cudaEventRecord(ev[0], s);
+  cudaEvent_t tev[12];
+  int n_tev = 0;
+  auto tmark = [&]() {
+    if (trace && n_tev < 12) {
+      cudaEventCreate(&tev[n_tev]);
+      cudaEventRecord(tev[n_tev++], s);
+    }
+  };
+  tmark();
 
-  // 1. sample pass on a prefix of the corpus (exact, bit-identical scores)
-  PdxView prefix = v;
-  prefix.n = p.n_s;
-  e = launch_pdx_knn(prefix, mode, dev_queries, nq, k, skeys, ws, s, launches);
-  if (e != cudaSuccess) return e;
-  mark(1);
-  // 2. operands and thresholds
-  knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine,
-                                                      qhi, qlo, qnorm);
-  knn_tc_threshold_kernel<<<(p.nq_pad + 127) / 128, 128, 0, s>>>(skeys, (unsigned)nq, p.nq_pad, (unsigned)k, cosine, qnorm,
-                                                                 dev_max_norm_bits, thr);
-  e = cudaMemsetAsync(cnt, 0, (size_t)p.nq_pad * 4, s);
-  if (e != cudaSuccess) return e;
-  *launches += 2;
-  CUtensorMap tm_qhi, tm_qlo;
-  if (!make_tmap_f32_rows(&tm_qhi, qhi, p.nq_pad, p.d_pad, QT) || !make_tmap_f32_rows(&tm_qlo, qlo, p.nq_pad, p.d_pad, QT))
-    return cudaErrorInvalidValue;
-  mark(2);
-  // 3. tensor-core filter
+  // 1. operands, first-pass thresholds, zeroed counters
+  knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, qh,
+                                                      qflag, thr, cnt);
+  ++*launches;
+  CUtensorMap tm_q;
+  if (!make_tmap_f16_rows(&tm_q, qh, p.nq_pad, p.d_pad, p.d_pad, QT)) return cudaErrorInvalidValue;
+  tmark();
+
+  // 2. filter passes over growing prefixes
   static bool attr_set = false;
   const size_t smem = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
   if (!attr_set) {
@@ -444,63 +502,90 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_x, int mod
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  size_t levels[4];
+  int n_levels = 0;
+  {
+    size_t cur = CAND_CAP < v.n ? CAND_CAP : v.n;
+    levels[n_levels++] = cur;
+    const size_t mids[2] = {v.n / 512, v.n / 16};
+    for (size_t nx : mids)
+      if (nx >= 4 * cur) {
+        cur = (nx + VT - 1) / VT * VT;
+        levels[n_levels++] = cur;
+      }
+    if (v.n > cur) levels[n_levels++] = v.n;
+  }
   KtArgs a{};
-  a.n = (unsigned)v.n;
-  a.d = (unsigned)v.d;
-  a.n_vtiles = (unsigned)((v.n + VT - 1) / VT);
-  a.n_qgroups = p.nq_pad / QT;
-  a.kblocks = p.d_pad / KB;
-  a.index_base = v.index_base;
+  a.n_qgroups = (p.nq_pad + QT - 1) / QT;
+  a.kblocks = (p.d_pad + KB - 1) / KB;
+  a.nq_pad = p.nq_pad;
   a.cosine = cosine;
-  a.inv_norms = dev_inv_norms;
+  a.eps = 1.05e-3f + 3.5e-7f * (float)v.d;
+  a.norms = dev_norms;
   a.thr = thr;
   a.cand_count = cnt;
-  a.cand = cand;
-  a.cap = (unsigned)knn_tc_cap();
-  unsigned grid = (unsigned)ws.num_sms;
-  if (grid > a.n_vtiles) grid = a.n_vtiles;
-  knn_tc_filter_kernel<<<grid, KT_THREADS, smem, s>>>(tm_x, tm_qhi, tm_qlo, a);
-  ++*launches;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  mark(3);
-  // 4. exact rescoring + selection
+  a.cand_idx = cand_idx;
+  a.cand_lb = cand_lb;
+  for (int l = 0; l < n_levels; ++l) {
+    const bool last = l == n_levels - 1;
+    a.n_rows = (unsigned)levels[l];
+    const unsigned long long units = (unsigned long long)((a.n_rows + VT - 1) / VT) * a.n_qgroups;
+    unsigned grid = (unsigned)ws.num_sms;
+    if (grid > units) grid = (unsigned)units;
+    if (last) cudaEventRecord(ev[1], s);
+    knn_tc_filter_kernel<<<grid, KT_THREADS, smem, s>>>(tm_xh, tm_q, a);
+    ++*launches;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (last) {
+      cudaEventRecord(ev[2], s);
+    } else {
+      knn_tc_select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>((unsigned)nq, (unsigned)k, qflag, cnt, cand_lb, thr);
+      ++*launches;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    tmark();
+  }
+  // 3. exact rescoring + selection
   const size_t rs_smem = ((v.d + 3) & ~(size_t)3) * 4 + (size_t)(RS_THREADS / 32) * k * 8;
   knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
-                                                                     dev_queries, cosine, cnt, cand, a.cap, (int)k, dev_keys);
+                                                                     dev_queries, cosine, qflag, cnt, cand_idx, (int)k, dev_keys);
   ++*launches;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  mark(4);
-  // 5. overflowed candidate lists -> the caller re-runs those queries on the exact scan
-  if (host_counts && overflow_queries) {
-    e = cudaMemcpyAsync(host_counts, cnt, nq * 4, cudaMemcpyDeviceToHost, s);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return e;
-    overflow_queries->clear();
-    for (size_t q = 0; q < nq; ++q)
-      if (host_counts[q] > a.cap) overflow_queries->push_back((unsigned)q);
-    if (trace) {
-      float t[4];
-      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
-      unsigned long long tot = 0, mx = 0;
-      for (size_t q = 0; q < nq; ++q) { tot += host_counts[q]; if (host_counts[q] > mx) mx = host_counts[q]; }
-      fprintf(stderr, "[knn_tc] sample(n_s=%u) %.2f ms | prep %.2f | filter %.2f | rescore %.2f | candidates total %llu max %llu overflow %zu\n",
-              p.n_s, t[0], t[1], t[2], t[3], tot, mx, overflow_queries->size());
-      for (auto& x : ev) cudaEventDestroy(x);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  cudaEventRecord(ev[3], s);
+  tmark();
+  // 4. overflowed / unfiltered queries -> the caller re-runs them on the exact scan
+  if ((e = cudaMemcpyAsync(host_counts, cnt, nq * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  overflow_queries->clear();
+  unsigned long long tot = 0, mx = 0;
+  for (size_t q = 0; q < nq; ++q) {
+    if (host_counts[q] > CAND_CAP) {
+      overflow_queries->push_back((unsigned)q);
+    } else {
+      tot += host_counts[q];
+      if (host_counts[q] > mx) mx = host_counts[q];
     }
   }
+  if (stats) {
+    cudaEventElapsedTime(&stats->filter_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&stats->total_ms, ev[0], ev[3]);
+    stats->filter_flops = 2.0 * (double)((v.n + VT - 1) / VT * VT) * (double)(a.kblocks * KB) * (double)p.nq_pad;
+    stats->candidates = tot;
+    stats->overflowed = (unsigned)overflow_queries->size();
+    stats->passes = n_levels;
+    if (trace) {
+      fprintf(stderr, "[knn_tc] passes %d | final filter %.3f ms | whole call %.3f ms | candidates total %llu max %llu | exact-scan queries %zu | phases (prep, passes.., rescore):",
+              n_levels, stats->filter_ms, stats->total_ms, tot, mx, overflow_queries->size());
+      for (int i = 0; i + 1 < n_tev; ++i) {
+        float t = 0;
+        cudaEventElapsedTime(&t, tev[i], tev[i + 1]);
+        fprintf(stderr, " %.3f", t);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  for (int i = 0; i < n_tev; ++i) cudaEventDestroy(tev[i]);
   return cudaSuccess;
-}
-
-cudaError_t launch_knn_tc_inv_norms(const float* dev_norms, size_t n, float* dev_inv, unsigned* dev_max_bits, cudaStream_t s,
-                                    uint64_t* launches) {
-  cudaError_t e = cudaMemsetAsync(dev_max_bits, 0, 4, s);
-  if (e != cudaSuccess) return e;
-  knn_tc_inv_norms_kernel<<<148 * 4, 256, 0, s>>>(dev_norms, (unsigned)n, dev_inv, dev_max_bits);
-  ++*launches;
-  return cudaGetLastError();
 }
 
 }  // namespace innr

@@ -437,31 +437,49 @@ def test_full_size_c4_c5_properties(ib, oracle):
 
 
 # ------------------------------------------------------------------------------------------------ tensor-core filter path
-@pytest.mark.parametrize("n,d,nq", [(20_000, 768, 64), (50_000, 100, 40), (8_192, 32, 130), (33_000, 8, 33)])
-def test_knn_tc_filter_path_is_exact(ib, oracle, n, d, nq):
-    """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
-    result bit-identical to the reference (indices AND scores), including a zero query, a zero vector, duplicates."""
+@pytest.fixture
+def tc_small(ib):
     ib.set_option("knn_tc_min_n", 4096)       # exercise the tensor-core path at test sizes
     ib.set_option("knn_tc_min_queries", 32)
+    yield ib
+    ib.set_option("knn_tc_min_n", 100000)
+
+
+@pytest.mark.parametrize("n,d,nq", [(20_000, 768, 64), (50_000, 100, 40), (8_192, 32, 130), (33_000, 8, 33),
+                                    (300_000, 64, 272)])
+def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
+    """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
+    result bit-identical to the reference (indices AND scores), including zero / tiny / huge vectors and queries,
+    duplicates (ties -> lower index first) and queries the filter hands to the exact scan."""
+    ib = tc_small
     rows = rand_rows(n, d, n + d)
     rows[17] = 0.0                      # zero-norm vector -> cosine 0.0
     rows[100] = rows[200] = rows[300]   # exact duplicates -> ties -> lower index first
+    rows[400:420] *= np.float32(1e-6)   # norms spread over many orders of magnitude (dot ranking != cosine ranking)
+    rows[420:440] *= np.float32(1e5)
+    rows[440] *= np.float32(1e-12)      # below the reference's 1e-9 cosine guard -> cosine 0.0, dot tiny
+    rows[441] *= np.float32(1e-30)      # denormal range
     qs = rand_rows(nq, d, 99)
-    qs[3] = 0.0                         # zero-norm query -> every cosine 0.0 -> first k indices (overflow fallback)
+    qs[3] = 0.0                         # zero-norm query -> every cosine 0.0 -> first k indices (exact-scan fallback)
     qs[5] = rows[300] * 2.0             # query parallel to the duplicates
+    qs[6] *= np.float32(1e-12)          # below the cosine guard
+    qs[7] *= np.float32(1e6)
+    qs[8] = -rows[421]                  # antiparallel to a huge vector
     gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
     for metric in ("cosine", "dot"):
         for k in (1, 10, 32):
             idx, sc = ib.batch_knn_many(metric, qs, gb, k)
+            st = ib.knn_tc_last_stats()
+            assert st["passes"] >= 2 and st["exact_scan_queries"] <= 4, st   # the filter really answered the batch
             widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
             assert np.array_equal(idx, widx), (metric, k, np.argwhere(idx != widx)[:5])
             assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
-    ib.set_option("knn_tc_min_n", 100000)
 
 
-def test_knn_tc_on_the_reference_lattice(ib, oracle):
-    """The G-ref lattice has near-ties below f32 resolution: the adversarial case for a TF32 filter."""
-    ib.set_option("knn_tc_min_n", 4096)
+def test_knn_tc_on_the_reference_lattice(tc_small, oracle):
+    """The G-ref lattice has near-ties below f32 resolution: the adversarial case for a low-precision
+    filter (many pairs inside the error band -> long candidate lists or the exact-scan fallback; never a wrong answer)."""
+    ib = tc_small
     n, d, nq, k = 30_000, 128, 64, 10
     dev = ib.DeviceBatch.generate("gref", 0, 0, n, d)
     rows = np.stack([oracle.generate_embedding(d, i) for i in range(n)])
@@ -471,4 +489,25 @@ def test_knn_tc_on_the_reference_lattice(ib, oracle):
         idx, sc = ib.batch_knn_many(metric, qs, dev, k)
         widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
         assert np.array_equal(idx, widx) and np.array_equal(bits(sc), bits(wsc)), metric
-    ib.set_option("knn_tc_min_n", 100000)
+
+
+def test_knn_tc_non_finite_inputs_fall_back_to_the_exact_scan(tc_small, oracle):
+    """A corpus with a non-finite norm never takes the filter path; a non-finite query is answered by the exact scan.
+    Scores compare with same_scores (NaN sign is not portable)."""
+    ib = tc_small
+    n, d, nq, k = 9_000, 48, 40, 10
+    rows = rand_rows(n, d, 5)
+    qs = rand_rows(nq, d, 6)
+    qs[2, 7] = np.inf
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    idx, sc = ib.batch_knn_many("dot", qs, gb, k)
+    assert ib.knn_tc_last_stats()["exact_scan_queries"] == 1
+    widx, wsc = oracle.batch_knn_many("dot", qs, ob, k, n_threads=8)
+    fin = np.isfinite(wsc).all(axis=1)
+    assert np.array_equal(idx[fin], widx[fin]) and same_scores(sc, wsc)
+    rows[123, 4] = np.inf               # corpus with a non-finite vector: exact scan for everything
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    qs = rand_rows(nq, d, 7)
+    idx, sc = ib.batch_knn_many("dot", qs, gb, k)   # +-inf scores order identically everywhere (cosine would be NaN)
+    widx, wsc = oracle.batch_knn_many("dot", qs, ob, k, n_threads=8)
+    assert np.array_equal(idx, widx) and same_scores(sc, wsc)
