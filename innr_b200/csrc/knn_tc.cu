@@ -12,7 +12,7 @@
 //                       A pass over rows [0, n_i) appends (index, lower bound) of every pair whose UPPER bound reaches
 //                       the query's threshold; the k-th largest LOWER bound of the appended pairs is a valid lower
 //                       bound of the reference's k-th best score and becomes the threshold of the next, larger pass
-//                       (n_0 = 4096 rows with threshold -inf, then n/512, n/16, n). No exact sample scan is needed.
+//                       (n_0 = 4096 rows, every pair kept, then n/128, n/16, n). No exact sample scan is needed.
 //   3. rescore          the final candidates (~20 k per query) are re-scored with the reference's exact sequential
 //                       f32 arithmetic and selected on the same 64-bit keys as the scan kernel -> indices and scores
 //                       bit-identical to batch_knn_dot / batch_knn_cosine. A query whose final list overflows, or
@@ -65,6 +65,7 @@ struct KtArgs {
   unsigned n_rows;          // rows [0, n_rows) of the corpus are filtered by this pass
   unsigned n_qgroups, kblocks, nq_pad;
   int cosine;
+  int dense;                // first pass (threshold -inf, n_rows <= CAND_CAP): slot = row, no counters
   float eps;
   const float* norms;       // exact ||x|| per vector
   const float* thr;         // nq_pad thresholds (+inf: accept nothing)
@@ -194,6 +195,18 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
           tc_fence_before_sync();
           if (lane == 0) mbar_arrive(&st->acc_empty[ab]);
         }
+        if (a.dense) {  // every pair is kept: lower bound to slot v of its query, no atomics (the counters are preset)
+          if (vvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < qt_u) {
+                const size_t o = (size_t)(qg * QT + c0 + j) * CAND_CAP + v;
+                a.cand_idx[o] = v;
+                a.cand_lb[o] = fmaf(__uint_as_float(r[j]), rn, -e);
+              }
+          }
+          continue;
+        }
         const float4* t4 = reinterpret_cast<const float4*>(&st->thr[ab][c0]);
         bool any = false;
 #pragma unroll
@@ -204,22 +217,20 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
           any |= fmaf(__uint_as_float(r[4 * j4 + 2]), rn, e) >= t.z;
           any |= fmaf(__uint_as_float(r[4 * j4 + 3]), rn, e) >= t.w;
         }
-        if (__any_sync(FULL_MASK, any && vvalid)) {  // rare (except in the first, dense pass): warp-aggregated appends
+        if (any && vvalid) {  // rare except in the first, dense pass. All atomics of the lane are issued before any
+                              // of their results is used, so their round trips overlap.
+          unsigned pos[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float sr = __uint_as_float(r[j]);
-            const bool hit = vvalid && (fmaf(sr, rn, e) >= st->thr[ab][c0 + j]);
-            const unsigned m = __ballot_sync(FULL_MASK, hit);
-            if (m) {
-              const unsigned q = qg * QT + c0 + j;
-              unsigned base = 0;
-              if (lane == __ffs(m) - 1) base = atomicAdd(&a.cand_count[q], (unsigned)__popc(m));
-              base = __shfl_sync(FULL_MASK, base, __ffs(m) - 1);
-              const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
-              if (hit && pos < CAND_CAP) {
-                a.cand_idx[(size_t)q * CAND_CAP + pos] = v;
-                a.cand_lb[(size_t)q * CAND_CAP + pos] = fmaf(sr, rn, -e);
-              }
+            const bool hit = (c0 + j < qt_u) && fmaf(__uint_as_float(r[j]), rn, e) >= st->thr[ab][c0 + j];
+            pos[j] = hit ? atomicAdd(&a.cand_count[qg * QT + c0 + j], 1u) : 0xFFFFFFFFu;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (pos[j] < CAND_CAP) {
+              const size_t o = (size_t)(qg * QT + c0 + j) * CAND_CAP + pos[j];
+              a.cand_idx[o] = v;
+              a.cand_lb[o] = fmaf(__uint_as_float(r[j]), rn, -e);
             }
           }
         }
@@ -268,7 +279,7 @@ __global__ void knn_tc_build_xh_kernel(const float* __restrict__ pdx, size_t ld,
 __global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned nq, unsigned d, unsigned nq_pad,
                                            unsigned d_pad, int cosine, __half* __restrict__ qh,
                                            unsigned* __restrict__ qflag, float* __restrict__ thr,
-                                           unsigned* __restrict__ cand_count) {
+                                           unsigned* __restrict__ cand_count, unsigned first_pass_rows) {
   const unsigned row = blockIdx.x;
   __shared__ float s_inv;
   __shared__ unsigned s_bad;
@@ -288,8 +299,8 @@ __global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned
     s_inv = inv;
     s_bad = bad;
     qflag[row] = bad;
-    thr[row] = (row < nq && !bad) ? -INFINITY : INFINITY;  // first pass: everything / nothing
-    cand_count[row] = 0;
+    thr[row] = INFINITY;                // queries the filter does not answer keep +inf (accept nothing) in every pass
+    cand_count[row] = first_pass_rows;  // the dense first pass stores the pair (q, row v) in slot v
   }
   __syncthreads();
   const float inv = s_inv;
@@ -333,14 +344,16 @@ template <int R>
 __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float* __restrict__ data, size_t ld, unsigned n,
                                                                     unsigned d, unsigned index_base,
                                                                     const float* __restrict__ queries, int cosine,
+                                                                    float eps, const float* __restrict__ norms,
                                                                     const unsigned* __restrict__ qflag,
                                                                     unsigned* __restrict__ cand_count,
-                                                                    const unsigned* __restrict__ cand, int k,
+                                                                    const unsigned* __restrict__ cand,
+                                                                    const float* __restrict__ cand_lb, int k,
                                                                     uint64_t* __restrict__ out_keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(sq + ((d + 3) & ~3u));
-  __shared__ float s_qn;
+  __shared__ float s_qn, s_bound;
   const unsigned q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (qflag[q]) {  // not filtered: reported as overflowed so that the caller runs the exact scan for it
@@ -353,22 +366,60 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
     for (unsigned i = 0; i < d; ++i) ss = __fadd_rn(ss, __fmul_rn(queries[(size_t)q * d + i], queries[(size_t)q * d + i]));
     s_qn = __fsqrt_rn(ss);
   }
-  __syncthreads();
-  const float qn = s_qn;
   unsigned cnt = cand_count[q];
   if (cnt > CAND_CAP) cnt = CAND_CAP;
+  const unsigned cnt_round = (cnt + 31u) / 32u * 32u;
+  // 1. the k-th largest lower bound of the final candidates bounds the k-th best score from below: only candidates
+  //    whose upper bound reaches it can be in the result (typically 10-20 of a few hundred)
+  {
+    WarpList<R> lbs;
+    lbs.init();
+    uint64_t t = KEY_SENTINEL;
+    for (unsigned c = threadIdx.x; c < cnt_round; c += blockDim.x) {
+      const bool valid = c < cnt;
+      const float lb = valid ? cand_lb[(size_t)q * CAND_CAP + c] : 0.0f;
+      lbs.offer(make_key_desc(lb, c), valid, t, k, lane);
+    }
+    block_tree_merge<R>(lbs, k, smem_keys);
+    if (warp == 0) {
+      const uint64_t kth = lbs.at(k - 1);
+      if (lane == 0)
+        s_bound = (kth == KEY_SENTINEL) ? -INFINITY : __uint_as_float(order_bits_to_f32_bits(~(uint32_t)(kth >> 32)));
+    }
+  }
+  __syncthreads();
+  const float qn = s_qn, bound = s_bound;
+  // 2. exact scores of the survivors, selection on the scan kernel's keys
   WarpList<R> list;
   list.init();
   uint64_t thr = KEY_SENTINEL;
-  const unsigned cnt_round = (cnt + 31u) / 32u * 32u;
   for (unsigned c = threadIdx.x; c < cnt_round; c += blockDim.x) {
-    const bool valid = c < cnt;
+    bool valid = c < cnt;
     uint64_t key = KEY_SENTINEL;
+    unsigned i = 0;
     if (valid) {
-      const unsigned i = cand[(size_t)q * CAND_CAP + c];
+      i = cand[(size_t)q * CAND_CAP + c];
+      const float lb = cand_lb[(size_t)q * CAND_CAP + c];
+      const float nv = norms[i];
+      const float e = cosine ? (nv > COS_NORM_EPS ? eps : 0.0f) : (eps * (nv >= TINY_NORM ? nv : 0.0f) + 1e-18f);
+      const float ub = fmaf(2.0f, e, lb) + 1e-6f * (fabsf(lb) + e);  // the filter's upper bound, rounding included
+      valid = ub >= bound;
+    }
+    if (valid) {
       const float* p = data + i;
       float acc = 0.0f, ss = 0.0f;
-      for (unsigned dd = 0; dd < d; ++dd) {  // the reference's sequential unfused sums (src/batch.rs:290-296, 676-681)
+      unsigned dd = 0;
+      for (; dd + 8 <= d; dd += 8) {  // the reference's sequential unfused sums (src/batch.rs:290-296, 676-681)
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(dd + u) * ld);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc = __fadd_rn(acc, __fmul_rn(sq[dd + u], v[u]));
+          ss = __fadd_rn(ss, __fmul_rn(v[u], v[u]));
+        }
+      }
+      for (; dd < d; ++dd) {
         const float v = __ldg(p + (size_t)dd * ld);
         acc = __fadd_rn(acc, __fmul_rn(sq[dd], v));
         ss = __fadd_rn(ss, __fmul_rn(v, v));
@@ -488,7 +539,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
 
   // 1. operands, first-pass thresholds, zeroed counters
   knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, qh,
-                                                      qflag, thr, cnt);
+                                                      qflag, thr, cnt, (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n));
   ++*launches;
   CUtensorMap tm_q;
   if (!make_tmap_f16_rows(&tm_q, qh, p.nq_pad, p.d_pad, p.d_pad, QT)) return cudaErrorInvalidValue;
@@ -507,7 +558,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   {
     size_t cur = CAND_CAP < v.n ? CAND_CAP : v.n;
     levels[n_levels++] = cur;
-    const size_t mids[2] = {v.n / 512, v.n / 16};
+    const size_t mids[2] = {v.n / 128, v.n / 16};
     for (size_t nx : mids)
       if (nx >= 4 * cur) {
         cur = (nx + VT - 1) / VT * VT;
@@ -529,6 +580,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   for (int l = 0; l < n_levels; ++l) {
     const bool last = l == n_levels - 1;
     a.n_rows = (unsigned)levels[l];
+    a.dense = l == 0;
     const unsigned long long units = (unsigned long long)((a.n_rows + VT - 1) / VT) * a.n_qgroups;
     unsigned grid = (unsigned)ws.num_sms;
     if (grid > units) grid = (unsigned)units;
@@ -548,7 +600,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   // 3. exact rescoring + selection
   const size_t rs_smem = ((v.d + 3) & ~(size_t)3) * 4 + (size_t)(RS_THREADS / 32) * k * 8;
   knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
-                                                                     dev_queries, cosine, qflag, cnt, cand_idx, (int)k, dev_keys);
+                                                                     dev_queries, cosine, a.eps, dev_norms, qflag, cnt, cand_idx, cand_lb,
+                                                                     (int)k, dev_keys);
   ++*launches;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(ev[3], s);
