@@ -16,43 +16,67 @@
 // with separately rounded multiply and add. fmaf on the GPU is IEEE-exact, so one thread holding the 32 chains
 // of one vector reproduces the CPU result bit for bit.
 //
-// Device layout: 16-byte chunks (16 dimensions), chunk-major: codes[c * ld + i]. One thread owns one vector; a
-// warp load is 512 contiguous bytes. u8 -> f32 is exact via the 2^23 magic number (PRMT + FADD, no I2F).
+// Device layout: 16-byte chunks (16 dimensions), chunk-major: codes[c * ld + i]. One thread owns one vector.
+// The chunk rows of a 256-vector tile (4 KB each, contiguous) are staged through a shared-memory ring by a producer
+// warp with cp.async.bulk + mbarriers (16 KB stages, 6 deep), so the bytes in flight towards HBM do not depend on
+// registers; consumers read their 16 bytes per chunk with one conflict-free LDS.128.
+// u8 -> f32 is exact via the 2^23 magic number (PRMT + FADD, no I2F); the subtraction and the FMA chains run as
+// packed FADD2 / FFMA2 (two IEEE-exact f32 operations per instruction: 2.3 instructions per byte instead of 3.3).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace innr {
 
 namespace {
 
-constexpr int U8_THREADS = 256;
+constexpr int U8_THREADS = 256;            // consumer threads = vectors per tile
+constexpr int U8_CTA = U8_THREADS + 32;     // + one producer warp
+constexpr int U8_STAGE_CHUNKS = 4;          // chunk rows per stage (even: chunk parity selects the accumulator half)
+constexpr int U8_STAGES = 6;
+constexpr int U8_ROW_BYTES = U8_THREADS * 16;
+constexpr int U8_STAGE_BYTES = U8_STAGE_CHUNKS * U8_ROW_BYTES;  // 16 KB
 
 // The 2^23 magic constant is kept in a register the compiler cannot see through, so that PRMT takes the byte
 // selector as its immediate operand (with a literal constant the selector is re-materialised by a MOV per byte).
 // (An asm mov is folded by ptxas too, so the value travels as a kernel argument: U8Args::magic.)
-#ifndef INNR_U8_I2F
-#define INNR_U8_I2F 0
-#endif
+__device__ __forceinline__ float byte_to_f32_biased(unsigned word, int k, unsigned magic) {
+  // bytes: [b_k, 0x00, 0x00, 0x4B] = 2^23 + b_k as f32
+  return __uint_as_float(__byte_perm(word, magic, 0x7440u | (unsigned)k));
+}
 __device__ __forceinline__ float byte_to_f32(unsigned word, int k, unsigned magic) {
-#if INNR_U8_I2F
-  (void)magic;
-  return __uint2float_rn((word >> (8 * k)) & 0xFFu);  // I2F.F32.U8 with a byte selector
-#else
-  // bytes: [b_k, 0x00, 0x00, 0x4B] = 2^23 + b_k as f32; subtracting 2^23 is exact
-  unsigned bits = __byte_perm(word, magic, 0x7440u | (unsigned)k);
-  return __fsub_rn(__uint_as_float(bits), 8388608.0f);
-#endif
+  return __fsub_rn(byte_to_f32_biased(word, k, magic), 8388608.0f);  // subtracting 2^23 is exact
 }
 
+// packed f32x2 (sm_100): two independent IEEE round-to-nearest operations per instruction
+__device__ __forceinline__ void add2(float& x0, float& x1, float c) {
+  uint64_t x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(y) : "f"(c));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+}
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t d, a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
+// 16 FMA chains advance by one element each: acc[j] = fma(q[j], float(byte j of v), acc[j])
 __device__ __forceinline__ void fma16(const uint4 v, const float* __restrict__ q, float* acc, unsigned magic) {
   const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 qv = *reinterpret_cast<const float4*>(q + 4 * g);  // 16-byte aligned by construction
-    acc[4 * g + 0] = fmaf(qv.x, byte_to_f32(w[g], 0, magic), acc[4 * g + 0]);
-    acc[4 * g + 1] = fmaf(qv.y, byte_to_f32(w[g], 1, magic), acc[4 * g + 1]);
-    acc[4 * g + 2] = fmaf(qv.z, byte_to_f32(w[g], 2, magic), acc[4 * g + 2]);
-    acc[4 * g + 3] = fmaf(qv.w, byte_to_f32(w[g], 3, magic), acc[4 * g + 3]);
+    float x0 = byte_to_f32_biased(w[g], 0, magic), x1 = byte_to_f32_biased(w[g], 1, magic);
+    float x2 = byte_to_f32_biased(w[g], 2, magic), x3 = byte_to_f32_biased(w[g], 3, magic);
+    add2(x0, x1, -8388608.0f);
+    add2(x2, x3, -8388608.0f);
+    fma2(acc[4 * g + 0], acc[4 * g + 1], qv.x, qv.y, x0, x1);
+    fma2(acc[4 * g + 2], acc[4 * g + 3], qv.z, qv.w, x2, x3);
   }
 }
 
@@ -62,60 +86,28 @@ __device__ __forceinline__ float hsum8(const float* v) {  // src/arch/x86_64.rs:
   return __fadd_rn(__fadd_rn(s0, s2), __fadd_rn(s1, s3));
 }
 
-// mixed_dot_u8_f32 of the smem query against the vector whose chunk 0 is at p
-__device__ __forceinline__ float mixed_dot(const uint4* __restrict__ p, size_t ld, unsigned d, unsigned chunks,
-                                           const float* __restrict__ sq, const unsigned magic) {
+// Everything after the 32-wide main loop: combine the 32 chains, 8-wide remainder chains, scalar tail; or the
+// portable sequential sum when d < 16. w = the (up to) two chunks after the main loop, zero padded.
+__device__ __forceinline__ float mixed_dot_finish(const float* acc, const unsigned* w, unsigned d,
+                                                  const float* __restrict__ sq, const unsigned magic) {
   if (d == 0) return 0.0f;
   if (d < 16) {  // portable path: sequential unfused sum (src/scalar.rs:353-358)
-    uint4 v = ldg_stream_u4(p);
-    const unsigned w[4] = {v.x, v.y, v.z, v.w};
     float s = 0.0f;
 #pragma unroll
     for (int e = 0; e < 16; ++e)
       if ((unsigned)e < d) s = __fadd_rn(s, __fmul_rn(sq[e], byte_to_f32(w[e >> 2], e & 3, magic)));
     return s;
   }
-  float acc[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
-  const unsigned chunks32 = d / 32;
-  unsigned b = 0;
-  for (; b + 2 <= chunks32; b += 2) {  // 64 dimensions per iteration, 4 loads in flight
-    uint4 v0 = ldg_stream_u4(p + (size_t)(2 * b) * ld);
-    uint4 v1 = ldg_stream_u4(p + (size_t)(2 * b + 1) * ld);
-    uint4 v2 = ldg_stream_u4(p + (size_t)(2 * b + 2) * ld);
-    uint4 v3 = ldg_stream_u4(p + (size_t)(2 * b + 3) * ld);
-    fma16(v0, sq + 32 * b, acc, magic);
-    fma16(v1, sq + 32 * b + 16, acc + 16, magic);
-    fma16(v2, sq + 32 * b + 32, acc, magic);
-    fma16(v3, sq + 32 * b + 48, acc + 16, magic);
-  }
-  for (; b < chunks32; ++b) {
-    uint4 v0 = ldg_stream_u4(p + (size_t)(2 * b) * ld);
-    uint4 v1 = ldg_stream_u4(p + (size_t)(2 * b + 1) * ld);
-    fma16(v0, sq + 32 * b, acc, magic);
-    fma16(v1, sq + 32 * b + 16, acc + 16, magic);
-  }
   float all[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     all[j] = __fadd_rn(__fadd_rn(acc[j], acc[8 + j]), __fadd_rn(acc[16 + j], acc[24 + j]));
   float result = hsum8(all);
-
-  // remainder: up to 31 elements in chunks 2*chunks32 (+1); zero padded in memory
-  const unsigned rs = chunks32 * 32, remaining = d - rs, n8 = (remaining / 8) * 8;
+  const unsigned rs = (d / 32) * 32, remaining = d - rs, n8 = (remaining / 8) * 8;
+  if (remaining == 0) return __fadd_rn(result, 0.0f);  // the empty 8-wide accumulator is still added (x86_64.rs:1004-1009)
   float rem[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) rem[j] = 0.0f;
-  unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (remaining > 0) {
-    uint4 v0 = ldg_stream_u4(p + (size_t)(2 * chunks32) * ld);
-    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-    if (remaining > 16) {
-      uint4 v1 = ldg_stream_u4(p + (size_t)(2 * chunks32 + 1) * ld);
-      w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
-    }
-  }
 #pragma unroll
   for (int e = 0; e < 24; ++e)  // 8-wide chunks (at most 3)
     if ((unsigned)e < n8) rem[e & 7] = fmaf(sq[rs + e], byte_to_f32(w[e >> 2], e & 3, magic), rem[e & 7]);
@@ -142,43 +134,123 @@ struct U8Args {
   float* scores_out;
 };
 
-#ifndef INNR_U8_MINB
-#define INNR_U8_MINB 3
-#endif
+struct U8Shared {
+  uint64_t full[U8_STAGES], empty[U8_STAGES];
+};
+
+// bulk copy global -> shared, completion on an mbarrier (complete_tx::bytes); 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
 template <int R, bool KNN>
-__global__ void __launch_bounds__(U8_THREADS, INNR_U8_MINB) u8_scan_kernel(const U8Args a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // [ring: U8_STAGES x 16 KB][query d_pad floats][misc 4 floats][barriers][keys]
+  unsigned char* ring = smem_raw;
   const unsigned d_pad = (a.d + 31) / 32 * 32 + 32;
-  float* sq = reinterpret_cast<float*>(smem_raw);
+  float* sq = reinterpret_cast<float*>(smem_raw + U8_STAGES * U8_STAGE_BYTES);
   float* s_misc = sq + d_pad;  // [0] = query_sum
-  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(s_misc + 4);
-  const int lane = threadIdx.x & 31;
+  U8Shared* st = reinterpret_cast<U8Shared*>(s_misc + 4);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(st + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool producer = warp == U8_THREADS / 32;
   for (unsigned i = threadIdx.x; i < d_pad; i += blockDim.x) sq[i] = i < a.d ? a.query[i] : 0.0f;
   if (threadIdx.x == 0) {  // query_context: query.iter().sum() sequential (src/scalar.rs:236-240)
     float s = 0.0f;
     for (unsigned i = 0; i < a.d; ++i) s = __fadd_rn(s, a.query[i]);
     s_misc[0] = s;
+    for (int sg = 0; sg < U8_STAGES; ++sg) {
+      tc::mbar_init(&st->full[sg], 1);
+      tc::mbar_init(&st->empty[sg], U8_THREADS / 32);
+    }
+    tc::fence_barrier_init();
   }
   __syncthreads();
   const float scale = __fdiv_rn(a.alpha, 255.0f);             // params.alpha / 255.0
   const float bias = __fmul_rn(a.offset, s_misc[0]);          // params.offset * ctx.query_sum
+  const unsigned stages_per_tile = (a.chunks + U8_STAGE_CHUNKS - 1) / U8_STAGE_CHUNKS;
+  const unsigned main_chunks = (a.d >= 16) ? (a.d / 32) * 2 : 0;  // chunks consumed by the 32-wide loop
 
   WarpList<R> lists[1];
   uint64_t thrs[1];
   lists[0].init();
   thrs[0] = KEY_SENTINEL;
 
-  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const unsigned i = tile * U8_THREADS + threadIdx.x;
-    const bool valid = i < a.n;
-    float score = 0.0f;
-    if (valid) {
-      float mixed = mixed_dot(a.data + i, a.ld, a.d, a.chunks, sq, a.magic);
-      score = (KNN || a.mode == 1) ? __fadd_rn(__fmul_rn(scale, mixed), bias) : mixed;  // src/scalar.rs:299
+  if (producer) {
+    if (lane == 0) {
+      unsigned slot = 0, phase = 1;  // the first pass over the ring finds every slot free
+      for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const unsigned long long col = (unsigned long long)tile * U8_THREADS;
+        const unsigned long long left = a.ld - col;  // vectors of this tile inside the row pitch (multiple of 16)
+        const unsigned row_bytes = (unsigned)(left < U8_THREADS ? left : U8_THREADS) * 16u;
+        for (unsigned sgi = 0; sgi < stages_per_tile; ++sgi) {
+          const unsigned c0 = sgi * U8_STAGE_CHUNKS;
+          const unsigned rows = min((unsigned)U8_STAGE_CHUNKS, a.chunks - c0);
+          while (!tc::mbar_try_wait(&st->empty[slot], phase)) __nanosleep(64);  // do not steal issue slots while full
+          tc::mbar_arrive_expect_tx(&st->full[slot], rows * row_bytes);
+          for (unsigned r = 0; r < rows; ++r)
+            bulk_load(ring + slot * U8_STAGE_BYTES + r * U8_ROW_BYTES, a.data + (size_t)(c0 + r) * a.ld + col, row_bytes,
+                      &st->full[slot]);
+          if (++slot == U8_STAGES) { slot = 0; phase ^= 1; }
+        }
+      }
     }
-    if (KNN) lists[0].offer(make_key_desc(score, a.index_base + i), valid, thrs[0], a.k, lane);
-    else if (valid) a.scores_out[i] = score;
+  } else {
+    const unsigned full_stages = main_chunks / U8_STAGE_CHUNKS;  // stages made of main-loop chunks only
+    unsigned slot = 0, phase = 0;
+    const uint4* const ring_v = reinterpret_cast<const uint4*>(ring) + threadIdx.x;
+    for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const unsigned i = tile * U8_THREADS + threadIdx.x;
+      const bool valid = i < a.n;
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+      unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      unsigned sgi = 0;
+      const float* qp = sq;
+      for (; sgi < full_stages; ++sgi, qp += 16 * U8_STAGE_CHUNKS) {
+        tc::mbar_wait(&st->full[slot], phase);
+        const uint4* sv = ring_v + slot * (U8_STAGE_BYTES / 16);
+        uint4 v[U8_STAGE_CHUNKS];
+#pragma unroll
+        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) v[g] = sv[g * U8_THREADS];
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&st->empty[slot]);  // the slot is in registers: the producer may refill it
+        if (++slot == U8_STAGES) { slot = 0; phase ^= 1; }
+#pragma unroll
+        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) fma16(v[g], qp + 16 * g, acc + 16 * (g & 1), a.magic);
+      }
+      for (; sgi < stages_per_tile; ++sgi) {  // last stage(s): remainder chunks (d % 64 != 0), or everything when d < 16
+        const unsigned c0 = sgi * U8_STAGE_CHUNKS;
+        tc::mbar_wait(&st->full[slot], phase);
+        const uint4* sv = ring_v + slot * (U8_STAGE_BYTES / 16);
+        uint4 v[U8_STAGE_CHUNKS];
+#pragma unroll
+        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) v[g] = sv[g * U8_THREADS];  // rows past `chunks`: stale, unused
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&st->empty[slot]);
+        if (++slot == U8_STAGES) { slot = 0; phase ^= 1; }
+#pragma unroll
+        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) {
+          const unsigned c = c0 + g;
+          if (c < main_chunks) {
+            fma16(v[g], sq + 16 * c, acc + 16 * (g & 1), a.magic);
+          } else if (c < a.chunks) {  // the (up to) two chunks of the remainder / of the d < 16 path
+            if (c == main_chunks) { w[0] = v[g].x; w[1] = v[g].y; w[2] = v[g].z; w[3] = v[g].w; }
+            else { w[4] = v[g].x; w[5] = v[g].y; w[6] = v[g].z; w[7] = v[g].w; }
+          }
+        }
+      }
+      const float mixed = mixed_dot_finish(acc, w, a.d, sq, a.magic);
+      const float score = (KNN || a.mode == 1) ? __fadd_rn(__fmul_rn(scale, mixed), bias) : mixed;  // src/scalar.rs:299
+      if (KNN) lists[0].offer(make_key_desc(score, a.index_base + i), valid, thrs[0], a.k, lane);
+      else if (valid) a.scores_out[i] = score;
+    }
   }
+  // the producer warp takes part in the CTA-wide merge with an empty list
   if (KNN) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
@@ -239,7 +311,8 @@ __global__ void quantize_u8_kernel(const float* __restrict__ values, size_t n, f
 
 size_t u8_smem(size_t d, size_t k, bool knn) {
   size_t d_pad = (d + 31) / 32 * 32 + 32;
-  return (d_pad + 4) * sizeof(float) + (knn ? (size_t)(U8_THREADS / 32) * k * sizeof(uint64_t) : 0);
+  return (size_t)U8_STAGES * U8_STAGE_BYTES + (d_pad + 4) * sizeof(float) + sizeof(U8Shared) +
+         (knn ? (size_t)(U8_CTA / 32) * k * sizeof(uint64_t) : 0);
 }
 
 template <int R, bool KNN>
@@ -250,11 +323,11 @@ cudaError_t launch_u8(const U8Args& a, size_t smem, int num_sms, cudaStream_t s)
     if (e != cudaSuccess) return e;
   }
   int occ = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, U8_THREADS, smem);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, U8_CTA, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorInvalidConfiguration;
-  unsigned grid = KNN ? balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms) : (a.n_tiles ? a.n_tiles : 1);
-  kern<<<grid, U8_THREADS, smem, s>>>(a);
+  unsigned grid = balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms);  // persistent: the ring stays warm
+  kern<<<grid, U8_CTA, smem, s>>>(a);
   return cudaGetLastError();
 }
 
