@@ -125,7 +125,11 @@ class ClockSampler:
             try:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                self.samples.append((time.perf_counter(), mhz, tuple(n for n, bit in names if mask & bit)))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                except Exception:
+                    watts = None
+                self.samples.append((time.perf_counter(), mhz, tuple(n for n, bit in names if mask & bit), watts))
             except Exception:
                 pass
             time.sleep(0.002)
@@ -141,7 +145,11 @@ class ClockSampler:
                 continue
             rs = tuple(n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
                        if v.lower().startswith("active"))
-            self.samples.append((time.perf_counter(), mhz, rs))
+            try:
+                watts = float(f[3])
+            except ValueError:
+                watts = None
+            self.samples.append((time.perf_counter(), mhz, rs, watts))
 
     def mark_begin(self):
         self.t_begin = time.perf_counter()
@@ -165,7 +173,9 @@ class ClockSampler:
         inside = [s for s in self.samples if lo <= s[0] <= hi]
         sm = [s[1] for s in inside]
         reasons = sorted({r for s in inside for r in s[2]})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+        watts = [s[3] for s in inside if s[3] is not None]
+        return {"power_w_max": max(watts) if watts else None,
+                "sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons, "sampler": self.mode,
                 "window_ms": (hi - lo) * 1e3 if self.t_end else None}
 
@@ -356,7 +366,7 @@ class MaxSim(Workload):
         self.out = self.torch.empty(self.n_local, dtype=self.torch.float32, device=self.dev)
         self.units_per_step = self.n  # docs scored per step by the whole job
         self.kernel_bytes = self.n_local * self.nt * self.dim * 4
-        self.kernel_name = "maxsim_kernel"
+        self.kernel_name = "maxsim_tc_kernel"
         self.launches = 1
         self.h2d, self.d2h = self.nq * self.dim * 4, self.n_local * 4
         self.corpus_gb = self.n * self.nt * self.dim * 4 / 1e9

@@ -65,7 +65,7 @@ struct TcArgs {
   unsigned n_docs, n_q;
   const float* q;
   int cosine;
-  int debug_mode;  // 0 normal; 1 = TMA streaming only; 4 = no epilogue math (profiling aids)
+  int debug_mode;  // 0 normal; 1 = TMA streaming only; 2 = hi pass only; 4 = no epilogue math (profiling aids)
   float* out;
 };
 
@@ -190,10 +190,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           for (int r = 0; r < 129; ++r) mbar_arrive(&st->empty[i % STAGES]);
         }
       }
+      if (a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
+        for (unsigned i = 0; i < n_tiles; ++i) {
+          const int s = i % STAGES;
+          mbar_wait(&st->full[s], (i / STAGES) & 1);
+          mbar_wait(&st->tmem_empty[s], ((i / STAGES) & 1) ^ 1);
+          tc_fence_after_sync();
+          issue_hi(s);
+          umma_commit(&st->empty[s]);
+          umma_commit(&st->tmem_full[s]);
+        }
+      }
       // hi(i) and lo(j) are issued in whatever order their inputs become ready (never block on one while the
       // other could run); lo(j) always follows hi(j) because both accumulate into the same TMEM columns.
       unsigned nh = 0, nl = 0;
-      while (a.debug_mode != 1 && nl < n_tiles) {
+      while (a.debug_mode != 1 && a.debug_mode != 2 && nl < n_tiles) {
         if (nl < nh) {  // lo(nl): the converters have written Xlo of tile nl to TMEM buffer nl % 2
           const int b = nl & 1;
           if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
@@ -224,6 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
       const int s = i % STAGES, b = i & 1;
       mbar_wait(&st->full[s], (i / STAGES) & 1);
+      if (a.debug_mode == 2) { mbar_arrive(&st->empty[s]); continue; }
       mbar_wait(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
       tc_fence_after_sync();
       const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Run on the GPU box (gpurun -- 'bash profiles/capture.sh <tag>'): per workload, the plain bench run, then the ncu launch
+# list (gpu__time_duration.sum, cold-cache + serialised: compare SHARES) and one `ncu --set full` capture of the dominant
+# kernel. Outputs land in gpurun_out/<tag>_*; the summaries worth judging are copied into profiles/ by hand
+# (profiles/summarise.py turns the .ncu-rep files into the CSV rows committed there).
+set -u
+TAG=${1:-r01}
+WORKLOADS=${2:-"knn_cosine_1q hamming u8 maxsim knn_cosine_multi batch_demo"}
+OUT=gpurun_out
+mkdir -p $OUT
+declare -A KERN=( [knn_cosine_1q]=pdx_scan_kernel [hamming]=hamming_kernel [u8]=u8_scan_kernel [maxsim]=maxsim_tc_kernel
+                  [knn_cosine_multi]=knn_tc_filter_kernel [batch_demo]=pdx_scan )
+declare -A COUNT=( [knn_cosine_1q]=2 [hamming]=2 [u8]=2 [maxsim]=2 [knn_cosine_multi]=8 [batch_demo]=2 )
+for w in $WORKLOADS; do
+  CMD="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline"
+  $CMD > $OUT/${TAG}_plain_$w.log 2>&1 || { echo "plain run of $w failed"; tail -5 $OUT/${TAG}_plain_$w.log; continue; }
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_$w.csv $CMD \
+      > $OUT/${TAG}_launches_$w.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:${KERN[$w]} -s 3 -c ${COUNT[$w]} -f -o $OUT/${TAG}_full_$w $CMD \
+      > $OUT/${TAG}_full_$w.log 2>&1
+  echo "$w: done"
+done
+ls -la $OUT | tail -30
