@@ -198,7 +198,7 @@ U8View u8_view(const innr_cuda_corpus* c) {
 }
 TokView tok_view(const innr_cuda_corpus* c) {
   return TokView{(const float*)c->dev, c->dev_offsets, c->n, c->d, c->total_tokens, c->uniform_tokens, c->tmap,
-                 c->tmap_valid};
+                 c->tmap_valid, c->dev_norms};
 }
 
 // Shared tail of every host-facing top-k call: keys device -> pinned -> decode.
@@ -1027,6 +1027,10 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
     CU(cudaMalloc(&c->dev, c->bytes));
     CU(cudaMemcpyAsync(c->dev, tokens, c->bytes, cudaMemcpyHostToDevice, ctx->stream));
     c->tmap_valid = make_token_tmap(&c->tmap, (const float*)c->dev, total, dim);
+    if (c->tmap_valid) {  // token-norm cache of the tcgen05 path (lives with its shard)
+      CU(cudaMalloc((void**)&c->dev_norms, total * sizeof(float)));
+      CU(launch_token_inv_norms((const float*)c->dev, total, dim, c->dev_norms, ctx->stream, &g_launches));
+    }
   }
   if (n_docs) {
     CU(cudaMalloc(&c->dev_offsets, (n_docs + 1) * sizeof(uint64_t)));
@@ -1056,6 +1060,10 @@ int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, 
     CU(cudaMalloc(&c->dev, c->bytes));
     CU(launch_generate_tokens(salt, first_doc * tokens_per_doc, c->total_tokens, dim, (float*)c->dev, ctx->stream, &g_launches));
     c->tmap_valid = make_token_tmap(&c->tmap, (const float*)c->dev, c->total_tokens, dim);
+    if (c->tmap_valid) {
+      CU(cudaMalloc((void**)&c->dev_norms, c->total_tokens * sizeof(float)));
+      CU(launch_token_inv_norms((const float*)c->dev, c->total_tokens, dim, c->dev_norms, ctx->stream, &g_launches));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
   }
   return INNR_OK;

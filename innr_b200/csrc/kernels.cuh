@@ -127,14 +127,17 @@ struct TokView {
   const uint64_t* doc_offsets;  // n_docs + 1 (device)
   size_t n_docs, dim, total_tokens;
   size_t uniform_tokens;        // > 0 when every doc has exactly this many tokens
-  CUtensorMap tmap;             // TMA map over the token matrix (box 32 floats x 128 rows, SWIZZLE_128B)
+  CUtensorMap tmap;             // TMA map over the token matrix (box 32 floats x 32 rows, SWIZZLE_128B)
   bool tmap_valid;
+  const float* inv_norms;       // per token 1/||x|| (0 when ||x||^2 <= 1e-18), computed once at upload; may be null
 };
 // tcgen05 path (maxsim_tc.cu): dim == 128, 1 <= n_q <= 32
 bool maxsim_tc_supported(const TokView& v, size_t n_q);
 cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
                              int num_sms, cudaStream_t s, uint64_t* launches);
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim);
+cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens, size_t dim, float* dev_inv,
+                                   cudaStream_t s, uint64_t* launches);
 cudaError_t launch_generate_tokens(uint64_t salt, uint64_t first_row, size_t n_rows, size_t dim, float* dev_tokens,
                                    cudaStream_t s, uint64_t* launches);
 cudaError_t launch_maxsim(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,

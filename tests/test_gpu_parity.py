@@ -311,6 +311,62 @@ def test_maxsim_colbert_shape_generated(ib, oracle):
         assert float(np.max(rel)) < 1e-5, float(np.max(rel))   # north_star: f32 scores within 1e-5 relative
 
 
+@pytest.mark.parametrize("shape", ["tiny_docs", "one_huge", "mixed", "few_docs", "single_token"])
+@pytest.mark.parametrize("nq", [32, 5])
+def test_maxsim_tc_stream_edges(ib, oracle, shape, nq):
+    """The tcgen05 path (dim 128, <= 32 query tokens) cuts every CTA's range into four document-aligned streams and
+    handles document boundaries inside a 32-token chunk as masked segments: documents shorter than a chunk (many per
+    chunk, with empty ones between), one document longer than many tiles, fewer documents than streams."""
+    dim = 128
+    rng = np.random.default_rng({"tiny_docs": 1, "one_huge": 2, "mixed": 3, "few_docs": 4, "single_token": 5}[shape] + nq)
+    if shape == "tiny_docs":
+        lens = rng.integers(0, 6, size=3000)
+    elif shape == "one_huge":
+        lens = np.array([3, 0, 7001, 2, 0, 0, 45])
+    elif shape == "mixed":
+        lens = np.concatenate([rng.integers(0, 40, size=500), [1500], rng.integers(100, 400, size=40), [0, 0, 1]])
+    elif shape == "few_docs":
+        lens = np.array([200, 31])
+    else:
+        lens = np.array([1])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    toks = rng.standard_normal((int(off[-1]), dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    corpus = ib.TokenCorpus.from_tokens(toks, off, dim)
+    for cos in (False, True):
+        got = ib.maxsim_corpus(q, corpus, cosine=cos)
+        want = oracle.maxsim_corpus(q, toks, off, cosine_flag=cos)
+        scale = _maxsim_scale(q, toks, off) if not cos else np.full(len(lens), float(nq))
+        err = np.abs(got.astype(np.float64) - want)
+        assert np.all(err <= 1e-5 * scale + 1e-6), (shape, cos, int(np.argmax(err - 1e-5 * scale)), float(err.max()))
+        assert np.all(got[lens == 0] == 0.0)
+
+
+def test_maxsim_tc_nan_and_zero_tokens(ib, oracle):
+    """NaN scores never replace the running max (`>` compare, x86_64.rs:135); a document whose every score is NaN sums
+    -inf; zero-norm tokens and zero-norm query tokens give cosine 0.0 (x86_64.rs:781-785)."""
+    dim, nq = 128, 8
+    rng = np.random.default_rng(77)
+    lens = np.array([40, 3, 64, 2])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    toks = rng.standard_normal((int(off[-1]), dim)).astype(np.float32)
+    toks[5, 17] = np.nan            # one NaN token inside doc 0
+    toks[40:43, 0] = np.nan         # doc 1: every token NaN
+    toks[50] = 0.0                  # zero-norm token in doc 2
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    q[3] = 0.0                      # zero-norm query token
+    corpus = ib.TokenCorpus.from_tokens(toks, off, dim)
+    for cos in (False, True):
+        got = ib.maxsim_corpus(q, corpus, cosine=cos)
+        want = oracle.maxsim_corpus(q, toks, off, cosine_flag=cos)
+        for j in (0, 2, 3):
+            assert abs(float(got[j]) - float(want[j])) <= 1e-4 * max(1.0, abs(float(want[j]))), (cos, j, got[j], want[j])
+        if cos:   # cosine of NaN vectors: aa/bb comparisons with NaN are false -> 0.0 per pair
+            assert np.isnan(want[1]) == np.isnan(got[1]) and (np.isnan(want[1]) or got[1] == want[1]), (got[1], want[1])
+        else:
+            assert got[1] == want[1] == -np.inf, (got[1], want[1])
+
+
 # ------------------------------------------------------------------------------------------------ sharding (K10)
 def test_sharded_merge_on_one_gpu(ib, oracle):
     """The multi-rank path emulated as one process over all ranks' data (B200_PROFILING.md: never run ranks that wait
