@@ -271,6 +271,7 @@ int innr_cuda_set_option(const char* name, double value) {
   else if (n == "knn_tc_min_n") g_opt.knn_tc_min_n = (size_t)value;
   else if (n == "knn_tc_min_queries") g_opt.knn_tc_min_queries = (size_t)value;
   else if (n == "maxsim_tc") g_opt.maxsim_tc = value != 0;
+  else if (n == "u8_scaled_chains") u8_set_scaled_chains(value != 0);
   else return fail(INNR_EINVAL, "unknown option: " + n);
   return INNR_OK;
 }

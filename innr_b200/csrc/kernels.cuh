@@ -118,6 +118,7 @@ cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, f
 // mode 0: raw mixed dot, 1: asymmetric score
 cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
                              cudaStream_t s, uint64_t* launches);
+void u8_set_scaled_chains(bool on);  // off = always the de-biasing path (tests compare both)
 cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
                           Workspace& ws, cudaStream_t s, uint64_t* launches);
 

@@ -22,6 +22,8 @@
 // registers; consumers read their 16 bytes per chunk with one conflict-free LDS.128.
 // u8 -> f32 is exact via the 2^23 magic number (PRMT + FADD, no I2F); the subtraction and the FMA chains run as
 // packed FADD2 / FFMA2 (two IEEE-exact f32 operations per instruction: 2.3 instructions per byte instead of 3.3).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -65,16 +67,30 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 
-// 16 FMA chains advance by one element each: acc[j] = fma(q[j], float(byte j of v), acc[j])
+// 16 FMA chains advance by one element each: acc[j] = fma(q[j], float(byte j of v), acc[j]).
+// SCALED: the byte enters as the f32 whose BITS are the byte (= b * 2^-149, exact) and the query was pre-multiplied by
+// 2^126, so the whole chain runs scaled by 2^-23 and needs no de-biasing FADD: PRMT + FFMA2 only (1.75 instructions
+// per byte instead of 2.3). Rounding commutes with the power-of-two scale as long as no intermediate leaves the
+// normal range, which the kernel guarantees by taking this path only when every query element is 0 or in
+// [2^-80, 4): all partial sums are then multiples of 2^-103, i.e. normal (>= 2^-126) after scaling, or zero.
+template <bool SCALED>
 __device__ __forceinline__ void fma16(const uint4 v, const float* __restrict__ q, float* acc, unsigned magic) {
   const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const float4 qv = *reinterpret_cast<const float4*>(q + 4 * g);  // 16-byte aligned by construction
-    float x0 = byte_to_f32_biased(w[g], 0, magic), x1 = byte_to_f32_biased(w[g], 1, magic);
-    float x2 = byte_to_f32_biased(w[g], 2, magic), x3 = byte_to_f32_biased(w[g], 3, magic);
-    add2(x0, x1, -8388608.0f);
-    add2(x2, x3, -8388608.0f);
+    float x0, x1, x2, x3;
+    if (SCALED) {
+      x0 = __uint_as_float(__byte_perm(w[g], 0u, 0x4440u));
+      x1 = __uint_as_float(__byte_perm(w[g], 0u, 0x4441u));
+      x2 = __uint_as_float(__byte_perm(w[g], 0u, 0x4442u));
+      x3 = __uint_as_float(__byte_perm(w[g], 0u, 0x4443u));
+    } else {
+      x0 = byte_to_f32_biased(w[g], 0, magic), x1 = byte_to_f32_biased(w[g], 1, magic);
+      x2 = byte_to_f32_biased(w[g], 2, magic), x3 = byte_to_f32_biased(w[g], 3, magic);
+      add2(x0, x1, -8388608.0f);
+      add2(x2, x3, -8388608.0f);
+    }
     fma2(acc[4 * g + 0], acc[4 * g + 1], qv.x, qv.y, x0, x1);
     fma2(acc[4 * g + 2], acc[4 * g + 3], qv.z, qv.w, x2, x3);
   }
@@ -89,7 +105,8 @@ __device__ __forceinline__ float hsum8(const float* v) {  // src/arch/x86_64.rs:
 // Everything after the 32-wide main loop: combine the 32 chains, 8-wide remainder chains, scalar tail; or the
 // portable sequential sum when d < 16. w = the (up to) two chunks after the main loop, zero padded.
 __device__ __forceinline__ float mixed_dot_finish(const float* acc, const unsigned* w, unsigned d,
-                                                  const float* __restrict__ sq, const unsigned magic) {
+                                                  const float* __restrict__ sq, const unsigned magic,
+                                                  const float unscale = 1.0f) {
   if (d == 0) return 0.0f;
   if (d < 16) {  // portable path: sequential unfused sum (src/scalar.rs:353-358)
     float s = 0.0f;
@@ -102,7 +119,7 @@ __device__ __forceinline__ float mixed_dot_finish(const float* acc, const unsign
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     all[j] = __fadd_rn(__fadd_rn(acc[j], acc[8 + j]), __fadd_rn(acc[16 + j], acc[24 + j]));
-  float result = hsum8(all);
+  float result = __fmul_rn(hsum8(all), unscale);  // 2^23 on the scaled path (exact), else 1
   const unsigned rs = (d / 32) * 32, remaining = d - rs, n8 = (remaining / 8) * 8;
   if (remaining == 0) return __fadd_rn(result, 0.0f);  // the empty 8-wide accumulator is still added (x86_64.rs:1004-1009)
   float rem[8];
@@ -125,6 +142,7 @@ struct U8Args {
   unsigned n, d, chunks, n_tiles, index_base;
   float alpha, offset;
   unsigned magic;      // 0x4B000000 (2^23 as f32 bits), see byte_to_f32
+  int allow_scaled;    // option "u8_scaled_chains" (default 1): PRMT + FFMA2 chains when the query allows it
   const float* query;  // device, d floats
   int k, mode;         // mode (scores kernel): 0 raw mixed dot, 1 asymmetric score
   uint64_t* partials;
@@ -133,6 +151,8 @@ struct U8Args {
   unsigned* tickets;
   float* scores_out;
 };
+
+int g_u8_allow_scaled = 1;
 
 struct U8Shared {
   uint64_t full[U8_STAGES], empty[U8_STAGES];
@@ -157,7 +177,14 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(st + 1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool producer = warp == U8_THREADS / 32;
-  for (unsigned i = threadIdx.x; i < d_pad; i += blockDim.x) sq[i] = i < a.d ? a.query[i] : 0.0f;
+  // Scaled chains (see fma16) need every query element of the 32-wide main loop to be 0 or in [2^-80, 4)
+  const unsigned main_elems = (a.d >= 16) ? (a.d / 32) * 32 : 0;
+  bool q_ok = true;
+  for (unsigned i = threadIdx.x; i < d_pad; i += blockDim.x) {
+    const float v = i < a.d ? a.query[i] : 0.0f;
+    sq[i] = v;
+    if (i < main_elems) q_ok &= (v == 0.0f) || (fabsf(v) >= 0x1p-80f && fabsf(v) < 4.0f);  // NaN fails both
+  }
   if (threadIdx.x == 0) {  // query_context: query.iter().sum() sequential (src/scalar.rs:236-240)
     float s = 0.0f;
     for (unsigned i = 0; i < a.d; ++i) s = __fadd_rn(s, a.query[i]);
@@ -168,7 +195,11 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
     }
     tc::fence_barrier_init();
   }
-  __syncthreads();
+  const bool scaled = __syncthreads_and(q_ok) && a.allow_scaled;
+  if (scaled) {  // only the main-loop part; the remainder / portable paths read the query as given
+    for (unsigned i = threadIdx.x; i < main_elems; i += blockDim.x) sq[i] *= 0x1p126f;  // exact: |q| < 4
+    __syncthreads();
+  }
   const float scale = __fdiv_rn(a.alpha, 255.0f);             // params.alpha / 255.0
   const float bias = __fmul_rn(a.offset, s_misc[0]);          // params.offset * ctx.query_sum
   const unsigned stages_per_tile = (a.chunks + U8_STAGE_CHUNKS - 1) / U8_STAGE_CHUNKS;
@@ -199,6 +230,8 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
       }
     }
   } else {
+   auto consume = [&](auto scaled_tag) {
+    constexpr bool SCALED = decltype(scaled_tag)::value;
     const unsigned full_stages = main_chunks / U8_STAGE_CHUNKS;  // stages made of main-loop chunks only
     unsigned slot = 0, phase = 0;
     const uint4* const ring_v = reinterpret_cast<const uint4*>(ring) + threadIdx.x;
@@ -221,7 +254,7 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
         if (lane == 0) tc::mbar_arrive(&st->empty[slot]);  // the slot is in registers: the producer may refill it
         if (++slot == U8_STAGES) { slot = 0; phase ^= 1; }
 #pragma unroll
-        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) fma16(v[g], qp + 16 * g, acc + 16 * (g & 1), a.magic);
+        for (int g = 0; g < U8_STAGE_CHUNKS; ++g) fma16<SCALED>(v[g], qp + 16 * g, acc + 16 * (g & 1), a.magic);
       }
       for (; sgi < stages_per_tile; ++sgi) {  // last stage(s): remainder chunks (d % 64 != 0), or everything when d < 16
         const unsigned c0 = sgi * U8_STAGE_CHUNKS;
@@ -237,18 +270,20 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
         for (int g = 0; g < U8_STAGE_CHUNKS; ++g) {
           const unsigned c = c0 + g;
           if (c < main_chunks) {
-            fma16(v[g], sq + 16 * c, acc + 16 * (g & 1), a.magic);
+            fma16<SCALED>(v[g], sq + 16 * c, acc + 16 * (g & 1), a.magic);
           } else if (c < a.chunks) {  // the (up to) two chunks of the remainder / of the d < 16 path
             if (c == main_chunks) { w[0] = v[g].x; w[1] = v[g].y; w[2] = v[g].z; w[3] = v[g].w; }
             else { w[4] = v[g].x; w[5] = v[g].y; w[6] = v[g].z; w[7] = v[g].w; }
           }
         }
       }
-      const float mixed = mixed_dot_finish(acc, w, a.d, sq, a.magic);
+      const float mixed = mixed_dot_finish(acc, w, a.d, sq, a.magic, SCALED ? 0x1p23f : 1.0f);
       const float score = (KNN || a.mode == 1) ? __fadd_rn(__fmul_rn(scale, mixed), bias) : mixed;  // src/scalar.rs:299
       if (KNN) lists[0].offer(make_key_desc(score, a.index_base + i), valid, thrs[0], a.k, lane);
       else if (valid) a.scores_out[i] = score;
     }
+   };
+   if (scaled) consume(std::true_type{}); else consume(std::false_type{});
   }
   // the producer warp takes part in the CTA-wide merge with an empty list
   if (KNN) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
@@ -343,11 +378,14 @@ U8Args make_args(const U8View& v, const float* q) {
   a.alpha = v.alpha;
   a.offset = v.offset;
   a.magic = 0x4B000000u;
+  a.allow_scaled = g_u8_allow_scaled;
   a.query = q;
   return a;
 }
 
 }  // namespace
+
+void u8_set_scaled_chains(bool on) { g_u8_allow_scaled = on ? 1 : 0; }
 
 cudaError_t launch_u8_pack(const uint8_t* dev_rows, size_t n, size_t d, uint4* dev_codes, size_t ld,
                            cudaStream_t s, uint64_t* launches) {

@@ -252,6 +252,55 @@ def test_u8_bit_exact(ib, oracle, d):
         assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want]))
 
 
+@pytest.mark.parametrize("d", [32, 64, 96, 384, 400, 777])
+@pytest.mark.parametrize("qkind", ["unit", "zeros", "wide_range", "cancel", "below_range", "denormal", "ge4", "nan"])
+def test_u8_scaled_chains_bit_exact(ib, oracle, d, qkind):
+    """The u8 scan runs its 32 FMA chains scaled by 2^-23 (byte bits as the f32 b*2^-149, query * 2^126) when every
+    main-loop query element is 0 or in [2^-80, 4), else with the de-biasing FADD. Both must reproduce dot_u8_f32_avx2
+    (src/arch/x86_64.rs:928-1020) bit for bit; queries at and beyond the edges of the admissible range are the cases."""
+    n = 2048 + 7
+    rng = np.random.default_rng(d * 31 + len(qkind))
+    mat = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    mat[0] = 0
+    mat[1] = 255
+    q = rng.uniform(-1, 1, d).astype(np.float32)
+    if qkind == "zeros":
+        q[::3] = 0.0
+        q[1::7] = -0.0
+    elif qkind == "wide_range":      # exponents spread over the whole admissible range
+        q = (np.ldexp(rng.uniform(0.5, 1.0, d), rng.integers(-79, 2, d)) * rng.choice([-1, 1], d)).astype(np.float32)
+        q[0], q[1] = np.float32(2.0 ** -80), np.float32(np.nextafter(np.float32(4.0), np.float32(0.0)))
+    elif qkind == "cancel":          # chains that cancel to tiny / zero partial sums
+        q[32:64] = -q[0:32] if d >= 64 else q[32:64]
+        mat[:, 32:64] = mat[:, 0:32] if d >= 64 else mat[:, 32:64]
+        q[5] = np.float32(2.0 ** -80)
+    elif qkind == "below_range":
+        q[3] = np.float32(2.0 ** -81)
+    elif qkind == "denormal":
+        q[3] = np.float32(1e-40)
+    elif qkind == "ge4":
+        q[7] = np.float32(4.0)
+        q[9] = np.float32(-3.0e20)
+    elif qkind == "nan":
+        q[11] = np.nan
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    corpus = ib.U8Corpus.from_rows(mat, gp)
+    want = np.array([oracle.mixed_dot_u8_f32(q, mat[i]) for i in range(n)], dtype=np.float32)
+    try:
+        for mode in (1, 0):
+            ib.set_option("u8_scaled_chains", mode)
+            got = ib.mixed_dot_u8_all(q, corpus)
+            assert np.array_equal(bits(got), bits(want)) or (
+                qkind == "nan" and np.array_equal(np.isnan(got), np.isnan(want))), (mode, qkind, d)
+    finally:
+        ib.set_option("u8_scaled_chains", 1)
+    if qkind != "nan":
+        got = ib.batch_knn_u8(q, corpus, gp, 10)
+        want_k = oracle.batch_knn_u8(q, mat, op, 10)
+        assert [i for i, _ in got] == [i for i, _ in want_k]
+        assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want_k]))
+
+
 def test_u8_generator_and_quantize(ib, oracle):
     n, d = 4000, 384
     gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
