@@ -113,6 +113,18 @@ int innr_cuda_batch_cosine(const innr_cuda_corpus* c, const float* query, size_t
  * Order: dot/cosine descending, L2 ascending; ties -> lower index (stable sort, src/batch.rs:756-758). */
 int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
                         size_t query_len, size_t k, uint64_t* out_idx, float* out_score, size_t* out_count);
+/* batch_knn_filtered (src/batch.rs:820-882). The reference takes a closure `Fn(usize) -> bool`; closures cannot cross
+ * the ABI, so the shim evaluates it into a bitmask first (the reference materialises `mask: Vec<bool>` itself, :839):
+ * bit i of mask_words[i / 64], LSB first. L2 distances of the passing vectors only (rows of rejected vectors are not
+ * read), stable ascending order, k clamped to the number of passing vectors; indices are positions in the batch. */
+int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                 const uint64_t* mask_words, size_t mask_len_words, uint64_t* out_idx,
+                                 float* out_score, size_t* out_count);
+/* batch_l2_squared_pruning (src/batch.rs:320-365): every vector none of whose partial squared distances (dimension by
+ * dimension, as the reference accumulates them) exceeded `threshold`, as (index, full squared distance) pairs in
+ * ascending index order. Writes min(*out_count, capacity) pairs; *out_count is the number of survivors. */
+int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* query, size_t query_len, float threshold,
+                                       uint64_t* out_idx, float* out_dist, size_t capacity, size_t* out_count);
 /* Device-pointer form used for row-sharded corpora: writes the shard's local top-k as sorted 64-bit
  * composite keys (n_queries x k, padded with 0xFFFF...F) into dev_keys on `stream`. Keys from all shards
  * are exchanged by the caller (one allgather) and merged with innr_cuda_merge_keys_dev. */

@@ -229,3 +229,42 @@ def batch_knn_dot(query, batch, k: int) -> BatchKnnResult:  # src/batch.rs:742 (
 
 def batch_knn_cosine(query, batch, k: int) -> BatchKnnResult:  # src/batch.rs:777 (descending)
     return _knn("cosine", query, batch, k)
+
+
+def batch_knn_filtered(query, batch, k: int, predicate) -> BatchKnnResult:  # src/batch.rs:820-882
+    """`predicate(index) -> bool` is evaluated on the host into a bitmask (the reference builds `mask: Vec<bool>` the
+    same way, :839); a numpy bool array of length N is accepted directly. Squared L2 of the passing vectors only."""
+    dev = _dev(batch)
+    q = _f32(query).reshape(-1)
+    assert q.size == dev.dimension, "query.len() != batch.dimension"
+    n = dev.num_vectors
+    if isinstance(predicate, np.ndarray):
+        bits = predicate.astype(bool).reshape(-1)
+        assert bits.size == n
+    else:
+        bits = np.fromiter((bool(predicate(i)) for i in range(n)), dtype=bool, count=n)
+    words = np.zeros((n + 63) // 64 + 1, np.uint64)
+    packed = np.packbits(bits, bitorder="little")
+    words.view(np.uint8)[:packed.size] = packed
+    kk = max(k, 1)
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_batch_knn_filtered", dev.h, _ptr(q, L.f32p), q.size, k, _ptr(words, L.u64p), words.size,
+           _ptr(idx, L.u64p), _ptr(sc, L.f32p), C.byref(cnt))
+    return BatchKnnResult(idx[:cnt.value], sc[:cnt.value])
+
+
+def batch_l2_squared_pruning(query, batch, threshold: float):  # src/batch.rs:320-365
+    """[(index, squared distance)] of the vectors none of whose partial distances exceeded `threshold`."""
+    dev = _dev(batch)
+    q = _f32(query).reshape(-1)
+    assert q.size == dev.dimension, "query.len() != batch.dimension"
+    n = dev.num_vectors
+    idx = np.zeros(max(n, 1), np.uint64)
+    ds = np.zeros(max(n, 1), np.float32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_batch_l2_squared_pruning", dev.h, _ptr(q, L.f32p), q.size, float(threshold), _ptr(idx, L.u64p),
+           _ptr(ds, L.f32p), n, C.byref(cnt))
+    m = cnt.value
+    return [(int(idx[j]), float(ds[j])) for j in range(m)]

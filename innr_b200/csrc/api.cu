@@ -587,6 +587,103 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   return INNR_OK;
 }
 
+// batch_knn_filtered (src/batch.rs:820-882): the closure predicate crosses the ABI as a bitmask (bit i of word i/64,
+// LSB first, like PackedBinary). L2, stable ascending sort of the passing vectors, k clamped to their number.
+int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                 const uint64_t* mask_words, size_t mask_len_words, uint64_t* out_idx,
+                                 float* out_score, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:829
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0) return INNR_OK;                                              // :831-836
+  if (!mask_words || mask_len_words < (c->n + 63) / 64) return fail(INNR_EINVAL, "mask shorter than the batch");
+  if (!out_idx || !out_score || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  const size_t words = (c->n + 63) / 64;
+  size_t passing = 0;
+  for (size_t w = 0; w < words; ++w) {
+    uint64_t m = mask_words[w];
+    if (w == words - 1 && (c->n & 63)) m &= (~0ull) >> (64 - (c->n & 63));  // bits past num_vectors are not vectors
+    passing += (size_t)__builtin_popcountll(m);
+  }
+  if (passing == 0) return INNR_OK;                                                     // :842-847
+  const size_t kk = k < passing ? k : passing;                                          // k.min(num_passing)
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  const size_t dev_words64 = c->ld / 64 + 2;  // the kernel reads whole u32 words up to the row pitch
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  CU(ctx->d_aux.reserve(dev_words64 * sizeof(uint64_t)));
+  CU(cudaMemsetAsync(ctx->d_aux.p, 0, dev_words64 * sizeof(uint64_t), ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_aux.p, mask_words, words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (c->d) CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_pdx_knn_filtered(pdx_view(c), (const float*)ctx->d_query.p, (const uint32_t*)ctx->d_aux.p, kk,
+                             (uint64_t*)ctx->d_keys.p, ctx->ws, ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) { decode_keys_f32(keys, kk, false, out_idx, out_score); });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+// batch_l2_squared_pruning (src/batch.rs:320-365): (index, squared distance) of every vector none of whose partial
+// distances exceeded `threshold`, ascending index. Writes min(count, capacity) pairs; *out_count = count.
+int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* query, size_t query_len, float threshold,
+                                       uint64_t* out_idx, float* out_dist, size_t capacity, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:325
+  if (!out_count) return fail(INNR_EINVAL, "null out_count");
+  *out_count = 0;
+  if (c->n == 0) return INNR_OK;
+  if (capacity && (!out_idx || !out_dist)) return fail(INNR_EINVAL, "null argument");
+  if (c->d == 0) {  // no dimension is ever processed: every vector survives with distance 0.0
+    for (size_t i = 0; i < c->n && i < capacity; ++i) { out_idx[i] = c->index_base + i; out_dist[i] = 0.0f; }
+    *out_count = c->n;
+    return INNR_OK;
+  }
+  if (!query) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  const size_t nb = compact_blocks(c->n);
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+  CU(ctx->d_aux.reserve((nb + 1) * sizeof(unsigned)));
+  CU(ctx->h_counts.reserve(64));
+  CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_pdx_scores(pdx_view(c), PDX_L2_PRUNE, (const float*)ctx->d_query.p, nullptr, (float*)ctx->d_scores.p,
+                       ctx->ws, ctx->stream, &g_launches, threshold));
+  CU(launch_compact_count((const float*)ctx->d_scores.p, c->n, (unsigned*)ctx->d_aux.p, ctx->stream, &g_launches));
+  CU(cudaMemcpyAsync(ctx->h_counts.p, (unsigned*)ctx->d_aux.p + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const size_t count = *(unsigned*)ctx->h_counts.p;
+  *out_count = count;
+  const size_t take = count < capacity ? count : capacity;
+  if (count) {
+    CU(ctx->d_keys.reserve(count * (sizeof(uint64_t) + sizeof(float))));
+    uint64_t* d_idx = (uint64_t*)ctx->d_keys.p;
+    float* d_dist = (float*)(d_idx + count);
+    CU(launch_compact_scatter((const float*)ctx->d_scores.p, c->n, c->index_base, (const unsigned*)ctx->d_aux.p, d_idx,
+                              d_dist, ctx->stream, &g_launches));
+    tm.stop();
+    if (take) {
+      CU(cudaMemcpyAsync(out_idx, d_idx, take * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(out_dist, d_dist, take * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+  } else {
+    tm.stop();
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  tm.finish();
+  return INNR_OK;
+}
+
 int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const float* dev_queries,
                                  size_t n_queries, size_t k, uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");

@@ -16,6 +16,7 @@ enum PdxMode : int {
   PDX_L2 = 2,           // batch_l2_squared_into     src/batch.rs:250-266
   PDX_NORMS = 3,        // batch_norms_into          src/batch.rs:672-686
   PDX_COSINE_NORMS = 4, // batch_cosine_into with caller-supplied norms  src/batch.rs:705-728
+  PDX_L2_PRUNE = 5,     // batch_l2_squared_pruning  src/batch.rs:320-365 (scores mode: pruned vectors -> -1.0)
 };
 
 struct Workspace {
@@ -47,9 +48,20 @@ struct PdxView {
 // Returns cudaSuccess or the launch error; `launches` is incremented per kernel launched.
 cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
                            uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
-// full score vectors: out[q * ld + i] (device). dev_norms only for PDX_COSINE_NORMS.
+// batch_knn_filtered (src/batch.rs:820-882): L2, one query; dev_mask = one bit per local vector (LSB-first u32 words,
+// zero padded to ld/32 + 1 words); vectors whose bit is clear are neither read nor offered.
+cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, const uint32_t* dev_mask, size_t k,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+// full score vectors: out[q * ld + i] (device). dev_norms only for PDX_COSINE_NORMS; threshold only for PDX_L2_PRUNE.
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches);
+                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches, float threshold = 0.0f);
+// stream compaction of a pruned distance vector (entries == -1.0 are dropped): ascending index order.
+// Pass 1 (count) fills dev_block_offsets[n_blocks + 1] (exclusive prefix, last = total); pass 2 scatters.
+size_t compact_blocks(size_t n);
+cudaError_t launch_compact_count(const float* dev_dist, size_t n, unsigned* dev_block_offsets, cudaStream_t s,
+                                 uint64_t* launches);
+cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t index_base, const unsigned* dev_block_offsets,
+                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, uint64_t* launches);
 // merge n_lists x nq x k sorted key lists -> nq x k; optional decode (idx u64, f32 score bits by `descending`)
 cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,

@@ -46,11 +46,13 @@ struct PdxArgs {
   unsigned* tickets;
   float* scores_out;      // scores mode: out[q * ld + i]
   const float* norms_in;  // PDX_COSINE_NORMS
+  const uint32_t* mask;   // MASKED: bit i set = vector i passes the predicate (batch_knn_filtered)
+  float threshold;        // PDX_L2_PRUNE
 };
 
 template <int MODE>
 __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
-  if (MODE == PDX_L2) {
+  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE) {
     float diff = __fsub_rn(q, v);                 // let diff = q_d - v_d;
     acc = __fadd_rn(acc, __fmul_rn(diff, diff));  // *dist += diff * diff;
   } else {
@@ -58,8 +60,9 @@ __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
   }
 }
 
-template <int MODE, int QB, int R, bool KNN>
+template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
 __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_in) {
+  static_assert(MODE != PDX_L2_PRUNE || (QB == 1 && !KNN), "pruning is a single-query scores scan");
   constexpr bool NEED_SS = (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS);
   constexpr bool NEED_DOT = (MODE != PDX_NORMS);
   constexpr int U = (QB == 1) ? 8 : 4;  // dimension rows in flight per thread
@@ -118,15 +121,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
 
   for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const unsigned i0 = tile * TILE + threadIdx.x * VPT;
-    const bool active = i0 < a.ld4;  // ld is a multiple of 4: the whole float4 is in bounds
+    bool active = i0 < a.ld4;  // ld is a multiple of 4: the whole float4 is in bounds
+    unsigned nib = 0xFu;       // MASKED: predicate bits of this thread's four vectors (i0 % 4 == 0: one word)
+    if (MASKED) {
+      nib = active ? (a.mask[i0 >> 5] >> (i0 & 31)) & 0xFu : 0u;
+      active = nib != 0;       // predicate pushdown: rows of rejected vectors are not even read
+    }
     float acc[QB][VPT];
-    float ss[VPT];
+    float ss[VPT];   // sum of squares; PDX_L2_PRUNE: running max of the non-NaN partial distances
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
-      ss[j] = 0.0f;
+      ss[j] = (MODE == PDX_L2_PRUNE) ? -INFINITY : 0.0f;  // the initial 0.0 is not a partial the reference tests
 #pragma unroll
       for (int q = 0; q < QB; ++q) acc[q][j] = 0.0f;
     }
+    const unsigned amask = (MODE == PDX_L2_PRUNE) ? __ballot_sync(FULL_MASK, active) : 0u;
     if (active) {
       const float* p = a.data + i0;
       unsigned dd = 0;
@@ -150,6 +159,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
               for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
             }
           }
+          if (MODE == PDX_L2_PRUNE) {
+            // the reference prunes vector i at the first dimension whose partial distance exceeds the threshold
+            // (src/batch.rs:347-351). Partial sums of squares never decrease until one becomes NaN (a NaN compares
+            // false and stays alive), so "some partial > threshold" == "max of the non-NaN partials > threshold".
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) ss[j] = fmaxf(ss[j], acc[0][j]);
+          }
+        }
+        if (MODE == PDX_L2_PRUNE) {  // every vector this warp owns in the tile is pruned: stop reading its rows
+          const bool dead = ss[0] > a.threshold && ss[1] > a.threshold && ss[2] > a.threshold && ss[3] > a.threshold;
+          if (__all_sync(amask, dead)) { dd = a.d; break; }
         }
       }
       for (; dd < a.d; ++dd) {  // D % U tail
@@ -167,6 +187,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
 #pragma unroll
             for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
           }
+        }
+        if (MODE == PDX_L2_PRUNE) {
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) ss[j] = fmaxf(ss[j], acc[0][j]);
         }
       }
     }
@@ -194,6 +218,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
           s[j] = c;
         } else if (MODE == PDX_NORMS) {
           s[j] = nrm[j];
+        } else if (MODE == PDX_L2_PRUNE) {
+          s[j] = ss[j] > a.threshold ? -1.0f : acc[q][j];  // distances are never negative: -1.0 marks "pruned"
         } else {
           s[j] = acc[q][j];
         }
@@ -205,7 +231,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
             const unsigned i = i0 + j;
             const uint64_t key = (MODE == PDX_L2) ? make_key_asc(s[j], a.index_base + i)
                                                   : make_key_desc(s[j], a.index_base + i);
-            lists[q].offer(key, active && i < a.n, thrs[q], a.k, lane);
+            lists[q].offer(key, active && i < a.n && (!MASKED || ((nib >> j) & 1u)), thrs[q], a.k, lane);
           }
         }
       } else if (active && q < a.nq_valid) {
@@ -217,9 +243,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
   if (KNN) block_finish<R, QB>(lists, a.nq_valid, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
-template <int MODE, int QB, int R, bool KNN>
+template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
 cudaError_t launch_one(const PdxArgs& a, size_t smem, int ny, int num_sms, cudaStream_t s) {
-  auto kern = pdx_scan_kernel<MODE, QB, R, KNN>;
+  auto kern = pdx_scan_kernel<MODE, QB, R, KNN, MASKED>;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -318,8 +344,34 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
   return cudaSuccess;
 }
 
+cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, const uint32_t* dev_mask, size_t k,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  PdxArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
+  a.n = (unsigned)v.n;
+  a.d = (unsigned)v.d;
+  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
+  a.index_base = v.index_base;
+  a.k = (int)k;
+  a.partials = ws.partials;
+  a.group_partials = ws.group_partials;
+  a.tickets = ws.tickets;
+  a.queries = dev_query;
+  a.nq_valid = 1;
+  a.out_keys = dev_keys;
+  a.mask = dev_mask;
+  const size_t smem = scan_smem_bytes(v.d, 1, (int)k, true);
+  if (smem > 227 * 1024 || k > 128) return cudaErrorInvalidValue;
+  cudaError_t e = (k <= 32) ? launch_one<PDX_L2, 1, 1, true, true>(a, smem, 1, ws.num_sms, s)
+                            : launch_one<PDX_L2, 1, 4, true, true>(a, smem, 1, ws.num_sms, s);
+  if (e == cudaSuccess) ++*launches;
+  return e;
+}
+
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches, float threshold) {
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
@@ -334,6 +386,7 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   a.nq_valid = 1;
   a.scores_out = dev_out;
   a.norms_in = dev_norms;
+  a.threshold = threshold;
   size_t smem = scan_smem_bytes(v.d, 1, 0, false);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e;
@@ -342,6 +395,7 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
     case PDX_L2: e = launch_one<PDX_L2, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
+    case PDX_L2_PRUNE: e = launch_one<PDX_L2_PRUNE, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     default: return cudaErrorInvalidValue;
   }
   if (e == cudaSuccess) ++*launches;
@@ -400,6 +454,129 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const floa
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// compaction of a pruned distance vector: survivors (entries != -1.0) in ascending index order, the order of the
+// reference's `alive.iter().enumerate().filter(..).collect()` (src/batch.rs:358-364)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int CP_THREADS = 256, CP_ITEMS = 4, CP_BLOCK = CP_THREADS * CP_ITEMS;
+
+__device__ __forceinline__ bool survivor(float d) { return !(d == -1.0f); }  // NaN distances survive (never pruned)
+
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const float* __restrict__ dist, unsigned n,
+                                                                   unsigned* __restrict__ block_counts) {
+  const unsigned base = blockIdx.x * CP_BLOCK;
+  unsigned c = 0;
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    const unsigned i = base + it * CP_THREADS + threadIdx.x;
+    c += __popc(__ballot_sync(FULL_MASK, i < n && survivor(dist[i])));
+  }
+  __shared__ unsigned s_c[CP_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;  // every lane of the warp holds the warp total
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) t += s_c[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// in place: counts -> exclusive prefix; offsets[n_blocks] = total. One CTA (n_blocks <= 2^32 / 1024).
+__global__ void __launch_bounds__(1024) compact_scan_kernel(unsigned* __restrict__ offsets, unsigned n_blocks) {
+  __shared__ unsigned s_w[32];
+  __shared__ unsigned s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned b0 = 0; b0 < n_blocks; b0 += 1024) {
+    const unsigned b = b0 + threadIdx.x;
+    const unsigned v = b < n_blocks ? offsets[b] : 0u;
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(FULL_MASK, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(FULL_MASK, w, o);
+        if (lane >= o) w += y;
+      }
+      s_w[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned carry = s_carry;
+    const unsigned incl = carry + (warp ? s_w[warp - 1] : 0u) + x;
+    if (b < n_blocks) offsets[b] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n_blocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const float* __restrict__ dist, unsigned n,
+                                                                     unsigned long long index_base,
+                                                                     const unsigned* __restrict__ block_offsets,
+                                                                     uint64_t* __restrict__ out_idx,
+                                                                     float* __restrict__ out_dist) {
+  const unsigned base = blockIdx.x * CP_BLOCK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ unsigned s_c[CP_ITEMS][CP_THREADS / 32];
+  float d[CP_ITEMS];
+  unsigned bal[CP_ITEMS];
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    const unsigned i = base + it * CP_THREADS + threadIdx.x;
+    d[it] = i < n ? dist[i] : -1.0f;
+    bal[it] = __ballot_sync(FULL_MASK, survivor(d[it]));
+    if (lane == 0) s_c[it][warp] = __popc(bal[it]);
+  }
+  __syncthreads();
+  // position of (it, warp) inside the block: items are laid out it-major (index = base + it*256 + tid)
+  unsigned before = block_offsets[blockIdx.x];
+#pragma unroll
+  for (int it = 0; it < CP_ITEMS; ++it) {
+    unsigned pre = 0;
+    for (int w = 0; w < warp; ++w) pre += s_c[it][w];
+    if (survivor(d[it])) {
+      const unsigned pos = before + pre + __popc(bal[it] & ((1u << lane) - 1u));
+      out_idx[pos] = index_base + base + it * CP_THREADS + threadIdx.x;
+      out_dist[pos] = d[it];
+    }
+    unsigned tot = 0;
+    for (int w = 0; w < CP_THREADS / 32; ++w) tot += s_c[it][w];
+    before += tot;
+  }
+}
+}  // namespace
+
+size_t compact_blocks(size_t n) { return (n + CP_BLOCK - 1) / CP_BLOCK; }
+
+cudaError_t launch_compact_count(const float* dev_dist, size_t n, unsigned* dev_block_offsets, cudaStream_t s,
+                                 uint64_t* launches) {
+  const unsigned nb = (unsigned)compact_blocks(n);
+  if (nb == 0) return cudaMemsetAsync(dev_block_offsets, 0, sizeof(unsigned), s);
+  compact_count_kernel<<<nb, CP_THREADS, 0, s>>>(dev_dist, (unsigned)n, dev_block_offsets);
+  compact_scan_kernel<<<1, 1024, 0, s>>>(dev_block_offsets, nb);
+  *launches += 2;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t index_base, const unsigned* dev_block_offsets,
+                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, uint64_t* launches) {
+  const unsigned nb = (unsigned)compact_blocks(n);
+  if (nb == 0) return cudaSuccess;
+  compact_scatter_kernel<<<nb, CP_THREADS, 0, s>>>(dev_dist, (unsigned)n, index_base, dev_block_offsets, dev_idx, dev_out);
+  ++*launches;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,

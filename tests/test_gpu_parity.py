@@ -230,6 +230,49 @@ def test_hamming_generator_and_multi_query(ib, oracle):
     assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
 
 
+# ------------------------------------------------------------------------------------------------ filtered / pruning
+@pytest.mark.parametrize("n,d,sel", [(5000, 33, 0.5), (70001, 16, 0.01), (4097, 128, 0.9), (300, 7, 0.0), (2049, 5, 1.0)])
+def test_knn_filtered_bit_exact(ib, oracle, n, d, sel):
+    """batch_knn_filtered (src/batch.rs:820-882) with the predicate as a bitmask: passing set, L2 bits, stable order."""
+    rng = np.random.default_rng(n + d)
+    rows = rng.integers(-4, 5, size=(n, d)).astype(np.float32) if d < 10 else rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    mask = rng.random(n) < sel
+    if sel == 0.0:
+        mask[:] = False
+        mask[n // 2] = True          # exactly one passing vector
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for k in (1, 10, 100):
+        got = ib.batch_knn_filtered(q, gb, k, mask)
+        want = oracle.batch_knn_filtered(q, ob, k, lambda i: bool(mask[i]))
+        assert list(got.indices) == list(want.indices), (k, got.indices[:5], want.indices[:5])
+        assert np.array_equal(bits(got.scores), bits(want.scores))
+        assert all(mask[int(i)] for i in got.indices)
+
+
+@pytest.mark.parametrize("n,d", [(5000, 33), (70001, 16), (1025, 128), (300, 1)])
+def test_l2_pruning_bit_exact(ib, oracle, n, d):
+    """batch_l2_squared_pruning (src/batch.rs:320-365): survivor set, order and distance bits, over thresholds from
+    'nothing survives' to 'everything survives', with NaN / inf rows (a NaN partial never exceeds the threshold)."""
+    rng = np.random.default_rng(n * 3 + d)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[7, 0] = np.nan
+    rows[9, d - 1] = np.inf
+    if d > 2:
+        rows[11, 0] = 1e20           # overflows to inf in the first dimension, then inf - ... stays inf
+        rows[13, 1] = np.nan         # NaN after a finite first partial
+    q = rng.standard_normal(d).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    full = oracle.batch_l2_squared(q, ob)
+    finite = full[np.isfinite(full)]
+    for thr in (-1.0, 0.0, float(np.quantile(finite, 0.001)), float(np.quantile(finite, 0.3)), float(finite.max()),
+                float("inf"), float("nan")):
+        got = ib.batch_l2_squared_pruning(q, gb, thr)
+        want = oracle.batch_l2_squared_pruning(q, ob, thr)
+        assert [i for i, _ in got] == [i for i, _ in want], (thr, len(got), len(want))
+        assert same_scores([s for _, s in got], [s for _, s in want]), thr
+
+
 # ------------------------------------------------------------------------------------------------ u8
 @pytest.mark.parametrize("d", [1, 8, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 100, 128, 384, 777])
 def test_u8_bit_exact(ib, oracle, d):

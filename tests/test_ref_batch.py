@@ -260,6 +260,80 @@ def test_cosine_knn_normalized_matches_dot_knn(api):  # :439-466
     assert api.batch_knn_cosine(q, b, 5).indices == api.batch_knn_dot(q, b, 5).indices
 
 
+# ---- batch_knn_filtered: src/batch.rs:1353-1420, tests/batch_tests.rs:461-474
+def test_filtered_knn_basic(api):
+    b = api.VerticalBatch.from_rows([[0.0, 0.0], [1.0, 0.0], [0.1, 0.0], [10.0, 0.0]])
+    r = api.batch_knn_filtered([0.0, 0.0], b, 2, lambda i: i % 2 == 0)
+    assert list(r.indices) == [0, 2]
+
+
+def test_filtered_knn_none_pass(api):
+    b = api.VerticalBatch.from_rows([[1.0, 0.0], [2.0, 0.0]])
+    assert len(api.batch_knn_filtered([0.0, 0.0], b, 2, lambda i: False).indices) == 0
+
+
+def test_filtered_knn_all_pass(api):
+    b = api.VerticalBatch.from_rows([[0.0, 0.0], [1.0, 0.0], [2.0, 0.0]])
+    f = api.batch_knn_filtered([0.0, 0.0], b, 2, lambda i: True)
+    u = api.batch_knn([0.0, 0.0], b, 2)
+    assert list(f.indices) == list(u.indices)
+
+
+def test_filtered_knn_k_larger_than_passing(api):
+    b = api.VerticalBatch.from_rows([[1.0], [2.0], [3.0]])
+    r = api.batch_knn_filtered([0.0], b, 10, lambda i: i == 0)
+    assert list(r.indices) == [0]
+
+
+def test_filtered_knn_preserves_original_indices(api):
+    b = api.VerticalBatch.from_rows([[100.0], [100.0], [0.1], [100.0], [0.2]])
+    r = api.batch_knn_filtered([0.0], b, 2, lambda i: i in (2, 4))
+    assert list(r.indices) == [2, 4]
+
+
+def test_filtered_knn_integration(api):
+    b = api.VerticalBatch.from_rows([[float(i), 0.0] for i in range(100)])
+    r = api.batch_knn_filtered([50.0, 0.0], b, 5, lambda i: i % 2 == 0)
+    assert len(r.indices) == 5 and r.indices[0] == 50
+    assert all(int(i) % 2 == 0 for i in r.indices)
+
+
+# ---- batch_l2_squared_pruning: src/batch.rs:971-988, 1475-1505, tests/batch_tests.rs:297-349
+def test_batch_pruning(api):
+    b = api.VerticalBatch.from_rows([[0.0, 0.0], [1.0, 0.0], [10.0, 0.0]])
+    s = api.batch_l2_squared_pruning([0.0, 0.0], b, 2.0)
+    assert sorted(i for i, _ in s) == [0, 1]
+
+
+def test_pruning_threshold_zero(api):
+    b = api.VerticalBatch.from_rows([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    s = api.batch_l2_squared_pruning([0.0, 0.0], b, 0.0)
+    assert len(s) == 1 and s[0][0] == 0 and abs(s[0][1]) < 1e-9
+
+
+def test_pruning_all_and_none_survive(api):
+    b = api.VerticalBatch.from_rows([[0.1, 0.0], [0.0, 0.1]])
+    assert len(api.batch_l2_squared_pruning([0.0, 0.0], b, 100.0)) == 2
+    b = api.VerticalBatch.from_rows([[10.0, 0.0], [0.0, 10.0]])
+    assert api.batch_l2_squared_pruning([0.0, 0.0], b, 0.5) == []
+
+
+def test_pruning_filters_far_vectors_and_distances(api):
+    b = api.VerticalBatch.from_rows([[0.0, 0.0], [1.0, 0.0], [100.0, 100.0], [2.0, 0.0]])
+    s = api.batch_l2_squared_pruning([0.0, 0.0], b, 5.0)
+    assert [i for i, _ in s] == [0, 1, 3]
+    full = api.batch_l2_squared([0.0, 0.0], b)
+    for i, dist in s:
+        assert abs(dist - float(full[i])) < 1e-6
+
+
+def test_pruning_tight_threshold(api):
+    b = api.VerticalBatch.from_rows([[float(i), 0.0] for i in range(100)])
+    s = api.batch_l2_squared_pruning([50.0, 0.0], b, 4.0)
+    idx = [i for i, _ in s]
+    assert len(idx) <= 5 and 50 in idx
+
+
 # ---- examples/batch_demo.rs:77-123 (knn == brute force at 20x8, k=3, generate_embedding)
 def test_demo_knn_matches_bruteforce(api, oracle):
     dim, n, k = 8, 20, 3
