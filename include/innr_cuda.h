@@ -155,6 +155,12 @@ int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_
  * must equal the corpus dimension (src/binary.rs:155-159). */
 int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
                           uint32_t* out_host);
+/* binary_dot (src/binary.rs:178-185: sum of popcount(a & b)) and binary_jaccard (:198-213: intersection as f32 /
+ * union as f32, 1.0 for an empty union) of one query code against every code of the corpus. Exact. */
+int innr_cuda_binary_dot_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                             uint32_t* out_host);
+int innr_cuda_binary_jaccard_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                                 float* out_host);
 /* caller composition examples/binary_demo.rs:174-180: all distances, stable sort_by_key, take(k). */
 int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
                            size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,

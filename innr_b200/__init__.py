@@ -11,7 +11,8 @@ from .backend import Backend, dense_backend  # noqa: F401
 from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, batch_dot, batch_knn,  # noqa: F401
                     batch_knn_cosine, batch_knn_dot, batch_knn_filtered, batch_knn_many, batch_l2_squared,
                     batch_l2_squared_pruning, batch_norms)
-from .binary import (BinaryCorpus, PackedBinary, binary_hamming, encode_binary, hamming_all,  # noqa: F401
+from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, binary_hamming, binary_jaccard,  # noqa: F401
+                     binary_jaccard_all, encode_binary, hamming_all,
                      hamming_topk, hamming_topk_many)
 from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_cosine  # noqa: F401
 from .scalar import (QuantizationParams, QuantizedU8, U8Corpus, asymmetric_dot_u8, asymmetric_dot_u8_all,  # noqa: F401

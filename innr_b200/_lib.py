@@ -60,6 +60,8 @@ SIGNATURES = {
     "innr_cuda_upload_binary": [u64p, sz, sz, u64, handle_p],
     "innr_cuda_generate_binary": [u64, u64, sz, sz, u64, handle_p],
     "innr_cuda_hamming_all": [vp, u64p, sz, u32p],
+    "innr_cuda_binary_dot_all": [vp, u64p, sz, u32p],
+    "innr_cuda_binary_jaccard_all": [vp, u64p, sz, f32p],
     "innr_cuda_hamming_topk": [vp, u64p, sz, sz, sz, u64p, u32p, szp],
     "innr_cuda_hamming_topk_keys_dev": [vp, vp, sz, sz, vp, vp],
     "innr_cuda_encode_binary": [f32p, sz, f32, u64p],

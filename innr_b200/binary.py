@@ -1,5 +1,5 @@
 """Host-side mirror of innr::binary (src/binary.rs) over the CUDA C-ABI: `PackedBinary`, `encode_binary`,
-`binary_hamming`, plus the corpus-level entries the device path adds (`BinaryCorpus`, `hamming_topk`) for the
+`binary_hamming`, `binary_dot`, `binary_jaccard`, plus the corpus-level entries the device path adds (`BinaryCorpus`, `hamming_topk`) for the
 caller composition in examples/binary_demo.rs:174-180."""
 from __future__ import annotations
 
@@ -97,6 +97,35 @@ def hamming_all(query: PackedBinary, corpus: BinaryCorpus) -> np.ndarray:
     q = np.ascontiguousarray(query.data, dtype=np.uint64)
     L.call("innr_cuda_hamming_all", corpus.h, q.ctypes.data_as(L.u64p), query.dimension, out.ctypes.data_as(L.u32p))
     return out
+
+
+def binary_dot_all(query: PackedBinary, corpus: BinaryCorpus) -> np.ndarray:
+    out = np.zeros(corpus.num_codes, np.uint32)
+    q = np.ascontiguousarray(query.data, dtype=np.uint64)
+    L.call("innr_cuda_binary_dot_all", corpus.h, q.ctypes.data_as(L.u64p), query.dimension, out.ctypes.data_as(L.u32p))
+    return out
+
+
+def binary_jaccard_all(query: PackedBinary, corpus: BinaryCorpus) -> np.ndarray:
+    out = np.zeros(corpus.num_codes, np.float32)
+    q = np.ascontiguousarray(query.data, dtype=np.uint64)
+    L.call("innr_cuda_binary_jaccard_all", corpus.h, q.ctypes.data_as(L.u64p), query.dimension,
+           out.ctypes.data_as(L.f32p))
+    return out
+
+
+def binary_dot(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:178 (pairwise; 1-code corpus)
+    assert a.dimension == b.dimension
+    if a.dimension == 0:
+        return 0
+    return int(binary_dot_all(a, BinaryCorpus.from_codes([b]))[0])
+
+
+def binary_jaccard(a: PackedBinary, b: PackedBinary) -> float:  # src/binary.rs:198
+    assert a.dimension == b.dimension
+    if a.dimension == 0:
+        return 1.0
+    return float(binary_jaccard_all(a, BinaryCorpus.from_codes([b]))[0])
 
 
 def binary_hamming(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:154 (pairwise; 1-code corpus)

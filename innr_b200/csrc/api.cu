@@ -859,6 +859,46 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
   return INNR_OK;
 }
 
+// binary_dot / binary_jaccard of one query against every code (src/binary.rs:178-213)
+static int binary_setop_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits, bool jaccard,
+                            void* out_host) {
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "dimension mismatch");  // assert_eq!(a.dimension, b.dimension)
+  if (c->n == 0) return INNR_OK;
+  if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  if (c->words == 0) {  // no words: intersection 0, union 0 -> dot 0, jaccard 1.0
+    for (size_t i = 0; i < c->n; ++i) {
+      if (jaccard) ((float*)out_host)[i] = 1.0f; else ((uint32_t*)out_host)[i] = 0u;
+    }
+    return INNR_OK;
+  }
+  rc = stage_binary_queries(*ctx, c, query_words, 1);
+  if (rc) return rc;
+  CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
+  Timed tm(*ctx);
+  if (jaccard)
+    CU(launch_binary_jaccard_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (float*)ctx->d_scores.p, ctx->stream, &g_launches));
+  else
+    CU(launch_binary_dot_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (uint32_t*)ctx->d_scores.p, ctx->stream, &g_launches));
+  tm.stop();
+  CU(cudaMemcpyAsync(out_host, ctx->d_scores.p, c->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+int innr_cuda_binary_dot_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                             uint32_t* out_host) {
+  return binary_setop_all(c, query_words, query_dim_bits, false, out_host);
+}
+int innr_cuda_binary_jaccard_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
+                                 float* out_host) {
+  return binary_setop_all(c, query_words, query_dim_bits, true, out_host);
+}
+
 int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
                            size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,
                            size_t* out_count) {

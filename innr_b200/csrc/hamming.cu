@@ -150,6 +150,42 @@ __global__ void encode_binary_kernel(const float* __restrict__ values, size_t n,
   }
 }
 
+// binary_dot (src/binary.rs:178-185) and binary_jaccard (:198-213) of one query against every code: same scan shape,
+// AND / OR instead of XOR. JACCARD: intersection as f32 / union as f32, 1.0 when the union is empty.
+template <bool JACCARD>
+__global__ void __launch_bounds__(HAM_THREADS) binary_setops_kernel(const HamArgs a, float* __restrict__ jaccard_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sq = reinterpret_cast<uint4*>(smem_raw);
+  for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
+    uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
+    sq[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+  }
+  __syncthreads();
+  const unsigned i = blockIdx.x * HAM_THREADS + threadIdx.x;
+  if (i >= a.n) return;
+  const uint4* p = a.data + i;
+  unsigned inter = 0, uni = 0;
+  unsigned c = 0;
+  for (; c + 4 <= a.chunks; c += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ldg_stream_u4(p + (size_t)(c + u) * a.ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 q = sq[c + u];
+      inter += __popc(v[u].x & q.x) + __popc(v[u].y & q.y) + __popc(v[u].z & q.z) + __popc(v[u].w & q.w);
+      if (JACCARD) uni += __popc(v[u].x | q.x) + __popc(v[u].y | q.y) + __popc(v[u].z | q.z) + __popc(v[u].w | q.w);
+    }
+  }
+  for (; c < a.chunks; ++c) {
+    const uint4 v = ldg_stream_u4(p + (size_t)c * a.ld), q = sq[c];
+    inter += __popc(v.x & q.x) + __popc(v.y & q.y) + __popc(v.z & q.z) + __popc(v.w & q.w);
+    if (JACCARD) uni += __popc(v.x | q.x) + __popc(v.y | q.y) + __popc(v.z | q.z) + __popc(v.w | q.w);
+  }
+  if (JACCARD) jaccard_out[i] = uni == 0 ? 1.0f : __fdiv_rn(__uint2float_rn(inter), __uint2float_rn(uni));
+  else a.dist_out[i] = inter;
+}
+
 template <int CHUNKS_CT, int R, bool TOPK>
 cudaError_t launch_ham(const HamArgs& a, size_t smem, int num_sms, cudaStream_t s) {
   auto kern = hamming_kernel<CHUNKS_CT, R, TOPK>;
@@ -216,6 +252,25 @@ cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words
   cudaError_t e = (v.chunks == 8) ? launch_ham<8, 1, false>(a, smem, 148, s) : launch_ham<0, 1, false>(a, smem, 148, s);
   if (e == cudaSuccess) ++*launches;
   return e;
+}
+
+cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
+                                  cudaStream_t s, uint64_t* launches) {
+  if (v.n == 0) return cudaSuccess;
+  HamArgs a = make_args(v, dev_query_words);
+  a.dist_out = dev_out;
+  binary_setops_kernel<false><<<a.n_tiles, HAM_THREADS, v.chunks * sizeof(uint4), s>>>(a, nullptr);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_query_words, float* dev_out,
+                                      cudaStream_t s, uint64_t* launches) {
+  if (v.n == 0) return cudaSuccess;
+  HamArgs a = make_args(v, dev_query_words);
+  binary_setops_kernel<true><<<a.n_tiles, HAM_THREADS, v.chunks * sizeof(uint4), s>>>(a, dev_out);
+  ++*launches;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,

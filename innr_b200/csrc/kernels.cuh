@@ -109,6 +109,10 @@ cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, 
                                    uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
                                cudaStream_t s, uint64_t* launches);
+cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
+                                  cudaStream_t s, uint64_t* launches);
+cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_query_words, float* dev_out,
+                                      cudaStream_t s, uint64_t* launches);
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
                                 uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,

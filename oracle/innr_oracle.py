@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
             "innr_ref_packed_binary_mask": (None, [_u64p, sz]),
             "innr_ref_encode_binary": (None, [_f32p, sz, f32, _u64p]),
             "innr_ref_binary_hamming": (C.c_uint32, [_u64p, _u64p, sz]),
+            "innr_ref_binary_dot": (C.c_uint32, [_u64p, _u64p, sz]),
+            "innr_ref_binary_jaccard": (C.c_float, [_u64p, _u64p, sz]),
             "innr_ref_hamming_topk": (sz, [_u64p, _u64p, sz, sz, sz, _u64p, _u32p]),
             "innr_ref_qparams_from_range": (None, [f32, f32, _f32p, _f32p]),
             "innr_ref_qparams_fit": (None, [_f32p, sz, _f32p, _f32p]),
@@ -416,6 +418,16 @@ def binary_hamming(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:15
     assert a.dimension == b.dimension, (
         f"innr::binary_hamming: dimension mismatch ({a.dimension} vs {b.dimension})")
     return int(lib().innr_ref_binary_hamming(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
+
+
+def binary_dot(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:178
+    assert a.dimension == b.dimension
+    return int(lib().innr_ref_binary_dot(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
+
+
+def binary_jaccard(a: PackedBinary, b: PackedBinary) -> float:  # src/binary.rs:198
+    assert a.dimension == b.dimension
+    return float(lib().innr_ref_binary_jaccard(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
 
 
 def hamming_topk(query_words, codes, k):

@@ -888,6 +888,17 @@ uint32_t innr_ref_binary_hamming(const uint64_t* a, const uint64_t* b, size_t wo
   for (size_t w = 0; w < words; ++w) s += (uint32_t)__builtin_popcountll(a[w] ^ b[w]);
   return s;
 }
+uint32_t innr_ref_binary_dot(const uint64_t* a, const uint64_t* b, size_t words) {  // src/binary.rs:178-185
+  uint32_t s = 0;
+  for (size_t w = 0; w < words; ++w) s += (uint32_t)__builtin_popcountll(a[w] & b[w]);
+  return s;
+}
+float innr_ref_binary_jaccard(const uint64_t* a, const uint64_t* b, size_t words) {  // src/binary.rs:198-213
+  const uint32_t inter = innr_ref_binary_dot(a, b, words);
+  uint32_t uni = 0;
+  for (size_t w = 0; w < words; ++w) uni += (uint32_t)__builtin_popcountll(a[w] | b[w]);
+  return uni == 0 ? 1.0f : (float)inter / (float)uni;  // intersection as f32 / union as f32
+}
 size_t innr_ref_hamming_topk(const uint64_t* q, const uint64_t* codes, size_t n, size_t words, size_t k,
                              uint64_t* out_idx, uint32_t* out_dist) {
   if (n == 0 || k == 0) return 0;

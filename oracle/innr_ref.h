@@ -121,6 +121,8 @@ void innr_ref_maxsim_corpus(const float* q, size_t nq, const float* tokens, cons
 void innr_ref_packed_binary_mask(uint64_t* words, size_t dim_bits);
 void innr_ref_encode_binary(const float* v, size_t n, float threshold, uint64_t* out_words); /* :133-141 */
 uint32_t innr_ref_binary_hamming(const uint64_t* a, const uint64_t* b, size_t words);         /* :154-165 */
+uint32_t innr_ref_binary_dot(const uint64_t* a, const uint64_t* b, size_t words);             /* :178-185 */
+float innr_ref_binary_jaccard(const uint64_t* a, const uint64_t* b, size_t words);            /* :198-213 */
 /* caller composition examples/binary_demo.rs:174-180: all distances, stable sort_by_key, take k */
 size_t innr_ref_hamming_topk(const uint64_t* q, const uint64_t* codes, size_t n, size_t words, size_t k,
                              uint64_t* out_idx, uint32_t* out_dist);

@@ -230,6 +230,27 @@ def test_hamming_generator_and_multi_query(ib, oracle):
     assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
 
 
+@pytest.mark.parametrize("dim", [1, 63, 64, 65, 200, 768, 1024])
+def test_binary_dot_jaccard_scans_exact(ib, oracle, dim):
+    """binary_dot / binary_jaccard (src/binary.rs:178-213) of one query against a corpus: integer-exact intersection,
+    bit-exact f32 quotient, empty-union convention 1.0."""
+    n = 3001
+    rng = np.random.default_rng(dim)
+    words = (dim + 63) // 64
+    codes = rng.integers(0, 2**63, size=(n, words), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, words), dtype=np.uint64)
+    codes[5] = 0                       # empty code
+    q = rng.integers(0, 2**63, size=words, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    gq, oq = ib.PackedBinary(q.copy(), dim), oracle.PackedBinary(q.copy(), dim)
+    corpus = ib.BinaryCorpus.from_words(codes, n, dim)
+    got_dot, got_j = ib.binary_dot_all(gq, corpus), ib.binary_jaccard_all(gq, corpus)
+    for i in range(0, n, 13):
+        oc = oracle.PackedBinary(codes[i].copy(), dim)
+        assert int(got_dot[i]) == oracle.binary_dot(oq, oc), (dim, i)
+        assert np.float32(got_j[i]).tobytes() == np.float32(oracle.binary_jaccard(oq, oc)).tobytes(), (dim, i)
+    z = ib.PackedBinary.zeros(dim)
+    assert float(ib.binary_jaccard_all(z, corpus)[5]) == 1.0 and int(ib.binary_dot_all(z, corpus)[5]) == 0
+
+
 # ------------------------------------------------------------------------------------------------ filtered / pruning
 @pytest.mark.parametrize("n,d,sel", [(5000, 33, 0.5), (70001, 16, 0.01), (4097, 128, 0.9), (300, 7, 0.0), (2049, 5, 1.0)])
 def test_knn_filtered_bit_exact(ib, oracle, n, d, sel):

@@ -92,3 +92,40 @@ def test_hamming_topk_composition_small(api, oracle):  # examples/binary_demo.rs
     want = sorted(range(n), key=lambda i: (full[i], i))[:k]       # stable sort_by_key == (h, index)
     assert [int(i) for i in idx] == want
     assert [int(d) for d in dist] == [full[i] for i in want]
+
+
+# ---- binary_dot / binary_jaccard: src/binary.rs:228-244, 330-372, 444-474, doc tests :170-174, :190-196
+def test_dot_jaccard_basic(api):
+    a, b = api.PackedBinary.zeros(4), api.PackedBinary.zeros(4)
+    a.set(0, True); a.set(1, True)
+    b.set(1, True); b.set(2, True)
+    assert api.binary_hamming(a, b) == 2
+    assert api.binary_dot(a, b) == 1
+    assert abs(api.binary_jaccard(a, b) - 1.0 / 3.0) < 1e-6
+
+
+def test_multi_word_dot_jaccard(api):
+    a, b = api.PackedBinary.zeros(128), api.PackedBinary.zeros(128)
+    for i in (0, 64, 65):
+        a.set(i, True)
+    for i in (0, 64, 100):
+        b.set(i, True)
+    assert api.binary_dot(a, b) == 2
+    assert abs(api.binary_jaccard(a, b) - 0.5) < 1e-6
+
+
+def test_dot_self_jaccard_identical_disjoint_empty(api):
+    v = api.encode_binary([1.0, -1.0, 1.0, -1.0, 1.0], 0.0)
+    assert api.binary_dot(v, v) == 3
+    v = api.encode_binary([1.0, -1.0, 1.0], 0.0)
+    assert abs(api.binary_jaccard(v, v) - 1.0) < 1e-6
+    a, b = api.encode_binary([1.0, -1.0], 0.0), api.encode_binary([-1.0, 1.0], 0.0)
+    assert abs(api.binary_jaccard(a, b)) < 1e-6
+    assert abs(api.binary_jaccard(api.PackedBinary.zeros(4), api.PackedBinary.zeros(4)) - 1.0) < 1e-6
+
+
+def test_dot_jaccard_doc_examples(api):
+    a = api.encode_binary([1.0, -1.0, 1.0, -1.0], 0.0)
+    b = api.encode_binary([1.0, 1.0, -1.0, -1.0], 0.0)
+    assert api.binary_dot(a, b) == 1
+    assert abs(api.binary_jaccard(a, b) - 1.0 / 3.0) < 1e-6
