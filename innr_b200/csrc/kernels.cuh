@@ -148,7 +148,7 @@ struct TokView {
   bool tmap_valid;
   const float* inv_norms;       // per token 1/||x|| (0 when ||x||^2 <= 1e-18), computed once at upload; may be null
 };
-// tcgen05 path (maxsim_tc.cu): dim == 128, 1 <= n_q <= 32
+// tcgen05 path (maxsim_tc.cu): dim in {32, 64, 96, 128}, 1 <= n_q <= 256 (one corpus pass per 32 query tokens)
 bool maxsim_tc_supported(const TokView& v, size_t n_q);
 cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
                              int num_sms, cudaStream_t s, uint64_t* launches);

@@ -39,20 +39,27 @@ using namespace tc;
 constexpr int TC_THREADS = 320;   // 4 epilogue + 4 converter + TMA + MMA warps
 constexpr int TILE_M = 128;                 // tokens per tile (UMMA M)
 constexpr int CHUNK = 32;                   // tokens per stream per tile (one TMEM lane quadrant)
-constexpr int DIM = 128;                    // K
 constexpr int NQ = 32;                      // query tokens (padded)
 constexpr int UMMA_N = 64;                  // [Qhi ; Qlo]
-constexpr int STAGES = 3;
+constexpr int ACC = 3;                      // TMEM accumulator stages (64 columns each)
+constexpr int MAX_STAGES = 8;
 constexpr int PANEL_BYTES = TILE_M * 128;   // 16 KB: [128 rows][32 floats], 128-byte swizzle
-constexpr int STAGE_BYTES = 4 * PANEL_BYTES;
 constexpr int BOX_BYTES = CHUNK * 128;      // one TMA box: 32 rows x 128 B
 constexpr int QPANEL_BYTES = UMMA_N * 128;  // 8 KB
-constexpr int QBYTES = 4 * QPANEL_BYTES;
 constexpr float EPS_SQ = 1e-9f * 1e-9f;
-constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo buffers of 128 columns
+constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo buffers of DIM (<= 128) columns
+
+// P = dim / 32 panels of 32 floats (dim 32, 64, 96, 128): the shared-memory ring deepens as the tile shrinks
+template <int P>
+struct Shape {
+  static constexpr int DIM = 32 * P;
+  static constexpr int STAGE_BYTES = P * PANEL_BYTES;
+  static constexpr int QBYTES = P * QPANEL_BYTES;
+  static constexpr int STAGES = P == 4 ? 3 : (P == 3 ? 4 : (P == 2 ? 6 : MAX_STAGES));
+};
 
 struct SharedTail {  // everything after the operand buffers
-  uint64_t full[STAGES], empty[STAGES], lo_ready[2], lo_free[2], tmem_full[STAGES], tmem_empty[STAGES];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], lo_ready[2], lo_free[2], tmem_full[ACC], tmem_empty[ACC];
   unsigned long long s_tok[5];  // token boundaries of the four streams
   unsigned s_doc[5];            // document boundaries of the four streams
   uint32_t tmem_base;
@@ -65,6 +72,7 @@ struct TcArgs {
   unsigned n_docs, n_q;
   const float* q;
   int debug_mode;  // 0 normal; 1 = TMA streaming only; 2 = hi pass only; 4 = no epilogue math (profiling aids)
+  int accumulate;  // 0: out[doc] = sum; 1: out[doc] += sum (second and later groups of 32 query tokens)
   float* out;
 };
 
@@ -120,12 +128,14 @@ __device__ __forceinline__ void addmul2(float& x0, float& x1, float y0, float y1
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 }
 
-template <bool COSINE>
+template <bool COSINE, int P>
 __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_constant__ CUtensorMap tm_tokens,
                                                                    const TcArgs a) {
+  constexpr int DIM = Shape<P>::DIM, STAGES = Shape<P>::STAGES, STAGE_BYTES = Shape<P>::STAGE_BYTES,
+                QBYTES = Shape<P>::QBYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_tok = smem;                                  // STAGES x 64 KB
-  uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // 32 KB
+  uint8_t* s_tok = smem;                                  // STAGES x (P x 16 KB)
+  uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // P x 8 KB
   SharedTail* st = reinterpret_cast<SharedTail*>(s_q + QBYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -163,8 +173,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&st->full[s], 1);
       mbar_init(&st->empty[s], 129);  // hi MMAs done reading (1 commit) + 128 converter threads done reading
-      mbar_init(&st->tmem_full[s], 1);
-      mbar_init(&st->tmem_empty[s], 4);
+    }
+    for (int t = 0; t < ACC; ++t) {
+      mbar_init(&st->tmem_full[t], 1);
+      mbar_init(&st->tmem_empty[t], 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&st->lo_ready[b], 128);
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
         for (int w = 0; w < 4; ++w) {
           const int r0 = (int)(row[w] < (long long)st->s_tok[w + 1] ? row[w] : last_row);  // rows past the matrix end are zero-filled
 #pragma unroll
-          for (int p = 0; p < 4; ++p) tma_load_2d(dst + p * PANEL_BYTES + w * BOX_BYTES, &tm_tokens, &st->full[s], p * 32, r0);
+          for (int p = 0; p < P; ++p) tma_load_2d(dst + p * PANEL_BYTES + w * BOX_BYTES, &tm_tokens, &st->full[s], p * 32, r0);
           row[w] += CHUNK;
         }
       }
@@ -232,9 +244,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQ);
     const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(s_q));
     const uint64_t a_desc0 = make_smem_desc_kmajor_sw128(smem_u32(s_tok));
-    auto issue_hi = [&](int s) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
+    auto issue_hi = [&](int s, int t) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
       const uint64_t ad0 = desc_advance(a_desc0, (uint32_t)s * STAGE_BYTES);
-      const uint32_t acc = tmem + s * UMMA_N;
+      const uint32_t acc = tmem + t * UMMA_N;
       umma_tf32_c<false>(acc, ad0, q_desc, idesc);
 #pragma unroll
       for (int kk = 1; kk < DIM / 8; ++kk)
@@ -259,14 +271,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     }
     if (a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
       for (unsigned i = 0; i < n_tiles; ++i) {
-        const int s = i % STAGES;
+        const int s = i % STAGES, t = i % ACC;
         mbar_wait(&st->full[s], (i / STAGES) & 1);
-        mbar_wait(&st->tmem_empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_wait(&st->tmem_empty[t], ((i / ACC) & 1) ^ 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          issue_hi(s);
+          issue_hi(s, t);
           umma_commit(&st->empty[s]);
-          umma_commit(&st->tmem_full[s]);
+          umma_commit(&st->tmem_full[t]);
         }
         __syncwarp();
       }
@@ -281,8 +293,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
         if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
           tc_fence_after_sync();
           if (elect_one_sync()) {
-            issue_lo(nl % STAGES, b);
-            umma_commit(&st->tmem_full[nl % STAGES]);  // accumulator complete for the epilogue
+            issue_lo(nl % ACC, b);
+            umma_commit(&st->tmem_full[nl % ACC]);  // accumulator complete for the epilogue
             umma_commit(&st->lo_free[b]);              // Xlo buffer may be overwritten
           }
           __syncwarp();
@@ -290,13 +302,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           progressed = true;
         }
       }
-      if (nh < n_tiles && nh < nl + STAGES) {  // hi(nh): X as loaded
-        const int s = nh % STAGES;
+      if (nh < n_tiles && nh < nl + ACC) {  // hi(nh): X as loaded
+        const int s = nh % STAGES, t = nh % ACC;
         if (mbar_try_wait(&st->full[s], (nh / STAGES) & 1) &&
-            mbar_try_wait(&st->tmem_empty[s], ((nh / STAGES) & 1) ^ 1)) {
+            mbar_try_wait(&st->tmem_empty[t], ((nh / ACC) & 1) ^ 1)) {
           tc_fence_after_sync();
           if (elect_one_sync()) {
-            issue_hi(s);
+            issue_hi(s, t);
             umma_commit(&st->empty[s]);  // 1 of 129: the tensor core has finished reading the stage
           }
           __syncwarp();
@@ -320,12 +332,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
       const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * DIM;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < P; ++p) {
         const uint8_t* pbase = base + p * PANEL_BYTES;
         float4 v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(pbase + ((c ^ (row & 7)) << 4));
-        if (p == 3) mbar_arrive(&st->empty[s]);  // this thread has read its whole row: 1 of 129
+        if (p == P - 1) mbar_arrive(&st->empty[s]);  // this thread has read its whole row: 1 of 129
         uint32_t lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -354,13 +366,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     for (int j = 0; j < NQ; ++j) carry[j] = -INFINITY;
     const unsigned n_q = a.n_q;
     for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
-      const int t = i % STAGES;
+      const int t = i % ACC;
       const unsigned long long c0 = s_lo + (unsigned long long)i * CHUNK;
       const unsigned long long g = c0 + lane;
       const bool active = c0 < s_hi;  // warp-uniform: this stream still has tokens in tile i
       float rt = 1.0f;
       if (COSINE && active) rt = g < s_hi ? __ldg(a.inv_norms + g) : 0.0f;
-      mbar_wait_sleepy(&st->tmem_full[t], (i / STAGES) & 1);
+      mbar_wait_sleepy(&st->tmem_full[t], (i / ACC) & 1);
       tc_fence_after_sync();
       uint32_t rh[32], rl[32];
       if (active) {
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
             if (j < (int)n_q) total += carry[j];
             carry[j] = -INFINITY;
           }
-          if (lane == 0) a.out[cur_doc] = total;
+          if (lane == 0) a.out[cur_doc] = a.accumulate ? a.out[cur_doc] + total : total;
         }
         pos = seg_end;
       }
@@ -447,7 +459,7 @@ __global__ void token_inv_norms_kernel(const float* __restrict__ tokens, size_t 
 }  // namespace
 
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim) {
-  if (dim != DIM || total_tokens == 0) return false;
+  if (dim == 0 || dim % 32 != 0 || dim > 128 || total_tokens == 0) return false;
   return make_tmap_f32_rows(m, dev_tokens, total_tokens, dim, CHUNK);
 }
 
@@ -459,24 +471,40 @@ cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens,
   return cudaGetLastError();
 }
 
-size_t maxsim_tc_smem_bytes() { return (size_t)STAGES * STAGE_BYTES + QBYTES + sizeof(SharedTail); }
-
+// dim 32 / 64 / 96 / 128; more than 32 query tokens: one corpus pass per group of 32 (the sum over query tokens is
+// additive across groups)
 bool maxsim_tc_supported(const TokView& v, size_t n_q) {
-  return v.dim == DIM && n_q >= 1 && n_q <= NQ && v.total_tokens > 0 && v.tmap_valid && v.inv_norms != nullptr &&
-         v.total_tokens < 0x7FFFFF00ull;
+  return v.dim >= 32 && v.dim <= 128 && v.dim % 32 == 0 && n_q >= 1 && n_q <= 8 * NQ && v.total_tokens > 0 &&
+         v.tmap_valid && v.inv_norms != nullptr && v.total_tokens < 0x7FFFFF00ull;
 }
 
-cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
-                             int num_sms, cudaStream_t s, uint64_t* launches) {
+namespace {
+template <bool COSINE, int P>
+cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
+  constexpr size_t smem = (size_t)Shape<P>::STAGES * Shape<P>::STAGE_BYTES + Shape<P>::QBYTES + sizeof(SharedTail);
   static bool attr_set = false;
-  const size_t smem = maxsim_tc_smem_bytes();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(maxsim_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  maxsim_tc_kernel<COSINE, P><<<grid, TC_THREADS, smem, s>>>(tm, a);
+  return cudaGetLastError();
+}
+template <bool COSINE>
+cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
+  switch (dim) {
+    case 32: return launch_shape<COSINE, 1>(tm, a, grid, s);
+    case 64: return launch_shape<COSINE, 2>(tm, a, grid, s);
+    case 96: return launch_shape<COSINE, 3>(tm, a, grid, s);
+    case 128: return launch_shape<COSINE, 4>(tm, a, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+}  // namespace
+
+cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
+                             int num_sms, cudaStream_t s, uint64_t* launches) {
   // empty documents never see a token: their score is 0.0 (src/maxsim.rs:97-99)
   cudaError_t e = cudaMemsetAsync(dev_scores, 0, v.n_docs * sizeof(float), s);
   if (e != cudaSuccess) return e;
@@ -486,8 +514,6 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   a.uniform_tokens = v.uniform_tokens;
   a.total_tokens = v.total_tokens;
   a.n_docs = (unsigned)v.n_docs;
-  a.n_q = (unsigned)n_q;
-  a.q = dev_q;
   a.out = dev_scores;
   static const int dbg = getenv("INNR_MAXSIM_DEBUG") ? atoi(getenv("INNR_MAXSIM_DEBUG")) : 0;
   a.debug_mode = dbg;
@@ -496,10 +522,15 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   if (grid > tiles) grid = (unsigned)tiles;
   if (grid > v.n_docs) grid = (unsigned)v.n_docs;
   if (grid == 0) grid = 1;
-  if (cosine) maxsim_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(v.tmap, a);
-  else maxsim_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(v.tmap, a);
-  ++*launches;
-  return cudaGetLastError();
+  for (size_t q0 = 0; q0 < n_q; q0 += NQ) {
+    a.n_q = (unsigned)(n_q - q0 < NQ ? n_q - q0 : NQ);
+    a.q = dev_q + q0 * v.dim;
+    a.accumulate = q0 > 0;
+    e = cosine ? launch_dim<true>(v.dim, v.tmap, a, grid, s) : launch_dim<false>(v.dim, v.tmap, a, grid, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace innr

@@ -455,6 +455,27 @@ def test_maxsim_tc_stream_edges(ib, oracle, shape, nq):
         assert np.all(got[lens == 0] == 0.0)
 
 
+@pytest.mark.parametrize("dim", [32, 64, 96, 128])
+@pytest.mark.parametrize("nq", [1, 33, 64, 100])
+def test_maxsim_tc_dims_and_query_groups(ib, oracle, dim, nq):
+    """tcgen05 path at every supported token dimension, and with more than 32 query tokens (one corpus pass per group
+    of 32, partial sums accumulated per document) -- the reference's own bench shapes use 32 and 64 query tokens
+    (benches/maxsim.rs:21,44)."""
+    rng = np.random.default_rng(dim * 7 + nq)
+    lens = np.concatenate([rng.integers(0, 300, size=120), [0, 1, 700]])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    toks = rng.standard_normal((int(off[-1]), dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    corpus = ib.TokenCorpus.from_tokens(toks, off, dim)
+    for cos in (False, True):
+        got = ib.maxsim_corpus(q, corpus, cosine=cos)
+        want = oracle.maxsim_corpus(q, toks, off, cosine_flag=cos)
+        scale = _maxsim_scale(q, toks, off) if not cos else np.full(len(lens), float(nq))
+        err = np.abs(got.astype(np.float64) - want)
+        assert np.all(err <= 1e-5 * scale + 1e-6), (dim, nq, cos, float(err.max()))
+        assert np.all(got[lens == 0] == 0.0)
+
+
 def test_maxsim_tc_nan_and_zero_tokens(ib, oracle):
     """NaN scores never replace the running max (`>` compare, x86_64.rs:135); a document whose every score is NaN sums
     -inf; zero-norm tokens and zero-norm query tokens give cosine 0.0 (x86_64.rs:781-785)."""
