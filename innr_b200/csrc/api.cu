@@ -522,9 +522,27 @@ static int knn_tc_prepare(innr_cuda_corpus* c, DeviceCtx* ctx, const PdxView& v,
   return INNR_OK;
 }
 
+// k > 128: one scores pass per query, then rounds of the generic selection over the score vector (scan_f32.cu:
+// launch_topk_from_scores). Exact for any k <= N; the corpus is read once per query, the 4 B/vector score array
+// once per 128 results.
+static int big_k_from_scores(DeviceCtx* ctx, const void* dev_scores, int kind, size_t n, uint64_t index_base, size_t k,
+                             uint64_t* dev_keys, cudaStream_t s) {
+  CU(launch_topk_from_scores(dev_scores, kind, n, (uint32_t)index_base, k, dev_keys, ctx->ws, s, &g_launches));
+  return INNR_OK;
+}
+
 static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
                         uint64_t* dev_keys, cudaStream_t s) {
   PdxView v = pdx_view(c);
+  if (k > MAX_FUSED_K) {
+    CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+    for (size_t q = 0; q < nq; ++q) {
+      CU(launch_pdx_scores(v, mode, dev_queries + q * c->d, nullptr, (float*)ctx->d_scores.p, ctx->ws, s, &g_launches));
+      int rc = big_k_from_scores(ctx, ctx->d_scores.p, mode == PDX_L2 ? 0 : 1, c->n, c->index_base, k, dev_keys + q * k, s);
+      if (rc) return rc;
+    }
+    return INNR_OK;
+  }
   if (g_opt.knn_tc && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries && knn_tc_supported(v, mode, nq, k)) {
     int rc = knn_tc_prepare(c, ctx, v, s);
     if (rc) return rc;
@@ -564,7 +582,6 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;                           // src/batch.rs:388-393
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;                                               // k.min(num_vectors)
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
@@ -607,7 +624,7 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
   }
   if (passing == 0) return INNR_OK;                                                     // :842-847
   const size_t kk = k < passing ? k : passing;                                          // k.min(num_passing)
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
+  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "batch_knn_filtered: k > 128 is not covered yet");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
@@ -691,7 +708,6 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
   int rc = metric_to_mode(metric, &mode);
   if (rc) return rc;
   if (k == 0 || n_queries == 0) return INNR_OK;
-  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
@@ -707,7 +723,7 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
 int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,
                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, void* stream) {
   if (k == 0 || n_queries == 0 || n_lists == 0) return INNR_OK;
-  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "merge of more than 128 keys per list is not covered yet (sharded k > 128)");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
@@ -725,7 +741,6 @@ int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, ui
   int rc = check_index_range(n, 0);
   if (rc) return rc;
   const size_t kk = k < n ? k : n;
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   rc = current_ctx(&ctx);
@@ -899,6 +914,21 @@ int innr_cuda_binary_jaccard_all(const innr_cuda_corpus* c, const uint64_t* quer
   return binary_setop_all(c, query_words, query_dim_bits, true, out_host);
 }
 
+static int hamming_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const uint64_t* dev_query_words, size_t nq, size_t k,
+                        uint64_t* dev_keys, cudaStream_t s) {
+  if (k <= MAX_FUSED_K) {
+    CU(launch_hamming_topk(bin_view(c), dev_query_words, nq, k, dev_keys, ctx->ws, s, &g_launches));
+    return INNR_OK;
+  }
+  CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
+  for (size_t q = 0; q < nq; ++q) {
+    CU(launch_hamming_all(bin_view(c), dev_query_words + q * 2 * c->chunks, (uint32_t*)ctx->d_scores.p, s, &g_launches));
+    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 2, c->n, c->index_base, k, dev_keys + q * k, s);
+    if (rc) return rc;
+  }
+  return INNR_OK;
+}
+
 int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
                            size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,
                            size_t* out_count) {
@@ -908,7 +938,6 @@ int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_word
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_dist || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
@@ -926,8 +955,8 @@ int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_word
   if (rc) return rc;
   CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
   Timed tm(*ctx);
-  CU(launch_hamming_topk(bin_view(c), (const uint64_t*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p,
-                         ctx->ws, ctx->stream, &g_launches));
+  rc = hamming_keys(c, ctx, (const uint64_t*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p, ctx->stream);
+  if (rc) return rc;
   tm.stop();
   rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
     for (size_t q = 0; q < n_queries; ++q)
@@ -945,7 +974,6 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
                                     size_t k, uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
@@ -955,8 +983,7 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  CU(launch_hamming_topk(bin_view(c), dev_query_words, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
-  return INNR_OK;
+  return hamming_keys(c, ctx, dev_query_words, n_queries, k, dev_keys, s);
 }
 
 int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words) {
@@ -1093,6 +1120,21 @@ int innr_cuda_asymmetric_dot_u8_all(const innr_cuda_corpus* c, const float* quer
   return u8_scores(c, 1, query, query_len, out_host, "asymmetric_dot_u8: dimension mismatch");
 }
 
+static int u8_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const float* dev_queries, size_t nq, size_t k,
+                   uint64_t* dev_keys, cudaStream_t s) {
+  if (k <= MAX_FUSED_K) {
+    CU(launch_u8_knn(u8_view(c), dev_queries, nq, k, dev_keys, ctx->ws, s, &g_launches));
+    return INNR_OK;
+  }
+  CU(ctx->d_scores.reserve(c->n * sizeof(float)));
+  for (size_t q = 0; q < nq; ++q) {
+    CU(launch_u8_scores(u8_view(c), 1, dev_queries + q * c->d, (float*)ctx->d_scores.p, s, &g_launches));
+    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 1, c->n, c->index_base, k, dev_keys + q * k, s);
+    if (rc) return rc;
+  }
+  return INNR_OK;
+}
+
 int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size_t n_queries, size_t query_len,
                            size_t k, uint64_t* out_idx, float* out_score, size_t* out_count) {
   if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
@@ -1101,7 +1143,6 @@ int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size
   if (query_len != c->d) return fail(INNR_EINVAL, "asymmetric_dot_u8_precomputed: dimension mismatch");
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128 is not covered by the fused selection yet");
   if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
@@ -1111,8 +1152,8 @@ int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size
   CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
   CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   Timed tm(*ctx);
-  CU(launch_u8_knn(u8_view(c), (const float*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
-                   ctx->stream, &g_launches));
+  rc = u8_keys(c, ctx, (const float*)ctx->d_query.p, n_queries, kk, (uint64_t*)ctx->d_keys.p, ctx->stream);
+  if (rc) return rc;
   tm.stop();
   rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
     for (size_t q = 0; q < n_queries; ++q) decode_keys_f32(keys + q * kk, kk, true, out_idx + q * k, out_score + q * k);
@@ -1126,7 +1167,6 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
                                     uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "k > 128");
   std::lock_guard<std::mutex> lk(g_mu);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
@@ -1136,8 +1176,7 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  CU(launch_u8_knn(u8_view(c), dev_queries, n_queries, k, dev_keys, ctx->ws, s, &g_launches));
-  return INNR_OK;
+  return u8_keys(c, ctx, dev_queries, n_queries, k, dev_keys, s);
 }
 
 // ------------------------------------------------------------------------------------------ MaxSim

@@ -66,6 +66,10 @@ cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t ind
 cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
                               uint64_t* launches);
+// k smallest keys of a device score vector for ANY k (rounds of <= 128): kind 0 f32 ascending, 1 f32 descending,
+// 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128.
+cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
 // keys from a plain f32 array (TopK analogue): ascending, id = i
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, uint64_t* launches);

@@ -396,6 +396,7 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
     case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_L2_PRUNE: e = launch_one<PDX_L2_PRUNE, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
+    case PDX_COSINE_FUSED: e = launch_one<PDX_COSINE_FUSED, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     default: return cudaErrorInvalidValue;
   }
   if (e == cudaSuccess) ++*launches;
@@ -431,10 +432,16 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int 
   }
 }
 
-template <int R>
-__global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const float* dist, unsigned n, int k,
-                                                                     uint64_t* partials, uint64_t* group_partials,
-                                                                     uint64_t* out_keys, unsigned* tickets) {
+// Selection over a device score vector. KIND 0: f32 ascending (TopK analogue / L2), 1: f32 descending (dot, cosine,
+// u8), 2: u32 ascending (Hamming). Keys carry index_base + i. `floor_key` (device, may be null) makes the launch one
+// ROUND of a larger selection: only keys strictly greater than *floor_key take part, so consecutive rounds of <= 128
+// keys each, every one starting above the last key of the round before, enumerate the k smallest keys for any k
+// (keys are unique: the index is their low half).
+template <int R, int KIND>
+__global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* scores, unsigned n, unsigned index_base,
+                                                                  int k, const uint64_t* floor_key, uint64_t* partials,
+                                                                  uint64_t* group_partials, uint64_t* out_keys,
+                                                                  unsigned* tickets) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* smem_keys = reinterpret_cast<uint64_t*>(smem_raw);
   const int lane = threadIdx.x & 31;
@@ -442,13 +449,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_distances_kernel(const floa
   uint64_t thrs[1];
   lists[0].init();
   thrs[0] = KEY_SENTINEL;
+  const bool has_floor = floor_key != nullptr;
+  const uint64_t floor = has_floor ? *floor_key : 0ull;
   // grid-stride over whole warps so every lane reaches the ballots together
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned n_round = (n + 31u) / 32u * 32u;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool valid = i < n;
-    const float dv = valid ? dist[i] : 0.0f;
-    lists[0].offer(make_key_asc(dv, i), valid, thrs[0], k, lane);
+    bool valid = i < n;
+    uint64_t key = KEY_SENTINEL;
+    if (valid) {
+      if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], index_base + i);
+      else if (KIND == 1) key = make_key_desc(static_cast<const float*>(scores)[i], index_base + i);
+      else key = make_key_asc(static_cast<const float*>(scores)[i], index_base + i);
+      valid = !has_floor || (key > floor && floor != KEY_SENTINEL);
+    }
+    lists[0].offer(key, valid, thrs[0], k, lane);
   }
   block_finish<R, 1>(lists, 1, k, smem_keys, partials, group_partials, out_keys, tickets);
 }
@@ -592,22 +607,38 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
   return cudaGetLastError();
 }
 
-cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
-                                       Workspace& ws, cudaStream_t s, uint64_t* launches) {
-  if (k > 128) return cudaErrorInvalidValue;
+// k keys of a score vector, any k: rounds of <= 128 keys, each bounded below by the last key of the round before
+// (read on the device: no host synchronisation between rounds)
+cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
   unsigned grid = (unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS);
   unsigned cap = (unsigned)ws.num_sms * 4u;
   if (grid > cap) grid = cap;
   if (grid == 0) grid = 1;
-  size_t smem = (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t);
-  if (k <= 32)
-    topk_distances_kernel<1><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
-                                                              ws.group_partials, dev_keys, ws.tickets);
-  else
-    topk_distances_kernel<4><<<grid, SCAN_THREADS, smem, s>>>(dev_dist, (unsigned)n, (int)k, ws.partials,
-                                                              ws.group_partials, dev_keys, ws.tickets);
-  ++*launches;
-  return cudaGetLastError();
+  for (size_t done = 0; done < k; done += 128) {
+    const int kr = (int)std::min<size_t>(128, k - done);
+    const uint64_t* floor = done ? dev_keys + done - 1 : nullptr;
+    uint64_t* out = dev_keys + done;
+    const size_t smem = (size_t)(SCAN_THREADS / 32) * kr * sizeof(uint64_t);
+#define INNR_TOPK_LAUNCH(R, KIND)                                                                                   \
+  topk_scores_kernel<R, KIND><<<grid, SCAN_THREADS, smem, s>>>(dev_scores, (unsigned)n, index_base, kr, floor,       \
+                                                               ws.partials, ws.group_partials, out, ws.tickets)
+    if (kr <= 32) {
+      if (kind == 0) INNR_TOPK_LAUNCH(1, 0); else if (kind == 1) INNR_TOPK_LAUNCH(1, 1); else INNR_TOPK_LAUNCH(1, 2);
+    } else {
+      if (kind == 0) INNR_TOPK_LAUNCH(4, 0); else if (kind == 1) INNR_TOPK_LAUNCH(4, 1); else INNR_TOPK_LAUNCH(4, 2);
+    }
+#undef INNR_TOPK_LAUNCH
+    ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
+                                       Workspace& ws, cudaStream_t s, uint64_t* launches) {
+  return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches);
 }
 
 }  // namespace innr

@@ -251,6 +251,44 @@ def test_binary_dot_jaccard_scans_exact(ib, oracle, dim):
     assert float(ib.binary_jaccard_all(z, corpus)[5]) == 1.0 and int(ib.binary_dot_all(z, corpus)[5]) == 0
 
 
+# ------------------------------------------------------------------------------------------------ k > 128
+@pytest.mark.parametrize("k", [129, 300, 1000, 5000])
+def test_big_k_all_paths_exact(ib, oracle, k):
+    """k > 128 leaves the fused register lists: one scores pass, then rounds of <= 128 keys over the score vector,
+    each round bounded below by the last key of the round before. Same bits and order as the reference's full sort,
+    with heavy ties (integer-valued rows) and k > N."""
+    n, d = 4000, 24
+    rng = np.random.default_rng(k)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    q = rng.integers(-3, 4, size=d).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for name in ("batch_knn_dot", "batch_knn_cosine"):
+        got, want = getattr(ib, name)(q, gb, k), getattr(oracle, name)(q, ob, k)
+        assert len(got.indices) == min(k, n)
+        assert list(got.indices) == list(want.indices), name
+        assert np.array_equal(bits(got.scores), bits(want.scores)), name
+    assert_knn_equal(ib.batch_knn(q, gb, k), oracle.batch_knn(q, ob, k), ties_as_sets=True)
+    # Hamming
+    codes = rng.integers(0, 2**62, size=(n, 2), dtype=np.uint64)
+    qc = rng.integers(0, 2**62, size=2, dtype=np.uint64)
+    gi, gd = ib.hamming_topk(qc, codes, k)
+    wi, wd = oracle.hamming_topk(qc, codes, k)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    # u8
+    mat = rng.integers(0, 256, size=(n, 48), dtype=np.uint8)
+    q8 = rng.uniform(-1, 1, 48).astype(np.float32)
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    got = ib.batch_knn_u8(q8, ib.U8Corpus.from_rows(mat, gp), gp, k)
+    want = oracle.batch_knn_u8(q8, mat, op, k)
+    assert [i for i, _ in got] == [i for i, _ in want]
+    assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want]))
+    # TopK analogue
+    dist = rng.integers(0, 50, size=n).astype(np.float32)
+    got = ib.topk_from_distances(dist, k)
+    order = sorted(range(n), key=lambda i: (dist[i], i))[:k]
+    assert [i for i, _ in got] == order and [s for _, s in got] == [float(dist[i]) for i in order]
+
+
 # ------------------------------------------------------------------------------------------------ filtered / pruning
 @pytest.mark.parametrize("n,d,sel", [(5000, 33, 0.5), (70001, 16, 0.01), (4097, 128, 0.9), (300, 7, 0.0), (2049, 5, 1.0)])
 def test_knn_filtered_bit_exact(ib, oracle, n, d, sel):
