@@ -125,6 +125,13 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
  * ascending index order. Writes min(*out_count, capacity) pairs; *out_count is the number of survivors. */
 int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* query, size_t query_len, float threshold,
                                        uint64_t* out_idx, float* out_dist, size_t capacity, size_t* out_count);
+/* Re-rank stage of the reference's documented two-stage retrieval (src/scalar.rs:366-368 "Re-rank top candidates with
+ * exact batch_knn_dot", examples/binary_demo.rs:235-237 "binary retrieves top-1000 candidates, then rerank"): the exact
+ * batch_knn (L2) / batch_knn_dot / batch_knn_cosine result over the sub-batch formed by `candidates` (distinct global
+ * indices), with the original indices reported; scores bit-identical to the full scan's, ties -> lower index. */
+int innr_cuda_batch_knn_subset(const innr_cuda_corpus* c, int metric, const float* query, size_t query_len,
+                               const uint64_t* candidates, size_t n_candidates, size_t k, uint64_t* out_idx,
+                               float* out_score, size_t* out_count);
 /* Device-pointer form used for row-sharded corpora: writes the shard's local top-k as sorted 64-bit
  * composite keys (n_queries x k, padded with 0xFFFF...F) into dev_keys on `stream`. Keys from all shards
  * are exchanged by the caller (one allgather) and merged with innr_cuda_merge_keys_dev. */
@@ -151,6 +158,9 @@ int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, ui
 /* generator: word w of code r = splitmix64(salt + r*words + w) */
 int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t dim_bits,
                               uint64_t index_base, innr_cuda_corpus** out);
+/* encode_binary (src/binary.rs:133-141: bit = v > threshold) of every vector of a device-resident f32 corpus, without
+ * a host round trip; the code set inherits the corpus' index_base (one ingest, several encodings). */
+int innr_cuda_binary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out);
 /* binary_hamming (src/binary.rs:154) of the query against every code: out_host n x u32. query_dim_bits
  * must equal the corpus dimension (src/binary.rs:155-159). */
 int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
@@ -177,6 +187,8 @@ int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, fl
 /* G-hash f32 rows (salt + r*d + j) quantised on the device with quantize_u8's formula (src/scalar.rs:212-225) */
 int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
                           uint64_t index_base, innr_cuda_corpus** out);
+/* quantize_u8 (src/scalar.rs:212-225) of every vector of a device-resident f32 corpus, without a host round trip. */
+int innr_cuda_u8_from_f32(const innr_cuda_corpus* f32_corpus, float alpha, float offset, innr_cuda_corpus** out);
 /* quantize_u8 (src/scalar.rs:212-225) of a host f32 buffer */
 int innr_cuda_quantize_u8(const float* values, size_t n, float alpha, float offset, uint8_t* out_codes);
 /* mixed_dot_u8_f32 (src/scalar.rs:314) of the query against every row: out_host n floats */

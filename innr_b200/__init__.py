@@ -9,7 +9,7 @@ from ._lib import (InnrCudaError, backend_name, build, init, knn_tc_last_stats, 
                    launch_count, lib, set_option)
 from .backend import Backend, dense_backend  # noqa: F401
 from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, batch_dot, batch_knn,  # noqa: F401
-                    batch_knn_cosine, batch_knn_dot, batch_knn_filtered, batch_knn_many, batch_l2_squared,
+                    batch_knn_cosine, batch_knn_dot, batch_knn_filtered, batch_knn_many, batch_knn_subset, batch_l2_squared,
                     batch_l2_squared_pruning, batch_norms)
 from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, binary_hamming, binary_jaccard,  # noqa: F401
                      binary_jaccard_all, encode_binary, hamming_all,

@@ -52,6 +52,9 @@ SIGNATURES = {
     "innr_cuda_batch_norms": [vp, f32p],
     "innr_cuda_batch_cosine": [vp, f32p, sz, f32p, sz, f32p],
     "innr_cuda_batch_knn": [vp, ci, f32p, sz, sz, sz, u64p, f32p, szp],
+    "innr_cuda_batch_knn_subset": [vp, ci, f32p, sz, u64p, sz, sz, u64p, f32p, szp],
+    "innr_cuda_binary_from_f32": [vp, f32, handle_p],
+    "innr_cuda_u8_from_f32": [vp, f32, f32, handle_p],
     "innr_cuda_batch_knn_filtered": [vp, f32p, sz, sz, u64p, sz, u64p, f32p, szp],
     "innr_cuda_batch_l2_squared_pruning": [vp, f32p, sz, f32, u64p, f32p, sz, szp],
     "innr_cuda_batch_knn_keys_dev": [vp, ci, vp, sz, sz, vp, vp],

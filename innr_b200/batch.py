@@ -268,3 +268,21 @@ def batch_l2_squared_pruning(query, batch, threshold: float):  # src/batch.rs:32
            _ptr(ds, L.f32p), n, C.byref(cnt))
     m = cnt.value
     return [(int(idx[j]), float(ds[j])) for j in range(m)]
+
+
+def batch_knn_subset(metric: str, query, batch, candidates, k: int) -> BatchKnnResult:
+    """Exact re-rank of `candidates` (distinct global indices): the reference's batch_knn / batch_knn_dot /
+    batch_knn_cosine over the sub-batch of those vectors, original indices reported (second stage of the two-stage
+    retrieval the reference documents, src/scalar.rs:366-368, examples/binary_demo.rs:235-237)."""
+    dev = _dev(batch)
+    q = _f32(query).reshape(-1)
+    assert q.size == dev.dimension, "query.len() != batch.dimension"
+    cand = np.ascontiguousarray(candidates, dtype=np.uint64).reshape(-1)
+    kk = max(min(k, cand.size), 1)
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    cnt = C.c_size_t(0)
+    m = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
+    L.call("innr_cuda_batch_knn_subset", dev.h, m, _ptr(q, L.f32p), q.size, _ptr(cand, L.u64p), cand.size, k,
+           _ptr(idx, L.u64p), _ptr(sc, L.f32p), C.byref(cnt))
+    return BatchKnnResult(idx[:cnt.value], sc[:cnt.value])

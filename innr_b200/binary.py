@@ -86,6 +86,15 @@ class BinaryCorpus:
                               index_base)
 
     @classmethod
+    def from_f32(cls, batch, threshold: float = 0.0):
+        """encode_binary (src/binary.rs:133-141) of every vector of a device-resident f32 corpus, on the device."""
+        from .batch import _dev
+        dev = _dev(batch)
+        h = C.c_void_p()
+        L.call("innr_cuda_binary_from_f32", dev.h, C.c_float(threshold), C.byref(h))
+        return cls(_Handle(h), dev.num_vectors, dev.dimension, dev.index_base)
+
+    @classmethod
     def generate(cls, salt: int, first_row: int, n: int, dimension: int, index_base: int = 0):
         h = C.c_void_p()
         L.call("innr_cuda_generate_binary", salt, first_row, n, dimension, index_base, C.byref(h))

@@ -604,6 +604,51 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   return INNR_OK;
 }
 
+// Re-rank stage of the reference's two-stage pipeline (src/scalar.rs:366-368, examples/binary_demo.rs:235-237): exact
+// batch_knn / batch_knn_dot / batch_knn_cosine restricted to `candidates` (global indices, distinct), i.e. the result of
+// the reference function on the sub-batch of those vectors with their original indices reported; ties -> lower index.
+int innr_cuda_batch_knn_subset(const innr_cuda_corpus* c, int metric, const float* query, size_t query_len,
+                               const uint64_t* candidates, size_t n_candidates, size_t k, uint64_t* out_idx,
+                               float* out_score, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0 || n_candidates == 0) return INNR_OK;
+  if (!out_idx || !out_score || !candidates || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  for (size_t j = 0; j < n_candidates; ++j)
+    if (candidates[j] < c->index_base || candidates[j] - c->index_base >= c->n)
+      return fail(INNR_EINVAL, "batch_knn_subset: candidate index out of bounds");
+  const size_t kk = k < n_candidates ? k : n_candidates;
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  CU(ctx->d_aux.reserve(n_candidates * sizeof(uint32_t)));
+  CU(ctx->d_scores.reserve(n_candidates * sizeof(float)));
+  CU(ctx->h_pin.reserve(n_candidates * sizeof(uint32_t)));
+  uint32_t* h = (uint32_t*)ctx->h_pin.p;
+  for (size_t j = 0; j < n_candidates; ++j) h[j] = (uint32_t)candidates[j];
+  CU(cudaMemcpyAsync(ctx->d_aux.p, h, n_candidates * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (c->d) CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  CU(launch_subset_scores(pdx_view(c), mode, (const float*)ctx->d_query.p, (const uint32_t*)ctx->d_aux.p, n_candidates,
+                          (float*)ctx->d_scores.p, ctx->stream, &g_launches));
+  CU(launch_topk_from_scores(ctx->d_scores.p, mode == PDX_L2 ? 0 : 1, n_candidates, 0, kk, (uint64_t*)ctx->d_keys.p,
+                             ctx->ws, ctx->stream, &g_launches, (const uint32_t*)ctx->d_aux.p));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) {
+    decode_keys_f32(keys, kk, metric != INNR_METRIC_L2, out_idx, out_score);
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
 // batch_knn_filtered (src/batch.rs:820-882): the closure predicate crosses the ABI as a bitmask (bit i of word i/64,
 // LSB first, like PackedBinary). L2, stable ascending sort of the passing vectors, k clamped to their number.
 int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
@@ -874,6 +919,25 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
   return INNR_OK;
 }
 
+// encode_binary (src/binary.rs:133-141) of every vector of a device-resident f32 corpus, on the device: the derived
+// code set shares the f32 corpus' index_base, so first-pass indices feed innr_cuda_batch_knn_subset directly.
+int innr_cuda_binary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out) {
+  if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(f32_corpus, &ctx);
+  if (rc) return rc;
+  rc = alloc_binary(*ctx, f32_corpus->n, f32_corpus->d, f32_corpus->index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_binary_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, threshold,
+                              (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
 // binary_dot / binary_jaccard of one query against every code (src/binary.rs:178-213)
 static int binary_setop_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits, bool jaccard,
                             void* out_host) {
@@ -1049,6 +1113,24 @@ int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, fl
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_u8");
+  }
+  return INNR_OK;
+}
+
+// quantize_u8 (src/scalar.rs:212-225) of every vector of a device-resident f32 corpus, on the device
+int innr_cuda_u8_from_f32(const innr_cuda_corpus* f32_corpus, float alpha, float offset, innr_cuda_corpus** out) {
+  if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  std::lock_guard<std::mutex> lk(g_mu);
+  DeviceCtx* ctx;
+  int rc = ctx_for(f32_corpus, &ctx);
+  if (rc) return rc;
+  rc = alloc_u8(*ctx, f32_corpus->n, f32_corpus->d, alpha, offset, f32_corpus->index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_u8_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, alpha, offset,
+                          (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
   }
   return INNR_OK;
 }

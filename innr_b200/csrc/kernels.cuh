@@ -69,7 +69,11 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
 // k smallest keys of a device score vector for ANY k (rounds of <= 128): kind 0 f32 ascending, 1 f32 descending,
 // 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128.
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                                    const uint32_t* dev_ids = nullptr);
+// exact scores (mode = PDX_DOT / PDX_L2 / PDX_COSINE_FUSED) of m candidate vectors given by GLOBAL id
+cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
+                                 float* dev_out, cudaStream_t s, uint64_t* launches);
 // keys from a plain f32 array (TopK analogue): ascending, id = i
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, uint64_t* launches);
@@ -121,6 +125,8 @@ cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_word
                                 uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
                                  cudaStream_t s, uint64_t* launches);
+cudaError_t launch_binary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float threshold,
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
 
 // u8 codes (u8.cu): chunk-major layout codes[c * ld + i] (uint4 = 16 dims), chunks = ceil(d/16)
 struct U8View {
@@ -135,6 +141,8 @@ cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size
                                uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, float offset, uint8_t* dev_out,
                                cudaStream_t s, uint64_t* launches);
+cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float alpha, float offset,
+                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
 // mode 0: raw mixed dot, 1: asymmetric score
 cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
                              cudaStream_t s, uint64_t* launches);

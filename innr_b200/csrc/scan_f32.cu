@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int 
 // (keys are unique: the index is their low half).
 template <int R, int KIND>
 __global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* scores, unsigned n, unsigned index_base,
+                                                                  const uint32_t* ids,  // null: id = index_base + i
                                                                   int k, const uint64_t* floor_key, uint64_t* partials,
                                                                   uint64_t* group_partials, uint64_t* out_keys,
                                                                   unsigned* tickets) {
@@ -458,9 +459,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* s
     bool valid = i < n;
     uint64_t key = KEY_SENTINEL;
     if (valid) {
-      if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], index_base + i);
-      else if (KIND == 1) key = make_key_desc(static_cast<const float*>(scores)[i], index_base + i);
-      else key = make_key_asc(static_cast<const float*>(scores)[i], index_base + i);
+      const unsigned id = ids ? ids[i] : index_base + i;
+      if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], id);
+      else if (KIND == 1) key = make_key_desc(static_cast<const float*>(scores)[i], id);
+      else key = make_key_asc(static_cast<const float*>(scores)[i], id);
       valid = !has_floor || (key > floor && floor != KEY_SENTINEL);
     }
     lists[0].offer(key, valid, thrs[0], k, lane);
@@ -607,10 +609,80 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
   return cudaGetLastError();
 }
 
+namespace {
+// Exact scores of a SUBSET of the corpus (re-rank stage of a two-stage search: binary / u8 first pass -> exact f32,
+// src/scalar.rs:366-368, examples/binary_demo.rs:235-237). One thread per candidate, the reference's sequential unfused
+// arithmetic (same bits as the full scan); out-of-range candidates score the metric's worst value.
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS) subset_scores_kernel(const float* __restrict__ data, size_t ld, unsigned n,
+                                                                    unsigned d, unsigned index_base,
+                                                                    const float* __restrict__ query,
+                                                                    const uint32_t* __restrict__ cand, unsigned m,
+                                                                    float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  __shared__ float s_qn;
+  for (unsigned i = threadIdx.x; i < d; i += blockDim.x) sq[i] = query[i];
+  if (threadIdx.x == 0) {
+    float ss = 0.0f;
+    for (unsigned i = 0; i < d; ++i) ss = __fadd_rn(ss, __fmul_rn(query[i], query[i]));
+    s_qn = __fsqrt_rn(ss);
+  }
+  __syncthreads();
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const unsigned gid = cand[j];
+  const unsigned i = gid - index_base;  // candidates carry global ids
+  if (gid < index_base || i >= n) {
+    out[j] = MODE == PDX_L2 ? __int_as_float(0x7FC00000) : __int_as_float(0xFFC00000);  // sorts last under total_cmp
+    return;
+  }
+  const float* p = data + i;
+  float acc = 0.0f, ss = 0.0f;
+  for (unsigned dd = 0; dd < d; ++dd) {
+    const float v = __ldg(p + (size_t)dd * ld);
+    accumulate<MODE == PDX_COSINE_FUSED ? PDX_DOT : MODE>(sq[dd], v, acc);
+    if (MODE == PDX_COSINE_FUSED) ss = __fadd_rn(ss, __fmul_rn(v, v));
+  }
+  float sc = acc;
+  if (MODE == PDX_COSINE_FUSED) {
+    const float nrm = __fsqrt_rn(ss), qn = s_qn;
+    sc = (!(qn < NORM_EPS) && nrm > NORM_EPS) ? __fdiv_rn(acc, __fmul_rn(qn, nrm)) : 0.0f;
+  }
+  out[j] = sc;
+}
+}  // namespace
+
+cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
+                                 float* dev_out, cudaStream_t s, uint64_t* launches) {
+  if (m == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((m + SCAN_THREADS - 1) / SCAN_THREADS);
+  const size_t smem = ((v.d + 3) & ~(size_t)3) * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+#define INNR_SUBSET(MODE)                                                                                           \
+  {                                                                                                                 \
+    auto kern = subset_scores_kernel<MODE>;                                                                         \
+    if (smem > 48 * 1024) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      if (e != cudaSuccess) return e;                                                                               \
+    }                                                                                                               \
+    kern<<<grid, SCAN_THREADS, smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base, dev_query,      \
+                                          dev_cand, (unsigned)m, dev_out);                                          \
+  }
+  if (mode == PDX_DOT) INNR_SUBSET(PDX_DOT)
+  else if (mode == PDX_L2) INNR_SUBSET(PDX_L2)
+  else if (mode == PDX_COSINE_FUSED) INNR_SUBSET(PDX_COSINE_FUSED)
+  else return cudaErrorInvalidValue;
+#undef INNR_SUBSET
+  ++*launches;
+  return cudaGetLastError();
+}
+
 // k keys of a score vector, any k: rounds of <= 128 keys, each bounded below by the last key of the round before
 // (read on the device: no host synchronisation between rounds)
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                                    const uint32_t* dev_ids) {
   unsigned grid = (unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS);
   unsigned cap = (unsigned)ws.num_sms * 4u;
   if (grid > cap) grid = cap;
@@ -621,7 +693,7 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
     uint64_t* out = dev_keys + done;
     const size_t smem = (size_t)(SCAN_THREADS / 32) * kr * sizeof(uint64_t);
 #define INNR_TOPK_LAUNCH(R, KIND)                                                                                   \
-  topk_scores_kernel<R, KIND><<<grid, SCAN_THREADS, smem, s>>>(dev_scores, (unsigned)n, index_base, kr, floor,       \
+  topk_scores_kernel<R, KIND><<<grid, SCAN_THREADS, smem, s>>>(dev_scores, (unsigned)n, index_base, dev_ids, kr, floor, \
                                                                ws.partials, ws.group_partials, out, ws.tickets)
     if (kr <= 32) {
       if (kind == 0) INNR_TOPK_LAUNCH(1, 0); else if (kind == 1) INNR_TOPK_LAUNCH(1, 1); else INNR_TOPK_LAUNCH(1, 2);
@@ -638,7 +710,7 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
 
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, uint64_t* launches) {
-  return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches);
+  return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches, nullptr);
 }
 
 }  // namespace innr

@@ -337,6 +337,27 @@ __global__ void generate_u8_kernel(uint64_t salt, uint64_t first_row, unsigned n
   }
 }
 
+// quantize_u8 (src/scalar.rs:212-225) of a device-resident PDX f32 corpus straight into the chunk-major u8 layout:
+// thread (chunk c, vector i) reads 16 dimension rows (coalesced along i) and writes one uint4
+__global__ void u8_from_pdx_kernel(const float* __restrict__ pdx, size_t ld_f, unsigned n, unsigned d, float alpha,
+                                   float offset, uint4* __restrict__ codes, size_t ld, unsigned chunks) {
+  const size_t total = (size_t)chunks * ld;
+  const float inv_alpha = __fdiv_rn(255.0f, alpha);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const unsigned c = (unsigned)(t / ld);
+    const size_t i = t % ld;
+    unsigned w[4] = {0, 0, 0, 0};
+    if (i < n) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const unsigned dd = 16 * c + e;
+        if (dd < d) w[e >> 2] |= quantize_one(pdx[(size_t)dd * ld_f + i], offset, inv_alpha) << (8 * (e & 3));
+      }
+    }
+    codes[t] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 __global__ void quantize_u8_kernel(const float* __restrict__ values, size_t n, float alpha, float offset,
                                    uint8_t* __restrict__ out) {
   const float inv_alpha = __fdiv_rn(255.0f, alpha);
@@ -399,6 +420,15 @@ cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size
                                uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   generate_u8_kernel<<<148 * 16, 256, 0, s>>>(salt, first_row, (unsigned)n, (unsigned)d, alpha, offset, dev_codes, ld,
+                                              (unsigned)((d + 15) / 16));
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float alpha, float offset,
+                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+  if (n == 0 || d == 0) return cudaSuccess;
+  u8_from_pdx_kernel<<<148 * 16, 256, 0, s>>>(dev_pdx, ld_f, (unsigned)n, (unsigned)d, alpha, offset, dev_codes, ld,
                                               (unsigned)((d + 15) / 16));
   ++*launches;
   return cudaGetLastError();

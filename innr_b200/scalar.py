@@ -67,6 +67,15 @@ class U8Corpus:
         return self._handle.h
 
     @classmethod
+    def from_f32(cls, batch, params: QuantizationParams):
+        """quantize_u8 (src/scalar.rs:212-225) of every vector of a device-resident f32 corpus, on the device."""
+        from .batch import _dev
+        dev = _dev(batch)
+        h = C.c_void_p()
+        L.call("innr_cuda_u8_from_f32", dev.h, C.c_float(params.alpha), C.c_float(params.offset), C.byref(h))
+        return cls(_Handle(h), dev.num_vectors, dev.dimension, params, dev.index_base)
+
+    @classmethod
     def from_rows(cls, rows, params: QuantizationParams, index_base: int = 0, dimension=None):
         if isinstance(rows, np.ndarray):
             mat = np.ascontiguousarray(rows, dtype=np.uint8)

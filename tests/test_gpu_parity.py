@@ -251,6 +251,49 @@ def test_binary_dot_jaccard_scans_exact(ib, oracle, dim):
     assert float(ib.binary_jaccard_all(z, corpus)[5]) == 1.0 and int(ib.binary_dot_all(z, corpus)[5]) == 0
 
 
+# ------------------------------------------------------------------------------------------------ two-stage retrieval
+@pytest.mark.parametrize("n,d", [(3000, 96), (5000, 200), (1500, 7)])
+def test_derived_encodings_and_rerank(ib, oracle, n, d):
+    """one f32 ingest, binary and u8 encodings derived on the device (bit-identical to encode_binary /
+    quantize_u8 of every row), first pass on the codes, exact re-rank of the candidates (= the reference's function on
+    the gathered sub-batch, original indices)."""
+    rng = np.random.default_rng(n + d)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    rows[3] = 0.0
+    q = rng.standard_normal(d).astype(np.float32)
+    base = 1000
+    gb = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d, index_base=base)
+    # binary: Hamming distances of the derived codes == oracle on encode_binary of each row
+    bc = ib.BinaryCorpus.from_f32(gb, 0.0)
+    qb_g, qb_o = ib.encode_binary(q, 0.0), oracle.encode_binary(q, 0.0)
+    got = ib.hamming_all(qb_g, bc)
+    want = np.array([oracle.binary_hamming(qb_o, oracle.encode_binary(rows[i], 0.0)) for i in range(n)], np.uint32)
+    assert np.array_equal(got, want)
+    # u8: derived codes == quantize_u8 of each row (checked through exact mixed dots against the oracle's codes)
+    gp, op = ib.QuantizationParams.from_range(-3.0, 3.0), oracle.QuantizationParams.from_range(-3.0, 3.0)
+    uc = ib.U8Corpus.from_f32(gb, gp)
+    mat = oracle.quantize_u8(rows.reshape(-1), op).data.reshape(n, d)
+    gm = ib.mixed_dot_u8_all(q, uc)
+    for i in range(0, n, 37):
+        assert np.float32(gm[i]).tobytes() == np.float32(oracle.mixed_dot_u8_f32(q, mat[i])).tobytes()
+    # two-stage: Hamming top-300 (k > 128) -> exact re-rank top-10, all three metrics
+    cand, _ = ib.hamming_topk_many(np.asarray(qb_g.data, np.uint64).reshape(1, -1), bc, 300)
+    cand = cand[0]
+    assert cand.min() >= base
+    local = (cand - base).astype(np.int64)
+    order = np.argsort(local, kind="stable")
+    sub = oracle.VerticalBatch.from_flat(rows[local[order]].reshape(-1), len(local), d)
+    for metric, fn in (("dot", "batch_knn_dot"), ("cosine", "batch_knn_cosine"), ("l2", "batch_knn")):
+        got = ib.batch_knn_subset(metric, q, gb, cand, 10)
+        want = getattr(oracle, fn)(q, sub, 10)
+        want_idx = [int(local[order][int(j)]) + base for j in want.indices]
+        assert np.array_equal(bits(got.scores), bits(want.scores)), metric
+        if metric != "l2":
+            assert [int(i) for i in got.indices] == want_idx, metric
+        else:
+            assert sorted(int(i) for i in got.indices) == sorted(want_idx)
+
+
 # ------------------------------------------------------------------------------------------------ k > 128
 @pytest.mark.parametrize("k", [129, 300, 1000, 5000])
 def test_big_k_all_paths_exact(ib, oracle, k):
