@@ -83,6 +83,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC ? 1 : 0)
+      : "memory");
+}
 // kind::f16, A = B = F16 (format 0), K-major, F32 accumulate
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -139,26 +148,31 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
     }
   } else if (warp == 5) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      for (unsigned it = 0; it < n_iters; ++it) {
-        const unsigned ul = it / a.kblocks, kb = it % a.kblocks;
-        const unsigned qg = (u_lo + ul) % a.n_qgroups;
-        const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
-        const uint32_t idesc = make_idesc_f16(VT, (int)qt_u);
+    // the whole warp runs the loop (warp-uniform addresses and descriptors), one elected lane issues
+    const uint64_t x_desc0 = make_smem_desc_kmajor_sw128(smem_u32(smem));
+    const uint64_t q_desc0 = make_smem_desc_kmajor_sw128(smem_u32(smem + X_BYTES));
+    unsigned it = 0;
+    for (unsigned ul = 0; ul < n_units; ++ul) {
+      const unsigned qg = (u_lo + ul) % a.n_qgroups;
+      const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
+      const uint32_t idesc = make_idesc_f16(VT, (int)qt_u);
+      const uint32_t acc = tmem + (ul & 1) * QT;
+      mbar_wait(&st->acc_empty[ul & 1], ((ul >> 1) & 1) ^ 1);
+      for (unsigned kb = 0; kb < a.kblocks; ++kb, ++it) {
         const int s = it % KSTAGES;
-        if (kb == 0) mbar_wait(&st->acc_empty[ul & 1], ((ul >> 1) & 1) ^ 1);
         mbar_wait(&st->full[s], (it / KSTAGES) & 1);
         tc_fence_after_sync();
-        const uint32_t xb = smem_u32(smem + s * KSTAGE_BYTES);
-        const uint32_t acc = tmem + (ul & 1) * QT;
+        if (elect_one_sync()) {
+          const uint64_t xd = desc_advance(x_desc0, (uint32_t)s * KSTAGE_BYTES);
+          const uint64_t qd = desc_advance(q_desc0, (uint32_t)s * KSTAGE_BYTES);
+          if (kb == 0) umma_f16_c<false>(acc, xd, qd, idesc);
+          else umma_f16_c<true>(acc, xd, qd, idesc);
 #pragma unroll
-        for (int ks = 0; ks < KB / 16; ++ks) {
-          const uint64_t ad = make_smem_desc_kmajor_sw128(xb + ks * 32);
-          const uint64_t bd = make_smem_desc_kmajor_sw128(xb + X_BYTES + ks * 32);
-          umma_f16(acc, ad, bd, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 1; ks < KB / 16; ++ks) umma_f16_c<true>(acc, desc_advance(xd, ks * 32), desc_advance(qd, ks * 32), idesc);
+          umma_commit(&st->empty[s]);  // the stage is no longer read by the tensor core
+          if (kb == a.kblocks - 1) umma_commit(&st->acc_full[ul & 1]);
         }
-        umma_commit(&st->empty[s]);  // the stage is no longer read by the tensor core
-        if (kb == a.kblocks - 1) umma_commit(&st->acc_full[ul & 1]);
+        __syncwarp();
       }
     }
   } else {
@@ -558,7 +572,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   {
     size_t cur = CAND_CAP < v.n ? CAND_CAP : v.n;
     levels[n_levels++] = cur;
-    const size_t mids[2] = {v.n / 128, v.n / 16};
+    static const int sched = getenv("INNR_KNN_TC_SCHED") ? atoi(getenv("INNR_KNN_TC_SCHED")) : 0;
+    const size_t mids[2] = {sched == 1 ? 0 : (sched == 2 ? v.n / 64 : v.n / 128), sched == 1 ? v.n / 32 : (sched == 2 ? v.n / 8 : v.n / 16)};
     for (size_t nx : mids)
       if (nx >= 4 * cur) {
         cur = (nx + VT - 1) / VT * VT;
