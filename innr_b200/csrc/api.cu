@@ -85,12 +85,17 @@ struct Options {
   bool maxsim_tc = true;
 } g_opt;
 
+// One mutex per device: calls on different GPUs run concurrently from different host threads (one stream + one
+// workspace per device are what a call owns); g_mu guards the process-wide options and statistics only.
 std::mutex g_mu;
+std::mutex g_dev_mu[MAX_DEVICES];
 DeviceCtx g_ctx[MAX_DEVICES];
-uint64_t g_launches = 0;
+LaunchCounter g_launches{0};
 KnnTcStats g_tc_stats;
 thread_local int t_device = -1;
 thread_local std::string t_err;
+std::mutex& dev_mu(int d) { return g_dev_mu[(d >= 0 && d < MAX_DEVICES) ? d : 0]; }
+int cur_dev() { return t_device < 0 ? 0 : t_device; }
 
 int fail(int code, const std::string& msg) {
   t_err = msg;
@@ -229,7 +234,7 @@ int innr_cuda_device_count(int* out_count) {
 }
 
 int innr_cuda_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(device));
   DeviceCtx* c;
   int rc = ensure_ctx(device, &c);
   if (rc == INNR_OK) t_device = device;
@@ -237,8 +242,8 @@ int innr_cuda_init(int device) {
 }
 
 int innr_cuda_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
   for (int i = 0; i < MAX_DEVICES; ++i) {
+    std::lock_guard<std::mutex> lk(g_dev_mu[i]);
     DeviceCtx& c = g_ctx[i];
     if (!c.ready) continue;
     cudaSetDevice(i);
@@ -326,7 +331,7 @@ static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, in
 int innr_cuda_upload_f32_pdx(const float* host_pdx, size_t n, size_t d, uint64_t index_base,
                              innr_cuda_corpus** out) {
   if (!out || (!host_pdx && n * d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -345,7 +350,7 @@ int innr_cuda_upload_f32_pdx(const float* host_pdx, size_t n, size_t d, uint64_t
 int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64_t index_base,
                               innr_cuda_corpus** out) {
   if (!out || (!host_rows && n * d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -370,7 +375,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   if (!out) return fail(INNR_EINVAL, "null out");
   if (ld < n || (ld % 4) != 0 || ((uintptr_t)dev_pdx % 16) != 0)
     return fail(INNR_EINVAL, "wrap_f32_pdx_dev: need ld >= n, ld % 4 == 0, 16-byte aligned base");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -392,7 +397,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
 int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
                                uint64_t index_base, innr_cuda_corpus** out) {
   if (!out || (generator != 0 && generator != 1)) return fail(INNR_EINVAL, "bad argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -408,7 +413,7 @@ int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row,
 
 int innr_cuda_free(innr_cuda_corpus* c) {
   if (!c) return INNR_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   cudaSetDevice(c->device);
   if (c->owns && c->dev) cudaFree(c->dev);
   if (c->dev_offsets) cudaFree(c->dev_offsets);
@@ -433,7 +438,7 @@ int innr_cuda_corpus_info(const innr_cuda_corpus* c, int* kind, size_t* n, size_
 int innr_cuda_extract_vector(const innr_cuda_corpus* c, size_t i, float* out_host) {
   if (!c || c->kind != 0 || !out_host) return fail(INNR_EINVAL, "extract_vector: need an f32 corpus");
   if (i >= c->n) return fail(INNR_EINVAL, "extract_vector: index out of bounds");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -454,7 +459,7 @@ static int pdx_scores(const innr_cuda_corpus* c, int mode, const float* query, s
     return fail(INNR_EINVAL, "query.len() != batch.dimension");                       // src/batch.rs:251,285
   if (c->n == 0) return INNR_OK;
   if (!out_host || (mode != PDX_NORMS && !query && c->d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -552,8 +557,13 @@ static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const flo
     CU(ctx->d_tcws.reserve(knn_tc_workspace_bytes(c->n, c->d, nq, k)));
     CU(ctx->h_counts.reserve(nq * sizeof(unsigned)));
     std::vector<unsigned> overflow;
+    KnnTcStats st;
     CU(launch_pdx_knn_tc(v, c->tm_xh, c->dev_norms, mode, dev_queries, nq, k, dev_keys, ctx->d_tcws.p,
-                         (unsigned*)ctx->h_counts.p, ctx->ws, s, &g_launches, &overflow, &g_tc_stats));
+                         (unsigned*)ctx->h_counts.p, ctx->ws, s, &g_launches, &overflow, &st));
+    {
+      std::lock_guard<std::mutex> lg(g_mu);
+      g_tc_stats = st;
+    }
     for (unsigned q : overflow)
       CU(launch_pdx_knn(v, mode, dev_queries + (size_t)q * c->d, 1, k, dev_keys + (size_t)q * k, ctx->ws, s, &g_launches));
     return INNR_OK;
@@ -582,7 +592,7 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;                           // src/batch.rs:388-393
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;                                               // k.min(num_vectors)
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -622,7 +632,7 @@ int innr_cuda_batch_knn_subset(const innr_cuda_corpus* c, int metric, const floa
     if (candidates[j] < c->index_base || candidates[j] - c->index_base >= c->n)
       return fail(INNR_EINVAL, "batch_knn_subset: candidate index out of bounds");
   const size_t kk = k < n_candidates ? k : n_candidates;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -670,7 +680,7 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
   if (passing == 0) return INNR_OK;                                                     // :842-847
   const size_t kk = k < passing ? k : passing;                                          // k.min(num_passing)
   if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "batch_knn_filtered: k > 128 is not covered yet");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -707,7 +717,7 @@ int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* q
     return INNR_OK;
   }
   if (!query) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -753,7 +763,7 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
   int rc = metric_to_mode(metric, &mode);
   if (rc) return rc;
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -769,7 +779,7 @@ int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t
                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, void* stream) {
   if (k == 0 || n_queries == 0 || n_lists == 0) return INNR_OK;
   if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "merge of more than 128 keys per list is not covered yet (sharded k > 128)");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -786,7 +796,7 @@ int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, ui
   int rc = check_index_range(n, 0);
   if (rc) return rc;
   const size_t kk = k < n ? k : n;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -836,7 +846,7 @@ static int alloc_binary(DeviceCtx& ctx, size_t n, size_t dim_bits, uint64_t inde
 int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, uint64_t index_base,
                             innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -860,7 +870,7 @@ int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, ui
 int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t dim_bits, uint64_t index_base,
                               innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -898,7 +908,7 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
     return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");             // src/binary.rs:155-159
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -923,7 +933,7 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
 // code set shares the f32 corpus' index_base, so first-pass indices feed innr_cuda_batch_knn_subset directly.
 int innr_cuda_binary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out) {
   if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
   DeviceCtx* ctx;
   int rc = ctx_for(f32_corpus, &ctx);
   if (rc) return rc;
@@ -945,7 +955,7 @@ static int binary_setop_all(const innr_cuda_corpus* c, const uint64_t* query_wor
   if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "dimension mismatch");  // assert_eq!(a.dimension, b.dimension)
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1002,7 +1012,7 @@ int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_word
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_dist || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1038,7 +1048,7 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
                                     size_t k, uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1053,7 +1063,7 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
 int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words) {
   if (n == 0) return INNR_OK;
   if (!values || !out_words) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1097,7 +1107,7 @@ static int alloc_u8(DeviceCtx& ctx, size_t n, size_t d, float alpha, float offse
 int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, float offset, uint64_t index_base,
                         innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1120,7 +1130,7 @@ int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, fl
 // quantize_u8 (src/scalar.rs:212-225) of every vector of a device-resident f32 corpus, on the device
 int innr_cuda_u8_from_f32(const innr_cuda_corpus* f32_corpus, float alpha, float offset, innr_cuda_corpus** out) {
   if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
   DeviceCtx* ctx;
   int rc = ctx_for(f32_corpus, &ctx);
   if (rc) return rc;
@@ -1138,7 +1148,7 @@ int innr_cuda_u8_from_f32(const innr_cuda_corpus* f32_corpus, float alpha, float
 int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
                           uint64_t index_base, innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1155,7 +1165,7 @@ int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d,
 int innr_cuda_quantize_u8(const float* values, size_t n, float alpha, float offset, uint8_t* out_codes) {
   if (n == 0) return INNR_OK;
   if (!values || !out_codes) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1174,7 +1184,7 @@ static int u8_scores(const innr_cuda_corpus* c, int mode, const float* query, si
   if (query_len != c->d) return fail(INNR_EINVAL, mismatch_msg);
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1226,7 +1236,7 @@ int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
   if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1249,7 +1259,7 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
                                     uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1265,7 +1275,7 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
 int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, size_t n_docs, size_t dim,
                             uint64_t index_base, innr_cuda_corpus** out) {
   if (!out || (n_docs && !doc_offsets)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1302,7 +1312,7 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
 int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, size_t tokens_per_doc, size_t dim,
                               uint64_t index_base, innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1352,7 +1362,7 @@ int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_
   if (n_q && c->total_tokens && q_dim != c->d) return fail(INNR_EINVAL, "dimension mismatch (doc)");  // src/maxsim.rs:107-110
   if (c->n == 0) return INNR_OK;
   if (!out_scores_host || (n_q * q_dim && !q_tokens)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1374,7 +1384,7 @@ int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, s
                          float* dev_scores, void* stream) {
   if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
   if (c->n == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;

@@ -12,6 +12,15 @@
 
 namespace innr {
 
+// function attributes, events and similar driver state are per device: launchers keep them in [16]-arrays indexed by
+// the calling thread's current device (one host process may drive every GPU of the box)
+inline int current_device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 15;
+}
+
+
 constexpr uint64_t KEY_SENTINEL = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned FULL_MASK = 0xFFFFFFFFu;
 

@@ -221,7 +221,7 @@ cudaError_t launch_ham(const HamArgs& a, size_t smem, int num_sms, cudaStream_t 
 }  // namespace
 
 cudaError_t launch_binary_pack(const uint64_t* dev_words_rowmajor, size_t n, size_t words, size_t dim_bits,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || words == 0) return cudaSuccess;
   unsigned chunks = (unsigned)((words + 1) / 2);
   binary_pack_kernel<<<148 * 8, 256, 0, s>>>(dev_words_rowmajor, (unsigned)n, (unsigned)words, (unsigned)dim_bits,
@@ -231,7 +231,7 @@ cudaError_t launch_binary_pack(const uint64_t* dev_words_rowmajor, size_t n, siz
 }
 
 cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t words, size_t dim_bits,
-                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || words == 0) return cudaSuccess;
   unsigned chunks = (unsigned)((words + 1) / 2);
   generate_binary_kernel<<<148 * 16, 256, 0, s>>>(salt, first_row, (unsigned)n, (unsigned)words, (unsigned)dim_bits,
@@ -241,7 +241,7 @@ cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, 
 }
 
 cudaError_t launch_binary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float threshold,
-                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   binary_from_pdx_kernel<<<148 * 16, 256, 0, s>>>(dev_pdx, ld_f, (unsigned)n, (unsigned)d, threshold, dev_codes, ld,
                                                   (unsigned)((d + 127) / 128));
@@ -250,7 +250,7 @@ cudaError_t launch_binary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, 
 }
 
 cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
-                                 cudaStream_t s, uint64_t* launches) {
+                                 cudaStream_t s, LaunchCounter* launches) {
   size_t n_words = (n + 63) / 64;
   if (n_words == 0) return cudaSuccess;
   unsigned grid = (unsigned)((n_words * 32 + 255) / 256);
@@ -273,7 +273,7 @@ static HamArgs make_args(const BinView& v, const uint64_t* q) {
 }
 
 cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
-                               cudaStream_t s, uint64_t* launches) {
+                               cudaStream_t s, LaunchCounter* launches) {
   if (v.n == 0) return cudaSuccess;
   HamArgs a = make_args(v, dev_query_words);
   a.dist_out = dev_out;
@@ -284,7 +284,7 @@ cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words
 }
 
 cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
-                                  cudaStream_t s, uint64_t* launches) {
+                                  cudaStream_t s, LaunchCounter* launches) {
   if (v.n == 0) return cudaSuccess;
   HamArgs a = make_args(v, dev_query_words);
   a.dist_out = dev_out;
@@ -294,7 +294,7 @@ cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_wo
 }
 
 cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_query_words, float* dev_out,
-                                      cudaStream_t s, uint64_t* launches) {
+                                      cudaStream_t s, LaunchCounter* launches) {
   if (v.n == 0) return cudaSuccess;
   HamArgs a = make_args(v, dev_query_words);
   binary_setops_kernel<true><<<a.n_tiles, HAM_THREADS, v.chunks * sizeof(uint4), s>>>(a, dev_out);
@@ -303,7 +303,7 @@ cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_quer
 }
 
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
-                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   if (k > 128) return cudaErrorInvalidValue;
   for (size_t q = 0; q < nq; ++q) {
     HamArgs a = make_args(v, dev_query_words + q * 2 * v.chunks);

@@ -5,9 +5,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 namespace innr {
+
+using LaunchCounter = std::atomic<uint64_t>;  // kernels launched so far (all devices, all threads)
 
 // modes of the f32 PDX scan (scan_f32.cu)
 enum PdxMode : int {
@@ -47,36 +50,36 @@ struct PdxView {
 // kNN: queries on device (nq x d row-major); writes nq x k sorted keys (sentinel padded) into dev_keys.
 // Returns cudaSuccess or the launch error; `launches` is incremented per kernel launched.
 cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
-                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 // batch_knn_filtered (src/batch.rs:820-882): L2, one query; dev_mask = one bit per local vector (LSB-first u32 words,
 // zero padded to ld/32 + 1 words); vectors whose bit is clear are neither read nor offered.
 cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, const uint32_t* dev_mask, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 // full score vectors: out[q * ld + i] (device). dev_norms only for PDX_COSINE_NORMS; threshold only for PDX_L2_PRUNE.
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches, float threshold = 0.0f);
+                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold = 0.0f);
 // stream compaction of a pruned distance vector (entries == -1.0 are dropped): ascending index order.
 // Pass 1 (count) fills dev_block_offsets[n_blocks + 1] (exclusive prefix, last = total); pass 2 scatters.
 size_t compact_blocks(size_t n);
 cudaError_t launch_compact_count(const float* dev_dist, size_t n, unsigned* dev_block_offsets, cudaStream_t s,
-                                 uint64_t* launches);
+                                 LaunchCounter* launches);
 cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t index_base, const unsigned* dev_block_offsets,
-                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, uint64_t* launches);
+                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, LaunchCounter* launches);
 // merge n_lists x nq x k sorted key lists -> nq x k; optional decode (idx u64, f32 score bits by `descending`)
 cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
-                              uint64_t* launches);
+                              LaunchCounter* launches);
 // k smallest keys of a device score vector for ANY k (rounds of <= 128): kind 0 f32 ascending, 1 f32 descending,
 // 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128.
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
                                     const uint32_t* dev_ids = nullptr);
 // exact scores (mode = PDX_DOT / PDX_L2 / PDX_COSINE_FUSED) of m candidate vectors given by GLOBAL id
 cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
-                                 float* dev_out, cudaStream_t s, uint64_t* launches);
+                                 float* dev_out, cudaStream_t s, LaunchCounter* launches);
 // keys from a plain f32 array (TopK analogue): ascending, id = i
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
-                                       Workspace& ws, cudaStream_t s, uint64_t* launches);
+                                       Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 
 // tensor-core filter path for large query batches (knn_tc.cu): dot / cosine, k <= 32, exact results
 struct KnnTcStats {
@@ -91,19 +94,19 @@ size_t knn_tc_dpad(size_t d);  // row pitch (elements) of the f16 operand copy
 size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k);
 // once per corpus: dev_xh (n x knn_tc_dpad(d) f16) = unit vectors, from the PDX corpus and its exact norms
 cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* dev_xh, unsigned* dev_scratch_u32,
-                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, uint64_t* launches);
+                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, LaunchCounter* launches);
 // host_counts: pinned buffer of nq unsigned; overflow_queries receives the queries the filter could not answer
 // (the caller re-runs them on the exact scan). Synchronises the stream once at the end.
 cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
                               const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys, void* workspace,
-                              unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                              unsigned* host_counts, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
                               std::vector<unsigned>* overflow_queries, KnnTcStats* stats);
 
 // layout / generator kernels (layout.cu)
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,
-                                         cudaStream_t s, uint64_t* launches);
+                                         cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
-                                    float* dev_pdx, size_t ld, cudaStream_t s, uint64_t* launches);
+                                    float* dev_pdx, size_t ld, cudaStream_t s, LaunchCounter* launches);
 
 // binary codes (hamming.cu): chunk-major layout codes[c * ld + i] (uint4 = 128 bits), chunks = ceil(words/2)
 struct BinView {
@@ -112,21 +115,21 @@ struct BinView {
   uint32_t index_base;
 };
 cudaError_t launch_binary_pack(const uint64_t* dev_words_rowmajor, size_t n, size_t words, size_t dim_bits,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t words, size_t dim_bits,
-                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_hamming_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
-                               cudaStream_t s, uint64_t* launches);
+                               cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_words, uint32_t* dev_out,
-                                  cudaStream_t s, uint64_t* launches);
+                                  cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_query_words, float* dev_out,
-                                      cudaStream_t s, uint64_t* launches);
+                                      cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
-                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches);
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
-                                 cudaStream_t s, uint64_t* launches);
+                                 cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_binary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float threshold,
-                                   uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+                                   uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 
 // u8 codes (u8.cu): chunk-major layout codes[c * ld + i] (uint4 = 16 dims), chunks = ceil(d/16)
 struct U8View {
@@ -136,19 +139,19 @@ struct U8View {
   uint32_t index_base;
 };
 cudaError_t launch_u8_pack(const uint8_t* dev_rows, size_t n, size_t d, uint4* dev_codes, size_t ld,
-                           cudaStream_t s, uint64_t* launches);
+                           cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, float offset, uint8_t* dev_out,
-                               cudaStream_t s, uint64_t* launches);
+                               cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float alpha, float offset,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches);
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 // mode 0: raw mixed dot, 1: asymmetric score
 cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
-                             cudaStream_t s, uint64_t* launches);
+                             cudaStream_t s, LaunchCounter* launches);
 void u8_set_scaled_chains(bool on);  // off = always the de-biasing path (tests compare both)
 cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
-                          Workspace& ws, cudaStream_t s, uint64_t* launches);
+                          Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 
 // MaxSim (maxsim.cu)
 struct TokView {
@@ -163,13 +166,13 @@ struct TokView {
 // tcgen05 path (maxsim_tc.cu): dim in {32, 64, 96, 128}, 1 <= n_q <= 256 (one corpus pass per 32 query tokens)
 bool maxsim_tc_supported(const TokView& v, size_t n_q);
 cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
-                             int num_sms, cudaStream_t s, uint64_t* launches);
+                             int num_sms, cudaStream_t s, LaunchCounter* launches);
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim);
 cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens, size_t dim, float* dev_inv,
-                                   cudaStream_t s, uint64_t* launches);
+                                   cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_generate_tokens(uint64_t salt, uint64_t first_row, size_t n_rows, size_t dim, float* dev_tokens,
-                                   cudaStream_t s, uint64_t* launches);
+                                   cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_maxsim(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
-                          cudaStream_t s, uint64_t* launches);
+                          cudaStream_t s, LaunchCounter* launches);
 
 }  // namespace innr

@@ -504,7 +504,7 @@ bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k) {
 // Xh + its tensor map from the PDX corpus and its exact norms; *host_nonfinite = vectors with a NaN / inf norm (the
 // caller disables the path for the corpus when it is not 0). Synchronises the stream.
 cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* dev_xh, unsigned* dev_scratch_u32,
-                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, uint64_t* launches) {
+                                CUtensorMap* tm_xh, unsigned* host_nonfinite, cudaStream_t s, LaunchCounter* launches) {
   const unsigned d_pad = (unsigned)knn_tc_dpad(v.d);
   cudaError_t e = cudaMemsetAsync(dev_scratch_u32, 0, 4, s);
   if (e != cudaSuccess) return e;
@@ -523,7 +523,7 @@ cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* 
 
 cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
                               const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys, void* workspace,
-                              unsigned* host_counts, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                              unsigned* host_counts, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
                               std::vector<unsigned>* overflow_queries, KnnTcStats* stats) {
   const int cosine = mode == PDX_COSINE_FUSED;
   const KnnTcPlan p = make_plan(v.d, nq);
@@ -536,7 +536,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   float* cand_lb = (float*)(w + p.off_lb);
   cudaError_t e;
   static const bool trace = getenv("INNR_KNN_TC_TRACE") != nullptr;
-  static cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call begin, final pass begin / end, call end
+  static cudaEvent_t ev_dev[16][4] = {};  // per device: call begin, final pass begin / end, call end
+  cudaEvent_t(&ev)[4] = ev_dev[current_device_slot()];
   if (!ev[0])
     for (auto& x : ev)
       if ((e = cudaEventCreate(&x)) != cudaSuccess) return e;
@@ -560,7 +561,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   tmark();
 
   // 2. filter passes over growing prefixes
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   const size_t smem = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
   if (!attr_set) {
     e = cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -53,7 +53,7 @@ __global__ void generate_tokens_kernel(uint64_t salt, uint64_t first_row, size_t
 }  // namespace
 
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,
-                                         cudaStream_t s, uint64_t* launches) {
+                                         cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((d + 31) / 32));
   transpose_rows_to_pdx_kernel<<<grid, dim3(32, 8), 0, s>>>(dev_rows, (unsigned)n, (unsigned)d, dev_pdx, ld);
@@ -62,7 +62,7 @@ cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t
 }
 
 cudaError_t launch_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
-                                    float* dev_pdx, size_t ld, cudaStream_t s, uint64_t* launches) {
+                                    float* dev_pdx, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   generate_f32_pdx_kernel<<<148 * 16, 256, 0, s>>>(generator, salt, first_row, (unsigned)n, (unsigned)d, dev_pdx, ld);
   ++*launches;
@@ -70,7 +70,7 @@ cudaError_t launch_generate_f32_pdx(int generator, uint64_t salt, uint64_t first
 }
 
 cudaError_t launch_generate_tokens(uint64_t salt, uint64_t first_row, size_t n_rows, size_t dim, float* dev_tokens,
-                                   cudaStream_t s, uint64_t* launches) {
+                                   cudaStream_t s, LaunchCounter* launches) {
   if (n_rows == 0 || dim == 0) return cudaSuccess;
   generate_tokens_kernel<<<148 * 16, 256, 0, s>>>(salt, first_row, n_rows, (unsigned)dim, dev_tokens);
   ++*launches;

@@ -167,7 +167,7 @@ size_t maxsim_smem(size_t dim, size_t n_q) {
 }  // namespace
 
 cudaError_t launch_maxsim(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
-                          cudaStream_t s, uint64_t* launches) {
+                          cudaStream_t s, LaunchCounter* launches) {
   if (v.n_docs == 0) return cudaSuccess;
   size_t smem = maxsim_smem(v.dim, n_q);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;

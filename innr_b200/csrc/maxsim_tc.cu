@@ -464,7 +464,7 @@ bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_token
 }
 
 cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens, size_t dim, float* dev_inv,
-                                   cudaStream_t s, uint64_t* launches) {
+                                   cudaStream_t s, LaunchCounter* launches) {
   if (total_tokens == 0) return cudaSuccess;
   token_inv_norms_kernel<<<(unsigned)((total_tokens + 7) / 8), 256, 0, s>>>(dev_tokens, total_tokens, (unsigned)dim, dev_inv);
   ++*launches;
@@ -482,7 +482,8 @@ namespace {
 template <bool COSINE, int P>
 cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
   constexpr size_t smem = (size_t)Shape<P>::STAGES * Shape<P>::STAGE_BYTES + Shape<P>::QBYTES + sizeof(SharedTail);
-  static bool attr_set = false;
+  static bool attr_set_dev[16] = {};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -504,7 +505,7 @@ cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsig
 }  // namespace
 
 cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
-                             int num_sms, cudaStream_t s, uint64_t* launches) {
+                             int num_sms, cudaStream_t s, LaunchCounter* launches) {
   // empty documents never see a token: their score is 0.0 (src/maxsim.rs:97-99)
   cudaError_t e = cudaMemsetAsync(dev_scores, 0, v.n_docs * sizeof(float), s);
   if (e != cudaSuccess) return e;

@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
 template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
 cudaError_t launch_one(const PdxArgs& a, size_t smem, int ny, int num_sms, cudaStream_t s) {
   auto kern = pdx_scan_kernel<MODE, QB, R, KNN, MASKED>;
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[16] = {};
+  size_t& smem_set = smem_set_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -283,7 +284,7 @@ size_t scan_smem_bytes(size_t d, int qb, int k, bool knn) {
 unsigned pdx_max_grid(int num_sms) { return (unsigned)num_sms * 8u; }
 
 cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
-                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
@@ -345,7 +346,7 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
 }
 
 cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, const uint32_t* dev_mask, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
@@ -371,7 +372,7 @@ cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, co
 }
 
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, uint64_t* launches, float threshold) {
+                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold) {
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const float
 size_t compact_blocks(size_t n) { return (n + CP_BLOCK - 1) / CP_BLOCK; }
 
 cudaError_t launch_compact_count(const float* dev_dist, size_t n, unsigned* dev_block_offsets, cudaStream_t s,
-                                 uint64_t* launches) {
+                                 LaunchCounter* launches) {
   const unsigned nb = (unsigned)compact_blocks(n);
   if (nb == 0) return cudaMemsetAsync(dev_block_offsets, 0, sizeof(unsigned), s);
   compact_count_kernel<<<nb, CP_THREADS, 0, s>>>(dev_dist, (unsigned)n, dev_block_offsets);
@@ -587,7 +588,7 @@ cudaError_t launch_compact_count(const float* dev_dist, size_t n, unsigned* dev_
 }
 
 cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t index_base, const unsigned* dev_block_offsets,
-                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, uint64_t* launches) {
+                                   uint64_t* dev_idx, float* dev_out, cudaStream_t s, LaunchCounter* launches) {
   const unsigned nb = (unsigned)compact_blocks(n);
   if (nb == 0) return cudaSuccess;
   compact_scatter_kernel<<<nb, CP_THREADS, 0, s>>>(dev_dist, (unsigned)n, index_base, dev_block_offsets, dev_idx, dev_out);
@@ -597,7 +598,7 @@ cudaError_t launch_compact_scatter(const float* dev_dist, size_t n, uint64_t ind
 
 cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
-                              uint64_t* launches) {
+                              LaunchCounter* launches) {
   if (k > 128) return cudaErrorInvalidValue;
   if (k <= 32)
     merge_keys_kernel<1><<<(unsigned)nq, 32, 0, s>>>(dev_in, (int)n_lists, (int)nq, (int)k, descending,
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) subset_scores_kernel(const float
 }  // namespace
 
 cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
-                                 float* dev_out, cudaStream_t s, uint64_t* launches) {
+                                 float* dev_out, cudaStream_t s, LaunchCounter* launches) {
   if (m == 0) return cudaSuccess;
   const unsigned grid = (unsigned)((m + SCAN_THREADS - 1) / SCAN_THREADS);
   const size_t smem = ((v.d + 3) & ~(size_t)3) * sizeof(float);
@@ -681,7 +682,7 @@ cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_qu
 // k keys of a score vector, any k: rounds of <= 128 keys, each bounded below by the last key of the round before
 // (read on the device: no host synchronisation between rounds)
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
-                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, uint64_t* launches,
+                                    uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
                                     const uint32_t* dev_ids) {
   unsigned grid = (unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS);
   unsigned cap = (unsigned)ws.num_sms * 4u;
@@ -709,7 +710,7 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
 }
 
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
-                                       Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                                       Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches, nullptr);
 }
 

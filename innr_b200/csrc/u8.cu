@@ -409,7 +409,7 @@ U8Args make_args(const U8View& v, const float* q) {
 void u8_set_scaled_chains(bool on) { g_u8_allow_scaled = on ? 1 : 0; }
 
 cudaError_t launch_u8_pack(const uint8_t* dev_rows, size_t n, size_t d, uint4* dev_codes, size_t ld,
-                           cudaStream_t s, uint64_t* launches) {
+                           cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   u8_pack_kernel<<<148 * 8, 256, 0, s>>>(dev_rows, (unsigned)n, (unsigned)d, dev_codes, ld, (unsigned)((d + 15) / 16));
   ++*launches;
@@ -417,7 +417,7 @@ cudaError_t launch_u8_pack(const uint8_t* dev_rows, size_t n, size_t d, uint4* d
 }
 
 cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   generate_u8_kernel<<<148 * 16, 256, 0, s>>>(salt, first_row, (unsigned)n, (unsigned)d, alpha, offset, dev_codes, ld,
                                               (unsigned)((d + 15) / 16));
@@ -426,7 +426,7 @@ cudaError_t launch_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size
 }
 
 cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float alpha, float offset,
-                               uint4* dev_codes, size_t ld, cudaStream_t s, uint64_t* launches) {
+                               uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches) {
   if (n == 0 || d == 0) return cudaSuccess;
   u8_from_pdx_kernel<<<148 * 16, 256, 0, s>>>(dev_pdx, ld_f, (unsigned)n, (unsigned)d, alpha, offset, dev_codes, ld,
                                               (unsigned)((d + 15) / 16));
@@ -435,7 +435,7 @@ cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size
 }
 
 cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, float offset, uint8_t* dev_out,
-                               cudaStream_t s, uint64_t* launches) {
+                               cudaStream_t s, LaunchCounter* launches) {
   if (n == 0) return cudaSuccess;
   unsigned grid = (unsigned)((n + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
@@ -445,7 +445,7 @@ cudaError_t launch_quantize_u8(const float* dev_values, size_t n, float alpha, f
 }
 
 cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
-                             cudaStream_t s, uint64_t* launches) {
+                             cudaStream_t s, LaunchCounter* launches) {
   if (v.n == 0) return cudaSuccess;
   U8Args a = make_args(v, dev_query);
   a.mode = mode;
@@ -458,7 +458,7 @@ cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, 
 }
 
 cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
-                          Workspace& ws, cudaStream_t s, uint64_t* launches) {
+                          Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   if (k > 128) return cudaErrorInvalidValue;
   size_t smem = u8_smem(v.d, k, true);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;

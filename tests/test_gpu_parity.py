@@ -251,6 +251,86 @@ def test_binary_dot_jaccard_scans_exact(ib, oracle, dim):
     assert float(ib.binary_jaccard_all(z, corpus)[5]) == 1.0 and int(ib.binary_dot_all(z, corpus)[5]) == 0
 
 
+# ------------------------------------------------------------------------------------------------ host threads
+def test_concurrent_host_threads(ib, oracle):
+    """SURVEY 8b 'Threading': handles are immutable after upload and calls from several host threads must be safe
+    (a per-device mutex serialises them; ctypes drops the GIL during the call). Every thread must get its own exact
+    answer."""
+    import threading
+    n, d, k = 20000, 64, 10
+    rows = rand_rows(n, d, 99)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    codes = np.random.default_rng(5).integers(0, 2**62, size=(n, 4), dtype=np.uint64)
+    bc = ib.BinaryCorpus.from_words(codes, n, 256)
+    qs = rand_rows(16, d, 123)
+    qcs = np.random.default_rng(6).integers(0, 2**62, size=(16, 4), dtype=np.uint64)
+    want = [oracle.batch_knn_cosine(qs[i], ob, k) for i in range(16)]
+    want_h = [oracle.hamming_topk(qcs[i], codes, k) for i in range(16)]
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(6):
+                i = (t * 5 + rep) % 16
+                if (t + rep) % 2 == 0:
+                    got = ib.batch_knn_cosine(qs[i], gb, k)
+                    assert list(got.indices) == list(want[i].indices)
+                    assert np.array_equal(bits(got.scores), bits(want[i].scores))
+                else:
+                    gi, gd = ib.hamming_topk_many(qcs[i].reshape(1, -1), bc, k)
+                    assert np.array_equal(gi[0], want_h[i][0]) and np.array_equal(gd[0], want_h[i][1])
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+
+
+def test_one_process_two_devices(ib, oracle):
+    """one host process driving several GPUs, one thread and one row shard per device
+    (per-device mutexes, per-device function attributes): local top-k per shard, merged on the host by key order."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    n, d, k = 50000, 96, 10
+    rows = rand_rows(n, d, 7)
+    q = rand_rows(1, d, 8)[0]
+    want = oracle.batch_knn_cosine(q, oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d), k)
+    half = n // 2
+    out, errors = {}, []
+
+    def worker(dev):
+        try:
+            ib.init(dev)
+            lo, hi = (0, half) if dev == 0 else (half, n)
+            shard = ib.DeviceBatch.from_rows_flat(rows[lo:hi].reshape(-1), hi - lo, d, index_base=lo)
+            for _ in range(5):
+                idx, sc = ib.batch_knn_many("cosine", q.reshape(1, -1), shard, k)
+            toks = rand_rows(40 * 30, 128, 9 + dev)
+            off = np.arange(0, 40 * 30 + 1, 30, dtype=np.uint64)
+            ms = ib.maxsim_corpus(rand_rows(32, 128, 11), ib.TokenCorpus.from_tokens(toks, off, 128), cosine=True)
+            ref = oracle.maxsim_corpus(rand_rows(32, 128, 11), toks, off, cosine_flag=True)
+            assert np.allclose(ms, ref, rtol=1e-5, atol=1e-5)
+            out[dev] = (idx[0], sc[0])
+        except Exception as e:  # noqa: BLE001
+            errors.append((dev, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(dv,)) for dv in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    ib.init(0)
+    assert not errors, errors
+    pairs = sorted(((-float(s), int(i)) for dv in (0, 1) for i, s in zip(*out[dv])))[:k]
+    assert [i for _, i in pairs] == [int(i) for i in want.indices]
+
+
 # ------------------------------------------------------------------------------------------------ two-stage retrieval
 @pytest.mark.parametrize("n,d", [(3000, 96), (5000, 200), (1500, 7)])
 def test_derived_encodings_and_rerank(ib, oracle, n, d):
