@@ -79,6 +79,41 @@ __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
   return r;
 }
 
+// ---- packed f32x2 arithmetic (sm_100): two independent IEEE round-to-nearest operations per instruction. Results are
+// bit-identical to the scalar __fmul_rn / __fadd_rn / __fsub_rn (no contraction can happen across an asm boundary).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// a + b as fma(a, one, b) with `one` = {1.0f, 1.0f} held in a register the compiler cannot see through (a kernel
+// argument): a * 1 is exact, so this is exactly the rounded sum -- but unlike add.rn.f32x2 it cannot be contracted
+// with a preceding multiply. ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into ONE FFMA2 despite the explicit rounding
+// modifiers (seen in the SASS, also with -fmad=false), which would break the reference's unfused mul-then-add.
+__device__ __forceinline__ uint64_t add2_unfusable(uint64_t a, uint64_t b, uint64_t one2) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(one2), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2_rn(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ---- stateless synthetic generators; the oracle has the same functions on the CPU ----
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -48,6 +48,7 @@ struct PdxArgs {
   const float* norms_in;  // PDX_COSINE_NORMS
   const uint32_t* mask;   // MASKED: bit i set = vector i passes the predicate (batch_knn_filtered)
   float threshold;        // PDX_L2_PRUNE
+  float one;              // 1.0f, opaque to the compiler (see add2_unfusable)
 };
 
 template <int MODE>
@@ -57,6 +58,17 @@ __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
     acc = __fadd_rn(acc, __fmul_rn(diff, diff));  // *dist += diff * diff;
   } else {
     acc = __fadd_rn(acc, __fmul_rn(q, v));        // *prod += q_d * v_d;
+  }
+}
+
+// the same for two vectors at once (acc, v: packed pairs; q2 = {q, q}): unfused mul + add per lane, bit-identical
+template <int MODE>
+__device__ __forceinline__ void accumulate2(uint64_t q2, uint64_t v2, uint64_t& acc2, uint64_t one2) {
+  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE) {
+    const uint64_t diff = sub2_rn(q2, v2);
+    acc2 = add2_unfusable(mul2_rn(diff, diff), acc2, one2);
+  } else {
+    acc2 = add2_unfusable(mul2_rn(q2, v2), acc2, one2);
   }
 }
 
@@ -127,15 +139,50 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
       nib = active ? (a.mask[i0 >> 5] >> (i0 & 31)) & 0xFu : 0u;
       active = nib != 0;       // predicate pushdown: rows of rejected vectors are not even read
     }
-    float acc[QB][VPT];
-    float ss[VPT];   // sum of squares; PDX_L2_PRUNE: running max of the non-NaN partial distances
+    // accumulators as packed pairs (vectors 0,1 and 2,3 of this thread): the unfused multiply and add of the reference
+    // run as FMUL2 / FADD2 -- two IEEE operations per instruction, same bits, half the FP32 issue slots (what bounds
+    // the multi-query kernel)
+    uint64_t acc2[QB][2];
+    uint64_t ss2[2];
+    float mx[VPT];   // PDX_L2_PRUNE: running max of the non-NaN partial distances
 #pragma unroll
-    for (int j = 0; j < VPT; ++j) {
-      ss[j] = (MODE == PDX_L2_PRUNE) ? -INFINITY : 0.0f;  // the initial 0.0 is not a partial the reference tests
+    for (int h = 0; h < 2; ++h) {
+      ss2[h] = 0ull;  // {+0.0f, +0.0f}
 #pragma unroll
-      for (int q = 0; q < QB; ++q) acc[q][j] = 0.0f;
+      for (int q = 0; q < QB; ++q) acc2[q][h] = 0ull;
     }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) mx[j] = -INFINITY;  // the initial 0.0 is not a partial the reference tests
     const unsigned amask = (MODE == PDX_L2_PRUNE) ? __ballot_sync(FULL_MASK, active) : 0u;
+    const uint64_t one2 = pack2(a.one, a.one);
+    auto step = [&](const float4& v, unsigned dq) {
+      const uint64_t v01 = pack2(v.x, v.y), v23 = pack2(v.z, v.w);
+      if (NEED_SS) {
+        ss2[0] = add2_unfusable(mul2_rn(v01, v01), ss2[0], one2);
+        ss2[1] = add2_unfusable(mul2_rn(v23, v23), ss2[1], one2);
+      }
+      if (NEED_DOT) {
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const float qv = sq[(size_t)dq * QB + q];
+          const uint64_t q2 = pack2(qv, qv);
+          accumulate2<MODE>(q2, v01, acc2[q][0], one2);
+          accumulate2<MODE>(q2, v23, acc2[q][1], one2);
+        }
+      }
+      if (MODE == PDX_L2_PRUNE) {
+        // the reference prunes vector i at the first dimension whose partial distance exceeds the threshold
+        // (src/batch.rs:347-351). Partial sums of squares never decrease until one becomes NaN (a NaN compares
+        // false and stays alive), so "some partial > threshold" == "max of the non-NaN partials > threshold".
+        float p0, p1, p2, p3;
+        unpack2(acc2[0][0], p0, p1);
+        unpack2(acc2[0][1], p2, p3);
+        mx[0] = fmaxf(mx[0], p0);
+        mx[1] = fmaxf(mx[1], p1);
+        mx[2] = fmaxf(mx[2], p2);
+        mx[3] = fmaxf(mx[3], p3);
+      }
+    };
     if (active) {
       const float* p = a.data + i0;
       unsigned dd = 0;
@@ -145,54 +192,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
         for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(p + (size_t)u * a.ld);
         p += (size_t)U * a.ld;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float vv[VPT] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          if (NEED_SS) {
-#pragma unroll
-            for (int j = 0; j < VPT; ++j) ss[j] = __fadd_rn(ss[j], __fmul_rn(vv[j], vv[j]));
-          }
-          if (NEED_DOT) {
-#pragma unroll
-            for (int q = 0; q < QB; ++q) {
-              const float qv = sq[(size_t)(dd + u) * QB + q];
-#pragma unroll
-              for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
-            }
-          }
-          if (MODE == PDX_L2_PRUNE) {
-            // the reference prunes vector i at the first dimension whose partial distance exceeds the threshold
-            // (src/batch.rs:347-351). Partial sums of squares never decrease until one becomes NaN (a NaN compares
-            // false and stays alive), so "some partial > threshold" == "max of the non-NaN partials > threshold".
-#pragma unroll
-            for (int j = 0; j < VPT; ++j) ss[j] = fmaxf(ss[j], acc[0][j]);
-          }
-        }
+        for (int u = 0; u < U; ++u) step(v[u], dd + u);
         if (MODE == PDX_L2_PRUNE) {  // every vector this warp owns in the tile is pruned: stop reading its rows
-          const bool dead = ss[0] > a.threshold && ss[1] > a.threshold && ss[2] > a.threshold && ss[3] > a.threshold;
+          const bool dead = mx[0] > a.threshold && mx[1] > a.threshold && mx[2] > a.threshold && mx[3] > a.threshold;
           if (__all_sync(amask, dead)) { dd = a.d; break; }
         }
       }
       for (; dd < a.d; ++dd) {  // D % U tail
-        float4 v = ldg_stream_f4(p);
+        const float4 v = ldg_stream_f4(p);
         p += a.ld;
-        const float vv[VPT] = {v.x, v.y, v.z, v.w};
-        if (NEED_SS) {
-#pragma unroll
-          for (int j = 0; j < VPT; ++j) ss[j] = __fadd_rn(ss[j], __fmul_rn(vv[j], vv[j]));
-        }
-        if (NEED_DOT) {
-#pragma unroll
-          for (int q = 0; q < QB; ++q) {
-            const float qv = sq[(size_t)dd * QB + q];
-#pragma unroll
-            for (int j = 0; j < VPT; ++j) accumulate<MODE>(qv, vv[j], acc[q][j]);
-          }
-        }
-        if (MODE == PDX_L2_PRUNE) {
-#pragma unroll
-          for (int j = 0; j < VPT; ++j) ss[j] = fmaxf(ss[j], acc[0][j]);
-        }
+        step(v, dd);
       }
+    }
+    float acc[QB][VPT];
+    float ss[VPT];
+    unpack2(ss2[0], ss[0], ss[1]);
+    unpack2(ss2[1], ss[2], ss[3]);
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      unpack2(acc2[q][0], acc[q][0], acc[q][1]);
+      unpack2(acc2[q][1], acc[q][2], acc[q][3]);
+    }
+    if (MODE == PDX_L2_PRUNE) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) ss[j] = mx[j];
     }
 
     // epilogue: scores (and keys)
@@ -295,6 +318,7 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
   a.d = (unsigned)v.d;
   a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
   a.index_base = v.index_base;
+  a.one = 1.0f;
   a.k = (int)k;
   a.partials = ws.partials;
   a.group_partials = ws.group_partials;
@@ -355,6 +379,7 @@ cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, co
   a.d = (unsigned)v.d;
   a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
   a.index_base = v.index_base;
+  a.one = 1.0f;
   a.k = (int)k;
   a.partials = ws.partials;
   a.group_partials = ws.group_partials;
@@ -383,6 +408,7 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   a.d = (unsigned)v.d;
   a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
   a.index_base = v.index_base;
+  a.one = 1.0f;
   a.queries = dev_query;
   a.nq_valid = 1;
   a.scores_out = dev_out;
