@@ -791,13 +791,13 @@ def test_full_size_c4_c5_properties(ib, oracle):
 @pytest.fixture
 def tc_small(ib):
     ib.set_option("knn_tc_min_n", 4096)       # exercise the tensor-core path at test sizes
-    ib.set_option("knn_tc_min_queries", 32)
+    ib.set_option("knn_tc_min_queries", 9)
     yield ib
     ib.set_option("knn_tc_min_n", 100000)
 
 
 @pytest.mark.parametrize("n,d,nq", [(20_000, 768, 64), (50_000, 100, 40), (8_192, 32, 130), (33_000, 8, 33),
-                                    (300_000, 64, 272)])
+                                    (300_000, 64, 272), (120_000, 96, 9), (40_000, 200, 17)])
 def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
     """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
     result bit-identical to the reference (indices AND scores), including zero / tiny / huge vectors and queries,
