@@ -81,7 +81,7 @@ struct DeviceCtx {
 struct Options {
   bool knn_tc = true;
   size_t knn_tc_min_n = 100000;
-  size_t knn_tc_min_queries = 9;  // measured: one filter call 6.3 ms for 2..64 queries, 8-query scan pass 6.3 ms
+  size_t knn_tc_min_queries = 2;  // measured at 10M x 768: filter call 2.6 ms for 2..64 queries, 8-query scan pass 6.3 ms
   bool maxsim_tc = true;
 } g_opt;
 

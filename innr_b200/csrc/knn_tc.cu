@@ -51,13 +51,21 @@ constexpr int KSTAGES = 4;
 constexpr int X_BYTES = VT * KB * 2;   // 16 KB
 constexpr int Q_BYTES = QT * KB * 2;   // 32 KB
 constexpr int KSTAGE_BYTES = X_BYTES + Q_BYTES;
+// Q-resident variant (<= 64 queries, <= 12 K blocks): the whole f16 query operand stays in shared memory (one 8 KB box of
+// 64 rows per K block) and the ring carries X only, twice as deep -- with few queries the pass is a pure HBM stream of
+// Xh and the 4 x 16 KB of X the streaming variant keeps in flight per SM are far too little (5.7 ms instead of 2.2)
+constexpr int QR_ROWS = 64;
+constexpr int QR_BOX_BYTES = QR_ROWS * KB * 2;   // 8 KB
+constexpr int QR_MAX_KBLOCKS = 12;
+constexpr int QR_STAGES = 8;
+constexpr int KT_MAX_STAGES = 8;
 constexpr float COS_NORM_EPS = 1e-9f;   // src/batch.rs:721-727
 constexpr float TINY_NORM = 1e-30f;     // below this a vector / query is not normalised (handled by the exact path)
 constexpr unsigned CAND_CAP = 4096;
 
 struct KtShared {
-  uint64_t full[KSTAGES], empty[KSTAGES], acc_full[2], acc_empty[2];
-  float thr[2][QT];
+  uint64_t full[KT_MAX_STAGES], empty[KT_MAX_STAGES], acc_full[2], acc_empty[2], q_full;
+  alignas(16) float thr[2][QT];  // read as float4
   uint32_t tmem_base;
 };
 
@@ -97,11 +105,16 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+template <bool QRES>
 __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __grid_constant__ CUtensorMap tm_x,
                                                                        const __grid_constant__ CUtensorMap tm_q,
                                                                        const KtArgs a) {
+  constexpr int NST = QRES ? QR_STAGES : KSTAGES;
+  constexpr int ST_BYTES = QRES ? X_BYTES : KSTAGE_BYTES;
+  constexpr int RING_BYTES = NST * ST_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
-  KtShared* st = reinterpret_cast<KtShared*>(smem + KSTAGES * KSTAGE_BYTES);
+  uint8_t* s_qres = smem + RING_BYTES;  // QRES: kblocks x 8 KB
+  KtShared* st = reinterpret_cast<KtShared*>(smem + RING_BYTES + (QRES ? QR_MAX_KBLOCKS * QR_BOX_BYTES : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // contiguous range of (vector tile, query group) units for this CTA, query group fastest: the X tile of consecutive
@@ -114,10 +127,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
   const unsigned n_iters = n_units * a.kblocks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < KSTAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(&st->full[s], 1);
       mbar_init(&st->empty[s], 1);
     }
+    mbar_init(&st->q_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&st->acc_full[b], 1);
       mbar_init(&st->acc_empty[b], 4);
@@ -135,23 +149,28 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
   if (warp == 4) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
+      if (QRES && n_iters) {  // the whole query operand once (one group: n_qgroups == 1)
+        mbar_arrive_expect_tx(&st->q_full, a.kblocks * QR_BOX_BYTES);
+        for (unsigned kb = 0; kb < a.kblocks; ++kb) tma_load_2d(s_qres + kb * QR_BOX_BYTES, &tm_q, &st->q_full, (int)(kb * KB), 0);
+      }
       for (unsigned it = 0; it < n_iters; ++it) {
         const unsigned unit = u_lo + it / a.kblocks, kb = it % a.kblocks;
         const unsigned vt = unit / a.n_qgroups, qg = unit % a.n_qgroups;
-        const int s = it % KSTAGES;
-        mbar_wait(&st->empty[s], ((it / KSTAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&st->full[s], KSTAGE_BYTES);
-        uint8_t* sb = smem + s * KSTAGE_BYTES;
+        const int s = it % NST;
+        mbar_wait(&st->empty[s], ((it / NST) & 1) ^ 1);
+        mbar_arrive_expect_tx(&st->full[s], ST_BYTES);
+        uint8_t* sb = smem + s * ST_BYTES;
         tma_load_2d(sb, &tm_x, &st->full[s], (int)(kb * KB), (int)(vt * VT));
-        tma_load_2d(sb + X_BYTES, &tm_q, &st->full[s], (int)(kb * KB), (int)(qg * QT));
+        if (!QRES) tma_load_2d(sb + X_BYTES, &tm_q, &st->full[s], (int)(kb * KB), (int)(qg * QT));
       }
     }
   } else if (warp == 5) {
     // =========================== MMA issuer ===========================
     // the whole warp runs the loop (warp-uniform addresses and descriptors), one elected lane issues
     const uint64_t x_desc0 = make_smem_desc_kmajor_sw128(smem_u32(smem));
-    const uint64_t q_desc0 = make_smem_desc_kmajor_sw128(smem_u32(smem + X_BYTES));
+    const uint64_t q_desc0 = make_smem_desc_kmajor_sw128(smem_u32(QRES ? s_qres : smem + X_BYTES));
     unsigned it = 0;
+    if (QRES && n_units) mbar_wait(&st->q_full, 0);
     for (unsigned ul = 0; ul < n_units; ++ul) {
       const unsigned qg = (u_lo + ul) % a.n_qgroups;
       const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
@@ -159,12 +178,12 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
       const uint32_t acc = tmem + (ul & 1) * QT;
       mbar_wait(&st->acc_empty[ul & 1], ((ul >> 1) & 1) ^ 1);
       for (unsigned kb = 0; kb < a.kblocks; ++kb, ++it) {
-        const int s = it % KSTAGES;
-        mbar_wait(&st->full[s], (it / KSTAGES) & 1);
+        const int s = it % NST;
+        mbar_wait(&st->full[s], (it / NST) & 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          const uint64_t xd = desc_advance(x_desc0, (uint32_t)s * KSTAGE_BYTES);
-          const uint64_t qd = desc_advance(q_desc0, (uint32_t)s * KSTAGE_BYTES);
+          const uint64_t xd = desc_advance(x_desc0, (uint32_t)s * ST_BYTES);
+          const uint64_t qd = desc_advance(q_desc0, QRES ? kb * QR_BOX_BYTES : (uint32_t)s * ST_BYTES);
           if (kb == 0) umma_f16_c<false>(acc, xd, qd, idesc);
           else umma_f16_c<true>(acc, xd, qd, idesc);
 #pragma unroll
@@ -556,16 +575,20 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, qh,
                                                       qflag, thr, cnt, (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n));
   ++*launches;
+  const bool qres = p.nq_pad <= QR_ROWS && (p.d_pad + KB - 1) / KB <= QR_MAX_KBLOCKS;
   CUtensorMap tm_q;
-  if (!make_tmap_f16_rows(&tm_q, qh, p.nq_pad, p.d_pad, p.d_pad, QT)) return cudaErrorInvalidValue;
+  if (!make_tmap_f16_rows(&tm_q, qh, p.nq_pad, p.d_pad, p.d_pad, qres ? QR_ROWS : QT)) return cudaErrorInvalidValue;
   tmark();
 
   // 2. filter passes over growing prefixes
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
-  const size_t smem = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
+  const size_t smem_stream = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
+  const size_t smem_qres = (size_t)QR_STAGES * X_BYTES + (size_t)QR_MAX_KBLOCKS * QR_BOX_BYTES + sizeof(KtShared);
   if (!attr_set) {
-    e = cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(knn_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(knn_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qres);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -602,7 +625,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
     unsigned grid = (unsigned)ws.num_sms;
     if (grid > units) grid = (unsigned)units;
     if (last) cudaEventRecord(ev[1], s);
-    knn_tc_filter_kernel<<<grid, KT_THREADS, smem, s>>>(tm_xh, tm_q, a);
+    if (qres) knn_tc_filter_kernel<true><<<grid, KT_THREADS, smem_qres, s>>>(tm_xh, tm_q, a);
+    else knn_tc_filter_kernel<false><<<grid, KT_THREADS, smem_stream, s>>>(tm_xh, tm_q, a);
     ++*launches;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (last) {

@@ -791,13 +791,15 @@ def test_full_size_c4_c5_properties(ib, oracle):
 @pytest.fixture
 def tc_small(ib):
     ib.set_option("knn_tc_min_n", 4096)       # exercise the tensor-core path at test sizes
-    ib.set_option("knn_tc_min_queries", 9)
+    ib.set_option("knn_tc_min_queries", 1)
     yield ib
     ib.set_option("knn_tc_min_n", 100000)
+    ib.set_option("knn_tc_min_queries", 2)
 
 
 @pytest.mark.parametrize("n,d,nq", [(20_000, 768, 64), (50_000, 100, 40), (8_192, 32, 130), (33_000, 8, 33),
-                                    (300_000, 64, 272), (120_000, 96, 9), (40_000, 200, 17)])
+                                    (300_000, 64, 272), (120_000, 96, 9), (40_000, 200, 17), (70_000, 768, 1), (9_000, 48, 2),
+                                    (25_000, 1000, 5)])
 def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
     """Large query batches go through tcgen05 as a pruning filter (csrc/knn_tc.cu); the exact rescoring must make the
     result bit-identical to the reference (indices AND scores), including zero / tiny / huge vectors and queries,
@@ -811,11 +813,14 @@ def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
     rows[440] *= np.float32(1e-12)      # below the reference's 1e-9 cosine guard -> cosine 0.0, dot tiny
     rows[441] *= np.float32(1e-30)      # denormal range
     qs = rand_rows(nq, d, 99)
-    qs[3] = 0.0                         # zero-norm query -> every cosine 0.0 -> first k indices (exact-scan fallback)
-    qs[5] = rows[300] * 2.0             # query parallel to the duplicates
-    qs[6] *= np.float32(1e-12)          # below the cosine guard
-    qs[7] *= np.float32(1e6)
-    qs[8] = -rows[421]                  # antiparallel to a huge vector
+    if nq > 8:
+        qs[3] = 0.0                     # zero-norm query -> every cosine 0.0 -> first k indices (exact-scan fallback)
+        qs[5] = rows[300] * 2.0         # query parallel to the duplicates
+        qs[6] *= np.float32(1e-12)      # below the cosine guard
+        qs[7] *= np.float32(1e6)
+        qs[8] = -rows[421]              # antiparallel to a huge vector
+    elif nq > 1:
+        qs[1] = rows[300] * 2.0
     gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
     for metric in ("cosine", "dot"):
         for k in (1, 10, 32):
