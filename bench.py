@@ -14,7 +14,7 @@ row-sharded over the N GPUs (one allgather of k keys + merge per query). Prints 
   cpu_baseline  the oracle (C++ restatement of innr 0.6.3, "port") timed on this box's host cores on a bounded sample
 
 Workloads: knn_cosine_1q (default, C2a) | knn_cosine_multi (C2b, --queries Q) | batch_demo (C1) | maxsim (C3) |
-hamming (C4) | u8 (C5). `--scale f` shrinks the corpus (for quick checks; reported in config).
+hamming (C4) | u8 (C5) | knn_cosine_1q_filter (C2a through the f16 filter path, an option). `--scale f` shrinks the corpus (for quick checks; reported in config).
 """
 import argparse
 import ctypes as C
@@ -36,6 +36,7 @@ WORKLOADS = {
     # name: (description, metric name, unit)
     "knn_cosine_1q": ("batch_knn_cosine 10M x 768 f32, 1 query/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
     "knn_cosine_multi": ("batch_knn_cosine 10M x 768 f32, Q queries/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
+    "knn_cosine_1q_filter": ("batch_knn_cosine 10M x 768 f32, 1 query/step, k=10, through the f16 tensor-core filter + exact rescoring (option knn_tc_min_queries=1; same bits as the scan)", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
     "batch_demo": ("batch_knn_dot 10K x 128 f32 G-ref lattice, 100 queries/step, k=10", "batch_knn_dot_top10_queries_per_s", "queries/s"),
     "maxsim": ("maxsim_cosine 32 x 128 query tokens vs 1M docs x 180 tokens x 128d", "maxsim_cosine_docs_per_s", "docs/s"),
     "hamming": ("binary_hamming top-100 over 100M 1024-bit codes, 1 query/step", "hamming_top100_queries_per_s", "queries/s"),
@@ -225,6 +226,12 @@ class KnnF32(Workload):
         passes = (self.nq + 7) // 8 if self.nq > 1 else 1
         self.kernel_bytes = self.n_local * self.d * 4 * passes
         self.kernel_name = "pdx_scan_kernel"
+        if a.workload == "knn_cosine_1q_filter":
+            # the bytes the filter actually streams: the f16 unit-vector copy (the f32 corpus is only touched by the
+            # ~200 rescored rows); reported against HBM like the scan
+            ib.set_option("knn_tc_min_queries", 1)
+            self.kernel_bytes = self.n_local * self.d * 2
+            self.kernel_name = "knn_tc_filter_kernel<QRES> (4 passes + exact rescoring: whole call)"
         self.launches = passes + 1  # scan launch(es) + merge/decode
         self.h2d, self.d2h = self.nq * self.d * 4, self.nq * self.k * 12
         self.corpus_gb = self.n * self.d * 4 / 1e9
@@ -405,7 +412,7 @@ class MaxSim(Workload):
 
 
 def make_workload(args, rank, world, torch):
-    cls = {"knn_cosine_1q": KnnF32, "knn_cosine_multi": KnnF32, "batch_demo": KnnF32, "maxsim": MaxSim,
+    cls = {"knn_cosine_1q": KnnF32, "knn_cosine_1q_filter": KnnF32, "knn_cosine_multi": KnnF32, "batch_demo": KnnF32, "maxsim": MaxSim,
            "hamming": Hamming, "u8": U8}[args.workload]
     return cls(args, rank, world, torch)
 
