@@ -6,8 +6,10 @@ from innr_b200 import synth, sharded
 ib.init(0)
 n, d = 10_000_000, 768
 shard = ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, 0, n, d)
-sk = sharded.ShardedKnn(shard, "f32", "cosine")
-for nq in (16, 64, 256):
+import os
+metric = os.environ.get("METRIC", "cosine")
+sk = sharded.ShardedKnn(shard, "f32", metric)
+for nq in (16, 64, 1024):
     qs = torch.from_numpy(synth.ghash_f32(synth.SALT_QUERY, 0, nq * d).reshape(nq, d)).cuda()
     for _ in range(3): sk.knn_dev(qs, nq, 10)
     torch.cuda.synchronize()

@@ -1,4 +1,5 @@
-// knn_tc.cu -- multi-query batch_knn_dot / batch_knn_cosine with the tensor cores as an exact-result FILTER.
+// knn_tc.cu -- multi-query batch_knn (L2) / batch_knn_dot / batch_knn_cosine with the tensor cores as an exact-result
+// FILTER.
 //
 // For large query batches (BASELINE C2b: 1024 queries over 10M x 768) scoring is a dense contraction. The reference
 // (src/batch.rs:742-800) scores every (query, vector) pair in f32 and fully sorts; results must stay bit-exact with
@@ -57,7 +58,7 @@ constexpr int KSTAGE_BYTES = X_BYTES + Q_BYTES;
 constexpr int QR_ROWS = 64;
 constexpr int QR_BOX_BYTES = QR_ROWS * KB * 2;   // 8 KB
 constexpr int QR_MAX_KBLOCKS = 12;
-constexpr int QR_STAGES = 8;
+constexpr int QR_STAGES = 7;    // 7 x 16 KB ring + 96 KB of Q + barriers and per-column arrays = 217 KB
 constexpr int KT_MAX_STAGES = 8;
 constexpr float COS_NORM_EPS = 1e-9f;   // src/batch.rs:721-727
 constexpr float TINY_NORM = 1e-30f;     // below this a vector / query is not normalised (handled by the exact path)
@@ -65,7 +66,10 @@ constexpr unsigned CAND_CAP = 4096;
 
 struct KtShared {
   uint64_t full[KT_MAX_STAGES], empty[KT_MAX_STAGES], acc_full[2], acc_empty[2], q_full;
-  alignas(16) float thr[2][QT];  // read as float4
+  alignas(16) float thr[2][QT];  // read as float4; L2: threshold minus the query's constant slack
+  alignas(16) float hlo[2][QT];  // L2: 1/(2||q||) * (1 - delta), per query column
+  alignas(16) float hhi[2][QT];  // L2: 1/(2||q||) * (1 + delta)
+  alignas(16) float cq[2][QT];   // L2: per-query constant slack (the reference's own rounding, relative to ||q||)
   uint32_t tmem_base;
 };
 
@@ -73,6 +77,8 @@ struct KtArgs {
   unsigned n_rows;          // rows [0, n_rows) of the corpus are filtered by this pass
   unsigned n_qgroups, kblocks, nq_pad;
   int cosine;
+  int l2;                   // squared-L2 metric: u = ||x|| S - ||x||^2 / (2||q||) ranks like -distance (see header)
+  const float* qaux;        // l2: 3 x nq_pad floats: hlo, hhi, cq
   int dense;                // first pass (threshold -inf, n_rows <= CAND_CAP): slot = row, no counters
   float eps;
   const float* norms;       // exact ||x|| per vector
@@ -202,8 +208,18 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
       const unsigned qt_u = min((unsigned)QT, a.nq_pad - qg * QT);
       const int ab = ul & 1;
       const unsigned v = vt * VT + warp * 32 + lane;  // local vector index of this lane
-      for (unsigned c = threadIdx.x; c < QT; c += 128) st->thr[ab][c] = c < qt_u ? a.thr[qg * QT + c] : INFINITY;
-      float rn = 0.0f, e = 0.0f;
+      for (unsigned c = threadIdx.x; c < QT; c += 128) {
+        const bool cv = c < qt_u;
+        float cq = 0.0f;
+        if (a.l2) {
+          st->hlo[ab][c] = cv ? a.qaux[qg * QT + c] : 0.0f;
+          st->hhi[ab][c] = cv ? a.qaux[a.nq_pad + qg * QT + c] : 0.0f;
+          cq = cv ? a.qaux[2 * a.nq_pad + qg * QT + c] : 0.0f;
+          st->cq[ab][c] = cq;
+        }
+        st->thr[ab][c] = cv ? a.thr[qg * QT + c] - cq : INFINITY;
+      }
+      float rn = 0.0f, e = 0.0f, xx = 0.0f;
       const bool vvalid = v < a.n_rows;
       if (vvalid) {
         const float nv = a.norms[v];
@@ -213,6 +229,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
         } else {
           rn = nv >= TINY_NORM ? nv : 0.0f;
           e = a.eps * rn + 1e-18f;
+          if (a.l2) xx = nv * nv;
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");  // thresholds of this unit visible to the 4 epilogue warps
@@ -228,6 +245,18 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
           tc_fence_before_sync();
           if (lane == 0) mbar_arrive(&st->acc_empty[ab]);
         }
+        // upper / lower bound of the pair's rank value: S*r +- e, for L2 minus ||x||^2 * 1/(2||q||) (widened by delta)
+        // and minus the query's constant slack on the lower side (the thresholds in shared memory carry it already)
+        auto upper = [&](int j) {
+          float u = fmaf(__uint_as_float(r[j]), rn, e);
+          if (a.l2) u = fmaf(-xx, st->hlo[ab][c0 + j], u);
+          return u;
+        };
+        auto lower = [&](int j) {
+          float l = fmaf(__uint_as_float(r[j]), rn, -e);
+          if (a.l2) l = fmaf(-xx, st->hhi[ab][c0 + j], l) - st->cq[ab][c0 + j];
+          return l;
+        };
         if (a.dense) {  // every pair is kept: lower bound to slot v of its query, no atomics (the counters are preset)
           if (vvalid) {
 #pragma unroll
@@ -235,27 +264,39 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
               if (c0 + j < qt_u) {
                 const size_t o = (size_t)(qg * QT + c0 + j) * CAND_CAP + v;
                 a.cand_idx[o] = v;
-                a.cand_lb[o] = fmaf(__uint_as_float(r[j]), rn, -e);
+                a.cand_lb[o] = lower(j);
               }
           }
           continue;
         }
         const float4* t4 = reinterpret_cast<const float4*>(&st->thr[ab][c0]);
         bool any = false;
+        if (a.l2) {
+          const float4* h4 = reinterpret_cast<const float4*>(&st->hlo[ab][c0]);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 t = t4[j4];
-          any |= fmaf(__uint_as_float(r[4 * j4 + 0]), rn, e) >= t.x;
-          any |= fmaf(__uint_as_float(r[4 * j4 + 1]), rn, e) >= t.y;
-          any |= fmaf(__uint_as_float(r[4 * j4 + 2]), rn, e) >= t.z;
-          any |= fmaf(__uint_as_float(r[4 * j4 + 3]), rn, e) >= t.w;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = t4[j4], h = h4[j4];
+            any |= fmaf(-xx, h.x, fmaf(__uint_as_float(r[4 * j4 + 0]), rn, e)) >= t.x;
+            any |= fmaf(-xx, h.y, fmaf(__uint_as_float(r[4 * j4 + 1]), rn, e)) >= t.y;
+            any |= fmaf(-xx, h.z, fmaf(__uint_as_float(r[4 * j4 + 2]), rn, e)) >= t.z;
+            any |= fmaf(-xx, h.w, fmaf(__uint_as_float(r[4 * j4 + 3]), rn, e)) >= t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 t = t4[j4];
+            any |= fmaf(__uint_as_float(r[4 * j4 + 0]), rn, e) >= t.x;
+            any |= fmaf(__uint_as_float(r[4 * j4 + 1]), rn, e) >= t.y;
+            any |= fmaf(__uint_as_float(r[4 * j4 + 2]), rn, e) >= t.z;
+            any |= fmaf(__uint_as_float(r[4 * j4 + 3]), rn, e) >= t.w;
+          }
         }
         if (any && vvalid) {  // rare except in the first, dense pass. All atomics of the lane are issued before any
                               // of their results is used, so their round trips overlap.
           unsigned pos[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const bool hit = (c0 + j < qt_u) && fmaf(__uint_as_float(r[j]), rn, e) >= st->thr[ab][c0 + j];
+            const bool hit = (c0 + j < qt_u) && upper(j) >= st->thr[ab][c0 + j];
             pos[j] = hit ? atomicAdd(&a.cand_count[qg * QT + c0 + j], 1u) : 0xFFFFFFFFu;
           }
 #pragma unroll
@@ -263,7 +304,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) knn_tc_filter_kernel(const __gr
             if (pos[j] < CAND_CAP) {
               const size_t o = (size_t)(qg * QT + c0 + j) * CAND_CAP + pos[j];
               a.cand_idx[o] = v;
-              a.cand_lb[o] = fmaf(__uint_as_float(r[j]), rn, -e);
+              a.cand_lb[o] = lower(j);
             }
           }
         }
@@ -308,11 +349,23 @@ __global__ void knn_tc_build_xh_kernel(const float* __restrict__ pdx, size_t ld,
   }
 }
 
+// ---- squared L2 through the same filter ------------------------------------------------------------------------
+// d(q,x) = ||q||^2 + ||x||^2 - 2 q.x, so u = (||q||^2 - d) / (2||q||) = ||x|| cos(q,x) - ||x||^2 / (2||q||) ranks like
+// -distance within a query, and ||x|| S +- ||x|| eps brackets its first term exactly as for the dot product. Slack
+// for everything else, relative to the two positive terms d <= 2(||q||^2 + ||x||^2) is made of:
+//   * the reference's own f32 result (sequential sum of d terms, 3 roundings each): |d_ref - d| <= (d+2) 2^-24 d
+//     -> (d+2) 2^-24 (||q|| + ||x||^2/||q||) in units of u: a per-query constant l2_cq and 2(d+2) 2^-24 on the second term;
+//   * ||x|| as stored (sqrt of the sequential f32 sum), its square, 1/(2||q||), the fmas of the bound itself:
+//     <= (2d + 16) 2^-24 relative on the second term.
+__host__ __device__ __forceinline__ float l2_delta(unsigned d) { return (4.0f * (float)d + 32.0f) * 5.9604645e-8f; }
+__host__ __device__ __forceinline__ float l2_cq(unsigned d, float qn) { return 2.0f * ((float)d + 2.0f) * 5.9604645e-8f * qn; }
+
 // ---- per call: Qh row = f16(q / ||q||); ||q|| is the sequential f32 sum of batch_cosine_into (src/batch.rs:714) ------
 __global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned nq, unsigned d, unsigned nq_pad,
-                                           unsigned d_pad, int cosine, __half* __restrict__ qh,
+                                           unsigned d_pad, int cosine, int l2, __half* __restrict__ qh,
                                            unsigned* __restrict__ qflag, float* __restrict__ thr,
-                                           unsigned* __restrict__ cand_count, unsigned first_pass_rows) {
+                                           unsigned* __restrict__ cand_count, float* __restrict__ qaux,
+                                           unsigned first_pass_rows) {
   const unsigned row = blockIdx.x;
   __shared__ float s_inv;
   __shared__ unsigned s_bad;
@@ -328,6 +381,14 @@ __global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned
       // answered by the exact scan
       bad = (!finite || qn < TINY_NORM || (cosine && qn < COS_NORM_EPS)) ? 1u : 0u;
       inv = bad ? 0.0f : 1.0f / qn;
+      if (l2) {  // see l2_slack(): h = 1/(2||q||) widened by delta, constant slack gamma * ||q||
+        const float h = bad ? 0.0f : 0.5f * inv;
+        qaux[row] = h * (1.0f - l2_delta(d));
+        qaux[nq_pad + row] = h * (1.0f + l2_delta(d));
+        qaux[2 * nq_pad + row] = bad ? 0.0f : l2_cq(d, qn);
+      }
+    } else if (l2) {
+      qaux[row] = qaux[nq_pad + row] = qaux[2 * nq_pad + row] = 0.0f;
     }
     s_inv = inv;
     s_bad = bad;
@@ -377,7 +438,7 @@ template <int R>
 __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float* __restrict__ data, size_t ld, unsigned n,
                                                                     unsigned d, unsigned index_base,
                                                                     const float* __restrict__ queries, int cosine,
-                                                                    float eps, const float* __restrict__ norms,
+                                                                    int l2, float eps, const float* __restrict__ norms,
                                                                     const unsigned* __restrict__ qflag,
                                                                     unsigned* __restrict__ cand_count,
                                                                     const unsigned* __restrict__ cand,
@@ -435,34 +496,48 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
       const float lb = cand_lb[(size_t)q * CAND_CAP + c];
       const float nv = norms[i];
       const float e = cosine ? (nv > COS_NORM_EPS ? eps : 0.0f) : (eps * (nv >= TINY_NORM ? nv : 0.0f) + 1e-18f);
-      const float ub = fmaf(2.0f, e, lb) + 1e-6f * (fabsf(lb) + e);  // the filter's upper bound, rounding included
+      float ub = fmaf(2.0f, e, lb) + 1e-6f * (fabsf(lb) + e);  // the filter's upper bound, rounding included
+      if (l2) {  // + the widening of the ||x||^2 / (2||q||) term and twice the query's constant slack
+        const float t = nv * nv * (0.5f / qn);
+        ub += 2.0f * l2_delta(d) * t + 2.0f * l2_cq(d, qn) + 1e-6f * t;
+      }
       valid = ub >= bound;
     }
     if (valid) {
       const float* p = data + i;
       float acc = 0.0f, ss = 0.0f;
       unsigned dd = 0;
-      for (; dd + 8 <= d; dd += 8) {  // the reference's sequential unfused sums (src/batch.rs:290-296, 676-681)
+      for (; dd + 8 <= d; dd += 8) {  // the reference's sequential unfused sums (src/batch.rs:257-265, 290-296, 676-681)
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(dd + u) * ld);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          acc = __fadd_rn(acc, __fmul_rn(sq[dd + u], v[u]));
-          ss = __fadd_rn(ss, __fmul_rn(v[u], v[u]));
+          if (l2) {
+            const float diff = __fsub_rn(sq[dd + u], v[u]);
+            acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+          } else {
+            acc = __fadd_rn(acc, __fmul_rn(sq[dd + u], v[u]));
+            ss = __fadd_rn(ss, __fmul_rn(v[u], v[u]));
+          }
         }
       }
       for (; dd < d; ++dd) {
         const float v = __ldg(p + (size_t)dd * ld);
-        acc = __fadd_rn(acc, __fmul_rn(sq[dd], v));
-        ss = __fadd_rn(ss, __fmul_rn(v, v));
+        if (l2) {
+          const float diff = __fsub_rn(sq[dd], v);
+          acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+        } else {
+          acc = __fadd_rn(acc, __fmul_rn(sq[dd], v));
+          ss = __fadd_rn(ss, __fmul_rn(v, v));
+        }
       }
       float s = acc;
       if (cosine) {
         const float nrm = __fsqrt_rn(ss);
         s = (!(qn < COS_NORM_EPS) && nrm > COS_NORM_EPS) ? __fdiv_rn(acc, __fmul_rn(qn, nrm)) : 0.0f;
       }
-      key = make_key_desc(s, index_base + i);
+      key = l2 ? make_key_asc(s, index_base + i) : make_key_desc(s, index_base + i);
     }
     list.offer(key, valid, thr, k, lane);
   }
@@ -486,7 +561,7 @@ bool make_tmap_f16_rows(CUtensorMap* m, const void* base, uint64_t rows, uint64_
 // workspace layout ------------------------------------------------------------------------------------------------------
 struct KnnTcPlan {
   unsigned nq_pad, d_pad;
-  size_t off_qh, off_qflag, off_thr, off_cnt, off_idx, off_lb, total;
+  size_t off_qh, off_qflag, off_thr, off_cnt, off_qaux, off_idx, off_lb, total;
 };
 
 KnnTcPlan make_plan(size_t d, size_t nq) {
@@ -499,6 +574,7 @@ KnnTcPlan make_plan(size_t d, size_t nq) {
   p.off_qflag = take((size_t)p.nq_pad * 4);
   p.off_thr = take((size_t)p.nq_pad * 4);
   p.off_cnt = take((size_t)p.nq_pad * 4);
+  p.off_qaux = take((size_t)p.nq_pad * 3 * 4);
   p.off_idx = take((size_t)p.nq_pad * CAND_CAP * 4);
   p.off_lb = take((size_t)p.nq_pad * CAND_CAP * 4);
   p.total = o;
@@ -516,7 +592,7 @@ size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) {
 }
 
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k) {
-  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED) && nq >= 1 && k >= 1 && k <= 32 && v.d >= 1 && v.n >= 4096 &&
+  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED || mode == PDX_L2) && nq >= 1 && k >= 1 && k <= 32 && v.d >= 1 && v.n >= 4096 &&
          v.n < 0x7FFFFF00ull;
 }
 
@@ -544,13 +620,14 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
                               const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys, void* workspace,
                               unsigned* host_counts, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
                               std::vector<unsigned>* overflow_queries, KnnTcStats* stats) {
-  const int cosine = mode == PDX_COSINE_FUSED;
+  const int cosine = mode == PDX_COSINE_FUSED, l2 = mode == PDX_L2;
   const KnnTcPlan p = make_plan(v.d, nq);
   uint8_t* w = (uint8_t*)workspace;
   __half* qh = (__half*)(w + p.off_qh);
   unsigned* qflag = (unsigned*)(w + p.off_qflag);
   float* thr = (float*)(w + p.off_thr);
   unsigned* cnt = (unsigned*)(w + p.off_cnt);
+  float* qaux = (float*)(w + p.off_qaux);
   unsigned* cand_idx = (unsigned*)(w + p.off_idx);
   float* cand_lb = (float*)(w + p.off_lb);
   cudaError_t e;
@@ -572,8 +649,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   tmark();
 
   // 1. operands, first-pass thresholds, zeroed counters
-  knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, qh,
-                                                      qflag, thr, cnt, (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n));
+  knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, l2, qh,
+                                                      qflag, thr, cnt, qaux, (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n));
   ++*launches;
   const bool qres = p.nq_pad <= QR_ROWS && (p.d_pad + KB - 1) / KB <= QR_MAX_KBLOCKS;
   CUtensorMap tm_q;
@@ -611,6 +688,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   a.kblocks = (p.d_pad + KB - 1) / KB;
   a.nq_pad = p.nq_pad;
   a.cosine = cosine;
+  a.l2 = l2;
+  a.qaux = qaux;
   a.eps = 1.05e-3f + 3.5e-7f * (float)v.d;
   a.norms = dev_norms;
   a.thr = thr;
@@ -641,7 +720,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   // 3. exact rescoring + selection
   const size_t rs_smem = ((v.d + 3) & ~(size_t)3) * 4 + (size_t)(RS_THREADS / 32) * k * 8;
   knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
-                                                                     dev_queries, cosine, a.eps, dev_norms, qflag, cnt, cand_idx, cand_lb,
+                                                                     dev_queries, cosine, l2, a.eps, dev_norms, qflag, cnt, cand_idx, cand_lb,
                                                                      (int)k, dev_keys);
   ++*launches;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;

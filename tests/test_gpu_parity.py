@@ -830,6 +830,17 @@ def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
             widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
             assert np.array_equal(idx, widx), (metric, k, np.argwhere(idx != widx)[:5])
             assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
+    # squared L2 (batch_knn, the TopK path: exact-tie groups compare as sets)
+    for k in (1, 10, 32):
+        idx, sc = ib.batch_knn_many("l2", qs, gb, k)
+        st = ib.knn_tc_last_stats()
+        assert st["passes"] >= 2 and st["exact_scan_queries"] <= 4, st
+        widx, wsc = oracle.batch_knn_many("l2", qs, ob, k, n_threads=8)
+        assert np.array_equal(bits(sc), bits(wsc)), ("l2", k, np.argwhere(bits(sc) != bits(wsc))[:5])
+        for j in range(nq):
+            got_r = type("R", (), {"indices": [int(i) for i in idx[j]], "scores": sc[j]})
+            want_r = type("R", (), {"indices": [int(i) for i in widx[j]], "scores": wsc[j]})
+            assert_knn_equal(got_r, want_r, ties_as_sets=True)
 
 
 def test_knn_tc_on_the_reference_lattice(tc_small, oracle):
