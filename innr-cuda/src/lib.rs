@@ -1,54 +1,7 @@
-# INTEGRATION — binding libinnr_cuda into innr (Rust)
+//! innr-cuda: thin sys + safe crate over libinnr_cuda (include/innr_cuda.h).
+//! UNVERIFIED SOURCE: written against the C header, never compiled here (no cargo/rustc in this environment,
+//! SURVEY F2). The same symbols are bound and exercised through Python ctypes (innr_b200/_lib.py, tests/).
 
-What a maintainer of arclabs561/innr adds to use the device path. Nothing here could be compiled in this
-environment (no `cargo`/`rustc`, no network — SURVEY F2); it is the reference-side binding written against
-`include/innr_cuda.h`, which *is* built and tested (Python `ctypes` binds the same symbols:
-`innr_b200/_lib.py`, `tests/test_abi.py` checks that every symbol the header declares is exported).
-
-## 1. Crate layout
-
-```
-innr/
-  Cargo.toml                 # + [features] cuda = ["dep:innr-cuda"]
-  innr-cuda/                 # new thin sys+safe crate (sources of this section live in this repo under innr-cuda/)
-    Cargo.toml               # links = "innr_cuda"
-    build.rs                 # nvcc -gencode arch=compute_100a,code=sm_100a -> libinnr_cuda.so
-    csrc/ include/           # this repo's innr_b200/csrc and include/
-    src/lib.rs               # extern "C" block + safe wrappers (below)
-  src/backend.rs             # + Backend::Cuda            (src/backend.rs:18-41)
-  src/batch.rs               # + DeviceBatch, cfg(feature = "cuda") branches
-  src/binary.rs src/scalar.rs src/maxsim.rs src/topk.rs   # same pattern
-```
-
-`innr-cuda/build.rs`:
-
-```rust
-use std::{env, path::PathBuf, process::Command};
-fn main() {
-    let out = PathBuf::from(env::var("OUT_DIR").unwrap());
-    let srcs = ["api.cu", "scan_f32.cu", "layout.cu", "hamming.cu", "u8.cu", "maxsim.cu", "maxsim_tc.cu", "knn_tc.cu"];
-    let mut objs = vec![];
-    for s in srcs {
-        let o = out.join(s).with_extension("o");
-        let st = Command::new("nvcc")
-            .args(["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-                   "-Xcompiler", "-fPIC,-ffp-contract=off", "-c"])
-            .arg(format!("csrc/{s}")).arg("-o").arg(&o).status().expect("nvcc");
-        assert!(st.success(), "nvcc failed on {s}");
-        objs.push(o);
-        println!("cargo:rerun-if-changed=csrc/{s}");
-    }
-    let so = out.join("libinnr_cuda.so");
-    assert!(Command::new("nvcc").args(["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o"])
-        .arg(&so).args(&objs).status().unwrap().success());
-    println!("cargo:rustc-link-search=native={}", out.display());
-    println!("cargo:rustc-link-lib=dylib=innr_cuda");
-}
-```
-
-## 2. `extern "C"` block (one line per symbol of `include/innr_cuda.h`)
-
-```rust
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_int, c_void};
 #[repr(C)] pub struct innr_cuda_corpus { _p: [u8; 0] }
@@ -111,15 +64,8 @@ extern "C" {
     pub fn innr_cuda_maxsim(c: *const innr_cuda_corpus, q_tokens: *const f32, n_q: usize, q_dim: usize, cosine_flag: c_int, out_scores: *mut f32) -> c_int;
     pub fn innr_cuda_maxsim_dev(c: *const innr_cuda_corpus, dev_q: *const f32, n_q: usize, cosine_flag: c_int, dev_scores: *mut f32, stream: *mut c_void) -> c_int;
 }
-```
 
-## 3. Safe wrappers: same panics, same results
-
-The shim asserts **before** the FFI call with the reference's own messages, so panic conditions and text stay
-identical (`src/batch.rs:251,285,386,711,743,778`, `src/binary.rs:155-159`, `src/scalar.rs:266-272`,
-`src/maxsim.rs:103-110`); the library re-checks and would answer `INNR_EINVAL`.
-
-```rust
+// ---- safe wrappers: same panics, same results ----
 pub struct DeviceBatch { h: *mut innr_cuda_corpus, n: usize, d: usize }
 unsafe impl Send for DeviceBatch {} unsafe impl Sync for DeviceBatch {}   // immutable after upload
 impl Drop for DeviceBatch { fn drop(&mut self) { unsafe { innr_cuda_free(self.h); } } }
@@ -178,24 +124,3 @@ fn check(rc: c_int) {
         panic!("innr-cuda: {msg}");       // INNR_EINVAL mirrors the reference's assert_eq! panics
     }
 }
-```
-
-`src/backend.rs`: `Backend` is `#[non_exhaustive]` (`:19`), so `Cuda` is a non-breaking addition; its `Display`
-arm returns `"cuda"` (= `innr_cuda_backend_name()`); `dense_backend(len)` keeps its CPU answers
-(`src/backend.rs:96-112` still pass) and a corpus-aware query (`DeviceBatch::backend() -> Backend::Cuda`) reports
-the device path, because `dense_backend(len)` has no corpus argument.
-
-## 4. Multi-GPU from Rust
-
-One process per GPU is what this repo's harness does (torch.distributed). A Rust host can instead drive all GPUs
-of a box from one process: `innr_cuda_init(g)` per device, one shard handle per device with
-`index_base = first global row`, `innr_cuda_batch_knn_keys_dev` on each device's stream, one
-`ncclAllGather(k × u64)` (or a peer copy into rank 0), then `innr_cuda_merge_keys_dev`. The key layout is
-`(order_bits(score) << 32) | global_index`, identical on every device, so the merge is a sort of distinct keys.
-
-## 5. What the Python mirror is
-
-`innr_b200/` binds the same C-ABI with `ctypes` and reproduces the reference's host types and error behaviour
-(`AssertionError` where the reference panics). It exists so the parity tests can be the reference's own tests
-(`tests/test_ref_*.py` run unchanged against the oracle and against the CUDA product). It is not a second
-implementation: every number it returns comes out of `libinnr_cuda.so`.
