@@ -39,29 +39,33 @@ using namespace tc;
 constexpr int TC_THREADS = 320;   // 4 epilogue + 4 converter + TMA + MMA warps
 constexpr int TILE_M = 128;                 // tokens per tile (UMMA M)
 constexpr int CHUNK = 32;                   // tokens per stream per tile (one TMEM lane quadrant)
-constexpr int NQ = 32;                      // query tokens (padded)
-constexpr int UMMA_N = 64;                  // [Qhi ; Qlo]
-constexpr int ACC = 3;                      // TMEM accumulator stages (64 columns each)
+constexpr int NQ = 32;                      // query tokens per group (one TMEM column block)
+constexpr int ACC_MAX = 3;                  // TMEM accumulator stages: 3 x 64 columns (G = 1) or 2 x 128 (G = 2)
 constexpr int MAX_STAGES = 8;
 constexpr int PANEL_BYTES = TILE_M * 128;   // 16 KB: [128 rows][32 floats], 128-byte swizzle
 constexpr int BOX_BYTES = CHUNK * 128;      // one TMA box: 32 rows x 128 B
-constexpr int QPANEL_BYTES = UMMA_N * 128;  // 8 KB
 constexpr float EPS_SQ = 1e-9f * 1e-9f;
 constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo buffers of DIM (<= 128) columns
 
-// P = dim / 32 panels of 32 floats (dim 32, 64, 96, 128): the shared-memory ring deepens as the tile shrinks
-template <int P>
+// P = dim / 32 panels of 32 floats (dim 32, 64, 96, 128); G = groups of 32 query tokens scored in ONE corpus pass
+// (B operand = [Qhi ; Qlo] of 64 G rows, accumulator 64 G columns). The shared-memory ring takes what the operands leave.
+template <int P, int G>
 struct Shape {
   static constexpr int DIM = 32 * P;
+  static constexpr int UMMA_N = 64 * G;                 // [Qhi ; Qlo]
+  static constexpr int ACC = G == 1 ? 3 : 2;
   static constexpr int STAGE_BYTES = P * PANEL_BYTES;
+  static constexpr int QPANEL_BYTES = UMMA_N * 128;     // one K panel of the B operand
   static constexpr int QBYTES = P * QPANEL_BYTES;
-  static constexpr int STAGES = P == 4 ? 3 : (P == 3 ? 4 : (P == 2 ? 6 : MAX_STAGES));
+  static constexpr int FIT = (227 * 1024 - 1024 - QBYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > MAX_STAGES ? MAX_STAGES : FIT;
 };
 
 struct SharedTail {  // everything after the operand buffers
-  uint64_t full[MAX_STAGES], empty[MAX_STAGES], lo_ready[2], lo_free[2], tmem_full[ACC], tmem_empty[ACC];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], lo_ready[2], lo_free[2], tmem_full[ACC_MAX], tmem_empty[ACC_MAX];
   unsigned long long s_tok[5];  // token boundaries of the four streams
   unsigned s_doc[5];            // document boundaries of the four streams
+  float part[4][CHUNK + 1];     // G = 2: per epilogue warp, first-group partial sums of the documents ending in the chunk
   uint32_t tmem_base;
 };
 
@@ -128,11 +132,13 @@ __device__ __forceinline__ void addmul2(float& x0, float& x1, float y0, float y1
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 }
 
-template <bool COSINE, int P>
+template <bool COSINE, int P, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_constant__ CUtensorMap tm_tokens,
                                                                    const TcArgs a) {
-  constexpr int DIM = Shape<P>::DIM, STAGES = Shape<P>::STAGES, STAGE_BYTES = Shape<P>::STAGE_BYTES,
-                QBYTES = Shape<P>::QBYTES;
+  using SH = Shape<P, G>;
+  constexpr int DIM = SH::DIM, STAGES = SH::STAGES, STAGE_BYTES = SH::STAGE_BYTES, QBYTES = SH::QBYTES,
+                UMMA_N = SH::UMMA_N, ACC = SH::ACC, QPANEL_BYTES = SH::QPANEL_BYTES, NQG = NQ * G;
+  static_assert(STAGES >= 2, "ring too shallow");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_tok = smem;                                  // STAGES x (P x 16 KB)
   uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // P x 8 KB
@@ -186,8 +192,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     tma_prefetch_desc(&tm_tokens);
   }
   if (warp == 9) tmem_alloc<512>(&st->tmem_base);
-  // B operand: rows 0..31 = Qhi, rows 32..63 = Qlo (cosine: rows pre-scaled by 1/||q||), K-major SW128 panels
-  for (int idx = threadIdx.x; idx < NQ * DIM; idx += blockDim.x) {
+  // B operand: rows [0, 32G) = Qhi, rows [32G, 64G) = Qlo (cosine: rows pre-scaled by 1/||q||), K-major SW128 panels
+  for (int idx = threadIdx.x; idx < NQG * DIM; idx += blockDim.x) {
     const int r = idx / DIM, k = idx % DIM;
     float v = (r < (int)a.n_q) ? a.q[(size_t)r * DIM + k] : 0.0f;
     if (COSINE && r < (int)a.n_q) {
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     const float lo = v - hi;
     *reinterpret_cast<float*>(s_q + sw128_offset(r, k, QPANEL_BYTES)) = hi;
-    *reinterpret_cast<float*>(s_q + sw128_offset(32 + r, k, QPANEL_BYTES)) = lo;
+    *reinterpret_cast<float*>(s_q + sw128_offset(NQG + r, k, QPANEL_BYTES)) = lo;
   }
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // MMA); one elected lane issues. A profile of the previous version showed this thread, not the tensor pipe, as the
     // limiter: 686 instructions per tile at IPC 0.2.
     const uint32_t idesc = make_idesc_tf32(TILE_M, UMMA_N);
-    const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQ);
+    const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQG);
     const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(s_q));
     const uint64_t a_desc0 = make_smem_desc_kmajor_sw128(smem_u32(s_tok));
     auto issue_hi = [&](int s, int t) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
@@ -361,10 +367,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     unsigned cur_doc = st->s_doc[warp];
     unsigned long long cur_end = 0;  // end token of cur_doc; 0 forces the first lookup
     bool have_doc = false;
-    float carry[NQ];                 // running max of query token j over the current document (all lanes hold all j)
+    float carry[G][NQ];  // running max of query token 32 g + j over the current document (all lanes hold all of them)
 #pragma unroll
-    for (int j = 0; j < NQ; ++j) carry[j] = -INFINITY;
-    const unsigned n_q = a.n_q;
+    for (int gq = 0; gq < G; ++gq)
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) carry[gq][j] = -INFINITY;
+    const int n_q = (int)a.n_q;
+    float* part = st->part[warp];
     for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
       const int t = i % ACC;
       const unsigned long long c0 = s_lo + (unsigned long long)i * CHUNK;
@@ -374,63 +383,88 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       if (COSINE && active) rt = g < s_hi ? __ldg(a.inv_norms + g) : 0.0f;
       mbar_wait_sleepy(&st->tmem_full[t], (i / ACC) & 1);
       tc_fence_after_sync();
-      uint32_t rh[32], rl[32];
-      if (active) {
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + t * UMMA_N;
-        tmem_ld_32x32b_x32(taddr, rh);
-        tmem_ld_32x32b_x32(taddr + 32, rl);
-        tmem_ld_wait();
+      if (!active) {
+        tc_fence_before_sync();
+        if (lane == 0) mbar_arrive(&st->tmem_empty[t]);
+        continue;
       }
-      tc_fence_before_sync();
-      if (lane == 0) mbar_arrive(&st->tmem_empty[t]);
-      if (!active) continue;
-      if (a.debug_mode == 4) { if (rh[0] == 0x12345u && rl[0] == 0x54321u) a.out[0] = rt; continue; }
-      float sc[NQ];
-#pragma unroll
-      for (int j = 0; j < NQ; j += 2) {
-        float x0 = __uint_as_float(rh[j]), x1 = __uint_as_float(rh[j + 1]);
-        addmul2(x0, x1, __uint_as_float(rl[j]), __uint_as_float(rl[j + 1]), rt, COSINE);
-        sc[j] = x0;
-        sc[j + 1] = x1;
-      }
-      if (COSINE && __any_sync(0xFFFFFFFFu, rt == 0.0f)) {  // rare: a token below the norm guard scores exactly 0.0 against
-        if (rt == 0.0f) {                                    // every query token (x86_64.rs:781-785), also when it holds NaN
-#pragma unroll
-          for (int j = 0; j < NQ; ++j) sc[j] = 0.0f;
-        }
-      }
-      // ---- segments of this chunk: [pos, seg_end) lies inside one document ----
+      const bool rt_zero = COSINE && __any_sync(0xFFFFFFFFu, rt == 0.0f);
       const unsigned long long c1 = c0 + CHUNK < s_hi ? c0 + CHUNK : s_hi;
-      unsigned long long pos = c0;
-      while (pos < c1) {  // warp-uniform
-        if (!have_doc || cur_end <= pos) {  // next non-empty document (empty ones keep the memset 0.0)
-          if (have_doc) ++cur_doc;
-          have_doc = true;
-          cur_end = doc_begin(a, cur_doc + 1);
-          while (cur_end <= pos) {
-            ++cur_doc;
+      // the query groups are reduced one after the other (registers: one group's scores at a time); both walk the same
+      // document segments of the chunk, so the cursor is rewound for the second group
+      const unsigned doc0 = cur_doc;
+      const unsigned long long end0 = cur_end;
+      const bool have0 = have_doc;
+#pragma unroll
+      for (int gq = 0; gq < G; ++gq) {
+        uint32_t rh[32], rl[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + t * UMMA_N + gq * NQ;
+        tmem_ld_32x32b_x32(taddr, rh);            // Xhi.Qhi + Xlo.Qhi
+        tmem_ld_32x32b_x32(taddr + NQ * G, rl);   // Xhi.Qlo
+        tmem_ld_wait();
+        if (gq == G - 1) {  // the accumulator is in registers: the MMA warp may overwrite it
+          tc_fence_before_sync();
+          if (lane == 0) mbar_arrive(&st->tmem_empty[t]);
+        }
+        if (a.debug_mode == 4) { if (rh[0] == 0x12345u && rl[0] == 0x54321u) a.out[0] = rt; continue; }
+        float sc[NQ];
+#pragma unroll
+        for (int j = 0; j < NQ; j += 2) {
+          float x0 = __uint_as_float(rh[j]), x1 = __uint_as_float(rh[j + 1]);
+          addmul2(x0, x1, __uint_as_float(rl[j]), __uint_as_float(rl[j + 1]), rt, COSINE);
+          sc[j] = x0;
+          sc[j + 1] = x1;
+        }
+        if (rt_zero) {          // rare: a token below the norm guard scores exactly 0.0 against every query token
+          if (rt == 0.0f) {     // (x86_64.rs:781-785), also when it holds NaN
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) sc[j] = 0.0f;
+          }
+        }
+        if (G > 1 && gq > 0) {
+          cur_doc = doc0;
+          cur_end = end0;
+          have_doc = have0;
+          __syncwarp();  // part[] of the first group is visible
+        }
+        // ---- segments of this chunk: [pos, seg_end) lies inside one document ----
+        unsigned long long pos = c0;
+        int seg = 0;
+        while (pos < c1) {  // warp-uniform
+          if (!have_doc || cur_end <= pos) {  // next non-empty document (empty ones keep the memset 0.0)
+            if (have_doc) ++cur_doc;
+            have_doc = true;
             cur_end = doc_begin(a, cur_doc + 1);
+            while (cur_end <= pos) {
+              ++cur_doc;
+              cur_end = doc_begin(a, cur_doc + 1);
+            }
           }
-        }
-        const unsigned long long seg_end = cur_end < c1 ? cur_end : c1;
-        if (pos == c0 && seg_end == c0 + CHUNK) {  // the whole chunk lies inside one document
+          const unsigned long long seg_end = cur_end < c1 ? cur_end : c1;
+          if (pos == c0 && seg_end == c0 + CHUNK) {  // the whole chunk lies inside one document
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) carry[j] = fmaxf(carry[j], redux_max(sc[j]));
-        } else {
-          const bool in = g >= pos && g < seg_end;
+            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], redux_max(sc[j]));
+          } else {
+            const bool in = g >= pos && g < seg_end;
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) carry[j] = fmaxf(carry[j], redux_max(in ? sc[j] : -INFINITY));
-        }
-        if (seg_end == cur_end) {  // the document ends here: sum of the maxima in query order from 0.0 (x86_64.rs:139)
-          float total = 0.0f;
-#pragma unroll
-          for (int j = 0; j < NQ; ++j) {
-            if (j < (int)n_q) total += carry[j];
-            carry[j] = -INFINITY;
+            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], redux_max(in ? sc[j] : -INFINITY));
           }
-          if (lane == 0) a.out[cur_doc] = a.accumulate ? a.out[cur_doc] + total : total;
+          if (seg_end == cur_end) {  // the document ends here: sum of the maxima in query order from 0.0 (x86_64.rs:139)
+            float total = (G > 1 && gq > 0) ? part[seg] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+              if (gq * NQ + j < n_q) total += carry[gq][j];
+              carry[gq][j] = -INFINITY;
+            }
+            if (gq == G - 1) {
+              if (lane == 0) a.out[cur_doc] = a.accumulate ? a.out[cur_doc] + total : total;
+            } else if (lane == 0) {
+              part[seg] = total;
+            }
+            ++seg;
+          }
+          pos = seg_end;
         }
-        pos = seg_end;
       }
     }
   }
@@ -471,34 +505,36 @@ cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens,
   return cudaGetLastError();
 }
 
-// dim 32 / 64 / 96 / 128; more than 32 query tokens: one corpus pass per group of 32 (the sum over query tokens is
-// additive across groups)
+// dim 32 / 64 / 96 / 128; up to 64 query tokens per corpus pass, more in several passes (the sum over query tokens is
+// additive across passes)
 bool maxsim_tc_supported(const TokView& v, size_t n_q) {
   return v.dim >= 32 && v.dim <= 128 && v.dim % 32 == 0 && n_q >= 1 && n_q <= 8 * NQ && v.total_tokens > 0 &&
          v.tmap_valid && v.inv_norms != nullptr && v.total_tokens < 0x7FFFFF00ull;
 }
 
 namespace {
-template <bool COSINE, int P>
+template <bool COSINE, int P, int G>
 cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
-  constexpr size_t smem = (size_t)Shape<P>::STAGES * Shape<P>::STAGE_BYTES + Shape<P>::QBYTES + sizeof(SharedTail);
+  using SH = Shape<P, G>;
+  constexpr size_t smem = (size_t)SH::STAGES * SH::STAGE_BYTES + SH::QBYTES + sizeof(SharedTail);
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  maxsim_tc_kernel<COSINE, P><<<grid, TC_THREADS, smem, s>>>(tm, a);
+  maxsim_tc_kernel<COSINE, P, G><<<grid, TC_THREADS, smem, s>>>(tm, a);
   return cudaGetLastError();
 }
-template <bool COSINE>
+template <bool COSINE, int G>
 cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
   switch (dim) {
-    case 32: return launch_shape<COSINE, 1>(tm, a, grid, s);
-    case 64: return launch_shape<COSINE, 2>(tm, a, grid, s);
-    case 96: return launch_shape<COSINE, 3>(tm, a, grid, s);
-    case 128: return launch_shape<COSINE, 4>(tm, a, grid, s);
+    case 32: return launch_shape<COSINE, 1, G>(tm, a, grid, s);
+    case 64: return launch_shape<COSINE, 2, G>(tm, a, grid, s);
+    case 96: return launch_shape<COSINE, 3, G>(tm, a, grid, s);
+    case 128: return launch_shape<COSINE, 4, G>(tm, a, grid, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -523,13 +559,19 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   if (grid > tiles) grid = (unsigned)tiles;
   if (grid > v.n_docs) grid = (unsigned)v.n_docs;
   if (grid == 0) grid = 1;
-  for (size_t q0 = 0; q0 < n_q; q0 += NQ) {
-    a.n_q = (unsigned)(n_q - q0 < NQ ? n_q - q0 : NQ);
+  // one corpus pass per 64 query tokens (two column groups per accumulator), a last pass of <= 32 with one group
+  for (size_t q0 = 0; q0 < n_q;) {
+    const size_t rem = n_q - q0;
+    const bool two = rem > NQ;
+    const size_t take = two ? (rem < 2 * NQ ? rem : 2 * NQ) : rem;
+    a.n_q = (unsigned)take;
     a.q = dev_q + q0 * v.dim;
     a.accumulate = q0 > 0;
-    e = cosine ? launch_dim<true>(v.dim, v.tmap, a, grid, s) : launch_dim<false>(v.dim, v.tmap, a, grid, s);
+    if (two) e = cosine ? launch_dim<true, 2>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 2>(v.dim, v.tmap, a, grid, s);
+    else e = cosine ? launch_dim<true, 1>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 1>(v.dim, v.tmap, a, grid, s);
     if (e != cudaSuccess) return e;
     ++*launches;
+    q0 += take;
   }
   return cudaSuccess;
 }

@@ -586,7 +586,7 @@ def test_maxsim_colbert_shape_generated(ib, oracle):
 
 
 @pytest.mark.parametrize("shape", ["tiny_docs", "one_huge", "mixed", "few_docs", "single_token"])
-@pytest.mark.parametrize("nq", [32, 5])
+@pytest.mark.parametrize("nq", [32, 5, 64, 47])
 def test_maxsim_tc_stream_edges(ib, oracle, shape, nq):
     """The tcgen05 path (dim 128, <= 32 query tokens) cuts every CTA's range into four document-aligned streams and
     handles document boundaries inside a 32-token chunk as masked segments: documents shorter than a chunk (many per
