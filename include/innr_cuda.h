@@ -84,6 +84,11 @@ int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64
  * (ld >= n, ld % 4 == 0, base 16-byte aligned): dev_pdx[dd*ld + i]. */
 int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t ld, uint64_t index_base,
                                innr_cuda_corpus** out);
+/* Matryoshka prefix scans (src/dense.rs:436-462 are the pairwise matryoshka_dot / matryoshka_cosine): a zero-copy view of
+ * the first min(prefix_dim, d) dimensions of every vector -- in the PDX layout those are simply the first rows. Every
+ * f32 entry works on the view and matches the reference's batch function on the truncated vectors. The view does not
+ * own device memory: free it before the corpus it was taken from. */
+int innr_cuda_prefix_view(const innr_cuda_corpus* c, size_t prefix_dim, innr_cuda_corpus** out);
 /* Synthetic corpus generated on the device:
  * generator 0 = G-hash: row r, dim j -> splitmix64(salt + r*d + j) (uniform [-1,1), 24-bit);
  * generator 1 = G-ref : row r = generate_embedding(d, seed = salt + r) (examples/batch_demo.rs:233-242).

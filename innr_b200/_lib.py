@@ -43,6 +43,7 @@ SIGNATURES = {
     "innr_cuda_upload_f32_pdx": [f32p, sz, sz, u64, handle_p],
     "innr_cuda_upload_f32_rows": [f32p, sz, sz, u64, handle_p],
     "innr_cuda_wrap_f32_pdx_dev": [vp, sz, sz, sz, u64, handle_p],
+    "innr_cuda_prefix_view": [vp, sz, handle_p],
     "innr_cuda_generate_f32_pdx": [ci, u64, u64, sz, sz, u64, handle_p],
     "innr_cuda_free": [vp],
     "innr_cuda_corpus_info": [vp, C.POINTER(ci), szp, szp, szp, u64p, szp],

@@ -84,6 +84,14 @@ class DeviceBatch:
         b._keepalive = keepalive
         return b
 
+    def prefix(self, prefix_dim: int) -> "DeviceBatch":
+        """Zero-copy view of the first `prefix_dim` dimensions (Matryoshka prefix, src/dense.rs:436-462)."""
+        h = C.c_void_p()
+        L.call("innr_cuda_prefix_view", self.h, prefix_dim, C.byref(h))
+        v = DeviceBatch(_Handle(h), self.num_vectors, min(prefix_dim, self.dimension), self.index_base)
+        v._keepalive = self  # the view does not own the device memory
+        return v
+
     def extract_vector(self, i: int) -> np.ndarray:
         out = np.zeros(self.dimension, np.float32)
         L.call("innr_cuda_extract_vector", self.h, i, _ptr(out, L.f32p))

@@ -394,6 +394,27 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   return INNR_OK;
 }
 
+// Matryoshka prefix (src/dense.rs:436-462 are the pairwise functions): in the PDX layout the first `prefix_dim`
+// dimensions of every vector ARE the first prefix_dim rows, so a truncated corpus is a zero-copy view. Every f32 entry
+// works on the view and equals the reference's batch function on VerticalBatch::from_rows of the truncated vectors.
+// The view does not own the memory: free it before its parent.
+int innr_cuda_prefix_view(const innr_cuda_corpus* c, size_t prefix_dim, innr_cuda_corpus** out) {
+  if (!out || !c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  const size_t d = prefix_dim < c->d ? prefix_dim : c->d;  // prefix_len.min(a.len())
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  int rc = new_corpus(0, c->device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* v = *out;
+  v->owns = false;
+  v->dev = c->dev;
+  v->n = c->n;
+  v->d = d;
+  v->ld = c->ld;
+  v->index_base = c->index_base;
+  v->bytes = c->ld * d * sizeof(float);
+  return INNR_OK;
+}
+
 int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
                                uint64_t index_base, innr_cuda_corpus** out) {
   if (!out || (generator != 0 && generator != 1)) return fail(INNR_EINVAL, "bad argument");

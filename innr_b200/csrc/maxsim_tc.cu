@@ -10,7 +10,8 @@
 // ~2^-21 relative to sum|q.x| (the f32 tolerance of the north_star, 1e-5, is 2^-16.6). The max over a document's
 // tokens and the sum over query tokens are fused in the TMEM->register epilogue; one f32 per document leaves the SM.
 //
-// Shape of the machine (one persistent CTA per SM, 320 threads, ~225 KB shared memory, 448 TMEM columns):
+// Shape of the machine (one persistent CTA per SM, 320 threads, ~225 KB shared memory, all 512 TMEM columns: accumulator
+// stages in [0, 256), two Xlo buffers in [256, 512)):
 //   The CTA's contiguous document range is cut into FOUR document-aligned token streams. A 128-row tile is made of
 //   the next 32 tokens of each stream (rows 32w..32w+31 = stream w), so TMEM lane quadrant w -- the only lanes warp w
 //   of a warpgroup may read -- always holds consecutive tokens of one stream and every epilogue warp carries its

@@ -374,6 +374,27 @@ def test_derived_encodings_and_rerank(ib, oracle, n, d):
             assert sorted(int(i) for i in got.indices) == sorted(want_idx)
 
 
+def test_matryoshka_prefix_view(ib, oracle):
+    """A prefix view (first D' rows of the PDX corpus, zero-copy) answers exactly like the reference's batch functions
+    on the truncated vectors -- single queries (scan) and query batches (tensor-core filter on the view's own operands)."""
+    n, d = 120_000, 96
+    rows = rand_rows(n, d, 21)
+    full = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    qs = rand_rows(12, d, 22)
+    for dp in (32, 80, 96, 200):
+        view = full.prefix(dp)
+        de = min(dp, d)
+        ob = oracle.VerticalBatch.from_flat(np.ascontiguousarray(rows[:, :de]).reshape(-1), n, de)
+        for metric in ("cosine", "dot", "l2"):
+            idx, sc = ib.batch_knn_many(metric, qs[:1, :de], view, 10)
+            widx, wsc = oracle.batch_knn_many(metric, np.ascontiguousarray(qs[:1, :de]), ob, 10)
+            assert np.array_equal(bits(sc), bits(wsc)) and (metric == "l2" or np.array_equal(idx, widx)), (dp, metric)
+            idx, sc = ib.batch_knn_many(metric, np.ascontiguousarray(qs[:, :de]), view, 10)
+            widx, wsc = oracle.batch_knn_many(metric, np.ascontiguousarray(qs[:, :de]), ob, 10, n_threads=8)
+            assert np.array_equal(bits(sc), bits(wsc)) and (metric == "l2" or np.array_equal(idx, widx)), (dp, metric)
+        assert np.array_equal(bits(ib.batch_dot(qs[0, :de], view)), bits(oracle.batch_dot(qs[0, :de], ob)))
+
+
 # ------------------------------------------------------------------------------------------------ k > 128
 @pytest.mark.parametrize("k", [129, 300, 1000, 5000])
 def test_big_k_all_paths_exact(ib, oracle, k):
