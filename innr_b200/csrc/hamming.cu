@@ -48,11 +48,35 @@ __device__ __forceinline__ unsigned code_distance(const uint4* __restrict__ p, s
   return dist;
 }
 
+// the same code against QB queries: the chunks are loaded once (CHUNKS_CT > 0: all in registers)
+template <int CHUNKS_CT, int QB>
+__device__ __forceinline__ void code_distance_multi(const uint4* __restrict__ p, size_t ld, unsigned chunks,
+                                                    const uint4* __restrict__ sq, unsigned (&dist)[QB]) {
+#pragma unroll
+  for (int q = 0; q < QB; ++q) dist[q] = 0;
+  if (CHUNKS_CT > 0) {
+    uint4 v[CHUNKS_CT > 0 ? CHUNKS_CT : 1];
+#pragma unroll
+    for (int c = 0; c < CHUNKS_CT; ++c) v[c] = ldg_stream_u4(p + (size_t)c * ld);
+#pragma unroll
+    for (int q = 0; q < QB; ++q)
+#pragma unroll
+      for (int c = 0; c < CHUNKS_CT; ++c) dist[q] += popc_u4(v[c], sq[q * CHUNKS_CT + c]);
+  } else {
+    for (unsigned c = 0; c < chunks; ++c) {
+      const uint4 v = ldg_stream_u4(p + (size_t)c * ld);
+#pragma unroll
+      for (int q = 0; q < QB; ++q) dist[q] += popc_u4(v, sq[q * chunks + c]);
+    }
+  }
+}
+
 struct HamArgs {
   const uint4* data;
   unsigned long long ld;
   unsigned n, chunks, n_tiles, index_base;
-  const uint64_t* query_words;  // device: 2*chunks words (zero padded)
+  const uint64_t* query_words;  // device: 2*chunks words per query (zero padded)
+  int nq_valid;                 // multi-query kernel: queries in this launch (<= QB)
   int k;
   uint64_t* partials;
   uint64_t* out_keys;
@@ -87,6 +111,45 @@ __global__ void __launch_bounds__(HAM_THREADS) hamming_kernel(const HamArgs a) {
     else if (valid) a.dist_out[i] = dist;
   }
   if (TOPK) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
+}
+
+// QB queries share one pass over the codes (top-k only): the scan is HBM-bound for one query with the ALU pipe a third
+// busy, so up to ~3 queries ride along for free and a batch of 4 costs about 1.5 passes
+template <int CHUNKS_CT, int R, int QB>
+__global__ void __launch_bounds__(HAM_THREADS) hamming_multi_kernel(const HamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sq = reinterpret_cast<uint4*>(smem_raw);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(sq + (size_t)QB * a.chunks);
+  const int lane = threadIdx.x & 31;
+  for (unsigned t = threadIdx.x; t < QB * a.chunks; t += blockDim.x) {
+    const unsigned q = t / a.chunks, c = t % a.chunks;
+    uint64_t w0 = 0, w1 = 0;
+    if ((int)q < a.nq_valid) {
+      w0 = a.query_words[(size_t)q * 2 * a.chunks + 2 * c];
+      w1 = a.query_words[(size_t)q * 2 * a.chunks + 2 * c + 1];
+    }
+    sq[t] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+  }
+  __syncthreads();
+  WarpList<R> lists[QB];
+  uint64_t thrs[QB];
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    lists[q].init();
+    thrs[q] = KEY_SENTINEL;
+  }
+  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const unsigned i = tile * HAM_THREADS + threadIdx.x;
+    const bool valid = i < a.n;
+    unsigned dist[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) dist[q] = 0;
+    if (valid) code_distance_multi<CHUNKS_CT, QB>(a.data + i, a.ld, a.chunks, sq, dist);
+#pragma unroll
+    for (int q = 0; q < QB; ++q)
+      if (q < a.nq_valid) lists[q].offer(make_key_u32(dist[q], a.index_base + i), valid, thrs[q], a.k, lane);
+  }
+  block_finish<R, QB>(lists, a.nq_valid, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
 // row-major words [n][words] -> chunk-major uint4, masking padding bits (PackedBinary::new)
@@ -302,10 +365,48 @@ cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_quer
   return cudaGetLastError();
 }
 
+namespace {
+// queries per pass: the 128-slot lists of k > 32 cost 8 registers per query and lane, and registers decide how many
+// bytes the CTAs of an SM keep in flight -- 4 queries per pass with 32-slot lists, 2 with 128-slot lists
+template <int R> constexpr int ham_qb() { return R == 1 ? 4 : 2; }
+template <int CHUNKS_CT, int R>
+cudaError_t launch_ham_multi(const HamArgs& a, size_t smem, int num_sms, cudaStream_t s) {
+  auto kern = hamming_multi_kernel<CHUNKS_CT, R, ham_qb<R>()>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HAM_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  kern<<<balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms), HAM_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
                                 uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   if (k > 128) return cudaErrorInvalidValue;
-  for (size_t q = 0; q < nq; ++q) {
+  size_t q0 = 0;
+  // batches: groups of 4 queries share one pass over the codes
+  const size_t qb = k <= 32 ? ham_qb<1>() : ham_qb<4>();
+  const size_t multi_smem = qb * v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
+  while (nq - q0 >= 2 && multi_smem <= 48 * 1024) {
+    const size_t take = nq - q0 < qb ? nq - q0 : qb;
+    HamArgs a = make_args(v, dev_query_words + q0 * 2 * v.chunks);
+    a.nq_valid = (int)take;
+    a.k = (int)k;
+    a.partials = ws.partials;
+    a.group_partials = ws.group_partials;
+    a.tickets = ws.tickets;
+    a.out_keys = dev_keys + q0 * k;
+    cudaError_t e;
+    if (v.chunks == 8)
+      e = (k <= 32) ? launch_ham_multi<8, 1>(a, multi_smem, ws.num_sms, s) : launch_ham_multi<8, 4>(a, multi_smem, ws.num_sms, s);
+    else
+      e = (k <= 32) ? launch_ham_multi<0, 1>(a, multi_smem, ws.num_sms, s) : launch_ham_multi<0, 4>(a, multi_smem, ws.num_sms, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+    q0 += take;
+  }
+  for (size_t q = q0; q < nq; ++q) {
     HamArgs a = make_args(v, dev_query_words + q * 2 * v.chunks);
     a.k = (int)k;
     a.partials = ws.partials;

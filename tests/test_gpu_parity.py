@@ -476,6 +476,26 @@ def test_l2_pruning_bit_exact(ib, oracle, n, d):
         assert same_scores([s for _, s in got], [s for _, s in want]), thr
 
 
+@pytest.mark.parametrize("dim,nq", [(1024, 2), (1024, 4), (1024, 9), (200, 5), (64, 7)])
+def test_hamming_query_batches_share_a_pass(ib, oracle, dim, nq):
+    """Batches of Hamming queries run four per pass over the codes; each must equal the single-query result
+    (distance, then lower index: stable sort_by_key), with the heavy ties of near-uniform codes."""
+    n = 30_011
+    rng = np.random.default_rng(dim + nq)
+    words = (dim + 63) // 64
+    codes = rng.integers(0, 2**63, size=(n, words), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, words), dtype=np.uint64)
+    if dim % 64:
+        codes[:, -1] &= np.uint64((1 << (dim % 64)) - 1)
+    qs = codes[rng.integers(0, n, size=nq)] ^ np.uint64(0x5)
+    if dim % 64:
+        qs[:, -1] &= np.uint64((1 << (dim % 64)) - 1)
+    corpus = ib.BinaryCorpus.from_words(codes, n, dim)
+    for k in (1, 10, 100):
+        gi, gd = ib.hamming_topk_many(qs, corpus, k)
+        wi, wd = oracle.hamming_topk_many(qs, codes, k, n_threads=4)
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd), (dim, nq, k)
+
+
 # ------------------------------------------------------------------------------------------------ u8
 @pytest.mark.parametrize("d", [1, 8, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 100, 128, 384, 777])
 def test_u8_bit_exact(ib, oracle, d):
