@@ -216,6 +216,13 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
 /* G-hash token rows (salt + row*dim + j), every doc `tokens_per_doc` tokens; docs [first_doc, first_doc+n_docs) */
 int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, size_t tokens_per_doc,
                               size_t dim, uint64_t index_base, innr_cuda_corpus** out);
+/* A batch of queries against the document set (the caller loop of examples/maxsim_colbert.rs:171-174, for several
+ * queries): q_tokens is n_queries x n_q x q_dim, out_scores n_queries x n_docs (query-major). Same per-query results
+ * as innr_cuda_maxsim; on the tcgen05 path two queries of <= 32 tokens share every pass over the corpus. */
+int innr_cuda_maxsim_batch(const innr_cuda_corpus* c, const float* q_tokens, size_t n_queries, size_t n_q, size_t q_dim,
+                           int cosine_flag, float* out_scores_host);
+int innr_cuda_maxsim_batch_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_queries, size_t n_q,
+                               int cosine_flag, float* dev_scores, void* stream);
 /* maxsim (cosine_flag 0) / maxsim_cosine (1) of the query token set against every doc:
  * out_scores_host n_docs floats. Empty query or empty doc -> 0.0 (src/maxsim.rs:97-99). q_dim must equal dim. */
 int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_q, size_t q_dim,

@@ -14,7 +14,7 @@ from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, ba
 from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, binary_hamming, binary_jaccard,  # noqa: F401
                      binary_jaccard_all, encode_binary, hamming_all,
                      hamming_topk, hamming_topk_many)
-from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_cosine  # noqa: F401
+from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_corpus_batch, maxsim_cosine  # noqa: F401
 from .scalar import (QuantizationParams, QuantizedU8, U8Corpus, asymmetric_dot_u8, asymmetric_dot_u8_all,  # noqa: F401
                      batch_knn_u8, batch_knn_u8_many, mixed_dot_u8_all, mixed_dot_u8_f32, quantize_u8)
 from .topk import topk_from_distances  # noqa: F401

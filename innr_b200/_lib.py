@@ -79,6 +79,8 @@ SIGNATURES = {
     "innr_cuda_upload_tokens": [f32p, u64p, sz, sz, u64, handle_p],
     "innr_cuda_generate_tokens": [u64, u64, sz, sz, sz, u64, handle_p],
     "innr_cuda_maxsim": [vp, f32p, sz, sz, ci, f32p],
+    "innr_cuda_maxsim_batch": [vp, f32p, sz, sz, sz, ci, f32p],
+    "innr_cuda_maxsim_batch_dev": [vp, vp, sz, sz, ci, vp, vp],
     "innr_cuda_maxsim_dev": [vp, vp, sz, ci, vp, vp],
 }
 STRING_GETTERS = ("innr_cuda_last_error", "innr_cuda_backend_name")

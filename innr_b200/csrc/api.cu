@@ -1401,6 +1401,61 @@ int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_
   return INNR_OK;
 }
 
+// A batch of queries against the document set (the caller loop of examples/maxsim_colbert.rs:171-174 over several
+// queries): q_tokens is n_queries x n_q x dim, scores n_queries x n_docs. On the tcgen05 path two queries of <= 32 tokens
+// share every corpus pass; other shapes run query by query.
+static int maxsim_batch_common(const innr_cuda_corpus* c, DeviceCtx* ctx, const float* dev_q, size_t n_queries, size_t n_q,
+                               int cosine, float* dev_scores, cudaStream_t s) {
+  TokView tv = tok_view(c);
+  if (n_q >= 1 && n_q <= 32 && c->total_tokens && c->d && g_opt.maxsim_tc && maxsim_tc_supported(tv, n_q)) {
+    cudaError_t e = launch_maxsim_tc_batch(tv, dev_q, n_queries, n_q, cosine, dev_scores, ctx->ws.num_sms, s, &g_launches);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_maxsim_tc_batch");
+    return INNR_OK;
+  }
+  for (size_t i = 0; i < n_queries; ++i) {
+    int rc = maxsim_common(c, ctx, dev_q + i * n_q * c->d, n_q, cosine, dev_scores + i * c->n, s);
+    if (rc) return rc;
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_maxsim_batch(const innr_cuda_corpus* c, const float* q_tokens, size_t n_queries, size_t n_q, size_t q_dim,
+                           int cosine_flag, float* out_scores_host) {
+  if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
+  if (n_q && c->total_tokens && q_dim != c->d) return fail(INNR_EINVAL, "dimension mismatch (doc)");  // src/maxsim.rs:107-110
+  if (c->n == 0 || n_queries == 0) return INNR_OK;
+  if (!out_scores_host || (n_q * q_dim && !q_tokens)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  const size_t qfloats = n_queries * n_q * c->d;
+  CU(ctx->d_query.reserve((qfloats + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(n_queries * c->n * sizeof(float)));
+  if (qfloats && c->total_tokens)
+    CU(cudaMemcpyAsync(ctx->d_query.p, q_tokens, qfloats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  rc = maxsim_batch_common(c, ctx, (const float*)ctx->d_query.p, n_queries, n_q, cosine_flag, (float*)ctx->d_scores.p,
+                           ctx->stream);
+  if (rc) return rc;
+  tm.stop();
+  CU(cudaMemcpyAsync(out_scores_host, ctx->d_scores.p, n_queries * c->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+int innr_cuda_maxsim_batch_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_queries, size_t n_q,
+                               int cosine_flag, float* dev_scores, void* stream) {
+  if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
+  if (c->n == 0 || n_queries == 0) return INNR_OK;
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  return maxsim_batch_common(c, ctx, dev_q_tokens, n_queries, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
+}
+
 int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_q, int cosine_flag,
                          float* dev_scores, void* stream) {
   if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");

@@ -167,6 +167,9 @@ struct TokView {
 bool maxsim_tc_supported(const TokView& v, size_t n_q);
 cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, int cosine, float* dev_scores,
                              int num_sms, cudaStream_t s, LaunchCounter* launches);
+// batch of n_queries queries of n_q <= 32 tokens each; scores n_queries x n_docs; two queries per corpus pass
+cudaError_t launch_maxsim_tc_batch(const TokView& v, const float* dev_q, size_t n_queries, size_t n_q, int cosine,
+                                   float* dev_scores, int num_sms, cudaStream_t s, LaunchCounter* launches);
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim);
 cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens, size_t dim, float* dev_inv,
                                    cudaStream_t s, LaunchCounter* launches);

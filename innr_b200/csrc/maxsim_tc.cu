@@ -79,6 +79,12 @@ struct TcArgs {
   int debug_mode;  // 0 normal; 1 = TMA streaming only; 2 = hi pass only; 4 = no epilogue math (profiling aids)
   int accumulate;  // 0: out[doc] = sum; 1: out[doc] += sum (second and later groups of 32 query tokens)
   float* out;
+  // G = 2 only: the two column groups are two DIFFERENT queries of <= 32 tokens each (batch of queries sharing one corpus
+  // pass): group 1 reads q_b / n_q_b and writes out_b; sums are kept apart
+  int split;
+  const float* q_b;
+  unsigned n_q_b;
+  float* out_b;
 };
 
 __device__ __forceinline__ unsigned long long doc_begin(const TcArgs& a, unsigned d) {
@@ -196,10 +202,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
   // B operand: rows [0, 32G) = Qhi, rows [32G, 64G) = Qlo (cosine: rows pre-scaled by 1/||q||), K-major SW128 panels
   for (int idx = threadIdx.x; idx < NQG * DIM; idx += blockDim.x) {
     const int r = idx / DIM, k = idx % DIM;
-    float v = (r < (int)a.n_q) ? a.q[(size_t)r * DIM + k] : 0.0f;
-    if (COSINE && r < (int)a.n_q) {
+    const bool second = G > 1 && a.split && r >= NQ;
+    const float* qsrc = second ? a.q_b + (size_t)(r - NQ) * DIM : a.q + (size_t)r * DIM;
+    const bool qvalid = (G > 1 && a.split) ? (second ? r - NQ < (int)a.n_q_b : r < (int)a.n_q) : r < (int)a.n_q;
+    float v = qvalid ? qsrc[k] : 0.0f;
+    if (COSINE && qvalid) {
       float aa = 0.0f;
-      const float* qp = a.q + (size_t)r * DIM;
+      const float* qp = qsrc;
       for (int kk = 0; kk < DIM; ++kk) aa = fmaf(qp[kk], qp[kk], aa);
       v = aa > EPS_SQ ? v / sqrtf(aa) : 0.0f;  // query with ~zero norm -> cosine 0 for every token (x86_64.rs:781-785)
     }
@@ -451,13 +460,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
             for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], redux_max(in ? sc[j] : -INFINITY));
           }
           if (seg_end == cur_end) {  // the document ends here: sum of the maxima in query order from 0.0 (x86_64.rs:139)
-            float total = (G > 1 && gq > 0) ? part[seg] : 0.0f;
+            const bool split = G > 1 && a.split;
+            const int lim = split ? (gq ? (int)a.n_q_b : n_q) : n_q - gq * NQ;  // query tokens of this group
+            float total = (G > 1 && gq > 0 && !split) ? part[seg] : 0.0f;
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
-              if (gq * NQ + j < n_q) total += carry[gq][j];
+              if (j < lim) total += carry[gq][j];
               carry[gq][j] = -INFINITY;
             }
-            if (gq == G - 1) {
+            if (split) {
+              if (lane == 0) (gq ? a.out_b : a.out)[cur_doc] = total;
+            } else if (gq == G - 1) {
               if (lane == 0) a.out[cur_doc] = a.accumulate ? a.out[cur_doc] + total : total;
             } else if (lane == 0) {
               part[seg] = total;
@@ -573,6 +586,40 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
     if (e != cudaSuccess) return e;
     ++*launches;
     q0 += take;
+  }
+  return cudaSuccess;
+}
+
+// A batch of queries (each <= 32 tokens) against the document set: two queries share every corpus pass (their tokens are
+// the two column groups of one accumulator); dev_scores is n_queries x n_docs.
+cudaError_t launch_maxsim_tc_batch(const TokView& v, const float* dev_q, size_t n_queries, size_t n_q, int cosine,
+                                   float* dev_scores, int num_sms, cudaStream_t s, LaunchCounter* launches) {
+  cudaError_t e = cudaMemsetAsync(dev_scores, 0, n_queries * v.n_docs * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  TcArgs a{};
+  a.doc_offsets = v.doc_offsets;
+  a.inv_norms = v.inv_norms;
+  a.uniform_tokens = v.uniform_tokens;
+  a.total_tokens = v.total_tokens;
+  a.n_docs = (unsigned)v.n_docs;
+  unsigned grid = (unsigned)num_sms;
+  const unsigned long long tiles = (v.total_tokens + TILE_M - 1) / TILE_M;
+  if (grid > tiles) grid = (unsigned)tiles;
+  if (grid > v.n_docs) grid = (unsigned)v.n_docs;
+  if (grid == 0) grid = 1;
+  for (size_t i = 0; i < n_queries; i += 2) {
+    const bool pair = i + 1 < n_queries;
+    a.q = dev_q + i * n_q * v.dim;
+    a.n_q = (unsigned)n_q;
+    a.out = dev_scores + i * v.n_docs;
+    a.split = pair ? 1 : 0;
+    a.q_b = pair ? dev_q + (i + 1) * n_q * v.dim : nullptr;
+    a.n_q_b = (unsigned)n_q;
+    a.out_b = pair ? dev_scores + (i + 1) * v.n_docs : nullptr;
+    if (pair) e = cosine ? launch_dim<true, 2>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 2>(v.dim, v.tmap, a, grid, s);
+    else e = cosine ? launch_dim<true, 1>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 1>(v.dim, v.tmap, a, grid, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
   }
   return cudaSuccess;
 }

@@ -58,6 +58,16 @@ def maxsim_corpus(query_tokens, corpus: TokenCorpus, cosine: bool = False) -> np
     return out
 
 
+def maxsim_corpus_batch(queries, corpus: TokenCorpus, cosine: bool = False) -> np.ndarray:
+    """`queries`: (n_queries, n_q, dim). Returns (n_queries, n_docs); row i equals maxsim_corpus(queries[i], ...)."""
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    assert q.ndim == 3, "queries must be (n_queries, n_q, dim)"
+    out = np.zeros((q.shape[0], corpus.num_docs), np.float32)
+    L.call("innr_cuda_maxsim_batch", corpus.h, q.ctypes.data_as(L.f32p), q.shape[0], q.shape[1], q.shape[2],
+           1 if cosine else 0, out.ctypes.data_as(L.f32p))
+    return out
+
+
 def _pair(query_tokens, doc_tokens, cosine: bool) -> float:
     q, d = _tokens(query_tokens, "query"), _tokens(doc_tokens, "doc")
     if q.shape[0] == 0 or d.shape[0] == 0:

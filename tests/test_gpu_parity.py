@@ -678,6 +678,28 @@ def test_maxsim_tc_dims_and_query_groups(ib, oracle, dim, nq):
         assert np.all(got[lens == 0] == 0.0)
 
 
+@pytest.mark.parametrize("n_queries,nq,dim", [(2, 32, 128), (5, 17, 128), (3, 32, 64), (1, 8, 96), (4, 40, 128), (3, 6, 48)])
+def test_maxsim_query_batches(ib, oracle, n_queries, nq, dim):
+    """Batches of queries: on the tcgen05 path two queries of <= 32 tokens share each corpus pass (their tokens are the two
+    column groups of one accumulator, sums kept apart); every row must equal the single-query result."""
+    rng = np.random.default_rng(n_queries * 1000 + nq + dim)
+    lens = np.concatenate([rng.integers(0, 120, size=150), [0, 900, 1]])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    toks = rng.standard_normal((int(off[-1]), dim)).astype(np.float32)
+    qs = rng.standard_normal((n_queries, nq, dim)).astype(np.float32)
+    corpus = ib.TokenCorpus.from_tokens(toks, off, dim)
+    for cos in (False, True):
+        got = ib.maxsim_corpus_batch(qs, corpus, cosine=cos)
+        for i in range(n_queries):
+            single = ib.maxsim_corpus(qs[i], corpus, cosine=cos)
+            want = oracle.maxsim_corpus(qs[i], toks, off, cosine_flag=cos)
+            scale = _maxsim_scale(qs[i], toks, off) if not cos else np.full(len(lens), float(nq))
+            assert np.all(np.abs(got[i].astype(np.float64) - want) <= 1e-5 * scale + 1e-6), (i, cos)
+            if nq <= 32 and dim % 32 == 0:
+                assert np.array_equal(bits(got[i]), bits(single)), (i, cos)   # same arithmetic, same bits
+            assert np.all(got[i][lens == 0] == 0.0)
+
+
 def test_maxsim_tc_nan_and_zero_tokens(ib, oracle):
     """NaN scores never replace the running max (`>` compare, x86_64.rs:135); a document whose every score is NaN sums
     -inf; zero-norm tokens and zero-norm query tokens give cosine 0.0 (x86_64.rs:781-785)."""
