@@ -814,6 +814,67 @@ def test_full_size_c2a_properties(ib, oracle):
     assert np.array_equal(merged, sharded.encode_keys(sc[0], idx[0], True))
 
 
+def test_full_size_c2b_filter_properties(ib, oracle):
+    """BASELINE C2b at full size (10M x 768, 1024 queries through the tcgen05 filter + exact rescoring): every list is
+    sorted by (score desc, index asc); sampled entries are re-derived bit-exactly on the CPU; and for a handful of
+    queries the whole list equals the bit-exact single-query scan (scores AND indices)."""
+    from innr_b200 import synth, sharded
+    if _free_gb() < 70:
+        pytest.skip("needs ~50 GB of free HBM")
+    n, d, k, nq = 10_000_000, 768, 10, 1024
+    whole = ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, 0, n, d)
+    qs = oracle.ghash_f32(synth.SALT_QUERY, 0, nq * d).reshape(nq, d)
+    rng = np.random.default_rng(3)
+    for metric, desc in (("cosine", True), ("l2", False)):
+        idx, sc = ib.batch_knn_many(metric, qs, whole, k)
+        st = ib.knn_tc_last_stats()
+        assert st["passes"] >= 2 and st["exact_scan_queries"] == 0, st
+        assert idx.shape == (nq, k)
+        for j in range(nq):
+            keys = sharded.encode_keys(sc[j], idx[j], desc)
+            assert np.all(keys[:-1] < keys[1:]), (metric, j)
+        for j in rng.integers(0, nq, size=12):
+            r = int(rng.integers(0, k))
+            row = oracle.ghash_f32(synth.SALT_CORPUS, int(idx[j, r]) * d, d)
+            one = oracle.VerticalBatch.from_flat(row, 1, d)
+            want = (oracle.batch_cosine(qs[j], one, oracle.batch_norms(one)) if metric == "cosine"
+                    else oracle.batch_l2_squared(qs[j], one))
+            assert np.float32(sc[j, r]).tobytes() == np.float32(want[0]).tobytes(), (metric, j, r)
+        ib.set_option("knn_tc", 0)
+        try:
+            for j in rng.integers(0, nq, size=4):
+                si, ss = ib.batch_knn_many(metric, qs[j], whole, k)      # the bit-exact scan
+                assert np.array_equal(si[0], idx[j]) and np.array_equal(bits(ss[0]), bits(sc[j])), (metric, j)
+        finally:
+            ib.set_option("knn_tc", 1)
+
+
+def test_full_size_c3_maxsim_properties(ib, oracle):
+    """BASELINE C3 at full size (1M docs x 180 tokens x 128d, 32 query tokens, generated on the device): a random sample
+    of documents is re-scored by the oracle from the stateless generator (<= 1e-5 relative, the north-star tolerance),
+    for maxsim_cosine and maxsim; two queries scored as a batch equal the single-query calls bit for bit."""
+    from innr_b200 import synth
+    if _free_gb() < 110:
+        pytest.skip("needs ~94 GB of free HBM")
+    n_docs, nt, dim, nq = 1_000_000, 180, 128, 32
+    corpus = ib.TokenCorpus.generate(synth.SALT_CORPUS, 0, n_docs, nt, dim)
+    qs = oracle.ghash_f32(synth.SALT_QUERY, 0, 2 * nq * dim).reshape(2, nq, dim)
+    rng = np.random.default_rng(4)
+    sample = np.concatenate([[0, n_docs - 1], rng.integers(0, n_docs, size=150)])
+    off = np.arange(0, (len(sample) + 1) * nt, nt, dtype=np.uint64)
+    toks = np.concatenate([oracle.ghash_f32(synth.SALT_CORPUS, int(dd) * nt * dim, nt * dim).reshape(nt, dim) for dd in sample])
+    singles = {}
+    for cos in (True, False):
+        got = ib.maxsim_corpus(qs[0], corpus, cosine=cos)
+        singles[cos] = got
+        want = oracle.maxsim_corpus(qs[0], toks, off, cosine_flag=cos, n_threads=8)
+        rel = np.abs(got[sample].astype(np.float64) - want) / np.maximum(np.abs(want), 1e-30)
+        assert float(rel.max()) < 1e-5, (cos, float(rel.max()))
+    both = ib.maxsim_corpus_batch(qs, corpus, cosine=True)
+    assert np.array_equal(bits(both[0]), bits(singles[True]))
+    assert np.array_equal(bits(both[1]), bits(ib.maxsim_corpus(qs[1], corpus, cosine=True)))
+
+
 def test_full_size_c4_c5_properties(ib, oracle):
     """BASELINE C4 (100M x 1024-bit, top-100) and C5 (50M x 384 u8, top-10) at full size: every returned entry is
     re-derived bit-exactly on the CPU; order is (distance asc | score desc, index asc); a random sample holds no
