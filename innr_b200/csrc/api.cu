@@ -358,13 +358,24 @@ int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
   if (c->bytes) {
+    // ingest in chunks of rows through one 256 MB device staging buffer (stream order keeps copy and transpose of
+    // consecutive chunks apart): the device never holds a second copy of the corpus
+    size_t chunk = (size_t)(256u << 20) / (d * sizeof(float));
+    chunk = chunk / 32 * 32;
+    if (chunk < 32) chunk = 32;
+    if (chunk > n) chunk = n;
     void* stage = nullptr;
-    CU(cudaMalloc(&stage, n * d * sizeof(float)));
-    cudaError_t e = cudaMemcpyAsync(stage, host_rows, n * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess)
-      e = launch_transpose_rows_to_pdx((const float*)stage, n, d, (float*)c->dev, c->ld, ctx->stream, &g_launches);
+    cudaError_t e = cudaMalloc(&stage, chunk * d * sizeof(float));
+    for (size_t i0 = 0; i0 < n && e == cudaSuccess; i0 += chunk) {
+      const size_t rows = n - i0 < chunk ? n - i0 : chunk;
+      const bool last = i0 + rows == n;
+      e = cudaMemcpyAsync(stage, host_rows + i0 * d, rows * d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess)
+        e = launch_transpose_rows_to_pdx((const float*)stage, rows, d, (float*)c->dev + i0, c->ld,
+                                         last ? c->ld - i0 : rows, ctx->stream, &g_launches);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(stage);
+    if (stage) cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_f32_rows");
   }
   return INNR_OK;

@@ -103,8 +103,9 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
                               std::vector<unsigned>* overflow_queries, KnnTcStats* stats);
 
 // layout / generator kernels (layout.cu)
+// n rows (row-major, device) -> columns [0, cols) of dev_pdx (cols >= n; columns past n are zero-filled)
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,
-                                         cudaStream_t s, LaunchCounter* launches);
+                                         size_t cols, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
                                     float* dev_pdx, size_t ld, cudaStream_t s, LaunchCounter* launches);
 

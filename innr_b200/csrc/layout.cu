@@ -12,8 +12,10 @@ namespace innr {
 
 namespace {
 
+// rows: n x d row-major (a chunk of the corpus); pdx: first column of the chunk inside the PDX matrix (row pitch ld);
+// columns [0, cols) are written (cols >= n: the tail of the last chunk zero-fills the pitch padding)
 __global__ void transpose_rows_to_pdx_kernel(const float* __restrict__ rows, unsigned n, unsigned d,
-                                             float* __restrict__ pdx, size_t ld) {
+                                             float* __restrict__ pdx, size_t ld, unsigned cols) {
   __shared__ float tile[32][33];
   const unsigned i0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   // read rows[i][d0 + tx] coalesced along d
@@ -25,7 +27,7 @@ __global__ void transpose_rows_to_pdx_kernel(const float* __restrict__ rows, uns
   // write pdx[dd][i0 + tx] coalesced along i
   for (unsigned r = threadIdx.y; r < 32; r += blockDim.y) {
     unsigned dd = d0 + r, i = i0 + threadIdx.x;
-    if (dd < d && i < ld) pdx[(size_t)dd * ld + i] = tile[threadIdx.x][r];
+    if (dd < d && i < cols) pdx[(size_t)dd * ld + i] = tile[threadIdx.x][r];
   }
 }
 
@@ -53,10 +55,10 @@ __global__ void generate_tokens_kernel(uint64_t salt, uint64_t first_row, size_t
 }  // namespace
 
 cudaError_t launch_transpose_rows_to_pdx(const float* dev_rows, size_t n, size_t d, float* dev_pdx, size_t ld,
-                                         cudaStream_t s, LaunchCounter* launches) {
-  if (n == 0 || d == 0) return cudaSuccess;
-  dim3 grid((unsigned)((ld + 31) / 32), (unsigned)((d + 31) / 32));
-  transpose_rows_to_pdx_kernel<<<grid, dim3(32, 8), 0, s>>>(dev_rows, (unsigned)n, (unsigned)d, dev_pdx, ld);
+                                         size_t cols, cudaStream_t s, LaunchCounter* launches) {
+  if (cols == 0 || d == 0) return cudaSuccess;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((d + 31) / 32));
+  transpose_rows_to_pdx_kernel<<<grid, dim3(32, 8), 0, s>>>(dev_rows, (unsigned)n, (unsigned)d, dev_pdx, ld, (unsigned)cols);
   ++*launches;
   return cudaGetLastError();
 }

@@ -187,6 +187,29 @@ def test_rows_upload_transposes_on_device(ib):
     assert np.array_equal(bits(a.extract_vector(n - 1)), bits(rows[n - 1]))
 
 
+def test_rows_upload_in_chunks(ib):
+    """A row-major corpus larger than the 256 MB staging chunk is ingested chunk by chunk (VerticalBatch::from_flat,
+    src/batch.rs:167, on the device): every column lands where the PDX layout says, the pitch padding stays zero."""
+    n, d = 700_001, 200            # 560 MB of rows -> 3 chunks, ragged last chunk
+    rng = np.random.default_rng(12)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    a = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    for i in (0, 1, 335_543, 335_544, 671_087, 671_088, n - 2, n - 1):
+        assert np.array_equal(bits(a.extract_vector(i)), bits(rows[i])), i
+    q = rng.standard_normal(d).astype(np.float32)
+    got = ib.batch_dot(q, a)
+    idx = rng.integers(0, n, size=2000)
+    want = np.array([np.float32(0)] * len(idx))
+    for j, i in enumerate(idx):
+        acc = np.float32(0)
+        for dd in range(d):
+            acc = np.float32(acc + np.float32(q[dd] * rows[i, dd]))
+        want[j] = acc
+    assert np.array_equal(bits(got[idx]), bits(want))
+    g = ib.batch_knn_dot(q, a, 10)
+    assert max(g.indices) < n
+
+
 def test_topk_from_distances_random(ib, oracle):
     rng = np.random.default_rng(3)
     for n, k in ((1, 1), (31, 5), (1000, 10), (100_000, 100), (5000, 128)):
