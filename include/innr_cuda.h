@@ -230,6 +230,20 @@ int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_
 int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_q, int cosine_flag,
                          float* dev_scores, void* stream);
 
+/* ---- one process, several GPUs ---------------------------------------------------------------------------
+ * Row shards living on different devices (created after innr_cuda_init(device) on the creating thread, each with
+ * index_base = its first global row). The call runs one host thread per shard -- calls on different devices do not
+ * serialise -- and merges the k keys per shard on the host in the device's own key order, so results equal the
+ * unsharded call (lower global index wins across shards). No collective library is involved. */
+int innr_cuda_batch_knn_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, int metric, const float* queries,
+                                size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
+                                size_t* out_count);
+int innr_cuda_hamming_topk_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const uint64_t* query_words,
+                                   size_t n_queries, size_t query_dim_bits, size_t k, uint64_t* out_idx,
+                                   uint32_t* out_dist, size_t* out_count);
+int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
+                                   size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
+                                   size_t* out_count);
 /* ---- timing hook for bench.py: average device time (ms) of the last call's dominant kernel, measured with
  *      CUDA events on the launching stream ---------------------------------------------------------- */
 int innr_cuda_last_kernel_ms(float* out_ms);

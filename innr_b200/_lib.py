@@ -79,6 +79,9 @@ SIGNATURES = {
     "innr_cuda_upload_tokens": [f32p, u64p, sz, sz, u64, handle_p],
     "innr_cuda_generate_tokens": [u64, u64, sz, sz, sz, u64, handle_p],
     "innr_cuda_maxsim": [vp, f32p, sz, sz, ci, f32p],
+    "innr_cuda_batch_knn_sharded": [vp, sz, ci, f32p, sz, sz, sz, u64p, f32p, szp],
+    "innr_cuda_hamming_topk_sharded": [vp, sz, u64p, sz, sz, sz, u64p, u32p, szp],
+    "innr_cuda_batch_knn_u8_sharded": [vp, sz, f32p, sz, sz, sz, u64p, f32p, szp],
     "innr_cuda_maxsim_batch": [vp, f32p, sz, sz, sz, ci, f32p],
     "innr_cuda_maxsim_batch_dev": [vp, vp, sz, sz, ci, vp, vp],
     "innr_cuda_maxsim_dev": [vp, vp, sz, ci, vp, vp],

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -1476,6 +1478,161 @@ int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, s
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
   return maxsim_common(c, ctx, dev_q_tokens, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ one process, several GPUs
+// Row shards on different devices, one host thread per shard (the per-device mutexes let them run concurrently), each
+// computing its local top-k through the single-device entry; the k x n_shards (key, index) pairs are merged on the
+// host in key order -- the same composite keys as on the device, so "lower global index wins" holds across shards.
+// This is the single-process counterpart of the torch.distributed / NCCL harness: a Rust host that owns all
+// GPUs of a box needs no collective library for an exchange of k keys per device.
+}  // extern "C"
+namespace {
+uint32_t host_order_bits(float x) {
+  uint32_t b;
+  std::memcpy(&b, &x, 4);
+  b ^= ((uint32_t)((int32_t)b >> 31)) >> 1;
+  return b ^ 0x80000000u;
+}
+struct ShardOut {
+  std::vector<uint64_t> idx;
+  std::vector<float> score;
+  std::vector<uint32_t> dist;
+  size_t count = 0;
+  int rc = INNR_OK;
+  std::string err;
+};
+template <class Call>
+int run_shards(size_t n_shards, Call call, std::vector<ShardOut>& outs) {
+  std::vector<std::thread> th;
+  th.reserve(n_shards);
+  for (size_t i = 0; i < n_shards; ++i)
+    th.emplace_back([&, i] {
+      outs[i].rc = call(i, outs[i]);
+      if (outs[i].rc) outs[i].err = t_err;  // the message is thread-local
+    });
+  for (auto& t : th) t.join();
+  for (size_t i = 0; i < n_shards; ++i)
+    if (outs[i].rc) return fail(outs[i].rc, "shard " + std::to_string(i) + ": " + outs[i].err);
+  return INNR_OK;
+}
+}  // namespace
+extern "C" {
+
+int innr_cuda_batch_knn_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, int metric, const float* queries,
+                                size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
+                                size_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 0) return fail(INNR_EINVAL, "need f32 PDX shards");
+    if (shards[i]->d != shards[0]->d) return fail(INNR_EINVAL, "shards differ in dimension");
+    n_total += shards[i]->n;
+  }
+  if (query_len != shards[0]->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
+  if (!out_idx || !out_score) return fail(INNR_EINVAL, "null argument");
+  std::vector<ShardOut> outs(n_shards);
+  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+    o.idx.assign(n_queries * k, 0);
+    o.score.assign(n_queries * k, 0.0f);
+    return innr_cuda_batch_knn(shards[i], metric, queries, n_queries, query_len, k, o.idx.data(), o.score.data(), &o.count);
+  }, outs);
+  if (rc) return rc;
+  const bool desc = metric != INNR_METRIC_L2;
+  const size_t kk = k < n_total ? k : n_total;
+  std::vector<std::pair<uint64_t, float>> all;
+  for (size_t q = 0; q < n_queries; ++q) {
+    all.clear();
+    for (size_t i = 0; i < n_shards; ++i)
+      for (size_t j = 0; j < outs[i].count; ++j) {
+        const float sc = outs[i].score[q * k + j];
+        const uint32_t ob = desc ? ~host_order_bits(sc) : host_order_bits(sc);
+        all.emplace_back(((uint64_t)ob << 32) | outs[i].idx[q * k + j], sc);
+      }
+    std::sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (size_t j = 0; j < kk; ++j) {
+      out_idx[q * k + j] = all[j].first & 0xFFFFFFFFull;
+      out_score[q * k + j] = all[j].second;
+    }
+  }
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+int innr_cuda_hamming_topk_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const uint64_t* query_words,
+                                   size_t n_queries, size_t query_dim_bits, size_t k, uint64_t* out_idx,
+                                   uint32_t* out_dist, size_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 1) return fail(INNR_EINVAL, "need binary shards");
+    n_total += shards[i]->n;
+  }
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
+  if (!out_idx || !out_dist) return fail(INNR_EINVAL, "null argument");
+  std::vector<ShardOut> outs(n_shards);
+  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+    o.idx.assign(n_queries * k, 0);
+    o.dist.assign(n_queries * k, 0);
+    return innr_cuda_hamming_topk(shards[i], query_words, n_queries, query_dim_bits, k, o.idx.data(), o.dist.data(), &o.count);
+  }, outs);
+  if (rc) return rc;
+  const size_t kk = k < n_total ? k : n_total;
+  std::vector<uint64_t> all;
+  for (size_t q = 0; q < n_queries; ++q) {
+    all.clear();
+    for (size_t i = 0; i < n_shards; ++i)
+      for (size_t j = 0; j < outs[i].count; ++j)
+        all.push_back(((uint64_t)outs[i].dist[q * k + j] << 32) | outs[i].idx[q * k + j]);
+    std::sort(all.begin(), all.end());
+    for (size_t j = 0; j < kk; ++j) {
+      out_idx[q * k + j] = all[j] & 0xFFFFFFFFull;
+      out_dist[q * k + j] = (uint32_t)(all[j] >> 32);
+    }
+  }
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
+                                   size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
+                                   size_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 2) return fail(INNR_EINVAL, "need u8 shards");
+    n_total += shards[i]->n;
+  }
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
+  if (!out_idx || !out_score) return fail(INNR_EINVAL, "null argument");
+  std::vector<ShardOut> outs(n_shards);
+  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+    o.idx.assign(n_queries * k, 0);
+    o.score.assign(n_queries * k, 0.0f);
+    return innr_cuda_batch_knn_u8(shards[i], queries, n_queries, query_len, k, o.idx.data(), o.score.data(), &o.count);
+  }, outs);
+  if (rc) return rc;
+  const size_t kk = k < n_total ? k : n_total;
+  std::vector<std::pair<uint64_t, float>> all;
+  for (size_t q = 0; q < n_queries; ++q) {
+    all.clear();
+    for (size_t i = 0; i < n_shards; ++i)
+      for (size_t j = 0; j < outs[i].count; ++j) {
+        const float sc = outs[i].score[q * k + j];
+        all.emplace_back(((uint64_t)(~host_order_bits(sc)) << 32) | outs[i].idx[q * k + j], sc);
+      }
+    std::sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (size_t j = 0; j < kk; ++j) {
+      out_idx[q * k + j] = all[j].first & 0xFFFFFFFFull;
+      out_score[q * k + j] = all[j].second;
+    }
+  }
+  if (out_count) *out_count = kk;
+  return INNR_OK;
 }
 
 }  // extern "C"

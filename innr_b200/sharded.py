@@ -118,3 +118,54 @@ class ShardedKnn:
         dq = src.to(f"cuda:{t.cuda.current_device()}", non_blocking=True)
         idx, score = self.knn_dev(dq, nq, k)
         return idx.cpu().numpy().astype(np.uint64), score.cpu().numpy()
+
+
+# ---- one process, several GPUs: the C-ABI's own sharded entries (no torch.distributed, no NCCL) -------------------------
+def _handle_array(shards):
+    arr = (C.c_void_p * len(shards))(*[sh.h for sh in shards])
+    return arr
+
+
+def batch_knn_sharded(metric: str, queries, shards, k: int):
+    """`shards`: DeviceBatch row shards (possibly on different devices, each with its index_base). One host thread per
+    shard inside the library; the k keys per shard are merged on the host. Returns (idx, scores) of shape (nq, <=k)."""
+    qs = np.ascontiguousarray(queries, dtype=np.float32)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq, qlen = qs.shape
+    kk = max(k, 1)
+    idx = np.zeros((nq, kk), np.uint64)
+    sc = np.zeros((nq, kk), np.float32)
+    cnt = C.c_size_t(0)
+    m = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
+    L.call("innr_cuda_batch_knn_sharded", _handle_array(shards), len(shards), m, qs.ctypes.data_as(L.f32p), nq, qlen, k,
+           idx.ctypes.data_as(L.u64p), sc.ctypes.data_as(L.f32p), C.byref(cnt))
+    return idx[:, :cnt.value], sc[:, :cnt.value]
+
+
+def hamming_topk_sharded(query_words, shards, k: int):
+    qs = np.ascontiguousarray(query_words, dtype=np.uint64)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq = qs.shape[0]
+    kk = max(k, 1)
+    idx = np.zeros((nq, kk), np.uint64)
+    ds = np.zeros((nq, kk), np.uint32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_hamming_topk_sharded", _handle_array(shards), len(shards), qs.ctypes.data_as(L.u64p), nq,
+           shards[0].dimension, k, idx.ctypes.data_as(L.u64p), ds.ctypes.data_as(L.u32p), C.byref(cnt))
+    return idx[:, :cnt.value], ds[:, :cnt.value]
+
+
+def batch_knn_u8_sharded(queries, shards, k: int):
+    qs = np.ascontiguousarray(queries, dtype=np.float32)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq, qlen = qs.shape
+    kk = max(k, 1)
+    idx = np.zeros((nq, kk), np.uint64)
+    sc = np.zeros((nq, kk), np.float32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_batch_knn_u8_sharded", _handle_array(shards), len(shards), qs.ctypes.data_as(L.f32p), nq, qlen, k,
+           idx.ctypes.data_as(L.u64p), sc.ctypes.data_as(L.f32p), C.byref(cnt))
+    return idx[:, :cnt.value], sc[:, :cnt.value]

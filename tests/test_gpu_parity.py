@@ -313,6 +313,40 @@ def test_concurrent_host_threads(ib, oracle):
     assert not errors, errors[:3]
 
 
+def test_c_abi_sharded_entries(ib, oracle):
+    """innr_cuda_*_sharded: row shards (here three on one device; test_one_process_two_devices spreads them over two),
+    one host thread per shard inside the library, host merge in the device's key order == the unsharded result,
+    with heavy ties across shard boundaries."""
+    from innr_b200 import sharded
+    n, d, nq = 9001, 40, 5
+    rng = np.random.default_rng(14)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    qs = rng.integers(-3, 4, size=(nq, d)).astype(np.float32)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    cuts = [0, 2500, 2500, 7003, n]          # one empty shard
+    shards = [ib.DeviceBatch.from_rows_flat(rows[a:b].reshape(-1), b - a, d, index_base=a) for a, b in zip(cuts, cuts[1:])]
+    for metric in ("dot", "cosine", "l2"):
+        for k in (1, 10, 100, 300):
+            idx, sc = sharded.batch_knn_sharded(metric, qs, shards, k)
+            widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=4)
+            assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
+            if metric != "l2":
+                assert np.array_equal(idx, widx), (metric, k)
+    codes = rng.integers(0, 2**62, size=(n, 3), dtype=np.uint64)
+    qc = rng.integers(0, 2**62, size=(2, 3), dtype=np.uint64)
+    bsh = [ib.BinaryCorpus.from_words(codes[a:b], b - a, 192, index_base=a) for a, b in zip(cuts, cuts[1:])]
+    gi, gd = sharded.hamming_topk_sharded(qc, bsh, 100)
+    wi, wd = oracle.hamming_topk_many(qc, codes, 100, n_threads=2)
+    assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+    mat = rng.integers(0, 256, size=(n, 48), dtype=np.uint8)
+    q8 = rng.uniform(-1, 1, size=(3, 48)).astype(np.float32)
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    ush = [ib.U8Corpus.from_rows(mat[a:b], gp, index_base=a, dimension=48) for a, b in zip(cuts, cuts[1:])]
+    ui, us = sharded.batch_knn_u8_sharded(q8, ush, 10)
+    wi, ws = oracle.batch_knn_u8_many(q8, mat, op, 10, n_threads=2)
+    assert np.array_equal(ui, wi) and np.array_equal(bits(us), bits(ws))
+
+
 def test_one_process_two_devices(ib, oracle):
     """one host process driving several GPUs, one thread and one row shard per device
     (per-device mutexes, per-device function attributes): local top-k per shard, merged on the host by key order."""
@@ -352,6 +386,19 @@ def test_one_process_two_devices(ib, oracle):
     assert not errors, errors
     pairs = sorted(((-float(s), int(i)) for dv in (0, 1) for i, s in zip(*out[dv])))[:k]
     assert [i for _, i in pairs] == [int(i) for i in want.indices]
+    # the library's own sharded entry over shards on both devices
+    from innr_b200 import sharded
+    shards = []
+    for dev, (lo, hi) in enumerate(((0, half), (half, n))):
+        ib.init(dev)
+        shards.append(ib.DeviceBatch.from_rows_flat(rows[lo:hi].reshape(-1), hi - lo, d, index_base=lo))
+    ib.init(0)
+    qs = rand_rows(6, d, 31)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for metric in ("cosine", "dot"):
+        idx, sc = sharded.batch_knn_sharded(metric, qs, shards, k)
+        widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=4)
+        assert np.array_equal(idx, widx) and np.array_equal(bits(sc), bits(wsc)), metric
 
 
 # ------------------------------------------------------------------------------------------------ two-stage retrieval
