@@ -96,6 +96,34 @@ __device__ __forceinline__ void fma16(const uint4 v, const float* __restrict__ q
   }
 }
 
+// the same 16 bytes against TWO queries: the byte -> f32 conversion (the PRMTs) is shared
+template <bool SCALED>
+__device__ __forceinline__ void fma16_pair(const uint4 v, const float* __restrict__ qa, const float* __restrict__ qb,
+                                           float* acc_a, float* acc_b, unsigned magic) {
+  const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float x0, x1, x2, x3;
+    if (SCALED) {
+      x0 = __uint_as_float(__byte_perm(w[g], 0u, 0x4440u));
+      x1 = __uint_as_float(__byte_perm(w[g], 0u, 0x4441u));
+      x2 = __uint_as_float(__byte_perm(w[g], 0u, 0x4442u));
+      x3 = __uint_as_float(__byte_perm(w[g], 0u, 0x4443u));
+    } else {
+      x0 = byte_to_f32_biased(w[g], 0, magic), x1 = byte_to_f32_biased(w[g], 1, magic);
+      x2 = byte_to_f32_biased(w[g], 2, magic), x3 = byte_to_f32_biased(w[g], 3, magic);
+      add2(x0, x1, -8388608.0f);
+      add2(x2, x3, -8388608.0f);
+    }
+    const float4 a4 = *reinterpret_cast<const float4*>(qa + 4 * g);
+    fma2(acc_a[4 * g + 0], acc_a[4 * g + 1], a4.x, a4.y, x0, x1);
+    fma2(acc_a[4 * g + 2], acc_a[4 * g + 3], a4.z, a4.w, x2, x3);
+    const float4 b4 = *reinterpret_cast<const float4*>(qb + 4 * g);
+    fma2(acc_b[4 * g + 0], acc_b[4 * g + 1], b4.x, b4.y, x0, x1);
+    fma2(acc_b[4 * g + 2], acc_b[4 * g + 3], b4.z, b4.w, x2, x3);
+  }
+}
+
 __device__ __forceinline__ float hsum8(const float* v) {  // src/arch/x86_64.rs:982-987
   float s0 = __fadd_rn(v[0], v[4]), s1 = __fadd_rn(v[1], v[5]);
   float s2 = __fadd_rn(v[2], v[6]), s3 = __fadd_rn(v[3], v[7]);
@@ -144,6 +172,7 @@ struct U8Args {
   unsigned magic;      // 0x4B000000 (2^23 as f32 bits), see byte_to_f32
   int allow_scaled;    // option "u8_scaled_chains" (default 1): PRMT + FFMA2 chains when the query allows it
   const float* query;  // device, d floats
+  const float* query_b;  // pair kernel: the second query
   int k, mode;         // mode (scores kernel): 0 raw mixed dot, 1 asymmetric score
   uint64_t* partials;
   uint64_t* out_keys;
@@ -156,6 +185,11 @@ int g_u8_allow_scaled = 1;
 
 struct U8Shared {
   uint64_t full[U8_STAGES], empty[U8_STAGES];
+};
+// pair kernel: 64 accumulators per thread leave room for one CTA per SM only, so its ring is twice as deep
+constexpr int U8_PAIR_STAGES = 12;
+struct U8PairShared {
+  uint64_t full[U8_PAIR_STAGES], empty[U8_PAIR_STAGES];
 };
 
 // bulk copy global -> shared, completion on an mbarrier (complete_tx::bytes); 16-byte aligned, size % 16 == 0
@@ -287,6 +321,127 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
   }
   // the producer warp takes part in the CTA-wide merge with an empty list
   if (KNN) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
+}
+
+// Two queries per pass (top-k only): the scan is instruction-bound under the power cap and the byte -> f32 conversion is
+// more than half of its instructions, so a second query rides along for ~40 % more work instead of 100 %.
+// a.query = query A, a.query_b = query B; keys to a.out_keys (A) and a.out_keys + k (B).
+template <int R>
+__global__ void __launch_bounds__(U8_CTA, 1) u8_scan_pair_kernel(const U8Args a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;
+  const unsigned d_pad = (a.d + 31) / 32 * 32 + 32;
+  float* sqa = reinterpret_cast<float*>(smem_raw + U8_PAIR_STAGES * U8_STAGE_BYTES);
+  float* sqb = sqa + d_pad;
+  float* s_misc = sqb + d_pad;  // [0], [1] = query sums
+  U8PairShared* st = reinterpret_cast<U8PairShared*>(s_misc + 4);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(st + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool producer = warp == U8_THREADS / 32;
+  const unsigned main_elems = (a.d >= 16) ? (a.d / 32) * 32 : 0;
+  bool q_ok = true;
+  for (unsigned i = threadIdx.x; i < d_pad; i += blockDim.x) {
+    const float va = i < a.d ? a.query[i] : 0.0f, vb = i < a.d ? a.query_b[i] : 0.0f;
+    sqa[i] = va;
+    sqb[i] = vb;
+    if (i < main_elems)
+      q_ok &= ((va == 0.0f) || (fabsf(va) >= 0x1p-80f && fabsf(va) < 4.0f)) &&
+              ((vb == 0.0f) || (fabsf(vb) >= 0x1p-80f && fabsf(vb) < 4.0f));
+  }
+  if (threadIdx.x < 2) {  // query_context of each query: sequential sum (src/scalar.rs:236-240)
+    const float* qp = threadIdx.x ? a.query_b : a.query;
+    float sum = 0.0f;
+    for (unsigned i = 0; i < a.d; ++i) sum = __fadd_rn(sum, qp[i]);
+    s_misc[threadIdx.x] = sum;
+  }
+  if (threadIdx.x == 0) {
+    for (int sg = 0; sg < U8_PAIR_STAGES; ++sg) {
+      tc::mbar_init(&st->full[sg], 1);
+      tc::mbar_init(&st->empty[sg], U8_THREADS / 32);
+    }
+    tc::fence_barrier_init();
+  }
+  const bool scaled = __syncthreads_and(q_ok) && a.allow_scaled;
+  if (scaled) {
+    for (unsigned i = threadIdx.x; i < main_elems; i += blockDim.x) {
+      sqa[i] *= 0x1p126f;
+      sqb[i] *= 0x1p126f;
+    }
+    __syncthreads();
+  }
+  const float scale = __fdiv_rn(a.alpha, 255.0f);
+  const float bias_a = __fmul_rn(a.offset, s_misc[0]), bias_b = __fmul_rn(a.offset, s_misc[1]);
+  const unsigned stages_per_tile = (a.chunks + U8_STAGE_CHUNKS - 1) / U8_STAGE_CHUNKS;
+  const unsigned main_chunks = (a.d >= 16) ? (a.d / 32) * 2 : 0;
+
+  WarpList<R> lists[2];
+  uint64_t thrs[2];
+  lists[0].init();
+  lists[1].init();
+  thrs[0] = thrs[1] = KEY_SENTINEL;
+
+  if (producer) {
+    if (lane == 0) {
+      unsigned slot = 0, phase = 1;
+      for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const unsigned long long col = (unsigned long long)tile * U8_THREADS;
+        const unsigned long long left = a.ld - col;
+        const unsigned row_bytes = (unsigned)(left < U8_THREADS ? left : U8_THREADS) * 16u;
+        for (unsigned sgi = 0; sgi < stages_per_tile; ++sgi) {
+          const unsigned c0 = sgi * U8_STAGE_CHUNKS;
+          const unsigned rows = min((unsigned)U8_STAGE_CHUNKS, a.chunks - c0);
+          while (!tc::mbar_try_wait(&st->empty[slot], phase)) __nanosleep(64);
+          tc::mbar_arrive_expect_tx(&st->full[slot], rows * row_bytes);
+          for (unsigned r = 0; r < rows; ++r)
+            bulk_load(ring + slot * U8_STAGE_BYTES + r * U8_ROW_BYTES, a.data + (size_t)(c0 + r) * a.ld + col, row_bytes,
+                      &st->full[slot]);
+          if (++slot == U8_PAIR_STAGES) { slot = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    auto consume = [&](auto scaled_tag) {
+      constexpr bool SCALED = decltype(scaled_tag)::value;
+      unsigned slot = 0, phase = 0;
+      const uint4* const ring_v = reinterpret_cast<const uint4*>(ring) + threadIdx.x;
+      for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const unsigned i = tile * U8_THREADS + threadIdx.x;
+        const bool valid = i < a.n;
+        float acc_a[32], acc_b[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc_a[c] = acc_b[c] = 0.0f;
+        unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (unsigned sgi = 0; sgi < stages_per_tile; ++sgi) {
+          const unsigned c0 = sgi * U8_STAGE_CHUNKS;
+          tc::mbar_wait(&st->full[slot], phase);
+          const uint4* sv = ring_v + slot * (U8_STAGE_BYTES / 16);
+          uint4 v[U8_STAGE_CHUNKS];
+#pragma unroll
+          for (int g = 0; g < U8_STAGE_CHUNKS; ++g) v[g] = sv[g * U8_THREADS];  // rows past `chunks`: stale, unused
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&st->empty[slot]);
+          if (++slot == U8_PAIR_STAGES) { slot = 0; phase ^= 1; }
+#pragma unroll
+          for (int g = 0; g < U8_STAGE_CHUNKS; ++g) {
+            const unsigned c = c0 + g;
+            if (c < main_chunks) {
+              fma16_pair<SCALED>(v[g], sqa + 16 * c, sqb + 16 * c, acc_a + 16 * (g & 1), acc_b + 16 * (g & 1), a.magic);
+            } else if (c < a.chunks) {
+              if (c == main_chunks) { w[0] = v[g].x; w[1] = v[g].y; w[2] = v[g].z; w[3] = v[g].w; }
+              else { w[4] = v[g].x; w[5] = v[g].y; w[6] = v[g].z; w[7] = v[g].w; }
+            }
+          }
+        }
+        const float unscale = SCALED ? 0x1p23f : 1.0f;
+        const float ma = mixed_dot_finish(acc_a, w, a.d, sqa, a.magic, unscale);
+        const float mb = mixed_dot_finish(acc_b, w, a.d, sqb, a.magic, unscale);
+        lists[0].offer(make_key_desc(__fadd_rn(__fmul_rn(scale, ma), bias_a), a.index_base + i), valid, thrs[0], a.k, lane);
+        lists[1].offer(make_key_desc(__fadd_rn(__fmul_rn(scale, mb), bias_b), a.index_base + i), valid, thrs[1], a.k, lane);
+      }
+    };
+    if (scaled) consume(std::true_type{}); else consume(std::false_type{});
+  }
+  block_finish<R, 2>(lists, 2, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
 __global__ void u8_pack_kernel(const uint8_t* __restrict__ rows, unsigned n, unsigned d, uint4* __restrict__ codes,
@@ -457,12 +612,44 @@ cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, 
   return e;
 }
 
+namespace {
+template <int R>
+cudaError_t launch_u8_pair(const U8Args& a, size_t smem, int num_sms, cudaStream_t s) {
+  auto kern = u8_scan_pair_kernel<R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, U8_CTA, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  kern<<<balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms), U8_CTA, smem, s>>>(a);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
                           Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   if (k > 128) return cudaErrorInvalidValue;
   size_t smem = u8_smem(v.d, k, true);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  for (size_t q = 0; q < nq; ++q) {
+  size_t q0 = 0;
+  // query batches: two queries per pass
+  const size_t d_pad = (v.d + 31) / 32 * 32 + 32;
+  const size_t pair_smem = (size_t)U8_PAIR_STAGES * U8_STAGE_BYTES + (2 * d_pad + 4) * sizeof(float) + sizeof(U8PairShared) +
+                           (size_t)(U8_CTA / 32) * k * sizeof(uint64_t);
+  for (; nq - q0 >= 2 && pair_smem <= 227 * 1024; q0 += 2) {
+    U8Args a = make_args(v, dev_queries + q0 * v.d);
+    a.query_b = dev_queries + (q0 + 1) * v.d;
+    a.k = (int)k;
+    a.partials = ws.partials;
+    a.group_partials = ws.group_partials;
+    a.tickets = ws.tickets;
+    a.out_keys = dev_keys + q0 * k;
+    cudaError_t e = (k <= 32) ? launch_u8_pair<1>(a, pair_smem, ws.num_sms, s) : launch_u8_pair<4>(a, pair_smem, ws.num_sms, s);
+    if (e != cudaSuccess) return e;
+    ++*launches;
+  }
+  for (size_t q = q0; q < nq; ++q) {
     U8Args a = make_args(v, dev_queries + q * v.d);
     a.k = (int)k;
     a.partials = ws.partials;

@@ -637,6 +637,25 @@ def test_u8_scaled_chains_bit_exact(ib, oracle, d, qkind):
         assert np.array_equal(bits([s for _, s in got]), bits([s for _, s in want_k]))
 
 
+@pytest.mark.parametrize("d,nq", [(384, 2), (384, 5), (100, 4), (33, 3), (8, 2), (777, 7)])
+def test_u8_query_batches_share_a_pass(ib, oracle, d, nq):
+    """batch_knn_u8 for several queries: two queries share each pass over the codes (the byte -> f32 conversion is
+    shared); every list must be bit-identical to the single-query result, incl. a query that forces the de-biasing
+    path for its pair (|q| >= 4) and every tail shape."""
+    n = 5000
+    rng = np.random.default_rng(d * 7 + nq)
+    mat = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    qs = rng.uniform(-1, 1, size=(nq, d)).astype(np.float32)
+    qs[-1, 0] = 7.5                                  # outside the scaled-chain range
+    gp, op = ib.QuantizationParams.from_range(-2.0, 1.0), oracle.QuantizationParams.from_range(-2.0, 1.0)
+    corpus = ib.U8Corpus.from_rows(mat, gp)
+    for k in (1, 10, 100):
+        gi, gs = ib.batch_knn_u8_many(qs, corpus, k)
+        wi, ws = oracle.batch_knn_u8_many(qs, mat, op, k, n_threads=4)
+        assert np.array_equal(gi, wi), (d, nq, k)
+        assert np.array_equal(bits(gs), bits(ws)), (d, nq, k)
+
+
 def test_u8_generator_and_quantize(ib, oracle):
     n, d = 4000, 384
     gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
