@@ -406,6 +406,7 @@ __global__ void knn_tc_prep_queries_kernel(const float* __restrict__ q, unsigned
 
 // ---- between passes: threshold of the next pass = k-th largest lower bound among the appended pairs ------------------
 // one warp per query; also resets the counter for the next pass
+template <int R>
 __global__ void knn_tc_select_kernel(unsigned nq, unsigned k, const unsigned* __restrict__ qflag,
                                      unsigned* __restrict__ cand_count, const float* __restrict__ cand_lb,
                                      float* __restrict__ thr) {
@@ -415,7 +416,7 @@ __global__ void knn_tc_select_kernel(unsigned nq, unsigned k, const unsigned* __
   if (qflag[q]) return;  // thr stays +inf
   unsigned cnt = cand_count[q];
   if (cnt > CAND_CAP) cnt = CAND_CAP;  // any k stored pairs give a valid bound
-  WarpList<1> list;
+  WarpList<R> list;
   list.init();
   uint64_t t = KEY_SENTINEL;
   for (unsigned c0 = 0; c0 < cnt; c0 += 32) {
@@ -592,7 +593,7 @@ size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) {
 }
 
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k) {
-  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED || mode == PDX_L2) && nq >= 1 && k >= 1 && k <= 32 && v.d >= 1 && v.n >= 4096 &&
+  return (mode == PDX_DOT || mode == PDX_COSINE_FUSED || mode == PDX_L2) && nq >= 1 && k >= 1 && k <= 128 && v.d >= 1 && v.n >= 4096 &&
          v.n < 0x7FFFFF00ull;
 }
 
@@ -711,7 +712,8 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
     if (last) {
       cudaEventRecord(ev[2], s);
     } else {
-      knn_tc_select_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, s>>>((unsigned)nq, (unsigned)k, qflag, cnt, cand_lb, thr);
+      if (k <= 32) knn_tc_select_kernel<1><<<(unsigned)((nq + 3) / 4), 128, 0, s>>>((unsigned)nq, (unsigned)k, qflag, cnt, cand_lb, thr);
+      else knn_tc_select_kernel<4><<<(unsigned)((nq + 3) / 4), 128, 0, s>>>((unsigned)nq, (unsigned)k, qflag, cnt, cand_lb, thr);
       ++*launches;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
@@ -719,9 +721,14 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   }
   // 3. exact rescoring + selection
   const size_t rs_smem = ((v.d + 3) & ~(size_t)3) * 4 + (size_t)(RS_THREADS / 32) * k * 8;
-  knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
-                                                                     dev_queries, cosine, l2, a.eps, dev_norms, qflag, cnt, cand_idx, cand_lb,
-                                                                     (int)k, dev_keys);
+  if (k <= 32)
+    knn_tc_rescore_kernel<1><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
+                                                                       dev_queries, cosine, l2, a.eps, dev_norms, qflag, cnt, cand_idx,
+                                                                       cand_lb, (int)k, dev_keys);
+  else
+    knn_tc_rescore_kernel<4><<<(unsigned)nq, RS_THREADS, rs_smem, s>>>(v.data, v.ld, (unsigned)v.n, (unsigned)v.d, v.index_base,
+                                                                       dev_queries, cosine, l2, a.eps, dev_norms, qflag, cnt, cand_idx,
+                                                                       cand_lb, (int)k, dev_keys);
   ++*launches;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   cudaEventRecord(ev[3], s);

@@ -1036,18 +1036,18 @@ def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
         qs[1] = rows[300] * 2.0
     gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
     for metric in ("cosine", "dot"):
-        for k in (1, 10, 32):
+        for k in (1, 10, 32, 100):
             idx, sc = ib.batch_knn_many(metric, qs, gb, k)
             st = ib.knn_tc_last_stats()
-            assert st["passes"] >= 2 and st["exact_scan_queries"] <= 4, st   # the filter really answered the batch
+            assert st["passes"] >= 2 and (k > 32 or st["exact_scan_queries"] <= 4), st   # the filter really answered the batch
             widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
             assert np.array_equal(idx, widx), (metric, k, np.argwhere(idx != widx)[:5])
             assert np.array_equal(bits(sc), bits(wsc)), (metric, k)
     # squared L2 (batch_knn, the TopK path: exact-tie groups compare as sets)
-    for k in (1, 10, 32):
+    for k in (1, 10, 32, 100):
         idx, sc = ib.batch_knn_many("l2", qs, gb, k)
         st = ib.knn_tc_last_stats()
-        assert st["passes"] >= 2 and st["exact_scan_queries"] <= 4, st
+        assert st["passes"] >= 2 and (k > 32 or st["exact_scan_queries"] <= 4), st
         widx, wsc = oracle.batch_knn_many("l2", qs, ob, k, n_threads=8)
         assert np.array_equal(bits(sc), bits(wsc)), ("l2", k, np.argwhere(bits(sc) != bits(wsc))[:5])
         for j in range(nq):
