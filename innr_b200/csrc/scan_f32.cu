@@ -106,20 +106,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
       unsigned dd = idx / QB, q = idx % QB;
       sq[idx] = (dd < a.d && (int)q < a.nq_valid) ? a.queries[(size_t)q * a.d + dd] : 0.0f;
     }
-    if ((MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS) && threadIdx.x < QB) {
-      // query_norm = query.iter().map(|x| x * x).sum::<f32>().sqrt()   (src/batch.rs:714) -- sequential
+  }
+  __syncthreads();
+  if (NEED_DOT && (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS)) {
+    // query_norm = query.iter().map(|x| x * x).sum::<f32>().sqrt()   (src/batch.rs:714) -- sequential, so one thread per
+    // query; read from the shared-memory copy (a dependent chain of global loads cost ~20 us per launch)
+    if (threadIdx.x < QB) {
       float ss = 0.0f;
       if ((int)threadIdx.x < a.nq_valid) {
-        const float* qp = a.queries + (size_t)threadIdx.x * a.d;
         for (unsigned dd = 0; dd < a.d; ++dd) {
-          float x = qp[dd];
+          const float x = sq[(size_t)dd * QB + threadIdx.x];
           ss = __fadd_rn(ss, __fmul_rn(x, x));
         }
       }
       s_qn[threadIdx.x] = __fsqrt_rn(ss);
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   WarpList<R> lists[QB];
   uint64_t thrs[QB];

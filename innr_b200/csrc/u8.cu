@@ -219,10 +219,7 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
     sq[i] = v;
     if (i < main_elems) q_ok &= (v == 0.0f) || (fabsf(v) >= 0x1p-80f && fabsf(v) < 4.0f);  // NaN fails both
   }
-  if (threadIdx.x == 0) {  // query_context: query.iter().sum() sequential (src/scalar.rs:236-240)
-    float s = 0.0f;
-    for (unsigned i = 0; i < a.d; ++i) s = __fadd_rn(s, a.query[i]);
-    s_misc[0] = s;
+  if (threadIdx.x == 0) {
     for (int sg = 0; sg < U8_STAGES; ++sg) {
       tc::mbar_init(&st->full[sg], 1);
       tc::mbar_init(&st->empty[sg], U8_THREADS / 32);
@@ -230,6 +227,12 @@ __global__ void __launch_bounds__(U8_CTA, 2) u8_scan_kernel(const U8Args a) {
     tc::fence_barrier_init();
   }
   const bool scaled = __syncthreads_and(q_ok) && a.allow_scaled;
+  if (threadIdx.x == 32) {  // query_context: query.iter().sum() sequential (src/scalar.rs:236-240), from the shared copy
+    float s = 0.0f;         // (a dependent chain of global loads would delay every CTA by several microseconds)
+    for (unsigned i = 0; i < a.d; ++i) s = __fadd_rn(s, sq[i]);
+    s_misc[0] = s;
+  }
+  __syncthreads();
   if (scaled) {  // only the main-loop part; the remainder / portable paths read the query as given
     for (unsigned i = threadIdx.x; i < main_elems; i += blockDim.x) sq[i] *= 0x1p126f;  // exact: |q| < 4
     __syncthreads();
@@ -348,12 +351,6 @@ __global__ void __launch_bounds__(U8_CTA, 1) u8_scan_pair_kernel(const U8Args a)
       q_ok &= ((va == 0.0f) || (fabsf(va) >= 0x1p-80f && fabsf(va) < 4.0f)) &&
               ((vb == 0.0f) || (fabsf(vb) >= 0x1p-80f && fabsf(vb) < 4.0f));
   }
-  if (threadIdx.x < 2) {  // query_context of each query: sequential sum (src/scalar.rs:236-240)
-    const float* qp = threadIdx.x ? a.query_b : a.query;
-    float sum = 0.0f;
-    for (unsigned i = 0; i < a.d; ++i) sum = __fadd_rn(sum, qp[i]);
-    s_misc[threadIdx.x] = sum;
-  }
   if (threadIdx.x == 0) {
     for (int sg = 0; sg < U8_PAIR_STAGES; ++sg) {
       tc::mbar_init(&st->full[sg], 1);
@@ -362,6 +359,13 @@ __global__ void __launch_bounds__(U8_CTA, 1) u8_scan_pair_kernel(const U8Args a)
     tc::fence_barrier_init();
   }
   const bool scaled = __syncthreads_and(q_ok) && a.allow_scaled;
+  if (threadIdx.x == 32 || threadIdx.x == 64) {  // query_context of each query: sequential sum (src/scalar.rs:236-240)
+    const float* qp = threadIdx.x == 64 ? sqb : sqa;
+    float sum = 0.0f;
+    for (unsigned i = 0; i < a.d; ++i) sum = __fadd_rn(sum, qp[i]);
+    s_misc[threadIdx.x == 64 ? 1 : 0] = sum;
+  }
+  __syncthreads();
   if (scaled) {
     for (unsigned i = threadIdx.x; i < main_elems; i += blockDim.x) {
       sqa[i] *= 0x1p126f;
