@@ -66,6 +66,7 @@ struct SharedTail {  // everything after the operand buffers
   uint64_t full[MAX_STAGES], empty[MAX_STAGES], lo_ready[2], lo_free[2], tmem_full[ACC_MAX], tmem_empty[ACC_MAX];
   unsigned long long s_tok[5];  // token boundaries of the four streams
   unsigned s_doc[5];            // document boundaries of the four streams
+  float q_inv[2 * NQ];          // cosine: 1/||q_r|| per query token row
   float part[4][CHUNK + 1];     // G = 2: per epilogue warp, first-group partial sums of the documents ending in the chunk
   uint32_t tmem_base;
 };
@@ -200,18 +201,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
   }
   if (warp == 9) tmem_alloc<512>(&st->tmem_base);
   // B operand: rows [0, 32G) = Qhi, rows [32G, 64G) = Qlo (cosine: rows pre-scaled by 1/||q||), K-major SW128 panels
+  auto q_row = [&](int r, bool& qvalid) -> const float* {
+    const bool second = G > 1 && a.split && r >= NQ;
+    qvalid = (G > 1 && a.split) ? (second ? r - NQ < (int)a.n_q_b : r < (int)a.n_q) : r < (int)a.n_q;
+    return second ? a.q_b + (size_t)(r - NQ) * DIM : a.q + (size_t)r * DIM;
+  };
+  if (COSINE) {  // 1/||q_r|| once per query token (one thread per row), not once per element
+    if ((int)threadIdx.x < NQG) {
+      bool qvalid;
+      const float* qp = q_row((int)threadIdx.x, qvalid);
+      float aa = 0.0f;
+      if (qvalid)
+        for (int kk = 0; kk < DIM; ++kk) aa = fmaf(qp[kk], qp[kk], aa);
+      // a query token with ~zero norm scores cosine 0 against every token (x86_64.rs:781-785)
+      st->q_inv[threadIdx.x] = (qvalid && aa > EPS_SQ) ? 1.0f / sqrtf(aa) : 0.0f;
+    }
+    __syncthreads();
+  }
   for (int idx = threadIdx.x; idx < NQG * DIM; idx += blockDim.x) {
     const int r = idx / DIM, k = idx % DIM;
-    const bool second = G > 1 && a.split && r >= NQ;
-    const float* qsrc = second ? a.q_b + (size_t)(r - NQ) * DIM : a.q + (size_t)r * DIM;
-    const bool qvalid = (G > 1 && a.split) ? (second ? r - NQ < (int)a.n_q_b : r < (int)a.n_q) : r < (int)a.n_q;
+    bool qvalid;
+    const float* qsrc = q_row(r, qvalid);
     float v = qvalid ? qsrc[k] : 0.0f;
-    if (COSINE && qvalid) {
-      float aa = 0.0f;
-      const float* qp = qsrc;
-      for (int kk = 0; kk < DIM; ++kk) aa = fmaf(qp[kk], qp[kk], aa);
-      v = aa > EPS_SQ ? v / sqrtf(aa) : 0.0f;  // query with ~zero norm -> cosine 0 for every token (x86_64.rs:781-785)
-    }
+    if (COSINE) v *= st->q_inv[r];
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     const float lo = v - hi;
     *reinterpret_cast<float*>(s_q + sw128_offset(r, k, QPANEL_BYTES)) = hi;
