@@ -197,6 +197,18 @@ class Workload:
         t = self.torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
         return t, t.numpy()
 
+    def fetch(self, idx, score):
+        """D2H of a result pair into pinned host tensors with ONE stream synchronisation."""
+        key = (tuple(idx.shape), idx.dtype, score.dtype)
+        if getattr(self, "_fetch_key", None) != key:
+            self._fetch_key = key
+            self._h_idx = self.torch.empty(idx.shape, dtype=idx.dtype).pin_memory()
+            self._h_sc = self.torch.empty(score.shape, dtype=score.dtype).pin_memory()
+        self._h_idx.copy_(idx, non_blocking=True)
+        self._h_sc.copy_(score, non_blocking=True)
+        self.torch.cuda.current_stream().synchronize()
+        return self._h_idx, self._h_sc
+
 
 class KnnF32(Workload):
     def setup(self):
@@ -253,7 +265,7 @@ class KnnF32(Workload):
         q = self.q_host_t[i % self.q_host_t.shape[0]]
         dq = q.to(self.dev, non_blocking=True)
         idx, sc = self.sk.knn_dev(dq, self.nq, self.k)
-        return idx.cpu(), sc.cpu()
+        return self.fetch(idx, sc)
 
     def cpu_baseline(self, cores, budget_queries=None):
         from oracle import innr_oracle as orc
@@ -301,7 +313,7 @@ class Hamming(Workload):
             return ib.hamming_topk_many(self.q_host[i % 16].view(np.uint64).reshape(1, -1), self.shard, self.k)
         dq = self.q_host_t[i % 16].to(self.dev, non_blocking=True)
         idx, ds = self.sk.knn_dev(dq, 1, self.k)
-        return idx.cpu(), ds.cpu()
+        return self.fetch(idx, ds)
 
     def cpu_baseline(self, cores, budget_queries=None):
         from oracle import innr_oracle as orc
@@ -347,7 +359,7 @@ class U8(Workload):
             return ib.batch_knn_u8_many(self.q_host[i % 16].reshape(1, -1), self.shard, self.k)
         dq = self.q_host_t[i % 16].to(self.dev, non_blocking=True)
         idx, sc = self.sk.knn_dev(dq, 1, self.k)
-        return idx.cpu(), sc.cpu()
+        return self.fetch(idx, sc)
 
     def cpu_baseline(self, cores, budget_queries=None):
         from oracle import innr_oracle as orc
