@@ -185,6 +185,28 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
 /* encode_binary (src/binary.rs:133-141): bit i = values[i] > threshold; out_words ceil(n/64) u64 */
 int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words);
 
+/* ---- packed ternary codes: src/ternary.rs (2 bits per value: 01 = +1, 10 = -1; 32 values per u64) -------- */
+/* words: host, n x ceil(dimension/32) u64 (PackedTernary::data()); padding pairs of the last word are masked on upload
+ * (PackedTernary::new, src/ternary.rs:72-79). */
+int innr_cuda_upload_ternary(const uint64_t* words, size_t n, size_t dimension, uint64_t index_base,
+                             innr_cuda_corpus** out);
+/* encode_ternary (src/ternary.rs:163-173: v > t -> +1, v < -t -> -1) of every vector of a device-resident f32 corpus */
+int innr_cuda_ternary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out);
+/* encode_ternary of a flat host array: out_words = ceil(n/32) u64 */
+int innr_cuda_encode_ternary(const float* values, size_t n, float threshold, uint64_t* out_words);
+/* One query against every code. op 0: ternary_dot (:191, query = packed words, i32 result), 1: ternary_hamming (:301,
+ * packed words, u32 result), 2: ternary::asymmetric_dot (:286, query = f32[dimension], sequential unfused f32 sum,
+ * bit-exact). query_dim must equal the corpus dimension. Scores are written as f32 (out_f32_host) and / or, for the
+ * integer ops, as i32 (out_i32_host); either may be NULL. */
+#define INNR_TERNARY_DOT 0
+#define INNR_TERNARY_HAMMING 1
+#define INNR_TERNARY_ASYMMETRIC_DOT 2
+int innr_cuda_ternary_scores_all(const innr_cuda_corpus* c, int op, const void* query, size_t query_dim,
+                                 float* out_f32_host, int32_t* out_i32_host);
+/* top-k of those scores (dot / asymmetric dot descending, Hamming ascending; ties -> lower index), any k <= n */
+int innr_cuda_ternary_topk(const innr_cuda_corpus* c, int op, const void* query, size_t query_dim, size_t k,
+                           uint64_t* out_idx, float* out_score, size_t* out_count);
+
 /* ---- scalar-quantised u8 codes: src/scalar.rs:44-393 --------------------------------------------- */
 /* rows: host, n x d bytes (each QuantizedU8::data() packed contiguously by the shim). */
 int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, float offset,

@@ -69,6 +69,11 @@ SIGNATURES = {
     "innr_cuda_hamming_topk": [vp, u64p, sz, sz, sz, u64p, u32p, szp],
     "innr_cuda_hamming_topk_keys_dev": [vp, vp, sz, sz, vp, vp],
     "innr_cuda_encode_binary": [f32p, sz, f32, u64p],
+    "innr_cuda_upload_ternary": [u64p, sz, sz, u64, handle_p],
+    "innr_cuda_ternary_from_f32": [vp, f32, handle_p],
+    "innr_cuda_encode_ternary": [f32p, sz, f32, u64p],
+    "innr_cuda_ternary_scores_all": [vp, ci, vp, sz, f32p, C.POINTER(C.c_int32)],
+    "innr_cuda_ternary_topk": [vp, ci, vp, sz, sz, u64p, f32p, szp],
     "innr_cuda_upload_u8": [u8p, sz, sz, f32, f32, u64, handle_p],
     "innr_cuda_generate_u8": [u64, u64, sz, sz, f32, f32, u64, handle_p],
     "innr_cuda_quantize_u8": [f32p, sz, f32, f32, u8p],

@@ -17,7 +17,7 @@
 using namespace innr;
 
 struct innr_cuda_corpus {
-  int kind = 0;  // 0 f32 pdx, 1 binary, 2 u8, 3 tokens
+  int kind = 0;  // 0 f32 pdx, 1 binary, 2 u8, 3 tokens, 4 ternary
   int device = 0;
   bool owns = true;
   void* dev = nullptr;
@@ -1303,6 +1303,175 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
     return INNR_OK;
   }
   return u8_keys(c, ctx, dev_queries, n_queries, k, dev_keys, s);
+}
+
+// ------------------------------------------------------------------------------------------ ternary codes
+static int alloc_ternary(DeviceCtx& ctx, size_t n, size_t dim, uint64_t index_base, innr_cuda_corpus** out) {
+  int rc = check_index_range(n, index_base);
+  if (rc) return rc;
+  rc = new_corpus(4, ctx.device, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  c->n = n;
+  c->dim_bits = dim;  // dimension (values)
+  c->d = dim;
+  c->words = (dim + 31) / 32;
+  c->chunks = (c->words + 1) / 2;
+  c->ld = round_up(n, 16);
+  c->index_base = index_base;
+  c->bytes = c->chunks * c->ld * sizeof(uint4);
+  if (c->bytes) {
+    cudaError_t e = cudaMalloc(&c->dev, c->bytes);
+    if (e != cudaSuccess) {
+      delete c;
+      *out = nullptr;
+      return cuda_fail(e, "cudaMalloc(ternary corpus)");
+    }
+  }
+  return INNR_OK;
+}
+static TerView ter_view(const innr_cuda_corpus* c) {
+  return TerView{(const uint4*)c->dev, c->n, c->ld, c->words, c->chunks, c->d, (uint32_t)c->index_base};
+}
+
+int innr_cuda_upload_ternary(const uint64_t* words, size_t n, size_t dimension, uint64_t index_base,
+                             innr_cuda_corpus** out) {
+  if (!out) return fail(INNR_EINVAL, "null out");
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  rc = alloc_ternary(*ctx, n, dimension, index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    if (!words) return fail(INNR_EINVAL, "null words");
+    void* stage = nullptr;
+    CU(cudaMalloc(&stage, n * c->words * sizeof(uint64_t)));
+    cudaError_t e = cudaMemcpyAsync(stage, words, n * c->words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = launch_ternary_pack((const uint64_t*)stage, n, c->words, dimension, (uint4*)c->dev, c->ld, ctx->stream, &g_launches);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return cuda_fail(e, "upload_ternary");
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_ternary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out) {
+  if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(f32_corpus, &ctx);
+  if (rc) return rc;
+  rc = alloc_ternary(*ctx, f32_corpus->n, f32_corpus->d, f32_corpus->index_base, out);
+  if (rc) return rc;
+  innr_cuda_corpus* c = *out;
+  if (c->bytes) {
+    CU(launch_ternary_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, threshold,
+                               (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return INNR_OK;
+}
+
+int innr_cuda_encode_ternary(const float* values, size_t n, float threshold, uint64_t* out_words) {
+  if (n == 0) return INNR_OK;
+  if (!values || !out_words) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  const size_t n_words = (n + 31) / 32;
+  CU(ctx->d_scores.reserve(n * sizeof(float)));
+  CU(ctx->d_aux.reserve(n_words * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx->d_scores.p, values, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_encode_ternary((const float*)ctx->d_scores.p, n, threshold, (uint64_t*)ctx->d_aux.p, ctx->stream, &g_launches));
+  CU(cudaMemcpyAsync(out_words, ctx->d_aux.p, n_words * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return INNR_OK;
+}
+
+// op 0: ternary_dot (query = packed words), 1: ternary_hamming (packed words), 2: ternary::asymmetric_dot (f32 query).
+// Stages the query, runs the scan into d_scores (f32) and optionally d_aux (i32).
+static int ternary_scores_dev(const innr_cuda_corpus* c, DeviceCtx* ctx, int op, const void* query, size_t query_dim,
+                              bool want_i32) {
+  if (op < 0 || op > 2) return fail(INNR_EINVAL, "unknown ternary op");
+  if (query_dim != c->d)  // src/ternary.rs:192-196 / :287 assert_eq!
+    return fail(INNR_EINVAL, op == 0 ? "innr::ternary_dot: dimension mismatch" : "dimension mismatch");
+  CU(ctx->d_scores.reserve(c->n * sizeof(float)));
+  if (want_i32) CU(ctx->d_aux.reserve(c->n * sizeof(int32_t)));
+  if (op == 2) {
+    CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+    CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    const size_t padded = 2 * c->chunks;  // words, zero padded to whole chunks
+    CU(ctx->d_query.reserve(padded * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(ctx->d_query.p, 0, padded * sizeof(uint64_t), ctx->stream));
+    std::vector<uint64_t> w((const uint64_t*)query, (const uint64_t*)query + c->words);
+    const size_t rem = c->d % 32;
+    if (rem && !w.empty()) w.back() &= (1ull << (rem * 2)) - 1;  // PackedTernary::new masks the query's padding too
+    CU(cudaMemcpyAsync(ctx->d_query.p, w.data(), c->words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // w is a stack-owned staging copy
+  }
+  CU(launch_ternary_scores(ter_view(c), op, (const uint64_t*)ctx->d_query.p, (const float*)ctx->d_query.p,
+                           (float*)ctx->d_scores.p, want_i32 ? (int32_t*)ctx->d_aux.p : nullptr, ctx->stream, &g_launches));
+  return INNR_OK;
+}
+
+int innr_cuda_ternary_scores_all(const innr_cuda_corpus* c, int op, const void* query, size_t query_dim,
+                                 float* out_f32_host, int32_t* out_i32_host) {
+  if (!c || c->kind != 4) return fail(INNR_EINVAL, "need a ternary corpus");
+  if (c->n == 0) return INNR_OK;
+  if ((!out_f32_host && !out_i32_host) || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  if (c->d == 0) {  // no dimensions: every score is 0
+    if (query_dim != 0) return fail(INNR_EINVAL, "dimension mismatch");
+    for (size_t i = 0; i < c->n; ++i) {
+      if (out_f32_host) out_f32_host[i] = 0.0f;
+      if (out_i32_host) out_i32_host[i] = 0;
+    }
+    return INNR_OK;
+  }
+  Timed tm(*ctx);
+  rc = ternary_scores_dev(c, ctx, op, query, query_dim, out_i32_host != nullptr && op != 2);
+  if (rc) return rc;
+  tm.stop();
+  if (out_f32_host) CU(cudaMemcpyAsync(out_f32_host, ctx->d_scores.p, c->n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_i32_host && op != 2)
+    CU(cudaMemcpyAsync(out_i32_host, ctx->d_aux.p, c->n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  tm.finish();
+  return INNR_OK;
+}
+
+// top-k over the ternary scores: dot / asymmetric dot descending, Hamming ascending; ties -> lower index (stable sort)
+int innr_cuda_ternary_topk(const innr_cuda_corpus* c, int op, const void* query, size_t query_dim, size_t k,
+                           uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 4) return fail(INNR_EINVAL, "need a ternary corpus");
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0) return INNR_OK;
+  if (!out_idx || !out_score || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional ternary corpus");
+  const size_t kk = k < c->n ? k : c->n;
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  Timed tm(*ctx);
+  rc = ternary_scores_dev(c, ctx, op, query, query_dim, false);
+  if (rc) return rc;
+  CU(launch_topk_from_scores(ctx->d_scores.p, op == 1 ? 0 : 1, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p,
+                             ctx->ws, ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) { decode_keys_f32(keys, kk, op != 1, out_idx, out_score); });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
 }
 
 // ------------------------------------------------------------------------------------------ MaxSim

@@ -132,6 +132,22 @@ cudaError_t launch_encode_binary(const float* dev_values, size_t n, float thresh
 cudaError_t launch_binary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float threshold,
                                    uint4* dev_codes, size_t ld, cudaStream_t s, LaunchCounter* launches);
 
+// ternary codes (ternary.cu): chunk-major layout codes[c * ld + i] (uint4 = 64 two-bit values), chunks = ceil(dim/64)
+struct TerView {
+  const uint4* data;
+  size_t n, ld, words, chunks, dim;
+  uint32_t index_base;
+};
+cudaError_t launch_ternary_pack(const uint64_t* dev_words_rowmajor, size_t n, size_t words, size_t dim, uint4* dev_codes,
+                                size_t ld, cudaStream_t s, LaunchCounter* launches);
+cudaError_t launch_ternary_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size_t d, float threshold, uint4* dev_codes,
+                                    size_t ld, cudaStream_t s, LaunchCounter* launches);
+cudaError_t launch_encode_ternary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words, cudaStream_t s,
+                                  LaunchCounter* launches);
+// op 0 ternary_dot, 1 ternary_hamming (query = packed words), 2 asymmetric_dot (query = f32); scores as f32 and/or i32
+cudaError_t launch_ternary_scores(const TerView& v, int op, const uint64_t* dev_query_words, const float* dev_query,
+                                  float* dev_out_f32, int32_t* dev_out_i32, cudaStream_t s, LaunchCounter* launches);
+
 // u8 codes (u8.cu): chunk-major layout codes[c * ld + i] (uint4 = 16 dims), chunks = ceil(d/16)
 struct U8View {
   const uint4* data;

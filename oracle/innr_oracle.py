@@ -70,6 +70,11 @@ def lib() -> C.CDLL:
             "innr_ref_encode_binary": (None, [_f32p, sz, f32, _u64p]),
             "innr_ref_binary_hamming": (C.c_uint32, [_u64p, _u64p, sz]),
             "innr_ref_binary_dot": (C.c_uint32, [_u64p, _u64p, sz]),
+            "innr_ref_packed_ternary_mask": (None, [_u64p, sz]),
+            "innr_ref_encode_ternary": (None, [_f32p, sz, f32, _u64p]),
+            "innr_ref_ternary_dot": (C.c_int32, [_u64p, _u64p, sz]),
+            "innr_ref_ternary_hamming": (C.c_uint32, [_u64p, _u64p, sz]),
+            "innr_ref_ternary_asymmetric_dot": (C.c_float, [_f32p, _u64p, sz]),
             "innr_ref_binary_jaccard": (C.c_float, [_u64p, _u64p, sz]),
             "innr_ref_hamming_topk": (sz, [_u64p, _u64p, sz, sz, sz, _u64p, _u32p]),
             "innr_ref_qparams_from_range": (None, [f32, f32, _f32p, _f32p]),
@@ -428,6 +433,72 @@ def binary_dot(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:178
 def binary_jaccard(a: PackedBinary, b: PackedBinary) -> float:  # src/binary.rs:198
     assert a.dimension == b.dimension
     return float(lib().innr_ref_binary_jaccard(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
+
+
+class PackedTernary:  # src/ternary.rs:50-157
+    def __init__(self, data, dimension: int):
+        data = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        expect = (dimension + 31) // 32
+        assert data.size == expect, (
+            f"PackedTernary: data length {data.size} doesn't match dimension {dimension} (expected {expect} words)")
+        if data.size:
+            lib().innr_ref_packed_ternary_mask(_p(data, _u64p), dimension)
+        self.data = data
+        self.dimension = dimension
+
+    @classmethod
+    def zeros(cls, dimension):
+        return cls(np.zeros((dimension + 31) // 32, np.uint64), dimension)
+
+    def set(self, idx, val):
+        if idx >= self.dimension:
+            return
+        w, b = idx // 32, (idx % 32) * 2
+        cur = int(self.data[w]) & ~(0b11 << b) & 0xFFFFFFFFFFFFFFFF
+        bits = 0b01 if val == 1 else (0b10 if val == -1 else 0)
+        self.data[w] = np.uint64(cur | (bits << b))
+
+    def get(self, idx):
+        if idx >= self.dimension:
+            return 0
+        bits = (int(self.data[idx // 32]) >> ((idx % 32) * 2)) & 0b11
+        return 1 if bits == 0b01 else (-1 if bits == 0b10 else 0)
+
+    def nnz(self):
+        return sum(1 for i in range(self.dimension) if self.get(i) != 0)
+
+    def memory_bytes(self):
+        return self.data.size * 8
+
+
+def encode_ternary(values, threshold: float) -> PackedTernary:  # src/ternary.rs:163
+    v = _f32(values)
+    out = np.zeros((v.size + 31) // 32, np.uint64)
+    if v.size:
+        lib().innr_ref_encode_ternary(_p(v, _f32p), v.size, C.c_float(threshold), _p(out, _u64p))
+    return PackedTernary(out, v.size)
+
+
+def ternary_dot(a: PackedTernary, b: PackedTernary) -> int:  # src/ternary.rs:191
+    assert a.dimension == b.dimension, f"innr::ternary_dot: dimension mismatch ({a.dimension} vs {b.dimension})"
+    return int(lib().innr_ref_ternary_dot(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
+
+
+def ternary_hamming(a: PackedTernary, b: PackedTernary) -> int:  # src/ternary.rs:301
+    assert a.dimension == b.dimension
+    return int(lib().innr_ref_ternary_hamming(_p(a.data, _u64p), _p(b.data, _u64p), a.data.size))
+
+
+def ternary_asymmetric_dot(query, t: PackedTernary) -> float:  # src/ternary.rs:286 (ternary::asymmetric_dot)
+    q = _f32(query)
+    assert q.size == t.dimension
+    return float(lib().innr_ref_ternary_asymmetric_dot(_p(q, _f32p), _p(t.data, _u64p), t.dimension))
+
+
+def ternary_sparsity(v: PackedTernary) -> float:  # src/ternary.rs:327
+    if v.dimension == 0:
+        return 0.0
+    return float(np.float32(1.0) - np.float32(v.nnz()) / np.float32(v.dimension))
 
 
 def hamming_topk(query_words, codes, k):

@@ -899,6 +899,54 @@ float innr_ref_binary_jaccard(const uint64_t* a, const uint64_t* b, size_t words
   for (size_t w = 0; w < words; ++w) uni += (uint32_t)__builtin_popcountll(a[w] | b[w]);
   return uni == 0 ? 1.0f : (float)inter / (float)uni;  // intersection as f32 / union as f32
 }
+// ---- ternary (src/ternary.rs) ---------------------------------------------------------------
+void innr_ref_packed_ternary_mask(uint64_t* words, size_t dimension) {  // PackedTernary::new :72-79
+  const size_t rem = dimension % 32;
+  const size_t n = (dimension + 31) / 32;
+  if (rem != 0 && n) words[n - 1] &= (1ULL << (rem * 2)) - 1;
+}
+void innr_ref_encode_ternary(const float* v, size_t n, float threshold, uint64_t* out_words) {  // :163-173
+  const size_t words = (n + 31) / 32;
+  for (size_t w = 0; w < words; ++w) out_words[w] = 0;
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t bits = 0;
+    if (v[i] > threshold) bits = 1;        // set(i, 1)  -> 0b01
+    else if (v[i] < -threshold) bits = 2;  // set(i, -1) -> 0b10
+    out_words[i / 32] |= bits << ((i % 32) * 2);
+  }
+}
+static const uint64_t T_ODD = 0x5555555555555555ULL, T_EVEN = 0xAAAAAAAAAAAAAAAAULL;
+int32_t innr_ref_ternary_dot(const uint64_t* a, const uint64_t* b, size_t words) {  // :191-281 (popcnt path == portable)
+  int64_t same = 0, diff = 0;
+  for (size_t w = 0; w < words; ++w) {
+    const uint64_t wa = a[w], wb = b[w];
+    const uint64_t pos_a = wa & ~((wa & T_EVEN) >> 1) & T_ODD, pos_b = wb & ~((wb & T_EVEN) >> 1) & T_ODD;
+    const uint64_t neg_a = ~wa & ((wa & T_EVEN) >> 1) & T_ODD, neg_b = ~wb & ((wb & T_EVEN) >> 1) & T_ODD;
+    same += __builtin_popcountll((pos_a & pos_b) | (neg_a & neg_b));
+    diff += __builtin_popcountll((pos_a & neg_b) | (neg_a & pos_b));
+  }
+  return (int32_t)(same - diff);
+}
+uint32_t innr_ref_ternary_hamming(const uint64_t* a, const uint64_t* b, size_t words) {  // :301-324
+  uint32_t d = 0;
+  for (size_t w = 0; w < words; ++w) {
+    const uint64_t wa = a[w], wb = b[w];
+    const uint64_t nz_a = (wa & T_ODD) | ((wa & T_EVEN) >> 1), nz_b = (wb & T_ODD) | ((wb & T_EVEN) >> 1);
+    const uint64_t x = wa ^ wb;
+    const uint64_t df = (x & T_ODD) | ((x & T_EVEN) >> 1);
+    d += (uint32_t)__builtin_popcountll(df & nz_a & nz_b);
+  }
+  return d;
+}
+float innr_ref_ternary_asymmetric_dot(const float* q, const uint64_t* t, size_t dimension) {  // :286-296
+  float sum = 0.0f;
+  for (size_t i = 0; i < dimension; ++i) {
+    const uint64_t bits = (t[i / 32] >> ((i % 32) * 2)) & 3;
+    const float tv = bits == 1 ? 1.0f : (bits == 2 ? -1.0f : 0.0f);  // ternary.get(i) as f32
+    sum += q[i] * tv;                                                // unfused (-ffp-contract=off)
+  }
+  return sum;
+}
 size_t innr_ref_hamming_topk(const uint64_t* q, const uint64_t* codes, size_t n, size_t words, size_t k,
                              uint64_t* out_idx, uint32_t* out_dist) {
   if (n == 0 || k == 0) return 0;

@@ -123,6 +123,12 @@ void innr_ref_encode_binary(const float* v, size_t n, float threshold, uint64_t*
 uint32_t innr_ref_binary_hamming(const uint64_t* a, const uint64_t* b, size_t words);         /* :154-165 */
 uint32_t innr_ref_binary_dot(const uint64_t* a, const uint64_t* b, size_t words);             /* :178-185 */
 float innr_ref_binary_jaccard(const uint64_t* a, const uint64_t* b, size_t words);            /* :198-213 */
+/* ---- src/ternary.rs: 2 bits per value (01 = +1, 10 = -1), 32 values per u64 ---- */
+void innr_ref_packed_ternary_mask(uint64_t* words, size_t dimension);                            /* :72-79 */
+void innr_ref_encode_ternary(const float* v, size_t n, float threshold, uint64_t* out_words);   /* :163-173 */
+int32_t innr_ref_ternary_dot(const uint64_t* a, const uint64_t* b, size_t words);                /* :191-281 */
+uint32_t innr_ref_ternary_hamming(const uint64_t* a, const uint64_t* b, size_t words);           /* :301-324 */
+float innr_ref_ternary_asymmetric_dot(const float* q, const uint64_t* t, size_t dimension);      /* :286-296 */
 /* caller composition examples/binary_demo.rs:174-180: all distances, stable sort_by_key, take k */
 size_t innr_ref_hamming_topk(const uint64_t* q, const uint64_t* codes, size_t n, size_t words, size_t k,
                              uint64_t* out_idx, uint32_t* out_dist);

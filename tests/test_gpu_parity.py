@@ -566,6 +566,43 @@ def test_hamming_query_batches_share_a_pass(ib, oracle, dim, nq):
         assert np.array_equal(gi, wi) and np.array_equal(gd, wd), (dim, nq, k)
 
 
+# ------------------------------------------------------------------------------------------------ ternary
+@pytest.mark.parametrize("dim", [1, 31, 32, 33, 63, 64, 65, 128, 200, 768])
+def test_ternary_scans_exact(ib, oracle, dim):
+    """ternary_dot / ternary_hamming (integer-exact) and ternary::asymmetric_dot (sequential unfused f32 sum, bit-exact)
+    of one query against a corpus; top-k in the reference's stable order; encodings derived on the device."""
+    n = 3001
+    rng = np.random.default_rng(dim)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    rows[7] = 0.0
+    codes_o = [oracle.encode_ternary(rows[i], 0.4) for i in range(n)]
+    words = np.stack([c.data for c in codes_o])
+    corpus = ib.TernaryCorpus.from_words(words, n, dim)
+    derived = ib.TernaryCorpus.from_f32(ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, dim), 0.4)
+    qf = rng.standard_normal(dim).astype(np.float32)
+    if dim > 2:
+        qf[1] = -0.0
+    qg, qo = ib.encode_ternary(qf, 0.4), oracle.encode_ternary(qf, 0.4)
+    assert np.array_equal(qg.data, qo.data)
+    for corp in (corpus, derived):
+        d = ib.ternary_scores_all("dot", qg, corp)
+        h = ib.ternary_scores_all("hamming", qg, corp)
+        a = ib.ternary_scores_all("asymmetric_dot", qf, corp)
+        for i in range(0, n, 7):
+            assert int(d[i]) == oracle.ternary_dot(qo, codes_o[i]), (dim, i)
+            assert int(h[i]) == oracle.ternary_hamming(qo, codes_o[i]), (dim, i)
+            assert np.float32(a[i]).tobytes() == np.float32(oracle.ternary_asymmetric_dot(qf, codes_o[i])).tobytes(), (dim, i)
+    want_d = np.array([oracle.ternary_dot(qo, c) for c in codes_o])
+    want_h = np.array([oracle.ternary_hamming(qo, c) for c in codes_o])
+    for k in (1, 10, 300):
+        idx, sc = ib.ternary_topk("dot", qg, corpus, k)
+        order = sorted(range(n), key=lambda i: (-want_d[i], i))[:k]
+        assert [int(i) for i in idx] == order and [int(s) for s in sc] == [int(want_d[i]) for i in order]
+        idx, sc = ib.ternary_topk("hamming", qg, corpus, k)
+        order = sorted(range(n), key=lambda i: (want_h[i], i))[:k]
+        assert [int(i) for i in idx] == order and [int(s) for s in sc] == [int(want_h[i]) for i in order]
+
+
 # ------------------------------------------------------------------------------------------------ u8
 @pytest.mark.parametrize("d", [1, 8, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 100, 128, 384, 777])
 def test_u8_bit_exact(ib, oracle, d):
