@@ -270,6 +270,52 @@ __device__ __forceinline__ void block_finish(WarpList<R> (&lists)[QB], int nq_va
   const unsigned n_groups = (gridDim.x + FINISH_GROUP - 1) / FINISH_GROUP;
   const unsigned group = blockIdx.x / FINISH_GROUP;
   const unsigned group_size = min((unsigned)FINISH_GROUP, gridDim.x - group * FINISH_GROUP);
+  // Multi-query kernels (QB > 1, QB <= warps): ONE warp per query at every level instead of the whole CTA on one query
+  // after the other -- every warp parks its QB lists in shared memory (QB * warps * k keys, sized by the launcher),
+  // warp q merges the lists of query q; the group and top levels are merged the same way. A quarter of the
+  // synchronisations and no serial loop over queries (what the latency of small launches such as C1 is made of).
+  if (QB > 1) {
+#pragma unroll
+    for (int q = 0; q < QB; ++q)
+      if (q < nq_valid) lists[q].store(smem_keys + ((size_t)q * n_warps + warp) * k, k, lane);
+    __syncthreads();
+    if (warp < nq_valid) {
+      WarpList<R> acc;
+      acc.init();
+      warp_merge_lists<R, false>(acc, smem_keys + (size_t)warp * n_warps * k, 0, 1, n_warps, (size_t)k, k, lane);
+      acc.store(partials + ((size_t)blockIdx.x * nq_valid + warp) * k, k, lane);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = (atomicAdd(&tickets[1 + group], 1u) == group_size - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (warp < nq_valid) {  // last CTA of this group
+      WarpList<R> acc;
+      acc.init();
+      warp_merge_lists<R, true>(acc, partials + ((size_t)group * FINISH_GROUP * nq_valid + warp) * k, 0, 1, (int)group_size,
+                                (size_t)nq_valid * k, k, lane);
+      acc.store((n_groups == 1 ? out_keys + (size_t)warp * k : group_partials + ((size_t)group * nq_valid + warp) * k), k,
+                lane);
+    }
+    if (threadIdx.x == 0) tickets[1 + group] = 0u;  // ready for the next launch
+    if (n_groups == 1) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_flag = (atomicAdd(&tickets[0], 1u) == n_groups - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_flag) return;
+    __threadfence();
+    if (warp < nq_valid) {  // last group
+      WarpList<R> acc;
+      acc.init();
+      warp_merge_lists<R, true>(acc, group_partials + (size_t)warp * k, 0, 1, (int)n_groups, (size_t)nq_valid * k, k, lane);
+      acc.store(out_keys + (size_t)warp * k, k, lane);
+    }
+    if (threadIdx.x == 0) tickets[0] = 0u;
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < QB; ++q) {
     if (q >= nq_valid) break;

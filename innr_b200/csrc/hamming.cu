@@ -436,7 +436,7 @@ cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_word
   size_t q0 = 0;
   // batches: groups of 4 queries share one pass over the codes
   const size_t qb = k <= 32 ? ham_qb<1>() : ham_qb<4>();
-  const size_t multi_smem = qb * v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
+  const size_t multi_smem = qb * v.chunks * sizeof(uint4) + qb * (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
   while (nq - q0 >= 2 && multi_smem <= 48 * 1024) {
     const size_t take = nq - q0 < qb ? nq - q0 : qb;
     HamArgs a = make_args(v, dev_query_words + q0 * 2 * v.chunks);

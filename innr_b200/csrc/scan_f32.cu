@@ -301,7 +301,7 @@ size_t scan_smem_bytes(size_t d, int qb, int k, bool knn) {
   const int U = (qb == 1) ? 8 : 4;
   size_t d_pad = (d + U - 1) / U * U;
   size_t b = d_pad * qb * sizeof(float) + ((qb + 3) & ~3) * sizeof(float);
-  if (knn) b += (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t);
+  if (knn) b += (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t) * qb;  // QB > 1: every warp parks QB lists (block_finish)
   return b;
 }
 

@@ -640,7 +640,7 @@ cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, 
   // query batches: two queries per pass
   const size_t d_pad = (v.d + 31) / 32 * 32 + 32;
   const size_t pair_smem = (size_t)U8_PAIR_STAGES * U8_STAGE_BYTES + (2 * d_pad + 4) * sizeof(float) + sizeof(U8PairShared) +
-                           (size_t)(U8_CTA / 32) * k * sizeof(uint64_t);
+                           2 * (size_t)(U8_CTA / 32) * k * sizeof(uint64_t);
   for (; nq - q0 >= 2 && pair_smem <= 227 * 1024; q0 += 2) {
     U8Args a = make_args(v, dev_queries + q0 * v.d);
     a.query_b = dev_queries + (q0 + 1) * v.d;
