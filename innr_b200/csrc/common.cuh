@@ -174,9 +174,56 @@ struct WarpList {
       v[r] = (cur < x) ? cur : (prev_lt ? x : up);
     }
   }
+  // bitonic clean-up of a list that holds the 32*R smallest keys as a bitonic sequence: register-level
+  // compare-exchange for strides >= 32, shfl_xor for the rest
+  __device__ __forceinline__ void bitonic_cleanup(int lane) {
+#pragma unroll
+    for (int m = R / 2; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if ((r & m) == 0) {
+          const uint64_t lo = v[r] < v[r + m] ? v[r] : v[r + m];
+          const uint64_t hi = v[r] < v[r + m] ? v[r + m] : v[r];
+          v[r] = lo;
+          v[r + m] = hi;
+        }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t o = shfl_xor_u64(v[r], s);
+        const bool take_max = (lane & s) != 0;
+        v[r] = ((v[r] < o) != take_max) ? v[r] : o;
+      }
+    }
+  }
+  // insert up to 32 keys at once (one per lane, KEY_SENTINEL = none): sort them across the lanes (bitonic network, 15
+  // steps), fold them into the tail of the list (C[p] = min(A[p], B[N-1-p]) keeps the N smallest as a bitonic sequence)
+  // and clean up. ~280 instructions whatever the count, against ~60 per key one at a time (R = 4): the early phase of a
+  // scan, when most of a ballot still beats the threshold, is where a warp's selection time goes.
+  __device__ __forceinline__ void insert_batch(uint64_t x, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const uint64_t o = shfl_xor_u64(x, stride);
+        const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+        x = ((x < o) == keep_min) ? x : o;
+      }
+    }
+    const uint64_t rev = shfl_u64(x, 31 - lane);  // B[N-1-p] for the last register of the list
+    v[R - 1] = rev < v[R - 1] ? rev : v[R - 1];
+    bitonic_cleanup(lane);
+  }
   // offer one candidate per lane; thr = current k-th key (uniform), updated in place
   __device__ __forceinline__ void offer(uint64_t key, bool valid, uint64_t& thr, int k, int lane) {
     unsigned m = __ballot_sync(FULL_MASK, valid && key < thr);
+    if (__popc(m) >= (R == 1 ? 10 : 6)) {  // warp-uniform
+      insert_batch((valid && key < thr) ? key : KEY_SENTINEL, lane);
+      thr = at(k - 1);
+      return;
+    }
     while (m) {
       int src = __ffs(m) - 1;
       uint64_t x = shfl_u64(key, src);
@@ -200,26 +247,7 @@ struct WarpList {
       if (j < len) b = GLOBAL ? (uint64_t)__ldcg((const unsigned long long*)(src + j)) : src[j];
       v[r] = b < v[r] ? b : v[r];
     }
-#pragma unroll
-    for (int m = R / 2; m >= 1; m >>= 1) {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if ((r & m) == 0) {
-          const uint64_t lo = v[r] < v[r + m] ? v[r] : v[r + m];
-          const uint64_t hi = v[r] < v[r + m] ? v[r + m] : v[r];
-          v[r] = lo;
-          v[r + m] = hi;
-        }
-    }
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint64_t o = shfl_xor_u64(v[r], s);
-        const bool take_max = (lane & s) != 0;
-        v[r] = ((v[r] < o) != take_max) ? v[r] : o;
-      }
-    }
+    bitonic_cleanup(lane);
   }
   // write the first k keys to dst[0..k)
   __device__ __forceinline__ void store(uint64_t* dst, int k, int lane) const {
