@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           progressed = true;
         }
       }
-      if (!progressed) __nanosleep(20);
+      if (!progressed) __nanosleep(64);
     }
   } else if (warp >= 4) {
     // =========================== converters: Xlo -> TMEM ===========================
@@ -362,20 +362,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const uint8_t* pbase = base + p * PANEL_BYTES;
-        float4 v[8];
+        ulonglong2 v[8];  // two packed f32 pairs per 16-byte chunk: the pairs stay in 64-bit registers end to end
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(pbase + ((c ^ (row & 7)) << 4));
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const ulonglong2*>(pbase + ((c ^ (row & 7)) << 4));
         if (p == P - 1) mbar_arrive(&st->empty[s]);  // this thread has read its whole row: 1 of 129
         uint32_t lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          float x0 = v[c].x, x1 = v[c].y, x2 = v[c].z, x3 = v[c].w;
-          sub2(x0, x1, __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u));
-          sub2(x2, x3, __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u), __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u));
-          lo[4 * c + 0] = __float_as_uint(x0);
-          lo[4 * c + 1] = __float_as_uint(x1);
-          lo[4 * c + 2] = __float_as_uint(x2);
-          lo[4 * c + 3] = __float_as_uint(x3);
+          const uint64_t l01 = sub2_rn(v[c].x, v[c].x & 0xFFFFE000FFFFE000ull);  // x - trunc_tf32(x), two lanes
+          const uint64_t l23 = sub2_rn(v[c].y, v[c].y & 0xFFFFE000FFFFE000ull);
+          lo[4 * c + 0] = (uint32_t)l01;
+          lo[4 * c + 1] = (uint32_t)(l01 >> 32);
+          lo[4 * c + 2] = (uint32_t)l23;
+          lo[4 * c + 3] = (uint32_t)(l23 >> 32);
         }
         tmem_st_32x32b_x32(tdst + 32 * p, lo);
       }
@@ -389,7 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     unsigned cur_doc = st->s_doc[warp];
     unsigned long long cur_end = 0;  // end token of cur_doc; 0 forces the first lookup
     bool have_doc = false;
-    float carry[G][NQ];  // running max of query token 32 g + j over the current document (all lanes hold all of them)
+    float carry[G][NQ];  // per-lane running max of query token 32 g + j over this lane's tokens of the current document
 #pragma unroll
     for (int gq = 0; gq < G; ++gq)
 #pragma unroll
@@ -463,13 +462,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
             }
           }
           const unsigned long long seg_end = cur_end < c1 ? cur_end : c1;
+          // the running maxima stay per lane (one FMNMX per score); lanes are only combined when the document ends
           if (pos == c0 && seg_end == c0 + CHUNK) {  // the whole chunk lies inside one document
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], redux_max(sc[j]));
+            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], sc[j]);
           } else {
             const bool in = g >= pos && g < seg_end;
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], redux_max(in ? sc[j] : -INFINITY));
+            for (int j = 0; j < NQ; ++j) carry[gq][j] = fmaxf(carry[gq][j], in ? sc[j] : -INFINITY);
           }
           if (seg_end == cur_end) {  // the document ends here: sum of the maxima in query order from 0.0 (x86_64.rs:139)
             const bool split = G > 1 && a.split;
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
             float total = (G > 1 && gq > 0 && !split) ? part[seg] : 0.0f;
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
-              if (j < lim) total += carry[gq][j];
+              if (j < lim) total += redux_max(carry[gq][j]);
               carry[gq][j] = -INFINITY;
             }
             if (split) {
