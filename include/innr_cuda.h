@@ -130,6 +130,16 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
  * ascending index order. Writes min(*out_count, capacity) pairs; *out_count is the number of survivors. */
 int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* query, size_t query_len, float threshold,
                                        uint64_t* out_idx, float* out_dist, size_t capacity, size_t* out_count);
+/* batch_dimension_variance (src/batch.rs:572-592): out[dd] = variance of dimension row dd over the batch's vectors (mean
+ * and sum of squared deviations as the reference's sequential f32 sums, bit for bit); zeros when the batch holds <= 1
+ * vector. out_len must equal the batch dimension. Computed once per corpus handle (the corpus is immutable). */
+int innr_cuda_batch_dimension_variance(const innr_cuda_corpus* c, float* out, size_t out_len);
+/* batch_knn_reordered (src/batch.rs:621-659): exact L2 kNN whose distances are accumulated over the dimensions in
+ * decreasing-variance order (variance_order :599-603: stable under f32::total_cmp), then the reference's stable
+ * ascending sort -- ties -> lower index; scores bit-identical to the reference's (they differ from batch_knn's in the
+ * last bits because the summation order differs). k clamped to N; N == 0 or k == 0 -> empty. */
+int innr_cuda_batch_knn_reordered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                  uint64_t* out_idx, float* out_score, size_t* out_count);
 /* Re-rank stage of the reference's documented two-stage retrieval (src/scalar.rs:366-368 "Re-rank top candidates with
  * exact batch_knn_dot", examples/binary_demo.rs:235-237 "binary retrieves top-1000 candidates, then rerank"): the exact
  * batch_knn (L2) / batch_knn_dot / batch_knn_cosine result over the sub-batch formed by `candidates` (distinct global

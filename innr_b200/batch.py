@@ -203,6 +203,50 @@ def batch_cosine(query, batch, norms) -> np.ndarray:  # src/batch.rs:690
     return out
 
 
+def _into(out: list, values) -> None:
+    """The reference's `_into` contract: the caller's buffer is cleared, then filled (resized to N)."""
+    out.clear()
+    out.extend(float(x) for x in values)
+
+
+def batch_l2_squared_into(query, batch, out: list) -> None:  # src/batch.rs:250
+    _into(out, batch_l2_squared(query, batch))
+
+
+def batch_dot_into(query, batch, out: list) -> None:  # src/batch.rs:284
+    _into(out, batch_dot(query, batch))
+
+
+def batch_norms_into(batch, out: list) -> None:  # src/batch.rs:672
+    _into(out, batch_norms(batch))
+
+
+def batch_cosine_into(query, batch, norms, out: list) -> None:  # src/batch.rs:705
+    _into(out, batch_cosine(query, batch, norms))
+
+
+def batch_dimension_variance(batch) -> np.ndarray:  # src/batch.rs:572
+    """Variance of every dimension row (the reference's sequential sums, bit for bit); zeros for <= 1 vector."""
+    dev = _dev(batch)
+    out = np.zeros(dev.dimension, np.float32)
+    L.call("innr_cuda_batch_dimension_variance", dev.h, _ptr(out, L.f32p), out.size)
+    return out
+
+
+def batch_knn_reordered(query, batch, k: int) -> BatchKnnResult:  # src/batch.rs:621
+    """Exact L2 kNN with the dimensions accumulated in decreasing-variance order; ties -> lower index."""
+    dev = _dev(batch)
+    q = _f32(query).reshape(-1)
+    assert q.size == dev.dimension, "query.len() != batch.dimension"
+    kk = max(min(k, dev.num_vectors), 1)
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_batch_knn_reordered", dev.h, _ptr(q, L.f32p), q.size, k, _ptr(idx, L.u64p), _ptr(sc, L.f32p),
+           C.byref(cnt))
+    return BatchKnnResult(idx[:cnt.value], sc[:cnt.value])
+
+
 def batch_knn_many(metric: str, queries, batch, k: int):
     """n_queries x d queries in one call (shares corpus passes between queries). Returns (idx, scores) arrays
     of shape (n_queries, min(k, N))."""

@@ -38,6 +38,11 @@ struct innr_cuda_corpus {
   float* dev_norms = nullptr;
   void* dev_xh = nullptr;
   CUtensorMap tm_xh;
+  // f32 PDX: per-dimension variances and the order batch_knn_reordered walks the rows in, computed on first use (the
+  // corpus is immutable, so recomputing them per call as the reference does would give the same values)
+  bool var_ready = false;
+  std::vector<float> variances;
+  uint32_t* dev_order = nullptr;
 };
 
 namespace {
@@ -453,6 +458,7 @@ int innr_cuda_free(innr_cuda_corpus* c) {
   if (c->dev_offsets) cudaFree(c->dev_offsets);
   if (c->dev_norms) cudaFree(c->dev_norms);
   if (c->dev_xh) cudaFree(c->dev_xh);
+  if (c->dev_order) cudaFree(c->dev_order);
   delete c;
   return INNR_OK;
 }
@@ -643,6 +649,89 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
     for (size_t q = 0; q < n_queries; ++q)
       decode_keys_f32(keys + q * kk, kk, metric != INNR_METRIC_L2, out_idx + q * k, out_score + q * k);
   });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
+// batch_dimension_variance + variance_order (src/batch.rs:572-603) of a resident corpus, cached in the handle.
+static int ensure_variance_order(innr_cuda_corpus* c, DeviceCtx* ctx) {
+  if (c->var_ready) return INNR_OK;
+  std::vector<float> var(c->d, 0.0f);
+  if (c->d) {
+    CU(ctx->d_aux.reserve(c->d * sizeof(float)));
+    CU(launch_dimension_variance(pdx_view(c), (float*)ctx->d_aux.p, ctx->stream, &g_launches));
+    CU(cudaMemcpyAsync(var.data(), ctx->d_aux.p, c->d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // order.sort_by(|&a, &b| variances[b].total_cmp(&variances[a])): stable, decreasing under f32::total_cmp
+    auto ordered = [](float f) {
+      uint32_t b;
+      std::memcpy(&b, &f, 4);
+      return (int32_t)(b ^ ((uint32_t)((int32_t)b >> 31) >> 1));
+    };
+    std::vector<uint32_t> order(c->d);
+    for (size_t i = 0; i < c->d; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ordered(var[b]) < ordered(var[a]); });
+    if (!c->dev_order) CU(cudaMalloc((void**)&c->dev_order, c->d * sizeof(uint32_t)));
+    CU(cudaMemcpyAsync(c->dev_order, order.data(), c->d * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  c->variances.swap(var);
+  c->var_ready = true;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_dimension_variance(const innr_cuda_corpus* c, float* out, size_t out_len) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (out_len != c->d) return fail(INNR_EINVAL, "out_len != batch.dimension");
+  if (c->d == 0) return INNR_OK;
+  if (!out) return fail(INNR_EINVAL, "null argument");
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  rc = ensure_variance_order(const_cast<innr_cuda_corpus*>(c), ctx);
+  if (rc) return rc;
+  std::memcpy(out, c->variances.data(), c->d * sizeof(float));
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_reordered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                  uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:622
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0) return INNR_OK;                                             // src/batch.rs:624-629
+  if (!out_idx || !out_score || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < c->n ? k : c->n;
+  if (c->d == 0) {  // no row is ever added: every distance is 0.0 and the stable sort keeps index order
+    for (size_t j = 0; j < kk; ++j) { out_idx[j] = c->index_base + j; out_score[j] = 0.0f; }
+    if (out_count) *out_count = kk;
+    return INNR_OK;
+  }
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  rc = ensure_variance_order(const_cast<innr_cuda_corpus*>(c), ctx);
+  if (rc) return rc;
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  Timed tm(*ctx);
+  const PdxView v = pdx_view(c);
+  if (kk <= MAX_FUSED_K) {
+    CU(launch_pdx_knn_reordered(v, (const float*)ctx->d_query.p, c->dev_order, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                                ctx->stream, &g_launches));
+  } else {
+    CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+    CU(launch_pdx_scores(v, PDX_L2_PERM, (const float*)ctx->d_query.p, nullptr, (float*)ctx->d_scores.p, ctx->ws, ctx->stream,
+                         &g_launches, 0.0f, c->dev_order));
+    rc = big_k_from_scores(ctx, ctx->d_scores.p, 0, c->n, c->index_base, kk, (uint64_t*)ctx->d_keys.p, ctx->stream);
+    if (rc) return rc;
+  }
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) { decode_keys_f32(keys, kk, false, out_idx, out_score); });
   if (rc) return rc;
   if (out_count) *out_count = kk;
   return INNR_OK;

@@ -20,6 +20,7 @@ enum PdxMode : int {
   PDX_NORMS = 3,        // batch_norms_into          src/batch.rs:672-686
   PDX_COSINE_NORMS = 4, // batch_cosine_into with caller-supplied norms  src/batch.rs:705-728
   PDX_L2_PRUNE = 5,     // batch_l2_squared_pruning  src/batch.rs:320-365 (scores mode: pruned vectors -> -1.0)
+  PDX_L2_PERM = 6,      // batch_knn_reordered  src/batch.rs:621-659 (L2 summed over a permutation of the dimension rows)
 };
 
 struct Workspace {
@@ -57,7 +58,15 @@ cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, co
                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 // full score vectors: out[q * ld + i] (device). dev_norms only for PDX_COSINE_NORMS; threshold only for PDX_L2_PRUNE.
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold = 0.0f);
+                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold = 0.0f,
+                              const uint32_t* dev_perm = nullptr);
+// batch_knn_reordered (src/batch.rs:621-659): L2 distances accumulated over the dimension rows in the order dev_perm[0..d)
+// (a permutation of 0..d, device), ascending keys with ties -> lower index (the reference's stable sort); k <= 128.
+cudaError_t launch_pdx_knn_reordered(const PdxView& v, const float* dev_query, const uint32_t* dev_perm, size_t k,
+                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
+// batch_dimension_variance (src/batch.rs:572-592): out[dd] = variance of dimension row dd over the n vectors, each row's
+// two sums in the reference's sequential order (one warp per row; the chain of n dependent adds bounds it).
+cudaError_t launch_dimension_variance(const PdxView& v, float* dev_out, cudaStream_t s, LaunchCounter* launches);
 // stream compaction of a pruned distance vector (entries == -1.0 are dropped): ascending index order.
 // Pass 1 (count) fills dev_block_offsets[n_blocks + 1] (exclusive prefix, last = total); pass 2 scatters.
 size_t compact_blocks(size_t n);

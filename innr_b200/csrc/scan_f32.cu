@@ -47,13 +47,14 @@ struct PdxArgs {
   float* scores_out;      // scores mode: out[q * ld + i]
   const float* norms_in;  // PDX_COSINE_NORMS
   const uint32_t* mask;   // MASKED: bit i set = vector i passes the predicate (batch_knn_filtered)
+  const uint32_t* perm;   // PDX_L2_PERM: the order in which the dimension rows are accumulated (batch_knn_reordered)
   float threshold;        // PDX_L2_PRUNE
   float one;              // 1.0f, opaque to the compiler (see add2_unfusable)
 };
 
 template <int MODE>
 __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
-  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE) {
+  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE || MODE == PDX_L2_PERM) {
     float diff = __fsub_rn(q, v);                 // let diff = q_d - v_d;
     acc = __fadd_rn(acc, __fmul_rn(diff, diff));  // *dist += diff * diff;
   } else {
@@ -64,7 +65,7 @@ __device__ __forceinline__ void accumulate(float q, float v, float& acc) {
 // the same for two vectors at once (acc, v: packed pairs; q2 = {q, q}): unfused mul + add per lane, bit-identical
 template <int MODE>
 __device__ __forceinline__ void accumulate2(uint64_t q2, uint64_t v2, uint64_t& acc2, uint64_t one2) {
-  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE) {
+  if (MODE == PDX_L2 || MODE == PDX_L2_PRUNE || MODE == PDX_L2_PERM) {
     const uint64_t diff = sub2_rn(q2, v2);
     acc2 = add2_unfusable(mul2_rn(diff, diff), acc2, one2);
   } else {
@@ -75,6 +76,8 @@ __device__ __forceinline__ void accumulate2(uint64_t q2, uint64_t v2, uint64_t& 
 template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
 __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_in) {
   static_assert(MODE != PDX_L2_PRUNE || (QB == 1 && !KNN), "pruning is a single-query scores scan");
+  static_assert(MODE != PDX_L2_PERM || (QB == 1 && !MASKED), "the reordered scan is a single-query scan");
+  constexpr bool PERM = (MODE == PDX_L2_PERM);
   constexpr bool NEED_SS = (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS);
   constexpr bool NEED_DOT = (MODE != PDX_NORMS);
   constexpr int U = (QB == 1) ? 8 : 4;  // dimension rows in flight per thread
@@ -84,7 +87,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
   const unsigned d_pad = (a_in.d + U - 1) / U * U;
   float* sq = reinterpret_cast<float*>(smem_raw);
   float* s_qn = sq + (size_t)d_pad * QB;
-  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(s_qn + ((QB + 3) & ~3));
+  unsigned* s_perm = reinterpret_cast<unsigned*>(s_qn + ((QB + 3) & ~3));  // PERM: d_pad row indices (d_pad % 8 == 0)
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(s_perm + (PERM ? d_pad : 0u));
 
   const int lane = threadIdx.x & 31;
 
@@ -104,7 +108,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
   if (NEED_DOT) {
     for (unsigned idx = threadIdx.x; idx < d_pad * QB; idx += blockDim.x) {
       unsigned dd = idx / QB, q = idx % QB;
-      sq[idx] = (dd < a.d && (int)q < a.nq_valid) ? a.queries[(size_t)q * a.d + dd] : 0.0f;
+      if (PERM) {  // step j of the reordered scan pairs query[order[j]] with row order[j]
+        const unsigned row = dd < a.d ? a.perm[dd] : 0u;
+        s_perm[dd] = row;
+        sq[idx] = dd < a.d ? a.queries[row] : 0.0f;
+      } else {
+        sq[idx] = (dd < a.d && (int)q < a.nq_valid) ? a.queries[(size_t)q * a.d + dd] : 0.0f;
+      }
     }
   }
   __syncthreads();
@@ -192,8 +202,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
       for (; dd + U <= a.d; dd += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(p + (size_t)u * a.ld);
-        p += (size_t)U * a.ld;
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(PERM ? p + (size_t)s_perm[dd + u] * a.ld : p + (size_t)u * a.ld);
+        if (!PERM) p += (size_t)U * a.ld;
 #pragma unroll
         for (int u = 0; u < U; ++u) step(v[u], dd + u);
         if (MODE == PDX_L2_PRUNE) {  // every vector this warp owns in the tile is pruned: stop reading its rows
@@ -202,8 +212,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
         }
       }
       for (; dd < a.d; ++dd) {  // D % U tail
-        const float4 v = ldg_stream_f4(p);
-        p += a.ld;
+        const float4 v = ldg_stream_f4(PERM ? p + (size_t)s_perm[dd] * a.ld : p);
+        if (!PERM) p += a.ld;
         step(v, dd);
       }
     }
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
 #pragma unroll
           for (int j = 0; j < VPT; ++j) {
             const unsigned i = i0 + j;
-            const uint64_t key = (MODE == PDX_L2) ? make_key_asc(s[j], a.index_base + i)
+            const uint64_t key = (MODE == PDX_L2 || MODE == PDX_L2_PERM) ? make_key_asc(s[j], a.index_base + i)
                                                   : make_key_desc(s[j], a.index_base + i);
             lists[q].offer(key, active && i < a.n && (!MASKED || ((nib >> j) & 1u)), thrs[q], a.k, lane);
           }
@@ -297,10 +307,11 @@ unsigned knn_grid_x(unsigned n_tiles, size_t smem, int num_sms) {
   return balanced_grid(n_tiles, (unsigned)occ * (unsigned)num_sms);
 }
 
-size_t scan_smem_bytes(size_t d, int qb, int k, bool knn) {
+size_t scan_smem_bytes(size_t d, int qb, int k, bool knn, bool perm = false) {
   const int U = (qb == 1) ? 8 : 4;
   size_t d_pad = (d + U - 1) / U * U;
   size_t b = d_pad * qb * sizeof(float) + ((qb + 3) & ~3) * sizeof(float);
+  if (perm) b += d_pad * sizeof(unsigned);
   if (knn) b += (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t) * qb;  // QB > 1: every warp parks QB lists (block_finish)
   return b;
 }
@@ -399,9 +410,124 @@ cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, co
   return e;
 }
 
-cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
-                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold) {
+cudaError_t launch_pdx_knn_reordered(const PdxView& v, const float* dev_query, const uint32_t* dev_perm, size_t k,
+                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
   PdxArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
+  a.n = (unsigned)v.n;
+  a.d = (unsigned)v.d;
+  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
+  a.index_base = v.index_base;
+  a.one = 1.0f;
+  a.k = (int)k;
+  a.partials = ws.partials;
+  a.group_partials = ws.group_partials;
+  a.tickets = ws.tickets;
+  a.queries = dev_query;
+  a.nq_valid = 1;
+  a.out_keys = dev_keys;
+  a.perm = dev_perm;
+  const size_t smem = scan_smem_bytes(v.d, 1, (int)k, true, true);
+  if (smem > 227 * 1024 || k > 128 || !dev_perm) return cudaErrorInvalidValue;
+  cudaError_t e = (k <= 32) ? launch_one<PDX_L2_PERM, 1, 1, true>(a, smem, 1, ws.num_sms, s)
+                            : launch_one<PDX_L2_PERM, 1, 4, true>(a, smem, 1, ws.num_sms, s);
+  if (e == cudaSuccess) ++*launches;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch_dimension_variance (src/batch.rs:572-592). Both sums of a dimension row are sequential f32 sums over all n
+// vectors, so a row is one chain of n dependent adds whatever the hardware: one warp per row, rows in parallel (d warps);
+// the chain, not HBM, bounds it (~4 cycles per vector per pass).
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int VAR_WARPS = 4;
+
+constexpr int VAR_UV = 4;  // 128-value groups per step (512 values: 2 KB of shared memory per warp)
+
+// One sequential f32 sum over a dimension row: sum of x (CENTERED = false) or of (x - mean) * (x - mean), unfused.
+// The warp loads 512 consecutive values per step (the next step's loads are issued before this step's chain runs),
+// parks them in shared memory, and every lane replays the chain from broadcast 128-bit reads.
+template <bool CENTERED>
+__device__ __forceinline__ float row_chain(const float* row, unsigned n, float mean, int lane, float4* buf) {
+  float acc = 0.0f;
+  constexpr unsigned STEP = 128u * VAR_UV;
+  const unsigned n_steps = n / STEP;
+  float4 cur[VAR_UV], nxt[VAR_UV];
+  if (n_steps) {
+#pragma unroll
+    for (int u = 0; u < VAR_UV; ++u) cur[u] = ldg_stream_f4(row + 128u * u + 4u * lane);
+  }
+  for (unsigned st = 0; st < n_steps; ++st) {
+    if (st + 1 < n_steps) {
+      const float* p = row + (size_t)(st + 1) * STEP + 4u * lane;
+#pragma unroll
+      for (int u = 0; u < VAR_UV; ++u) nxt[u] = ldg_stream_f4(p + 128u * u);
+    }
+#pragma unroll
+    for (int u = 0; u < VAR_UV; ++u) {
+      float4 v = cur[u];
+      if (CENTERED) {  // computed once per value by the lane that loaded it
+        v.x = __fsub_rn(v.x, mean); v.y = __fsub_rn(v.y, mean); v.z = __fsub_rn(v.z, mean); v.w = __fsub_rn(v.w, mean);
+        v.x = __fmul_rn(v.x, v.x); v.y = __fmul_rn(v.y, v.y); v.z = __fmul_rn(v.z, v.z); v.w = __fmul_rn(v.w, v.w);
+      }
+      buf[u * 32 + lane] = v;
+    }
+    __syncwarp();
+#pragma unroll 16
+    for (int j = 0; j < VAR_UV * 32; ++j) {
+      const float4 x = buf[j];
+      acc = __fadd_rn(acc, x.x);
+      acc = __fadd_rn(acc, x.y);
+      acc = __fadd_rn(acc, x.z);
+      acc = __fadd_rn(acc, x.w);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < VAR_UV; ++u) cur[u] = nxt[u];
+  }
+#pragma unroll 8
+  for (unsigned i = n_steps * STEP; i < n; ++i) {  // tail (< 512 values): every lane reads the same value
+    float x = __ldg(row + i);
+    if (CENTERED) { x = __fsub_rn(x, mean); x = __fmul_rn(x, x); }
+    acc = __fadd_rn(acc, x);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(VAR_WARPS * 32) dimension_variance_kernel(const float* __restrict__ data, size_t ld,
+                                                                            unsigned n, unsigned d, float* __restrict__ out) {
+  __shared__ float4 s_buf[VAR_WARPS][VAR_UV * 32];
+  const unsigned dd = blockIdx.x * VAR_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (dd >= d) return;
+  float4* buf = s_buf[threadIdx.x >> 5];
+  const float* row = data + (size_t)dd * ld;
+  const float nf = (float)n;                                     // let n = batch.num_vectors as f32;
+  const float mean = __fdiv_rn(row_chain<false>(row, n, 0.0f, lane, buf), nf);
+  const float var = __fdiv_rn(row_chain<true>(row, n, mean, lane, buf), nf);
+  if (lane == 0) out[dd] = var;
+}
+
+}  // namespace
+
+cudaError_t launch_dimension_variance(const PdxView& v, float* dev_out, cudaStream_t s, LaunchCounter* launches) {
+  if (v.d == 0) return cudaSuccess;
+  if (v.n <= 1) return cudaMemsetAsync(dev_out, 0, v.d * sizeof(float), s);  // src/batch.rs:573-575
+  dimension_variance_kernel<<<(unsigned)((v.d + VAR_WARPS - 1) / VAR_WARPS), VAR_WARPS * 32, 0, s>>>(v.data, v.ld, (unsigned)v.n,
+                                                                                                  (unsigned)v.d, dev_out);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
+                              float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold,
+                              const uint32_t* dev_perm) {
+  PdxArgs a{};
+  a.perm = dev_perm;
   a.data = v.data;
   a.ld = v.ld;
   // columns actually scanned: n rounded up to a whole float4 (the row pitch is a multiple of 4, so the last float4 is
@@ -417,10 +543,11 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   a.scores_out = dev_out;
   a.norms_in = dev_norms;
   a.threshold = threshold;
-  size_t smem = scan_smem_bytes(v.d, 1, 0, false);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  size_t smem = scan_smem_bytes(v.d, 1, 0, false, mode == PDX_L2_PERM);
+  if (smem > 227 * 1024 || (mode == PDX_L2_PERM && !dev_perm)) return cudaErrorInvalidValue;
   cudaError_t e;
   switch (mode) {
+    case PDX_L2_PERM: e = launch_one<PDX_L2_PERM, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_L2: e = launch_one<PDX_L2, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;

@@ -57,6 +57,9 @@ def lib() -> C.CDLL:
             "innr_ref_batch_knn_cosine": (sz, [_f32p, _f32p, sz, sz, sz, _u64p, _f32p]),
             "innr_ref_batch_knn_filtered": (sz, [_f32p, _f32p, sz, sz, sz, _u8p, _u64p, _f32p]),
             "innr_ref_batch_l2_squared_pruning": (sz, [_f32p, _f32p, sz, sz, f32, _u64p, _f32p]),
+            "innr_ref_batch_dimension_variance": (None, [_f32p, sz, sz, _f32p]),
+            "innr_ref_variance_order": (None, [_f32p, sz, _u64p]),
+            "innr_ref_batch_knn_reordered": (sz, [_f32p, _f32p, sz, sz, sz, _u64p, _f32p]),
             "innr_ref_topk_new": (C.c_void_p, [sz]),
             "innr_ref_topk_free": (None, [C.c_void_p]),
             "innr_ref_topk_insert": (None, [C.c_void_p, C.c_uint32, f32]),
@@ -282,6 +285,44 @@ def batch_l2_squared_pruning(query, batch, threshold):  # src/batch.rs:320
     m = lib().innr_ref_batch_l2_squared_pruning(_p(q, _f32p), _p(batch.data, _f32p), batch.num_vectors,
                                                 batch.dimension, threshold, _p(idx, _u64p), _p(ds, _f32p))
     return [(int(idx[j]), float(ds[j])) for j in range(m)]
+
+
+def _into(out, values):  # `out.clear(); out.resize(n, ..)` then filled
+    out.clear()
+    out.extend(float(x) for x in values)
+
+
+def batch_l2_squared_into(query, batch, out):  # src/batch.rs:250
+    _into(out, batch_l2_squared(query, batch))
+
+
+def batch_dot_into(query, batch, out):  # src/batch.rs:284
+    _into(out, batch_dot(query, batch))
+
+
+def batch_norms_into(batch, out):  # src/batch.rs:672
+    _into(out, batch_norms(batch))
+
+
+def batch_cosine_into(query, batch, norms, out):  # src/batch.rs:705
+    _into(out, batch_cosine(query, batch, norms))
+
+
+def batch_dimension_variance(batch):  # src/batch.rs:572
+    out = np.zeros(batch.dimension, np.float32)
+    lib().innr_ref_batch_dimension_variance(_p(batch.data, _f32p), batch.num_vectors, batch.dimension, _p(out, _f32p))
+    return out
+
+
+def variance_order(variances):  # src/batch.rs:599
+    v = _f32(variances)
+    order = np.zeros(v.size, np.uint64)
+    lib().innr_ref_variance_order(_p(v, _f32p), v.size, _p(order, _u64p))
+    return [int(i) for i in order]
+
+
+def batch_knn_reordered(query, batch, k):  # src/batch.rs:621
+    return _knn("innr_ref_batch_knn_reordered", query, batch, k)
 
 
 def batch_knn_many(metric: str, queries, batch, k, n_threads=1):

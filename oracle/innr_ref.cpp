@@ -789,6 +789,63 @@ size_t innr_ref_batch_l2_squared_pruning(const float* q, const float* pdx, size_
   return m;
 }
 
+// batch_dimension_variance (src/batch.rs:572-592): per dimension row, mean = (sequential sum) / n, then the sequential
+// sum of (x - mean) * (x - mean), / n; n <= 1 or d == 0 -> zeros.
+void innr_ref_batch_dimension_variance(const float* pdx, size_t n, size_t d, float* out) {
+  if (n <= 1 || d == 0) {
+    for (size_t dd = 0; dd < d; ++dd) out[dd] = 0.0f;
+    return;
+  }
+  const float nf = (float)n;
+  for (size_t dd = 0; dd < d; ++dd) {
+    const float* row = pdx + dd * n;
+    float sum = 0.0f;
+    for (size_t i = 0; i < n; ++i) sum += row[i];
+    const float mean = sum / nf;
+    float acc = 0.0f;
+    for (size_t i = 0; i < n; ++i) acc += (row[i] - mean) * (row[i] - mean);
+    out[dd] = acc / nf;
+  }
+}
+
+// variance_order (src/batch.rs:599-603): stable sort of 0..d by decreasing variance under total_cmp
+void innr_ref_variance_order(const float* variances, size_t d, uint64_t* order) {
+  std::vector<size_t> o(d);
+  for (size_t i = 0; i < d; ++i) o[i] = i;
+  std::stable_sort(o.begin(), o.end(), [&](size_t a, size_t b) { return total_cmp(variances[b], variances[a]) < 0; });
+  for (size_t i = 0; i < d; ++i) order[i] = o[i];
+}
+
+// batch_knn_reordered (src/batch.rs:621-659): distances accumulated over the dimensions in variance order, then a
+// stable ascending sort (ties -> lower index, unlike batch_knn's TopK) and truncate.
+size_t innr_ref_batch_knn_reordered(const float* q, const float* pdx, size_t n, size_t d, size_t k,
+                                    uint64_t* out_idx, float* out_score) {
+  if (n == 0 || k == 0) return 0;
+  k = std::min(k, n);
+  std::vector<float> var(d);
+  std::vector<uint64_t> order(d);
+  innr_ref_batch_dimension_variance(pdx, n, d, var.data());
+  innr_ref_variance_order(var.data(), d, order.data());
+  std::vector<float> dist(n, 0.0f);
+  for (size_t j = 0; j < d; ++j) {
+    const size_t dd = (size_t)order[j];
+    const float qd = q[dd];
+    const float* row = pdx + dd * n;
+    for (size_t i = 0; i < n; ++i) {
+      float diff = qd - row[i];
+      dist[i] += diff * diff;
+    }
+  }
+  std::vector<Pair> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = {i, dist[i]};
+  std::stable_sort(v.begin(), v.end(), [](const Pair& a, const Pair& b) { return total_cmp(a.score, b.score) < 0; });
+  for (size_t j = 0; j < k; ++j) {
+    out_idx[j] = v[j].idx;
+    out_score[j] = v[j].score;
+  }
+  return k;
+}
+
 // ---- TopK -------------------------------------------------------------------
 innr_ref_topk* innr_ref_topk_new(size_t k) {
   if (k == 0) return nullptr;  // reference: assert!(k > 0, "innr::TopK: k must be >= 1")

@@ -96,6 +96,12 @@ size_t innr_ref_batch_knn_filtered(const float* q, const float* pdx, size_t n, s
 size_t innr_ref_batch_l2_squared_pruning(const float* q, const float* pdx, size_t n, size_t d,
                                          float threshold, uint64_t* out_idx, float* out_dist);
 
+/* src/batch.rs:572-592 (out[d]), :599-603 (order[d]), :621-659 */
+void innr_ref_batch_dimension_variance(const float* pdx, size_t n, size_t d, float* out);
+void innr_ref_variance_order(const float* variances, size_t d, uint64_t* order);
+size_t innr_ref_batch_knn_reordered(const float* q, const float* pdx, size_t n, size_t d, size_t k,
+                                    uint64_t* out_idx, float* out_score);
+
 /* ---- TopK: src/topk.rs:47-187 ------------------------------------------ */
 typedef struct innr_ref_topk innr_ref_topk;
 innr_ref_topk* innr_ref_topk_new(size_t k);           /* k == 0 -> NULL (reference panics, :65) */

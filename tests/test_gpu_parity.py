@@ -1128,3 +1128,61 @@ def test_knn_tc_non_finite_inputs_fall_back_to_the_exact_scan(tc_small, oracle):
     idx, sc = ib.batch_knn_many("dot", qs, gb, k)   # +-inf scores order identically everywhere (cosine would be NaN)
     widx, wsc = oracle.batch_knn_many("dot", qs, ob, k, n_threads=8)
     assert np.array_equal(idx, widx) and same_scores(sc, wsc)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch_dimension_variance / batch_knn_reordered (src/batch.rs:572-659): bit-exact variances (two sequential f32 sums
+# per dimension row), the same variance order, and distances summed in that order; ties -> lower index
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d", [(2, 1), (3, 5), (127, 8), (128, 9), (129, 16), (511, 33), (512, 7), (513, 64), (3000, 40),
+                                 (20000, 24)])
+def test_dimension_variance_bit_exact(ib, oracle, n, d):
+    rng = np.random.default_rng(n * 131 + d)
+    rows = (rng.standard_normal((n, d)) * rng.uniform(0.1, 3.0, size=d) + rng.uniform(-2, 2, size=d)).astype(np.float32)
+    if d > 2:
+        rows[:, 1] = 0.25          # constant row: variance exactly 0
+        rows[:, 2] = rows[:, 0]    # duplicate row: equal variances -> the stable order keeps the lower dimension first
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    g, w = ib.batch_dimension_variance(gb), oracle.batch_dimension_variance(ob)
+    assert np.array_equal(bits(g), bits(w)), (n, d)
+
+
+def test_dimension_variance_non_finite(ib, oracle):
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((700, 6)).astype(np.float32)
+    rows[13, 0] = np.inf      # mean inf -> x - mean = NaN for that row
+    rows[600, 1] = np.nan
+    rows[:, 2] = 3.0e38       # the sum overflows to +inf
+    rows[5, 3] = -0.0
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), 700, 6), oracle.VerticalBatch.from_flat(rows.reshape(-1), 700, 6)
+    assert same_scores(ib.batch_dimension_variance(gb), oracle.batch_dimension_variance(ob))
+
+
+@pytest.mark.parametrize("n,d", [(1, 3), (5, 2), (1000, 16), (1025, 37), (4097, 128), (30000, 48)])
+def test_knn_reordered_bit_exact(ib, oracle, n, d):
+    rng = np.random.default_rng(n + 7 * d)
+    rows = (rng.standard_normal((n, d)) * rng.uniform(0.05, 4.0, size=d)).astype(np.float32)
+    q = rng.standard_normal(d).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for k in (1, 10, 33, 128, 200, n + 3):
+        g, w = ib.batch_knn_reordered(q, gb, k), oracle.batch_knn_reordered(q, ob, k)
+        assert g.indices == w.indices, (n, d, k)
+        assert np.array_equal(bits(g.scores), bits(w.scores)), (n, d, k)
+    # summed in another order than batch_knn: same neighbours, scores equal up to rounding (reference's own check)
+    g, e = ib.batch_knn_reordered(q, gb, 5), ib.batch_knn(q, gb, 5)
+    assert np.allclose(g.scores, e.scores, rtol=1e-5)
+
+
+def test_knn_reordered_ties_and_equal_variances(ib, oracle):
+    rng = np.random.default_rng(17)
+    n, d = 5000, 12
+    rows = rng.integers(-1, 2, size=(n, d)).astype(np.float32)   # few distinct distances: ties everywhere
+    rows[:, 5] = rows[:, 4]                                       # equal variances
+    q = rng.integers(-1, 2, size=d).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for k in (7, 100, 300):
+        g, w = ib.batch_knn_reordered(q, gb, k), oracle.batch_knn_reordered(q, ob, k)
+        assert g.indices == w.indices and np.array_equal(bits(g.scores), bits(w.scores)), k
+    assert ib.batch_knn_reordered(q, gb, 0).indices == []
+    with pytest.raises(AssertionError):
+        ib.batch_knn_reordered(q[:-1], gb, 3)

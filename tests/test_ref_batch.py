@@ -355,3 +355,71 @@ def test_demo_timing_checksum(api, oracle):
         batch_sum = float(np.sum(api.batch_l2_squared(q, b), dtype=np.float64))
         naive_sum = float(np.sum((corpus.astype(np.float64) - q.astype(np.float64)) ** 2))
         assert abs(batch_sum - naive_sum) / max(abs(naive_sum), 1.0) < 1e-3
+
+
+# ---- reordered kNN and dimension variance: src/batch.rs:1219-1264, tests/batch_tests.rs:413-426
+def _sin_rows(n, d):
+    return [[np.float32(math.sin(i * 7 + dd * 3)) for dd in range(d)] for i in range(n)]
+
+
+def test_batch_knn_reordered_matches_exact(api):  # src/batch.rs:1220-1239
+    b = api.VerticalBatch.from_rows(_sin_rows(50, 16))
+    q = [np.float32(math.cos(i * 0.1)) for i in range(16)]
+    exact, reordered = api.batch_knn(q, b, 5), api.batch_knn_reordered(q, b, 5)
+    assert exact.indices == reordered.indices
+    for e, r in zip(exact.scores, reordered.scores):
+        assert abs(float(e) - float(r)) < 1e-4, f"distance mismatch: exact={e}, reordered={r}"
+
+
+def test_batch_knn_reordered_empty(api):  # src/batch.rs:1241-1246
+    b = api.VerticalBatch.from_rows([])
+    assert api.batch_knn_reordered([], b, 5).indices == []
+
+
+def test_batch_dimension_variance(api):  # src/batch.rs:1248-1264
+    b = api.VerticalBatch.from_rows([[1.0, 0.0], [1.0, 5.0], [1.0, 10.0]])
+    var = api.batch_dimension_variance(b)
+    assert abs(float(var[0])) < 1e-6, "constant dim should have 0 variance"
+    assert float(var[1]) > 10.0
+    assert float(var[1]) == float(np.float32(50.0) / np.float32(3.0))  # (25 + 0 + 25) / 3 in f32
+
+
+def test_batch_dimension_variance_degenerate(api):  # src/batch.rs:573-575: <= 1 vector -> zeros
+    assert list(api.batch_dimension_variance(api.VerticalBatch.from_rows([[3.0, -4.0, 5.0]]))) == [0.0, 0.0, 0.0]
+    assert list(api.batch_dimension_variance(api.VerticalBatch.from_rows([]))) == []
+
+
+def test_reordered_knn_matches_exact_large(api):  # tests/batch_tests.rs:413-426
+    b = api.VerticalBatch.from_rows(_sin_rows(200, 64))
+    q = [np.float32(math.cos(i * 0.1)) for i in range(64)]
+    assert api.batch_knn(q, b, 10).indices == api.batch_knn_reordered(q, b, 10).indices
+
+
+def test_reordered_knn_k_clamped_and_zero(api):  # src/batch.rs:624-631
+    b = api.VerticalBatch.from_rows([[0.0, 1.0], [2.0, 2.0], [0.5, 0.5]])
+    assert len(api.batch_knn_reordered([0.0, 0.0], b, 10).indices) == 3
+    assert api.batch_knn_reordered([0.0, 0.0], b, 0).indices == []
+    r = api.batch_knn_reordered([0.0, 0.0], b, 2)
+    assert r.indices == [2, 0] and list(r.scores) == [0.5, 1.0]
+
+
+def test_reordered_knn_ties_lower_index_first(api):  # stable sort_by(total_cmp), src/batch.rs:650-651
+    b = api.VerticalBatch.from_rows([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0], [0.0, -1.0], [0.0, 0.0]])
+    r = api.batch_knn_reordered([0.0, 0.0], b, 4)
+    assert r.indices == [4, 0, 1, 2]
+
+
+def test_into_batch_outputs_match_allocating_apis(api):  # tests/batch_tests.rs:188-213, src/batch.rs:915-947, 1008-1016
+    b = api.VerticalBatch.from_rows([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [1.0, 1.0, 0.0]])
+    q = [1.0, 0.5, 0.0]
+    out = [9.0] * 8  # stale contents must be cleared
+    api.batch_l2_squared_into(q, b, out)
+    assert out == list(api.batch_l2_squared(q, b))
+    api.batch_dot_into(q, b, out)
+    assert out == list(api.batch_dot(q, b))
+    norms = api.batch_norms(b)
+    norms_into = []
+    api.batch_norms_into(b, norms_into)
+    assert norms_into == list(norms)
+    api.batch_cosine_into(q, b, norms, out)
+    assert out == list(api.batch_cosine(q, b, norms))
