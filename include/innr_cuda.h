@@ -140,6 +140,13 @@ int innr_cuda_batch_dimension_variance(const innr_cuda_corpus* c, float* out, si
  * last bits because the summation order differs). k clamped to N; N == 0 or k == 0 -> empty. */
 int innr_cuda_batch_knn_reordered(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
                                   uint64_t* out_idx, float* out_score, size_t* out_count);
+/* batch_knn_adaptive (src/batch.rs:441-564): the reference's APPROXIMATE early-termination L2 kNN -- warm-up over the
+ * first warmup_dims dimensions, a threshold extrapolated from the k-th partial distance, pruning dimension by
+ * dimension (never below k candidates) with the threshold refreshed after every 32nd dimension. Reproduced exactly:
+ * the same candidates survive, with their complete distances, in the reference's stable ascending order. Rows of
+ * pruned vectors are not read. warmup_dims == 0 -> INNR_EINVAL ("warmup_dims must be > 0", the reference's assert). */
+int innr_cuda_batch_knn_adaptive(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                 size_t warmup_dims, uint64_t* out_idx, float* out_score, size_t* out_count);
 /* Re-rank stage of the reference's documented two-stage retrieval (src/scalar.rs:366-368 "Re-rank top candidates with
  * exact batch_knn_dot", examples/binary_demo.rs:235-237 "binary retrieves top-1000 candidates, then rerank"): the exact
  * batch_knn (L2) / batch_knn_dot / batch_knn_cosine result over the sub-batch formed by `candidates` (distinct global

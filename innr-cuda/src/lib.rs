@@ -43,6 +43,7 @@ extern "C" {
     pub fn innr_cuda_batch_l2_squared_pruning(c: *const innr_cuda_corpus, q: *const f32, q_len: usize, threshold: f32, out_idx: *mut u64, out_dist: *mut f32, capacity: usize, out_count: *mut usize) -> c_int;
     // dimension variance, reordered kNN ----------------------------------------- src/batch.rs:572-659
     pub fn innr_cuda_batch_dimension_variance(c: *const innr_cuda_corpus, out: *mut f32, out_len: usize) -> c_int;
+    pub fn innr_cuda_batch_knn_adaptive(c: *const innr_cuda_corpus, q: *const f32, q_len: usize, k: usize, warmup_dims: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
     pub fn innr_cuda_batch_knn_reordered(c: *const innr_cuda_corpus, q: *const f32, q_len: usize, k: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
     // binary -------------------------------------------------------------------- src/binary.rs:37-165
     pub fn innr_cuda_upload_binary(words: *const u64, n: usize, dim_bits: usize, index_base: u64, out: *mut *mut innr_cuda_corpus) -> c_int;
@@ -116,6 +117,15 @@ pub fn batch_l2_squared_pruning(q: &[f32], b: &DeviceBatch, threshold: f32) -> V
     let (mut idx, mut ds, mut cnt) = (vec![0u64; b.n.max(1)], vec![0f32; b.n.max(1)], 0usize);
     check(unsafe { innr_cuda_batch_l2_squared_pruning(b.h, q.as_ptr(), q.len(), threshold, idx.as_mut_ptr(), ds.as_mut_ptr(), b.n, &mut cnt) });
     idx.into_iter().zip(ds).take(cnt).map(|(i, d)| (i as usize, d)).collect()
+}
+pub fn batch_knn_adaptive(q: &[f32], b: &DeviceBatch, k: usize, warmup_dims: usize) -> innr::batch::BatchKnnResult {
+    assert_eq!(q.len(), b.d);                                          // src/batch.rs:447
+    assert!(warmup_dims > 0, "warmup_dims must be > 0");               // src/batch.rs:448
+    let kk = k.min(b.n).max(1);
+    let (mut idx, mut sc, mut cnt) = (vec![0u64; kk], vec![0f32; kk], 0usize);
+    check(unsafe { innr_cuda_batch_knn_adaptive(b.h, q.as_ptr(), q.len(), k, warmup_dims, idx.as_mut_ptr(), sc.as_mut_ptr(), &mut cnt) });
+    idx.truncate(cnt); sc.truncate(cnt);
+    innr::batch::BatchKnnResult { indices: idx.into_iter().map(|i| i as usize).collect(), scores: sc }
 }
 pub fn batch_dimension_variance(b: &DeviceBatch) -> Vec<f32> {          // src/batch.rs:572
     let mut out = vec![0f32; b.d];

@@ -9,7 +9,8 @@ from ._lib import (InnrCudaError, backend_name, build, init, knn_tc_last_stats, 
                    launch_count, lib, set_option)
 from .backend import Backend, dense_backend  # noqa: F401
 from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, batch_cosine_into,  # noqa: F401
-                    batch_dimension_variance, batch_dot, batch_dot_into, batch_knn, batch_knn_cosine, batch_knn_dot,
+                    batch_dimension_variance, batch_dot, batch_dot_into, batch_knn, batch_knn_adaptive, batch_knn_cosine,
+                    batch_knn_dot,
                     batch_knn_filtered, batch_knn_many, batch_knn_reordered, batch_knn_subset, batch_l2_squared,
                     batch_l2_squared_into, batch_l2_squared_pruning, batch_norms, batch_norms_into)
 from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, binary_hamming, binary_jaccard,  # noqa: F401

@@ -247,6 +247,21 @@ def batch_knn_reordered(query, batch, k: int) -> BatchKnnResult:  # src/batch.rs
     return BatchKnnResult(idx[:cnt.value], sc[:cnt.value])
 
 
+def batch_knn_adaptive(query, batch, k: int, warmup_dims: int) -> BatchKnnResult:  # src/batch.rs:441
+    """The reference's approximate early-termination kNN, reproduced exactly (same survivors, distances and order)."""
+    dev = _dev(batch)
+    q = _f32(query).reshape(-1)
+    assert q.size == dev.dimension, "query.len() != batch.dimension"
+    assert warmup_dims > 0, "warmup_dims must be > 0"
+    kk = max(min(k, dev.num_vectors), 1)
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    cnt = C.c_size_t(0)
+    L.call("innr_cuda_batch_knn_adaptive", dev.h, _ptr(q, L.f32p), q.size, k, warmup_dims, _ptr(idx, L.u64p),
+           _ptr(sc, L.f32p), C.byref(cnt))
+    return BatchKnnResult(idx[:cnt.value], sc[:cnt.value])
+
+
 def batch_knn_many(metric: str, queries, batch, k: int):
     """n_queries x d queries in one call (shares corpus passes between queries). Returns (idx, scores) arrays
     of shape (n_queries, min(k, N))."""

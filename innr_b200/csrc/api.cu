@@ -737,6 +737,106 @@ int innr_cuda_batch_knn_reordered(const innr_cuda_corpus* c, const float* query,
   return INNR_OK;
 }
 
+// batch_knn_adaptive (src/batch.rs:441-564): the reference's approximate early-termination kNN, reproduced exactly --
+// same candidate set, same distances (the sequential sum over all dimensions), same order. One pass per threshold
+// epoch (scan_f32.cu); the host only reads one counter per epoch to apply the reference's `alive_count > k` guard.
+int innr_cuda_batch_knn_adaptive(const innr_cuda_corpus* c, const float* query, size_t query_len, size_t k,
+                                 size_t warmup_dims, uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:447
+  if (warmup_dims == 0) return fail(INNR_EINVAL, "warmup_dims must be > 0");           // :448
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0) return INNR_OK;                                             // :450-455
+  if (!out_idx || !out_score || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < c->n ? k : c->n;
+  if (c->d == 0) {                                                                      // :458-463
+    for (size_t j = 0; j < kk; ++j) { out_idx[j] = c->index_base + j; out_score[j] = 0.0f; }
+    if (out_count) *out_count = kk;
+    return INNR_OK;
+  }
+  const size_t w = warmup_dims < c->d ? warmup_dims : c->d;
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  cudaStream_t s = ctx->stream;
+  const size_t words = c->ld / 32 + 2;
+  CU(ctx->d_query.reserve((c->d + 4) * sizeof(float)));
+  CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+  CU(ctx->d_keys.reserve(2 * kk * sizeof(uint64_t)));
+  CU(ctx->d_aux.reserve((2 * words + 8 + c->ld) * sizeof(uint32_t)));
+  CU(ctx->h_counts.reserve(64));
+  uint32_t* mask_a = (uint32_t*)ctx->d_aux.p;
+  uint32_t* mask_b = mask_a + words;
+  float* thr = (float*)(mask_b + words);
+  unsigned* pruned = (unsigned*)(thr + 4);
+  uint32_t* ev = (uint32_t*)(thr + 8);
+  float* dist = (float*)ctx->d_scores.p;
+  uint64_t* keys = (uint64_t*)ctx->d_keys.p;
+  const float* dq = (const float*)ctx->d_query.p;
+  unsigned* h_pruned = (unsigned*)ctx->h_counts.p;
+  CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, s));
+  Timed tm(*ctx);
+  const PdxView v = pdx_view(c);
+  auto read_pruned = [&](size_t* out) -> int {
+    CU(cudaMemcpyAsync(h_pruned, pruned, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *out = *h_pruned;
+    return INNR_OK;
+  };
+  // warm-up: the first w dimensions of every vector (a prefix of the same sequential sum)
+  PdxView vw = v;
+  vw.d = w;
+  CU(launch_pdx_scores(vw, PDX_L2, dq, nullptr, dist, ctx->ws, s, &g_launches));
+  CU(launch_topk_from_scores(dist, 0, c->n, 0, kk, keys, ctx->ws, s, &g_launches));
+  const float ratio = (float)c->d / (float)w;                                           // :486
+  CU(launch_adaptive_threshold(keys + kk - 1, ratio, thr, s, &g_launches));
+  CU(cudaMemsetAsync(pruned, 0, sizeof(unsigned), s));
+  CU(launch_adaptive_mark(v, dist, ratio, thr, mask_a, pruned, s, &g_launches));
+  size_t alive = c->n, p = 0;
+  rc = read_pruned(&p);
+  if (rc) return rc;
+  alive -= p;  // the k smallest estimates never exceed 1.5 x the k-th: at least k candidates stay
+  for (size_t d0 = w; d0 < c->d;) {
+    size_t last = (d0 + 31) / 32 * 32;  // the next dimension after which the reference refreshes the threshold
+    if (last >= c->d) last = c->d - 1;
+    const size_t d1 = last + 1;
+    const int no_prune = alive <= kk;
+    CU(cudaMemsetAsync(pruned, 0, sizeof(unsigned), s));
+    CU(launch_adaptive_epoch(v, dq, d0, d1, dist, mask_a, mask_b, thr, ev, pruned, no_prune, s, &g_launches));
+    if (!no_prune) {
+      rc = read_pruned(&p);
+      if (rc) return rc;
+      if (alive - p < kk) {
+        // The reference stops pruning when k candidates are left, and it meets the candidates in (dimension, index)
+        // order: of the p that exceeded the threshold in this epoch only the first alive - k die; the last
+        // k - (alive - p) of them in that order stay for good.
+        const size_t m = kk - (alive - p);
+        CU(ctx->d_tcws.reserve(c->n * sizeof(uint64_t)));
+        CU(launch_adaptive_event_keys(mask_a, mask_b, ev, c->n, (uint64_t*)ctx->d_tcws.p, s, &g_launches));
+        CU(launch_topk_from_scores(ctx->d_tcws.p, 3, c->n, 0, m, keys + kk, ctx->ws, s, &g_launches, nullptr, nullptr,
+                                   (unsigned)c->n, (unsigned)c->n));
+        CU(launch_adaptive_revive(keys + kk, m, mask_b, s, &g_launches));
+        alive = kk;
+      } else {
+        alive -= p;
+      }
+    }
+    if (last % 32 == 0 && alive > kk) {                                                  // :528-543
+      CU(launch_topk_from_scores(dist, 0, c->n, 0, kk, keys, ctx->ws, s, &g_launches, nullptr, mask_b));
+      CU(launch_adaptive_threshold(keys + kk - 1, 1.0f, thr, s, &g_launches));
+    }
+    std::swap(mask_a, mask_b);
+    d0 = d1;
+  }
+  CU(launch_topk_from_scores(dist, 0, c->n, (uint32_t)c->index_base, kk, keys, ctx->ws, s, &g_launches, nullptr, mask_a));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* hk) { decode_keys_f32(hk, kk, false, out_idx, out_score); });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
 // Re-rank stage of the reference's two-stage pipeline (src/scalar.rs:366-368, examples/binary_demo.rs:235-237): exact
 // batch_knn / batch_knn_dot / batch_knn_cosine restricted to `candidates` (global indices, distinct), i.e. the result of
 // the reference function on the sub-batch of those vectors with their original indices reported; ties -> lower index.
@@ -802,7 +902,6 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
   }
   if (passing == 0) return INNR_OK;                                                     // :842-847
   const size_t kk = k < passing ? k : passing;                                          // k.min(num_passing)
-  if (kk > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "batch_knn_filtered: k > 128 is not covered yet");
   std::lock_guard<std::mutex> lk(dev_mu(c->device));
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
@@ -815,8 +914,16 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
   CU(cudaMemcpyAsync(ctx->d_aux.p, mask_words, words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   if (c->d) CU(cudaMemcpyAsync(ctx->d_query.p, query, c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   Timed tm(*ctx);
-  CU(launch_pdx_knn_filtered(pdx_view(c), (const float*)ctx->d_query.p, (const uint32_t*)ctx->d_aux.p, kk,
-                             (uint64_t*)ctx->d_keys.p, ctx->ws, ctx->stream, &g_launches));
+  if (kk <= MAX_FUSED_K) {
+    CU(launch_pdx_knn_filtered(pdx_view(c), (const float*)ctx->d_query.p, (const uint32_t*)ctx->d_aux.p, kk,
+                               (uint64_t*)ctx->d_keys.p, ctx->ws, ctx->stream, &g_launches));
+  } else {  // any k: all distances (the passing vectors' are the same sums), then rounds of <= 128 over the passing ones
+    CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
+    CU(launch_pdx_scores(pdx_view(c), PDX_L2, (const float*)ctx->d_query.p, nullptr, (float*)ctx->d_scores.p, ctx->ws,
+                         ctx->stream, &g_launches));
+    CU(launch_topk_from_scores(ctx->d_scores.p, 0, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                               ctx->stream, &g_launches, nullptr, (const uint32_t*)ctx->d_aux.p));
+  }
   tm.stop();
   rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) { decode_keys_f32(keys, kk, false, out_idx, out_score); });
   if (rc) return rc;
@@ -901,11 +1008,20 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
 int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,
                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, void* stream) {
   if (k == 0 || n_queries == 0 || n_lists == 0) return INNR_OK;
-  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "merge of more than 128 keys per list is not covered yet (sharded k > 128)");
   std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
+  if (k > MAX_FUSED_K) {
+    uint64_t* keys_out = dev_keys_out;
+    if (!keys_out) {
+      CU(ctx->d_tcws.reserve(n_queries * k * sizeof(uint64_t)));
+      keys_out = (uint64_t*)ctx->d_tcws.p;
+    }
+    CU(launch_merge_keys_big(dev_keys_in, n_lists, n_queries, k, metric != INNR_METRIC_L2, keys_out, dev_idx, dev_score,
+                             ctx->ws, (cudaStream_t)stream, &g_launches));
+    return INNR_OK;
+  }
   CU(launch_merge_keys(dev_keys_in, n_lists, n_queries, k, metric != INNR_METRIC_L2, dev_keys_out, dev_idx, dev_score,
                        (cudaStream_t)stream, &g_launches));
   return INNR_OK;

@@ -79,10 +79,28 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
                               LaunchCounter* launches);
 // k smallest keys of a device score vector for ANY k (rounds of <= 128): kind 0 f32 ascending, 1 f32 descending,
-// 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128.
+// 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128. dev_mask (one bit per entry, LSB-first
+// u32 words) restricts the selection to the entries whose bit is set (batch_knn_filtered with k > 128).
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
-                                    const uint32_t* dev_ids = nullptr);
+                                    const uint32_t* dev_ids = nullptr, const uint32_t* dev_mask = nullptr, unsigned seg_len = 1,
+                                    unsigned seg_stride = 1);
+// the merge for k > 128 (any k): dev_keys_out (nq x k) is required
+cudaError_t launch_merge_keys_big(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
+                                  uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, Workspace& ws, cudaStream_t s,
+                                  LaunchCounter* launches);
+// batch_knn_adaptive (src/batch.rs:441-564), orchestrated by api.cu: see scan_f32.cu
+cudaError_t launch_adaptive_threshold(const uint64_t* dev_key, float scale, float* dev_thr, cudaStream_t s,
+                                      LaunchCounter* launches);
+cudaError_t launch_adaptive_mark(const PdxView& v, const float* dev_dist, float ratio, const float* dev_thr,
+                                 uint32_t* dev_mask_out, unsigned* dev_pruned, cudaStream_t s, LaunchCounter* launches);
+cudaError_t launch_adaptive_epoch(const PdxView& v, const float* dev_query, size_t d0, size_t d1, float* dev_dist,
+                                  const uint32_t* dev_mask_in, uint32_t* dev_mask_out, const float* dev_thr, uint32_t* dev_ev,
+                                  unsigned* dev_pruned, int no_prune, cudaStream_t s, LaunchCounter* launches);
+cudaError_t launch_adaptive_event_keys(const uint32_t* dev_before, const uint32_t* dev_after, const uint32_t* dev_ev, size_t n,
+                                       uint64_t* dev_keys, cudaStream_t s, LaunchCounter* launches);
+cudaError_t launch_adaptive_revive(const uint64_t* dev_keys, size_t m, uint32_t* dev_mask, cudaStream_t s,
+                                   LaunchCounter* launches);
 // exact scores (mode = PDX_DOT / PDX_L2 / PDX_COSINE_FUSED) of m candidate vectors given by GLOBAL id
 cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
                                  float* dev_out, cudaStream_t s, LaunchCounter* launches);

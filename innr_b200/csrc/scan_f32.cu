@@ -597,6 +597,8 @@ __global__ void __launch_bounds__(32) merge_keys_kernel(const uint64_t* in, int 
 template <int R, int KIND>
 __global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* scores, unsigned n, unsigned index_base,
                                                                   const uint32_t* ids,  // null: id = index_base + i
+                                                                  const uint32_t* mask, // non-null: only entries whose bit is set
+                                                                  unsigned seg_len, unsigned seg_stride,  // KIND 3 (see below)
                                                                   int k, const uint64_t* floor_key, uint64_t* partials,
                                                                   uint64_t* group_partials, uint64_t* out_keys,
                                                                   unsigned* tickets) {
@@ -613,14 +615,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* s
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned n_round = (n + 31u) / 32u * 32u;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    bool valid = i < n;
+    bool valid = i < n && (!mask || ((mask[i >> 5] >> (i & 31)) & 1u));
     uint64_t key = KEY_SENTINEL;
     if (valid) {
       const unsigned id = ids ? ids[i] : index_base + i;
-      if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], id);
+      if (KIND == 3) key = static_cast<const uint64_t*>(scores)[(size_t)(i / seg_len) * seg_stride + (i % seg_len)];
+      else if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], id);
       else if (KIND == 1) key = make_key_desc(static_cast<const float*>(scores)[i], id);
       else key = make_key_asc(static_cast<const float*>(scores)[i], id);
-      valid = !has_floor || (key > floor && floor != KEY_SENTINEL);
+      valid = (KIND != 3 || key != KEY_SENTINEL) && (!has_floor || (key > floor && floor != KEY_SENTINEL));
     }
     lists[0].offer(key, valid, thrs[0], k, lane);
   }
@@ -839,7 +842,7 @@ cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_qu
 // (read on the device: no host synchronisation between rounds)
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches,
-                                    const uint32_t* dev_ids) {
+                                    const uint32_t* dev_ids, const uint32_t* dev_mask, unsigned seg_len, unsigned seg_stride) {
   unsigned grid = (unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS);
   unsigned cap = (unsigned)ws.num_sms * 4u;
   if (grid > cap) grid = cap;
@@ -850,12 +853,14 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
     uint64_t* out = dev_keys + done;
     const size_t smem = (size_t)(SCAN_THREADS / 32) * kr * sizeof(uint64_t);
 #define INNR_TOPK_LAUNCH(R, KIND)                                                                                   \
-  topk_scores_kernel<R, KIND><<<grid, SCAN_THREADS, smem, s>>>(dev_scores, (unsigned)n, index_base, dev_ids, kr, floor, \
+  topk_scores_kernel<R, KIND><<<grid, SCAN_THREADS, smem, s>>>(dev_scores, (unsigned)n, index_base, dev_ids, dev_mask, seg_len, seg_stride, kr, floor, \
                                                                ws.partials, ws.group_partials, out, ws.tickets)
     if (kr <= 32) {
-      if (kind == 0) INNR_TOPK_LAUNCH(1, 0); else if (kind == 1) INNR_TOPK_LAUNCH(1, 1); else INNR_TOPK_LAUNCH(1, 2);
+      if (kind == 0) INNR_TOPK_LAUNCH(1, 0); else if (kind == 1) INNR_TOPK_LAUNCH(1, 1);
+      else if (kind == 2) INNR_TOPK_LAUNCH(1, 2); else INNR_TOPK_LAUNCH(1, 3);
     } else {
-      if (kind == 0) INNR_TOPK_LAUNCH(4, 0); else if (kind == 1) INNR_TOPK_LAUNCH(4, 1); else INNR_TOPK_LAUNCH(4, 2);
+      if (kind == 0) INNR_TOPK_LAUNCH(4, 0); else if (kind == 1) INNR_TOPK_LAUNCH(4, 1);
+      else if (kind == 2) INNR_TOPK_LAUNCH(4, 2); else INNR_TOPK_LAUNCH(4, 3);
     }
 #undef INNR_TOPK_LAUNCH
     ++*launches;
@@ -865,9 +870,236 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
   return cudaSuccess;
 }
 
+namespace {
+__global__ void decode_keys_kernel(const uint64_t* __restrict__ keys, size_t total, int descending, uint64_t* __restrict__ idx,
+                                   float* __restrict__ score) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint64_t key = keys[t];
+  if (idx) idx[t] = key & 0xFFFFFFFFull;
+  if (score) {
+    uint32_t hi = (uint32_t)(key >> 32);
+    if (descending) hi = ~hi;
+    score[t] = __uint_as_float(order_bits_to_f32_bits(hi));
+  }
+}
+}  // namespace
+
+// merge for k > 128: per query, selection rounds of <= 128 over the n_lists * k gathered keys, then one decode launch
+cudaError_t launch_merge_keys_big(const uint64_t* dev_in, size_t n_lists, size_t nq, size_t k, int descending,
+                                  uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, Workspace& ws, cudaStream_t s,
+                                  LaunchCounter* launches) {
+  for (size_t q = 0; q < nq; ++q) {
+    cudaError_t e = launch_topk_from_scores(dev_in + q * k, 3, n_lists * k, 0, k, dev_keys_out + q * k, ws, s, launches, nullptr,
+                                            nullptr, (unsigned)k, (unsigned)(nq * k));
+    if (e != cudaSuccess) return e;
+  }
+  if (dev_idx || dev_score) {
+    const size_t total = nq * k;
+    decode_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(dev_keys_out, total, descending, dev_idx, dev_score);
+    ++*launches;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch_knn_adaptive (src/batch.rs:441-564). The reference walks the dimensions one by one and, inside a dimension, the
+// vectors in index order, pruning a candidate when its partial distance exceeds a threshold that is refreshed after
+// every dimension d with d % 32 == 0 -- and never pruning once only k candidates are left. Between two refreshes the
+// threshold is constant, so an "epoch" (the dimensions up to and including the next refresh point) is one pass: every
+// live vector continues its sequential sum and notes the first dimension at which it exceeded the threshold. Unless
+// fewer than k candidates would remain, all of those are pruned, in any order; otherwise the host resolves the
+// reference's (dimension, index) order from the noted dimensions (api.cu). Rows of dead vectors are not read.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct AdaptArgs {
+  const float* data;
+  unsigned long long ld;
+  unsigned ld4;
+  const float* query;
+  unsigned d0, d1;          // dimensions [d0, d1) of this epoch
+  float* dist;              // partial distances (in/out)
+  const uint32_t* mask_in;  // bit i: vector i is a live candidate
+  uint32_t* mask_out;
+  const float* thr;         // thr[0]: the epoch's threshold (device)
+  uint32_t* ev;             // ev[i]: first dimension at which vector i exceeded the threshold (written when it did)
+  unsigned* pruned;         // += number of vectors that exceeded it
+  int no_prune;             // only k candidates left: accumulate, never prune (src/batch.rs:520 `alive_count > k`)
+};
+
+__global__ void __launch_bounds__(SCAN_THREADS) adaptive_epoch_kernel(const AdaptArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  const unsigned nd = a.d1 - a.d0;
+  for (unsigned j = threadIdx.x; j < nd; j += blockDim.x) sq[j] = a.query[a.d0 + j];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned i0 = (blockIdx.x * SCAN_THREADS + threadIdx.x) * VPT;
+  const bool in = i0 < a.ld4;
+  unsigned nib = in ? (a.mask_in[i0 >> 5] >> (i0 & 31)) & 0xFu : 0u;
+  unsigned n_dead = 0;
+  if (nib) {
+    float4 acc = *reinterpret_cast<const float4*>(a.dist + i0);
+    const float T = a.thr[0];
+    unsigned ex = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    const float* p = a.data + (size_t)a.d0 * a.ld + i0;
+    auto step = [&](const float4& v, unsigned j) {
+      const float q = sq[j];
+      float df;
+      df = __fsub_rn(q, v.x); acc.x = __fadd_rn(acc.x, __fmul_rn(df, df));
+      df = __fsub_rn(q, v.y); acc.y = __fadd_rn(acc.y, __fmul_rn(df, df));
+      df = __fsub_rn(q, v.z); acc.z = __fadd_rn(acc.z, __fmul_rn(df, df));
+      df = __fsub_rn(q, v.w); acc.w = __fadd_rn(acc.w, __fmul_rn(df, df));
+      if (!(ex & 1u) && acc.x > T) { ex |= 1u; e0 = a.d0 + j; }   // *dist > threshold  (src/batch.rs:520)
+      if (!(ex & 2u) && acc.y > T) { ex |= 2u; e1 = a.d0 + j; }
+      if (!(ex & 4u) && acc.z > T) { ex |= 4u; e2 = a.d0 + j; }
+      if (!(ex & 8u) && acc.w > T) { ex |= 8u; e3 = a.d0 + j; }
+    };
+    constexpr int U = 8;
+    unsigned j = 0;
+    for (; j + U <= nd; j += U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(p + (size_t)u * a.ld);
+      p += (size_t)U * a.ld;
+#pragma unroll
+      for (int u = 0; u < U; ++u) step(v[u], j + u);
+    }
+    for (; j < nd; ++j) {
+      const float4 v = ldg_stream_f4(p);
+      p += a.ld;
+      step(v, j);
+    }
+    *reinterpret_cast<float4*>(a.dist + i0) = acc;
+    if (!a.no_prune) {
+      const unsigned dead = ex & nib;
+      if (dead & 1u) a.ev[i0] = e0;
+      if (dead & 2u) a.ev[i0 + 1] = e1;
+      if (dead & 4u) a.ev[i0 + 2] = e2;
+      if (dead & 8u) a.ev[i0 + 3] = e3;
+      nib &= ~dead;
+      n_dead = __popc(dead);
+    }
+  }
+  // eight lanes hold the 32 bits of one mask word
+  unsigned w = nib << (4 * (lane & 7));
+  w |= __shfl_xor_sync(FULL_MASK, w, 1);
+  w |= __shfl_xor_sync(FULL_MASK, w, 2);
+  w |= __shfl_xor_sync(FULL_MASK, w, 4);
+  if (in && (lane & 7) == 0) a.mask_out[i0 >> 5] = w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_dead += __shfl_xor_sync(FULL_MASK, n_dead, o);
+  if (lane == 0 && n_dead) atomicAdd(a.pruned, n_dead);
+}
+
+// thr[0] = (score of *key) * scale, thr[1] = thr[0] * 1.5  (src/batch.rs:486-487, :496, :546)
+__global__ void adaptive_threshold_kernel(const uint64_t* key, float scale, float* thr) {
+  const float t = __fmul_rn(__uint_as_float(order_bits_to_f32_bits((uint32_t)(*key >> 32))), scale);
+  thr[0] = t;
+  thr[1] = __fmul_rn(t, 1.5f);
+}
+
+// first pruning round (src/batch.rs:493-501): candidate i dies when dist[i] * ratio > threshold * 1.5
+__global__ void __launch_bounds__(SCAN_THREADS) adaptive_mark_kernel(const float* __restrict__ dist, unsigned n, unsigned ld4,
+                                                                    float ratio, const float* __restrict__ thr,
+                                                                    uint32_t* __restrict__ mask_out, unsigned* pruned) {
+  const int lane = threadIdx.x & 31;
+  const unsigned i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const unsigned words32 = (ld4 + 31u) / 32u * 32u;
+  bool alive = false, dead = false;
+  if (i < n) {
+    dead = __fmul_rn(dist[i], ratio) > thr[1];
+    alive = !dead;
+  }
+  const unsigned w = __ballot_sync(FULL_MASK, alive);
+  const unsigned nd = __popc(__ballot_sync(FULL_MASK, dead));
+  if (lane == 0) {
+    if (i < words32) mask_out[i >> 5] = w;
+    if (nd) atomicAdd(pruned, nd);
+  }
+}
+
+// vectors that were live before the epoch and are not after it, as keys ordered by DEcreasing (dimension, index)
+__global__ void __launch_bounds__(SCAN_THREADS) adaptive_event_keys_kernel(const uint32_t* __restrict__ before,
+                                                                          const uint32_t* __restrict__ after,
+                                                                          const uint32_t* __restrict__ ev, unsigned n,
+                                                                          uint64_t* __restrict__ keys) {
+  const unsigned i = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const bool event = ((before[i >> 5] & ~after[i >> 5]) >> (i & 31)) & 1u;
+  keys[i] = event ? ~(((uint64_t)ev[i] << 32) | i) : KEY_SENTINEL;
+}
+
+__global__ void adaptive_revive_kernel(const uint64_t* __restrict__ keys, unsigned m, uint32_t* mask) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const unsigned i = (unsigned)(~keys[t] & 0xFFFFFFFFull);
+  atomicOr(mask + (i >> 5), 1u << (i & 31));
+}
+
+}  // namespace
+
+cudaError_t launch_adaptive_threshold(const uint64_t* dev_key, float scale, float* dev_thr, cudaStream_t s,
+                                      LaunchCounter* launches) {
+  adaptive_threshold_kernel<<<1, 1, 0, s>>>(dev_key, scale, dev_thr);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_mark(const PdxView& v, const float* dev_dist, float ratio, const float* dev_thr,
+                                 uint32_t* dev_mask_out, unsigned* dev_pruned, cudaStream_t s, LaunchCounter* launches) {
+  const unsigned ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
+  const unsigned span = (ld4 + 31u) / 32u * 32u;
+  adaptive_mark_kernel<<<(span + SCAN_THREADS - 1) / SCAN_THREADS, SCAN_THREADS, 0, s>>>(dev_dist, (unsigned)v.n, ld4, ratio,
+                                                                                      dev_thr, dev_mask_out, dev_pruned);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_epoch(const PdxView& v, const float* dev_query, size_t d0, size_t d1, float* dev_dist,
+                                  const uint32_t* dev_mask_in, uint32_t* dev_mask_out, const float* dev_thr, uint32_t* dev_ev,
+                                  unsigned* dev_pruned, int no_prune, cudaStream_t s, LaunchCounter* launches) {
+  AdaptArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
+  a.query = dev_query;
+  a.d0 = (unsigned)d0;
+  a.d1 = (unsigned)d1;
+  a.dist = dev_dist;
+  a.mask_in = dev_mask_in;
+  a.mask_out = dev_mask_out;
+  a.thr = dev_thr;
+  a.ev = dev_ev;
+  a.pruned = dev_pruned;
+  a.no_prune = no_prune;
+  const unsigned span = (a.ld4 + 31u) / 32u * 32u;  // whole mask words: every word of the output mask is written
+  const unsigned grid = (span / VPT + SCAN_THREADS - 1) / SCAN_THREADS;
+  adaptive_epoch_kernel<<<grid, SCAN_THREADS, (d1 - d0) * sizeof(float), s>>>(a);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_event_keys(const uint32_t* dev_before, const uint32_t* dev_after, const uint32_t* dev_ev, size_t n,
+                                       uint64_t* dev_keys, cudaStream_t s, LaunchCounter* launches) {
+  adaptive_event_keys_kernel<<<(unsigned)((n + SCAN_THREADS - 1) / SCAN_THREADS), SCAN_THREADS, 0, s>>>(dev_before, dev_after,
+                                                                                                     dev_ev, (unsigned)n, dev_keys);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_adaptive_revive(const uint64_t* dev_keys, size_t m, uint32_t* dev_mask, cudaStream_t s,
+                                   LaunchCounter* launches) {
+  if (m == 0) return cudaSuccess;
+  adaptive_revive_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(dev_keys, (unsigned)m, dev_mask);
+  ++*launches;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
-  return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches, nullptr);
+  return launch_topk_from_scores(dev_dist, 0, n, 0, k, dev_keys, ws, s, launches, nullptr, nullptr, 1, 1);
 }
 
 }  // namespace innr

@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
             "innr_ref_batch_knn_cosine": (sz, [_f32p, _f32p, sz, sz, sz, _u64p, _f32p]),
             "innr_ref_batch_knn_filtered": (sz, [_f32p, _f32p, sz, sz, sz, _u8p, _u64p, _f32p]),
             "innr_ref_batch_l2_squared_pruning": (sz, [_f32p, _f32p, sz, sz, f32, _u64p, _f32p]),
+            "innr_ref_batch_knn_adaptive": (sz, [_f32p, _f32p, sz, sz, sz, sz, _u64p, _f32p]),
             "innr_ref_batch_dimension_variance": (None, [_f32p, sz, sz, _f32p]),
             "innr_ref_variance_order": (None, [_f32p, sz, _u64p]),
             "innr_ref_batch_knn_reordered": (sz, [_f32p, _f32p, sz, sz, sz, _u64p, _f32p]),
@@ -285,6 +286,18 @@ def batch_l2_squared_pruning(query, batch, threshold):  # src/batch.rs:320
     m = lib().innr_ref_batch_l2_squared_pruning(_p(q, _f32p), _p(batch.data, _f32p), batch.num_vectors,
                                                 batch.dimension, threshold, _p(idx, _u64p), _p(ds, _f32p))
     return [(int(idx[j]), float(ds[j])) for j in range(m)]
+
+
+def batch_knn_adaptive(query, batch, k, warmup_dims):  # src/batch.rs:441
+    q = _f32(query)
+    assert q.size == batch.dimension
+    assert warmup_dims > 0, "warmup_dims must be > 0"
+    kk = max(1, min(k, max(batch.num_vectors, 1)))
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    m = lib().innr_ref_batch_knn_adaptive(_p(q, _f32p), _p(batch.data, _f32p), batch.num_vectors, batch.dimension, k,
+                                          warmup_dims, _p(idx, _u64p), _p(sc, _f32p))
+    return BatchKnnResult(idx[:m], sc[:m])
 
 
 def _into(out, values):  # `out.clear(); out.resize(n, ..)` then filled

@@ -789,6 +789,81 @@ size_t innr_ref_batch_l2_squared_pruning(const float* q, const float* pdx, size_
   return m;
 }
 
+// batch_knn_adaptive (src/batch.rs:441-564): warm-up over the first `warmup` dimensions, a threshold extrapolated from
+// the k-th partial distance, then dimension-by-dimension pruning (never below k candidates) with the threshold refreshed
+// after every dimension d with d % 32 == 0; survivors sorted (stable) by their complete distances.
+// warmup == 0 is the caller's assertion failure (`warmup_dims must be > 0`): returns SIZE_MAX.
+size_t innr_ref_batch_knn_adaptive(const float* q, const float* pdx, size_t n, size_t d, size_t k, size_t warmup,
+                                   uint64_t* out_idx, float* out_score) {
+  if (warmup == 0) return (size_t)-1;
+  if (n == 0 || k == 0) return 0;
+  k = std::min(k, n);
+  if (d == 0) {
+    for (size_t j = 0; j < k; ++j) { out_idx[j] = j; out_score[j] = 0.0f; }
+    return k;
+  }
+  warmup = std::min(warmup, d);
+  std::vector<float> dist(n, 0.0f);
+  std::vector<char> alive(n, 1);
+  size_t alive_count = n;
+  for (size_t dd = 0; dd < warmup; ++dd) {
+    const float qd = q[dd];
+    const float* row = pdx + dd * n;
+    for (size_t i = 0; i < n; ++i) {
+      float diff = qd - row[i];
+      dist[i] += diff * diff;
+    }
+  }
+  const float ratio = (float)d / (float)warmup;
+  float threshold;
+  {
+    std::vector<float> sorted(dist);
+    std::stable_sort(sorted.begin(), sorted.end(), [](float a, float b) { return total_cmp(a, b) < 0; });
+    threshold = sorted[k - 1] * ratio;  // k <= n always holds here
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const float estimated_full = dist[i] * ratio;
+    if (alive_count > k && estimated_full > threshold * 1.5f) {
+      alive[i] = 0;
+      --alive_count;
+    }
+  }
+  std::vector<float> buf(n);
+  for (size_t dd = warmup; dd < d; ++dd) {
+    const float qd = q[dd];
+    const float* row = pdx + dd * n;
+    for (size_t i = 0; i < n; ++i) {
+      if (!alive[i]) continue;
+      float diff = qd - row[i];
+      dist[i] += diff * diff;
+      if (alive_count > k && dist[i] > threshold) {
+        alive[i] = 0;
+        --alive_count;
+      }
+    }
+    if (dd % 32 == 0) {
+      size_t count = 0;
+      for (size_t i = 0; i < n; ++i)
+        if (alive[i]) buf[count++] = dist[i];
+      if (count >= k) {
+        std::nth_element(buf.begin(), buf.begin() + (k - 1), buf.begin() + count,
+                         [](float a, float b) { return total_cmp(a, b) < 0; });
+        threshold = buf[k - 1];
+      }
+    }
+  }
+  std::vector<Pair> v;
+  for (size_t i = 0; i < n; ++i)
+    if (alive[i]) v.push_back({i, dist[i]});
+  std::stable_sort(v.begin(), v.end(), [](const Pair& a, const Pair& b) { return total_cmp(a.score, b.score) < 0; });
+  const size_t m = std::min(k, v.size());
+  for (size_t j = 0; j < m; ++j) {
+    out_idx[j] = v[j].idx;
+    out_score[j] = v[j].score;
+  }
+  return m;
+}
+
 // batch_dimension_variance (src/batch.rs:572-592): per dimension row, mean = (sequential sum) / n, then the sequential
 // sum of (x - mean) * (x - mean), / n; n <= 1 or d == 0 -> zeros.
 void innr_ref_batch_dimension_variance(const float* pdx, size_t n, size_t d, float* out) {

@@ -96,6 +96,9 @@ size_t innr_ref_batch_knn_filtered(const float* q, const float* pdx, size_t n, s
 size_t innr_ref_batch_l2_squared_pruning(const float* q, const float* pdx, size_t n, size_t d,
                                          float threshold, uint64_t* out_idx, float* out_dist);
 
+/* src/batch.rs:441-564; returns (size_t)-1 when warmup == 0 (the reference's assertion) */
+size_t innr_ref_batch_knn_adaptive(const float* q, const float* pdx, size_t n, size_t d, size_t k, size_t warmup,
+                                   uint64_t* out_idx, float* out_score);
 /* src/batch.rs:572-592 (out[d]), :599-603 (order[d]), :621-659 */
 void innr_ref_batch_dimension_variance(const float* pdx, size_t n, size_t d, float* out);
 void innr_ref_variance_order(const float* variances, size_t d, uint64_t* order);

@@ -515,7 +515,7 @@ def test_knn_filtered_bit_exact(ib, oracle, n, d, sel):
         mask[:] = False
         mask[n // 2] = True          # exactly one passing vector
     gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
-    for k in (1, 10, 100):
+    for k in (1, 10, 100, 129, 700):   # > 128: a scores pass plus masked selection rounds
         got = ib.batch_knn_filtered(q, gb, k, mask)
         want = oracle.batch_knn_filtered(q, ob, k, lambda i: bool(mask[i]))
         assert list(got.indices) == list(want.indices), (k, got.indices[:5], want.indices[:5])
@@ -852,14 +852,16 @@ def test_maxsim_tc_nan_and_zero_tokens(ib, oracle):
 
 
 # ------------------------------------------------------------------------------------------------ sharding (K10)
-def test_sharded_merge_on_one_gpu(ib, oracle):
+@pytest.mark.parametrize("k", [10, 300])
+def test_sharded_merge_on_one_gpu(ib, oracle, k):
     """The multi-rank path emulated as one process over all ranks' data (B200_PROFILING.md: never run ranks that wait
     on one another on one GPU): 3 contiguous row shards with index_base, local keys via *_keys_dev on torch's
-    stream, concatenated as an allgather would, merged by merge_keys_kernel."""
+    stream, concatenated as an allgather would, merged by merge_keys_kernel (k > 128: selection rounds over the
+    gathered keys)."""
     import ctypes as C
     import torch
     from innr_b200 import _lib as L, sharded
-    n, d, k, nq = 9001, 40, 10, 5
+    n, d, nq = 9001, 40, 5
     rng = np.random.default_rng(4)
     rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)   # heavy ties
     qs = rng.integers(-3, 4, size=(nq, d)).astype(np.float32)
@@ -1186,3 +1188,58 @@ def test_knn_reordered_ties_and_equal_variances(ib, oracle):
     assert ib.batch_knn_reordered(q, gb, 0).indices == []
     with pytest.raises(AssertionError):
         ib.batch_knn_reordered(q[:-1], gb, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch_knn_adaptive (src/batch.rs:441-564): the approximate heuristic reproduced exactly -- survivors, complete
+# distances and order -- in every regime: thresholds that prune nothing, that prune most candidates, and that would
+# prune below k (the reference's `alive_count > k` guard then depends on the (dimension, index) visiting order)
+# ---------------------------------------------------------------------------------------------------------
+def _adaptive_case(rng, kind, n, d):
+    if kind == "gauss":            # flat spectrum: the extrapolated threshold is too tight, the guard binds
+        rows = rng.standard_normal((n, d))
+    elif kind == "mrl":            # decaying spectrum (Matryoshka-like): early dimensions carry the distance
+        rows = rng.standard_normal((n, d)) * (0.97 ** np.arange(d))
+    elif kind == "rising":         # later dimensions carry more than the warm-up suggests
+        rows = rng.standard_normal((n, d)) * np.linspace(0.2, 2.0, d)
+    elif kind == "planted":        # ten uniform-offset neighbours of the origin among far vectors: pruning is benign
+        rows = rng.integers(50, 100, size=(n, d)) * rng.choice([-1, 1], size=(n, d))
+        for j in range(min(10, n)):
+            rows[(j * 37) % n] = j + 1
+    else:                          # integer lattice: exact ties in partial and complete distances
+        rows = rng.integers(-2, 3, size=(n, d))
+    return rows.astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["gauss", "mrl", "rising", "ties", "planted"])
+@pytest.mark.parametrize("n,d", [(1, 5), (7, 3), (300, 40), (5000, 96), (4097, 130), (20000, 64)])
+def test_knn_adaptive_bit_exact(ib, oracle, kind, n, d):
+    rng = np.random.default_rng(n * 17 + d)
+    rows = _adaptive_case(rng, kind, n, d)
+    q = _adaptive_case(rng, kind, 1, d)[0] if kind != "planted" else np.zeros(d, np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for k in (1, 10, 100, 150, n, n + 5):
+        for w in (1, 8, 31, 32, 33, d, d + 9):
+            g, want = ib.batch_knn_adaptive(q, gb, k, w), oracle.batch_knn_adaptive(q, ob, k, w)
+            assert g.indices == want.indices, (kind, n, d, k, w, g.indices[:6], want.indices[:6])
+            assert np.array_equal(bits(g.scores), bits(want.scores)), (kind, n, d, k, w)
+
+
+def test_knn_adaptive_regimes_are_exercised(ib, oracle):
+    """The cases above must cover both outcomes: adaptive == exact kNN (benign pruning) and adaptive != exact kNN (true
+    neighbours pruned, the documented failure mode) -- otherwise the parity test proves less than it claims."""
+    rng = np.random.default_rng(3)
+    n, d, k = 5000, 96, 10
+    same = differ = 0
+    for kind in ("gauss", "planted"):
+        rows = _adaptive_case(rng, kind, n, d)
+        q = _adaptive_case(rng, kind, 1, d)[0] if kind != "planted" else np.zeros(d, np.float32)
+        gb = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+        a, e = ib.batch_knn_adaptive(q, gb, k, 8), ib.batch_knn(q, gb, k)
+        same += a.indices == e.indices
+        differ += a.indices != e.indices
+    assert same >= 1 and differ >= 1, (same, differ)
+    with pytest.raises(AssertionError):
+        ib.batch_knn_adaptive(np.zeros(d, np.float32), gb, k, 0)
+    with pytest.raises(AssertionError):
+        ib.batch_knn_adaptive(np.zeros(d - 1, np.float32), gb, k, 4)

@@ -423,3 +423,44 @@ def test_into_batch_outputs_match_allocating_apis(api):  # tests/batch_tests.rs:
     assert norms_into == list(norms)
     api.batch_cosine_into(q, b, norms, out)
     assert out == list(api.batch_cosine(q, b, norms))
+
+
+# ---- batch_knn_adaptive: src/batch.rs:1509-1572, tests/batch_tests.rs:269-292
+def test_batch_knn_adaptive_empty(api):
+    assert api.batch_knn_adaptive([], api.VerticalBatch.from_rows([]), 5, 2).indices == []
+
+
+def test_batch_knn_adaptive_k_zero(api):
+    assert api.batch_knn_adaptive([1.0, 2.0], api.VerticalBatch.from_rows([[1.0, 2.0]]), 0, 1).indices == []
+
+
+def test_batch_knn_adaptive_zero_warmup_panics(api):  # src/batch.rs:448 assert!(warmup_dims > 0, ..)
+    with pytest.raises(AssertionError):
+        api.batch_knn_adaptive([1.0, 2.0], api.VerticalBatch.from_rows([[1.0, 2.0]]), 1, 0)
+
+
+def test_batch_knn_adaptive_finds_nearest(api):  # src/batch.rs:1527-1545
+    b = api.VerticalBatch.from_rows([[0.0] * 4, [100.0] * 4, [0.1] * 4])
+    assert api.batch_knn([0.0] * 4, b, 1).indices[0] == 0
+    assert api.batch_knn_adaptive([0.0] * 4, b, 1, 2).indices[0] == 0
+
+
+def test_batch_knn_adaptive_keeps_k_finalized_candidates(api):  # src/batch.rs:1547-1561
+    b = api.VerticalBatch.from_rows([[0.0, 1.0]])
+    adaptive, exact = api.batch_knn_adaptive([0.0, 0.0], b, 1, 1), api.batch_knn([0.0, 0.0], b, 1)
+    assert len(adaptive.indices) == 1 and adaptive.indices == exact.indices
+    assert list(adaptive.scores) == list(exact.scores)
+
+
+def test_batch_knn_adaptive_zero_dimensional_batch_keeps_k(api):  # src/batch.rs:1563-1572
+    r = api.batch_knn_adaptive([], api.VerticalBatch.from_rows([[], [], []]), 2, 1)
+    assert r.indices == [0, 1] and list(r.scores) == [0.0, 0.0]
+
+
+def test_knn_adaptive_matches_basic(api):  # tests/batch_tests.rs:269-292
+    rows = [[np.float32(i), np.float32(math.sin(np.float32(i) * np.float32(0.1))),
+             np.float32(math.cos(np.float32(i) * np.float32(0.1)))] for i in range(100)]
+    b = api.VerticalBatch.from_rows(rows)
+    basic, adaptive = api.batch_knn([50.0, 0.0, 1.0], b, 10), api.batch_knn_adaptive([50.0, 0.0, 1.0], b, 10, 1)
+    for idx in basic.indices:
+        assert idx in adaptive.indices, f"Adaptive missing index {idx} from basic top-10"
