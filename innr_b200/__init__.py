@@ -17,8 +17,9 @@ from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, bin
                      binary_jaccard_all, encode_binary, hamming_all,
                      hamming_topk, hamming_topk_many)
 from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_corpus_batch, maxsim_cosine  # noqa: F401
-from .scalar import (QuantizationParams, QuantizedU8, U8Corpus, asymmetric_dot_u8, asymmetric_dot_u8_all,  # noqa: F401
-                     batch_knn_u8, batch_knn_u8_many, mixed_dot_u8_all, mixed_dot_u8_f32, quantize_u8)
+from .scalar import (QuantizationParams, QuantizedU8, QueryContext, U8Corpus, asymmetric_dot_u8,  # noqa: F401
+                     asymmetric_dot_u8_all, asymmetric_dot_u8_precomputed, batch_knn_u8, batch_knn_u8_many,
+                     mixed_dot_u8_all, mixed_dot_u8_f32, quantize_u8, query_context)
 from .ternary import (PackedTernary, TernaryCorpus, encode_ternary, ternary_asymmetric_dot, ternary_dot,  # noqa: F401
                       ternary_hamming, ternary_scores_all, ternary_sparsity, ternary_topk)
-from .topk import topk_from_distances  # noqa: F401
+from .topk import TopK, topk_from_distances  # noqa: F401

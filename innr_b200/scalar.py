@@ -20,20 +20,57 @@ class QuantizationParams:  # src/scalar.rs:44-163
         a = np.float32(mx) - np.float32(mn)
         return cls(a if a > 0.0 else 1.0, mn)
 
+    @staticmethod
+    def _range(v):
+        """min / max as the reference's scan finds them (:76-84): start at f32::MAX / f32::MIN, replace on strict
+        `<` / `>` only -- NaN never wins, the first of several equal extremes (e.g. +0.0 before -0.0) is kept."""
+        f32max = np.float32(np.finfo(np.float32).max)
+        mn, mx = f32max, -f32max
+        fin = v[~np.isnan(v)]
+        if fin.size:
+            lo, hi = fin[np.argmin(fin)], fin[np.argmax(fin)]
+            if lo < mn:
+                mn = lo
+            if hi > mx:
+                mx = hi
+        return mn, mx
+
     @classmethod
-    def fit(cls, values):  # :68-88 (host-side scan; fit_quantile stays on the CPU as well)
+    def fit(cls, values):  # :68-88 (parameter fitting is a host-side scan in the reference and here)
         v = np.asarray(values, dtype=np.float32).reshape(-1)
         if v.size == 0:
             return cls(1.0, 0.0)
-        return cls.from_range(float(np.min(v)), float(np.max(v)))
+        mn, mx = cls._range(v)
+        return cls.from_range(float(mn), float(mx))
+
+    @classmethod
+    def fit_quantile(cls, values, quantile: float):  # :104-137 (parameter fitting: a host-side sort, like the reference)
+        quantile = np.float32(quantile)
+        assert 0.0 < quantile <= 1.0, "quantile must be in (0.0, 1.0]"
+        v = np.asarray(values, dtype=np.float32).reshape(-1)
+        if v.size == 0:
+            return cls(1.0, 0.0)
+        if quantile >= 1.0:
+            return cls.fit(v)
+        v = v[np.isfinite(v)]
+        if v.size == 0:
+            return cls(1.0, 0.0)
+        bits = v.view(np.int32)
+        v = v[np.argsort(bits ^ ((bits >> 31) & 0x7FFFFFFF), kind="stable")]  # f32::total_cmp order (-0.0 < +0.0)
+        one, two, n = np.float32(1.0), np.float32(2.0), np.float32(v.size)
+        tail = (one - quantile) / two
+        lo = int(np.floor(tail * n))
+        hi = min(int(np.ceil((one - tail) * n)), v.size - 1)
+        return cls.from_range(float(v[lo]), float(v[hi]))
 
     @classmethod
     def fit_vectors(cls, vectors):  # :143-163
         vs = [np.asarray(v, dtype=np.float32).reshape(-1) for v in vectors]
-        vs = [v for v in vs if v.size]
-        if not vs:
+        v = np.concatenate(vs) if vs else np.zeros(0, np.float32)
+        mn, mx = cls._range(v)
+        if mn > mx:
             return cls(1.0, 0.0)
-        return cls.from_range(min(float(v.min()) for v in vs), max(float(v.max()) for v in vs))
+        return cls.from_range(float(mn), float(mx))
 
 
 class QuantizedU8:  # src/scalar.rs:171-208
@@ -135,6 +172,28 @@ def asymmetric_dot_u8(query, quantized: QuantizedU8, params: QuantizationParams)
     if q.size == 0:
         return 0.0
     return float(asymmetric_dot_u8_all(q, U8Corpus.from_rows(quantized.data.reshape(1, -1), params))[0])
+
+
+class QueryContext:  # src/scalar.rs:228-232
+    def __init__(self, query_sum: float):
+        self.query_sum = float(np.float32(query_sum))
+
+
+def query_context(query) -> QueryContext:  # src/scalar.rs:236-240: sequential f32 sum
+    s = np.float32(0.0)
+    for x in np.ascontiguousarray(query, dtype=np.float32).reshape(-1):
+        s = np.float32(s + x)
+    return QueryContext(float(s))
+
+
+def asymmetric_dot_u8_precomputed(query, quantized: QuantizedU8, params: QuantizationParams, ctx: QueryContext) -> float:
+    """src/scalar.rs:286-300: `(alpha / 255) * mixed + offset * ctx.query_sum` with the mixed dot from the device."""
+    q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+    assert q.size == quantized.dimension, (
+        f"asymmetric_dot_u8_precomputed: dimension mismatch ({q.size} vs {quantized.dimension})")
+    mixed = np.float32(mixed_dot_u8_f32(q, quantized.data)) if q.size else np.float32(0.0)
+    a, o = np.float32(params.alpha), np.float32(params.offset)
+    return float(np.float32(np.float32(a / np.float32(255.0)) * mixed) + np.float32(o * np.float32(ctx.query_sum)))
 
 
 def batch_knn_u8_many(queries, corpus: U8Corpus, k: int):

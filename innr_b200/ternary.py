@@ -159,3 +159,8 @@ def ternary_sparsity(v: PackedTernary) -> float:  # src/ternary.rs:327
     if v.dimension == 0:
         return 0.0
     return float(np.float32(1.0) - np.float32(v.nnz()) / np.float32(v.dimension))
+
+
+# the reference's own names inside `innr::ternary` (src/ternary.rs:286, :327)
+asymmetric_dot = ternary_asymmetric_dot
+sparsity = ternary_sparsity

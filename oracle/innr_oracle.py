@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
             "innr_ref_batch_dimension_variance": (None, [_f32p, sz, sz, _f32p]),
             "innr_ref_variance_order": (None, [_f32p, sz, _u64p]),
             "innr_ref_batch_knn_reordered": (sz, [_f32p, _f32p, sz, sz, sz, _u64p, _f32p]),
+            "innr_ref_qparams_fit_quantile": (i, [_f32p, sz, f32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+            "innr_ref_asymmetric_dot_u8_precomputed": (f32, [_f32p, _u8p, sz, f32, f32, f32]),
             "innr_ref_topk_new": (C.c_void_p, [sz]),
             "innr_ref_topk_free": (None, [C.c_void_p]),
             "innr_ref_topk_insert": (None, [C.c_void_p, C.c_uint32, f32]),
@@ -598,6 +600,14 @@ class QuantizationParams:  # src/scalar.rs:44-163
         lib().innr_ref_qparams_fit(_p(v, _f32p), v.size, C.byref(a), C.byref(o))
         return cls(a.value, o.value)
 
+    @classmethod
+    def fit_quantile(cls, values, quantile):  # :104-137
+        v = _f32(values)
+        a, o = C.c_float(), C.c_float()
+        rc = lib().innr_ref_qparams_fit_quantile(_p(v, _f32p), v.size, C.c_float(quantile), C.byref(a), C.byref(o))
+        assert rc == 0, "quantile must be in (0.0, 1.0]"
+        return cls(a.value, o.value)
+
 
 class QuantizedU8:  # src/scalar.rs:171-208
     def __init__(self, data, dimension):
@@ -643,6 +653,24 @@ def asymmetric_dot_u8(query, quantized: QuantizedU8, params: QuantizationParams)
         f"asymmetric_dot_u8: dimension mismatch ({q.size} vs {quantized.dimension})")
     return float(lib().innr_ref_asymmetric_dot_u8(_p(q, _f32p), _p(quantized.data, _u8p), q.size,
                                                   C.c_float(params.alpha), C.c_float(params.offset)))
+
+
+class QueryContext:  # src/scalar.rs:228-232
+    def __init__(self, query_sum: float):
+        self.query_sum = float(np.float32(query_sum))
+
+
+def query_context(query) -> QueryContext:  # src/scalar.rs:236
+    return QueryContext(query_sum(query))
+
+
+def asymmetric_dot_u8_precomputed(query, quantized: QuantizedU8, params: QuantizationParams, ctx: QueryContext) -> float:
+    q = _f32(query)  # src/scalar.rs:286
+    assert q.size == quantized.dimension, (
+        f"asymmetric_dot_u8_precomputed: dimension mismatch ({q.size} vs {quantized.dimension})")
+    return float(lib().innr_ref_asymmetric_dot_u8_precomputed(_p(q, _f32p), _p(quantized.data, _u8p), q.size,
+                                                              C.c_float(params.alpha), C.c_float(params.offset),
+                                                              C.c_float(ctx.query_sum)))
 
 
 def batch_knn_u8(query, corpus, params: QuantizationParams, k):  # src/scalar.rs:370

@@ -1116,6 +1116,41 @@ void innr_ref_qparams_fit(const float* v, size_t n, float* alpha, float* offset)
   }
   innr_ref_qparams_from_range(mn, mx, alpha, offset);
 }
+// QuantizationParams::fit_quantile (src/scalar.rs:104-137). quantile outside (0, 1] is the caller's assertion: returns 1.
+int innr_ref_qparams_fit_quantile(const float* v, size_t n, float quantile, float* alpha, float* offset) {
+  if (!(quantile > 0.0f && quantile <= 1.0f)) return 1;
+  if (n == 0) {
+    *alpha = 1.0f;
+    *offset = 0.0f;
+    return 0;
+  }
+  if (quantile >= 1.0f) {
+    innr_ref_qparams_fit(v, n, alpha, offset);
+    return 0;
+  }
+  std::vector<float> sorted;
+  for (size_t i = 0; i < n; ++i)
+    if (std::isfinite(v[i])) sorted.push_back(v[i]);
+  std::stable_sort(sorted.begin(), sorted.end(), [](float a, float b) { return total_cmp(a, b) < 0; });
+  if (sorted.empty()) {
+    *alpha = 1.0f;
+    *offset = 0.0f;
+    return 0;
+  }
+  const float tail = (1.0f - quantile) / 2.0f;
+  const float len = (float)sorted.size();
+  size_t lo_idx = (size_t)std::floor(tail * len);
+  size_t hi_idx = (size_t)std::ceil((1.0f - tail) * len);
+  hi_idx = std::min(hi_idx, sorted.size() - 1);
+  innr_ref_qparams_from_range(sorted[lo_idx], sorted[hi_idx], alpha, offset);
+  return 0;
+}
+// asymmetric_dot_u8_precomputed (src/scalar.rs:286-300): the caller supplies query_sum
+float innr_ref_asymmetric_dot_u8_precomputed(const float* q, const uint8_t* codes, size_t n, float alpha, float offset,
+                                             float query_sum) {
+  const float mixed = innr_ref_mixed_dot_u8_f32(q, codes, n);
+  return (alpha / 255.0f) * mixed + offset * query_sum;
+}
 void innr_ref_quantize_u8(const float* v, size_t n, float alpha, float offset, uint8_t* out) {
   float inv_alpha = 255.0f / alpha;
   for (size_t i = 0; i < n; ++i) {

@@ -145,6 +145,9 @@ size_t innr_ref_hamming_topk(const uint64_t* q, const uint64_t* codes, size_t n,
 /* ---- scalar u8: src/scalar.rs:44-393 ----------------------------------- */
 void innr_ref_qparams_from_range(float mn, float mx, float* alpha, float* offset); /* :54-60 */
 void innr_ref_qparams_fit(const float* v, size_t n, float* alpha, float* offset);  /* :68-88 */
+int innr_ref_qparams_fit_quantile(const float* v, size_t n, float quantile, float* alpha, float* offset); /* :104-137; 1 = assert */
+float innr_ref_asymmetric_dot_u8_precomputed(const float* q, const uint8_t* codes, size_t n, float alpha, float offset,
+                                             float query_sum);                                    /* :286-300 */
 void innr_ref_quantize_u8(const float* v, size_t n, float alpha, float offset, uint8_t* out); /* :212-225 */
 float innr_ref_query_sum(const float* q, size_t n);                                 /* :236-240 */
 float innr_ref_mixed_dot_u8_f32(const float* a, const uint8_t* b, size_t n);        /* :314-358 dispatch */

@@ -103,3 +103,53 @@ def test_quantize_u8_formula_edges(api):  # src/scalar.rs:212-225: round half aw
     p = api.QuantizationParams.from_range(0.0, 255.0)   # inv_alpha = 1
     q = api.quantize_u8([0.5, 1.5, 2.5, -3.0, 300.0, 254.5, float("nan")], p)
     assert list(q.data) == [1, 2, 3, 0, 255, 255, 0]
+
+
+def test_precomputed_matches_direct(api):  # src/scalar.rs:448-462
+    doc, query = [1.0, 2.0, 3.0], [0.5, 1.0, 1.5]
+    params = api.QuantizationParams.fit(doc)
+    quantized = api.quantize_u8(doc, params)
+    direct = api.asymmetric_dot_u8(query, quantized, params)
+    ctx = api.query_context(query)
+    precomputed = api.asymmetric_dot_u8_precomputed(query, quantized, params, ctx)
+    assert abs(direct - precomputed) < 1e-6, f"precomputed mismatch: direct={direct}, precomputed={precomputed}"
+    assert ctx.query_sum == 3.0
+    with pytest.raises(AssertionError):
+        api.asymmetric_dot_u8_precomputed(query[:2], quantized, params, ctx)
+
+
+def test_fit_quantile_clips_outliers(api):  # src/scalar.rs:557-579
+    values = [np.float32(i) / np.float32(49.0) - np.float32(1.0) for i in range(98)] + [100.0, -100.0]
+    full = api.QuantizationParams.fit(values)
+    clipped = api.QuantizationParams.fit_quantile(values, 0.95)
+    assert clipped.alpha < full.alpha, f"clipped alpha {clipped.alpha} should be < full alpha {full.alpha}"
+    assert clipped.alpha < 10.0
+
+
+def test_fit_quantile_edges(api):  # src/scalar.rs:104-137: quantile range assert, empty, q = 1 == fit, non-finite filtered
+    with pytest.raises(AssertionError):
+        api.QuantizationParams.fit_quantile([1.0], 0.0)
+    with pytest.raises(AssertionError):
+        api.QuantizationParams.fit_quantile([1.0], 1.5)
+    p = api.QuantizationParams.fit_quantile([], 0.9)
+    assert (p.alpha, p.offset) == (1.0, 0.0)
+    vals = [3.0, -1.0, 7.5, 0.25]
+    a, b = api.QuantizationParams.fit_quantile(vals, 1.0), api.QuantizationParams.fit(vals)
+    assert (a.alpha, a.offset) == (b.alpha, b.offset)
+    p = api.QuantizationParams.fit_quantile([float("nan"), float("inf")], 0.5)
+    assert (p.alpha, p.offset) == (1.0, 0.0)
+
+
+def test_fit_quantile_mirror_matches_oracle(oracle):
+    """The host mirror's numpy restatement of fit_quantile against the oracle's, over random inputs and quantiles."""
+    import innr_b200.scalar as mirror
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        n = int(rng.integers(1, 400))
+        v = (rng.standard_normal(n) * rng.choice([0.01, 1.0, 100.0])).astype(np.float32)
+        if rng.random() < 0.3:
+            v[rng.integers(0, n)] = rng.choice([np.inf, -np.inf, np.nan, -0.0, 0.0])
+        q = float(rng.choice([0.5, 0.9, 0.95, 0.99, 0.999, 1.0, float(rng.uniform(0.01, 1.0))]))
+        a, b = mirror.QuantizationParams.fit_quantile(v, q), oracle.QuantizationParams.fit_quantile(v, q)
+        assert np.float32(a.alpha).tobytes() == np.float32(b.alpha).tobytes(), (n, q)
+        assert np.float32(a.offset).tobytes() == np.float32(b.offset).tobytes(), (n, q)

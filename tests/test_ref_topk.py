@@ -1,5 +1,5 @@
-"""Ports of /root/reference/src/topk.rs:189-347 against the oracle's TopK restatement, plus the same cases pushed
-through `api.topk_from_distances` (device analogue: N inserts in id order == one fused selection; L2-path tie
+"""Ports of /root/reference/src/topk.rs:189-347 against the oracle's TopK restatement and the device-backed
+`innr_b200.TopK`, plus the same cases pushed through `api.topk_from_distances` (device analogue: N inserts in id order == one fused selection; L2-path tie
 rule SURVEY.md 8a row T: exact-tie groups compare as sets)."""
 import math
 
@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 
 
-def test_nan_candidate_does_not_poison_topk(oracle):  # :192-208
-    tk = oracle.TopK(2)
+def test_nan_candidate_does_not_poison_topk(api):  # :192-208
+    tk = api.TopK(2)
     tk.insert(0, float("nan"))
     tk.insert(1, 1.0)
     tk.insert(2, 0.5)
@@ -16,8 +16,8 @@ def test_nan_candidate_does_not_poison_topk(oracle):  # :192-208
     assert 2 in ids and 1 in ids
 
 
-def test_basic_top3(oracle):  # :213-228
-    top = oracle.TopK(3)
+def test_basic_top3(api):  # :213-228
+    top = api.TopK(3)
     for i, d in enumerate([1.5, 0.3, 2.0, 0.8, 5.0]):
         top.insert(i, d)
     assert len(top) == 3
@@ -25,8 +25,8 @@ def test_basic_top3(oracle):  # :213-228
     assert [(i, np.float32(d)) for i, d in r] == [(1, np.float32(0.3)), (3, np.float32(0.8)), (0, np.float32(1.5))]
 
 
-def test_threshold_tracking(oracle):  # :230-251
-    top = oracle.TopK(3)
+def test_threshold_tracking(api):  # :230-251
+    top = api.TopK(3)
     assert top.threshold() == math.inf
     top.insert(0, 1.0)
     assert top.threshold() == math.inf
@@ -42,8 +42,8 @@ def test_threshold_tracking(oracle):  # :230-251
     assert top.threshold() == 1.5
 
 
-def test_duplicate_distances(oracle):  # :254-266
-    top = oracle.TopK(3)
+def test_duplicate_distances(api):  # :254-266
+    top = api.TopK(3)
     for i in range(4):
         top.insert(i, 1.0)
     assert len(top) == 3
@@ -51,8 +51,8 @@ def test_duplicate_distances(oracle):  # :254-266
     assert len(r) == 3 and all(d == 1.0 for _, d in r)
 
 
-def test_k1_edge_case(oracle):  # :268-283
-    top = oracle.TopK(1)
+def test_k1_edge_case(api):  # :268-283
+    top = api.TopK(1)
     assert top.threshold() == math.inf
     for i, (d, t) in enumerate([(5.0, 5.0), (3.0, 3.0), (10.0, 3.0), (1.0, 1.0)]):
         top.insert(i, d)
@@ -60,24 +60,24 @@ def test_k1_edge_case(oracle):  # :268-283
     assert top.into_sorted() == [(3, 1.0)]
 
 
-def test_large_n_k10(oracle):  # :285-300
-    top = oracle.TopK(10)
+def test_large_n_k10(api):  # :285-300
+    top = api.TopK(10)
     for i in range(10_000):
         top.insert(i, float(i))
     r = top.into_sorted()
     assert [i for i, _ in r] == list(range(10)) and [d for _, d in r] == [float(i) for i in range(10)]
 
 
-def test_sorted_output_ascending(oracle):  # :302-316
-    top = oracle.TopK(5)
+def test_sorted_output_ascending(api):  # :302-316
+    top = api.TopK(5)
     for i in reversed(range(5)):
         top.insert(i, float(i))
     r = top.into_sorted()
     assert all(r[i][1] <= r[i + 1][1] for i in range(len(r) - 1))
 
 
-def test_is_empty_and_len(oracle):  # :318-333
-    top = oracle.TopK(4)
+def test_is_empty_and_len(api):  # :318-333
+    top = api.TopK(4)
     assert top.is_empty() and len(top) == 0
     top.insert(0, 1.0)
     assert not top.is_empty() and len(top) == 1
@@ -88,8 +88,8 @@ def test_is_empty_and_len(oracle):  # :318-333
     assert len(top) == 4
 
 
-def test_insert_in_sorted_order(oracle):  # :335-346
-    top = oracle.TopK(4)
+def test_insert_in_sorted_order(api):  # :335-346
+    top = api.TopK(4)
     for i in range(4):
         top.insert(i, float(i + 1))
     top.insert(4, 0.5)
@@ -97,9 +97,9 @@ def test_insert_in_sorted_order(oracle):  # :335-346
     assert r[0] == (4, 0.5) and r[3] == (2, 3.0)
 
 
-def test_new_zero_panics(oracle):  # :65 assert!(k > 0, "innr::TopK: k must be >= 1")
+def test_new_zero_panics(api):  # :65 assert!(k > 0, "innr::TopK: k must be >= 1")
     with pytest.raises(AssertionError):
-        oracle.TopK(0)
+        api.TopK(0)
 
 
 def test_binary_search_tie_drift_matches_survey(oracle):
