@@ -17,3 +17,10 @@ for name in ("batch_knn", "batch_knn_reordered"):
     print(name, "kernel ms median %.3f" % float(np.median(ms)), r.indices[:4])
 a, b = ib.batch_knn(q, batch, 10), ib.batch_knn_reordered(q, batch, 10)
 print("same neighbours:", a.indices == b.indices)
+for w in (32, 128):
+    for _ in range(2): r = ib.batch_knn_adaptive(q, batch, 10, w)
+    ms = []
+    for _ in range(5):
+        r = ib.batch_knn_adaptive(q, batch, 10, w); ms.append(ib.last_kernel_ms())
+    print("batch_knn_adaptive warmup", w, "kernel ms median %.3f" % float(np.median(ms)), r.indices[:4],
+          "overlap with exact top-10:", len(set(r.indices) & set(a.indices)))
