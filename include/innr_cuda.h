@@ -193,6 +193,11 @@ int innr_cuda_binary_dot_all(const innr_cuda_corpus* c, const uint64_t* query_wo
                              uint32_t* out_host);
 int innr_cuda_binary_jaccard_all(const innr_cuda_corpus* c, const uint64_t* query_words, size_t query_dim_bits,
                                  float* out_host);
+/* Top-k by similarity over a code set: op 0 = binary_dot (src/binary.rs:178), 1 = binary_jaccard (:198), descending, ties
+ * -> lower index (the caller composition of examples/binary_demo.rs:174-180 applied to the two similarities). Scores as
+ * f32 (dot counts are exact). */
+int innr_cuda_binary_topk(const innr_cuda_corpus* c, int op, const uint64_t* query_words, size_t query_dim_bits, size_t k,
+                          uint64_t* out_idx, float* out_score, size_t* out_count);
 /* caller composition examples/binary_demo.rs:174-180: all distances, stable sort_by_key, take(k). */
 int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
                            size_t query_dim_bits, size_t k, uint64_t* out_idx, uint32_t* out_dist,

@@ -14,7 +14,7 @@ from .batch import (BatchKnnResult, DeviceBatch, VerticalBatch, batch_cosine, ba
                     batch_knn_filtered, batch_knn_many, batch_knn_reordered, batch_knn_subset, batch_l2_squared,
                     batch_l2_squared_into, batch_l2_squared_pruning, batch_norms, batch_norms_into)
 from .binary import (BinaryCorpus, PackedBinary, binary_dot, binary_dot_all, binary_hamming, binary_jaccard,  # noqa: F401
-                     binary_jaccard_all, encode_binary, hamming_all,
+                     binary_jaccard_all, binary_topk, encode_binary, hamming_all,
                      hamming_topk, hamming_topk_many)
 from .maxsim import TokenCorpus, maxsim, maxsim_corpus, maxsim_corpus_batch, maxsim_cosine  # noqa: F401
 from .scalar import (QuantizationParams, QuantizedU8, QueryContext, U8Corpus, asymmetric_dot_u8,  # noqa: F401

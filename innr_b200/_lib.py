@@ -59,6 +59,7 @@ SIGNATURES = {
     "innr_cuda_batch_knn_filtered": [vp, f32p, sz, sz, u64p, sz, u64p, f32p, szp],
     "innr_cuda_batch_l2_squared_pruning": [vp, f32p, sz, f32, u64p, f32p, sz, szp],
     "innr_cuda_batch_knn_adaptive": [vp, f32p, sz, sz, sz, u64p, f32p, szp],
+    "innr_cuda_binary_topk": [vp, ci, u64p, sz, sz, u64p, f32p, szp],
     "innr_cuda_batch_dimension_variance": [vp, f32p, sz],
     "innr_cuda_batch_knn_reordered": [vp, f32p, sz, sz, u64p, f32p, szp],
     "innr_cuda_batch_knn_keys_dev": [vp, ci, vp, sz, sz, vp, vp],

@@ -123,6 +123,19 @@ def binary_jaccard_all(query: PackedBinary, corpus: BinaryCorpus) -> np.ndarray:
     return out
 
 
+def binary_topk(op: str, query: PackedBinary, corpus: BinaryCorpus, k: int):
+    """Top-k codes by `binary_dot` ("dot") or `binary_jaccard` ("jaccard"), descending, ties -> lower index.
+    Returns (indices uint64[m], scores float32[m])."""
+    kk = max(min(k, corpus.num_codes), 1)
+    idx = np.zeros(kk, np.uint64)
+    sc = np.zeros(kk, np.float32)
+    cnt = C.c_size_t(0)
+    q = np.ascontiguousarray(query.data, dtype=np.uint64)
+    L.call("innr_cuda_binary_topk", corpus.h, {"dot": 0, "jaccard": 1}[op], q.ctypes.data_as(L.u64p), query.dimension, k,
+           idx.ctypes.data_as(L.u64p), sc.ctypes.data_as(L.f32p), C.byref(cnt))
+    return idx[:cnt.value], sc[:cnt.value]
+
+
 def binary_dot(a: PackedBinary, b: PackedBinary) -> int:  # src/binary.rs:178 (pairwise; 1-code corpus)
     assert a.dimension == b.dimension
     if a.dimension == 0:

@@ -1227,6 +1227,55 @@ int innr_cuda_binary_jaccard_all(const innr_cuda_corpus* c, const uint64_t* quer
   return binary_setop_all(c, query_words, query_dim_bits, true, out_host);
 }
 
+// Top-k by binary_dot (op 0) or binary_jaccard (op 1) over a code set: the caller composition the reference shows for
+// Hamming (examples/binary_demo.rs:174-180) with the similarity ranked descending, ties -> lower index. Scores as f32
+// (dot counts are exact: dimension < 2^24).
+int innr_cuda_binary_topk(const innr_cuda_corpus* c, int op, const uint64_t* query_words, size_t query_dim_bits, size_t k,
+                          uint64_t* out_idx, float* out_score, size_t* out_count) {
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (op != 0 && op != 1) return fail(INNR_EINVAL, "binary_topk: op must be 0 (dot) or 1 (jaccard)");
+  if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "dimension mismatch");  // assert_eq!(a.dimension, b.dimension)
+  if (out_count) *out_count = 0;
+  if (c->n == 0 || k == 0) return INNR_OK;
+  if (!out_idx || !out_score || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
+  if (c->dim_bits >= (1u << 24)) return fail(INNR_EUNSUPPORTED, "binary_topk: dimension >= 2^24");
+  const size_t kk = k < c->n ? k : c->n;
+  if (c->words == 0) {  // no words: dot 0 / jaccard 1.0 for every code, index order
+    for (size_t j = 0; j < kk; ++j) { out_idx[j] = c->index_base + j; out_score[j] = op ? 1.0f : 0.0f; }
+    if (out_count) *out_count = kk;
+    return INNR_OK;
+  }
+  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  DeviceCtx* ctx;
+  int rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  rc = stage_binary_queries(*ctx, c, query_words, 1);
+  if (rc) return rc;
+  CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
+  CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
+  Timed tm(*ctx);
+  if (op)
+    CU(launch_binary_jaccard_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (float*)ctx->d_scores.p, ctx->stream, &g_launches));
+  else
+    CU(launch_binary_dot_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (uint32_t*)ctx->d_scores.p, ctx->stream, &g_launches));
+  CU(launch_topk_from_scores(ctx->d_scores.p, op ? 1 : 4, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                             ctx->stream, &g_launches));
+  tm.stop();
+  rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) {
+    if (op) {
+      decode_keys_f32(keys, kk, true, out_idx, out_score);
+    } else {
+      for (size_t j = 0; j < kk; ++j) {
+        out_idx[j] = keys[j] & 0xFFFFFFFFull;
+        out_score[j] = (float)(~(uint32_t)(keys[j] >> 32));
+      }
+    }
+  });
+  if (rc) return rc;
+  if (out_count) *out_count = kk;
+  return INNR_OK;
+}
+
 static int hamming_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const uint64_t* dev_query_words, size_t nq, size_t k,
                         uint64_t* dev_keys, cudaStream_t s) {
   if (k <= MAX_FUSED_K) {

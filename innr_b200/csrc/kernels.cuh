@@ -79,7 +79,7 @@ cudaError_t launch_merge_keys(const uint64_t* dev_in, size_t n_lists, size_t nq,
                               uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, cudaStream_t s,
                               LaunchCounter* launches);
 // k smallest keys of a device score vector for ANY k (rounds of <= 128): kind 0 f32 ascending, 1 f32 descending,
-// 2 u32 ascending; ids = index_base + i. Used by every top-k entry when k > 128. dev_mask (one bit per entry, LSB-first
+// 2 u32 ascending, 3 ready-made keys, 4 u32 descending; ids = index_base + i. Used by every top-k entry when k > 128. dev_mask (one bit per entry, LSB-first
 // u32 words) restricts the selection to the entries whose bit is set (batch_knn_filtered with k > 128).
 cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, uint32_t index_base, size_t k,
                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches,

@@ -620,6 +620,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) topk_scores_kernel(const void* s
     if (valid) {
       const unsigned id = ids ? ids[i] : index_base + i;
       if (KIND == 3) key = static_cast<const uint64_t*>(scores)[(size_t)(i / seg_len) * seg_stride + (i % seg_len)];
+      else if (KIND == 4) key = make_key_u32(~static_cast<const uint32_t*>(scores)[i], id);
       else if (KIND == 2) key = make_key_u32(static_cast<const uint32_t*>(scores)[i], id);
       else if (KIND == 1) key = make_key_desc(static_cast<const float*>(scores)[i], id);
       else key = make_key_asc(static_cast<const float*>(scores)[i], id);
@@ -857,10 +858,10 @@ cudaError_t launch_topk_from_scores(const void* dev_scores, int kind, size_t n, 
                                                                ws.partials, ws.group_partials, out, ws.tickets)
     if (kr <= 32) {
       if (kind == 0) INNR_TOPK_LAUNCH(1, 0); else if (kind == 1) INNR_TOPK_LAUNCH(1, 1);
-      else if (kind == 2) INNR_TOPK_LAUNCH(1, 2); else INNR_TOPK_LAUNCH(1, 3);
+      else if (kind == 2) INNR_TOPK_LAUNCH(1, 2); else if (kind == 3) INNR_TOPK_LAUNCH(1, 3); else INNR_TOPK_LAUNCH(1, 4);
     } else {
       if (kind == 0) INNR_TOPK_LAUNCH(4, 0); else if (kind == 1) INNR_TOPK_LAUNCH(4, 1);
-      else if (kind == 2) INNR_TOPK_LAUNCH(4, 2); else INNR_TOPK_LAUNCH(4, 3);
+      else if (kind == 2) INNR_TOPK_LAUNCH(4, 2); else if (kind == 3) INNR_TOPK_LAUNCH(4, 3); else INNR_TOPK_LAUNCH(4, 4);
     }
 #undef INNR_TOPK_LAUNCH
     ++*launches;

@@ -272,6 +272,13 @@ def test_binary_dot_jaccard_scans_exact(ib, oracle, dim):
         assert np.float32(got_j[i]).tobytes() == np.float32(oracle.binary_jaccard(oq, oc)).tobytes(), (dim, i)
     z = ib.PackedBinary.zeros(dim)
     assert float(ib.binary_jaccard_all(z, corpus)[5]) == 1.0 and int(ib.binary_dot_all(z, corpus)[5]) == 0
+    # top-k by similarity == stable descending sort of the full score vectors (ties -> lower index), any k
+    for k in (1, 10, 100, 400, n + 1):
+        for op, full in (("dot", got_dot.astype(np.float32)), ("jaccard", got_j)):
+            idx, sc = ib.binary_topk(op, gq, corpus, k)
+            order = np.lexsort((np.arange(n), -full.astype(np.float64)))[:k]
+            assert idx.tolist() == order.tolist(), (dim, op, k)
+            assert np.array_equal(bits(sc), bits(full[order])), (dim, op, k)
 
 
 # ------------------------------------------------------------------------------------------------ host threads
