@@ -58,6 +58,13 @@ def test_fuzz_f32_knn_scores_filtered_pruning(ib, oracle):
         g, w = ib.batch_l2_squared_pruning(q, gb, thr), oracle.batch_l2_squared_pruning(q, ob, thr)
         assert [i for i, _ in g] == [i for i, _ in w], (tag, "pruning", thr)
         assert np.array_equal(bits([s for _, s in g]), bits([s for _, s in w])), (tag, "pruning")
+        # variance order, reordered and adaptive kNN (src/batch.rs:441-659)
+        assert np.array_equal(bits(ib.batch_dimension_variance(gb)), bits(oracle.batch_dimension_variance(ob))), (tag, "variance")
+        g, w = ib.batch_knn_reordered(q, gb, 9), oracle.batch_knn_reordered(q, ob, 9)
+        assert list(g.indices) == list(w.indices) and np.array_equal(bits(g.scores), bits(w.scores)), (tag, "reordered")
+        wd = int(rng.integers(1, d + 3))
+        g, w = ib.batch_knn_adaptive(q, gb, 6, wd), oracle.batch_knn_adaptive(q, ob, 6, wd)
+        assert list(g.indices) == list(w.indices) and np.array_equal(bits(g.scores), bits(w.scores)), (tag, "adaptive", wd)
 
 
 def test_fuzz_hamming_and_u8(ib, oracle):

@@ -724,7 +724,9 @@ def _maxsim_scale(q, toks, off):
     return out
 
 
-@pytest.mark.parametrize("nq,dim", [(1, 4), (3, 30), (32, 128), (40, 64), (32, 16), (7, 129)])
+@pytest.mark.parametrize("nq,dim", [(1, 4), (3, 30), (32, 128), (40, 64), (32, 16), (7, 129),
+                                    # wide rows: the contraction runs over 256-column chunks, queries re-staged per chunk
+                                    (5, 300), (32, 768), (40, 1001), (300, 132), (33, 256), (2, 2050)])
 def test_maxsim_within_tolerance(ib, oracle, nq, dim):
     rng = np.random.default_rng(nq * 100 + dim)
     lens = rng.integers(0, 200, size=60)
