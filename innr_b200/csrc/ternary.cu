@@ -209,11 +209,16 @@ cudaError_t launch_ternary_scores(const TerView& v, int op, const uint64_t* dev_
   a.out_i32 = dev_out_i32;
   const unsigned grid = (unsigned)((v.n + TER_THREADS - 1) / TER_THREADS);
   const size_t smem = op == 2 ? v.chunks * 64 * sizeof(float) : v.chunks * sizeof(uint4);
-  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  if (smem > 227 * 1024 || op < 0 || op > 2) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {  // wide codes (> 12288 dimensions for the f32 query): opt in to the large carve-out
+    cudaError_t e = op == 0   ? cudaFuncSetAttribute(ternary_scores_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : op == 1 ? cudaFuncSetAttribute(ternary_scores_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(ternary_scores_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   if (op == 0) ternary_scores_kernel<0><<<grid, TER_THREADS, smem, s>>>(a);
   else if (op == 1) ternary_scores_kernel<1><<<grid, TER_THREADS, smem, s>>>(a);
-  else if (op == 2) ternary_scores_kernel<2><<<grid, TER_THREADS, smem, s>>>(a);
-  else return cudaErrorInvalidValue;
+  else ternary_scores_kernel<2><<<grid, TER_THREADS, smem, s>>>(a);
   ++*launches;
   return cudaGetLastError();
 }

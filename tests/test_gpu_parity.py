@@ -574,7 +574,7 @@ def test_hamming_query_batches_share_a_pass(ib, oracle, dim, nq):
 
 
 # ------------------------------------------------------------------------------------------------ ternary
-@pytest.mark.parametrize("dim", [1, 31, 32, 33, 63, 64, 65, 128, 200, 768])
+@pytest.mark.parametrize("dim", [1, 31, 32, 33, 63, 64, 65, 128, 200, 768, 13000])
 def test_ternary_scans_exact(ib, oracle, dim):
     """ternary_dot / ternary_hamming (integer-exact) and ternary::asymmetric_dot (sequential unfused f32 sum, bit-exact)
     of one query against a corpus; top-k in the reference's stable order; encodings derived on the device."""
