@@ -7,7 +7,7 @@
 // sequential, separately rounded multiply and add (src/batch.rs:257-265).
 //
 // Parity pinning: ports of the reference's own unit tests / examples / KATs live
-// in tests/test_oracle_*.py. Items recalled from Rust std and not verifiable
+// in tests/test_ref_*.py and tests/golden/reference_kats.json (tests/test_golden.py). Items recalled from Rust std and not verifiable
 // offline are marked [RECALLED].
 
 #include "innr_ref.h"
