@@ -389,6 +389,8 @@ class MaxSim(Workload):
         self.q_host_t, self.q_host = self.pinned(qs)
         self.q_dev = self.torch.from_numpy(qs).to(self.dev)
         self.out = self.torch.empty(self.n_local, dtype=self.torch.float32, device=self.dev)
+        self.out_host_t = self.torch.empty(self.n_local, dtype=self.torch.float32).pin_memory()  # caller-owned result buffer
+        self.out_host = self.out_host_t.numpy()
         self.units_per_step = self.n  # docs scored per step by the whole job
         self.kernel_bytes = self.n_local * self.nt * self.dim * 4
         self.kernel_name = "maxsim_tc_kernel"
@@ -405,7 +407,7 @@ class MaxSim(Workload):
 
     def step_e2e(self, i):
         import innr_b200 as ib
-        return ib.maxsim_corpus(self.q_host[i % 4], self.shard, cosine=True)
+        return ib.maxsim_corpus(self.q_host[i % 4], self.shard, cosine=True, out=self.out_host)
 
     def cpu_baseline(self, cores, budget_queries=None):
         from oracle import innr_oracle as orc

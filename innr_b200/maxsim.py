@@ -50,9 +50,13 @@ class TokenCorpus:
         return cls(_Handle(h), n_docs, dim, index_base)
 
 
-def maxsim_corpus(query_tokens, corpus: TokenCorpus, cosine: bool = False) -> np.ndarray:
+def maxsim_corpus(query_tokens, corpus: TokenCorpus, cosine: bool = False, out: np.ndarray | None = None) -> np.ndarray:
+    """Scores of every document. `out` (float32, num_docs, C-contiguous) lets the caller own the result buffer, as the
+    C-ABI does -- a page-locked one receives the device->host copy at full PCIe speed."""
     q = _tokens(query_tokens, "query")
-    out = np.zeros(corpus.num_docs, np.float32)
+    if out is None:
+        out = np.zeros(corpus.num_docs, np.float32)
+    assert out.dtype == np.float32 and out.size == corpus.num_docs and out.flags.c_contiguous, "out: float32[num_docs]"
     L.call("innr_cuda_maxsim", corpus.h, q.ctypes.data_as(L.f32p), q.shape[0], q.shape[1] if q.shape[0] else 0,
            1 if cosine else 0, out.ctypes.data_as(L.f32p))
     return out
