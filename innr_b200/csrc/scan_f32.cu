@@ -73,18 +73,22 @@ __device__ __forceinline__ void accumulate2(uint64_t q2, uint64_t v2, uint64_t& 
   }
 }
 
-template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
+template <int MODE, int QB, int R, bool KNN, bool MASKED = false, int UX = 0>
 __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_in) {
   static_assert(MODE != PDX_L2_PRUNE || (QB == 1 && !KNN), "pruning is a single-query scores scan");
   static_assert(MODE != PDX_L2_PERM || (QB == 1 && !MASKED), "the reordered scan is a single-query scan");
   constexpr bool PERM = (MODE == PDX_L2_PERM);
   constexpr bool NEED_SS = (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS);
   constexpr bool NEED_DOT = (MODE != PDX_NORMS);
-  constexpr int U = (QB == 1) ? 8 : 4;  // dimension rows in flight per thread
+  // dimension rows in flight per thread. The sum over d is sequential by contract, so a thread makes D / U round trips
+  // to memory: 8 (4 with eight queries' accumulators) saturate HBM when every SM holds several CTAs; launches with at
+  // most a couple of CTAs per SM (small corpora, small shards, C1) are bound by that latency chain instead and use the
+  // deep variants (UX = 32 / 16).
+  constexpr int U = UX ? UX : ((QB == 1) ? 8 : 4);
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // [d][QB] interleaved queries (padded so the d-loop can read whole float4 groups), then qnorm[QB], then keys
-  const unsigned d_pad = (a_in.d + U - 1) / U * U;
+  const unsigned d_pad = (a_in.d + 31u) / 32u * 32u;  // same for every U (scan_smem_bytes)
   float* sq = reinterpret_cast<float*>(smem_raw);
   float* s_qn = sq + (size_t)d_pad * QB;
   unsigned* s_perm = reinterpret_cast<unsigned*>(s_qn + ((QB + 3) & ~3));  // PERM: d_pad row indices (d_pad % 8 == 0)
@@ -279,9 +283,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
   if (KNN) block_finish<R, QB>(lists, a.nq_valid, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
 }
 
-template <int MODE, int QB, int R, bool KNN, bool MASKED = false>
+template <int MODE, int QB, int R, bool KNN, bool MASKED = false, int UX = 0>
 cudaError_t launch_one(const PdxArgs& a, size_t smem, int ny, int num_sms, cudaStream_t s) {
-  auto kern = pdx_scan_kernel<MODE, QB, R, KNN, MASKED>;
+  auto kern = pdx_scan_kernel<MODE, QB, R, KNN, MASKED, UX>;
   static size_t smem_set_dev[16] = {};
   size_t& smem_set = smem_set_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > smem_set) {
@@ -300,16 +304,15 @@ cudaError_t launch_one(const PdxArgs& a, size_t smem, int ny, int num_sms, cudaS
 }
 
 // grid.x the KNN launch will use (needed to size the merge workspace per query group)
-template <int MODE, int QB, int R>
+template <int MODE, int QB, int R, int UX = 0>
 unsigned knn_grid_x(unsigned n_tiles, size_t smem, int num_sms) {
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pdx_scan_kernel<MODE, QB, R, true>, SCAN_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pdx_scan_kernel<MODE, QB, R, true, false, UX>, SCAN_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
   return balanced_grid(n_tiles, (unsigned)occ * (unsigned)num_sms);
 }
 
 size_t scan_smem_bytes(size_t d, int qb, int k, bool knn, bool perm = false) {
-  const int U = (qb == 1) ? 8 : 4;
-  size_t d_pad = (d + U - 1) / U * U;
+  size_t d_pad = (d + 31) / 32 * 32;
   size_t b = d_pad * qb * sizeof(float) + ((qb + 3) & ~3) * sizeof(float);
   if (perm) b += d_pad * sizeof(unsigned);
   if (knn) b += (size_t)(SCAN_THREADS / 32) * k * sizeof(uint64_t) * qb;  // QB > 1: every warp parks QB lists (block_finish)
@@ -350,9 +353,16 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
     }
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     int ny = 1;
+    // at most ~2 CTAs per SM in the whole launch: the per-thread latency chain binds, use the deep-prefetch variants
+    const size_t groups_left8 = (nq - done + 7) / 8;
+    const bool deep = !big_k && (size_t)a.n_tiles * (qb == 8 ? groups_left8 : 1) <= 2 * (size_t)ws.num_sms;
     if (qb == 8) {
       unsigned gx = 1;
-      if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 8, 1>(a.n_tiles, smem, ws.num_sms);
+      if (deep) {
+        if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
+        else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
+        else gx = knn_grid_x<PDX_COSINE_FUSED, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
+      } else if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 8, 1>(a.n_tiles, smem, ws.num_sms);
       else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 8, 1>(a.n_tiles, smem, ws.num_sms);
       else gx = knn_grid_x<PDX_COSINE_FUSED, 8, 1>(a.n_tiles, smem, ws.num_sms);
       const size_t n_groups = (gx + FINISH_GROUP - 1) / FINISH_GROUP;
@@ -368,7 +378,9 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
     a.out_keys = dev_keys + done * k;
     cudaError_t e;
 #define INNR_DISPATCH(MODE)                                                                          \
-  if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, ny, ws.num_sms, s);                         \
+  if (qb == 8 && deep) e = launch_one<MODE, 8, 1, true, false, 16>(a, smem, ny, ws.num_sms, s);     \
+  else if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, ny, ws.num_sms, s);                    \
+  else if (deep) e = launch_one<MODE, 1, 1, true, false, 32>(a, smem, 1, ws.num_sms, s);             \
   else if (!big_k) e = launch_one<MODE, 1, 1, true>(a, smem, 1, ws.num_sms, s);                      \
   else e = launch_one<MODE, 1, 4, true>(a, smem, 1, ws.num_sms, s);
     if (mode == PDX_DOT) { INNR_DISPATCH(PDX_DOT) }
