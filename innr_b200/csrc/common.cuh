@@ -259,6 +259,64 @@ struct WarpList {
   }
 };
 
+// One candidate per lane for each of QB lists at once (the same vector scored against QB queries). When at least half of
+// the lists would take the batch path, ALL of them run it in lock step: the QB sorting networks are independent chains of
+// shuffles in one basic block, so their latencies overlap instead of adding up (a warp of the 8-query scan spends most
+// of a small shard's time here: every ballot still beats the thresholds). Otherwise each list takes its own path.
+template <int R, int QB>
+__device__ __forceinline__ void offer_multi(WarpList<R> (&lists)[QB], const uint64_t (&key)[QB], bool valid,
+                                            uint64_t (&thr)[QB], int nq_valid, int k, int lane) {
+  unsigned m[QB];
+  int heavy = 0;
+#pragma unroll
+  for (int q = 0; q < QB; ++q) {
+    m[q] = __ballot_sync(FULL_MASK, valid && q < nq_valid && key[q] < thr[q]);
+    heavy += __popc(m[q]) >= (R == 1 ? 10 : 6);
+  }
+  if (heavy * 2 >= QB) {  // warp-uniform
+    uint64_t x[QB];
+#pragma unroll
+    for (int q = 0; q < QB; ++q) x[q] = ((m[q] >> lane) & 1u) ? key[q] : KEY_SENTINEL;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const bool keep_min = ((lane & stride) == 0) == ((lane & size) == 0);
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const uint64_t o = shfl_xor_u64(x[q], stride);
+          x[q] = ((x[q] < o) == keep_min) ? x[q] : o;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) {
+      const uint64_t rev = shfl_u64(x[q], 31 - lane);
+      lists[q].v[R - 1] = rev < lists[q].v[R - 1] ? rev : lists[q].v[R - 1];
+    }
+    if (R == 1) {  // clean-up of all lists, stage by stage
+#pragma unroll
+      for (int st = 16; st >= 1; st >>= 1) {
+        const bool take_max = (lane & st) != 0;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const uint64_t o = shfl_xor_u64(lists[q].v[0], st);
+          lists[q].v[0] = ((lists[q].v[0] < o) != take_max) ? lists[q].v[0] : o;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < QB; ++q) lists[q].bitonic_cleanup(lane);
+    }
+#pragma unroll
+    for (int q = 0; q < QB; ++q) thr[q] = lists[q].at(k - 1);
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < QB; ++q)
+    if (m[q]) lists[q].offer(key[q], valid && q < nq_valid, thr[q], k, lane);
+}
+
 // Merge `n_lists` sorted key lists of length k (stride `stride` u64) from `src` into `list` with bitonic merges.
 // GLOBAL: src is global memory written by other CTAs of this launch -> read through L2 (ld.global.cg).
 template <int R, bool GLOBAL>

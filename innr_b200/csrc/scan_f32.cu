@@ -245,37 +245,48 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
 #pragma unroll
       for (int j = 0; j < VPT; ++j) nrm[j] = (active && i0 + j < a.n) ? a.norms_in[i0 + j] : 0.0f;
     }
-#pragma unroll
-    for (int q = 0; q < QB; ++q) {
-      float s[VPT];
+    auto score = [&](int q, int j) -> float {
+      if (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS) {
+        const float qn = s_qn[q];
+        // src/batch.rs:716-727: qn < eps -> 0 for all; norm > eps ? dot / (qn * norm) : 0
+        float c = 0.0f;
+        if (!(qn < NORM_EPS) && nrm[j] > NORM_EPS) c = __fdiv_rn(acc[q][j], __fmul_rn(qn, nrm[j]));
+        return c;
+      } else if (MODE == PDX_NORMS) {
+        return nrm[j];
+      } else if (MODE == PDX_L2_PRUNE) {
+        return ss[j] > a.threshold ? -1.0f : acc[q][j];  // distances are never negative: -1.0 marks "pruned"
+      }
+      return acc[q][j];
+    };
+    auto make_key = [&](float sc, unsigned i) -> uint64_t {
+      return (MODE == PDX_L2 || MODE == PDX_L2_PERM) ? make_key_asc(sc, a.index_base + i) : make_key_desc(sc, a.index_base + i);
+    };
+    if (KNN && QB > 1) {
+      // vector j of this thread against all QB queries at once: the QB lists are updated in lock step (offer_multi)
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
-        if (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS) {
-          const float qn = s_qn[q];
-          // src/batch.rs:716-727: qn < eps -> 0 for all; norm > eps ? dot / (qn * norm) : 0
-          float c = 0.0f;
-          if (!(qn < NORM_EPS) && nrm[j] > NORM_EPS) c = __fdiv_rn(acc[q][j], __fmul_rn(qn, nrm[j]));
-          s[j] = c;
-        } else if (MODE == PDX_NORMS) {
-          s[j] = nrm[j];
-        } else if (MODE == PDX_L2_PRUNE) {
-          s[j] = ss[j] > a.threshold ? -1.0f : acc[q][j];  // distances are never negative: -1.0 marks "pruned"
-        } else {
-          s[j] = acc[q][j];
-        }
-      }
-      if (KNN) {
-        if (q < a.nq_valid) {
+        const unsigned i = i0 + j;
+        uint64_t key[QB];
 #pragma unroll
-          for (int j = 0; j < VPT; ++j) {
-            const unsigned i = i0 + j;
-            const uint64_t key = (MODE == PDX_L2 || MODE == PDX_L2_PERM) ? make_key_asc(s[j], a.index_base + i)
-                                                  : make_key_desc(s[j], a.index_base + i);
-            lists[q].offer(key, active && i < a.n && (!MASKED || ((nib >> j) & 1u)), thrs[q], a.k, lane);
+        for (int q = 0; q < QB; ++q) key[q] = make_key(score(q, j), i);
+        offer_multi<R, QB>(lists, key, active && i < a.n && (!MASKED || ((nib >> j) & 1u)), thrs, a.nq_valid, a.k, lane);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < QB; ++q) {
+        if (KNN) {
+          if (q < a.nq_valid) {
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+              const unsigned i = i0 + j;
+              lists[q].offer(make_key(score(q, j), i), active && i < a.n && (!MASKED || ((nib >> j) & 1u)), thrs[q], a.k, lane);
+            }
           }
+        } else if (active && q < a.nq_valid) {
+          *reinterpret_cast<float4*>(a.scores_out + (size_t)q * a.ld + i0) =
+              make_float4(score(q, 0), score(q, 1), score(q, 2), score(q, 3));
         }
-      } else if (active && q < a.nq_valid) {
-        *reinterpret_cast<float4*>(a.scores_out + (size_t)q * a.ld + i0) = make_float4(s[0], s[1], s[2], s[3]);
       }
     }
   }
