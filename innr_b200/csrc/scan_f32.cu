@@ -367,9 +367,18 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
     // at most ~2 CTAs per SM in the whole launch: the per-thread latency chain binds, use the deep-prefetch variants
     const size_t groups_left8 = (nq - done + 7) / 8;
     const bool deep = !big_k && (size_t)a.n_tiles * (qb == 8 ? groups_left8 : 1) <= 2 * (size_t)ws.num_sms;
-    if (qb == 8) {
+    // not even one CTA per SM with eight queries per CTA (C1): four per CTA = twice the warps to hide latency with
+    if (qb == 8 && deep && (size_t)a.n_tiles * groups_left8 <= (size_t)ws.num_sms) {
+      qb = 4;
+      smem = scan_smem_bytes(v.d, 4, (int)k, true);
+    }
+    if (qb > 1) {
       unsigned gx = 1;
-      if (deep) {
+      if (qb == 4) {
+        if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 4, 1, 16>(a.n_tiles, smem, ws.num_sms);
+        else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 4, 1, 16>(a.n_tiles, smem, ws.num_sms);
+        else gx = knn_grid_x<PDX_COSINE_FUSED, 4, 1, 16>(a.n_tiles, smem, ws.num_sms);
+      } else if (deep) {
         if (mode == PDX_DOT) gx = knn_grid_x<PDX_DOT, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
         else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
         else gx = knn_grid_x<PDX_COSINE_FUSED, 8, 1, 16>(a.n_tiles, smem, ws.num_sms);
@@ -377,10 +386,10 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
       else if (mode == PDX_L2) gx = knn_grid_x<PDX_L2, 8, 1>(a.n_tiles, smem, ws.num_sms);
       else gx = knn_grid_x<PDX_COSINE_FUSED, 8, 1>(a.n_tiles, smem, ws.num_sms);
       const size_t n_groups = (gx + FINISH_GROUP - 1) / FINISH_GROUP;
-      size_t fit = ws.partials_cap / ((size_t)gx * 8 * k);
-      fit = std::min(fit, ws.group_cap / (n_groups * 8 * k));
+      size_t fit = ws.partials_cap / ((size_t)gx * qb * k);
+      fit = std::min(fit, ws.group_cap / (n_groups * qb * k));
       fit = std::min(fit, ws.tickets_cap / (1 + n_groups));
-      const size_t groups_left = (nq - done + 7) / 8;
+      const size_t groups_left = (nq - done + qb - 1) / qb;
       ny = (int)std::max<size_t>(1, std::min<size_t>(std::min<size_t>(fit, groups_left), 65535));
     }
     const size_t nq_launch = std::min<size_t>(nq - done, (size_t)ny * qb);
@@ -389,7 +398,8 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
     a.out_keys = dev_keys + done * k;
     cudaError_t e;
 #define INNR_DISPATCH(MODE)                                                                          \
-  if (qb == 8 && deep) e = launch_one<MODE, 8, 1, true, false, 16>(a, smem, ny, ws.num_sms, s);     \
+  if (qb == 4) e = launch_one<MODE, 4, 1, true, false, 16>(a, smem, ny, ws.num_sms, s);              \
+  else if (qb == 8 && deep) e = launch_one<MODE, 8, 1, true, false, 16>(a, smem, ny, ws.num_sms, s); \
   else if (qb == 8) e = launch_one<MODE, 8, 1, true>(a, smem, ny, ws.num_sms, s);                    \
   else if (deep) e = launch_one<MODE, 1, 1, true, false, 32>(a, smem, 1, ws.num_sms, s);             \
   else if (!big_k) e = launch_one<MODE, 1, 1, true>(a, smem, 1, ws.num_sms, s);                      \

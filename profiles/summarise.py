@@ -27,9 +27,10 @@ METRICS = [
 ]
 # which launch rows matter for traffic.json: (workload, kernel substring, pick) -- pick = "max" takes the longest launch
 DOMINANT = {"knn_cosine_1q": "pdx_scan_kernel", "hamming": "hamming_kernel", "u8": "u8_scan_kernel",
-            "maxsim": "maxsim_tc_kernel", "knn_cosine_multi": "knn_tc_filter_kernel"}
+            "maxsim": "maxsim_tc_kernel", "knn_cosine_multi": "knn_tc_filter_kernel", "batch_demo": "pdx_scan_kernel"}
 ALGORITHMIC = {"knn_cosine_1q": 30_720_000_000, "hamming": 12_800_000_000, "u8": 19_200_000_000,
-               "maxsim": 92_160_000_000, "knn_cosine_multi": 10_000_000 * 768 * 2}
+               "maxsim": 92_160_000_000, "knn_cosine_multi": 10_000_000 * 768 * 2,
+               "batch_demo": 10_000 * 128 * 4 * 25}  # 25 groups of 4 queries each read the (L2-resident) corpus once
 UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 
 
