@@ -29,3 +29,14 @@ for n in (2_000, 20_000, 200_000, 1_250_000):
     us = timeit(sk, q, 1, 10)
     print(f"f32 cosine n={n:>9} k= 10: {us:8.1f} us  (stream floor {n*768*4/6.544e12*1e6:7.1f} us)")
     del b, sk
+for n in (2_000, 20_000, 200_000, 1_250_000):
+    b = ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, 0, n, 768)
+    q = synth.ghash_f32(synth.SALT_QUERY, 0, 768)
+    for name in ("batch_dot", "batch_l2_squared"):
+        fn = getattr(ib, name)
+        for _ in range(3): fn(q, b)
+        ms = []
+        for _ in range(20):
+            fn(q, b); ms.append(ib.last_kernel_ms())
+        print(f"{name} n={n:>9}: kernel {float(np.median(ms))*1e3:8.1f} us  (stream floor {n*768*4/6.544e12*1e6:7.1f} us)")
+    del b

@@ -579,6 +579,19 @@ cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query
   size_t smem = scan_smem_bytes(v.d, 1, 0, false, mode == PDX_L2_PERM);
   if (smem > 227 * 1024 || (mode == PDX_L2_PERM && !dev_perm)) return cudaErrorInvalidValue;
   cudaError_t e;
+  // few tiles (<= 2 per SM): the D / U round trips of each thread bind, not HBM -> deep-prefetch instantiations
+  const bool deep = (size_t)a.n_tiles <= 2 * (size_t)ws.num_sms;
+  if (deep && (mode == PDX_DOT || mode == PDX_L2 || mode == PDX_NORMS || mode == PDX_COSINE_NORMS || mode == PDX_COSINE_FUSED)) {
+    switch (mode) {
+      case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false, false, 32>(a, smem, 1, ws.num_sms, s); break;
+      case PDX_L2: e = launch_one<PDX_L2, 1, 1, false, false, 32>(a, smem, 1, ws.num_sms, s); break;
+      case PDX_NORMS: e = launch_one<PDX_NORMS, 1, 1, false, false, 32>(a, smem, 1, ws.num_sms, s); break;
+      case PDX_COSINE_NORMS: e = launch_one<PDX_COSINE_NORMS, 1, 1, false, false, 32>(a, smem, 1, ws.num_sms, s); break;
+      default: e = launch_one<PDX_COSINE_FUSED, 1, 1, false, false, 32>(a, smem, 1, ws.num_sms, s); break;
+    }
+    if (e == cudaSuccess) ++*launches;
+    return e;
+  }
   switch (mode) {
     case PDX_L2_PERM: e = launch_one<PDX_L2_PERM, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
     case PDX_DOT: e = launch_one<PDX_DOT, 1, 1, false>(a, smem, 1, ws.num_sms, s); break;
