@@ -334,13 +334,13 @@ size_t scan_smem_bytes(size_t d, int qb, int k, bool knn, bool perm = false) {
 
 unsigned pdx_max_grid(int num_sms) { return (unsigned)num_sms * 8u; }
 
-cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
-                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
+namespace {
+// the arguments every scan launch shares. Columns actually scanned: n rounded up to a whole float4 (the row pitch is a
+// multiple of 4, so the last float4 is in bounds); a prefix view (n << ld) scans only its own columns.
+PdxArgs base_args(const PdxView& v, const Workspace& ws, size_t k) {
   PdxArgs a{};
   a.data = v.data;
   a.ld = v.ld;
-  // columns actually scanned: n rounded up to a whole float4 (the row pitch is a multiple of 4, so the last float4 is
-  // in bounds); a prefix view (n << ld) scans only its own columns
   a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
   a.n = (unsigned)v.n;
   a.d = (unsigned)v.d;
@@ -351,6 +351,14 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
   a.partials = ws.partials;
   a.group_partials = ws.group_partials;
   a.tickets = ws.tickets;
+  a.nq_valid = 1;
+  return a;
+}
+}  // namespace
+
+cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries, size_t nq, size_t k,
+                           uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
+  PdxArgs a = base_args(v, ws, k);
   const bool big_k = k > 32;
   // query blocking: 8 queries share one pass over the corpus when their lists fit in registers; several groups of 8
   // run as grid.y of ONE launch as long as their merge workspaces fit (small corpora / many queries: C1, sample pass)
@@ -418,21 +426,8 @@ cudaError_t launch_pdx_knn(const PdxView& v, int mode, const float* dev_queries,
 
 cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, const uint32_t* dev_mask, size_t k,
                                     uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
-  PdxArgs a{};
-  a.data = v.data;
-  a.ld = v.ld;
-  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
-  a.n = (unsigned)v.n;
-  a.d = (unsigned)v.d;
-  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
-  a.index_base = v.index_base;
-  a.one = 1.0f;
-  a.k = (int)k;
-  a.partials = ws.partials;
-  a.group_partials = ws.group_partials;
-  a.tickets = ws.tickets;
+  PdxArgs a = base_args(v, ws, k);
   a.queries = dev_query;
-  a.nq_valid = 1;
   a.out_keys = dev_keys;
   a.mask = dev_mask;
   const size_t smem = scan_smem_bytes(v.d, 1, (int)k, true);
@@ -445,21 +440,8 @@ cudaError_t launch_pdx_knn_filtered(const PdxView& v, const float* dev_query, co
 
 cudaError_t launch_pdx_knn_reordered(const PdxView& v, const float* dev_query, const uint32_t* dev_perm, size_t k,
                                      uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
-  PdxArgs a{};
-  a.data = v.data;
-  a.ld = v.ld;
-  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
-  a.n = (unsigned)v.n;
-  a.d = (unsigned)v.d;
-  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
-  a.index_base = v.index_base;
-  a.one = 1.0f;
-  a.k = (int)k;
-  a.partials = ws.partials;
-  a.group_partials = ws.group_partials;
-  a.tickets = ws.tickets;
+  PdxArgs a = base_args(v, ws, k);
   a.queries = dev_query;
-  a.nq_valid = 1;
   a.out_keys = dev_keys;
   a.perm = dev_perm;
   const size_t smem = scan_smem_bytes(v.d, 1, (int)k, true, true);
@@ -559,20 +541,9 @@ cudaError_t launch_dimension_variance(const PdxView& v, float* dev_out, cudaStre
 cudaError_t launch_pdx_scores(const PdxView& v, int mode, const float* dev_query, const float* dev_norms,
                               float* dev_out, Workspace& ws, cudaStream_t s, LaunchCounter* launches, float threshold,
                               const uint32_t* dev_perm) {
-  PdxArgs a{};
+  PdxArgs a = base_args(v, ws, 0);
   a.perm = dev_perm;
-  a.data = v.data;
-  a.ld = v.ld;
-  // columns actually scanned: n rounded up to a whole float4 (the row pitch is a multiple of 4, so the last float4 is
-  // in bounds); a prefix view (n << ld) scans only its own columns
-  a.ld4 = (unsigned)std::min<size_t>(v.ld, (v.n + 3) / 4 * 4);
-  a.n = (unsigned)v.n;
-  a.d = (unsigned)v.d;
-  a.n_tiles = (unsigned)(((size_t)a.ld4 + TILE - 1) / TILE);
-  a.index_base = v.index_base;
-  a.one = 1.0f;
   a.queries = dev_query;
-  a.nq_valid = 1;
   a.scores_out = dev_out;
   a.norms_in = dev_norms;
   a.threshold = threshold;
