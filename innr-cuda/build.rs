@@ -2,7 +2,7 @@
 use std::{env, path::PathBuf, process::Command};
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
-    let srcs = ["api.cu", "scan_f32.cu", "layout.cu", "hamming.cu", "u8.cu", "maxsim.cu", "maxsim_tc.cu", "knn_tc.cu"];
+    let srcs = ["api.cu", "scan_f32.cu", "layout.cu", "hamming.cu", "ternary.cu", "u8.cu", "maxsim.cu", "maxsim_tc.cu", "knn_tc.cu"];
     let mut objs = vec![];
     for s in srcs {
         let o = out.join(s).with_extension("o");

@@ -67,6 +67,19 @@ extern "C" {
     pub fn innr_cuda_generate_tokens(salt: u64, first_doc: u64, n_docs: usize, tokens_per_doc: usize, dim: usize, index_base: u64, out: *mut *mut innr_cuda_corpus) -> c_int;
     pub fn innr_cuda_maxsim(c: *const innr_cuda_corpus, q_tokens: *const f32, n_q: usize, q_dim: usize, cosine_flag: c_int, out_scores: *mut f32) -> c_int;
     pub fn innr_cuda_maxsim_dev(c: *const innr_cuda_corpus, dev_q: *const f32, n_q: usize, cosine_flag: c_int, dev_scores: *mut f32, stream: *mut c_void) -> c_int;
+    // sharded entries, prefix views, MaxSim batches, ternary codes, binary top-k ------- include/innr_cuda.h
+    pub fn innr_cuda_batch_knn_sharded(shards: *const *const innr_cuda_corpus, n_shards: usize, metric: c_int, queries: *const f32, n_queries: usize, q_len: usize, k: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
+    pub fn innr_cuda_batch_knn_u8_sharded(shards: *const *const innr_cuda_corpus, n_shards: usize, queries: *const f32, n_queries: usize, q_len: usize, k: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
+    pub fn innr_cuda_binary_topk(c: *const innr_cuda_corpus, op: c_int, query_words: *const u64, query_dim_bits: usize, k: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
+    pub fn innr_cuda_encode_ternary(v: *const f32, n: usize, threshold: f32, out_words: *mut u64) -> c_int;
+    pub fn innr_cuda_hamming_topk_sharded(shards: *const *const innr_cuda_corpus, n_shards: usize, q: *const u64, n_queries: usize, q_dim_bits: usize, k: usize, out_idx: *mut u64, out_dist: *mut u32, out_count: *mut usize) -> c_int;
+    pub fn innr_cuda_maxsim_batch(c: *const innr_cuda_corpus, q_tokens: *const f32, n_queries: usize, n_q: usize, q_dim: usize, cosine_flag: c_int, out_scores: *mut f32) -> c_int;
+    pub fn innr_cuda_maxsim_batch_dev(c: *const innr_cuda_corpus, dev_q: *const f32, n_queries: usize, n_q: usize, cosine_flag: c_int, dev_scores: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn innr_cuda_prefix_view(c: *const innr_cuda_corpus, prefix_dim: usize, out: *mut *mut innr_cuda_corpus) -> c_int;
+    pub fn innr_cuda_ternary_from_f32(f32_corpus: *const innr_cuda_corpus, threshold: f32, out: *mut *mut innr_cuda_corpus) -> c_int;
+    pub fn innr_cuda_ternary_scores_all(c: *const innr_cuda_corpus, op: c_int, query: *const c_void, query_dim: usize, out_f32: *mut f32, out_i32: *mut i32) -> c_int;
+    pub fn innr_cuda_ternary_topk(c: *const innr_cuda_corpus, op: c_int, query: *const c_void, query_dim: usize, k: usize, out_idx: *mut u64, out_score: *mut f32, out_count: *mut usize) -> c_int;
+    pub fn innr_cuda_upload_ternary(words: *const u64, n: usize, dimension: usize, index_base: u64, out: *mut *mut innr_cuda_corpus) -> c_int;
 }
 
 // ---- safe wrappers: same panics, same results ----
