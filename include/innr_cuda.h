@@ -61,7 +61,7 @@ const char* innr_cuda_backend_name(void);
 int innr_cuda_dense_backend(size_t len, int* out_is_cuda);
 /* Tuning knobs (process-wide). Names: "knn_tc" (1/0: tensor-core filter path for large dot/cosine query batches),
  * "knn_tc_min_n" (corpus size from which it is used, default 100000), "knn_tc_min_queries" (default 2; 1 sends single queries through the filter too),
- * "maxsim_tc" (1/0: tcgen05 MaxSim when dim is 32/64/96/128), "u8_scaled_chains" (1/0: PRMT + FFMA2
+ * "maxsim_tc" (1/0: tcgen05 MaxSim when dim <= 128 is a multiple of 4), "u8_scaled_chains" (1/0: PRMT + FFMA2
  * chains scaled by 2^-23 in the u8 scan when the query allows it). Results never depend on them. */
 int innr_cuda_set_option(const char* name, double value);
 /* Statistics of the most recent batch_knn call that went through the tensor-core filter (csrc/knn_tc.cu): time of the

@@ -1802,7 +1802,7 @@ static int maxsim_common(const innr_cuda_corpus* c, DeviceCtx* ctx, const float*
     if (c->n) CU(cudaMemsetAsync(dev_scores, 0, c->n * sizeof(float), s));
     return INNR_OK;
   }
-  // tcgen05/TMEM path when the shape fits (dim 32/64/96/128; query tokens in groups of 32); option "maxsim_tc" = 0 forces the CUDA-core kernel
+  // tcgen05/TMEM path when the shape fits (dim <= 128, a multiple of 4; query tokens in groups of 32); option "maxsim_tc" = 0 forces the CUDA-core kernel
   TokView tv = tok_view(c);
   cudaError_t e = (g_opt.maxsim_tc && maxsim_tc_supported(tv, n_q))
                       ? launch_maxsim_tc(tv, dev_q, n_q, cosine, dev_scores, ctx->ws.num_sms, s, &g_launches)

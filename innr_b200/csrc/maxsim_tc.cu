@@ -76,6 +76,7 @@ struct TcArgs {
   const float* inv_norms;  // per token 1/||x|| (0 for ||x||^2 <= 1e-18), cosine only
   unsigned long long uniform_tokens, total_tokens;
   unsigned n_docs, n_q;
+  unsigned dim;  // token dimension (a multiple of 4, <= 32 P): the columns up to 32 P are zero-filled by TMA / the query staging
   const float* q;
   int debug_mode;  // 0 normal; 1 = TMA streaming only; 2 = hi pass only; 4 = no epilogue math (profiling aids)
   int accumulate;  // 0: out[doc] = sum; 1: out[doc] += sum (second and later groups of 32 query tokens)
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
   auto q_row = [&](int r, bool& qvalid) -> const float* {
     const bool second = G > 1 && a.split && r >= NQ;
     qvalid = (G > 1 && a.split) ? (second ? r - NQ < (int)a.n_q_b : r < (int)a.n_q) : r < (int)a.n_q;
-    return second ? a.q_b + (size_t)(r - NQ) * DIM : a.q + (size_t)r * DIM;
+    return second ? a.q_b + (size_t)(r - NQ) * a.dim : a.q + (size_t)r * a.dim;
   };
   if (COSINE) {  // 1/||q_r|| once per query token (one thread per row), not once per element
     if ((int)threadIdx.x < NQG) {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       const float* qp = q_row((int)threadIdx.x, qvalid);
       float aa = 0.0f;
       if (qvalid)
-        for (int kk = 0; kk < DIM; ++kk) aa = fmaf(qp[kk], qp[kk], aa);
+        for (int kk = 0; kk < (int)a.dim; ++kk) aa = fmaf(qp[kk], qp[kk], aa);
       // a query token with ~zero norm scores cosine 0 against every token (x86_64.rs:781-785)
       st->q_inv[threadIdx.x] = (qvalid && aa > EPS_SQ) ? 1.0f / sqrtf(aa) : 0.0f;
     }
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const int r = idx / DIM, k = idx % DIM;
     bool qvalid;
     const float* qsrc = q_row(r, qvalid);
-    float v = qvalid ? qsrc[k] : 0.0f;
+    float v = (qvalid && k < (int)a.dim) ? qsrc[k] : 0.0f;
     if (COSINE) v *= st->q_inv[r];
     const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     const float lo = v - hi;
@@ -519,7 +520,9 @@ __global__ void token_inv_norms_kernel(const float* __restrict__ tokens, size_t 
 }  // namespace
 
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim) {
-  if (dim == 0 || dim % 32 != 0 || dim > 128 || total_tokens == 0) return false;
+  // TMA needs a 16-byte row pitch; a row that is not a whole number of 32-column panels is completed with zeros by the
+  // out-of-bounds fill of the last box
+  if (dim == 0 || dim % 4 != 0 || dim > 128 || total_tokens == 0) return false;
   return make_tmap_f32_rows(m, dev_tokens, total_tokens, dim, CHUNK);
 }
 
@@ -531,10 +534,10 @@ cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens,
   return cudaGetLastError();
 }
 
-// dim 32 / 64 / 96 / 128; up to 64 query tokens per corpus pass, more in several passes (the sum over query tokens is
+// dim <= 128, a multiple of 4 (panels of 32 columns, the last one zero-filled by TMA); up to 64 query tokens per corpus pass, more in several passes (the sum over query tokens is
 // additive across passes)
 bool maxsim_tc_supported(const TokView& v, size_t n_q) {
-  return v.dim >= 32 && v.dim <= 128 && v.dim % 32 == 0 && n_q >= 1 && n_q <= 8 * NQ && v.total_tokens > 0 &&
+  return v.dim >= 4 && v.dim <= 128 && v.dim % 4 == 0 && n_q >= 1 && n_q <= 8 * NQ && v.total_tokens > 0 &&
          v.tmap_valid && v.inv_norms != nullptr && v.total_tokens < 0x7FFFFF00ull;
 }
 
@@ -556,11 +559,11 @@ cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, 
 }
 template <bool COSINE, int G>
 cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
-  switch (dim) {
-    case 32: return launch_shape<COSINE, 1, G>(tm, a, grid, s);
-    case 64: return launch_shape<COSINE, 2, G>(tm, a, grid, s);
-    case 96: return launch_shape<COSINE, 3, G>(tm, a, grid, s);
-    case 128: return launch_shape<COSINE, 4, G>(tm, a, grid, s);
+  switch ((dim + 31) / 32) {  // panels of 32 columns; TMA zero-fills the columns of the last panel past `dim`
+    case 1: return launch_shape<COSINE, 1, G>(tm, a, grid, s);
+    case 2: return launch_shape<COSINE, 2, G>(tm, a, grid, s);
+    case 3: return launch_shape<COSINE, 3, G>(tm, a, grid, s);
+    case 4: return launch_shape<COSINE, 4, G>(tm, a, grid, s);
   }
   return cudaErrorInvalidValue;
 }
@@ -577,6 +580,7 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   a.uniform_tokens = v.uniform_tokens;
   a.total_tokens = v.total_tokens;
   a.n_docs = (unsigned)v.n_docs;
+  a.dim = (unsigned)v.dim;
   a.out = dev_scores;
   static const int dbg = getenv("INNR_MAXSIM_DEBUG") ? atoi(getenv("INNR_MAXSIM_DEBUG")) : 0;
   a.debug_mode = dbg;
@@ -614,6 +618,7 @@ cudaError_t launch_maxsim_tc_batch(const TokView& v, const float* dev_q, size_t 
   a.uniform_tokens = v.uniform_tokens;
   a.total_tokens = v.total_tokens;
   a.n_docs = (unsigned)v.n_docs;
+  a.dim = (unsigned)v.dim;
   unsigned grid = (unsigned)num_sms;
   const unsigned long long tiles = (v.total_tokens + TILE_M - 1) / TILE_M;
   if (grid > tiles) grid = (unsigned)tiles;

@@ -792,7 +792,7 @@ def test_maxsim_tc_stream_edges(ib, oracle, shape, nq):
         assert np.all(got[lens == 0] == 0.0)
 
 
-@pytest.mark.parametrize("dim", [32, 64, 96, 128])
+@pytest.mark.parametrize("dim", [32, 64, 96, 128, 4, 20, 36, 48, 100, 124])  # not a multiple of 32: TMA zero-fills the last panel
 @pytest.mark.parametrize("nq", [1, 33, 64, 100])
 def test_maxsim_tc_dims_and_query_groups(ib, oracle, dim, nq):
     """tcgen05 path at every supported token dimension, and with more than 32 query tokens (one corpus pass per group
