@@ -537,7 +537,7 @@ cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens,
 // dim <= 128, a multiple of 4 (panels of 32 columns, the last one zero-filled by TMA); up to 64 query tokens per corpus pass, more in several passes (the sum over query tokens is
 // additive across passes)
 bool maxsim_tc_supported(const TokView& v, size_t n_q) {
-  return v.dim >= 4 && v.dim <= 128 && v.dim % 4 == 0 && n_q >= 1 && n_q <= 8 * NQ && v.total_tokens > 0 &&
+  return v.dim >= 4 && v.dim <= 128 && v.dim % 4 == 0 && n_q >= 1 && v.total_tokens > 0 &&
          v.tmap_valid && v.inv_norms != nullptr && v.total_tokens < 0x7FFFFF00ull;
 }
 

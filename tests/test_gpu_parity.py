@@ -726,7 +726,8 @@ def _maxsim_scale(q, toks, off):
 
 @pytest.mark.parametrize("nq,dim", [(1, 4), (3, 30), (32, 128), (40, 64), (32, 16), (7, 129),
                                     # wide rows: the contraction runs over 256-column chunks, queries re-staged per chunk
-                                    (5, 300), (32, 768), (40, 1001), (300, 132), (33, 256), (2, 2050)])
+                                    (5, 300), (32, 768), (40, 1001), (300, 132), (33, 256), (2, 2050),
+                                    (300, 128), (700, 64)])  # many query tokens on the tcgen05 path: passes of 64
 def test_maxsim_within_tolerance(ib, oracle, nq, dim):
     rng = np.random.default_rng(nq * 100 + dim)
     lens = rng.integers(0, 200, size=60)
