@@ -167,3 +167,15 @@ def test_golden_configs_cuda():
     qs = ghash_f32(SQ, s["nq"] * s["d"]).reshape(s["nq"], s["d"])
     idx, sc = ib.batch_knn_u8_many(qs, c8, s["k"])
     assert np.array_equal(idx.astype(np.uint32), GOLD["c5_idx"]) and np.array_equal(bits(sc), GOLD["c5_score_bits"])
+
+
+def test_host_generators_match_oracle(oracle):
+    """innr_b200/synth.py (numpy twin of the device generators, used for bench and test queries) against the oracle's
+    C++ generators: same splitmix64 stream, same 24-bit f32 mapping, for arbitrary salts and offsets (wrap-around too)."""
+    from innr_b200 import synth
+    for salt, first, count in ((synth.SALT_CORPUS, 0, 1000), (synth.SALT_QUERY, 12345, 777), (synth.SALT_CODES, 2**40 + 5, 64),
+                               (0xFFFFFFFFFFFFFFF0, 0, 64), (0, 0, 3)):
+        assert np.array_equal(synth.ghash_u64(salt, first, count), oracle.ghash_u64(salt, first, count)), (salt, first)
+        a, b = synth.ghash_f32(salt, first, count), oracle.ghash_f32(salt, first, count)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (salt, first)
+        assert float(a.min()) >= -1.0 and float(a.max()) < 1.0
