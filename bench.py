@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the innr batch similarity-search hot path on B200.
+"""bench.py -- benchmark of the innr batch similarity-search hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME|all] [--impl reference] [--sharding nccl|inproc]
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
-A "step" is one pass of the hot path over one batch of synthetic input. The default workload is the configuration
-BASELINE.json's metric is quoted on: batch_knn_cosine top-10 over a 10M x 768 f32 corpus, one query per step,
-row-sharded over the N GPUs (one allgather of k keys + merge per query). Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path over one batch of synthetic input. Prints ONE JSON line on rank 0.
+
+The headline (top-level keys) is the configuration BASELINE.json's metric is quoted on -- C2a: batch_knn_cosine top-10
+over a 10M x 768 f32 corpus, one query per step, row-sharded over the N GPUs. With the default `--workload all` the same
+line also carries `workloads`: one entry per BASELINE.json config (C1 batch_demo, C2a, C2b 1024-query batches, C3 MaxSim
+docs/s, C4 Hamming top-100, C5 u8 kNN), each measured back to back in this process with the same K / W and with its own
+value / ms_per_step / e2e / roofline / clocks (and cpu_baseline at N == 1). `--workload NAME` measures that one only.
 
   value     queries/s (docs/s for maxsim) of the whole job, inputs resident in HBM, CUDA events, max over ranks
   e2e       the same metric through the public API with HOST buffers (pinned H2D of the query, D2H of the result)
-  roofline  dominant kernel: algorithmic bytes per launch / its CUDA-event time, against MEASURED_PEAKS.json
-  cpu_baseline  the oracle (C++ restatement of innr 0.6.3, "port") timed on this box's host cores on a bounded sample
+  roofline  dominant kernel: algorithmic bytes (or flops) per launch / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle (C++ restatement of innr 0.6.3, "port") timed on this box's host cores: one query per thread
+            over ALL rows of the config when host RAM allows (else the largest prefix that fits, flagged `extrapolated`)
 
-Workloads: knn_cosine_1q (default, C2a) | knn_cosine_multi (C2b, --queries Q) | batch_demo (C1) | maxsim (C3) |
-hamming (C4) | u8 (C5) | knn_cosine_1q_filter (C2a through the f16 filter path, an option). `--scale f` shrinks the corpus (for quick checks; reported in config).
+`--impl reference` times that CPU implementation as its own arm (rank 0 only), one step = one query per host thread over
+the whole config. `--scale f` shrinks every corpus (quick checks; reported in config).
 """
 import argparse
 import ctypes as C
+import gc
 import json
 import os
 import statistics
@@ -33,15 +39,78 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (description, metric name, unit)
-    "knn_cosine_1q": ("batch_knn_cosine 10M x 768 f32, 1 query/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
-    "knn_cosine_multi": ("batch_knn_cosine 10M x 768 f32, Q queries/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
-    "knn_cosine_1q_filter": ("batch_knn_cosine 10M x 768 f32, 1 query/step, k=10, through the f16 tensor-core filter + exact rescoring (option knn_tc_min_queries=1; same bits as the scan)", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
-    "batch_demo": ("batch_knn_dot 10K x 128 f32 G-ref lattice, 100 queries/step, k=10", "batch_knn_dot_top10_queries_per_s", "queries/s"),
-    "maxsim": ("maxsim_cosine 32 x 128 query tokens vs 1M docs x 180 tokens x 128d", "maxsim_cosine_docs_per_s", "docs/s"),
-    "hamming": ("binary_hamming top-100 over 100M 1024-bit codes, 1 query/step", "hamming_top100_queries_per_s", "queries/s"),
-    "u8": ("batch_knn_u8 50M x 384 u8 corpus, f32 query, k=10, 1 query/step", "batch_knn_u8_top10_queries_per_s", "queries/s"),
+    # name: (config id, description, metric name, unit)
+    "knn_cosine_1q": ("C2a", "batch_knn_cosine 10M x 768 f32, 1 query/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
+    "knn_cosine_multi": ("C2b", "batch_knn_cosine 10M x 768 f32, Q queries/step, k=10", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
+    "knn_cosine_1q_filter": ("C2a-filter", "batch_knn_cosine 10M x 768 f32, 1 query/step, k=10, through the f16 tensor-core filter + exact rescoring (option knn_tc_min_queries=1; same bits as the scan)", "batch_knn_cosine_top10_queries_per_s", "queries/s"),
+    "batch_demo": ("C1", "batch_knn_dot 10K x 128 f32 G-ref lattice, 100 queries/step, k=10", "batch_knn_dot_top10_queries_per_s", "queries/s"),
+    "maxsim": ("C3", "maxsim_cosine 32 x 128 query tokens vs 1M docs x 180 tokens x 128d", "maxsim_cosine_docs_per_s", "docs/s"),
+    "hamming": ("C4", "binary_hamming top-100 over 100M 1024-bit codes, 1 query/step", "hamming_top100_queries_per_s", "queries/s"),
+    "u8": ("C5", "batch_knn_u8 50M x 384 u8 corpus, f32 query, k=10, 1 query/step", "batch_knn_u8_top10_queries_per_s", "queries/s"),
 }
+HEADLINE = "knn_cosine_1q"
+ALL_ORDER = ["knn_cosine_1q", "knn_cosine_multi", "hamming", "u8", "batch_demo", "maxsim"]  # C3 last: it needs 93 GB
+PORT_NOTE = " (C++ restatement of innr 0.6.3, not the Rust crate)"
+
+
+def corpus_shape(workload, scale):
+    """(rows, bytes per row) of the config at `scale`."""
+    if workload == "batch_demo":
+        return int(10_000 * scale), 128 * 4
+    if workload in ("knn_cosine_1q", "knn_cosine_multi", "knn_cosine_1q_filter"):
+        return int(10_000_000 * scale), 768 * 4
+    if workload == "maxsim":
+        return int(1_000_000 * scale), 180 * 128 * 4
+    if workload == "hamming":
+        return int(100_000_000 * scale), 128
+    return int(50_000_000 * scale), 384
+
+
+def config_of(workload, scale, n_gpus, queries=1024):
+    """The `config` object -- identical in the b200 and reference arms (it names the workload, not the implementation)."""
+    n, row_bytes = corpus_shape(workload, scale)
+    gb = n * row_bytes / 1e9
+    desc = WORKLOADS[workload][1].replace("Q queries/step", f"{queries} queries/step")
+    return {"workload": desc, "id": WORKLOADS[workload][0], "scale": scale, "corpus_gb": round(gb, 3), "sharding": f"rows/{n_gpus}",
+            "l2": "inputs larger than L2 (corpus >> 126 MB), no flush" if gb / n_gpus > 0.5
+            else ("corpus is L2-resident by design of this config (latency-bound); no flush" if workload == "batch_demo"
+                  else "scaled-down corpus (quick check): may be L2-resident; no flush"),
+            "generator": "G-ref lattice" if workload == "batch_demo" else "G-hash (splitmix64)"}
+
+
+def host_mem_available():
+    """Bytes of host RAM this process may still take: min(system available, cgroup limit - usage)."""
+    avail = None
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            a, b = open(lim).read().strip(), open(cur).read().strip()
+            if a != "max" and int(a) < (1 << 60):
+                left = int(a) - int(b)
+                avail = left if avail is None else min(avail, left)
+        except Exception:
+            pass
+    return avail if avail is not None else 32 << 30
+
+
+def plan_cpu_sample(n_rows, row_bytes, per_thread_bytes_per_row, cores, full=True, max_rows=None):
+    """How many rows and threads the CPU leg can use: all rows and all cores when they fit in 80 % of the free host
+    RAM (corpus + one query's working set per thread), else fewer threads, else a prefix of the rows."""
+    budget = int(host_mem_available() * 0.8)
+    rows = n_rows if max_rows is None else min(n_rows, max_rows)
+    if not full:
+        return rows, cores  # small samples always fit
+    threads = cores
+    while threads > 1 and rows * (row_bytes + threads * per_thread_bytes_per_row) > budget:
+        threads -= 1
+    if rows * (row_bytes + threads * per_thread_bytes_per_row) > budget:
+        rows = max(1, budget // (row_bytes + threads * per_thread_bytes_per_row))
+    return rows, threads
 
 
 def load_traffic(workload, scale, world):
@@ -183,11 +252,16 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ workloads
 class Workload:
-    """One config of BASELINE.json on this rank's shard. Subclasses fill: setup(), step_dev(i), step_e2e(i),
-    units_per_step, kernel_bytes (algorithmic bytes of the dominant kernel per launch on THIS rank), launches."""
+    """One config of BASELINE.json on this rank's shard. __init__ fixes the shape and the host-side queries (no device
+    needed: the reference arm uses only that and the cpu_* methods); setup() builds the device shard.
+    Subclasses fill: step_dev(i), step_e2e(i), units_per_step, kernel_bytes (algorithmic bytes of the dominant kernel per
+    launch on THIS rank), cpu_prepare(cores, full) / cpu_step()."""
+    kernel_timed_by_keys_entry = False
 
-    def __init__(self, args, rank, world, torch):
-        self.args, self.rank, self.world, self.torch = args, rank, world, torch
+    def __init__(self, args, workload, rank, world):
+        self.args, self.workload, self.rank, self.world = args, workload, rank, world
+        self.torch = None
+        self._cpu = None
 
     @property
     def dev(self):
@@ -209,44 +283,88 @@ class Workload:
         self.torch.cuda.current_stream().synchronize()
         return self._h_idx, self._h_sc
 
+    def close(self):
+        """Drop the device shard (and the CPU sample) before the next workload is built."""
+        for name in ("sk", "shard", "q_dev", "out", "_cpu", "_h_idx", "_h_sc", "inproc"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        gc.collect()
+        if self.torch is not None:
+            self.torch.cuda.empty_cache()
+
+    # ---- CPU leg (oracle): one step = one query per host thread over the planned rows -------------------------------
+    def cpu_measure(self, cores, full=True, steps=1, warmup=0, budget_s=None):
+        """Returns (value in the workload's unit for the FULL config, info dict, seconds per step). When fewer rows than
+        the config's are used the rate is scaled by rows/N and `extrapolated` is true. budget_s bounds the whole run: if
+        the first warm-up step over all rows shows that W + K such steps would not fit, the remaining steps use the
+        prefix of the rows that does (the full-rows step time is reported beside the value)."""
+        t_start = time.perf_counter()
+        self.cpu_prepare(cores, full)
+        full_rows_step_s = None
+        for i in range(warmup):
+            _, dt = self.cpu_step()
+            left = steps + warmup - 1 - i
+            if i == 0 and budget_s and self._cpu["scales_with_rows"]:
+                remaining = max(budget_s - (time.perf_counter() - t_start), 0.05 * budget_s)
+                if dt * left > remaining:
+                    full_rows_step_s = dt
+                    self.cpu_prepare(cores, full, max_rows=max(1000, int(self._cpu["rows"] * remaining / (dt * left))))
+        dts, units = [], 0
+        for _ in range(steps):
+            u, dt = self.cpu_step()
+            units += u
+            dts.append(dt)
+        c = self._cpu
+        scale = c["rows"] / c["n"] if c["scales_with_rows"] else 1.0
+        value = units / sum(dts) * scale
+        info = {"cores": c["threads"], "rows": c["rows"], "rows_of_config": c["n"], "extrapolated": c["rows"] < c["n"] and c["scales_with_rows"],
+                "sample": c["sample"] + PORT_NOTE, "build_s": round(c["build_s"], 2)}
+        if full_rows_step_s is not None:
+            info["full_rows_step_s"] = round(full_rows_step_s, 3)
+            info["full_rows_value"] = c["threads"] / full_rows_step_s
+        return value, info, sum(dts) / len(dts)
+
 
 class KnnF32(Workload):
-    def setup(self):
-        import innr_b200 as ib
-        from innr_b200 import sharded, synth
-        a = self.args
-        demo = a.workload == "batch_demo"
-        self.n = int((10_000 if demo else 10_000_000) * a.scale)
-        self.d = 128 if demo else 768
-        self.k = 10
+    def __init__(self, args, workload, rank, world):
+        super().__init__(args, workload, rank, world)
+        from innr_b200 import synth
+        demo = workload == "batch_demo"
+        self.demo = demo
+        self.n, self.d, self.k = corpus_shape(workload, args.scale)[0], (128 if demo else 768), 10
         self.metric = "dot" if demo else "cosine"
-        self.nq = 100 if demo else (a.queries if a.workload == "knn_cosine_multi" else 1)
-        lo, hi = sharded.shard_range(self.n, self.rank, self.world)
-        self.n_local = hi - lo
-        gen, salt = ("gref", 0) if demo else ("ghash", synth.SALT_CORPUS)
-        self.shard = ib.DeviceBatch.generate(gen, salt, lo, self.n_local, self.d, index_base=lo)
-        self.sk = sharded.ShardedKnn(self.shard, "f32", self.metric)
+        self.nq = 100 if demo else (args.queries if workload == "knn_cosine_multi" else 1)
         n_distinct = 16
         if demo:
-            from innr_b200.synth import ghash_f32  # noqa: F401
             qs = np.stack([self._gref(self.d, 50_000 + j) for j in range(self.nq)])[None].repeat(n_distinct, 0)
         else:
             qs = synth.ghash_f32(synth.SALT_QUERY, 0, n_distinct * self.nq * self.d).reshape(n_distinct, self.nq, self.d)
-        self.q_host_t, self.q_host = self.pinned(qs)
-        self.q_dev = self.torch.from_numpy(qs).to(self.dev)
+        self.q_np = np.ascontiguousarray(qs)
         self.units_per_step = self.nq
+        self.h2d, self.d2h = self.nq * self.d * 4, self.nq * self.k * 12
+
+    def setup(self, torch):
+        import innr_b200 as ib
+        from innr_b200 import sharded, synth
+        self.torch = torch
+        lo, hi = sharded.shard_range(self.n, self.rank, self.world)
+        self.n_local = hi - lo
+        gen, salt = ("gref", 0) if self.demo else ("ghash", synth.SALT_CORPUS)
+        self.shard = ib.DeviceBatch.generate(gen, salt, lo, self.n_local, self.d, index_base=lo)
+        self.sk = sharded.ShardedKnn(self.shard, "f32", self.metric)
+        self.q_host_t, self.q_host = self.pinned(self.q_np)
+        self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         passes = (self.nq + 7) // 8 if self.nq > 1 else 1
         self.kernel_bytes = self.n_local * self.d * 4 * passes
         self.kernel_name = "pdx_scan_kernel"
-        if a.workload == "knn_cosine_1q_filter":
+        ib.set_option("knn_tc_min_queries", 2)
+        if self.workload == "knn_cosine_1q_filter":
             # the bytes the filter actually streams: the f16 unit-vector copy (the f32 corpus is only touched by the
             # ~200 rescored rows); reported against HBM like the scan
             ib.set_option("knn_tc_min_queries", 1)
             self.kernel_bytes = self.n_local * self.d * 2
             self.kernel_name = "knn_tc_filter_kernel<QRES> (4 passes + exact rescoring: whole call)"
-        self.launches = passes + 1  # scan launch(es) + merge/decode
-        self.h2d, self.d2h = self.nq * self.d * 4, self.nq * self.k * 12
-        self.corpus_gb = self.n * self.d * 4 / 1e9
+        self.kernel_timed_by_keys_entry = True
 
     @staticmethod
     def _gref(dim, seed):
@@ -267,42 +385,62 @@ class KnnF32(Workload):
         idx, sc = self.sk.knn_dev(dq, self.nq, self.k)
         return self.fetch(idx, sc)
 
-    def cpu_baseline(self, cores, budget_queries=None):
+    def keys_entry(self, L, q, b, stream):
+        L.call("innr_cuda_batch_knn_keys_dev", self.shard.h, self.sk._metric_id, C.c_void_p(q.data_ptr()), self.nq, self.k,
+               C.c_void_p(b["local"].data_ptr()), stream)
+
+    def cpu_prepare(self, cores, full, max_rows=None):
         from oracle import innr_oracle as orc
         from innr_b200 import synth
-        a = self.args
-        n_s = min(self.n, 10_000 if a.workload == "batch_demo" else (200_000 if budget_queries else 1_000_000))
-        if getattr(self, "_cpu_sample", (None,))[0] != n_s:  # built once, reused by every step of the reference arm
-            rows = (np.stack([orc.generate_embedding(self.d, i) for i in range(n_s)]) if a.workload == "batch_demo"
-                    else orc.ghash_f32(synth.SALT_CORPUS, 0, n_s * self.d).reshape(n_s, self.d))
-            self._cpu_sample = (n_s, orc.VerticalBatch.from_flat(rows.reshape(-1), n_s, self.d))
-        ob = self._cpu_sample[1]
-        nq = budget_queries or (4096 * cores if a.workload == "batch_demo" else 16 * cores)
-        qs = np.ascontiguousarray(self.q_host.reshape(-1, self.d)[:1].repeat(nq, 0))
+        # per query and thread the reference holds norms + scores (8 B/row) and the (usize, f32) pairs it sorts plus the
+        # stable sort's scratch (32 B/row)
+        rows, threads = plan_cpu_sample(self.n, self.d * 4, 40, cores, full, max_rows or (None if full else 200_000))
+        if self._cpu and self._cpu["rows"] == rows:
+            self._cpu["threads"] = threads
+            return
         t0 = time.perf_counter()
-        orc.batch_knn_many(self.metric, qs, ob, self.k, n_threads=cores)
-        dt = time.perf_counter() - t0
-        return nq / dt * (n_s / self.n), f"{nq} queries over the first {n_s} of {self.n} rows x {self.d}, one query per thread; rate scaled by {n_s}/{self.n} (path is linear in N)", dt
+        if self.demo:
+            ob = orc.VerticalBatch.from_flat(np.stack([orc.generate_embedding(self.d, i) for i in range(rows)]).reshape(-1), rows, self.d)
+        else:
+            ob = orc.ghash_vertical_batch(synth.SALT_CORPUS, 0, rows, self.d, cores)
+        what = "all" if rows == self.n else "the first"
+        self._cpu = {"rows": rows, "n": self.n, "threads": threads, "batch": ob, "scales_with_rows": True, "build_s": time.perf_counter() - t0,
+                     "sample": (f"one step = {self.nq} queries (the config's batch) spread over {threads} threads" if self.demo
+                                else f"one step = {threads} queries, one per thread,") + f" over {what} {rows} of {self.n} rows x {self.d}"}
+
+    def cpu_step(self):
+        from oracle import innr_oracle as orc
+        c = self._cpu
+        nq = self.nq if self.demo else c["threads"]
+        flat = self.q_np.reshape(-1, self.d)
+        qs = np.ascontiguousarray(flat[np.arange(nq) % flat.shape[0]])
+        t0 = time.perf_counter()
+        orc.batch_knn_many(self.metric, qs, c["batch"], self.k, n_threads=c["threads"])
+        return nq, time.perf_counter() - t0
 
 
 class Hamming(Workload):
-    def setup(self):
+    def __init__(self, args, workload, rank, world):
+        super().__init__(args, workload, rank, world)
+        from innr_b200 import synth
+        self.n, self.dim, self.k, self.nq = corpus_shape(workload, args.scale)[0], 1024, 100, 1
+        self.q_np = synth.ghash_u64(synth.SALT_QUERY, 0, 16 * 16).reshape(16, 16).view(np.int64)
+        self.units_per_step = 1
+        self.h2d, self.d2h = 128, self.k * 16
+
+    def setup(self, torch):
         import innr_b200 as ib
         from innr_b200 import sharded, synth
-        self.n, self.dim, self.k, self.nq = int(100_000_000 * self.args.scale), 1024, 100, 1
+        self.torch = torch
         lo, hi = sharded.shard_range(self.n, self.rank, self.world)
         self.n_local = hi - lo
         self.shard = ib.BinaryCorpus.generate(synth.SALT_CODES, lo, self.n_local, self.dim, index_base=lo)
         self.sk = sharded.ShardedKnn(self.shard, "binary")
-        qs = synth.ghash_u64(synth.SALT_QUERY, 0, 16 * 16).reshape(16, 16).view(np.int64)
-        self.q_host_t, self.q_host = self.pinned(qs)
-        self.q_dev = self.torch.from_numpy(qs).to(self.dev)
-        self.units_per_step = 1
+        self.q_host_t, self.q_host = self.pinned(self.q_np)
+        self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         self.kernel_bytes = self.n_local * 128
         self.kernel_name = "hamming_kernel"
-        self.launches = 2
-        self.h2d, self.d2h = 128, self.k * 16
-        self.corpus_gb = self.n * 128 / 1e9
+        self.kernel_timed_by_keys_entry = True
 
     def step_dev(self, i):
         return self.sk.knn_dev(self.q_dev[i % 16], 1, self.k)
@@ -315,40 +453,57 @@ class Hamming(Workload):
         idx, ds = self.sk.knn_dev(dq, 1, self.k)
         return self.fetch(idx, ds)
 
-    def cpu_baseline(self, cores, budget_queries=None):
+    def keys_entry(self, L, q, b, stream):
+        L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, C.c_void_p(q.data_ptr()), self.nq, self.k,
+               C.c_void_p(b["local"].data_ptr()), stream)
+
+    def cpu_prepare(self, cores, full, max_rows=None):
         from oracle import innr_oracle as orc
         from innr_b200 import synth
-        n_s = min(self.n, 2_000_000 if budget_queries else 10_000_000)
-        if getattr(self, "_cpu_sample", (None,))[0] != n_s:
-            self._cpu_sample = (n_s, orc.ghash_u64(synth.SALT_CODES, 0, n_s * 16).reshape(n_s, 16))
-        codes = self._cpu_sample[1]
-        nq = budget_queries or 8 * cores
-        qs = np.ascontiguousarray(self.q_host.view(np.uint64)[:1].repeat(nq, 0))
+        # per query and thread: the (usize, u32) pairs the caller sorts + the stable sort's scratch (32 B/code)
+        rows, threads = plan_cpu_sample(self.n, 128, 32, cores, full, max_rows or (None if full else 2_000_000))
+        if self._cpu and self._cpu["rows"] == rows:
+            self._cpu["threads"] = threads
+            return
         t0 = time.perf_counter()
-        orc.hamming_topk_many(qs, codes, self.k, n_threads=cores)
-        dt = time.perf_counter() - t0
-        return nq / dt * (n_s / self.n), f"{nq} queries over the first {n_s} of {self.n} codes; rate scaled by {n_s}/{self.n}", dt
+        codes = orc.ghash_u64_mt(synth.SALT_CODES, 0, rows * 16, cores).reshape(rows, 16)
+        what = "all" if rows == self.n else "the first"
+        self._cpu = {"rows": rows, "n": self.n, "threads": threads, "codes": codes, "scales_with_rows": True, "build_s": time.perf_counter() - t0,
+                     "sample": f"one step = {threads} queries, one per thread, over {what} {rows} of {self.n} codes x 1024 bit"}
+
+    def cpu_step(self):
+        from oracle import innr_oracle as orc
+        c = self._cpu
+        nq = c["threads"]
+        qs = np.ascontiguousarray(self.q_np.view(np.uint64)[np.arange(nq) % 16])
+        t0 = time.perf_counter()
+        orc.hamming_topk_many(qs, c["codes"], self.k, n_threads=c["threads"])
+        return nq, time.perf_counter() - t0
 
 
 class U8(Workload):
-    def setup(self):
+    def __init__(self, args, workload, rank, world):
+        super().__init__(args, workload, rank, world)
+        from innr_b200 import synth
+        self.n, self.d, self.k, self.nq = corpus_shape(workload, args.scale)[0], 384, 10, 1
+        self.q_np = synth.ghash_f32(synth.SALT_QUERY, 0, 16 * self.d).reshape(16, self.d)
+        self.units_per_step = 1
+        self.h2d, self.d2h = self.d * 4, self.k * 12
+
+    def setup(self, torch):
         import innr_b200 as ib
         from innr_b200 import sharded, synth
-        self.n, self.d, self.k, self.nq = int(50_000_000 * self.args.scale), 384, 10, 1
+        self.torch = torch
         lo, hi = sharded.shard_range(self.n, self.rank, self.world)
         self.n_local = hi - lo
         self.params = ib.QuantizationParams.from_range(-1.0, 1.0)
         self.shard = ib.U8Corpus.generate(synth.SALT_CORPUS, lo, self.n_local, self.d, self.params, index_base=lo)
         self.sk = sharded.ShardedKnn(self.shard, "u8")
-        qs = synth.ghash_f32(synth.SALT_QUERY, 0, 16 * self.d).reshape(16, self.d)
-        self.q_host_t, self.q_host = self.pinned(qs)
-        self.q_dev = self.torch.from_numpy(qs).to(self.dev)
-        self.units_per_step = 1
+        self.q_host_t, self.q_host = self.pinned(self.q_np)
+        self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         self.kernel_bytes = self.n_local * self.d
         self.kernel_name = "u8_scan_kernel"
-        self.launches = 2
-        self.h2d, self.d2h = self.d * 4, self.k * 12
-        self.corpus_gb = self.n * self.d / 1e9
+        self.kernel_timed_by_keys_entry = True
 
     def step_dev(self, i):
         return self.sk.knn_dev(self.q_dev[i % 16], 1, self.k)
@@ -361,42 +516,59 @@ class U8(Workload):
         idx, sc = self.sk.knn_dev(dq, 1, self.k)
         return self.fetch(idx, sc)
 
-    def cpu_baseline(self, cores, budget_queries=None):
+    def keys_entry(self, L, q, b, stream):
+        L.call("innr_cuda_batch_knn_u8_keys_dev", self.shard.h, C.c_void_p(q.data_ptr()), self.nq, self.k,
+               C.c_void_p(b["local"].data_ptr()), stream)
+
+    def cpu_prepare(self, cores, full, max_rows=None):
         from oracle import innr_oracle as orc
         from innr_b200 import synth
-        n_s = min(self.n, 500_000 if budget_queries else 2_000_000)
-        p = orc.QuantizationParams.from_range(-1.0, 1.0)
-        if getattr(self, "_cpu_sample", (None,))[0] != n_s:
-            self._cpu_sample = (n_s, orc.quantize_u8(orc.ghash_f32(synth.SALT_CORPUS, 0, n_s * self.d), p).data.reshape(n_s, self.d))
-        mat = self._cpu_sample[1]
-        nq = budget_queries or 32 * cores
-        qs = np.ascontiguousarray(self.q_host[:1].repeat(nq, 0))
+        # per query and thread: scores (4 B/row), the (usize, f32) pairs + the stable sort's scratch (32 B/row)
+        rows, threads = plan_cpu_sample(self.n, self.d, 36, cores, full, max_rows or (None if full else 500_000))
+        if self._cpu and self._cpu["rows"] == rows:
+            self._cpu["threads"] = threads
+            return
         t0 = time.perf_counter()
-        orc.batch_knn_u8_many(qs, mat, p, self.k, n_threads=cores)
-        dt = time.perf_counter() - t0
-        return nq / dt * (n_s / self.n), f"{nq} queries over the first {n_s} of {self.n} rows x {self.d}; rate scaled by {n_s}/{self.n}", dt
+        p = orc.QuantizationParams.from_range(-1.0, 1.0)
+        mat = orc.ghash_u8_rows(synth.SALT_CORPUS, 0, rows, self.d, p, cores)
+        what = "all" if rows == self.n else "the first"
+        self._cpu = {"rows": rows, "n": self.n, "threads": threads, "mat": mat, "params": p, "scales_with_rows": True,
+                     "build_s": time.perf_counter() - t0,
+                     "sample": f"one step = {threads} queries, one per thread, over {what} {rows} of {self.n} rows x {self.d}"}
+
+    def cpu_step(self):
+        from oracle import innr_oracle as orc
+        c = self._cpu
+        nq = c["threads"]
+        qs = np.ascontiguousarray(self.q_np[np.arange(nq) % 16])
+        t0 = time.perf_counter()
+        orc.batch_knn_u8_many(qs, c["mat"], c["params"], self.k, n_threads=c["threads"])
+        return nq, time.perf_counter() - t0
 
 
 class MaxSim(Workload):
-    def setup(self):
+    def __init__(self, args, workload, rank, world):
+        super().__init__(args, workload, rank, world)
+        from innr_b200 import synth
+        self.n, self.nt, self.dim, self.nq = corpus_shape(workload, args.scale)[0], 180, 128, 32
+        self.q_np = synth.ghash_f32(synth.SALT_QUERY, 0, 4 * self.nq * self.dim).reshape(4, self.nq, self.dim)
+        self.units_per_step = self.n  # docs scored per step by the whole job
+
+    def setup(self, torch):
         import innr_b200 as ib
         from innr_b200 import sharded, synth
-        self.n, self.nt, self.dim, self.nq = int(1_000_000 * self.args.scale), 180, 128, 32
+        self.torch = torch
         lo, hi = sharded.shard_range(self.n, self.rank, self.world)
         self.n_local = hi - lo
         self.shard = ib.TokenCorpus.generate(synth.SALT_CORPUS, lo, self.n_local, self.nt, self.dim, index_base=lo)
-        qs = synth.ghash_f32(synth.SALT_QUERY, 0, 4 * self.nq * self.dim).reshape(4, self.nq, self.dim)
-        self.q_host_t, self.q_host = self.pinned(qs)
-        self.q_dev = self.torch.from_numpy(qs).to(self.dev)
-        self.out = self.torch.empty(self.n_local, dtype=self.torch.float32, device=self.dev)
-        self.out_host_t = self.torch.empty(self.n_local, dtype=self.torch.float32).pin_memory()  # caller-owned result buffer
+        self.q_host_t, self.q_host = self.pinned(self.q_np)
+        self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
+        self.out = torch.empty(self.n_local, dtype=torch.float32, device=self.dev)
+        self.out_host_t = torch.empty(self.n_local, dtype=torch.float32).pin_memory()  # caller-owned result buffer
         self.out_host = self.out_host_t.numpy()
-        self.units_per_step = self.n  # docs scored per step by the whole job
         self.kernel_bytes = self.n_local * self.nt * self.dim * 4
         self.kernel_name = "maxsim_tc_kernel"
-        self.launches = 1
         self.h2d, self.d2h = self.nq * self.dim * 4, self.n_local * 4
-        self.corpus_gb = self.n * self.nt * self.dim * 4 / 1e9
 
     def step_dev(self, i):
         from innr_b200 import _lib as L
@@ -409,89 +581,227 @@ class MaxSim(Workload):
         import innr_b200 as ib
         return ib.maxsim_corpus(self.q_host[i % 4], self.shard, cosine=True, out=self.out_host)
 
-    def cpu_baseline(self, cores, budget_queries=None):
+    def cpu_prepare(self, cores, full, max_rows=None):
         from oracle import innr_oracle as orc
         from innr_b200 import synth
-        n_s = min(self.n, (250 if budget_queries else 2000) * cores)
-        reps = 1 if budget_queries else 24
-        if getattr(self, "_cpu_sample", (None,))[0] != n_s:
-            self._cpu_sample = (n_s, orc.ghash_f32(synth.SALT_CORPUS, 0, n_s * self.nt * self.dim).reshape(n_s * self.nt, self.dim))
-        toks = self._cpu_sample[1]
-        off = np.arange(0, n_s * self.nt + 1, self.nt, dtype=np.uint64)
+        # documents are independent and identical in shape: the rate does not depend on how many are scored, so a prefix
+        # is an exact sample of the config (no extrapolation involved); all docs when they fit in host RAM
+        rows, threads = plan_cpu_sample(self.n, self.nt * self.dim * 4, 0, cores, full, max_rows or (None if full else 250 * cores))
+        if self._cpu and self._cpu["rows"] == rows:
+            return
         t0 = time.perf_counter()
-        for r in range(reps):
-            orc.maxsim_corpus(self.q_host[r % self.q_host.shape[0]], toks, off, cosine_flag=True, n_threads=cores)
-        dt = time.perf_counter() - t0
-        return n_s * reps / dt, f"{n_s} docs x {self.nt} tokens x {self.dim}d scored {reps}x, docs split over threads", dt
+        toks = orc.ghash_f32_mt(synth.SALT_CORPUS, 0, rows * self.nt * self.dim, cores).reshape(rows * self.nt, self.dim)
+        off = np.arange(0, rows * self.nt + 1, self.nt, dtype=np.uint64)
+        what = "all" if rows == self.n else "the first"
+        self._cpu = {"rows": rows, "n": self.n, "threads": cores, "toks": toks, "off": off, "scales_with_rows": False, "i": 0,
+                     "build_s": time.perf_counter() - t0,
+                     "sample": f"one step = {what} {rows} of {self.n} docs x {self.nt} tokens x {self.dim}d scored once, docs split over {cores} threads"}
+
+    def cpu_step(self):
+        from oracle import innr_oracle as orc
+        c = self._cpu
+        q = self.q_np[c["i"] % 4]
+        c["i"] += 1
+        t0 = time.perf_counter()
+        orc.maxsim_corpus(q, c["toks"], c["off"], cosine_flag=True, n_threads=c["threads"])
+        return c["rows"], time.perf_counter() - t0
 
 
-def make_workload(args, rank, world, torch):
-    cls = {"knn_cosine_1q": KnnF32, "knn_cosine_1q_filter": KnnF32, "knn_cosine_multi": KnnF32, "batch_demo": KnnF32, "maxsim": MaxSim,
-           "hamming": Hamming, "u8": U8}[args.workload]
-    return cls(args, rank, world, torch)
-
-
-# ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank):
-    """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be built here) on this
-    box's host cores, all threads, on a bounded sample per step."""
-    if rank != 0:
-        return
-    desc, metric, unit = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-
-    w = make_workload(args, 0, 1, None)  # no device: only the query generators and cpu_baseline() are used
-    # queries only (no device): reuse the generators directly
-    from innr_b200 import synth
-    if isinstance(w, KnnF32):
-        demo = args.workload == "batch_demo"
-        w.n, w.d, w.k = int((10_000 if demo else 10_000_000) * args.scale), (128 if demo else 768), 10
-        w.metric = "dot" if demo else "cosine"
-        w.q_host = (np.stack([KnnF32._gref(w.d, 50_000 + j) for j in range(4)]) if demo
-                    else synth.ghash_f32(synth.SALT_QUERY, 0, 4 * w.d).reshape(4, w.d))
-    elif isinstance(w, Hamming):
-        w.n, w.k = int(100_000_000 * args.scale), 100
-        w.q_host = synth.ghash_u64(synth.SALT_QUERY, 0, 16 * 16).reshape(16, 16).view(np.int64)
-    elif isinstance(w, U8):
-        w.n, w.d, w.k = int(50_000_000 * args.scale), 384, 10
-        w.q_host = synth.ghash_f32(synth.SALT_QUERY, 0, 16 * w.d).reshape(16, w.d)
-    else:
-        w.n, w.nt, w.dim, w.nq = int(1_000_000 * args.scale), 180, 128, 32
-        w.q_host = synth.ghash_f32(synth.SALT_QUERY, 0, 4 * w.nq * w.dim).reshape(4, w.nq, w.dim)
-    for _ in range(args.warmup):
-        w.cpu_baseline(cores, budget_queries=cores)
-    vals, total = [], 0.0
-    sample = ""
-    for _ in range(args.steps):
-        v, sample, dt = w.cpu_baseline(cores, budget_queries=cores)
-        vals.append(v)
-        total += dt
-    value = len(vals) / sum(1.0 / v for v in vals)  # harmonic mean == total units / total time
-    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(args.workload),
-            "data": "synthetic", "config": {"workload": desc, "scale": args.scale},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
-                             "sample": sample + " (C++ restatement of innr 0.6.3, not the Rust crate)"},
-            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+def make_workload(args, workload, rank, world):
+    cls = {"knn_cosine_1q": KnnF32, "knn_cosine_1q_filter": KnnF32, "knn_cosine_multi": KnnF32, "batch_demo": KnnF32,
+           "maxsim": MaxSim, "hamming": Hamming, "u8": U8}[workload]
+    return cls(args, workload, rank, world)
 
 
 def dtype_of(workload):
     return {"hamming": "u64", "u8": "f32xu8"}.get(workload, "f32")
 
 
-# ------------------------------------------------------------------------------------------------ main
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be built here) on this
+    box's host cores: one step = one query per host thread over ALL rows of the config (the largest prefix that fits in
+    host RAM otherwise, flagged `extrapolated`)."""
+    if rank != 0:
+        return
+    workload = HEADLINE if args.workload == "all" else args.workload
+    _, _, metric, unit = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    w = make_workload(args, workload, 0, 1)
+    value, info, s_per_step = w.cpu_measure(cores, full=not args.ref_small_sample, steps=args.steps, warmup=args.warmup,
+                                            budget_s=args.ref_budget_s)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(workload),
+            "data": "synthetic", "config": config_of(workload, args.scale, args.gpus, args.queries),
+            "cpu_baseline": {"value": value, "unit": unit, "kind": "port", **info},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm
+def measure(w, args, env):
+    """Builds the workload's shard, times K steps device-resident (CUDA events, barrier + synchronize on both sides, max
+    over ranks), the dominant kernel alone, and K steps end to end with host buffers. Returns the workload's entry."""
+    torch, dist, ib = env["torch"], env["dist"], env["ib"]
+    rank, world, local_rank = env["rank"], env["world"], env["local_rank"]
+    from innr_b200 import _lib as L
+    steps, warmup = args.steps, args.warmup
+    cid, _, metric, unit = WORKLOADS[w.workload]
+    w.setup(torch)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timed region ---------------------------------------------------------------
+    for i in range(warmup):
+        w.step_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    sampler.mark_begin()
+    ev[0].record()
+    for i in range(steps):
+        kev[i][0].record()
+        w.step_dev(i)
+        kev[i][1].record()
+    ev[1].record()
+    barrier()
+    sampler.mark_end()
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
+    launches = ib.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in kev]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel alone: CUDA events around the library's scan launch only, on the launching stream ----------
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if w.kernel_timed_by_keys_entry:
+        b = w.sk._buffers(w.nq, w.k, w.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times = []
+        for i in range(min(steps, 20)):
+            q = w.q_dev[i % w.q_dev.shape[0]]
+            e0.record()
+            w.keys_entry(L, q, b, stream)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        kern_ms = sum(times) / len(times)
+    else:
+        kern_ms = sum(step_ms) / len(step_ms)
+    tc = ib.knn_tc_last_stats() if w.workload == "knn_cosine_multi" else None
+    barrier()
+
+    # ---- end-to-end through the public API with host buffers ---------------------------------------------
+    for i in range(min(warmup, 3)):
+        w.step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        w.step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+
+    value = w.units_per_step * steps / (total_ms / 1e3)
+    e2e_value = w.units_per_step * steps / e2e_s
+    peak, peak_src = load_peaks()
+    achieved = w.kernel_bytes / (kern_ms / 1e3) / 1e9
+    if w.workload == "batch_demo":
+        # the 5 MB corpus is L2-resident by construction: no HBM roofline applies; the launch is latency-bound
+        roofline = {"bound": "latency", "kernel": w.kernel_name, "achieved": achieved, "peak": None, "unit": "GB/s (from L2)",
+                    "frac": None, "traffic": load_traffic(w.workload, args.scale, world),
+                    "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms,
+                    "note": "corpus (5.12 MB) is L2-resident: one launch scores 100 queries; HBM fraction is not meaningful"}
+    else:
+        roofline = {"bound": "hbm", "kernel": w.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": load_traffic(w.workload, args.scale, world),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms}
+    if tc and tc["passes"] > 0 and tc["filter_ms"] > 0:
+        # large query batches: the dominant kernel is the tcgen05 filter (csrc/knn_tc.cu); algorithmic flops per launch =
+        # 2 * rows * d * queries of THIS rank, time = CUDA events around that launch inside the library
+        tpeak, tsrc = load_tensor_peak()
+        flops = 2.0 * w.n_local * w.d * w.nq
+        tf = flops / (tc["filter_ms"] / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "knn_tc_filter_kernel (kind::f16, exact rescoring after it)",
+                    "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None,
+                    "peak_source": tsrc, "algorithmic_flops_per_launch": flops, "kernel_ms": tc["filter_ms"],
+                    "call_ms": tc["total_ms"], "filter_passes": tc["passes"], "rescored_pairs": tc["candidates"],
+                    "exact_scan_queries": tc["exact_scan_queries"]}
+    if w.workload == "maxsim":
+        # secondary view (north_star asks for tensor-pipe utilisation): MMA flops the kernel issues per launch -- per
+        # 128-token tile one kind::tf32 MMA of N = 64 ([Qhi;Qlo]) and one of N = 32 (Xlo x Qhi), K = 128 -- against the
+        # TF32 dense peak, taken as half the measured bf16 figure (not measured separately: stated assumption)
+        tpeak, tsrc = load_tensor_peak()
+        issued = 2.0 * w.n_local * w.nt * w.dim * (64 + 32)
+        roofline["tensor"] = {"issued_tflops": issued / (kern_ms / 1e3) / 1e12, "tf32_peak_assumed": tpeak / 2,
+                              "frac": issued / (kern_ms / 1e3) / 1e12 / (tpeak / 2), "peak_source": tsrc + " / 2",
+                              "logical_flops_per_launch": 2.0 * w.n_local * w.nt * w.dim * w.nq}
+    entry = None
+    if rank == 0:
+        entry = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": dtype_of(w.workload), "data": "synthetic",
+            "config": config_of(w.workload, args.scale, world, args.queries),
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "clocks": clocks,
+        }
+    return entry
+
+
+def cpu_baseline_entry(w, unit, cache):
+    """The oracle on this box's host cores for workload w (rank 0, N == 1 only): one step over the full config."""
+    cores = os.cpu_count() or 1
+    key = (type(w).__name__, w.n, getattr(w, "d", 0), getattr(w, "metric", ""))
+    if key in cache:  # C2b scores the same corpus with the same per-query function as C2a: one query per thread either way
+        out = dict(cache[key])
+        out["sample"] = "same measurement as C2a (a 1024-query batch is 1024 independent single-query calls on the CPU): " + out["sample"]
+        return out
+    value, info, s_per_step = w.cpu_measure(cores, full=True, steps=1, warmup=0)
+    out = {"value": value, "unit": unit, "kind": "port", "step_s": round(s_per_step, 3), **info}
+    if not getattr(w, "demo", False) and w.workload != "maxsim":
+        # the small cache-resident sample the round-1 figures were extrapolated from, for comparison
+        w._cpu = None
+        v2, info2, _ = w.cpu_measure(cores, full=False, steps=1, warmup=0)
+        out["small_sample"] = {"value": v2, "rows": info2["rows"], "extrapolated": True}
+    cache[key] = out
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="knn_cosine_1q", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all"])
     ap.add_argument("--queries", type=int, default=1024, help="queries per step for knn_cosine_multi")
     ap.add_argument("--scale", type=float, default=1.0, help="corpus size multiplier (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-small-sample", action="store_true",
+                    help="reference arm: score a small prefix of the rows and scale (the round-1 behaviour)")
+    ap.add_argument("--ref-budget-s", type=float, default=420.0,
+                    help="reference arm: wall-clock bound of the whole run; if W + K full-size steps would exceed it, the "
+                         "steps after the first use the prefix of the rows that fits (flagged extrapolated)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -514,129 +824,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     ib.init(local_rank)
+    env = {"torch": torch, "dist": dist, "ib": ib, "rank": rank, "world": world, "local_rank": local_rank}
 
-    desc, metric, unit = WORKLOADS[args.workload]
-    w = make_workload(args, rank, world, torch)
-    w.setup()
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident timed region ---------------------------------------------------------------
-    for i in range(args.warmup):
-        w.step_dev(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    names = ALL_ORDER if args.workload == "all" else [args.workload]
+    entries, cpu_cache = {}, {}
+    t_all = time.perf_counter()
+    for name in names:
+        t0 = time.perf_counter()
+        w = make_workload(args, name, rank, world)
+        try:
+            entry = measure(w, args, env)
+            if rank == 0 and world == 1 and not args.no_cpu_baseline:
+                w.close()  # device memory first: the CPU leg needs the host RAM, not the GPU
+                entry["cpu_baseline"] = cpu_baseline_entry(w, WORKLOADS[name][3], cpu_cache)
+        except Exception as e:  # one workload must not take the headline down with it
+            if name == names[0]:
+                raise
+            entry = {"error": f"{type(e).__name__}: {e}"[:400]} if rank == 0 else None
+        finally:
+            w.close()
+        if rank == 0:
+            entry["wall_s"] = round(time.perf_counter() - t0, 1)
+            entries[name] = entry
     if rank == 0:
-        sampler.start()
-    l0 = ib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.mark_begin()
-    ev[0].record()
-    for i in range(args.steps):
-        kev[i][0].record()
-        w.step_dev(i)
-        kev[i][1].record()
-    ev[1].record()
-    barrier()
-    sampler.mark_end()
-    total_ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
-    launches = ib.launch_count() - l0
-    step_ms = [a.elapsed_time(b) for a, b in kev]
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- dominant kernel alone (N == 1: the step IS one scan launch + a 1-warp merge) ------------------
-    # kernel time = CUDA events around the library's scan launch only, on the launching stream
-    from innr_b200 import _lib as L
-    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    kern_ms = None
-    if hasattr(w, "sk"):
-        b = w.sk._buffers(w.nq, w.k, w.dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        times = []
-        for i in range(min(args.steps, 20)):
-            q = w.q_dev[i % w.q_dev.shape[0]]
-            e0.record()
-            if w.sk.kind == "f32":
-                L.call("innr_cuda_batch_knn_keys_dev", w.shard.h, w.sk._metric_id, C.c_void_p(q.data_ptr()), w.nq, w.k,
-                       C.c_void_p(b["local"].data_ptr()), stream)
-            elif w.sk.kind == "u8":
-                L.call("innr_cuda_batch_knn_u8_keys_dev", w.shard.h, C.c_void_p(q.data_ptr()), w.nq, w.k,
-                       C.c_void_p(b["local"].data_ptr()), stream)
-            else:
-                L.call("innr_cuda_hamming_topk_keys_dev", w.shard.h, C.c_void_p(q.data_ptr()), w.nq, w.k,
-                       C.c_void_p(b["local"].data_ptr()), stream)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        kern_ms = sum(times) / len(times)
-    else:
-        kern_ms = sum(step_ms) / len(step_ms)
-    barrier()
-
-    # ---- end-to-end through the public API with host buffers ---------------------------------------------
-    for i in range(min(args.warmup, 3)):
-        w.step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        w.step_e2e(i)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-
-    value = w.units_per_step * args.steps / (total_ms / 1e3)
-    e2e_value = w.units_per_step * args.steps / e2e_s
-    peak, peak_src = load_peaks()
-    achieved = w.kernel_bytes / (kern_ms / 1e3) / 1e9
-
-    roofline = {"bound": "hbm", "kernel": w.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": load_traffic(args.workload, args.scale, world),
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": int(w.kernel_bytes), "kernel_ms": kern_ms}
-    tc = ib.knn_tc_last_stats() if args.workload == "knn_cosine_multi" else None
-    if tc and tc["passes"] > 0 and tc["filter_ms"] > 0:
-        # large query batches: the dominant kernel is the tcgen05 filter (csrc/knn_tc.cu); algorithmic flops per launch =
-        # 2 * rows * d * queries of THIS rank, time = CUDA events around that launch inside the library
-        tpeak, tsrc = load_tensor_peak()
-        flops = 2.0 * w.n_local * w.d * w.nq
-        tf = flops / (tc["filter_ms"] / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "knn_tc_filter_kernel (kind::f16, exact rescoring after it)",
-                    "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak, "traffic": None,
-                    "peak_source": tsrc, "algorithmic_flops_per_launch": flops, "kernel_ms": tc["filter_ms"],
-                    "call_ms": tc["total_ms"], "filter_passes": tc["passes"], "rescored_pairs": tc["candidates"],
-                    "exact_scan_queries": tc["exact_scan_queries"]}
-    if rank == 0:
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": dtype_of(args.workload), "data": "synthetic",
-            "config": {"workload": desc, "scale": args.scale, "corpus_gb": round(w.corpus_gb, 3),
-                       "sharding": f"rows/{world}", "l2": "inputs larger than L2 (corpus >> 126 MB), no flush"
-                       if w.corpus_gb / world > 0.5 else "corpus is L2-resident by design of this config (latency-bound)",
-                       "generator": "G-ref lattice" if args.workload == "batch_demo" else "G-hash (splitmix64)"},
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h},
-            "gpu_launches": int(launches),
-            "roofline": roofline,
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            v, sample, _ = w.cpu_baseline(cores)
-            line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port",
-                                    "sample": sample + " (C++ restatement of innr 0.6.3, not the Rust crate)"}
+        line = dict(entries[names[0]])
+        if args.workload == "all":
+            line["workloads"] = {WORKLOADS[n][0]: entries[n] for n in names}
+            line["wall_s"] = round(time.perf_counter() - t_all, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

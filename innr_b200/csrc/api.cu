@@ -80,6 +80,12 @@ struct DeviceCtx {
   int device = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // The workspace and the scratch buffers below are shared by everything that runs on this device. Host-facing entries
+  // run on `stream` and synchronise before they return; `_dev` entries enqueue on the CALLER's stream and return at
+  // once, so they leave an event behind (ws_event on ws_stream) that the next user on any other stream waits for.
+  cudaEvent_t ws_event = nullptr;
+  cudaStream_t ws_stream = nullptr;
+  bool ws_pending = false;
   Workspace ws;
   Buf d_query, d_keys, d_scores, d_aux, d_tcws, h_pin, h_counts;
   float last_ms = 0.0f;
@@ -102,7 +108,32 @@ KnnTcStats g_tc_stats;
 thread_local int t_device = -1;
 thread_local std::string t_err;
 std::mutex& dev_mu(int d) { return g_dev_mu[(d >= 0 && d < MAX_DEVICES) ? d : 0]; }
-int cur_dev() { return t_device < 0 ? 0 : t_device; }
+// Device of entries that take no corpus: the one this thread bound with innr_cuda_init, else the thread's current CUDA
+// device (a host runtime such as torch has usually set it), else 0.
+int cur_dev() {
+  if (t_device >= 0) return t_device;
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) {
+    cudaGetLastError();
+    d = 0;
+  }
+  return (d >= 0 && d < MAX_DEVICES) ? d : 0;
+}
+// Every entry holds the device's mutex for its duration and leaves the calling thread's current CUDA device as it found
+// it (the library switches devices internally; a host runtime's own notion of the current device must not change).
+struct EntryGuard {
+  std::lock_guard<std::mutex> lk;
+  int prev = -1;
+  explicit EntryGuard(int device) : lk(dev_mu(device)) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  ~EntryGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 int fail(int code, const std::string& msg) {
   t_err = msg;
@@ -119,7 +150,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
-int ensure_ctx(int device, DeviceCtx** out) {
+int ensure_ctx(int device, DeviceCtx** out, bool dev_entry = false, cudaStream_t user = nullptr) {
   if (device < 0 || device >= MAX_DEVICES) return fail(INNR_EINVAL, "device index out of range");
   DeviceCtx& c = g_ctx[device];
   if (!c.ready) {
@@ -138,6 +169,7 @@ int ensure_ctx(int device, DeviceCtx** out) {
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c.ev0));
     CU(cudaEventCreate(&c.ev1));
+    CU(cudaEventCreateWithFlags(&c.ws_event, cudaEventDisableTiming));
     // per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
     // (the same buffers hold several query groups of one launch when the grid is small: scan_f32.cu, grid.y)
     c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32 * 4;
@@ -153,16 +185,36 @@ int ensure_ctx(int device, DeviceCtx** out) {
   } else {
     CU(cudaSetDevice(device));
   }
+  // order this call after the last `_dev` call that is still using the workspace on another stream
+  if (dev_entry) {
+    if (c.ws_pending && c.ws_stream != user) CU(cudaStreamWaitEvent(user, c.ws_event, 0));
+  } else if (c.ws_pending) {
+    CU(cudaStreamWaitEvent(c.stream, c.ws_event, 0));
+    c.ws_pending = false;  // host-facing entries synchronise c.stream before they return
+  }
   *out = &c;
   return INNR_OK;
 }
 
-int current_ctx(DeviceCtx** out) {
-  if (t_device < 0) t_device = 0;
-  return ensure_ctx(t_device, out);
-}
+// `_dev` entries: the work stays in flight on the caller's stream when the entry returns
+struct DevRelease {
+  DeviceCtx& c;
+  cudaStream_t s;
+  DevRelease(DeviceCtx& ctx, cudaStream_t stream) : c(ctx), s(stream) {}
+  ~DevRelease() {
+    if (cudaEventRecord(c.ws_event, s) == cudaSuccess) {
+      c.ws_pending = true;
+      c.ws_stream = s;
+    } else {
+      cudaGetLastError();
+    }
+  }
+};
+
+int current_ctx(DeviceCtx** out) { return ensure_ctx(cur_dev(), out); }
 
 int ctx_for(const innr_cuda_corpus* c, DeviceCtx** out) { return ensure_ctx(c->device, out); }
+int ctx_for_dev(const innr_cuda_corpus* c, DeviceCtx** out, cudaStream_t user) { return ensure_ctx(c->device, out, true, user); }
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -190,6 +242,31 @@ void decode_keys_f32(const uint64_t* keys, size_t count, bool descending, uint64
     out_score[j] = f;
   }
 }
+
+// frees everything a corpus handle owns (the device's mutex is held by the caller)
+void destroy_corpus(innr_cuda_corpus* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->owns && c->dev) cudaFree(c->dev);
+  if (c->dev_offsets) cudaFree(c->dev_offsets);
+  if (c->dev_norms) cudaFree(c->dev_norms);
+  if (c->dev_xh) cudaFree(c->dev_xh);
+  if (c->dev_order) cudaFree(c->dev_order);
+  delete c;
+}
+// Upload / generate entries: a failure after the handle exists frees it again and hands back NULL (a mid-upload error
+// must not strand a multi-GB allocation behind a pointer the caller will never wrap).
+struct CorpusGuard {
+  innr_cuda_corpus** out;
+  bool ok = false;
+  explicit CorpusGuard(innr_cuda_corpus** o) : out(o) {}
+  ~CorpusGuard() {
+    if (!ok && out && *out) {
+      destroy_corpus(*out);
+      *out = nullptr;
+    }
+  }
+};
 
 int new_corpus(int kind, int device, innr_cuda_corpus** out) {
   *out = new (std::nothrow) innr_cuda_corpus();
@@ -241,7 +318,7 @@ int innr_cuda_device_count(int* out_count) {
 }
 
 int innr_cuda_init(int device) {
-  std::lock_guard<std::mutex> lk(dev_mu(device));
+  EntryGuard lk(device);
   DeviceCtx* c;
   int rc = ensure_ctx(device, &c);
   if (rc == INNR_OK) t_device = device;
@@ -261,6 +338,7 @@ int innr_cuda_shutdown(void) {
     cudaFree(c.ws.tickets);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
+    cudaEventDestroy(c.ws_event);
     cudaStreamDestroy(c.stream);
     c = DeviceCtx();
   }
@@ -319,6 +397,7 @@ static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, in
   rc = new_corpus(0, ctx.device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n;
   c->d = d;
   c->ld = round_up(n, 64);
@@ -332,38 +411,42 @@ static int alloc_pdx(DeviceCtx& ctx, size_t n, size_t d, uint64_t index_base, in
       return cuda_fail(e, "cudaMalloc(corpus)");
     }
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_upload_f32_pdx(const float* host_pdx, size_t n, size_t d, uint64_t index_base,
                              innr_cuda_corpus** out) {
   if (!out || (!host_pdx && n * d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_pdx(*ctx, n, d, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(cudaMemsetAsync(c->dev, 0, c->bytes, ctx->stream));
     CU(cudaMemcpy2DAsync(c->dev, c->ld * sizeof(float), host_pdx, n * sizeof(float), n * sizeof(float), d,
                          cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64_t index_base,
                               innr_cuda_corpus** out) {
   if (!out || (!host_rows && n * d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_pdx(*ctx, n, d, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     // ingest in chunks of rows through one 256 MB device staging buffer (stream order keeps copy and transpose of
     // consecutive chunks apart): the device never holds a second copy of the corpus
@@ -385,6 +468,7 @@ int innr_cuda_upload_f32_rows(const float* host_rows, size_t n, size_t d, uint64
     if (stage) cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_f32_rows");
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
@@ -393,7 +477,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   if (!out) return fail(INNR_EINVAL, "null out");
   if (ld < n || (ld % 4) != 0 || ((uintptr_t)dev_pdx % 16) != 0)
     return fail(INNR_EINVAL, "wrap_f32_pdx_dev: need ld >= n, ld % 4 == 0, 16-byte aligned base");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -402,6 +486,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   rc = new_corpus(0, ctx->device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->owns = false;
   c->dev = (void*)dev_pdx;
   c->n = n;
@@ -409,6 +494,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
   c->ld = ld;
   c->index_base = index_base;
   c->bytes = ld * d * sizeof(float);
+  guard.ok = true;
   return INNR_OK;
 }
 
@@ -419,7 +505,7 @@ int innr_cuda_wrap_f32_pdx_dev(const float* dev_pdx, size_t n, size_t d, size_t 
 int innr_cuda_prefix_view(const innr_cuda_corpus* c, size_t prefix_dim, innr_cuda_corpus** out) {
   if (!out || !c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
   const size_t d = prefix_dim < c->d ? prefix_dim : c->d;  // prefix_len.min(a.len())
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   int rc = new_corpus(0, c->device, out);
   if (rc) return rc;
   innr_cuda_corpus* v = *out;
@@ -436,30 +522,26 @@ int innr_cuda_prefix_view(const innr_cuda_corpus* c, size_t prefix_dim, innr_cud
 int innr_cuda_generate_f32_pdx(int generator, uint64_t salt, uint64_t first_row, size_t n, size_t d,
                                uint64_t index_base, innr_cuda_corpus** out) {
   if (!out || (generator != 0 && generator != 1)) return fail(INNR_EINVAL, "bad argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_pdx(*ctx, n, d, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_generate_f32_pdx(generator, salt, first_row, n, d, (float*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_free(innr_cuda_corpus* c) {
   if (!c) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
-  cudaSetDevice(c->device);
-  if (c->owns && c->dev) cudaFree(c->dev);
-  if (c->dev_offsets) cudaFree(c->dev_offsets);
-  if (c->dev_norms) cudaFree(c->dev_norms);
-  if (c->dev_xh) cudaFree(c->dev_xh);
-  if (c->dev_order) cudaFree(c->dev_order);
-  delete c;
+  EntryGuard lk(c->device);
+  destroy_corpus(c);
   return INNR_OK;
 }
 
@@ -478,7 +560,7 @@ int innr_cuda_corpus_info(const innr_cuda_corpus* c, int* kind, size_t* n, size_
 int innr_cuda_extract_vector(const innr_cuda_corpus* c, size_t i, float* out_host) {
   if (!c || c->kind != 0 || !out_host) return fail(INNR_EINVAL, "extract_vector: need an f32 corpus");
   if (i >= c->n) return fail(INNR_EINVAL, "extract_vector: index out of bounds");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -499,7 +581,7 @@ static int pdx_scores(const innr_cuda_corpus* c, int mode, const float* query, s
     return fail(INNR_EINVAL, "query.len() != batch.dimension");                       // src/batch.rs:251,285
   if (c->n == 0) return INNR_OK;
   if (!out_host || (mode != PDX_NORMS && !query && c->d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -576,14 +658,18 @@ static int big_k_from_scores(DeviceCtx* ctx, const void* dev_scores, int kind, s
   return INNR_OK;
 }
 
+// Writes min(k, n) keys per query at row stride `k` (k <= 128: the fused lists are sentinel-initialised, so the rows come
+// out sentinel-padded to k by themselves; k > 128: the caller pre-fills dev_keys with sentinels when k > n).
 static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
                         uint64_t* dev_keys, cudaStream_t s) {
   PdxView v = pdx_view(c);
   if (k > MAX_FUSED_K) {
+    const size_t kk = k < c->n ? k : c->n;
+    if (kk < k) CU(cudaMemsetAsync(dev_keys, 0xFF, nq * k * sizeof(uint64_t), s));
     CU(ctx->d_scores.reserve(c->ld * sizeof(float)));
     for (size_t q = 0; q < nq; ++q) {
       CU(launch_pdx_scores(v, mode, dev_queries + q * c->d, nullptr, (float*)ctx->d_scores.p, ctx->ws, s, &g_launches));
-      int rc = big_k_from_scores(ctx, ctx->d_scores.p, mode == PDX_L2 ? 0 : 1, c->n, c->index_base, k, dev_keys + q * k, s);
+      int rc = big_k_from_scores(ctx, ctx->d_scores.p, mode == PDX_L2 ? 0 : 1, c->n, c->index_base, kk, dev_keys + q * k, s);
       if (rc) return rc;
     }
     return INNR_OK;
@@ -632,7 +718,7 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;                           // src/batch.rs:388-393
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;                                               // k.min(num_vectors)
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -686,7 +772,7 @@ int innr_cuda_batch_dimension_variance(const innr_cuda_corpus* c, float* out, si
   if (out_len != c->d) return fail(INNR_EINVAL, "out_len != batch.dimension");
   if (c->d == 0) return INNR_OK;
   if (!out) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -709,7 +795,7 @@ int innr_cuda_batch_knn_reordered(const innr_cuda_corpus* c, const float* query,
     if (out_count) *out_count = kk;
     return INNR_OK;
   }
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -755,7 +841,7 @@ int innr_cuda_batch_knn_adaptive(const innr_cuda_corpus* c, const float* query, 
     return INNR_OK;
   }
   const size_t w = warmup_dims < c->d ? warmup_dims : c->d;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -855,7 +941,7 @@ int innr_cuda_batch_knn_subset(const innr_cuda_corpus* c, int metric, const floa
     if (candidates[j] < c->index_base || candidates[j] - c->index_base >= c->n)
       return fail(INNR_EINVAL, "batch_knn_subset: candidate index out of bounds");
   const size_t kk = k < n_candidates ? k : n_candidates;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -902,7 +988,7 @@ int innr_cuda_batch_knn_filtered(const innr_cuda_corpus* c, const float* query, 
   }
   if (passing == 0) return INNR_OK;                                                     // :842-847
   const size_t kk = k < passing ? k : passing;                                          // k.min(num_passing)
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -947,7 +1033,7 @@ int innr_cuda_batch_l2_squared_pruning(const innr_cuda_corpus* c, const float* q
     return INNR_OK;
   }
   if (!query) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -993,25 +1079,33 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
   int rc = metric_to_mode(metric, &mode);
   if (rc) return rc;
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
-  DeviceCtx* ctx;
-  rc = ctx_for(c, &ctx);
-  if (rc) return rc;
+  EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
-  if (c->n == 0) {
+  DeviceCtx* ctx;
+  rc = ctx_for_dev(c, &ctx, s);
+  if (rc) return rc;
+  DevRelease rel(*ctx, s);
+  if (c->n == 0) {  // rows are n_queries x k, sentinel-padded (header contract)
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  return knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, dev_queries, n_queries, k < c->n ? k : c->n, dev_keys, s);
+  return knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, dev_queries, n_queries, k, dev_keys, s);
 }
 
 int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,
                              uint64_t* dev_keys_out, uint64_t* dev_idx, float* dev_score, void* stream) {
   if (k == 0 || n_queries == 0 || n_lists == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  // the device is the one the key lists live on (the calling thread need not have bound it with innr_cuda_init)
+  int device = cur_dev();
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, dev_keys_in) == cudaSuccess && attr.type == cudaMemoryTypeDevice) device = attr.device;
+  else cudaGetLastError();
+  EntryGuard lk(device);
+  cudaStream_t us = (cudaStream_t)stream;
   DeviceCtx* ctx;
-  int rc = current_ctx(&ctx);
+  int rc = ensure_ctx(device, &ctx, true, us);
   if (rc) return rc;
+  DevRelease rel(*ctx, us);
   if (k > MAX_FUSED_K) {
     uint64_t* keys_out = dev_keys_out;
     if (!keys_out) {
@@ -1035,7 +1129,7 @@ int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, ui
   int rc = check_index_range(n, 0);
   if (rc) return rc;
   const size_t kk = k < n ? k : n;
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1063,6 +1157,7 @@ static int alloc_binary(DeviceCtx& ctx, size_t n, size_t dim_bits, uint64_t inde
   rc = new_corpus(1, ctx.device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n;
   c->dim_bits = dim_bits;
   c->words = (dim_bits + 63) / 64;
@@ -1079,19 +1174,21 @@ static int alloc_binary(DeviceCtx& ctx, size_t n, size_t dim_bits, uint64_t inde
       return cuda_fail(e, "cudaMalloc(binary corpus)");
     }
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, uint64_t index_base,
                             innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_binary(*ctx, n, dim_bits, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     if (!words) return fail(INNR_EINVAL, "null words");
     void* stage = nullptr;
@@ -1103,23 +1200,26 @@ int innr_cuda_upload_binary(const uint64_t* words, size_t n, size_t dim_bits, ui
     cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_binary");
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_generate_binary(uint64_t salt, uint64_t first_row, size_t n, size_t dim_bits, uint64_t index_base,
                               innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_binary(*ctx, n, dim_bits, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_generate_binary(salt, first_row, n, c->words, dim_bits, (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
@@ -1147,7 +1247,7 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
     return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");             // src/binary.rs:155-159
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1172,18 +1272,20 @@ int innr_cuda_hamming_all(const innr_cuda_corpus* c, const uint64_t* query_words
 // code set shares the f32 corpus' index_base, so first-pass indices feed innr_cuda_batch_knn_subset directly.
 int innr_cuda_binary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out) {
   if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
-  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
+  EntryGuard lk(f32_corpus->device);
   DeviceCtx* ctx;
   int rc = ctx_for(f32_corpus, &ctx);
   if (rc) return rc;
   rc = alloc_binary(*ctx, f32_corpus->n, f32_corpus->d, f32_corpus->index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_binary_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, threshold,
                               (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
@@ -1194,7 +1296,7 @@ static int binary_setop_all(const innr_cuda_corpus* c, const uint64_t* query_wor
   if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "dimension mismatch");  // assert_eq!(a.dimension, b.dimension)
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1245,7 +1347,7 @@ int innr_cuda_binary_topk(const innr_cuda_corpus* c, int op, const uint64_t* que
     if (out_count) *out_count = kk;
     return INNR_OK;
   }
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1282,10 +1384,12 @@ static int hamming_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const uint64_
     CU(launch_hamming_topk(bin_view(c), dev_query_words, nq, k, dev_keys, ctx->ws, s, &g_launches));
     return INNR_OK;
   }
+  const size_t kk = k < c->n ? k : c->n;  // rows stay k wide, sentinel-padded
+  if (kk < k) CU(cudaMemsetAsync(dev_keys, 0xFF, nq * k * sizeof(uint64_t), s));
   CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
   for (size_t q = 0; q < nq; ++q) {
     CU(launch_hamming_all(bin_view(c), dev_query_words + q * 2 * c->chunks, (uint32_t*)ctx->d_scores.p, s, &g_launches));
-    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 2, c->n, c->index_base, k, dev_keys + q * k, s);
+    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 2, c->n, c->index_base, kk, dev_keys + q * k, s);
     if (rc) return rc;
   }
   return INNR_OK;
@@ -1300,7 +1404,7 @@ int innr_cuda_hamming_topk(const innr_cuda_corpus* c, const uint64_t* query_word
   if (c->n == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_dist || (!query_words && c->words)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1336,11 +1440,12 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
                                     size_t k, uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
-  DeviceCtx* ctx;
-  int rc = ctx_for(c, &ctx);
-  if (rc) return rc;
+  EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceCtx* ctx;
+  int rc = ctx_for_dev(c, &ctx, s);
+  if (rc) return rc;
+  DevRelease rel(*ctx, s);
   if (c->n == 0 || c->words == 0) {
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
@@ -1351,7 +1456,7 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
 int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words) {
   if (n == 0) return INNR_OK;
   if (!values || !out_words) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1373,6 +1478,7 @@ static int alloc_u8(DeviceCtx& ctx, size_t n, size_t d, float alpha, float offse
   rc = new_corpus(2, ctx.device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n;
   c->d = d;
   c->chunks = (d + 15) / 16;
@@ -1389,19 +1495,21 @@ static int alloc_u8(DeviceCtx& ctx, size_t n, size_t d, float alpha, float offse
       return cuda_fail(e, "cudaMalloc(u8 corpus)");
     }
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, float offset, uint64_t index_base,
                         innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_u8(*ctx, n, d, alpha, offset, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     if (!rows) return fail(INNR_EINVAL, "null rows");
     void* stage = nullptr;
@@ -1412,48 +1520,53 @@ int innr_cuda_upload_u8(const uint8_t* rows, size_t n, size_t d, float alpha, fl
     cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_u8");
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 // quantize_u8 (src/scalar.rs:212-225) of every vector of a device-resident f32 corpus, on the device
 int innr_cuda_u8_from_f32(const innr_cuda_corpus* f32_corpus, float alpha, float offset, innr_cuda_corpus** out) {
   if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
-  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
+  EntryGuard lk(f32_corpus->device);
   DeviceCtx* ctx;
   int rc = ctx_for(f32_corpus, &ctx);
   if (rc) return rc;
   rc = alloc_u8(*ctx, f32_corpus->n, f32_corpus->d, alpha, offset, f32_corpus->index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_u8_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, alpha, offset,
                           (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_generate_u8(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset,
                           uint64_t index_base, innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_u8(*ctx, n, d, alpha, offset, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_generate_u8(salt, first_row, n, d, alpha, offset, (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_quantize_u8(const float* values, size_t n, float alpha, float offset, uint8_t* out_codes) {
   if (n == 0) return INNR_OK;
   if (!values || !out_codes) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1472,7 +1585,7 @@ static int u8_scores(const innr_cuda_corpus* c, int mode, const float* query, si
   if (query_len != c->d) return fail(INNR_EINVAL, mismatch_msg);
   if (c->n == 0) return INNR_OK;
   if (!out_host || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1506,10 +1619,12 @@ static int u8_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const float* dev_q
     CU(launch_u8_knn(u8_view(c), dev_queries, nq, k, dev_keys, ctx->ws, s, &g_launches));
     return INNR_OK;
   }
+  const size_t kk = k < c->n ? k : c->n;  // rows stay k wide, sentinel-padded
+  if (kk < k) CU(cudaMemsetAsync(dev_keys, 0xFF, nq * k * sizeof(uint64_t), s));
   CU(ctx->d_scores.reserve(c->n * sizeof(float)));
   for (size_t q = 0; q < nq; ++q) {
     CU(launch_u8_scores(u8_view(c), 1, dev_queries + q * c->d, (float*)ctx->d_scores.p, s, &g_launches));
-    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 1, c->n, c->index_base, k, dev_keys + q * k, s);
+    int rc = big_k_from_scores(ctx, ctx->d_scores.p, 1, c->n, c->index_base, kk, dev_keys + q * k, s);
     if (rc) return rc;
   }
   return INNR_OK;
@@ -1524,7 +1639,7 @@ int innr_cuda_batch_knn_u8(const innr_cuda_corpus* c, const float* queries, size
   if (!out_idx || !out_score || (!queries && c->d)) return fail(INNR_EINVAL, "null argument");
   const size_t kk = k < c->n ? k : c->n;
   if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1547,11 +1662,12 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
                                     uint64_t* dev_keys, void* stream) {
   if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
   if (k == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
-  DeviceCtx* ctx;
-  int rc = ctx_for(c, &ctx);
-  if (rc) return rc;
+  EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
+  DeviceCtx* ctx;
+  int rc = ctx_for_dev(c, &ctx, s);
+  if (rc) return rc;
+  DevRelease rel(*ctx, s);
   if (c->n == 0 || c->d == 0) {
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
@@ -1566,6 +1682,7 @@ static int alloc_ternary(DeviceCtx& ctx, size_t n, size_t dim, uint64_t index_ba
   rc = new_corpus(4, ctx.device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n;
   c->dim_bits = dim;  // dimension (values)
   c->d = dim;
@@ -1582,6 +1699,7 @@ static int alloc_ternary(DeviceCtx& ctx, size_t n, size_t dim, uint64_t index_ba
       return cuda_fail(e, "cudaMalloc(ternary corpus)");
     }
   }
+  guard.ok = true;
   return INNR_OK;
 }
 static TerView ter_view(const innr_cuda_corpus* c) {
@@ -1591,13 +1709,14 @@ static TerView ter_view(const innr_cuda_corpus* c) {
 int innr_cuda_upload_ternary(const uint64_t* words, size_t n, size_t dimension, uint64_t index_base,
                              innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = alloc_ternary(*ctx, n, dimension, index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     if (!words) return fail(INNR_EINVAL, "null words");
     void* stage = nullptr;
@@ -1609,30 +1728,33 @@ int innr_cuda_upload_ternary(const uint64_t* words, size_t n, size_t dimension, 
     cudaFree(stage);
     if (e != cudaSuccess) return cuda_fail(e, "upload_ternary");
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_ternary_from_f32(const innr_cuda_corpus* f32_corpus, float threshold, innr_cuda_corpus** out) {
   if (!out || !f32_corpus || f32_corpus->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
-  std::lock_guard<std::mutex> lk(dev_mu(f32_corpus->device));
+  EntryGuard lk(f32_corpus->device);
   DeviceCtx* ctx;
   int rc = ctx_for(f32_corpus, &ctx);
   if (rc) return rc;
   rc = alloc_ternary(*ctx, f32_corpus->n, f32_corpus->d, f32_corpus->index_base, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   if (c->bytes) {
     CU(launch_ternary_from_pdx((const float*)f32_corpus->dev, f32_corpus->ld, f32_corpus->n, f32_corpus->d, threshold,
                                (uint4*)c->dev, c->ld, ctx->stream, &g_launches));
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_encode_ternary(const float* values, size_t n, float threshold, uint64_t* out_words) {
   if (n == 0) return INNR_OK;
   if (!values || !out_words) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1678,7 +1800,7 @@ int innr_cuda_ternary_scores_all(const innr_cuda_corpus* c, int op, const void* 
   if (!c || c->kind != 4) return fail(INNR_EINVAL, "need a ternary corpus");
   if (c->n == 0) return INNR_OK;
   if ((!out_f32_host && !out_i32_host) || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1711,7 +1833,7 @@ int innr_cuda_ternary_topk(const innr_cuda_corpus* c, int op, const void* query,
   if (!out_idx || !out_score || (!query && c->d)) return fail(INNR_EINVAL, "null argument");
   if (c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional ternary corpus");
   const size_t kk = k < c->n ? k : c->n;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1732,7 +1854,7 @@ int innr_cuda_ternary_topk(const innr_cuda_corpus* c, int op, const void* query,
 int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, size_t n_docs, size_t dim,
                             uint64_t index_base, innr_cuda_corpus** out) {
   if (!out || (n_docs && !doc_offsets)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
@@ -1744,6 +1866,7 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
   rc = new_corpus(3, ctx->device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n_docs;
   c->d = dim;
   c->index_base = index_base;
@@ -1763,19 +1886,21 @@ int innr_cuda_upload_tokens(const float* tokens, const uint64_t* doc_offsets, si
     CU(cudaMemcpyAsync(c->dev_offsets, doc_offsets, (n_docs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  guard.ok = true;
   return INNR_OK;
 }
 
 int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, size_t tokens_per_doc, size_t dim,
                               uint64_t index_base, innr_cuda_corpus** out) {
   if (!out) return fail(INNR_EINVAL, "null out");
-  std::lock_guard<std::mutex> lk(dev_mu(cur_dev()));
+  EntryGuard lk(cur_dev());
   DeviceCtx* ctx;
   int rc = current_ctx(&ctx);
   if (rc) return rc;
   rc = new_corpus(3, ctx->device, out);
   if (rc) return rc;
   innr_cuda_corpus* c = *out;
+  CorpusGuard guard(out);
   c->n = n_docs;
   c->d = dim;
   c->index_base = index_base;
@@ -1792,6 +1917,7 @@ int innr_cuda_generate_tokens(uint64_t salt, uint64_t first_doc, size_t n_docs, 
     }
     CU(cudaStreamSynchronize(ctx->stream));
   }
+  guard.ok = true;
   return INNR_OK;
 }
 
@@ -1819,7 +1945,7 @@ int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_
   if (n_q && c->total_tokens && q_dim != c->d) return fail(INNR_EINVAL, "dimension mismatch (doc)");  // src/maxsim.rs:107-110
   if (c->n == 0) return INNR_OK;
   if (!out_scores_host || (n_q * q_dim && !q_tokens)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1861,7 +1987,7 @@ int innr_cuda_maxsim_batch(const innr_cuda_corpus* c, const float* q_tokens, siz
   if (n_q && c->total_tokens && q_dim != c->d) return fail(INNR_EINVAL, "dimension mismatch (doc)");  // src/maxsim.rs:107-110
   if (c->n == 0 || n_queries == 0) return INNR_OK;
   if (!out_scores_host || (n_q * q_dim && !q_tokens)) return fail(INNR_EINVAL, "null argument");
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
   int rc = ctx_for(c, &ctx);
   if (rc) return rc;
@@ -1885,10 +2011,11 @@ int innr_cuda_maxsim_batch_dev(const innr_cuda_corpus* c, const float* dev_q_tok
                                int cosine_flag, float* dev_scores, void* stream) {
   if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
   if (c->n == 0 || n_queries == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
-  int rc = ctx_for(c, &ctx);
+  int rc = ctx_for_dev(c, &ctx, (cudaStream_t)stream);
   if (rc) return rc;
+  DevRelease rel(*ctx, (cudaStream_t)stream);
   return maxsim_batch_common(c, ctx, dev_q_tokens, n_queries, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
 }
 
@@ -1896,10 +2023,11 @@ int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, s
                          float* dev_scores, void* stream) {
   if (!c || c->kind != 3) return fail(INNR_EINVAL, "need a token corpus");
   if (c->n == 0) return INNR_OK;
-  std::lock_guard<std::mutex> lk(dev_mu(c->device));
+  EntryGuard lk(c->device);
   DeviceCtx* ctx;
-  int rc = ctx_for(c, &ctx);
+  int rc = ctx_for_dev(c, &ctx, (cudaStream_t)stream);
   if (rc) return rc;
+  DevRelease rel(*ctx, (cudaStream_t)stream);
   return maxsim_common(c, ctx, dev_q_tokens, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
 }
 

@@ -98,6 +98,10 @@ def lib() -> C.CDLL:
             "innr_ref_splitmix64": (C.c_uint64, [C.c_uint64]),
             "innr_ref_ghash_f32": (None, [C.c_uint64, C.c_uint64, sz, _f32p]),
             "innr_ref_ghash_u64": (None, [C.c_uint64, C.c_uint64, sz, _u64p]),
+            "innr_ref_ghash_f32_mt": (None, [C.c_uint64, C.c_uint64, sz, _f32p, i]),
+            "innr_ref_ghash_u64_mt": (None, [C.c_uint64, C.c_uint64, sz, _u64p, i]),
+            "innr_ref_ghash_pdx_mt": (None, [C.c_uint64, C.c_uint64, sz, sz, _f32p, i]),
+            "innr_ref_ghash_u8_mt": (None, [C.c_uint64, C.c_uint64, sz, sz, f32, f32, _u8p, i]),
             "innr_ref_batch_knn_many": (sz, [i, _f32p, sz, _f32p, sz, sz, sz, _u64p, _f32p, i]),
             "innr_ref_hamming_topk_many": (sz, [_u64p, sz, _u64p, sz, sz, sz, _u64p, _u32p, i]),
             "innr_ref_batch_knn_u8_many": (sz, [_f32p, sz, _u8p, sz, sz, f32, f32, sz, _u64p, _f32p, i]),
@@ -729,4 +733,36 @@ def ghash_u64(salt: int, first_idx: int, count: int) -> np.ndarray:
     out = np.zeros(count, np.uint64)
     if count:
         lib().innr_ref_ghash_u64(C.c_uint64(salt), C.c_uint64(first_idx), count, _p(out, _u64p))
+    return out
+
+
+# multi-threaded generators for bench.py's CPU legs (full BASELINE-size corpora built on the host in their final layout)
+def ghash_f32_mt(salt: int, first_idx: int, count: int, n_threads: int) -> np.ndarray:
+    out = np.empty(count, np.float32)
+    if count:
+        lib().innr_ref_ghash_f32_mt(C.c_uint64(salt), C.c_uint64(first_idx), count, _p(out, _f32p), n_threads)
+    return out
+
+
+def ghash_u64_mt(salt: int, first_idx: int, count: int, n_threads: int) -> np.ndarray:
+    out = np.empty(count, np.uint64)
+    if count:
+        lib().innr_ref_ghash_u64_mt(C.c_uint64(salt), C.c_uint64(first_idx), count, _p(out, _u64p), n_threads)
+    return out
+
+
+def ghash_vertical_batch(salt: int, first_row: int, n: int, d: int, n_threads: int) -> "VerticalBatch":
+    """VerticalBatch.from_flat(ghash rows [first_row, first_row+n) x d) without the row-major intermediate."""
+    data = np.empty(n * d, np.float32)
+    if n * d:
+        lib().innr_ref_ghash_pdx_mt(C.c_uint64(salt), C.c_uint64(first_row), n, d, _p(data, _f32p), n_threads)
+    return VerticalBatch(data, n, d)
+
+
+def ghash_u8_rows(salt: int, first_row: int, n: int, d: int, params: "QuantizationParams", n_threads: int) -> np.ndarray:
+    """quantize_u8 of ghash rows: (n, d) uint8, row-major."""
+    out = np.empty((n, d), np.uint8)
+    if n * d:
+        lib().innr_ref_ghash_u8_mt(C.c_uint64(salt), C.c_uint64(first_row), n, d, params.alpha, params.offset,
+                                   _p(out, _u8p), n_threads)
     return out

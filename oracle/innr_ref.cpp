@@ -596,6 +596,20 @@ static void parallel_queries(size_t nq, int n_threads, F f) {
   for (auto& x : th) x.join();
 }
 
+template <class F>
+static void parallel_ranges(size_t total, int n_threads, F f) {
+  if (n_threads <= 1 || total < 4096) {
+    f((size_t)0, total);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (total + (size_t)n_threads - 1) / (size_t)n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const size_t lo = std::min(total, per * (size_t)t), hi = std::min(total, lo + per);
+    if (lo < hi) th.emplace_back([=] { f(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
 extern "C" {
 
 int innr_ref_host_has_avx512(void) { return __builtin_cpu_supports("avx512f") ? 1 : 0; }
@@ -1233,6 +1247,43 @@ void innr_ref_ghash_f32(uint64_t salt, uint64_t first_idx, size_t count, float* 
 }
 void innr_ref_ghash_u64(uint64_t salt, uint64_t first_idx, size_t count, uint64_t* out) {
   for (size_t i = 0; i < count; ++i) out[i] = innr_ref_splitmix64(salt + first_idx + i);
+}
+
+// ---- multi-threaded corpus generators for bench.py's CPU legs (same values as the single-threaded generators above;
+//      they exist so a full BASELINE-size corpus can be built on the host in seconds, directly in its final layout) ----
+void innr_ref_ghash_f32_mt(uint64_t salt, uint64_t first_idx, size_t count, float* out, int n_threads) {
+  parallel_ranges(count, n_threads, [=](size_t lo, size_t hi) { innr_ref_ghash_f32(salt, first_idx + lo, hi - lo, out + lo); });
+}
+void innr_ref_ghash_u64_mt(uint64_t salt, uint64_t first_idx, size_t count, uint64_t* out, int n_threads) {
+  parallel_ranges(count, n_threads, [=](size_t lo, size_t hi) { innr_ref_ghash_u64(salt, first_idx + lo, hi - lo, out + lo); });
+}
+// G-hash rows [first_row, first_row + n) of dimension d written as a VerticalBatch: pdx[dd * n + i] = value(row i, dim dd)
+// (what from_flat, src/batch.rs:167-183, makes of the row-major generator output -- without the row-major copy)
+void innr_ref_ghash_pdx_mt(uint64_t salt, uint64_t first_row, size_t n, size_t d, float* pdx, int n_threads) {
+  parallel_ranges(n, n_threads, [=](size_t lo, size_t hi) {
+    constexpr size_t B = 256;  // rows per block: the d x B tile of writes stays cache-resident
+    for (size_t i0 = lo; i0 < hi; i0 += B) {
+      const size_t i1 = std::min(hi, i0 + B);
+      for (size_t i = i0; i < i1; ++i) {
+        const uint64_t base = salt + (first_row + i) * (uint64_t)d;
+        for (size_t dd = 0; dd < d; ++dd) {
+          uint64_t u = innr_ref_splitmix64(base + dd);
+          pdx[dd * n + i] = (float)(u >> 40) * (1.0f / 8388608.0f) - 1.0f;
+        }
+      }
+    }
+  });
+}
+// quantize_u8 (src/scalar.rs:212-225) of G-hash f32 rows, row-major n x d codes, without the f32 intermediate
+void innr_ref_ghash_u8_mt(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset, uint8_t* out,
+                          int n_threads) {
+  parallel_ranges(n, n_threads, [=](size_t lo, size_t hi) {
+    std::vector<float> row(d);
+    for (size_t i = lo; i < hi; ++i) {
+      innr_ref_ghash_f32(salt, (first_row + i) * (uint64_t)d, d, row.data());
+      innr_ref_quantize_u8(row.data(), d, alpha, offset, out + i * d);
+    }
+  });
 }
 
 // ---- multi-threaded drivers -------------------------------------------------------

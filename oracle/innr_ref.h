@@ -167,6 +167,14 @@ void innr_ref_generate_normalized(size_t dim, uint64_t seed, float* out);  /* ex
 uint64_t innr_ref_splitmix64(uint64_t x);
 void innr_ref_ghash_f32(uint64_t salt, uint64_t first_idx, size_t count, float* out);
 void innr_ref_ghash_u64(uint64_t salt, uint64_t first_idx, size_t count, uint64_t* out);
+/* multi-threaded forms for bench.py's CPU legs (same values), and generators that write the final layouts directly */
+void innr_ref_ghash_f32_mt(uint64_t salt, uint64_t first_idx, size_t count, float* out, int n_threads);
+void innr_ref_ghash_u64_mt(uint64_t salt, uint64_t first_idx, size_t count, uint64_t* out, int n_threads);
+/* rows [first_row, first_row+n) x d as a VerticalBatch (pdx[dd*n + i]); == from_flat of the row-major generator output */
+void innr_ref_ghash_pdx_mt(uint64_t salt, uint64_t first_row, size_t n, size_t d, float* pdx, int n_threads);
+/* quantize_u8 of G-hash rows: row-major n x d codes */
+void innr_ref_ghash_u8_mt(uint64_t salt, uint64_t first_row, size_t n, size_t d, float alpha, float offset, uint8_t* out,
+                          int n_threads);
 
 /* ---- multi-threaded drivers for the CPU baseline (north_star: queries spread over all cores,
  *      one query per thread, shared read-only corpus) ---------------------- */

@@ -911,6 +911,106 @@ def test_sharded_merge_on_one_gpu(ib, oracle, k):
     assert np.array_equal(i1, i2) and np.array_equal(bits(s1), bits(s2))
 
 
+@pytest.mark.parametrize("k", [10, 100, 300])
+def test_keys_dev_shard_smaller_than_k(ib, oracle, k):
+    """A shard that holds fewer rows than k (the last ranks of a small corpus): the `_dev` entries must still write
+    n_queries x k rows, sentinel-padded (include/innr_cuda.h), so the gathered lists merge to the unsharded result --
+    also for several queries at once and for k > 128 (selection rounds)."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L
+    d, nq = 24, 3
+    sizes = [7, 400, 3]   # two shards smaller than every k tested, one larger than k = 10 / 100 / 300
+    n = sum(sizes)
+    rng = np.random.default_rng(11)
+    rows = rng.integers(-2, 3, size=(n, d)).astype(np.float32)
+    qs = rng.integers(-2, 3, size=(nq, d)).astype(np.float32)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    dq = torch.from_numpy(qs).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    base, shards = 0, []
+    for m in sizes:
+        shards.append(ib.DeviceBatch.from_pdx(np.ascontiguousarray(rows[base:base + m].T).reshape(-1), m, d, index_base=base))
+        base += m
+    kk = min(k, n)
+    for metric, mid, single in (("dot", L.METRIC_DOT, "batch_knn_dot"), ("cosine", L.METRIC_COSINE, "batch_knn_cosine")):
+        gathered = torch.full((len(sizes) * nq * k,), 12345, dtype=torch.int64, device="cuda")  # poison: rows must be overwritten
+        for r, sh in enumerate(shards):
+            L.call("innr_cuda_batch_knn_keys_dev", sh.h, mid, C.c_void_p(dq.data_ptr()), nq, k,
+                   C.c_void_p(gathered[r * nq * k:].data_ptr()), stream)
+        idx = torch.empty(nq * k, dtype=torch.int64, device="cuda")
+        sc = torch.empty(nq * k, dtype=torch.float32, device="cuda")
+        L.call("innr_cuda_merge_keys_dev", C.c_void_p(gathered.data_ptr()), len(sizes), nq, k, mid, None,
+               C.c_void_p(idx.data_ptr()), C.c_void_p(sc.data_ptr()), stream)
+        torch.cuda.synchronize()
+        g = gathered.cpu().numpy().view(np.uint64).reshape(len(sizes), nq, k)
+        for r, m in enumerate(sizes):   # every row: min(k, m) keys then sentinels
+            assert np.all(g[r, :, min(k, m):] == np.uint64(0xFFFFFFFFFFFFFFFF)), (metric, r)
+            assert np.all(g[r, :, :min(k, m)] != np.uint64(0xFFFFFFFFFFFFFFFF)), (metric, r)
+        idx, sc = idx.cpu().numpy().reshape(nq, k), sc.cpu().numpy().reshape(nq, k)
+        for j in range(nq):
+            w = getattr(oracle, single)(qs[j], ob, k)
+            assert idx[j, :kk].tolist() == w.indices and np.array_equal(bits(sc[j, :kk]), bits(w.scores)), (metric, j)
+    # the same contract on the Hamming and u8 entries
+    codes = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
+    qc = rng.integers(0, 2**63, size=(nq, 4), dtype=np.uint64)
+    base, gathered = 0, torch.full((len(sizes) * nq * k,), 12345, dtype=torch.int64, device="cuda")
+    dqc = torch.from_numpy(qc.view(np.int64)).cuda()
+    keep = []
+    for r, m in enumerate(sizes):
+        sh = ib.BinaryCorpus.from_words(codes[base:base + m], m, 256, index_base=base)
+        keep.append(sh)
+        L.call("innr_cuda_hamming_topk_keys_dev", sh.h, C.c_void_p(dqc.data_ptr()), nq, k,
+               C.c_void_p(gathered[r * nq * k:].data_ptr()), stream)
+        base += m
+    keys = torch.empty(nq * k, dtype=torch.int64, device="cuda")
+    idx = torch.empty(nq * k, dtype=torch.int64, device="cuda")
+    L.call("innr_cuda_merge_keys_dev", C.c_void_p(gathered.data_ptr()), len(sizes), nq, k, L.METRIC_L2,
+           C.c_void_p(keys.data_ptr()), C.c_void_p(idx.data_ptr()), None, stream)
+    torch.cuda.synchronize()
+    idx = idx.cpu().numpy().reshape(nq, k)
+    for j in range(nq):
+        wi, wd = oracle.hamming_topk(qc[j], codes, k)
+        assert idx[j, :kk].tolist() == wi.tolist(), j
+
+
+def test_dev_entries_on_different_streams_do_not_share_the_workspace_unordered(ib, oracle):
+    """`_dev` entries return while their kernels are still in flight on the CALLER's stream; the per-device workspace
+    (partial lists, tickets) is ordered between streams by an event, so back-to-back calls on two streams, and a
+    host-facing call right behind them, all give the single-call results."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L
+    n, d, k, nq = 300_000, 64, 10, 1
+    rows = rand_rows(n, d, 21)
+    qs = rand_rows(4, d, 22)
+    db = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    want = [ib.batch_knn_many("dot", qs[j], db, k) for j in range(4)]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    dq = torch.from_numpy(qs).cuda()
+    outs = [torch.empty(k, dtype=torch.int64, device="cuda") for _ in range(4)]
+    torch.cuda.synchronize()
+    for rep in range(20):
+        for j, st in enumerate((s1, s2, s1, s2)):
+            L.call("innr_cuda_batch_knn_keys_dev", db.h, L.METRIC_DOT, C.c_void_p(dq[j].data_ptr()), nq, k,
+                   C.c_void_p(outs[j].data_ptr()), C.c_void_p(st.cuda_stream))
+        host = ib.batch_knn_many("dot", qs[rep % 4], db, k)   # internal stream, right behind the asynchronous calls
+        torch.cuda.synchronize()
+        assert np.array_equal(host[0], want[rep % 4][0]) and np.array_equal(bits(host[1]), bits(want[rep % 4][1]))
+        for j in range(4):
+            keys = outs[j].cpu().numpy().view(np.uint64)
+            assert (keys & np.uint64(0xFFFFFFFF)).tolist() == want[j][0][0].tolist(), (rep, j)
+
+
+def test_entries_leave_the_current_device_alone(ib):
+    import torch
+    before = torch.cuda.current_device()
+    ib.batch_knn_dot(np.ones(4, np.float32), ib.VerticalBatch.from_flat(np.ones(8, np.float32), 2, 4), 1)
+    assert torch.cuda.current_device() == before
+    x = torch.ones(4, device="cuda") * 2   # torch still works on its own device after library calls
+    assert float(x.sum()) == 8.0
+
+
 # ------------------------------------------------------------------------------------------------ full BASELINE sizes
 def _free_gb():
     import torch
