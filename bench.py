@@ -262,6 +262,7 @@ class Workload:
         self.args, self.workload, self.rank, self.world = args, workload, rank, world
         self.torch = None
         self._cpu = None
+        self.exchange = None  # PeerExchange of this rank (N > 1, --sharding peer)
 
     @property
     def dev(self):
@@ -285,7 +286,7 @@ class Workload:
 
     def close(self):
         """Drop the device shard (and the CPU sample) before the next workload is built."""
-        for name in ("sk", "shard", "q_dev", "out", "_cpu", "_h_idx", "_h_sc", "inproc"):
+        for name in ("sk", "shard", "q_dev", "out", "_cpu", "_h_idx", "_h_sc"):
             if hasattr(self, name):
                 setattr(self, name, None)
         gc.collect()
@@ -351,7 +352,7 @@ class KnnF32(Workload):
         self.n_local = hi - lo
         gen, salt = ("gref", 0) if self.demo else ("ghash", synth.SALT_CORPUS)
         self.shard = ib.DeviceBatch.generate(gen, salt, lo, self.n_local, self.d, index_base=lo)
-        self.sk = sharded.ShardedKnn(self.shard, "f32", self.metric)
+        self.sk = sharded.ShardedKnn(self.shard, "f32", self.metric, exchange=self.exchange)
         self.q_host_t, self.q_host = self.pinned(self.q_np)
         self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         passes = (self.nq + 7) // 8 if self.nq > 1 else 1
@@ -435,7 +436,7 @@ class Hamming(Workload):
         lo, hi = sharded.shard_range(self.n, self.rank, self.world)
         self.n_local = hi - lo
         self.shard = ib.BinaryCorpus.generate(synth.SALT_CODES, lo, self.n_local, self.dim, index_base=lo)
-        self.sk = sharded.ShardedKnn(self.shard, "binary")
+        self.sk = sharded.ShardedKnn(self.shard, "binary", exchange=self.exchange)
         self.q_host_t, self.q_host = self.pinned(self.q_np)
         self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         self.kernel_bytes = self.n_local * 128
@@ -498,7 +499,7 @@ class U8(Workload):
         self.n_local = hi - lo
         self.params = ib.QuantizationParams.from_range(-1.0, 1.0)
         self.shard = ib.U8Corpus.generate(synth.SALT_CORPUS, lo, self.n_local, self.d, self.params, index_base=lo)
-        self.sk = sharded.ShardedKnn(self.shard, "u8")
+        self.sk = sharded.ShardedKnn(self.shard, "u8", exchange=self.exchange)
         self.q_host_t, self.q_host = self.pinned(self.q_np)
         self.q_dev = torch.from_numpy(self.q_np).to(self.dev)
         self.kernel_bytes = self.n_local * self.d
@@ -648,6 +649,7 @@ def measure(w, args, env):
     from innr_b200 import _lib as L
     steps, warmup = args.steps, args.warmup
     cid, _, metric, unit = WORKLOADS[w.workload]
+    w.exchange = env.get("exchange")
     w.setup(torch)
     torch.cuda.synchronize()
 
@@ -663,6 +665,24 @@ def measure(w, args, env):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    # ---- N > 1: the peer-mapped exchange must give what the NCCL allgather + merge path gives (same bits, every rank)
+    exchange_check = None
+    if world > 1 and getattr(w, "sk", None) is not None and w.exchange is not None and w.exchange.fits(w.nq, w.k):
+        from innr_b200 import sharded
+        ref_sk = sharded.ShardedKnn(w.shard, w.sk.kind, w.sk.metric)
+        bad = 0
+        for i in range(4):
+            q = w.q_dev[i % w.q_dev.shape[0]]
+            a = [t.clone() for t in w.sk.knn_dev(q, w.nq, w.k)]
+            b = [t.clone() for t in ref_sk.knn_dev(q, w.nq, w.k)]
+            torch.cuda.synchronize()
+            bad += int(not (torch.equal(a[0], b[0]) and torch.equal(a[1].double(), b[1].double())))
+        bad = int(max_over_ranks(float(bad)))
+        exchange_check = "peer exchange == nccl allgather + merge on 4 steps, all ranks" if bad == 0 else f"MISMATCH on {bad} steps"
+        if bad or w.exchange.status() != 0:
+            raise RuntimeError(f"{w.workload}: {exchange_check}; exchange status {w.exchange.status()}")
+        del ref_sk
 
     # ---- device-resident timed region ---------------------------------------------------------------
     for i in range(warmup):
@@ -765,6 +785,10 @@ def measure(w, args, env):
             "roofline": roofline,
             "clocks": clocks,
         }
+        if world > 1:
+            entry["exchange"] = env["exchange_desc"] if getattr(w, "sk", None) is not None else "none (documents are independent)"
+            if exchange_check:
+                entry["exchange_check"] = exchange_check
     return entry
 
 
@@ -797,6 +821,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="corpus size multiplier (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-shard top-k lists meet -- peer-mapped mailboxes (one launch, default) or one "
+                         "NCCL allgather + merge launch (the comparison)")
     ap.add_argument("--ref-small-sample", action="store_true",
                     help="reference arm: score a small prefix of the rows and scale (the round-1 behaviour)")
     ap.add_argument("--ref-budget-s", type=float, default=420.0,
@@ -824,7 +851,23 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     ib.init(local_rank)
-    env = {"torch": torch, "dist": dist, "ib": ib, "rank": rank, "world": world, "local_rank": local_rank}
+    env = {"torch": torch, "dist": dist, "ib": ib, "rank": rank, "world": world, "local_rank": local_rank,
+           "exchange": None, "exchange_desc": "nccl all_gather_into_tensor of k keys per rank + merge launch"}
+    if world > 1 and args.sharding == "peer":
+        # mailboxes mapped between the ranks with CUDA IPC; every rank must succeed or all use the NCCL path
+        from innr_b200 import sharded
+        ex, why = None, ""
+        try:
+            ex = sharded.PeerExchange.for_process_group(dist)
+        except Exception as e:  # e.g. no peer access between the GPUs, IPC not permitted in this container
+            why = f"{type(e).__name__}: {e}"[:200]
+        ok = torch.tensor([1 if ex is not None else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            env["exchange"] = ex
+            env["exchange_desc"] = "peer-mapped mailboxes over NVLink (CUDA IPC): publish + wait + merge in one launch, no NCCL on the data path"
+        else:
+            env["exchange_desc"] += f" (peer exchange unavailable on some rank: {why or 'see other ranks'})"
 
     names = ALL_ORDER if args.workload == "all" else [args.workload]
     entries, cpu_cache = {}, {}

@@ -274,6 +274,33 @@ int innr_cuda_maxsim(const innr_cuda_corpus* c, const float* q_tokens, size_t n_
 int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, size_t n_q, int cosine_flag,
                          float* dev_scores, void* stream);
 
+/* ---- cross-GPU exchange of per-shard top-k lists without a collective library (csrc/exchange.cu) ---------
+ * Every rank owns a small mailbox in its device memory and maps every peer's (CUDA IPC between processes,
+ * peer access inside one process). innr_cuda_exchange_merge_dev is ONE kernel launch: it publishes this rank's sorted
+ * key lists into all mailboxes over NVLink, raises a flag, waits for the peers' flags and merges the n_ranks lists --
+ * every rank obtains the same merged top-k (what ncclAllGather + innr_cuda_merge_keys_dev produce, in one launch and
+ * without NCCL). All ranks must make the same sequence of calls with the same (n_queries, k). k <= 128 and
+ * n_queries * k <= slot_keys; larger requests: gather the lists yourself and use innr_cuda_merge_keys_dev. */
+typedef struct innr_cuda_exchange innr_cuda_exchange;
+/* on the calling thread's device (innr_cuda_init); slot_keys == 0 -> 16384 keys per rank and call */
+int innr_cuda_exchange_create(int n_ranks, int rank, size_t slot_keys, innr_cuda_exchange** out);
+/* 64-byte cudaIpcMemHandle_t of this rank's mailbox, to be handed to the other processes */
+int innr_cuda_exchange_ipc_handle(const innr_cuda_exchange* ex, void* out_handle64);
+/* handles: n_ranks x 64 bytes in rank order (the own entry is ignored) */
+int innr_cuda_exchange_connect_ipc(innr_cuda_exchange* ex, const void* handles);
+/* ranks 0..n_ranks-1 living in THIS process (possibly on different devices): enables peer access and connects them all */
+int innr_cuda_exchange_connect_local(innr_cuda_exchange* const* all, int n_ranks);
+int innr_cuda_exchange_free(innr_cuda_exchange* ex);
+/* a call whose peers do not publish within the timeout (default 10 s) gives up and sets the status to 1 */
+int innr_cuda_exchange_set_timeout_ms(innr_cuda_exchange* ex, double ms);
+int innr_cuda_exchange_status(innr_cuda_exchange* ex, int* out_status);
+/* dev_local_keys: n_queries x k sorted keys of this rank's shard (what the *_keys_dev entries write). Outputs (device,
+ * any may be NULL): merged keys, indices (u64), scores decoded for `metric` (f32), key high halves (u32: Hamming
+ * distances). publish_only != 0: publish and return without waiting or merging (ranks that do not need the result). */
+int innr_cuda_exchange_merge_dev(innr_cuda_exchange* ex, const uint64_t* dev_local_keys, size_t n_queries, size_t k,
+                                 int metric, int publish_only, uint64_t* dev_keys_out, uint64_t* dev_idx,
+                                 float* dev_score, uint32_t* dev_dist, void* stream);
+
 /* ---- one process, several GPUs ---------------------------------------------------------------------------
  * Row shards living on different devices (created after innr_cuda_init(device) on the creating thread, each with
  * index_base = its first global row). The call runs one host thread per shard -- calls on different devices do not

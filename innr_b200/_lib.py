@@ -91,6 +91,14 @@ SIGNATURES = {
     "innr_cuda_batch_knn_sharded": [vp, sz, ci, f32p, sz, sz, sz, u64p, f32p, szp],
     "innr_cuda_hamming_topk_sharded": [vp, sz, u64p, sz, sz, sz, u64p, u32p, szp],
     "innr_cuda_batch_knn_u8_sharded": [vp, sz, f32p, sz, sz, sz, u64p, f32p, szp],
+    "innr_cuda_exchange_create": [ci, ci, sz, handle_p],
+    "innr_cuda_exchange_ipc_handle": [vp, vp],
+    "innr_cuda_exchange_connect_ipc": [vp, vp],
+    "innr_cuda_exchange_connect_local": [vp, ci],
+    "innr_cuda_exchange_free": [vp],
+    "innr_cuda_exchange_set_timeout_ms": [vp, C.c_double],
+    "innr_cuda_exchange_status": [vp, C.POINTER(ci)],
+    "innr_cuda_exchange_merge_dev": [vp, vp, sz, sz, ci, ci, vp, vp, vp, vp, vp],
     "innr_cuda_maxsim_batch": [vp, f32p, sz, sz, sz, ci, f32p],
     "innr_cuda_maxsim_batch_dev": [vp, vp, sz, sz, ci, vp, vp],
     "innr_cuda_maxsim_dev": [vp, vp, sz, ci, vp, vp],

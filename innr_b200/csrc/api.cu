@@ -45,6 +45,20 @@ struct innr_cuda_corpus {
   uint32_t* dev_order = nullptr;
 };
 
+// One rank's end of the peer-mapped key exchange (exchange.cu).
+struct innr_cuda_exchange {
+  int device = 0, n_ranks = 1, rank = 0;
+  size_t slot_keys = 0;
+  void* mailbox = nullptr;                 // cudaMalloc'd on `device`
+  std::vector<void*> peers;                // every rank's mailbox as mapped here (peers[rank] == mailbox)
+  std::vector<char> ipc_opened;            // peers[i] came from cudaIpcOpenMemHandle
+  void** dev_peer_table = nullptr;
+  unsigned* dev_status = nullptr;
+  uint64_t calls = 0;                      // number of the last call made on this rank
+  uint64_t timeout_ns = 10ull * 1000 * 1000 * 1000;
+  bool connected = false;
+};
+
 namespace {
 
 constexpr int MAX_DEVICES = 16;
@@ -2029,6 +2043,172 @@ int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, s
   if (rc) return rc;
   DevRelease rel(*ctx, (cudaStream_t)stream);
   return maxsim_common(c, ctx, dev_q_tokens, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ peer-mapped exchange
+static ExchangeView ex_view(const innr_cuda_exchange* x) {
+  return ExchangeView{(uint64_t*)x->mailbox, (uint64_t* const*)x->dev_peer_table, x->n_ranks, x->rank, x->slot_keys,
+                      x->dev_status, x->timeout_ns};
+}
+
+int innr_cuda_exchange_create(int n_ranks, int rank, size_t slot_keys, innr_cuda_exchange** out) {
+  if (!out || n_ranks < 1 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return fail(INNR_EINVAL, "exchange_create: bad rank / n_ranks");
+  if (slot_keys == 0) slot_keys = 16384;
+  const int device = cur_dev();
+  EntryGuard lk(device);
+  DeviceCtx* ctx;
+  int rc = current_ctx(&ctx);
+  if (rc) return rc;
+  innr_cuda_exchange* x = new (std::nothrow) innr_cuda_exchange();
+  if (!x) return fail(INNR_ENOMEM, "host allocation failed");
+  x->device = device;
+  x->n_ranks = n_ranks;
+  x->rank = rank;
+  x->slot_keys = slot_keys;
+  x->peers.assign(n_ranks, nullptr);
+  x->ipc_opened.assign(n_ranks, 0);
+  const size_t bytes = exchange_mailbox_bytes(n_ranks, slot_keys);
+  cudaError_t e = cudaMalloc(&x->mailbox, bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->mailbox, 0, bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&x->dev_peer_table, n_ranks * sizeof(void*));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&x->dev_status, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(x->dev_status, 0, sizeof(unsigned));
+  if (e != cudaSuccess) {
+    if (x->mailbox) cudaFree(x->mailbox);
+    if (x->dev_peer_table) cudaFree(x->dev_peer_table);
+    if (x->dev_status) cudaFree(x->dev_status);
+    delete x;
+    return cuda_fail(e, "exchange_create");
+  }
+  x->peers[rank] = x->mailbox;
+  if (n_ranks == 1) {
+    e = cudaMemcpy(x->dev_peer_table, x->peers.data(), sizeof(void*), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "exchange_create");
+    x->connected = true;
+  }
+  *out = x;
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_ipc_handle(const innr_cuda_exchange* x, void* out_handle64) {
+  if (!x || !out_handle64) return fail(INNR_EINVAL, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  EntryGuard lk(x->device);
+  CU(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, x->mailbox));
+  std::memcpy(out_handle64, &h, 64);
+  return INNR_OK;
+}
+
+static int exchange_finish_connect(innr_cuda_exchange* x) {
+  CU(cudaSetDevice(x->device));
+  CU(cudaMemcpy(x->dev_peer_table, x->peers.data(), x->n_ranks * sizeof(void*), cudaMemcpyHostToDevice));
+  x->connected = true;
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_connect_ipc(innr_cuda_exchange* x, const void* handles) {
+  if (!x || !handles) return fail(INNR_EINVAL, "null argument");
+  EntryGuard lk(x->device);
+  CU(cudaSetDevice(x->device));
+  for (int r = 0; r < x->n_ranks; ++r) {
+    if (r == x->rank || x->peers[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peers[r] = p;
+    x->ipc_opened[r] = 1;
+  }
+  return exchange_finish_connect(x);
+}
+
+int innr_cuda_exchange_connect_local(innr_cuda_exchange* const* all, int n_ranks) {
+  if (!all || n_ranks < 1) return fail(INNR_EINVAL, "null argument");
+  for (int r = 0; r < n_ranks; ++r)
+    if (!all[r] || all[r]->n_ranks != n_ranks || all[r]->rank != r || all[r]->slot_keys != all[0]->slot_keys)
+      return fail(INNR_EINVAL, "exchange_connect_local: objects must be ranks 0..n-1 of one exchange");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int r = 0; r < n_ranks; ++r) {
+    innr_cuda_exchange* x = all[r];
+    std::lock_guard<std::mutex> lk(dev_mu(x->device));
+    cudaSetDevice(x->device);
+    for (int p = 0; p < n_ranks; ++p) {
+      if (all[p]->device != x->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, x->device, all[p]->device);
+        if (!can) {
+          if (prev >= 0) cudaSetDevice(prev);
+          return fail(INNR_EUNSUPPORTED, "exchange_connect_local: no peer access between the devices");
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[p]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          if (prev >= 0) cudaSetDevice(prev);
+          return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        }
+        cudaGetLastError();
+      }
+      x->peers[p] = all[p]->mailbox;
+    }
+    int rc = exchange_finish_connect(x);
+    if (rc) {
+      if (prev >= 0) cudaSetDevice(prev);
+      return rc;
+    }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_free(innr_cuda_exchange* x) {
+  if (!x) return INNR_OK;
+  EntryGuard lk(x->device);
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < x->n_ranks; ++r)
+    if (x->ipc_opened[r] && x->peers[r]) cudaIpcCloseMemHandle(x->peers[r]);
+  cudaFree(x->mailbox);
+  cudaFree(x->dev_peer_table);
+  cudaFree(x->dev_status);
+  cudaGetLastError();
+  delete x;
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_set_timeout_ms(innr_cuda_exchange* x, double ms) {
+  if (!x || !(ms > 0)) return fail(INNR_EINVAL, "bad argument");
+  x->timeout_ns = (uint64_t)(ms * 1e6);
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_status(innr_cuda_exchange* x, int* out_status) {
+  if (!x || !out_status) return fail(INNR_EINVAL, "null argument");
+  EntryGuard lk(x->device);
+  CU(cudaSetDevice(x->device));
+  unsigned v = 0;
+  CU(cudaMemcpy(&v, x->dev_status, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  *out_status = (int)v;
+  return INNR_OK;
+}
+
+int innr_cuda_exchange_merge_dev(innr_cuda_exchange* x, const uint64_t* dev_local_keys, size_t n_queries, size_t k,
+                                 int metric, int publish_only, uint64_t* dev_keys_out, uint64_t* dev_idx,
+                                 float* dev_score, uint32_t* dev_dist, void* stream) {
+  if (!x || !x->connected) return fail(INNR_EINVAL, "exchange is not connected");
+  if (k == 0 || n_queries == 0) return INNR_OK;
+  if (k > MAX_FUSED_K) return fail(INNR_EUNSUPPORTED, "exchange_merge_dev: k > 128 (gather the lists and use innr_cuda_merge_keys_dev)");
+  if (n_queries * k > x->slot_keys) return fail(INNR_EUNSUPPORTED, "exchange_merge_dev: n_queries * k exceeds the mailbox slot");
+  if (!dev_local_keys) return fail(INNR_EINVAL, "null argument");
+  EntryGuard lk(x->device);
+  DeviceCtx* ctx;
+  int rc = ensure_ctx(x->device, &ctx, true, (cudaStream_t)stream);
+  if (rc) return rc;
+  ++x->calls;
+  CU(launch_exchange_merge(ex_view(x), dev_local_keys, n_queries, k, x->calls, publish_only, metric != INNR_METRIC_L2,
+                           dev_keys_out, dev_idx, dev_score, dev_dist, (cudaStream_t)stream, &g_launches));
+  return INNR_OK;
 }
 
 // ------------------------------------------------------------------------------------------ one process, several GPUs

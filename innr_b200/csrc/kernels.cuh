@@ -104,6 +104,23 @@ cudaError_t launch_adaptive_revive(const uint64_t* dev_keys, size_t m, uint32_t*
 // exact scores (mode = PDX_DOT / PDX_L2 / PDX_COSINE_FUSED) of m candidate vectors given by GLOBAL id
 cudaError_t launch_subset_scores(const PdxView& v, int mode, const float* dev_query, const uint32_t* dev_cand, size_t m,
                                  float* dev_out, cudaStream_t s, LaunchCounter* launches);
+// cross-GPU exchange + merge of per-shard top-k lists through peer-mapped mailboxes (exchange.cu)
+constexpr int EX_MAX_CTAS = 64;
+constexpr int EX_THREADS = 256;
+struct ExchangeView {
+  uint64_t* mailbox;                 // this rank's mailbox (device memory of this rank)
+  uint64_t* const* dev_peer_table;   // device array [n_ranks]: every rank's mailbox as mapped in this process
+  int n_ranks, rank;
+  size_t slot_keys;                  // capacity of one (parity, rank) slot, in keys
+  unsigned* dev_status;              // set to 1 by a call whose peers did not publish within timeout_ns
+  uint64_t timeout_ns;
+};
+size_t exchange_mailbox_bytes(int n_ranks, size_t slot_keys);
+// dev_local_keys: nq x k sorted keys (k <= 128, nq * k <= slot_keys). `call` numbers the calls 1, 2, ... identically on
+// every rank. Outputs (any may be null): merged keys, indices, f32 scores (decoded by `descending`), u32 high halves.
+cudaError_t launch_exchange_merge(const ExchangeView& x, const uint64_t* dev_local_keys, size_t nq, size_t k, uint64_t call,
+                                  int publish_only, int descending, uint64_t* dev_keys_out, uint64_t* dev_idx,
+                                  float* dev_score, uint32_t* dev_dist, cudaStream_t s, LaunchCounter* launches);
 // keys from a plain f32 array (TopK analogue): ascending, id = i
 cudaError_t launch_topk_from_distances(const float* dev_dist, size_t n, size_t k, uint64_t* dev_keys,
                                        Workspace& ws, cudaStream_t s, LaunchCounter* launches);

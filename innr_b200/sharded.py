@@ -53,15 +53,86 @@ def merge_keys_host(key_lists: np.ndarray, k: int) -> np.ndarray:
     return np.sort(flat)[:k]
 
 
-class ShardedKnn:
-    """One rank's view of a row-sharded corpus. kind: 'f32' (DeviceBatch), 'u8' (U8Corpus), 'binary' (BinaryCorpus)."""
+class PeerExchange:
+    """One rank's end of the peer-mapped key exchange (csrc/exchange.cu, include/innr_cuda.h): a mailbox in this rank's
+    device memory that every peer writes into over NVLink, and ONE kernel per call that publishes, waits and merges --
+    the replacement of `all_gather_into_tensor` + merge launch on the sharded top-k path. Built on the calling thread's
+    device (innr_b200.init)."""
 
-    def __init__(self, shard, kind: str = "f32", metric: str = "cosine", group=None):
+    def __init__(self, n_ranks: int, rank: int, slot_keys: int = 0):
+        self.n_ranks, self.rank = int(n_ranks), int(rank)
+        h = C.c_void_p()
+        L.call("innr_cuda_exchange_create", self.n_ranks, self.rank, slot_keys, C.byref(h))
+        self.h = h
+        self.slot_keys = slot_keys or 16384
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                L.lib().innr_cuda_exchange_free(h)
+            except Exception:
+                pass
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        L.call("innr_cuda_exchange_ipc_handle", self.h, buf)
+        return buf.raw
+
+    def connect_ipc(self, handles) -> None:
+        """handles: the 64-byte handles of all ranks, in rank order (each rank's own entry is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.n_ranks
+        L.call("innr_cuda_exchange_connect_ipc", self.h, C.create_string_buffer(blob, len(blob)))
+
+    @staticmethod
+    def connect_local(exchanges) -> None:
+        """All ranks of one exchange living in THIS process (possibly on different devices)."""
+        arr = (C.c_void_p * len(exchanges))(*[x.h for x in exchanges])
+        L.call("innr_cuda_exchange_connect_local", arr, len(exchanges))
+
+    @classmethod
+    def for_process_group(cls, dist, group=None, slot_keys: int = 0) -> "PeerExchange":
+        """One process per GPU (torch.distributed): every rank creates its mailbox, the IPC handles travel through the
+        process group once, every rank maps all peers."""
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ex = cls(world, rank, slot_keys)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, ex.ipc_handle(), group=group)
+            ex.connect_ipc(handles)
+        return ex
+
+    def set_timeout_ms(self, ms: float) -> None:
+        L.call("innr_cuda_exchange_set_timeout_ms", self.h, C.c_double(ms))
+
+    def status(self) -> int:
+        v = C.c_int(0)
+        L.call("innr_cuda_exchange_status", self.h, C.byref(v))
+        return int(v.value)
+
+    def fits(self, nq: int, k: int) -> bool:
+        return 0 < k <= 128 and nq * k <= self.slot_keys
+
+    def merge_dev(self, local_keys_ptr: int, nq: int, k: int, metric_id: int, stream, keys_out=None, idx=None,
+                  score=None, dist_out=None, publish_only: bool = False) -> None:
+        vp = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        L.call("innr_cuda_exchange_merge_dev", self.h, C.c_void_p(local_keys_ptr), nq, k, metric_id, int(publish_only),
+               vp(keys_out), vp(idx), vp(score), vp(dist_out), stream)
+
+
+class ShardedKnn:
+    """One rank's view of a row-sharded corpus. kind: 'f32' (DeviceBatch), 'u8' (U8Corpus), 'binary' (BinaryCorpus).
+    `exchange`: a connected PeerExchange (keys travel through peer-mapped mailboxes, one launch) or None (one NCCL
+    `all_gather_into_tensor` of k keys per rank + the merge launch)."""
+
+    def __init__(self, shard, kind: str = "f32", metric: str = "cosine", group=None, exchange=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.shard, self.kind, self.metric, self.group = shard, kind, metric, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.exchange = exchange
         self._metric_id = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
         self._bufs = {}
 
@@ -92,6 +163,14 @@ class ShardedKnn:
             L.call("innr_cuda_batch_knn_u8_keys_dev", self.shard.h, qp, nq, k, lp, stream)
         else:
             L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
+        if self.exchange is not None and self.exchange.fits(nq, k):
+            # publish / wait / merge / decode in ONE launch, no collective call
+            if self.kind == "binary":
+                self.exchange.merge_dev(b["local"].data_ptr(), nq, k, L.METRIC_L2, stream, idx=b["idx"], dist_out=b["score"])
+            else:
+                m = L.METRIC_L2 if (self.kind == "f32" and self.metric == "l2") else L.METRIC_DOT
+                self.exchange.merge_dev(b["local"].data_ptr(), nq, k, m, stream, idx=b["idx"], score=b["score"])
+            return b["idx"].view(nq, k), b["score"].view(nq, k)
         if self.world > 1:
             self.dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
             src, n_lists = b["gathered"], self.world

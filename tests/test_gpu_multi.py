@@ -1,0 +1,69 @@
+"""Tests that need TWO OR MORE GPUs in one box (gpurun --gpus 2): the peer-mapped exchange between devices of one process,
+between processes (CUDA IPC), and the C-ABI's own sharded entries. On a 1-GPU box they skip with an explicit reason."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+needs2 = pytest.mark.skipif("_n_gpus() < 2", reason="needs >= 2 GPUs in one box (run with gpurun --gpus 2)")
+
+
+@needs2
+def test_exchange_between_processes_equals_nccl_and_oracle():
+    n = min(_n_gpus(), 4)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mp_exchange_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mp_exchange_check ok" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
+
+
+@needs2
+def test_exchange_between_devices_of_one_process(oracle):
+    """One host thread drives two devices: each rank's kernel waits for the other's flag, which arrives as soon as the
+    other device's launch (queued right behind it by the same thread) has published."""
+    import ctypes as C
+    import torch
+    import innr_b200 as ib
+    from innr_b200 import _lib as L, sharded
+    world, n, d, k, nq = 2, 40_000, 64, 10, 4
+    rng = np.random.default_rng(8)
+    rows = rng.standard_normal((n, d)).astype(np.float32)
+    qs = rng.standard_normal((nq, d)).astype(np.float32)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    shards, exs, dqs, outs = [], [], [], []
+    for r in range(world):
+        ib.init(r)
+        lo, hi = sharded.shard_range(n, r, world)
+        shards.append(ib.DeviceBatch.from_rows_flat(rows[lo:hi].reshape(-1), hi - lo, d, index_base=lo))
+        exs.append(sharded.PeerExchange(world, r))
+        with torch.cuda.device(r):
+            dqs.append(torch.from_numpy(qs).cuda())
+            outs.append((torch.empty(nq * k, dtype=torch.int64, device=f"cuda:{r}"), torch.empty(nq * k, dtype=torch.int64, device=f"cuda:{r}"),
+                         torch.empty(nq * k, dtype=torch.float32, device=f"cuda:{r}")))
+    sharded.PeerExchange.connect_local(exs)
+    for rep in range(4):
+        for r in range(world):
+            with torch.cuda.device(r):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                L.call("innr_cuda_batch_knn_keys_dev", shards[r].h, L.METRIC_COSINE, C.c_void_p(dqs[r].data_ptr()), nq, k,
+                       C.c_void_p(outs[r][0].data_ptr()), st)
+                exs[r].merge_dev(outs[r][0].data_ptr(), nq, k, L.METRIC_DOT, st, idx=outs[r][1], score=outs[r][2])
+        for r in range(world):
+            torch.cuda.synchronize(r)
+            assert exs[r].status() == 0
+            idx, sc = outs[r][1].cpu().numpy().reshape(nq, k), outs[r][2].cpu().numpy().reshape(nq, k)
+            for j in range(nq):
+                w = oracle.batch_knn_cosine(qs[j], ob, k)
+                assert idx[j].tolist() == w.indices and sc[j].tobytes() == w.scores.tobytes(), (rep, r, j)
+    ib.init(0)

@@ -911,6 +911,64 @@ def test_sharded_merge_on_one_gpu(ib, oracle, k):
     assert np.array_equal(i1, i2) and np.array_equal(bits(s1), bits(s2))
 
 
+@pytest.mark.parametrize("k,nq", [(10, 5), (100, 2), (10, 70)])
+def test_peer_exchange_emulated_on_one_gpu(ib, oracle, k, nq):
+    """The peer-mapped exchange (csrc/exchange.cu) with all three ranks emulated on ONE device: ranks that are not the
+    target publish only (ranks that wait on one another must not share a GPU), the target publishes, finds every flag
+    raised, merges and decodes in the same launch. Every rank takes the target role, over several calls (both mailbox
+    parities, slot reuse); nq = 70 spreads the queries over several CTAs."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L, sharded
+    n, d, world = 6000, 32, 3
+    rng = np.random.default_rng(5)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    shards = []
+    for r in range(world):
+        lo, hi = sharded.shard_range(n, r, world)
+        shards.append(ib.DeviceBatch.from_pdx(np.ascontiguousarray(rows[lo:hi].T).reshape(-1), hi - lo, d, index_base=lo))
+    exs = [sharded.PeerExchange(world, r) for r in range(world)]
+    sharded.PeerExchange.connect_local(exs)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for call, target in enumerate([2, 0, 1, 1, 0]):
+        qs = rng.integers(-3, 4, size=(nq, d)).astype(np.float32)
+        dq = torch.from_numpy(qs).cuda()
+        loc = [torch.empty(nq * k, dtype=torch.int64, device="cuda") for _ in range(world)]
+        for r in range(world):
+            L.call("innr_cuda_batch_knn_keys_dev", shards[r].h, L.METRIC_COSINE, C.c_void_p(dq.data_ptr()), nq, k,
+                   C.c_void_p(loc[r].data_ptr()), stream)
+        idx = torch.empty(nq * k, dtype=torch.int64, device="cuda")
+        sc = torch.empty(nq * k, dtype=torch.float32, device="cuda")
+        for r in [x for x in range(world) if x != target] + [target]:
+            exs[r].merge_dev(loc[r].data_ptr(), nq, k, L.METRIC_DOT, stream, idx=idx if r == target else None,
+                             score=sc if r == target else None, publish_only=(r != target))
+        torch.cuda.synchronize()
+        assert exs[target].status() == 0
+        idx_h, sc_h = idx.cpu().numpy().reshape(nq, k), sc.cpu().numpy().reshape(nq, k)
+        for j in range(nq):
+            w = oracle.batch_knn_cosine(qs[j], ob, k)
+            assert idx_h[j].tolist() == w.indices and np.array_equal(bits(sc_h[j]), bits(w.scores)), (call, target, j)
+
+
+def test_peer_exchange_times_out_instead_of_hanging(ib):
+    """A rank whose peers never publish gives up after the timeout and reports it; nothing spins forever."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L, sharded
+    exs = [sharded.PeerExchange(2, r) for r in range(2)]
+    sharded.PeerExchange.connect_local(exs)
+    exs[0].set_timeout_ms(50.0)
+    loc = torch.zeros(10, dtype=torch.int64, device="cuda")
+    idx = torch.empty(10, dtype=torch.int64, device="cuda")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    exs[0].merge_dev(loc.data_ptr(), 1, 10, L.METRIC_DOT, stream, idx=idx)   # rank 1 never calls
+    torch.cuda.synchronize()
+    assert exs[0].status() == 1
+    with pytest.raises(NotImplementedError):   # k > 128 and oversized requests are refused, not truncated
+        exs[0].merge_dev(loc.data_ptr(), 1, 200, L.METRIC_DOT, stream, idx=idx)
+
+
 @pytest.mark.parametrize("k", [10, 100, 300])
 def test_keys_dev_shard_smaller_than_k(ib, oracle, k):
     """A shard that holds fewer rows than k (the last ranks of a small corpus): the `_dev` entries must still write
