@@ -241,12 +241,18 @@ class ClockSampler:
             self.t.join(timeout=2)
         lo, hi = self.t_begin or 0.0, self.t_end or float("inf")
         inside = [s for s in self.samples if lo <= s[0] <= hi]
+        nearest = False
+        if not inside and self.samples:  # a timed region shorter than the sampling period (C1: < 1 ms): nearest samples
+            mid = 0.5 * (lo + min(hi, self.samples[-1][0]))
+            inside = sorted(self.samples, key=lambda s: abs(s[0] - mid))[:3]
+            nearest = True
         sm = [s[1] for s in inside]
         reasons = sorted({r for s in inside for r in s[2]})
         watts = [s[3] for s in inside if s[3] is not None]
         return {"power_w_max": max(watts) if watts else None,
                 "sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
                 "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons, "sampler": self.mode,
+                "nearest_samples_outside_window": nearest,
                 "window_ms": (hi - lo) * 1e3 if self.t_end else None}
 
 
