@@ -798,6 +798,70 @@ def measure(w, args, env):
     return entry
 
 
+def run_inproc(args):
+    """One process, N GPUs, no torch.distributed: row shards on every device, queries and results in HOST buffers, the
+    C-ABI's own sharded entries (persistent worker thread per device + peer-mapped exchange inside the library). Every
+    number here is end to end by construction (wall clock around the host-facing call)."""
+    import torch
+    import innr_b200 as ib
+    from innr_b200 import sharded, synth
+    n_dev = args.gpus
+    if torch.cuda.device_count() < n_dev:
+        raise SystemExit(f"--gpus {n_dev} but only {torch.cuda.device_count()} devices are visible")
+    peak, peak_src = load_peaks()
+    names = ["knn_cosine_1q", "hamming", "u8"] if args.workload == "all" else [args.workload]
+    entries = {}
+    for name in names:
+        cid, _, metric, unit = WORKLOADS[name]
+        n, row_bytes = corpus_shape(name, args.scale)
+        shards = []
+        for dev in range(n_dev):
+            ib.init(dev)
+            lo, hi = sharded.shard_range(n, dev, n_dev)
+            if name == "knn_cosine_1q":
+                shards.append(ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, lo, hi - lo, 768, index_base=lo))
+            elif name == "hamming":
+                shards.append(ib.BinaryCorpus.generate(synth.SALT_CODES, lo, hi - lo, 1024, index_base=lo))
+            elif name == "u8":
+                shards.append(ib.U8Corpus.generate(synth.SALT_CORPUS, lo, hi - lo, 384, ib.QuantizationParams.from_range(-1.0, 1.0), index_base=lo))
+            else:
+                raise SystemExit(f"--sharding inproc covers knn_cosine_1q, hamming and u8, not {name}")
+        ib.init(0)
+        if name == "knn_cosine_1q":
+            qs = synth.ghash_f32(synth.SALT_QUERY, 0, 16 * 768).reshape(16, 768)
+            call = lambda i: sharded.batch_knn_sharded("cosine", qs[i % 16], shards, 10)  # noqa: E731
+        elif name == "hamming":
+            qs = synth.ghash_u64(synth.SALT_QUERY, 0, 16 * 16).reshape(16, 16)
+            call = lambda i: sharded.hamming_topk_sharded(qs[i % 16], shards, 100)  # noqa: E731
+        else:
+            qs = synth.ghash_f32(synth.SALT_QUERY, 0, 16 * 384).reshape(16, 384)
+            call = lambda i: sharded.batch_knn_u8_sharded(qs[i % 16], shards, 10)  # noqa: E731
+        for i in range(max(args.warmup, 3)):
+            call(i)
+        l0 = ib.launch_count()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            call(i)
+        dt = time.perf_counter() - t0
+        entries[cid] = {"metric": metric, "value": args.steps / dt, "unit": unit, "n_gpus": n_dev, "steps": args.steps,
+                        "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+                        "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(name), "data": "synthetic",
+                        "config": config_of(name, args.scale, n_dev, args.queries),
+                        "e2e": {"value": args.steps / dt, "unit": unit, "h2d_bytes_per_step": int(qs[0].nbytes) * n_dev,
+                                "d2h_bytes_per_step": (100 if name == "hamming" else 10) * 12},
+                        "gpu_launches": int(ib.launch_count() - l0),
+                        "roofline": {"bound": "hbm", "kernel": "whole host-facing call (wall clock), all devices", "achieved": n * row_bytes / dt * args.steps / 1e9,
+                                     "peak": peak * n_dev, "unit": "GB/s", "frac": n * row_bytes / dt * args.steps / 1e9 / (peak * n_dev),
+                                     "traffic": None, "peak_source": peak_src + f" x {n_dev}"},
+                        "exchange": "one process: worker thread per device + peer-mapped mailbox merge on device 0 (innr_cuda_*_sharded)"}
+        del shards
+        gc.collect()
+    first = entries[WORKLOADS[names[0]][0]]
+    line = dict(first)
+    line["workloads"] = entries
+    print(json.dumps(line), flush=True)
+
+
 def cpu_baseline_entry(w, unit, cache):
     """The oracle on this box's host cores for workload w (rank 0, N == 1 only): one step over the full config."""
     cores = os.cpu_count() or 1
@@ -827,9 +891,10 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="corpus size multiplier (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the per-shard top-k lists meet -- peer-mapped mailboxes (one launch, default) or one "
-                         "NCCL allgather + merge launch (the comparison)")
+    ap.add_argument("--sharding", default="peer", choices=["peer", "nccl", "inproc"],
+                    help="N > 1: how the per-shard top-k lists meet -- peer-mapped mailboxes (one launch, default), one "
+                         "NCCL allgather + merge launch (the comparison), or `inproc`: ONE process (no torchrun) drives "
+                         "all N GPUs through the C-ABI's innr_cuda_*_sharded entries (what a Rust host would call)")
     ap.add_argument("--ref-small-sample", action="store_true",
                     help="reference arm: score a small prefix of the rows and scale (the round-1 behaviour)")
     ap.add_argument("--ref-budget-s", type=float, default=420.0,
@@ -844,6 +909,11 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.sharding == "inproc":
+        if world > 1:
+            raise SystemExit("--sharding inproc runs in ONE process: start it with plain `python bench.py --gpus N --sharding inproc`")
+        run_inproc(args)
         return
 
     import torch

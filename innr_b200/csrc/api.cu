@@ -8,6 +8,11 @@
 #include <mutex>
 #include <string>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <map>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -2233,6 +2238,173 @@ struct ShardOut {
   int rc = INNR_OK;
   std::string err;
 };
+// ---- in-process sharding over distinct devices: persistent worker threads + the peer-mapped exchange -------------
+// One worker per shard stays alive between calls (thread creation costs more than an eighth-of-a-corpus scan); a call
+// hands every worker one closure and waits for all of them. Workers spin briefly after a job before they block, so
+// back-to-back calls find them hot.
+class ShardPool {
+ public:
+  explicit ShardPool(size_t n) : n_(n) {
+    for (size_t i = 0; i < n; ++i) th_.emplace_back([this, i] { loop(i); });
+  }
+  ~ShardPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void run(const std::function<void(size_t)>& job) {
+    job_ = &job;
+    done_.store(0, std::memory_order_relaxed);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      gen_.fetch_add(1, std::memory_order_release);
+    }
+    cv_.notify_all();
+    while (done_.load(std::memory_order_acquire) != n_) std::this_thread::yield();
+  }
+
+ private:
+  void loop(size_t i) {
+    uint64_t seen = 0;
+    for (;;) {
+      // hot phase: poll the generation counter for a while, then block
+      bool got = false;
+      for (int spin = 0; spin < 20000 && !got; ++spin) got = gen_.load(std::memory_order_acquire) != seen;
+      if (!got) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+      }
+      seen = gen_.load(std::memory_order_acquire);
+      if (stop_) return;
+      (*job_)(i);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  size_t n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::atomic<uint64_t> gen_{0};
+  std::atomic<size_t> done_{0};
+  const std::function<void(size_t)>* job_ = nullptr;
+  bool stop_ = false;
+};
+
+struct ShardGroup {  // one per distinct ordered device list
+  std::vector<innr_cuda_exchange*> ex;
+  std::unique_ptr<ShardPool> pool;
+  std::vector<Buf> pin_q, pin_out;  // per shard pinned staging (queries in, root results out)
+  std::vector<Buf> d_idx, d_score;  // root outputs
+  std::mutex mu;                    // one sharded call at a time per group (the exchange numbers its calls)
+};
+std::mutex g_groups_mu;
+std::map<std::vector<int>, std::unique_ptr<ShardGroup>> g_groups;
+
+// Devices of the shards if they are pairwise distinct and a group can be (or was) set up, else nullptr (the caller
+// then takes the thread-per-shard + host-merge route, which also serves several shards on one device).
+ShardGroup* shard_group_for(const innr_cuda_corpus* const* shards, size_t n_shards) {
+  if (n_shards < 2) return nullptr;
+  std::vector<int> devs(n_shards);
+  for (size_t i = 0; i < n_shards; ++i) devs[i] = shards[i]->device;
+  std::vector<int> sorted_devs = devs;
+  std::sort(sorted_devs.begin(), sorted_devs.end());
+  if (std::adjacent_find(sorted_devs.begin(), sorted_devs.end()) != sorted_devs.end()) return nullptr;
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto it = g_groups.find(devs);
+  if (it != g_groups.end()) return it->second.get();  // may hold nullptr: set-up failed once, do not retry per call
+  std::unique_ptr<ShardGroup> g(new ShardGroup());
+  bool ok = true;
+  const int saved = t_device;
+  for (size_t i = 0; i < n_shards && ok; ++i) {
+    t_device = devs[i];
+    innr_cuda_exchange* x = nullptr;
+    ok = innr_cuda_exchange_create((int)n_shards, (int)i, 0, &x) == INNR_OK;
+    if (ok) g->ex.push_back(x);
+  }
+  t_device = saved;
+  if (ok) ok = innr_cuda_exchange_connect_local(g->ex.data(), (int)n_shards) == INNR_OK;
+  if (!ok) {
+    for (auto* x : g->ex) innr_cuda_exchange_free(x);
+    g_groups[devs] = nullptr;
+    return nullptr;
+  }
+  g->pool.reset(new ShardPool(n_shards));
+  g->pin_q.resize(n_shards);
+  g->pin_out.resize(n_shards);
+  g->d_idx.resize(n_shards);
+  g->d_score.resize(n_shards);
+  for (size_t i = 0; i < n_shards; ++i) g->pin_q[i].pinned = g->pin_out[i].pinned = true;
+  ShardGroup* raw = g.get();
+  g_groups[devs] = std::move(g);
+  return raw;
+}
+
+// The exchange route of the three sharded entries. `enqueue_keys(i, ctx, dev_query, dev_keys)` queues shard i's local
+// top-k on ctx->stream. Shard 0's device is the root: it merges and its result travels back; the others only publish.
+// Returns INNR_EUNSUPPORTED when the request does not fit the mailboxes (caller falls back).
+template <class EnqueueKeys>
+int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, size_t n_shards, const void* queries,
+                         size_t query_bytes, size_t nq, size_t k, int metric, bool want_dist, EnqueueKeys enqueue_keys,
+                         uint64_t* out_idx, float* out_score, uint32_t* out_dist) {
+  if (k > MAX_FUSED_K || nq * k > g->ex[0]->slot_keys) return INNR_EUNSUPPORTED;
+  std::lock_guard<std::mutex> call_lk(g->mu);
+  std::vector<int> rcs(n_shards, INNR_OK);
+  std::vector<std::string> errs(n_shards);
+  const size_t out_bytes = nq * k * (sizeof(uint64_t) + sizeof(uint32_t));
+  std::function<void(size_t)> job = [&](size_t i) {
+    auto body = [&]() -> int {
+      const innr_cuda_corpus* c = shards[i];
+      EntryGuard lk(c->device);
+      DeviceCtx* ctx;
+      int rc = ctx_for(c, &ctx);
+      if (rc) return rc;
+      cudaStream_t s = ctx->stream;
+      CU(g->pin_q[i].reserve(query_bytes));
+      std::memcpy(g->pin_q[i].p, queries, query_bytes);
+      CU(ctx->d_query.reserve(query_bytes + 16));
+      CU(ctx->d_keys.reserve(nq * k * sizeof(uint64_t)));
+      CU(cudaMemcpyAsync(ctx->d_query.p, g->pin_q[i].p, query_bytes, cudaMemcpyHostToDevice, s));
+      rc = enqueue_keys(i, ctx, ctx->d_query.p, (uint64_t*)ctx->d_keys.p);
+      if (rc) return rc;
+      innr_cuda_exchange* x = g->ex[i];
+      ++x->calls;
+      if (i != 0) {
+        CU(launch_exchange_merge(ex_view(x), (const uint64_t*)ctx->d_keys.p, nq, k, x->calls, 1, 0, nullptr, nullptr, nullptr,
+                                 nullptr, s, &g_launches));
+        return INNR_OK;  // stays in flight on this device's stream; the root's merge is what waits for it
+      }
+      CU(g->d_idx[0].reserve(nq * k * sizeof(uint64_t)));
+      CU(g->d_score[0].reserve(nq * k * sizeof(uint32_t)));
+      CU(g->pin_out[0].reserve(out_bytes));
+      CU(launch_exchange_merge(ex_view(x), (const uint64_t*)ctx->d_keys.p, nq, k, x->calls, 0, metric != INNR_METRIC_L2, nullptr,
+                               (uint64_t*)g->d_idx[0].p, want_dist ? nullptr : (float*)g->d_score[0].p,
+                               want_dist ? (uint32_t*)g->d_score[0].p : nullptr, s, &g_launches));
+      char* h = (char*)g->pin_out[0].p;
+      CU(cudaMemcpyAsync(h, g->d_idx[0].p, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpyAsync(h + nq * k * sizeof(uint64_t), g->d_score[0].p, nq * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      unsigned st = 0;
+      CU(cudaMemcpy(&st, x->dev_status, sizeof(unsigned), cudaMemcpyDeviceToHost));
+      if (st) return fail(INNR_ECUDA, "sharded call: a shard did not publish its keys within the exchange timeout");
+      return INNR_OK;
+    };
+    rcs[i] = body();
+    if (rcs[i]) errs[i] = t_err;
+  };
+  g->pool->run(job);
+  for (size_t i = 0; i < n_shards; ++i)
+    if (rcs[i]) return fail(rcs[i], "shard " + std::to_string(i) + ": " + errs[i]);
+  const char* h = (const char*)g->pin_out[0].p;
+  std::memcpy(out_idx, h, nq * k * sizeof(uint64_t));
+  if (want_dist) std::memcpy(out_dist, h + nq * k * sizeof(uint64_t), nq * k * sizeof(uint32_t));
+  else std::memcpy(out_score, h + nq * k * sizeof(uint64_t), nq * k * sizeof(float));
+  return INNR_OK;
+}
+
 template <class Call>
 int run_shards(size_t n_shards, Call call, std::vector<ShardOut>& outs) {
   std::vector<std::thread> th;
@@ -2264,15 +2436,37 @@ int innr_cuda_batch_knn_sharded(const innr_cuda_corpus* const* shards, size_t n_
   if (query_len != shards[0]->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");
   if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_score) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < n_total ? k : n_total;
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  // distinct devices: every shard scans on its own stream, the lists meet in the root's mailbox over NVLink and are
+  // merged there in the same launch (csrc/exchange.cu); one D2H of k results, no host merge
+  if (ShardGroup* g = shard_group_for(shards, n_shards)) {
+    rc = sharded_via_exchange(g, shards, n_shards, queries, n_queries * query_len * sizeof(float), n_queries, k, metric, false,
+                              [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk) -> int {
+                                innr_cuda_corpus* c = const_cast<innr_cuda_corpus*>(shards[i]);
+                                if (c->n == 0) {
+                                  CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), ctx->stream));
+                                  return INNR_OK;
+                                }
+                                return knn_keys_dev(c, ctx, mode, (const float*)dq, n_queries, k, dk, ctx->stream);
+                              },
+                              out_idx, out_score, nullptr);
+    if (rc == INNR_OK) {
+      if (out_count) *out_count = kk;
+      return INNR_OK;
+    }
+    if (rc != INNR_EUNSUPPORTED) return rc;
+  }
   std::vector<ShardOut> outs(n_shards);
-  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+  rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
     o.idx.assign(n_queries * k, 0);
     o.score.assign(n_queries * k, 0.0f);
     return innr_cuda_batch_knn(shards[i], metric, queries, n_queries, query_len, k, o.idx.data(), o.score.data(), &o.count);
   }, outs);
   if (rc) return rc;
   const bool desc = metric != INNR_METRIC_L2;
-  const size_t kk = k < n_total ? k : n_total;
   std::vector<std::pair<uint64_t, float>> all;
   for (size_t q = 0; q < n_queries; ++q) {
     all.clear();
@@ -2304,14 +2498,44 @@ int innr_cuda_hamming_topk_sharded(const innr_cuda_corpus* const* shards, size_t
   }
   if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_dist) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < n_total ? k : n_total;
+  int rc = INNR_OK;
+  bool same_dim = true;
+  for (size_t i = 0; i < n_shards; ++i) same_dim = same_dim && shards[i]->dim_bits == query_dim_bits;
+  if (ShardGroup* g = (same_dim && shards[0]->words) ? shard_group_for(shards, n_shards) : nullptr) {
+    // the query codes in the form the scan reads them: padded to whole 128-bit chunks, padding bits masked
+    const innr_cuda_corpus* c0 = shards[0];
+    const size_t qw = 2 * c0->chunks, rem = c0->dim_bits % 64;
+    std::vector<uint64_t> padded(n_queries * qw, 0);
+    for (size_t q = 0; q < n_queries; ++q)
+      for (size_t w = 0; w < c0->words; ++w) {
+        uint64_t x = query_words[q * c0->words + w];
+        if (w + 1 == c0->words && rem) x &= (1ull << rem) - 1;
+        padded[q * qw + w] = x;
+      }
+    rc = sharded_via_exchange(g, shards, n_shards, padded.data(), padded.size() * sizeof(uint64_t), n_queries, k, INNR_METRIC_L2, true,
+                              [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk) -> int {
+                                const innr_cuda_corpus* c = shards[i];
+                                if (c->n == 0) {
+                                  CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), ctx->stream));
+                                  return INNR_OK;
+                                }
+                                return hamming_keys(c, ctx, (const uint64_t*)dq, n_queries, k, dk, ctx->stream);
+                              },
+                              out_idx, nullptr, out_dist);
+    if (rc == INNR_OK) {
+      if (out_count) *out_count = kk;
+      return INNR_OK;
+    }
+    if (rc != INNR_EUNSUPPORTED) return rc;
+  }
   std::vector<ShardOut> outs(n_shards);
-  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+  rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
     o.idx.assign(n_queries * k, 0);
     o.dist.assign(n_queries * k, 0);
     return innr_cuda_hamming_topk(shards[i], query_words, n_queries, query_dim_bits, k, o.idx.data(), o.dist.data(), &o.count);
   }, outs);
   if (rc) return rc;
-  const size_t kk = k < n_total ? k : n_total;
   std::vector<uint64_t> all;
   for (size_t q = 0; q < n_queries; ++q) {
     all.clear();
@@ -2340,14 +2564,34 @@ int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t
   }
   if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;
   if (!out_idx || !out_score) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = k < n_total ? k : n_total;
+  int rc = INNR_OK;
+  bool same_dim = true;
+  for (size_t i = 0; i < n_shards; ++i) same_dim = same_dim && shards[i]->d == query_len && shards[i]->d > 0;
+  if (ShardGroup* g = same_dim ? shard_group_for(shards, n_shards) : nullptr) {
+    rc = sharded_via_exchange(g, shards, n_shards, queries, n_queries * query_len * sizeof(float), n_queries, k, INNR_METRIC_DOT, false,
+                              [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk) -> int {
+                                const innr_cuda_corpus* c = shards[i];
+                                if (c->n == 0) {
+                                  CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), ctx->stream));
+                                  return INNR_OK;
+                                }
+                                return u8_keys(c, ctx, (const float*)dq, n_queries, k, dk, ctx->stream);
+                              },
+                              out_idx, out_score, nullptr);
+    if (rc == INNR_OK) {
+      if (out_count) *out_count = kk;
+      return INNR_OK;
+    }
+    if (rc != INNR_EUNSUPPORTED) return rc;
+  }
   std::vector<ShardOut> outs(n_shards);
-  int rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
+  rc = run_shards(n_shards, [&](size_t i, ShardOut& o) {
     o.idx.assign(n_queries * k, 0);
     o.score.assign(n_queries * k, 0.0f);
     return innr_cuda_batch_knn_u8(shards[i], queries, n_queries, query_len, k, o.idx.data(), o.score.data(), &o.count);
   }, outs);
   if (rc) return rc;
-  const size_t kk = k < n_total ? k : n_total;
   std::vector<std::pair<uint64_t, float>> all;
   for (size_t q = 0; q < n_queries; ++q) {
     all.clear();

@@ -67,3 +67,49 @@ def test_exchange_between_devices_of_one_process(oracle):
                 w = oracle.batch_knn_cosine(qs[j], ob, k)
                 assert idx[j].tolist() == w.indices and sc[j].tobytes() == w.scores.tobytes(), (rep, r, j)
     ib.init(0)
+
+
+@needs2
+def test_c_abi_sharded_entries_over_devices(oracle):
+    """innr_cuda_*_sharded with one shard per DEVICE: persistent worker threads enqueue the shard scans, the lists meet in
+    the root device's mailbox (peer-mapped, csrc/exchange.cu) and are merged in the same launch. Results equal the
+    unsharded oracle answer, repeatedly (both mailbox parities), also with an empty shard and with requests that do
+    not fit the mailbox route (k > 128 -> host merge)."""
+    import torch
+    import innr_b200 as ib
+    from innr_b200 import sharded
+    n_dev = min(torch.cuda.device_count(), 4)
+    n, d, nq = 30_001, 40, 5
+    rng = np.random.default_rng(14)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)   # heavy ties across shard boundaries
+    ob = oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    cuts = [n * r // n_dev for r in range(n_dev + 1)]
+    if n_dev >= 3:
+        cuts[1] = cuts[2]          # an empty shard on device 1... (rows move to device 0)
+    shards, bsh, ush = [], [], []
+    codes = rng.integers(0, 2**62, size=(n, 3), dtype=np.uint64)
+    mat = rng.integers(0, 256, size=(n, 48), dtype=np.uint8)
+    gp, op = ib.QuantizationParams.from_range(-1.0, 1.0), oracle.QuantizationParams.from_range(-1.0, 1.0)
+    for dev, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        ib.init(dev)
+        shards.append(ib.DeviceBatch.from_rows_flat(rows[a:b].reshape(-1), b - a, d, index_base=a))
+        bsh.append(ib.BinaryCorpus.from_words(codes[a:b], b - a, 192, index_base=a))
+        ush.append(ib.U8Corpus.from_rows(mat[a:b], gp, index_base=a, dimension=48))
+    ib.init(0)
+    for rep in range(3):
+        qs = rng.integers(-3, 4, size=(nq, d)).astype(np.float32)
+        for metric in ("dot", "cosine", "l2"):
+            for k in (1, 10, 100, 300):
+                idx, sc = sharded.batch_knn_sharded(metric, qs, shards, k)
+                widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=4)
+                assert sc.tobytes() == wsc.tobytes(), (rep, metric, k)
+                if metric != "l2":
+                    assert np.array_equal(idx, widx), (rep, metric, k)
+        qc = rng.integers(0, 2**62, size=(2, 3), dtype=np.uint64)
+        gi, gd = sharded.hamming_topk_sharded(qc, bsh, 100)
+        wi, wd = oracle.hamming_topk_many(qc, codes, 100, n_threads=2)
+        assert np.array_equal(gi, wi) and np.array_equal(gd, wd), rep
+        q8 = rng.uniform(-1, 1, size=(3, 48)).astype(np.float32)
+        ui, us = sharded.batch_knn_u8_sharded(q8, ush, 10)
+        wi, ws = oracle.batch_knn_u8_many(q8, mat, op, 10, n_threads=2)
+        assert np.array_equal(ui, wi) and us.tobytes() == ws.tobytes(), rep
