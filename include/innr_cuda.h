@@ -70,6 +70,13 @@ int innr_cuda_set_option(const char* name, double value);
  * NULL. bench.py's tensor roofline reads this. */
 int innr_cuda_knn_tc_last_stats(float* out_filter_ms, float* out_total_ms, double* out_filter_flops,
                                 uint64_t* out_candidates, uint32_t* out_exact_scan_queries, int* out_passes);
+/* Test hook for the filter's error bound: runs the operands + the dense first pass of the filter and returns, for every
+ * query and every row < min(n, 4096), the pair's LOWER bound exactly as production computes it (row-major n_queries x
+ * *out_rows), eps, and per query 1 when the filter does not answer it (zero / non-finite norm). The tests assert
+ * lower <= reference score (in the filter's units) <= lower + 2 * eps * r on adversarial inputs. Needs >= 4096 rows. */
+int innr_cuda_knn_tc_debug_bounds(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                                  size_t query_len, float* out_lower, size_t* out_rows, float* out_eps,
+                                  uint32_t* out_qflags);
 /* number of kernels the library has launched so far (bench.py's gpu_launches counter) */
 int innr_cuda_launch_count(uint64_t* out_count);
 

@@ -280,6 +280,23 @@ def batch_knn_many(metric: str, queries, batch, k: int):
     return idx[:, :cnt.value], sc[:, :cnt.value]
 
 
+def knn_tc_debug_bounds(metric: str, queries, batch):
+    """Test hook (include/innr_cuda.h: innr_cuda_knn_tc_debug_bounds): the tensor-core filter's LOWER bound for every
+    (query, row < min(N, 4096)) pair exactly as production computes it. Returns (lower[nq, rows], eps, qflags[nq])."""
+    dev = _dev(batch)
+    qs = _f32(queries)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq, qlen = qs.shape
+    lower = np.zeros((nq, 4096), np.float32)
+    rows, eps = C.c_size_t(0), C.c_float(0)
+    flags = np.zeros(nq, np.uint32)
+    m = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
+    L.call("innr_cuda_knn_tc_debug_bounds", dev.h, m, _ptr(qs, L.f32p), nq, qlen, _ptr(lower, L.f32p), C.byref(rows),
+           C.byref(eps), _ptr(flags, L.u32p))
+    return lower.reshape(-1)[:nq * rows.value].reshape(nq, rows.value), float(eps.value), flags
+
+
 def _knn(metric: str, query, batch, k: int) -> BatchKnnResult:
     q = _f32(query).reshape(1, -1)
     idx, sc = batch_knn_many(metric, q, batch, k)

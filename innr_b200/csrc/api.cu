@@ -717,6 +717,38 @@ static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const flo
   return INNR_OK;
 }
 
+static int metric_to_mode(int metric, int* mode);
+
+// Test hook for the tensor-core filter's error bound (tests/test_gpu_parity.py::test_knn_tc_bound_*): the lower bounds of
+// the dense first pass for rows < min(n, 4096), row-major n_queries x *out_rows, plus eps and the per-query flag
+// (1 = the filter does not answer this query: zero / non-finite norm). The corpus needs >= 4096 rows; returns
+// INNR_EUNSUPPORTED when the corpus cannot take the filter path (non-finite norms, no memory).
+extern "C" int innr_cuda_knn_tc_debug_bounds(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                                             size_t query_len, float* out_lower, size_t* out_rows, float* out_eps,
+                                             uint32_t* out_qflags) {
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");
+  if (!queries || !out_lower || !out_rows || !out_eps || !out_qflags || n_queries == 0) return fail(INNR_EINVAL, "null argument");
+  PdxView v = pdx_view(c);
+  if (!knn_tc_supported(v, mode, n_queries, 10)) return fail(INNR_EUNSUPPORTED, "corpus too small for the filter path");
+  EntryGuard lk(c->device);
+  DeviceCtx* ctx;
+  rc = ctx_for(c, &ctx);
+  if (rc) return rc;
+  rc = knn_tc_prepare(const_cast<innr_cuda_corpus*>(c), ctx, v, ctx->stream);
+  if (rc) return rc;
+  if (c->tc_state != 1) return fail(INNR_EUNSUPPORTED, "corpus cannot take the filter path (non-finite norms or no memory)");
+  CU(ctx->d_query.reserve((n_queries * c->d + 4) * sizeof(float)));
+  CU(ctx->d_tcws.reserve(knn_tc_workspace_bytes(c->n, c->d, n_queries, 10)));
+  CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_knn_tc_debug_bounds(v, c->tm_xh, c->dev_norms, mode, (const float*)ctx->d_query.p, n_queries, ctx->d_tcws.p, out_lower,
+                                out_rows, out_eps, out_qflags, ctx->ws.num_sms, ctx->stream, &g_launches));
+  return INNR_OK;
+}
+
 static int metric_to_mode(int metric, int* mode) {
   switch (metric) {
     case INNR_METRIC_DOT: *mode = PDX_DOT; return INNR_OK;

@@ -135,6 +135,12 @@ struct KnnTcStats {
 };
 bool knn_tc_supported(const PdxView& v, int mode, size_t nq, size_t k);
 size_t knn_tc_dpad(size_t d);  // row pitch (elements) of the f16 operand copy
+float knn_tc_eps(size_t d);    // the filter's bound on |S - cosine|
+// test hook: lower bounds of the dense first pass (rows < min(n, 4096)) for every query; see knn_tc.cu
+cudaError_t launch_knn_tc_debug_bounds(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
+                                       const float* dev_queries, size_t nq, void* workspace, float* host_lower,
+                                       size_t* out_rows, float* out_eps, unsigned* host_qflags, int num_sms, cudaStream_t s,
+                                       LaunchCounter* launches);
 size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k);
 // once per corpus: dev_xh (n x knn_tc_dpad(d) f16) = unit vectors, from the PDX corpus and its exact norms
 cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* dev_xh, unsigned* dev_scratch_u32,

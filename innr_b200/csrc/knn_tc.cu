@@ -585,6 +585,9 @@ KnnTcPlan make_plan(size_t d, size_t nq) {
 }  // namespace
 
 size_t knn_tc_dpad(size_t d) { return (d + 7) / 8 * 8; }
+// |S - cos| <= eps (header of this file): f16 rounding of both unit vectors, f32 accumulation in the tensor core, and the
+// distance of the reference's own sequential f32 score from the real-valued one
+float knn_tc_eps(size_t d) { return 1.05e-3f + 3.5e-7f * (float)d; }
 
 size_t knn_tc_workspace_bytes(size_t n, size_t d, size_t nq, size_t k) {
   (void)n;
@@ -614,6 +617,65 @@ cudaError_t launch_knn_tc_build(const PdxView& v, const float* dev_norms, void* 
   e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) return e;
   if (!make_tmap_f16_rows(tm_xh, dev_xh, v.n, d_pad, d_pad, VT)) return cudaErrorInvalidValue;
+  return cudaSuccess;
+}
+
+// Test hook (innr_cuda_knn_tc_debug_bounds): the operands and the DENSE first pass of the filter only -- for every query
+// q and every row v < min(n, CAND_CAP) the pair's lower bound lands in cand_lb[q * CAND_CAP + v] exactly as the
+// production passes compute it. Copies them to host_lower (nq x rows) and reports eps; synchronises the stream.
+cudaError_t launch_knn_tc_debug_bounds(const PdxView& v, const CUtensorMap& tm_xh, const float* dev_norms, int mode,
+                                       const float* dev_queries, size_t nq, void* workspace, float* host_lower,
+                                       size_t* out_rows, float* out_eps, unsigned* host_qflags, int num_sms, cudaStream_t s,
+                                       LaunchCounter* launches) {
+  const int cosine = mode == PDX_COSINE_FUSED, l2 = mode == PDX_L2;
+  const KnnTcPlan p = make_plan(v.d, nq);
+  uint8_t* w = (uint8_t*)workspace;
+  __half* qh = (__half*)(w + p.off_qh);
+  unsigned* qflag = (unsigned*)(w + p.off_qflag);
+  float* thr = (float*)(w + p.off_thr);
+  unsigned* cnt = (unsigned*)(w + p.off_cnt);
+  float* qaux = (float*)(w + p.off_qaux);
+  const unsigned rows = (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n);
+  knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, l2, qh,
+                                                      qflag, thr, cnt, qaux, rows);
+  ++*launches;
+  const bool qres = p.nq_pad <= QR_ROWS && (p.d_pad + KB - 1) / KB <= QR_MAX_KBLOCKS;
+  CUtensorMap tm_q;
+  if (!make_tmap_f16_rows(&tm_q, qh, p.nq_pad, p.d_pad, p.d_pad, qres ? QR_ROWS : QT)) return cudaErrorInvalidValue;
+  const size_t smem_stream = (size_t)KSTAGES * KSTAGE_BYTES + sizeof(KtShared);
+  const size_t smem_qres = (size_t)QR_STAGES * X_BYTES + (size_t)QR_MAX_KBLOCKS * QR_BOX_BYTES + sizeof(KtShared);
+  cudaError_t e = cudaFuncSetAttribute(knn_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(knn_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_qres);
+  if (e != cudaSuccess) return e;
+  KtArgs a{};
+  a.n_qgroups = (p.nq_pad + QT - 1) / QT;
+  a.kblocks = (p.d_pad + KB - 1) / KB;
+  a.nq_pad = p.nq_pad;
+  a.cosine = cosine;
+  a.l2 = l2;
+  a.qaux = qaux;
+  a.eps = knn_tc_eps(v.d);
+  a.norms = dev_norms;
+  a.thr = thr;
+  a.cand_count = cnt;
+  a.cand_idx = (unsigned*)(w + p.off_idx);
+  a.cand_lb = (float*)(w + p.off_lb);
+  a.n_rows = rows;
+  a.dense = 1;
+  const unsigned long long units = (unsigned long long)((rows + VT - 1) / VT) * a.n_qgroups;
+  unsigned grid = (unsigned)num_sms;
+  if (grid > units) grid = (unsigned)units;
+  if (qres) knn_tc_filter_kernel<true><<<grid, KT_THREADS, smem_qres, s>>>(tm_xh, tm_q, a);
+  else knn_tc_filter_kernel<false><<<grid, KT_THREADS, smem_stream, s>>>(tm_xh, tm_q, a);
+  ++*launches;
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = cudaMemcpy2DAsync(host_lower, rows * sizeof(float), a.cand_lb, CAND_CAP * sizeof(float), rows * sizeof(float), nq,
+                             cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(host_qflags, qflag, nq * sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+  *out_rows = rows;
+  *out_eps = a.eps;
   return cudaSuccess;
 }
 
@@ -691,7 +753,7 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   a.cosine = cosine;
   a.l2 = l2;
   a.qaux = qaux;
-  a.eps = 1.05e-3f + 3.5e-7f * (float)v.d;
+  a.eps = knn_tc_eps(v.d);
   a.norms = dev_norms;
   a.thr = thr;
   a.cand_count = cnt;

@@ -1263,6 +1263,145 @@ def test_knn_tc_filter_path_is_exact(tc_small, oracle, n, d, nq):
             assert_knn_equal(got_r, want_r, ties_as_sets=True)
 
 
+def _half_ulp_unit_vector(d, rng, eta):
+    """A UNIT vector of dimension d whose every component sits `eta` (in units of its binade, |eta| a hair off 2^-11 = half
+    an f16 ulp) away from an f16-representable value, all on the same side: t_k = 2^-j (m_k + eta) with m_k = 1 + i_k 2^-10,
+    i_k small -- mantissas near 1.0, where a half-ulp is the largest RELATIVE error f16 rounding can make. The i_k are
+    chosen so that sum t_k^2 = 1 to ~1e-6, which keeps x / ||x|| (computed in f32 on the device) on the intended side of
+    the rounding boundary. Returns the vector in float64 (random signs are the caller's business)."""
+    J = int(np.ceil(np.log(d) / np.log(4.0))) + 1
+    i0 = 0 if eta > 0 else 1                      # eta < 0: stay clear of the binade's lower edge (the ulp halves below it)
+    unit = (1.0 + i0 * 2.0 ** -10 + eta) ** 2
+    # every component starts at level J (one unit of 4^-J each); promoting a component 1 / 2 / 3 levels up adds 3 / 15 /
+    # 63 units. Greedy change-making brings the squared norm to just below 1; >= 200 components stay at level J and
+    # absorb the remainder (< 3 units) with a few mantissa steps each.
+    extra = 4.0 ** J / unit - d
+    lev = np.full(d, J)
+    k = 0
+    for up, gain in ((3, 63), (2, 15), (1, 3)):
+        cnt = int(min(d - 200 - k, extra // gain))
+        lev[k:k + cnt] = J - up
+        k += cnt
+        extra -= cnt * gain
+    assert 0.0 <= extra < 3.0, (d, extra)
+    a = k
+    steps = np.full(d, i0, np.int64)
+
+    def total():
+        return float(np.sum(4.0 ** -lev * (1.0 + steps * 2.0 ** -10 + eta) ** 2))
+    k = a  # bump the mantissas of the small components round-robin until the squared norm reaches 1
+    while total() < 1.0:
+        steps[k] += 1
+        k = k + 1 if k + 1 < d else a
+    assert steps.max() <= 12 and abs(total() - 1.0) < 8e-3 / d, (steps.max(), total())
+    t = 2.0 ** -lev * (1.0 + steps * 2.0 ** -10 + eta)
+    return t[rng.permutation(d)]
+
+
+@pytest.mark.parametrize("d", [768, 4096, 12288])
+def test_knn_tc_bound_holds_on_adversarial_inputs(ib, oracle, d):
+    """The f16 tensor-core filter may only prune what its bound allows: for every (query, row) pair the reference's score
+    must lie inside [lower, lower + 2 e] as the filter computes it (csrc/knn_tc.cu; eps = 1.05e-3 + 3.5e-7 d). Driven
+    with inputs built to maximise the f16 rounding error -- every normalised component a hair off a half-ulp boundary
+    with aligned signs, parallel and antiparallel to the query (where Cauchy-Schwarz is tight) -- plus f16-subnormal
+    components, norms from 1e-30 to 1e30 and random rows, for all three metrics. Reports the worst |S r - ref| / e."""
+    rng = np.random.default_rng(d)
+    n = 4096
+    rows = np.zeros((n, d), np.float64)
+    half_ulp = 2.0 ** -11
+    etas = [half_ulp - 2.0 ** -15, half_ulp + 2.0 ** -15, -(half_ulp - 2.0 ** -15), 3 * half_ulp - 2.0 ** -15]
+    qvecs = []
+    for e_i, eta in enumerate(etas):
+        x = _half_ulp_unit_vector(d, rng, eta)
+        qvecs.append(x.copy())
+        base = e_i * 64
+        for r in range(64):
+            y = x.copy()
+            if r % 4 == 1:
+                y = -y                                     # antiparallel: cos = -1
+            if r % 4 == 2:
+                sgn = rng.choice([-1.0, 1.0], size=d)      # same magnitudes, random signs: the errors partly cancel
+                y = y * sgn
+            if r % 4 == 3:
+                y[rng.permutation(d)[: d // 2]] *= 2.0 ** -9   # half of the components become f16-subnormal after normalisation
+            rows[base + r] = y * 10.0 ** rng.uniform(-3, 3)
+    # norms spanning 1e-30 .. 1e30, heavy-tailed components, and plain Gaussian rows
+    k0 = 64 * len(etas)
+    rows[k0:k0 + 512] = rng.standard_normal((512, d)) * (10.0 ** rng.uniform(-30, 30, size=(512, 1)) / np.sqrt(d))
+    rows[k0 + 512:k0 + 1024] = rng.standard_normal((512, d)) * np.exp(rng.standard_normal((512, d)) * 4.0)
+    rows[k0 + 1024:] = rng.standard_normal((n - k0 - 1024, d))
+    rows[k0 + 1030] = 0.0
+    rows32 = rows.astype(np.float32)
+    qs = np.stack(qvecs + [-qvecs[0], rows[k0 + 1500], rows[k0 + 1501] * 1e20, rows[k0 + 700] * 1e-3]).astype(np.float32)
+    nq = qs.shape[0]
+    gb = ib.VerticalBatch.from_flat(rows32.reshape(-1), n, d)
+    ob = oracle.VerticalBatch.from_flat(rows32.reshape(-1), n, d)
+    norms = oracle.batch_norms(ob)
+    assert np.isfinite(norms).all()
+    f32 = np.float32
+    worst = {}
+    for metric in ("cosine", "dot", "l2"):
+        lower, eps, flags = ib.knn_tc_debug_bounds(metric, qs, gb)
+        assert lower.shape == (nq, n) and abs(eps - (1.05e-3 + 3.5e-7 * d)) < 1e-9 and not flags.any()
+        for j in range(nq):
+            q = qs[j]
+            qn = f32(np.sqrt(f32(oracle.batch_dot(q, oracle.VerticalBatch.from_flat(q, 1, d))[0])))
+            if metric == "cosine":
+                ref = oracle.batch_cosine(q, ob, norms).astype(np.float64)
+                e = np.where(norms > 1e-9, eps, 0.0)
+                lo, hi = lower[j].astype(np.float64), lower[j].astype(np.float64) + 2 * e
+            elif metric == "dot":
+                ref = oracle.batch_dot(q, ob).astype(np.float64) / float(qn)        # the filter's units: score / ||q||
+                r = np.where(norms >= 1e-30, norms, 0.0).astype(np.float64)
+                e = eps * r + 1e-18
+                lo, hi = lower[j].astype(np.float64), lower[j].astype(np.float64) + 2 * e
+            else:
+                dist = oracle.batch_l2_squared(q, ob).astype(np.float64)
+                ref = (float(qn) ** 2 - dist) / (2 * float(qn))                       # u = (||q||^2 - d) / (2 ||q||)
+                r = np.where(norms >= 1e-30, norms, 0.0).astype(np.float64)
+                e = eps * r + 1e-18
+                delta = (4.0 * d + 32.0) * 2.0 ** -24
+                cq = 2.0 * (d + 2.0) * 2.0 ** -24 * float(qn)
+                xx = norms.astype(np.float64) ** 2
+                h = 0.5 / float(qn)
+                lo = lower[j].astype(np.float64)
+                hi = lo + 2 * e + xx * h * 2 * delta + 2 * cq                         # upper(j) + cq in the kernel's terms
+            slack = 1e-6 * (np.abs(lo) + np.abs(hi)) + 1e-30                          # f32 rounding of the bounds themselves
+            bad = (ref < lo - slack) | (ref > hi + slack)
+            assert not bad.any(), (metric, j, int(np.argmax(bad)), ref[bad][:3], lo[bad][:3], hi[bad][:3])
+            mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+            ratio = np.where(half > 0, np.abs(ref - mid) / np.maximum(half, 1e-300), 0.0)
+            worst[metric] = max(worst.get(metric, 0.0), float(ratio.max()))
+            if metric == "cosine":
+                worst["cosine_abs"] = max(worst.get("cosine_abs", 0.0), float(np.abs(ref - mid).max()))
+    print(f"d={d}: eps = {eps:.3e}; worst |S r - ref| / e = {worst}")
+    # the construction really is adversarial: the half-ulp rows reach (almost) the whole f16 budget of 2^-10 = 9.77e-4
+    assert worst["cosine_abs"] > 8.5e-4, worst
+    assert max(worst["cosine"], worst["dot"], worst["l2"]) <= 1.0
+
+
+def test_knn_tc_candidate_overflow_falls_back_to_the_exact_scan(tc_small, oracle):
+    """300 000 rows that all lie inside the filter's error band of the best score (a cloud of near-duplicates around the
+    query direction) at k = 128: every row is a candidate, the per-query list (4096 slots) overflows, and the query must
+    be answered by the exact scan -- still bit for bit."""
+    ib = tc_small
+    n, d, k = 300_000, 64, 128
+    rng = np.random.default_rng(77)
+    u = rng.standard_normal(d)
+    u /= np.linalg.norm(u)
+    rows = (u[None, :] + 2e-4 * rng.standard_normal((n, d))).astype(np.float32)   # cos(u, row) = 1 - O(1e-6): all within eps
+    qs = np.stack([u, 3.0 * u, u + 1e-3 * rng.standard_normal(d)]).astype(np.float32)
+    gb, ob = ib.VerticalBatch.from_flat(rows.reshape(-1), n, d), oracle.VerticalBatch.from_flat(rows.reshape(-1), n, d)
+    for metric in ("cosine", "dot", "l2"):
+        idx, sc = ib.batch_knn_many(metric, qs, gb, k)
+        st = ib.knn_tc_last_stats()
+        assert st["passes"] >= 2 and st["exact_scan_queries"] == qs.shape[0], (metric, st)   # every list overflowed
+        widx, wsc = oracle.batch_knn_many(metric, qs, ob, k, n_threads=8)
+        assert np.array_equal(bits(sc), bits(wsc)), metric
+        if metric != "l2":
+            assert np.array_equal(idx, widx), metric
+
+
 def test_knn_tc_on_the_reference_lattice(tc_small, oracle):
     """The G-ref lattice has near-ties below f32 resolution: the adversarial case for a low-precision
     filter (many pairs inside the error band -> long candidate lists or the exact-scan fallback; never a wrong answer)."""
