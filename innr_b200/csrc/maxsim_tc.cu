@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&st->full[s], 1);
-      mbar_init(&st->empty[s], 129);  // hi MMAs done reading (1 commit) + 128 converter threads done reading
+      mbar_init(&st->empty[s], 5);  // hi MMAs done reading (1 commit) + 4 converter warps done reading (one elected
+                                    // arrive per warp: 128 per-thread arrives on one mbarrier serialise in the LSU and
+                                    // showed up as a quarter of the kernel's shared-memory wavefronts)
     }
     for (int t = 0; t < ACC; ++t) {
       mbar_init(&st->tmem_full[t], 1);
       mbar_init(&st->tmem_empty[t], 4);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&st->lo_ready[b], 128);
+      mbar_init(&st->lo_ready[b], 4);  // one elected arrive per converter warp
       mbar_init(&st->lo_free[b], 1);
     }
     fence_barrier_init();
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (unsigned i = 0; i < n_tiles; ++i) {
         mbar_wait(&st->full[i % STAGES], (i / STAGES) & 1);
         if (lane == 0)
-          for (int r = 0; r < 129; ++r) mbar_arrive(&st->empty[i % STAGES]);
+          for (int r = 0; r < 5; ++r) mbar_arrive(&st->empty[i % STAGES]);
         __syncwarp();
       }
     }
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           tc_fence_after_sync();
           if (elect_one_sync()) {
             issue_hi(s, t);
-            umma_commit(&st->empty[s]);  // 1 of 129: the tensor core has finished reading the stage
+            umma_commit(&st->empty[s]);  // 1 of 5: the tensor core has finished reading the stage
           }
           __syncwarp();
           ++nh;
@@ -355,7 +357,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
       const int s = i % STAGES, b = i & 1;
       mbar_wait_sleepy(&st->full[s], (i / STAGES) & 1);
-      if (a.debug_mode == 2) { mbar_arrive(&st->empty[s]); continue; }
+      if (a.debug_mode == 2) {
+        if (lane == 0) mbar_arrive(&st->empty[s]);
+        continue;
+      }
       mbar_wait_sleepy(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
       tc_fence_after_sync();
       const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
@@ -366,7 +371,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
         ulonglong2 v[8];  // two packed f32 pairs per 16-byte chunk: the pairs stay in 64-bit registers end to end
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const ulonglong2*>(pbase + ((c ^ (row & 7)) << 4));
-        if (p == P - 1) mbar_arrive(&st->empty[s]);  // this thread has read its whole row: 1 of 129
+        if (p == P - 1) {  // every lane of this warp has read its whole row: 1 of 5
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st->empty[s]);
+        }
         uint32_t lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -381,7 +389,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      mbar_arrive(&st->lo_ready[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&st->lo_ready[b]);
     }
   } else {
     // =========================== epilogue (warp w = TMEM lane quadrant w = stream w) ===========================

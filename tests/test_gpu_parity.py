@@ -1304,7 +1304,7 @@ def test_knn_tc_bound_holds_on_adversarial_inputs(ib, oracle, d):
     must lie inside [lower, lower + 2 e] as the filter computes it (csrc/knn_tc.cu; eps = 1.05e-3 + 3.5e-7 d). Driven
     with inputs built to maximise the f16 rounding error -- every normalised component a hair off a half-ulp boundary
     with aligned signs, parallel and antiparallel to the query (where Cauchy-Schwarz is tight) -- plus f16-subnormal
-    components, norms from 1e-30 to 1e30 and random rows, for all three metrics. Reports the worst |S r - ref| / e."""
+    components, norms from 1e-30 to 1e18 and random rows, for all three metrics. Reports the worst |S r - ref| / e."""
     rng = np.random.default_rng(d)
     n = 4096
     rows = np.zeros((n, d), np.float64)
@@ -1327,12 +1327,14 @@ def test_knn_tc_bound_holds_on_adversarial_inputs(ib, oracle, d):
             rows[base + r] = y * 10.0 ** rng.uniform(-3, 3)
     # norms spanning 1e-30 .. 1e30, heavy-tailed components, and plain Gaussian rows
     k0 = 64 * len(etas)
-    rows[k0:k0 + 512] = rng.standard_normal((512, d)) * (10.0 ** rng.uniform(-30, 30, size=(512, 1)) / np.sqrt(d))
+    # (1e18 is as far up as f32 goes here: the squared norm must stay finite, or the reference's own score is NaN and
+    # the corpus never takes the filter path)
+    rows[k0:k0 + 512] = rng.standard_normal((512, d)) * (10.0 ** rng.uniform(-30, 18, size=(512, 1)) / np.sqrt(d))
     rows[k0 + 512:k0 + 1024] = rng.standard_normal((512, d)) * np.exp(rng.standard_normal((512, d)) * 4.0)
     rows[k0 + 1024:] = rng.standard_normal((n - k0 - 1024, d))
     rows[k0 + 1030] = 0.0
     rows32 = rows.astype(np.float32)
-    qs = np.stack(qvecs + [-qvecs[0], rows[k0 + 1500], rows[k0 + 1501] * 1e20, rows[k0 + 700] * 1e-3]).astype(np.float32)
+    qs = np.stack(qvecs + [-qvecs[0], rows[k0 + 1500], rows[k0 + 1501] * 1e15, rows[k0 + 700] * 1e-3]).astype(np.float32)
     nq = qs.shape[0]
     gb = ib.VerticalBatch.from_flat(rows32.reshape(-1), n, d)
     ob = oracle.VerticalBatch.from_flat(rows32.reshape(-1), n, d)
