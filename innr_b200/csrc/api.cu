@@ -1407,12 +1407,19 @@ int innr_cuda_binary_topk(const innr_cuda_corpus* c, int op, const uint64_t* que
   CU(ctx->d_scores.reserve(c->n * sizeof(uint32_t)));
   CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
   Timed tm(*ctx);
-  if (op)
-    CU(launch_binary_jaccard_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (float*)ctx->d_scores.p, ctx->stream, &g_launches));
-  else
-    CU(launch_binary_dot_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (uint32_t*)ctx->d_scores.p, ctx->stream, &g_launches));
-  CU(launch_topk_from_scores(ctx->d_scores.p, op ? 1 : 4, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
-                             ctx->stream, &g_launches));
+  const size_t fused_smem = c->chunks * sizeof(uint4) + 8 * kk * sizeof(uint64_t);
+  if (kk <= MAX_FUSED_K && fused_smem <= 48 * 1024) {
+    // one pass: the selection rides on the scan (same keys as the two-step route below), nothing of size n is written
+    CU(launch_binary_setops_topk(bin_view(c), op, (const uint64_t*)ctx->d_query.p, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                                 ctx->stream, &g_launches));
+  } else {
+    if (op)
+      CU(launch_binary_jaccard_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (float*)ctx->d_scores.p, ctx->stream, &g_launches));
+    else
+      CU(launch_binary_dot_all(bin_view(c), (const uint64_t*)ctx->d_query.p, (uint32_t*)ctx->d_scores.p, ctx->stream, &g_launches));
+    CU(launch_topk_from_scores(ctx->d_scores.p, op ? 1 : 4, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p, ctx->ws,
+                               ctx->stream, &g_launches));
+  }
   tm.stop();
   rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) {
     if (op) {
@@ -1822,7 +1829,7 @@ int innr_cuda_encode_ternary(const float* values, size_t n, float threshold, uin
 // op 0: ternary_dot (query = packed words), 1: ternary_hamming (packed words), 2: ternary::asymmetric_dot (f32 query).
 // Stages the query, runs the scan into d_scores (f32) and optionally d_aux (i32).
 static int ternary_scores_dev(const innr_cuda_corpus* c, DeviceCtx* ctx, int op, const void* query, size_t query_dim,
-                              bool want_i32) {
+                              bool want_i32, bool stage_only = false) {
   if (op < 0 || op > 2) return fail(INNR_EINVAL, "unknown ternary op");
   if (query_dim != c->d)  // src/ternary.rs:192-196 / :287 assert_eq!
     return fail(INNR_EINVAL, op == 0 ? "innr::ternary_dot: dimension mismatch" : "dimension mismatch");
@@ -1841,6 +1848,7 @@ static int ternary_scores_dev(const innr_cuda_corpus* c, DeviceCtx* ctx, int op,
     CU(cudaMemcpyAsync(ctx->d_query.p, w.data(), c->words * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));  // w is a stack-owned staging copy
   }
+  if (stage_only) return INNR_OK;
   CU(launch_ternary_scores(ter_view(c), op, (const uint64_t*)ctx->d_query.p, (const float*)ctx->d_query.p,
                            (float*)ctx->d_scores.p, want_i32 ? (int32_t*)ctx->d_aux.p : nullptr, ctx->stream, &g_launches));
   return INNR_OK;
@@ -1890,10 +1898,19 @@ int innr_cuda_ternary_topk(const innr_cuda_corpus* c, int op, const void* query,
   if (rc) return rc;
   CU(ctx->d_keys.reserve(kk * sizeof(uint64_t)));
   Timed tm(*ctx);
-  rc = ternary_scores_dev(c, ctx, op, query, query_dim, false);
-  if (rc) return rc;
-  CU(launch_topk_from_scores(ctx->d_scores.p, op == 1 ? 0 : 1, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p,
-                             ctx->ws, ctx->stream, &g_launches));
+  const size_t q_bytes = op == 2 ? c->chunks * 64 * sizeof(float) : c->chunks * sizeof(uint4);
+  if (kk <= MAX_FUSED_K && q_bytes + 8 * kk * sizeof(uint64_t) <= 200 * 1024) {
+    // one pass: query staged, scan with the selection fused in (same keys as the two-step route below)
+    rc = ternary_scores_dev(c, ctx, op, query, query_dim, false, true);
+    if (rc) return rc;
+    CU(launch_ternary_topk(ter_view(c), op, (const uint64_t*)ctx->d_query.p, (const float*)ctx->d_query.p, kk,
+                           (uint64_t*)ctx->d_keys.p, ctx->ws, ctx->stream, &g_launches));
+  } else {
+    rc = ternary_scores_dev(c, ctx, op, query, query_dim, false);
+    if (rc) return rc;
+    CU(launch_topk_from_scores(ctx->d_scores.p, op == 1 ? 0 : 1, c->n, (uint32_t)c->index_base, kk, (uint64_t*)ctx->d_keys.p,
+                               ctx->ws, ctx->stream, &g_launches));
+  }
   tm.stop();
   rc = fetch_keys(*ctx, 1, kk, tm, [&](const uint64_t* keys) { decode_keys_f32(keys, kk, op != 1, out_idx, out_score); });
   if (rc) return rc;

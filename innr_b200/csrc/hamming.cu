@@ -282,6 +282,64 @@ __global__ void encode_binary_kernel(const float* __restrict__ values, size_t n,
   }
 }
 
+// intersection (and, for JACCARD, union) popcounts of one code against the query
+template <bool JACCARD>
+__device__ __forceinline__ void setop_counts(const HamArgs& a, const uint4* __restrict__ p, const uint4* __restrict__ sq,
+                                             unsigned& inter, unsigned& uni) {
+  inter = 0;
+  uni = 0;
+  unsigned c = 0;
+  for (; c + 4 <= a.chunks; c += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ldg_stream_u4(p + (size_t)(c + u) * a.ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 q = sq[c + u];
+      inter += __popc(v[u].x & q.x) + __popc(v[u].y & q.y) + __popc(v[u].z & q.z) + __popc(v[u].w & q.w);
+      if (JACCARD) uni += __popc(v[u].x | q.x) + __popc(v[u].y | q.y) + __popc(v[u].z | q.z) + __popc(v[u].w | q.w);
+    }
+  }
+  for (; c < a.chunks; ++c) {
+    const uint4 v = ldg_stream_u4(p + (size_t)c * a.ld), q = sq[c];
+    inter += __popc(v.x & q.x) + __popc(v.y & q.y) + __popc(v.z & q.z) + __popc(v.w & q.w);
+    if (JACCARD) uni += __popc(v.x | q.x) + __popc(v.y | q.y) + __popc(v.z | q.z) + __popc(v.w | q.w);
+  }
+}
+
+// Top-k by binary_dot / binary_jaccard with the selection fused into the scan (one pass, nothing of size n written):
+// descending similarity, ties -> lower index. Keys as launch_topk_from_scores builds them from the score vectors:
+// dot (~count << 32) | index, Jaccard make_key_desc(intersection as f32 / union as f32, index).
+template <bool JACCARD, int R>
+__global__ void __launch_bounds__(HAM_THREADS) binary_setops_topk_kernel(const HamArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sq = reinterpret_cast<uint4*>(smem_raw);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(sq + a.chunks);
+  const int lane = threadIdx.x & 31;
+  for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
+    uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
+    sq[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+  }
+  __syncthreads();
+  WarpList<R> lists[1];
+  uint64_t thrs[1];
+  lists[0].init();
+  thrs[0] = KEY_SENTINEL;
+  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const unsigned i = tile * HAM_THREADS + threadIdx.x;
+    const bool valid = i < a.n;
+    uint64_t key = KEY_SENTINEL;
+    if (valid) {
+      unsigned inter, uni;
+      setop_counts<JACCARD>(a, a.data + i, sq, inter, uni);
+      if (JACCARD) key = make_key_desc(uni == 0 ? 1.0f : __fdiv_rn(__uint2float_rn(inter), __uint2float_rn(uni)), a.index_base + i);
+      else key = make_key_u32(~inter, a.index_base + i);
+    }
+    lists[0].offer(key, valid, thrs[0], a.k, lane);
+  }
+  block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
+}
+
 // binary_dot (src/binary.rs:178-185) and binary_jaccard (:198-213) of one query against every code: same scan shape,
 // AND / OR instead of XOR. JACCARD: intersection as f32 / union as f32, 1.0 when the union is empty.
 template <bool JACCARD>
@@ -412,6 +470,38 @@ cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_quer
   binary_setops_kernel<true><<<a.n_tiles, HAM_THREADS, v.chunks * sizeof(uint4), s>>>(a, dev_out);
   ++*launches;
   return cudaGetLastError();
+}
+
+namespace {
+template <bool JACCARD, int R>
+cudaError_t launch_setops_topk(const HamArgs& a, size_t smem, int num_sms, cudaStream_t s) {
+  auto kern = binary_setops_topk_kernel<JACCARD, R>;
+  int occ = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, HAM_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  kern<<<balanced_grid(a.n_tiles, (unsigned)occ * (unsigned)num_sms), HAM_THREADS, smem, s>>>(a);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// fused single-pass top-k (k <= 128) by binary_dot (jaccard = 0) or binary_jaccard (1)
+cudaError_t launch_binary_setops_topk(const BinView& v, int jaccard, const uint64_t* dev_query_words, size_t k, uint64_t* dev_keys,
+                                      Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
+  if (v.n == 0 || k == 0 || k > 128) return cudaErrorInvalidValue;
+  HamArgs a = make_args(v, dev_query_words);
+  a.k = (int)k;
+  a.partials = ws.partials;
+  a.group_partials = ws.group_partials;
+  a.tickets = ws.tickets;
+  a.out_keys = dev_keys;
+  const size_t smem = v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (k <= 32) e = jaccard ? launch_setops_topk<true, 1>(a, smem, ws.num_sms, s) : launch_setops_topk<false, 1>(a, smem, ws.num_sms, s);
+  else e = jaccard ? launch_setops_topk<true, 4>(a, smem, ws.num_sms, s) : launch_setops_topk<false, 4>(a, smem, ws.num_sms, s);
+  if (e == cudaSuccess) ++*launches;
+  return e;
 }
 
 namespace {

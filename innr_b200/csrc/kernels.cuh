@@ -175,6 +175,9 @@ cudaError_t launch_binary_dot_all(const BinView& v, const uint64_t* dev_query_wo
                                   cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_binary_jaccard_all(const BinView& v, const uint64_t* dev_query_words, float* dev_out,
                                       cudaStream_t s, LaunchCounter* launches);
+// fused single-pass top-k (k <= 128) by binary_dot (jaccard = 0) / binary_jaccard (1): descending, ties -> lower index
+cudaError_t launch_binary_setops_topk(const BinView& v, int jaccard, const uint64_t* dev_query_words, size_t k, uint64_t* dev_keys,
+                                      Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_words, size_t nq, size_t k,
                                 uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 cudaError_t launch_encode_binary(const float* dev_values, size_t n, float threshold, uint64_t* dev_words,
@@ -216,6 +219,9 @@ cudaError_t launch_u8_from_pdx(const float* dev_pdx, size_t ld_f, size_t n, size
 // mode 0: raw mixed dot, 1: asymmetric score
 cudaError_t launch_u8_scores(const U8View& v, int mode, const float* dev_query, float* dev_out,
                              cudaStream_t s, LaunchCounter* launches);
+// fused single-pass top-k (k <= 128) of the ternary scores (dot / asymmetric dot descending, Hamming ascending)
+cudaError_t launch_ternary_topk(const TerView& v, int op, const uint64_t* dev_query_words, const float* dev_query, size_t k,
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches);
 void u8_set_scaled_chains(bool on);  // off = always the de-biasing path (tests compare both)
 cudaError_t launch_u8_knn(const U8View& v, const float* dev_queries, size_t nq, size_t k, uint64_t* dev_keys,
                           Workspace& ws, cudaStream_t s, LaunchCounter* launches);

@@ -43,24 +43,10 @@ __device__ __forceinline__ unsigned ham32(unsigned wa, unsigned wb) {
   return __popc(df & nz_a & nz_b);
 }
 
-// OP 0: ternary_dot, 1: ternary_hamming, 2: asymmetric_dot
+// score of one code (its first chunk at p): f32 value (what the scores kernel writes), and for the integer ops the raw i32
 template <int OP>
-__global__ void __launch_bounds__(TER_THREADS) ternary_scores_kernel(const TerArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint4* sqw = reinterpret_cast<uint4*>(smem_raw);
-  float* sqf = reinterpret_cast<float*>(smem_raw);
-  if (OP == 2) {
-    for (unsigned k = threadIdx.x; k < a.chunks * 64; k += blockDim.x) sqf[k] = k < a.dim ? a.query[k] : 0.0f;
-  } else {
-    for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
-      const uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
-      sqw[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
-    }
-  }
-  __syncthreads();
-  const unsigned i = blockIdx.x * TER_THREADS + threadIdx.x;
-  if (i >= a.n) return;
-  const uint4* p = a.data + i;
+__device__ __forceinline__ float ternary_score(const TerArgs& a, const uint4* __restrict__ p, const uint4* __restrict__ sqw,
+                                               const float* __restrict__ sqf, int32_t& si) {
   if (OP == 2) {
     float sum = 0.0f;
     unsigned k = 0;
@@ -79,24 +65,85 @@ __global__ void __launch_bounds__(TER_THREADS) ternary_scores_kernel(const TerAr
         }
       }
     }
-    a.out_f32[i] = sum;
-  } else {
-    unsigned same = 0, diff = 0, ham = 0;
-    for (unsigned c = 0; c < a.chunks; ++c) {
-      const uint4 v = ldg_stream_u4(p + (size_t)c * a.ld), q = sqw[c];
-      if (OP == 0) {
-        dot32(v.x, q.x, same, diff);
-        dot32(v.y, q.y, same, diff);
-        dot32(v.z, q.z, same, diff);
-        dot32(v.w, q.w, same, diff);
-      } else {
-        ham += ham32(v.x, q.x) + ham32(v.y, q.y) + ham32(v.z, q.z) + ham32(v.w, q.w);
-      }
-    }
-    const int32_t s = OP == 0 ? (int32_t)same - (int32_t)diff : (int32_t)ham;
-    if (a.out_i32) a.out_i32[i] = s;
-    if (a.out_f32) a.out_f32[i] = (float)s;
+    si = 0;
+    return sum;
   }
+  unsigned same = 0, diff = 0, ham = 0;
+  for (unsigned c = 0; c < a.chunks; ++c) {
+    const uint4 v = ldg_stream_u4(p + (size_t)c * a.ld), q = sqw[c];
+    if (OP == 0) {
+      dot32(v.x, q.x, same, diff);
+      dot32(v.y, q.y, same, diff);
+      dot32(v.z, q.z, same, diff);
+      dot32(v.w, q.w, same, diff);
+    } else {
+      ham += ham32(v.x, q.x) + ham32(v.y, q.y) + ham32(v.z, q.z) + ham32(v.w, q.w);
+    }
+  }
+  si = OP == 0 ? (int32_t)same - (int32_t)diff : (int32_t)ham;
+  return (float)si;
+}
+
+// OP 0: ternary_dot, 1: ternary_hamming, 2: asymmetric_dot
+template <int OP>
+__global__ void __launch_bounds__(TER_THREADS) ternary_scores_kernel(const TerArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sqw = reinterpret_cast<uint4*>(smem_raw);
+  float* sqf = reinterpret_cast<float*>(smem_raw);
+  if (OP == 2) {
+    for (unsigned k = threadIdx.x; k < a.chunks * 64; k += blockDim.x) sqf[k] = k < a.dim ? a.query[k] : 0.0f;
+  } else {
+    for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
+      const uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
+      sqw[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+    }
+  }
+  __syncthreads();
+  const unsigned i = blockIdx.x * TER_THREADS + threadIdx.x;
+  if (i >= a.n) return;
+  int32_t si = 0;
+  const float sc = ternary_score<OP>(a, a.data + i, sqw, sqf, si);
+  if (OP != 2 && a.out_i32) a.out_i32[i] = si;
+  if (a.out_f32) a.out_f32[i] = sc;
+}
+
+// The same scan with the top-k fused in (one pass, nothing of size n written): dot / asymmetric dot descending, Hamming
+// ascending, ties -> lower index -- the keys launch_topk_from_scores builds from the f32 score vector.
+template <int OP, int R>
+__global__ void __launch_bounds__(TER_THREADS) ternary_topk_kernel(const TerArgs a, int k, unsigned index_base, unsigned n_tiles,
+                                                                  uint64_t* partials, uint64_t* group_partials,
+                                                                  uint64_t* out_keys, unsigned* tickets) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* sqw = reinterpret_cast<uint4*>(smem_raw);
+  float* sqf = reinterpret_cast<float*>(smem_raw);
+  const size_t q_bytes = OP == 2 ? (size_t)a.chunks * 64 * sizeof(float) : (size_t)a.chunks * sizeof(uint4);
+  uint64_t* smem_keys = reinterpret_cast<uint64_t*>(smem_raw + q_bytes);
+  if (OP == 2) {
+    for (unsigned kk = threadIdx.x; kk < a.chunks * 64; kk += blockDim.x) sqf[kk] = kk < a.dim ? a.query[kk] : 0.0f;
+  } else {
+    for (unsigned c = threadIdx.x; c < a.chunks; c += blockDim.x) {
+      const uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
+      sqw[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  WarpList<R> lists[1];
+  uint64_t thrs[1];
+  lists[0].init();
+  thrs[0] = KEY_SENTINEL;
+  for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const unsigned i = tile * TER_THREADS + threadIdx.x;
+    const bool valid = i < a.n;
+    uint64_t key = KEY_SENTINEL;
+    if (valid) {
+      int32_t si;
+      const float sc = ternary_score<OP>(a, a.data + i, sqw, sqf, si);
+      key = OP == 1 ? make_key_asc(sc, index_base + i) : make_key_desc(sc, index_base + i);
+    }
+    lists[0].offer(key, valid, thrs[0], k, lane);
+  }
+  block_finish<R, 1>(lists, 1, k, smem_keys, partials, group_partials, out_keys, tickets);
 }
 
 // row-major words [n][words] -> chunk-major uint4, masking the padding pairs of the last word (PackedTernary::new)
@@ -221,6 +268,44 @@ cudaError_t launch_ternary_scores(const TerView& v, int op, const uint64_t* dev_
   else ternary_scores_kernel<2><<<grid, TER_THREADS, smem, s>>>(a);
   ++*launches;
   return cudaGetLastError();
+}
+
+namespace {
+template <int OP, int R>
+cudaError_t launch_ter_topk(const TerArgs& a, size_t k, uint32_t index_base, uint64_t* dev_keys, Workspace& ws, cudaStream_t s) {
+  auto kern = ternary_topk_kernel<OP, R>;
+  const size_t q_bytes = OP == 2 ? (size_t)a.chunks * 64 * sizeof(float) : (size_t)a.chunks * sizeof(uint4);
+  const size_t smem = q_bytes + (size_t)(TER_THREADS / 32) * k * sizeof(uint64_t);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+  int occ = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TER_THREADS, smem)) != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  const unsigned n_tiles = (a.n + TER_THREADS - 1) / TER_THREADS;
+  kern<<<balanced_grid(n_tiles, (unsigned)occ * (unsigned)ws.num_sms), TER_THREADS, smem, s>>>(a, (int)k, index_base, n_tiles, ws.partials,
+                                                                                             ws.group_partials, dev_keys, ws.tickets);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// fused single-pass top-k (k <= 128) of the ternary scores: the keys of launch_topk_from_scores over the f32 score vector
+cudaError_t launch_ternary_topk(const TerView& v, int op, const uint64_t* dev_query_words, const float* dev_query, size_t k,
+                                uint64_t* dev_keys, Workspace& ws, cudaStream_t s, LaunchCounter* launches) {
+  if (v.n == 0 || k == 0 || k > 128 || op < 0 || op > 2) return cudaErrorInvalidValue;
+  TerArgs a{};
+  a.data = v.data;
+  a.ld = v.ld;
+  a.n = (unsigned)v.n;
+  a.chunks = (unsigned)v.chunks;
+  a.dim = (unsigned)v.dim;
+  a.query_words = dev_query_words;
+  a.query = dev_query;
+  cudaError_t e;
+  if (k <= 32) e = op == 0 ? launch_ter_topk<0, 1>(a, k, v.index_base, dev_keys, ws, s) : op == 1 ? launch_ter_topk<1, 1>(a, k, v.index_base, dev_keys, ws, s) : launch_ter_topk<2, 1>(a, k, v.index_base, dev_keys, ws, s);
+  else e = op == 0 ? launch_ter_topk<0, 4>(a, k, v.index_base, dev_keys, ws, s) : op == 1 ? launch_ter_topk<1, 4>(a, k, v.index_base, dev_keys, ws, s) : launch_ter_topk<2, 4>(a, k, v.index_base, dev_keys, ws, s);
+  if (e == cudaSuccess) ++*launches;
+  return e;
 }
 
 }  // namespace innr

@@ -21,6 +21,12 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
+def sharded_order_bits(scores):
+    """f32::total_cmp order as unsigned integers (the key codec of innr_b200/sharded.py, csrc/common.cuh)."""
+    from innr_b200 import sharded
+    return sharded.order_bits(np.asarray(scores, dtype=np.float32)).astype(np.int64)
+
+
 def same_scores(a, b):
     """Bit equality, except that any NaN matches any NaN: NaN sign/payload is not portable across the reference's
     own targets (x86 propagates the operand payload and makes 0*inf a NEGATIVE NaN, aarch64 a positive default
@@ -608,6 +614,15 @@ def test_ternary_scans_exact(ib, oracle, dim):
         idx, sc = ib.ternary_topk("hamming", qg, corpus, k)
         order = sorted(range(n), key=lambda i: (want_h[i], i))[:k]
         assert [int(i) for i in idx] == order and [int(s) for s in sc] == [int(want_h[i]) for i in order]
+    # asymmetric dot top-k (fused single pass for k <= 128, score vector + selection rounds above): descending under
+    # total_cmp, ties -> lower index, scores bit-identical to the full scan's
+    a_full = ib.ternary_scores_all("asymmetric_dot", qf, corpus)
+    okey = sharded_order_bits(a_full)
+    for k in (1, 10, 100, 300):
+        idx, sc = ib.ternary_topk("asymmetric_dot", qf, corpus, k)
+        order = sorted(range(n), key=lambda i: (-int(okey[i]), i))[:k]
+        assert [int(i) for i in idx] == order, (dim, k)
+        assert np.array_equal(bits(sc), bits(a_full[order])), (dim, k)
 
 
 # ------------------------------------------------------------------------------------------------ u8
