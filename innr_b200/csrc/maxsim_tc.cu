@@ -42,7 +42,7 @@ constexpr int TILE_M = 128;                 // tokens per tile (UMMA M)
 constexpr int CHUNK = 32;                   // tokens per stream per tile (one TMEM lane quadrant)
 constexpr int NQ = 32;                      // query tokens per group (one TMEM column block)
 constexpr int ACC_MAX = 3;                  // TMEM accumulator stages: 3 x 64 columns (G = 1) or 2 x 128 (G = 2)
-constexpr int MAX_SLOTS = 14;               // ring of K panels (16 KB each)
+constexpr int MAX_STAGES = 8;
 constexpr int PANEL_BYTES = TILE_M * 128;   // 16 KB: [128 rows][32 floats], 128-byte swizzle
 constexpr int BOX_BYTES = CHUNK * 128;      // one TMA box: 32 rows x 128 B
 constexpr float EPS_SQ = 1e-9f * 1e-9f;
@@ -55,19 +55,15 @@ struct Shape {
   static constexpr int DIM = 32 * P;
   static constexpr int UMMA_N = 64 * G;                 // [Qhi ; Qlo]
   static constexpr int ACC = G == 1 ? 3 : 2;
+  static constexpr int STAGE_BYTES = P * PANEL_BYTES;
   static constexpr int QPANEL_BYTES = UMMA_N * 128;     // one K panel of the B operand
   static constexpr int QBYTES = P * QPANEL_BYTES;
-  // The token ring is PANEL-granular: a slot holds one K panel (32 dimensions) of one 128-token tile. Every consumer
-  // works panel by panel (an MMA instruction touches one panel; a converter thread reads 128 B of its row per panel), so
-  // the producer refills a slot as soon as that panel has been read instead of waiting for the whole 64 KB tile, and
-  // the ring holds a non-integral number of tiles (10 panels = 2.5 tiles next to the 64 KB operand of a query pair,
-  // where a tile-granular ring had 2 stages and starved the converters: 29 % of the stall samples of the pair kernel).
-  static constexpr int FIT = (227 * 1024 - 1536 - QBYTES) / PANEL_BYTES;
-  static constexpr int NSLOTS = FIT > MAX_SLOTS ? MAX_SLOTS : FIT;
+  static constexpr int FIT = (227 * 1024 - 1024 - QBYTES) / STAGE_BYTES;
+  static constexpr int STAGES = FIT > MAX_STAGES ? MAX_STAGES : FIT;
 };
 
 struct SharedTail {  // everything after the operand buffers
-  uint64_t full[MAX_SLOTS], empty[MAX_SLOTS], lo_ready[2], lo_free[2], tmem_full[ACC_MAX], tmem_empty[ACC_MAX];
+  uint64_t full[MAX_STAGES], empty[MAX_STAGES], lo_ready[2], lo_free[2], tmem_full[ACC_MAX], tmem_empty[ACC_MAX];
   unsigned long long s_tok[5];  // token boundaries of the four streams
   unsigned s_doc[5];            // document boundaries of the four streams
   float q_inv[2 * NQ];          // cosine: 1/||q_r|| per query token row
@@ -149,12 +145,12 @@ template <bool COSINE, int P, int G>
 __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_constant__ CUtensorMap tm_tokens,
                                                                    const TcArgs a) {
   using SH = Shape<P, G>;
-  constexpr int DIM = SH::DIM, NSLOTS = SH::NSLOTS, QBYTES = SH::QBYTES,
+  constexpr int DIM = SH::DIM, STAGES = SH::STAGES, STAGE_BYTES = SH::STAGE_BYTES, QBYTES = SH::QBYTES,
                 UMMA_N = SH::UMMA_N, ACC = SH::ACC, QPANEL_BYTES = SH::QPANEL_BYTES, NQG = NQ * G;
-  static_assert(NSLOTS >= 2 * P, "ring too shallow");
+  static_assert(STAGES >= 2, "ring too shallow");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_tok = smem;                                  // NSLOTS x 16 KB panels
-  uint8_t* s_q = smem + NSLOTS * PANEL_BYTES;             // P x 8 G KB
+  uint8_t* s_tok = smem;                                  // STAGES x (P x 16 KB)
+  uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // P x 8 KB
   SharedTail* st = reinterpret_cast<SharedTail*>(s_q + QBYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -189,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       st->s_tok[w] = doc_begin(a, d);
       prev = d;
     }
-    for (int s = 0; s < NSLOTS; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&st->full[s], 1);
       mbar_init(&st->empty[s], 5);  // hi MMAs done reading (1 commit) + 4 converter warps done reading (one elected
                                     // arrive per warp: 128 per-thread arrives on one mbarrier serialise in the LSU and
@@ -256,26 +252,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (int w = 0; w < 4; ++w) row[w] = (long long)st->s_tok[w];
       // an exhausted stream keeps loading its last box (valid memory, masked in the epilogue)
       const long long last_row = a.total_tokens > CHUNK ? (long long)a.total_tokens - CHUNK : 0;
-      int slot = 0;
-      uint32_t phase = 0;
       for (unsigned i = 0; i < n_tiles; ++i) {
-        int r0[4];
+        const int s = i % STAGES;
+        mbar_wait_sleepy(&st->empty[s], ((i / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&st->full[s], STAGE_BYTES);
+        uint8_t* dst = s_tok + s * STAGE_BYTES;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          r0[w] = (int)(row[w] < (long long)st->s_tok[w + 1] ? row[w] : last_row);  // rows past the matrix end are zero-filled
+          const int r0 = (int)(row[w] < (long long)st->s_tok[w + 1] ? row[w] : last_row);  // rows past the matrix end are zero-filled
+#pragma unroll
+          for (int p = 0; p < P; ++p) tma_load_2d(dst + p * PANEL_BYTES + w * BOX_BYTES, &tm_tokens, &st->full[s], p * 32, r0);
           row[w] += CHUNK;
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          mbar_wait_sleepy(&st->empty[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&st->full[slot], PANEL_BYTES);
-          uint8_t* dst = s_tok + slot * PANEL_BYTES;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) tma_load_2d(dst + w * BOX_BYTES, &tm_tokens, &st->full[slot], p * 32, r0[w]);
-          if (++slot == NSLOTS) {
-            slot = 0;
-            phase ^= 1;
-          }
         }
       }
     }
@@ -288,16 +275,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQG);
     const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(s_q));
     const uint64_t a_desc0 = make_smem_desc_kmajor_sw128(smem_u32(s_tok));
-    // one K panel (32 dimensions = 4 MMAs of K = 8) of the hi pass: A = the panel as TMA wrote it (the tensor core reads
-    // the TF32 part = Xhi), B = K panel `p` of [Qhi ; Qlo]
-    auto issue_hi_panel = [&](int slot, int p, int t) {
-      const uint64_t ad0 = desc_advance(a_desc0, (uint32_t)slot * PANEL_BYTES);
-      const uint64_t qd0 = desc_advance(q_desc, (uint32_t)p * QPANEL_BYTES);
+    auto issue_hi = [&](int s, int t) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
+      const uint64_t ad0 = desc_advance(a_desc0, (uint32_t)s * STAGE_BYTES);
       const uint32_t acc = tmem + t * UMMA_N;
-      if (p == 0) umma_tf32_c<false>(acc, ad0, qd0, idesc);
-      else umma_tf32_c<true>(acc, ad0, qd0, idesc);
+      umma_tf32_c<false>(acc, ad0, q_desc, idesc);
 #pragma unroll
-      for (int kk = 1; kk < 4; ++kk) umma_tf32_c<true>(acc, desc_advance(ad0, kk * 32), desc_advance(qd0, kk * 32), idesc);
+      for (int kk = 1; kk < DIM / 8; ++kk)
+        umma_tf32_c<true>(acc, desc_advance(ad0, (kk >> 2) * PANEL_BYTES + (kk & 3) * 32),
+                          desc_advance(q_desc, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc);
     };
     // A = Xlo in tensor memory (128 lanes x 128 columns); B = the Qhi rows only (N = 32): Qlo.Xlo is below
     // 2^-22 of the product and is not worth a quarter of the tensor work (the kernel runs under the power cap).
@@ -307,30 +292,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (int kk = 0; kk < DIM / 8; ++kk)
         umma_tf32_ts_c<true>(acc, src + kk * 8, desc_advance(q_desc, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc_lo);
     };
-    if (a.debug_mode == 1) {  // profiling aid: TMA streaming only
-      int slot = 0;
-      uint32_t phase = 0;
-      for (unsigned it = 0; it < n_tiles * P; ++it) {
-        mbar_wait(&st->full[slot], phase);
+    if (a.debug_mode == 1) {
+      for (unsigned i = 0; i < n_tiles; ++i) {
+        mbar_wait(&st->full[i % STAGES], (i / STAGES) & 1);
         if (lane == 0)
-          for (int r = 0; r < 5; ++r) mbar_arrive(&st->empty[slot]);
+          for (int r = 0; r < 5; ++r) mbar_arrive(&st->empty[i % STAGES]);
         __syncwarp();
-        if (++slot == NSLOTS) {
-          slot = 0;
-          phase ^= 1;
-        }
       }
     }
-    // hi panels and lo(j) are issued in whatever order their inputs become ready (never block on one while the other
-    // could run); lo(j) always follows the last hi panel of tile j because both accumulate into the same TMEM columns.
-    // debug_mode 2 (profiling aid): hi pass only -- the accumulator is handed to the epilogue after the last hi panel.
+    if (a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
+      for (unsigned i = 0; i < n_tiles; ++i) {
+        const int s = i % STAGES, t = i % ACC;
+        mbar_wait(&st->full[s], (i / STAGES) & 1);
+        mbar_wait(&st->tmem_empty[t], ((i / ACC) & 1) ^ 1);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          issue_hi(s, t);
+          umma_commit(&st->empty[s]);
+          umma_commit(&st->tmem_full[t]);
+        }
+        __syncwarp();
+      }
+    }
+    // hi(i) and lo(j) are issued in whatever order their inputs become ready (never block on one while the
+    // other could run); lo(j) always follows hi(j) because both accumulate into the same TMEM columns.
     unsigned nh = 0, nl = 0;
-    int hp = 0, hslot = 0;
-    uint32_t hphase = 0;
-    const bool hi_only = a.debug_mode == 2;
-    while (a.debug_mode != 1 && (hi_only ? nh : nl) < n_tiles) {
+    while (a.debug_mode != 1 && a.debug_mode != 2 && nl < n_tiles) {
       bool progressed = false;
-      if (!hi_only && nl < nh) {  // lo(nl): the converters have written Xlo of tile nl to TMEM buffer nl % 2
+      if (nl < nh) {  // lo(nl): the converters have written Xlo of tile nl to TMEM buffer nl % 2
         const int b = nl & 1;
         if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
           tc_fence_after_sync();
@@ -344,25 +333,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           progressed = true;
         }
       }
-      if (nh < n_tiles && (hi_only || nh < nl + ACC)) {  // next hi panel of tile nh: X as loaded
-        const int t = nh % ACC;
-        if (mbar_try_wait(&st->full[hslot], hphase) &&
-            (hp > 0 || mbar_try_wait(&st->tmem_empty[t], ((nh / ACC) & 1) ^ 1))) {
+      if (nh < n_tiles && nh < nl + ACC) {  // hi(nh): X as loaded
+        const int s = nh % STAGES, t = nh % ACC;
+        if (mbar_try_wait(&st->full[s], (nh / STAGES) & 1) &&
+            mbar_try_wait(&st->tmem_empty[t], ((nh / ACC) & 1) ^ 1)) {
           tc_fence_after_sync();
           if (elect_one_sync()) {
-            issue_hi_panel(hslot, hp, t);
-            umma_commit(&st->empty[hslot]);  // 1 of 5: the tensor core has finished reading the panel
-            if (hi_only && hp == P - 1) umma_commit(&st->tmem_full[t]);
+            issue_hi(s, t);
+            umma_commit(&st->empty[s]);  // 1 of 5: the tensor core has finished reading the stage
           }
           __syncwarp();
-          if (++hslot == NSLOTS) {
-            hslot = 0;
-            hphase ^= 1;
-          }
-          if (++hp == P) {
-            hp = 0;
-            ++nh;
-          }
+          ++nh;
           progressed = true;
         }
       }
@@ -373,31 +354,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // One token row per thread = one TMEM lane per thread (warps 4-7 own lane quadrants 0-3). A panel row (8 chunks
     // of 16 B) is loaded at once, split, and written as 32 TMEM columns with one tcgen05.st.
     const int row = threadIdx.x - 128;
-    int slot = 0;
-    uint32_t phase = 0;
     for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
-      const int b = i & 1;
-      if (a.debug_mode != 2) {
-        mbar_wait_sleepy(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
+      const int s = i % STAGES, b = i & 1;
+      mbar_wait_sleepy(&st->full[s], (i / STAGES) & 1);
+      if (a.debug_mode == 2) {
+        if (lane == 0) mbar_arrive(&st->empty[s]);
+        continue;
       }
+      mbar_wait_sleepy(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
       const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * DIM;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        mbar_wait_sleepy(&st->full[slot], phase);
-        const uint8_t* pbase = s_tok + slot * PANEL_BYTES + row * 128;
-        if (++slot == NSLOTS) {
-          slot = 0;
-          phase ^= 1;
-        }
-        uint64_t* const empty_bar = &st->empty[slot == 0 ? NSLOTS - 1 : slot - 1];
-        if (a.debug_mode == 2) {
-          if (lane == 0) mbar_arrive(empty_bar);
-          continue;
-        }
+        const uint8_t* pbase = base + p * PANEL_BYTES;
         ulonglong2 v[8];  // two packed f32 pairs per 16-byte chunk: the pairs stay in 64-bit registers end to end
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const ulonglong2*>(pbase + ((c ^ (row & 7)) << 4));
+        if (p == P - 1) {  // every lane of this warp has read its whole row: 1 of 5
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st->empty[s]);
+        }
         uint32_t lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -408,13 +385,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           lo[4 * c + 2] = (uint32_t)l23;
           lo[4 * c + 3] = (uint32_t)(l23 >> 32);
         }
-        // every lane of this warp has consumed its 128 bytes of the panel (the values went through the subtractions):
-        // one elected arrive per warp, 1 of 5
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar);
         tmem_st_32x32b_x32(tdst + 32 * p, lo);
       }
-      if (a.debug_mode == 2) continue;
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
@@ -589,7 +561,7 @@ namespace {
 template <bool COSINE, int P, int G>
 cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
   using SH = Shape<P, G>;
-  constexpr size_t smem = (size_t)SH::NSLOTS * PANEL_BYTES + SH::QBYTES + sizeof(SharedTail);
+  constexpr size_t smem = (size_t)SH::STAGES * SH::STAGE_BYTES + SH::QBYTES + sizeof(SharedTail);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
