@@ -905,6 +905,40 @@ def run_inproc(args):
     print(json.dumps(line), flush=True)
 
 
+def inproc_selfcheck(n_dev, steps):
+    """Runs on rank 0 of an N-process job while the other ranks wait on the host: the C-ABI's own sharded entries (ONE
+    process driving all N devices: worker thread per device + peer-mapped mailbox merge, what a Rust host would call) on
+    a 2M x 768 corpus sharded over the N devices, compared bit for bit with the unsharded call on one device, and timed.
+    This is the one place the driver's multi-GPU lease exercises the in-process path."""
+    import innr_b200 as ib
+    from innr_b200 import sharded, synth
+    n, d, k = 2_000_000, 768, 10
+    shards = []
+    for dev in range(n_dev):
+        ib.init(dev)
+        lo, hi = sharded.shard_range(n, dev, n_dev)
+        shards.append(ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, lo, hi - lo, d, index_base=lo))
+    ib.init(0)
+    whole = ib.DeviceBatch.generate("ghash", synth.SALT_CORPUS, 0, n, d)
+    qs = synth.ghash_f32(synth.SALT_QUERY, 0, 8 * d).reshape(8, d)
+    bad = 0
+    for j in range(8):
+        gi, gs = sharded.batch_knn_sharded("cosine", qs[j], shards, k)
+        wi, ws = ib.batch_knn_many("cosine", qs[j], whole, k)
+        bad += int(not (np.array_equal(gi, wi) and gs.tobytes() == ws.tobytes()))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        sharded.batch_knn_sharded("cosine", qs[i % 8], shards, k)
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ib.batch_knn_many("cosine", qs[i % 8], whole, k)
+    ms1 = (time.perf_counter() - t0) / steps * 1e3
+    return {"check": "innr_cuda_batch_knn_sharded over %d devices == unsharded call on 8 queries" % n_dev if bad == 0
+            else f"MISMATCH on {bad} of 8 queries", "rows": n, "ms_per_call_sharded": ms, "ms_per_call_one_device": ms1,
+            "speedup": ms1 / ms, "note": "host buffers in and out, wall clock; one process, worker thread per device"}
+
+
 def cpu_baseline_entry(w, unit, cache):
     """The oracle on this box's host cores for workload w (rank 0, N == 1 only): one step over the full config."""
     cores = os.cpu_count() or 1
@@ -934,6 +968,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="corpus size multiplier (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inproc-check", action="store_true", help="N > 1: skip rank 0's one-process-all-devices self-check")
     ap.add_argument("--sharding", default="peer", choices=["peer", "nccl", "inproc"],
                     help="N > 1: how the per-shard top-k lists meet -- peer-mapped mailboxes (one launch, default), one "
                          "NCCL allgather + merge launch (the comparison), or `inproc`: ONE process (no torchrun) drives "
@@ -1008,11 +1043,30 @@ def main():
         if rank == 0:
             entry["wall_s"] = round(time.perf_counter() - t0, 1)
             entries[name] = entry
+    inproc = None
+    if world > 1 and args.workload == "all" and not args.no_inproc_check:
+        # rank 0 drives every device from this one process through the C-ABI's sharded entries; the other ranks wait on
+        # the HOST (store key), not in a device-side barrier, so their GPUs are idle for rank 0's kernels
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            try:
+                inproc = inproc_selfcheck(world, min(args.steps, 50))
+            except Exception as e:  # never takes the measured line down
+                inproc = {"error": f"{type(e).__name__}: {e}"[:300]}
+            store.set("innr_inproc_done", "1")
+        else:
+            store.wait(["innr_inproc_done"])
     if rank == 0:
         line = dict(entries[names[0]])
         if args.workload == "all":
             line["workloads"] = {WORKLOADS[n][0]: entries[n] for n in names}
             line["wall_s"] = round(time.perf_counter() - t_all, 1)
+        if inproc:
+            line["inproc_check"] = inproc
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

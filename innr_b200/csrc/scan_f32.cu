@@ -122,21 +122,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
     }
   }
   __syncthreads();
-  if (NEED_DOT && (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS)) {
+  constexpr bool NEED_QN = NEED_DOT && (MODE == PDX_COSINE_FUSED || MODE == PDX_COSINE_NORMS);
+  if (NEED_QN) {
     // query_norm = query.iter().map(|x| x * x).sum::<f32>().sqrt()   (src/batch.rs:714) -- sequential, so one thread per
-    // query; read from the shared-memory copy (a dependent chain of global loads cost ~20 us per launch)
-    if (threadIdx.x < QB) {
+    // query; read from the shared-memory copy (a dependent chain of global loads cost ~20 us per launch). The chain is
+    // d dependent multiply-adds (~3 us at d = 768) and its result is only needed in the first tile's epilogue, so the
+    // CTA does NOT wait for it here: the last warp computes it and joins the scan late, the other warps start streaming
+    // at once, and the barrier in front of the first epilogue (below) finds it long finished.
+    if (threadIdx.x >= SCAN_THREADS - 32 && threadIdx.x - (SCAN_THREADS - 32) < QB) {
+      const unsigned q = threadIdx.x - (SCAN_THREADS - 32);
       float ss = 0.0f;
-      if ((int)threadIdx.x < a.nq_valid) {
+      if ((int)q < a.nq_valid) {
         for (unsigned dd = 0; dd < a.d; ++dd) {
-          const float x = sq[(size_t)dd * QB + threadIdx.x];
+          const float x = sq[(size_t)dd * QB + q];
           ss = __fadd_rn(ss, __fmul_rn(x, x));
         }
       }
-      s_qn[threadIdx.x] = __fsqrt_rn(ss);
+      s_qn[q] = __fsqrt_rn(ss);
     }
-    __syncthreads();
   }
+  bool qn_visible = !NEED_QN;
 
   WarpList<R> lists[QB];
   uint64_t thrs[QB];
@@ -236,6 +241,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) pdx_scan_kernel(const PdxArgs a_
     }
 
     // epilogue: scores (and keys)
+    if (!qn_visible) {  // first tile of this CTA: the query norm written by the last warp (CTA-uniform branch)
+      __syncthreads();
+      qn_visible = true;
+    }
     float nrm[VPT];
     if (MODE == PDX_COSINE_FUSED || MODE == PDX_NORMS) {
 #pragma unroll
