@@ -154,6 +154,8 @@ struct EntryGuard {
   }
 };
 
+void shard_groups_shutdown();  // defined with the in-process sharding state below
+
 int fail(int code, const std::string& msg) {
   t_err = msg;
   return code;
@@ -345,6 +347,7 @@ int innr_cuda_init(int device) {
 }
 
 int innr_cuda_shutdown(void) {
+  shard_groups_shutdown();  // worker threads, mailboxes and staging of the in-process sharded entries
   for (int i = 0; i < MAX_DEVICES; ++i) {
     std::lock_guard<std::mutex> lk(g_dev_mu[i]);
     DeviceCtx& c = g_ctx[i];
@@ -2352,6 +2355,24 @@ struct ShardGroup {  // one per distinct ordered device list
 };
 std::mutex g_groups_mu;
 std::map<std::vector<int>, std::unique_ptr<ShardGroup>> g_groups;
+
+void shard_groups_shutdown() {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  for (auto& kv : g_groups) {
+    ShardGroup* g = kv.second.get();
+    if (!g) continue;
+    g->pool.reset();  // joins the workers
+    for (size_t i = 0; i < g->ex.size(); ++i) {
+      cudaSetDevice(g->ex[i]->device);
+      g->pin_q[i].release();
+      g->pin_out[i].release();
+      g->d_idx[i].release();
+      g->d_score[i].release();
+      innr_cuda_exchange_free(g->ex[i]);
+    }
+  }
+  g_groups.clear();
+}
 
 // Devices of the shards if they are pairwise distinct and a group can be (or was) set up, else nullptr (the caller
 // then takes the thread-per-shard + host-merge route, which also serves several shards on one device).

@@ -738,7 +738,9 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
     size_t cur = CAND_CAP < v.n ? CAND_CAP : v.n;
     levels[n_levels++] = cur;
     static const int sched = getenv("INNR_KNN_TC_SCHED") ? atoi(getenv("INNR_KNN_TC_SCHED")) : 0;
-    const size_t mids[2] = {sched == 1 ? 0 : (sched == 2 ? v.n / 64 : v.n / 128), sched == 1 ? v.n / 32 : (sched == 2 ? v.n / 8 : v.n / 16)};
+    // 0 (default): n/128, n/16 | 1: n/32 | 2: n/64, n/8 | 3: n/128 only | 4: n/64 only | 5: n/256, n/32
+    const size_t mids[2] = {sched == 1 ? 0 : (sched == 2 ? v.n / 64 : (sched == 4 ? v.n / 64 : (sched == 5 ? v.n / 256 : v.n / 128))),
+                            sched == 1 ? v.n / 32 : (sched == 2 ? v.n / 8 : (sched == 3 || sched == 4 ? 0 : (sched == 5 ? v.n / 32 : v.n / 16)))};
     for (size_t nx : mids)
       if (nx >= 4 * cur) {
         cur = (nx + VT - 1) / VT * VT;
