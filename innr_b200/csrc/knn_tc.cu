@@ -30,6 +30,7 @@
 // accumulators in TMEM so the epilogue of one unit overlaps the MMAs of the next.
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -508,7 +509,26 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
       const float* p = data + i;
       float acc = 0.0f, ss = 0.0f;
       unsigned dd = 0;
-      for (; dd + 8 <= d; dd += 8) {  // the reference's sequential unfused sums (src/batch.rs:257-265, 290-296, 676-681)
+      // the reference's sequential unfused sums (src/batch.rs:257-265, 290-296, 676-681). Only a few threads of the CTA
+      // get here (the survivors of the bound test), each walking d rows of the PDX corpus one 4-byte element at a time:
+      // a latency chain of d / RSU round trips, so the rows are fetched 32 at a time
+      constexpr int RSU = 32;
+      for (; dd + RSU <= d; dd += RSU) {
+        float v[RSU];
+#pragma unroll
+        for (int u = 0; u < RSU; ++u) v[u] = __ldg(p + (size_t)(dd + u) * ld);
+#pragma unroll
+        for (int u = 0; u < RSU; ++u) {
+          if (l2) {
+            const float diff = __fsub_rn(sq[dd + u], v[u]);
+            acc = __fadd_rn(acc, __fmul_rn(diff, diff));
+          } else {
+            acc = __fadd_rn(acc, __fmul_rn(sq[dd + u], v[u]));
+            ss = __fadd_rn(ss, __fmul_rn(v[u], v[u]));
+          }
+        }
+      }
+      for (; dd + 8 <= d; dd += 8) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(dd + u) * ld);
@@ -712,8 +732,14 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
   tmark();
 
   // 1. operands, first-pass thresholds, zeroed counters
+  // The dense first pass keeps every pair of its rows. For k <= 32, 1024 rows are enough: the k-th best of a 1024-row
+  // sample lets about rows_next / 1024 * k pairs per query through the next pass, and the selection over 1024 pairs
+  // costs a quarter of what it cost over 4096 (0.15 ms of the 1024-query call). Larger k keep 4096.
+  static const int first_env = getenv("INNR_KNN_TC_FIRST") ? atoi(getenv("INNR_KNN_TC_FIRST")) : 0;
+  const size_t first_rows = std::min<size_t>(v.n, first_env > 0 ? std::min<size_t>((size_t)first_env, CAND_CAP)
+                                                                : (k <= 32 ? (size_t)1024 : (size_t)CAND_CAP));
   knn_tc_prep_queries_kernel<<<p.nq_pad, 128, 0, s>>>(dev_queries, (unsigned)nq, (unsigned)v.d, p.nq_pad, p.d_pad, cosine, l2, qh,
-                                                      qflag, thr, cnt, qaux, (unsigned)(CAND_CAP < v.n ? CAND_CAP : v.n));
+                                                      qflag, thr, cnt, qaux, (unsigned)first_rows);
   ++*launches;
   const bool qres = p.nq_pad <= QR_ROWS && (p.d_pad + KB - 1) / KB <= QR_MAX_KBLOCKS;
   CUtensorMap tm_q;
@@ -732,20 +758,41 @@ cudaError_t launch_pdx_knn_tc(const PdxView& v, const CUtensorMap& tm_xh, const 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  size_t levels[4];
+  size_t levels[6];
   int n_levels = 0;
   {
-    size_t cur = CAND_CAP < v.n ? CAND_CAP : v.n;
+    size_t cur = first_rows;
     levels[n_levels++] = cur;
     static const int sched = getenv("INNR_KNN_TC_SCHED") ? atoi(getenv("INNR_KNN_TC_SCHED")) : 0;
-    // 0 (default): n/128, n/16 | 1: n/32 | 2: n/64, n/8 | 3: n/128 only | 4: n/64 only | 5: n/256, n/32
-    const size_t mids[2] = {sched == 1 ? 0 : (sched == 2 ? v.n / 64 : (sched == 4 ? v.n / 64 : (sched == 5 ? v.n / 256 : v.n / 128))),
-                            sched == 1 ? v.n / 32 : (sched == 2 ? v.n / 8 : (sched == 3 || sched == 4 ? 0 : (sched == 5 ? v.n / 32 : v.n / 16)))};
+    // Prefixes between the dense pass and the whole corpus. Measured at 10M x 768, 1024 queries, k = 10 (whole call,
+    // ms; `profiles/r02_knn_tc_schedules.log`): n/256, n/32 14.8-15.3 | n/128, n/16 (round 1) 15.6-15.9 | n/32 only
+    // 15.0-15.4 | n/64 only 15.5 | n/128 only 16.8. Fewer / smaller prefixes cost less themselves but leave a looser
+    // threshold: the next pass appends more pairs, and every append drags its whole warp through the 32-column slow
+    // path (1.7 M pairs: +2.3 ms on the final pass).
+    // 0 (default): n/256, n/32 for k <= 32, n/128, n/16 above | 1: n/32 | 2: n/64, n/8 | 3: n/128 | 4: n/64 | 6: n/128, n/16
+    const bool fine = sched == 0 ? k <= 32 : false;
+    const size_t mids[2] = {sched == 1 ? 0 : (sched == 2 || sched == 4 ? v.n / 64 : (fine ? v.n / 256 : v.n / 128)),
+                            sched == 1 ? v.n / 32 : (sched == 2 ? v.n / 8 : (sched == 3 || sched == 4 ? 0 : (fine ? v.n / 32 : v.n / 16)))};
     for (size_t nx : mids)
       if (nx >= 4 * cur) {
         cur = (nx + VT - 1) / VT * VT;
         levels[n_levels++] = cur;
       }
+    // a pass over `next` rows with the threshold of a `cur`-row sample appends about next / cur * k pairs per query:
+    // keep that under half of the list (CAND_CAP) with extra prefixes where the standard ones leave a larger step
+    // (small corpora, where n/256 and n/32 are below the 4 x rule)
+    const size_t g_safe = std::max<size_t>(4, (size_t)(CAND_CAP / 2) / k);
+    size_t extra[3];
+    int n_extra = 0;
+    for (size_t top = v.n; top / cur > g_safe && n_extra < 3;) {  // from the top down: the extra prefixes stay small
+      top = ((top + g_safe - 1) / g_safe + VT - 1) / VT * VT;
+      if (top <= cur) break;
+      extra[n_extra++] = top;
+    }
+    while (n_extra > 0 && n_levels < 5) {
+      cur = extra[--n_extra];
+      levels[n_levels++] = cur;
+    }
     if (v.n > cur) levels[n_levels++] = v.n;
   }
   KtArgs a{};

@@ -50,14 +50,17 @@ constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo 
 
 // P = dim / 32 panels of 32 floats (dim 32, 64, 96, 128); G = groups of 32 query tokens scored in ONE corpus pass
 // (B operand = [Qhi ; Qlo] of 64 G rows, accumulator 64 G columns). The shared-memory ring takes what the operands leave.
-template <int P, int G>
+// KH = K halves per tile (token dimensions 129..256): a tile's 128 tokens arrive as KH stages of 128 columns each, and
+// both passes accumulate over the halves into the same TMEM columns (KH = 2 only with G = 1: the B operand of a 256-d
+// query group is 64 KB, a query pair's footprint).
+template <int P, int G, int KH = 1>
 struct Shape {
-  static constexpr int DIM = 32 * P;
+  static constexpr int DIM = 32 * P;                    // columns per stage
   static constexpr int UMMA_N = 64 * G;                 // [Qhi ; Qlo]
   static constexpr int ACC = G == 1 ? 3 : 2;
   static constexpr int STAGE_BYTES = P * PANEL_BYTES;
   static constexpr int QPANEL_BYTES = UMMA_N * 128;     // one K panel of the B operand
-  static constexpr int QBYTES = P * QPANEL_BYTES;
+  static constexpr int QBYTES = P * KH * QPANEL_BYTES;
   static constexpr int FIT = (227 * 1024 - 1024 - QBYTES) / STAGE_BYTES;
   static constexpr int STAGES = FIT > MAX_STAGES ? MAX_STAGES : FIT;
 };
@@ -141,13 +144,14 @@ __device__ __forceinline__ void addmul2(float& x0, float& x1, float y0, float y1
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 }
 
-template <bool COSINE, int P, int G>
+template <bool COSINE, int P, int G, int KH = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_constant__ CUtensorMap tm_tokens,
                                                                    const TcArgs a) {
-  using SH = Shape<P, G>;
+  using SH = Shape<P, G, KH>;
   constexpr int DIM = SH::DIM, STAGES = SH::STAGES, STAGE_BYTES = SH::STAGE_BYTES, QBYTES = SH::QBYTES,
-                UMMA_N = SH::UMMA_N, ACC = SH::ACC, QPANEL_BYTES = SH::QPANEL_BYTES, NQG = NQ * G;
+                UMMA_N = SH::UMMA_N, ACC = SH::ACC, QPANEL_BYTES = SH::QPANEL_BYTES, NQG = NQ * G, DIMT = DIM * KH;
   static_assert(STAGES >= 2, "ring too shallow");
+  static_assert(KH == 1 || (G == 1 && P == 4), "K halves: full 128-column stages, one query group");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_tok = smem;                                  // STAGES x (P x 16 KB)
   uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // P x 8 KB
@@ -221,8 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     }
     __syncthreads();
   }
-  for (int idx = threadIdx.x; idx < NQG * DIM; idx += blockDim.x) {
-    const int r = idx / DIM, k = idx % DIM;
+  for (int idx = threadIdx.x; idx < NQG * DIMT; idx += blockDim.x) {
+    const int r = idx / DIMT, k = idx % DIMT;
     bool qvalid;
     const float* qsrc = q_row(r, qvalid);
     float v = (qvalid && k < (int)a.dim) ? qsrc[k] : 0.0f;
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const unsigned t = (unsigned)((st->s_tok[w + 1] - st->s_tok[w] + CHUNK - 1) / CHUNK);
     n_tiles = t > n_tiles ? t : n_tiles;
   }
+  const unsigned n_it = n_tiles * KH;  // stages: iteration it = K half (it % KH) of tile it / KH
 
   if (warp == 8) {
     // =========================== TMA producer ===========================
@@ -252,8 +257,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (int w = 0; w < 4; ++w) row[w] = (long long)st->s_tok[w];
       // an exhausted stream keeps loading its last box (valid memory, masked in the epilogue)
       const long long last_row = a.total_tokens > CHUNK ? (long long)a.total_tokens - CHUNK : 0;
-      for (unsigned i = 0; i < n_tiles; ++i) {
+      for (unsigned i = 0; i < n_it; ++i) {
         const int s = i % STAGES;
+        const int half = KH == 1 ? 0 : (int)(i % KH);
         mbar_wait_sleepy(&st->empty[s], ((i / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&st->full[s], STAGE_BYTES);
         uint8_t* dst = s_tok + s * STAGE_BYTES;
@@ -261,8 +267,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
         for (int w = 0; w < 4; ++w) {
           const int r0 = (int)(row[w] < (long long)st->s_tok[w + 1] ? row[w] : last_row);  // rows past the matrix end are zero-filled
 #pragma unroll
-          for (int p = 0; p < P; ++p) tma_load_2d(dst + p * PANEL_BYTES + w * BOX_BYTES, &tm_tokens, &st->full[s], p * 32, r0);
-          row[w] += CHUNK;
+          for (int p = 0; p < P; ++p)  // columns past `dim` (last panels of the last half) are zero-filled by TMA
+            tma_load_2d(dst + p * PANEL_BYTES + w * BOX_BYTES, &tm_tokens, &st->full[s], half * DIM + p * 32, r0);
+          if (half == KH - 1) row[w] += CHUNK;
         }
       }
     }
@@ -275,25 +282,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     const uint32_t idesc_lo = make_idesc_tf32(TILE_M, NQG);
     const uint64_t q_desc = make_smem_desc_kmajor_sw128(smem_u32(s_q));
     const uint64_t a_desc0 = make_smem_desc_kmajor_sw128(smem_u32(s_tok));
-    auto issue_hi = [&](int s, int t) {  // A = X tile in shared memory (tensor core reads the TF32 part = Xhi)
+    auto issue_hi = [&](int s, int t, int half) {  // A = X stage in shared memory (tensor core reads the TF32 part = Xhi)
       const uint64_t ad0 = desc_advance(a_desc0, (uint32_t)s * STAGE_BYTES);
+      const uint64_t qd0 = desc_advance(q_desc, (uint32_t)half * P * QPANEL_BYTES);  // this half's K panels of the B operand
       const uint32_t acc = tmem + t * UMMA_N;
-      umma_tf32_c<false>(acc, ad0, q_desc, idesc);
+      if (KH == 1 || half == 0) umma_tf32_c<false>(acc, ad0, qd0, idesc);
+      else umma_tf32_c<true>(acc, ad0, qd0, idesc);
 #pragma unroll
       for (int kk = 1; kk < DIM / 8; ++kk)
         umma_tf32_c<true>(acc, desc_advance(ad0, (kk >> 2) * PANEL_BYTES + (kk & 3) * 32),
-                          desc_advance(q_desc, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc);
+                          desc_advance(qd0, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc);
     };
     // A = Xlo in tensor memory (128 lanes x 128 columns); B = the Qhi rows only (N = 32): Qlo.Xlo is below
     // 2^-22 of the product and is not worth a quarter of the tensor work (the kernel runs under the power cap).
-    auto issue_lo = [&](int t, int b) {
+    auto issue_lo = [&](int t, int b, int half) {
       const uint32_t acc = tmem + t * UMMA_N, src = tmem + LO_COL0 + b * DIM;
+      const uint64_t qd0 = desc_advance(q_desc, (uint32_t)half * P * QPANEL_BYTES);
 #pragma unroll
       for (int kk = 0; kk < DIM / 8; ++kk)
-        umma_tf32_ts_c<true>(acc, src + kk * 8, desc_advance(q_desc, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc_lo);
+        umma_tf32_ts_c<true>(acc, src + kk * 8, desc_advance(qd0, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc_lo);
     };
     if (a.debug_mode == 1) {
-      for (unsigned i = 0; i < n_tiles; ++i) {
+      for (unsigned i = 0; i < n_it; ++i) {
         mbar_wait(&st->full[i % STAGES], (i / STAGES) & 1);
         if (lane == 0)
           for (int r = 0; r < 5; ++r) mbar_arrive(&st->empty[i % STAGES]);
@@ -301,45 +311,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       }
     }
     if (a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
-      for (unsigned i = 0; i < n_tiles; ++i) {
-        const int s = i % STAGES, t = i % ACC;
+      for (unsigned i = 0; i < n_it; ++i) {
+        const unsigned tile = i / KH;
+        const int s = i % STAGES, t = tile % ACC, half = (int)(i % KH);
         mbar_wait(&st->full[s], (i / STAGES) & 1);
-        mbar_wait(&st->tmem_empty[t], ((i / ACC) & 1) ^ 1);
+        if (half == 0) mbar_wait(&st->tmem_empty[t], ((tile / ACC) & 1) ^ 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
-          issue_hi(s, t);
+          issue_hi(s, t, half);
           umma_commit(&st->empty[s]);
-          umma_commit(&st->tmem_full[t]);
+          if (half == KH - 1) umma_commit(&st->tmem_full[t]);
         }
         __syncwarp();
       }
     }
     // hi(i) and lo(j) are issued in whatever order their inputs become ready (never block on one while the
     // other could run); lo(j) always follows hi(j) because both accumulate into the same TMEM columns.
-    unsigned nh = 0, nl = 0;
-    while (a.debug_mode != 1 && a.debug_mode != 2 && nl < n_tiles) {
+    unsigned nh = 0, nl = 0;  // counted in stages (K halves of tiles)
+    while (a.debug_mode != 1 && a.debug_mode != 2 && nl < n_it) {
       bool progressed = false;
-      if (nl < nh) {  // lo(nl): the converters have written Xlo of tile nl to TMEM buffer nl % 2
+      if (nl < nh) {  // lo(nl): the converters have written Xlo of stage nl to TMEM buffer nl % 2
         const int b = nl & 1;
         if (mbar_try_wait(&st->lo_ready[b], (nl >> 1) & 1)) {
+          const unsigned tile = nl / KH;
+          const int half = (int)(nl % KH);
           tc_fence_after_sync();
           if (elect_one_sync()) {
-            issue_lo(nl % ACC, b);
-            umma_commit(&st->tmem_full[nl % ACC]);  // accumulator complete for the epilogue
-            umma_commit(&st->lo_free[b]);              // Xlo buffer may be overwritten
+            issue_lo(tile % ACC, b, half);
+            if (half == KH - 1) umma_commit(&st->tmem_full[tile % ACC]);  // accumulator complete for the epilogue
+            umma_commit(&st->lo_free[b]);                                   // Xlo buffer may be overwritten
           }
           __syncwarp();
           ++nl;
           progressed = true;
         }
       }
-      if (nh < n_tiles && nh < nl + ACC) {  // hi(nh): X as loaded
-        const int s = nh % STAGES, t = nh % ACC;
+      if (nh < n_it && nh < nl + ACC * KH) {  // hi(nh): X as loaded
+        const unsigned tile = nh / KH;
+        const int s = nh % STAGES, t = tile % ACC, half = (int)(nh % KH);
         if (mbar_try_wait(&st->full[s], (nh / STAGES) & 1) &&
-            mbar_try_wait(&st->tmem_empty[t], ((nh / ACC) & 1) ^ 1)) {
+            (half > 0 || mbar_try_wait(&st->tmem_empty[t], ((tile / ACC) & 1) ^ 1))) {
           tc_fence_after_sync();
           if (elect_one_sync()) {
-            issue_hi(s, t);
+            issue_hi(s, t, half);
             umma_commit(&st->empty[s]);  // 1 of 5: the tensor core has finished reading the stage
           }
           __syncwarp();
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // One token row per thread = one TMEM lane per thread (warps 4-7 own lane quadrants 0-3). A panel row (8 chunks
     // of 16 B) is loaded at once, split, and written as 32 TMEM columns with one tcgen05.st.
     const int row = threadIdx.x - 128;
-    for (unsigned i = 0; a.debug_mode != 1 && i < n_tiles; ++i) {
+    for (unsigned i = 0; a.debug_mode != 1 && i < n_it; ++i) {
       const int s = i % STAGES, b = i & 1;
       mbar_wait_sleepy(&st->full[s], (i / STAGES) & 1);
       if (a.debug_mode == 2) {
@@ -538,7 +552,7 @@ __global__ void token_inv_norms_kernel(const float* __restrict__ tokens, size_t 
 bool make_token_tmap(CUtensorMap* m, const float* dev_tokens, size_t total_tokens, size_t dim) {
   // TMA needs a 16-byte row pitch; a row that is not a whole number of 32-column panels is completed with zeros by the
   // out-of-bounds fill of the last box
-  if (dim == 0 || dim % 4 != 0 || dim > 128 || total_tokens == 0) return false;
+  if (dim == 0 || dim % 4 != 0 || dim > 256 || total_tokens == 0) return false;
   return make_tmap_f32_rows(m, dev_tokens, total_tokens, dim, CHUNK);
 }
 
@@ -550,31 +564,36 @@ cudaError_t launch_token_inv_norms(const float* dev_tokens, size_t total_tokens,
   return cudaGetLastError();
 }
 
-// dim <= 128, a multiple of 4 (panels of 32 columns, the last one zero-filled by TMA); up to 64 query tokens per corpus pass, more in several passes (the sum over query tokens is
-// additive across passes)
+// dim <= 256, a multiple of 4 (panels of 32 columns, the last ones zero-filled by TMA; 129..256: two K halves per
+// tile); up to 64 query tokens per corpus pass (32 above dim 128), more in several passes (the sum over query tokens
+// is additive across passes)
 bool maxsim_tc_supported(const TokView& v, size_t n_q) {
-  return v.dim >= 4 && v.dim <= 128 && v.dim % 4 == 0 && n_q >= 1 && v.total_tokens > 0 &&
+  return v.dim >= 4 && v.dim <= 256 && v.dim % 4 == 0 && n_q >= 1 && v.total_tokens > 0 &&
          v.tmap_valid && v.inv_norms != nullptr && v.total_tokens < 0x7FFFFF00ull;
 }
 
 namespace {
-template <bool COSINE, int P, int G>
+template <bool COSINE, int P, int G, int KH = 1>
 cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
-  using SH = Shape<P, G>;
+  using SH = Shape<P, G, KH>;
   constexpr size_t smem = (size_t)SH::STAGES * SH::STAGE_BYTES + SH::QBYTES + sizeof(SharedTail);
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P, G, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  maxsim_tc_kernel<COSINE, P, G><<<grid, TC_THREADS, smem, s>>>(tm, a);
+  maxsim_tc_kernel<COSINE, P, G, KH><<<grid, TC_THREADS, smem, s>>>(tm, a);
   return cudaGetLastError();
 }
 template <bool COSINE, int G>
 cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
+  if (dim > 128) {  // 129..256 columns: two K halves of 128 columns per tile, one query group per pass
+    if (G != 1) return cudaErrorInvalidValue;
+    return launch_shape<COSINE, 4, 1, 2>(tm, a, grid, s);
+  }
   switch ((dim + 31) / 32) {  // panels of 32 columns; TMA zero-fills the columns of the last panel past `dim`
     case 1: return launch_shape<COSINE, 1, G>(tm, a, grid, s);
     case 2: return launch_shape<COSINE, 2, G>(tm, a, grid, s);
@@ -608,7 +627,7 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   // one corpus pass per 64 query tokens (two column groups per accumulator), a last pass of <= 32 with one group
   for (size_t q0 = 0; q0 < n_q;) {
     const size_t rem = n_q - q0;
-    const bool two = rem > NQ;
+    const bool two = rem > NQ && v.dim <= 128;  // two column groups per pass need the B operand to fit: dim <= 128
     const size_t take = two ? (rem < 2 * NQ ? rem : 2 * NQ) : rem;
     a.n_q = (unsigned)take;
     a.q = dev_q + q0 * v.dim;
@@ -640,8 +659,9 @@ cudaError_t launch_maxsim_tc_batch(const TokView& v, const float* dev_q, size_t 
   if (grid > tiles) grid = (unsigned)tiles;
   if (grid > v.n_docs) grid = (unsigned)v.n_docs;
   if (grid == 0) grid = 1;
-  for (size_t i = 0; i < n_queries; i += 2) {
-    const bool pair = i + 1 < n_queries;
+  const size_t per_pass = v.dim <= 128 ? 2 : 1;  // dim > 128: the B operand of one 256-d query fills a pair's space
+  for (size_t i = 0; i < n_queries; i += per_pass) {
+    const bool pair = per_pass == 2 && i + 1 < n_queries;
     a.q = dev_q + i * n_q * v.dim;
     a.n_q = (unsigned)n_q;
     a.out = dev_scores + i * v.n_docs;
