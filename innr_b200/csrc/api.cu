@@ -2428,6 +2428,8 @@ int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, s
   std::function<void(size_t)> job = [&](size_t i) {
     auto body = [&]() -> int {
       const innr_cuda_corpus* c = shards[i];
+      innr_cuda_exchange* x = g->ex[i];
+      ++x->calls;  // first thing: a shard that fails below must not leave the ranks' call numbers out of step
       EntryGuard lk(c->device);
       DeviceCtx* ctx;
       int rc = ctx_for(c, &ctx);
@@ -2440,8 +2442,6 @@ int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, s
       CU(cudaMemcpyAsync(ctx->d_query.p, g->pin_q[i].p, query_bytes, cudaMemcpyHostToDevice, s));
       rc = enqueue_keys(i, ctx, ctx->d_query.p, (uint64_t*)ctx->d_keys.p);
       if (rc) return rc;
-      innr_cuda_exchange* x = g->ex[i];
-      ++x->calls;
       if (i != 0) {
         CU(launch_exchange_merge(ex_view(x), (const uint64_t*)ctx->d_keys.p, nq, k, x->calls, 1, 0, nullptr, nullptr, nullptr,
                                  nullptr, s, &g_launches));

@@ -509,25 +509,9 @@ __global__ void __launch_bounds__(RS_THREADS) knn_tc_rescore_kernel(const float*
       const float* p = data + i;
       float acc = 0.0f, ss = 0.0f;
       unsigned dd = 0;
-      // the reference's sequential unfused sums (src/batch.rs:257-265, 290-296, 676-681). Only a few threads of the CTA
-      // get here (the survivors of the bound test), each walking d rows of the PDX corpus one 4-byte element at a time:
-      // a latency chain of d / RSU round trips, so the rows are fetched 32 at a time
-      constexpr int RSU = 32;
-      for (; dd + RSU <= d; dd += RSU) {
-        float v[RSU];
-#pragma unroll
-        for (int u = 0; u < RSU; ++u) v[u] = __ldg(p + (size_t)(dd + u) * ld);
-#pragma unroll
-        for (int u = 0; u < RSU; ++u) {
-          if (l2) {
-            const float diff = __fsub_rn(sq[dd + u], v[u]);
-            acc = __fadd_rn(acc, __fmul_rn(diff, diff));
-          } else {
-            acc = __fadd_rn(acc, __fmul_rn(sq[dd + u], v[u]));
-            ss = __fadd_rn(ss, __fmul_rn(v[u], v[u]));
-          }
-        }
-      }
+      // the reference's sequential unfused sums (src/batch.rs:257-265, 290-296, 676-681), 8 rows in flight per thread
+      // (32 in flight measured slower: 1.0 ms instead of 0.6 for 1024 queries -- every row of a candidate is its own
+      // 32-byte sector 4 ld bytes from the last one, and the deeper queue only thrashes the TLB)
       for (; dd + 8 <= d; dd += 8) {
         float v[8];
 #pragma unroll

@@ -628,7 +628,8 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   for (size_t q0 = 0; q0 < n_q;) {
     const size_t rem = n_q - q0;
     const bool two = rem > NQ && v.dim <= 128;  // two column groups per pass need the B operand to fit: dim <= 128
-    const size_t take = two ? (rem < 2 * NQ ? rem : 2 * NQ) : rem;
+    const size_t cap = two ? 2 * NQ : NQ;
+    const size_t take = rem < cap ? rem : cap;
     a.n_q = (unsigned)take;
     a.q = dev_q + q0 * v.dim;
     a.accumulate = q0 > 0;
