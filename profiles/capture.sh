@@ -11,6 +11,13 @@ mkdir -p $OUT
 declare -A KERN=( [knn_cosine_1q]=pdx_scan_kernel [hamming]=hamming_kernel [u8]=u8_scan_kernel [maxsim]=maxsim_tc_kernel
                   [knn_cosine_multi]=knn_tc_filter_kernel [batch_demo]=pdx_scan )
 declare -A COUNT=( [knn_cosine_1q]=2 [hamming]=2 [u8]=2 [maxsim]=2 [knn_cosine_multi]=8 [batch_demo]=2 )
+# the driver's own command (all workloads in one process): plain run, then its ncu launch list -- the kernels' SHARES of a
+# step must agree with bench.py's live CUDA-event numbers (per-launch times under ncu are cold-cache and serialised)
+DEF="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+$DEF > $OUT/${TAG}_plain_default.log 2>&1 || { echo "plain default run failed"; tail -5 $OUT/${TAG}_plain_default.log; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/${TAG}_launches_default.csv $DEF \
+    > $OUT/${TAG}_launches_default.log 2>&1
+echo "default command: done"
 for w in $WORKLOADS; do
   CMD="python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline"
   $CMD > $OUT/${TAG}_plain_$w.log 2>&1 || { echo "plain run of $w failed"; tail -5 $OUT/${TAG}_plain_$w.log; continue; }
