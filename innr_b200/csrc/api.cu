@@ -200,6 +200,8 @@ int ensure_ctx(int device, DeviceCtx** out, bool dev_entry = false, cudaStream_t
     c.ws.tickets_cap = 16384;
     CU(cudaMalloc(&c.ws.tickets, c.ws.tickets_cap * sizeof(unsigned)));
     CU(cudaMemset(c.ws.tickets, 0, c.ws.tickets_cap * sizeof(unsigned)));
+    CU(cudaMalloc(&c.ws.shared_thr, 64 * sizeof(unsigned long long)));
+    CU(cudaMemset(c.ws.shared_thr, 0xFF, 64 * sizeof(unsigned long long)));
     c.h_pin.pinned = true;
     c.h_counts.pinned = true;
     c.ready = true;
@@ -358,6 +360,7 @@ int innr_cuda_shutdown(void) {
     cudaFree(c.ws.partials);
     cudaFree(c.ws.group_partials);
     cudaFree(c.ws.tickets);
+    cudaFree(c.ws.shared_thr);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
     cudaEventDestroy(c.ws_event);

@@ -216,11 +216,13 @@ struct WarpList {
     v[R - 1] = rev < v[R - 1] ? rev : v[R - 1];
     bitonic_cleanup(lane);
   }
-  // offer one candidate per lane; thr = current k-th key (uniform), updated in place
-  __device__ __forceinline__ void offer(uint64_t key, bool valid, uint64_t& thr, int k, int lane) {
-    unsigned m = __ballot_sync(FULL_MASK, valid && key < thr);
+  // offer one candidate per lane; thr = current k-th key (uniform), updated in place. `cap` (uniform) is an outside
+  // bound on the k-th key of the WHOLE selection (SharedThreshold below): keys at or above it cannot be in the result.
+  __device__ __forceinline__ void offer(uint64_t key, bool valid, uint64_t& thr, int k, int lane, uint64_t cap = KEY_SENTINEL) {
+    uint64_t lim = thr < cap ? thr : cap;
+    unsigned m = __ballot_sync(FULL_MASK, valid && key < lim);
     if (__popc(m) >= (R == 1 ? 10 : 6)) {  // warp-uniform
-      insert_batch((valid && key < thr) ? key : KEY_SENTINEL, lane);
+      insert_batch((valid && key < lim) ? key : KEY_SENTINEL, lane);
       thr = at(k - 1);
       return;
     }
@@ -229,8 +231,9 @@ struct WarpList {
       uint64_t x = shfl_u64(key, src);
       insert(x, lane);
       thr = at(k - 1);
+      lim = thr < cap ? thr : cap;
       if (lane == src) valid = false;
-      m = __ballot_sync(FULL_MASK, valid && key < thr);
+      m = __ballot_sync(FULL_MASK, valid && key < lim);
     }
   }
   // Merge a sorted ascending list src[0..len) (len <= 32*R) into this list, keeping the 32*R smallest of the
@@ -339,6 +342,38 @@ __device__ __forceinline__ void block_tree_merge(WarpList<R>& list, int k, uint6
   }
 }
 
+// A launch-wide bound on the k-th key, shared by every warp of every CTA of a single-query selection. A warp's own
+// k-th key bounds the k-th key of the whole selection from above (the whole set contains that warp's k keys), so the
+// minimum over all warps is a valid filter for everybody: a key above it cannot be in the result, and the warp that
+// published the bound keeps the k keys that justify it (they only leave its list for smaller ones). Without it every
+// warp fills its own list -- k (1 + ln(n_warp / k)) insertions per warp, which at k = 100 is most of a warp's
+// instructions on a small shard; with it the whole launch makes about that many insertions in total.
+// One 64-bit word per launch in the workspace, KEY_SENTINEL between launches (reset by block_finish's last CTA).
+struct SharedThreshold {
+  unsigned long long* word;
+  uint64_t seen;  // last value read
+  __device__ __forceinline__ void init(unsigned long long* w) {
+    word = w;
+    seen = KEY_SENTINEL;
+  }
+  // once per tile, before the tile's loads are consumed: a relaxed L2 read (the value only ever decreases)
+  __device__ __forceinline__ uint64_t read() {
+    if (word) {
+      unsigned long long v;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word));
+      seen = v;
+    }
+    return seen;
+  }
+  // after an offer: publish this warp's k-th key if it undercuts what the launch knows (fire-and-forget reduction)
+  __device__ __forceinline__ void publish(uint64_t thr, int lane) {
+    if (word && thr < seen) {
+      if (lane == 0) asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(word), "l"((unsigned long long)thr) : "memory");
+      seen = thr;
+    }
+  }
+};
+
 // Ticket counters used by block_finish: tickets[0] = top level, tickets[1 + g] = group g.
 constexpr int FINISH_GROUP = 32;  // CTAs per first-level merge group
 
@@ -350,7 +385,7 @@ constexpr int FINISH_GROUP = 32;  // CTAs per first-level merge group
 template <int R, int QB>
 __device__ __forceinline__ void block_finish(WarpList<R> (&lists)[QB], int nq_valid, int k, uint64_t* smem_keys,
                                              uint64_t* partials, uint64_t* group_partials, uint64_t* out_keys,
-                                             unsigned* tickets) {
+                                             unsigned* tickets, unsigned long long* shared_thr = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   __shared__ unsigned s_flag;
   const unsigned n_groups = (gridDim.x + FINISH_GROUP - 1) / FINISH_GROUP;
@@ -427,13 +462,18 @@ __device__ __forceinline__ void block_finish(WarpList<R> (&lists)[QB], int nq_va
                                             : group_partials + ((size_t)group * nq_valid + q) * k), k, lane);
   }
   if (threadIdx.x == 0) tickets[1 + group] = 0u;  // ready for the next launch
-  if (n_groups == 1) return;
+  if (n_groups == 1) {
+    // the last CTA of the launch (every other CTA has left its scan loop): the shared bound is KEY_SENTINEL again
+    if (threadIdx.x == 0 && shared_thr) *shared_thr = KEY_SENTINEL;
+    return;
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_flag = (atomicAdd(&tickets[0], 1u) == n_groups - 1) ? 1u : 0u;
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
+  if (threadIdx.x == 0 && shared_thr) *shared_thr = KEY_SENTINEL;
   // ---- last group: merge the group lists ----
 #pragma unroll
   for (int q = 0; q < QB; ++q) {

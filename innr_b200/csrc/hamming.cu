@@ -131,6 +131,7 @@ struct HamArgs {
   uint64_t* out_keys;
   uint64_t* group_partials;
   unsigned* tickets;
+  unsigned long long* shared_thr;  // single-query top-k launches: launch-wide bound on the k-th key (may be null)
   uint32_t* dist_out;
 };
 
@@ -150,16 +151,23 @@ __global__ void __launch_bounds__(HAM_THREADS) hamming_kernel(const HamArgs a) {
   uint64_t thrs[1];
   lists[0].init();
   thrs[0] = KEY_SENTINEL;
+  SharedThreshold sh;
+  sh.init(TOPK ? a.shared_thr : nullptr);
 
   for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const unsigned i = tile * HAM_THREADS + threadIdx.x;
     const bool valid = i < a.n;
+    const uint64_t cap = TOPK ? sh.read() : KEY_SENTINEL;  // issued ahead of the code loads, used after them
     unsigned dist = 0;
     if (valid) dist = code_distance<CHUNKS_CT>(a.data + i, a.ld, a.chunks, sq);
-    if (TOPK) lists[0].offer(make_key_u32(dist, a.index_base + i), valid, thrs[0], a.k, lane);
-    else if (valid) a.dist_out[i] = dist;
+    if (TOPK) {
+      lists[0].offer(make_key_u32(dist, a.index_base + i), valid, thrs[0], a.k, lane, cap);
+      sh.publish(thrs[0], lane);
+    } else if (valid) {
+      a.dist_out[i] = dist;
+    }
   }
-  if (TOPK) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets);
+  if (TOPK) block_finish<R, 1>(lists, 1, a.k, smem_keys, a.partials, a.group_partials, a.out_keys, a.tickets, a.shared_thr);
 }
 
 // QB queries share one pass over the codes (top-k only): the scan is HBM-bound for one query with the ALU pipe a third
@@ -551,6 +559,7 @@ cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_word
     a.partials = ws.partials;
     a.group_partials = ws.group_partials;
     a.tickets = ws.tickets;
+    a.shared_thr = ws.shared_thr;
     a.out_keys = dev_keys + q * k;
     size_t smem = v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
     cudaError_t e;

@@ -30,6 +30,7 @@ struct Workspace {
   size_t group_cap = 0;                // in u64
   unsigned* tickets = nullptr;         // [0] top level, [1+g] group g; zeroed once, self-resetting
   size_t tickets_cap = 0;
+  unsigned long long* shared_thr = nullptr;  // launch-wide bound on the k-th key (common.cuh: SharedThreshold); all ones between launches
   int num_sms = 0;
 };
 

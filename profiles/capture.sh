@@ -25,6 +25,12 @@ for w in $WORKLOADS; do
       > $OUT/${TAG}_launches_$w.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:${KERN[$w]} -s 3 -c ${COUNT[$w]} -f -o $OUT/${TAG}_full_$w $CMD \
       > $OUT/${TAG}_full_$w.log 2>&1
+  # gpurun brings back at most 64 MiB: export what the summaries need (all raw metrics; per-instruction samples and
+  # shared-memory wavefronts) and drop the report itself
+  ncu -i $OUT/${TAG}_full_$w.ncu-rep --page raw --csv > $OUT/${TAG}_full_$w.raw.csv 2>/dev/null
+  ncu -i $OUT/${TAG}_full_$w.ncu-rep --page source --csv --print-source sass 2>/dev/null | \
+      python profiles/top_sass.py > $OUT/${TAG}_full_$w.top_sass.txt
+  rm -f $OUT/${TAG}_full_$w.ncu-rep
   echo "$w: done"
 done
 ls -la $OUT | tail -30

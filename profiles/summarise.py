@@ -35,7 +35,10 @@ UNIT_SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (profiles/capture.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     lines = [l for l in out.splitlines() if l.startswith('"')]
     rd = list(csv.reader(io.StringIO("\n".join(lines))))
     return rd[0], rd[1], rd[2:]  # header, units, launches
@@ -47,6 +50,8 @@ def main():
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for w, kern in DOMINANT.items():
         rep = os.path.join(ROOT, "gpurun_out", f"{tag}_full_{w}.ncu-rep")
+        if not os.path.exists(rep):
+            rep = os.path.join(ROOT, "gpurun_out", f"{tag}_full_{w}.raw.csv")
         if not os.path.exists(rep):
             continue
         hdr, units, rows = raw_rows(rep)
