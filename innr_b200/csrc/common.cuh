@@ -349,28 +349,46 @@ __device__ __forceinline__ void block_tree_merge(WarpList<R>& list, int k, uint6
 // warp fills its own list -- k (1 + ln(n_warp / k)) insertions per warp, which at k = 100 is most of a warp's
 // instructions on a small shard; with it the whole launch makes about that many insertions in total.
 // One 64-bit word per launch in the workspace, KEY_SENTINEL between launches (reset by block_finish's last CTA).
+// Every warp of every SM polling one global word would serialise in a single L2 slice (measured: 100 M codes, one
+// read per warp and tile = 3 M same-address reads, scan 1.84 -> 2.08 ms), so the traffic is two-level: warps talk to
+// two words in SHARED memory (the CTA's view of the bound, the CTA's own best k-th key); one thread per CTA reconciles
+// them with the global word every SHARED_THR_PERIOD tiles.
+constexpr int SHARED_THR_PERIOD = 4;
 struct SharedThreshold {
-  unsigned long long* word;
-  uint64_t seen;  // last value read
-  __device__ __forceinline__ void init(unsigned long long* w) {
+  unsigned long long* word;   // global, one per launch (null: disabled)
+  unsigned long long* s_cap;  // shared: what this CTA last saw (min of global and its own)
+  unsigned long long* s_min;  // shared: smallest k-th key any warp of this CTA has reached
+  // call by all threads before the CTA's first barrier
+  __device__ __forceinline__ void init(unsigned long long* w, unsigned long long* cap, unsigned long long* mn) {
     word = w;
-    seen = KEY_SENTINEL;
-  }
-  // once per tile, before the tile's loads are consumed: a relaxed L2 read (the value only ever decreases)
-  __device__ __forceinline__ uint64_t read() {
-    if (word) {
-      unsigned long long v;
-      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word));
-      seen = v;
+    s_cap = cap;
+    s_min = mn;
+    if (threadIdx.x == 0) {
+      *s_cap = KEY_SENTINEL;
+      *s_min = KEY_SENTINEL;
     }
-    return seen;
   }
-  // after an offer: publish this warp's k-th key if it undercuts what the launch knows (fire-and-forget reduction)
-  __device__ __forceinline__ void publish(uint64_t thr, int lane) {
-    if (word && thr < seen) {
-      if (lane == 0) asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(word), "l"((unsigned long long)thr) : "memory");
-      seen = thr;
+  // once per tile (iteration `it` of the CTA's tile loop), before the tile's loads are consumed
+  __device__ __forceinline__ uint64_t read(unsigned it) {
+    if (!word) return KEY_SENTINEL;
+    if (threadIdx.x == 0 && (it % SHARED_THR_PERIOD) == 0) {
+      unsigned long long g;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(word));
+      const unsigned long long mine = *reinterpret_cast<volatile unsigned long long*>(s_min);
+      if (mine < g) {
+        asm volatile("red.relaxed.gpu.global.min.u64 [%0], %1;" ::"l"(word), "l"(mine) : "memory");
+        g = mine;
+      }
+      *reinterpret_cast<volatile unsigned long long*>(s_cap) = g;
     }
+    // the CTA's own best k-th key is visible to its warps at once, the other CTAs' at the next refresh
+    const unsigned long long c = *reinterpret_cast<volatile unsigned long long*>(s_cap);
+    const unsigned long long m = *reinterpret_cast<volatile unsigned long long*>(s_min);
+    return c < m ? c : m;
+  }
+  // after an offer: this warp's k-th key (uniform), if it undercuts what the CTA knows
+  __device__ __forceinline__ void publish(uint64_t thr, uint64_t cap, int lane) {
+    if (word && thr < cap && lane == 0) atomicMin(s_min, (unsigned long long)thr);
   }
 };
 

@@ -10,6 +10,8 @@
 // code i. One thread owns one code; consecutive threads read consecutive 16-byte chunks, so every warp load is
 // 512 contiguous bytes and no cross-lane reduction is needed. Integer arithmetic: results are exact.
 // Key = (distance << 32) | global index: ascending distance, ties -> lower index == stable sort_by_key.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -145,24 +147,26 @@ __global__ void __launch_bounds__(HAM_THREADS) hamming_kernel(const HamArgs a) {
     uint64_t w0 = a.query_words[2 * c], w1 = a.query_words[2 * c + 1];
     sq[c] = make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
   }
+  __shared__ unsigned long long s_thr[2];
+  SharedThreshold sh;
+  sh.init(TOPK ? a.shared_thr : nullptr, &s_thr[0], &s_thr[1]);
   __syncthreads();
 
   WarpList<R> lists[1];
   uint64_t thrs[1];
   lists[0].init();
   thrs[0] = KEY_SENTINEL;
-  SharedThreshold sh;
-  sh.init(TOPK ? a.shared_thr : nullptr);
 
-  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+  unsigned it = 0;
+  for (unsigned tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
     const unsigned i = tile * HAM_THREADS + threadIdx.x;
     const bool valid = i < a.n;
-    const uint64_t cap = TOPK ? sh.read() : KEY_SENTINEL;  // issued ahead of the code loads, used after them
+    const uint64_t cap = TOPK ? sh.read(it) : KEY_SENTINEL;
     unsigned dist = 0;
     if (valid) dist = code_distance<CHUNKS_CT>(a.data + i, a.ld, a.chunks, sq);
     if (TOPK) {
       lists[0].offer(make_key_u32(dist, a.index_base + i), valid, thrs[0], a.k, lane, cap);
-      sh.publish(thrs[0], lane);
+      sh.publish(thrs[0], cap, lane);
     } else if (valid) {
       a.dist_out[i] = dist;
     }
@@ -559,7 +563,8 @@ cudaError_t launch_hamming_topk(const BinView& v, const uint64_t* dev_query_word
     a.partials = ws.partials;
     a.group_partials = ws.group_partials;
     a.tickets = ws.tickets;
-    a.shared_thr = ws.shared_thr;
+    static const bool shared_off = getenv("INNR_SHARED_THR") && atoi(getenv("INNR_SHARED_THR")) == 0;  // A/B switch
+    a.shared_thr = shared_off ? nullptr : ws.shared_thr;
     a.out_keys = dev_keys + q * k;
     size_t smem = v.chunks * sizeof(uint4) + (size_t)(HAM_THREADS / 32) * k * sizeof(uint64_t);
     cudaError_t e;
