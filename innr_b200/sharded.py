@@ -186,6 +186,67 @@ class ShardedKnn:
                None, C.c_void_p(b["idx"].data_ptr()), C.c_void_p(b["score"].data_ptr()), stream)
         return b["idx"].view(nq, k), b["score"].view(nq, k)
 
+    # ---- pipelined form: the exchange of query i runs on a side stream under the scan of query i + 1 ------------------
+    def _keys(self, dev_queries, nq, k, local, stream):
+        qp, lp = C.c_void_p(dev_queries.data_ptr()), C.c_void_p(local.data_ptr())
+        if self.kind == "f32":
+            L.call("innr_cuda_batch_knn_keys_dev", self.shard.h, self._metric_id, qp, nq, k, lp, stream)
+        elif self.kind == "u8":
+            L.call("innr_cuda_batch_knn_u8_keys_dev", self.shard.h, qp, nq, k, lp, stream)
+        else:
+            L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
+
+    def knn_dev_pipelined(self, dev_queries, nq: int, k: int):
+        """Throughput form of knn_dev for a stream of queries. The exchange is a barrier between the ranks: done on the
+        scan's stream it adds its own latency AND the ranks' per-step skew to every step. Here the shard scan of this
+        call is queued on torch's current stream and its exchange + merge on a high-priority side stream (one CTA; it
+        finds a free slot next to the next scan's CTAs), so consecutive calls overlap and a rank only ever waits for
+        data that is two calls old. Returns (idx, score, event): the tensors are valid once `event` has completed
+        (`torch.cuda.current_stream().wait_event(event)` or `drain()`); they are reused by the call after next.
+        Falls back to knn_dev (event None) without a peer exchange or for requests that do not fit its mailboxes."""
+        t = self.torch
+        if self.exchange is None or not self.exchange.fits(nq, k):
+            idx, sc = self.knn_dev(dev_queries, nq, k)
+            return idx, sc, None
+        key = ("pipe", nq, k)
+        if key not in self._bufs:
+            dev = dev_queries.device
+            mk = lambda dt: t.empty(nq * k, dtype=dt, device=dev)  # noqa: E731
+            self._bufs[key] = {"slots": [dict(local=mk(t.int64), idx=mk(t.int64),
+                                              score=mk(t.float32 if self.kind != "binary" else t.int32),
+                                              scan_done=t.cuda.Event(), ex_done=t.cuda.Event(), used=False) for _ in range(2)],
+                               "calls": 0}
+            if getattr(self, "_ex_stream", None) is None:
+                self._ex_stream = t.cuda.Stream(device=dev, priority=-1)
+        st = self._bufs[key]
+        slot = st["slots"][st["calls"] & 1]
+        st["calls"] += 1
+        main = t.cuda.current_stream()
+        if slot["used"]:
+            main.wait_event(slot["ex_done"])   # the exchange of two calls ago has read `local` (long done)
+        self._keys(dev_queries, nq, k, slot["local"], C.c_void_p(main.cuda_stream))
+        slot["scan_done"].record(main)
+        ex = self._ex_stream
+        ex.wait_event(slot["scan_done"])
+        exs = C.c_void_p(ex.cuda_stream)
+        if self.kind == "binary":
+            self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, L.METRIC_L2, exs, idx=slot["idx"], dist_out=slot["score"])
+        else:
+            m = L.METRIC_L2 if (self.kind == "f32" and self.metric == "l2") else L.METRIC_DOT
+            self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, m, exs, idx=slot["idx"], score=slot["score"])
+        slot["ex_done"].record(ex)
+        slot["used"] = True
+        return slot["idx"].view(nq, k), slot["score"].view(nq, k), slot["ex_done"]
+
+    def drain(self):
+        """Makes torch's current stream wait for every exchange queued by knn_dev_pipelined."""
+        main = self.torch.cuda.current_stream()
+        for key, st in self._bufs.items():
+            if isinstance(key, tuple) and key and key[0] == "pipe":
+                for slot in st["slots"]:
+                    if slot["used"]:
+                        main.wait_event(slot["ex_done"])
+
     def knn(self, queries_host: np.ndarray, k: int, pinned_stage=None):
         """End-to-end call with HOST buffers: H2D of the queries, shard scan, allgather, merge, D2H of the result."""
         t = self.torch

@@ -49,6 +49,29 @@ def main():
                         w = getattr(orc, "batch_knn_" + metric)(qs[j], ob, k)
                         if a[0][j].cpu().tolist() != w.indices or a[1][j].cpu().numpy().tobytes() != w.scores.tobytes():
                             failures.append(("f32-vs-oracle", metric, nq, k, j))
+    # pipelined form: the exchange of call i runs on a side stream under the scan of call i + 1; results of call i are
+    # read after call i + 1 has been queued (they stay valid until call i + 2 reuses their buffers)
+    peer = sharded.ShardedKnn(shard, "f32", "cosine", exchange=ex)
+    sync = sharded.ShardedKnn(shard, "f32", "cosine")
+    qs = synth.ghash_f32(synth.SALT_QUERY, 5000, 9 * d).reshape(9, d)
+    dqs = torch.from_numpy(qs).to(dev)
+    main = torch.cuda.current_stream()
+    got, pending = [], None
+    for i in range(9):
+        cur = peer.knn_dev_pipelined(dqs[i], 1, 10)
+        if pending is not None:
+            main.wait_event(pending[2])
+            got.append((pending[0].clone(), pending[1].clone()))
+        pending = cur
+    main.wait_event(pending[2])
+    got.append((pending[0].clone(), pending[1].clone()))
+    peer.drain()
+    torch.cuda.synchronize()
+    for i in range(9):
+        want = [t.clone() for t in sync.knn_dev(dqs[i], 1, 10)]
+        torch.cuda.synchronize()
+        if not same(got[i], want):
+            failures.append(("pipelined", i))
     # Hamming (heavy ties) and u8
     nb = 200_000
     lo, hi = sharded.shard_range(nb, rank, world)
