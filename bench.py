@@ -844,6 +844,10 @@ def measure(w, args, env):
         }
         if batch:
             entry["query_batch"] = batch
+        if getattr(w, "sk", None) is not None and w.workload != "knn_cosine_multi":
+            entry["step_overlap"] = ("device-resident steps are independent queries: their scans alternate between two streams "
+                                     "(two workspaces per device), so the head of scan i+1 fills the SMs under the tail and the "
+                                     "merge of scan i; roofline.kernel_ms is the same launch back to back on ONE stream")
         if world > 1:
             entry["exchange"] = env["exchange_desc"] if getattr(w, "sk", None) is not None else "none (documents are independent)"
             if exchange_check:

@@ -99,13 +99,20 @@ struct DeviceCtx {
   int device = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  // The workspace and the scratch buffers below are shared by everything that runs on this device. Host-facing entries
+  // The workspaces and the scratch buffers below are shared by everything that runs on this device. Host-facing entries
   // run on `stream` and synchronise before they return; `_dev` entries enqueue on the CALLER's stream and return at
-  // once, so they leave an event behind (ws_event on ws_stream) that the next user on any other stream waits for.
-  cudaEvent_t ws_event = nullptr;
-  cudaStream_t ws_stream = nullptr;
-  bool ws_pending = false;
-  Workspace ws;
+  // once, so they leave an event behind (ws_event[lane] on ws_stream[lane]) that the next user of that lane on any
+  // other stream waits for. Lane 0 = `ws` + every scratch buffer (all entries may use it); lane 1 = `ws_alt`, used only
+  // by the fused k <= 128 scans of `_dev` entries, which need nothing but a Workspace: two independent scans on two
+  // caller streams then overlap (the ramp at the end of one launch is filled by the head of the next -- what makes a
+  // 1/8-corpus shard scan as fast per byte as a whole-corpus one).
+  cudaEvent_t ws_event[2] = {nullptr, nullptr};
+  cudaStream_t ws_stream[2] = {nullptr, nullptr};
+  bool ws_pending[2] = {false, false};
+  uint64_t ws_seq[2] = {0, 0};
+  uint64_t seq = 0;
+  Workspace ws, ws_alt;
+  Workspace& lane_ws(int lane) { return lane ? ws_alt : ws; }
   Buf d_query, d_keys, d_scores, d_aux, d_tcws, h_pin, h_counts;
   float last_ms = 0.0f;
 };
@@ -171,7 +178,34 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
   } while (0)
 
-int ensure_ctx(int device, DeviceCtx** out, bool dev_entry = false, cudaStream_t user = nullptr) {
+// per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
+// (the same buffers hold several query groups of one launch when the grid is small: scan_f32.cu, grid.y)
+int alloc_workspace(Workspace& w, int num_sms) {
+  w.num_sms = num_sms;
+  w.partials_cap = (size_t)num_sms * 8 * 8 * 32 * 4;
+  CU(cudaMalloc(&w.partials, w.partials_cap * sizeof(uint64_t)));
+  w.group_cap = (size_t)(num_sms * 8 / 32 + 2) * 8 * 128 * 4;
+  CU(cudaMalloc(&w.group_partials, w.group_cap * sizeof(uint64_t)));
+  w.tickets_cap = 16384;
+  CU(cudaMalloc(&w.tickets, w.tickets_cap * sizeof(unsigned)));
+  CU(cudaMemset(w.tickets, 0, w.tickets_cap * sizeof(unsigned)));
+  CU(cudaMalloc(&w.shared_thr, 64 * sizeof(unsigned long long)));
+  CU(cudaMemset(w.shared_thr, 0xFF, 64 * sizeof(unsigned long long)));
+  return INNR_OK;
+}
+void free_workspace(Workspace& w) {
+  cudaFree(w.partials);
+  cudaFree(w.group_partials);
+  cudaFree(w.tickets);
+  cudaFree(w.shared_thr);
+}
+
+// How an entry uses the device's shared state: WS_HOST = host-facing (lane 0, runs on the context's stream and
+// synchronises), WS_DEV = `_dev` entry that may touch the scratch buffers (lane 0, caller's stream), WS_DEV_SCAN = `_dev`
+// entry that needs a Workspace and nothing else (either lane), WS_NONE = neither.
+enum WsUse { WS_HOST, WS_DEV, WS_DEV_SCAN, WS_NONE };
+
+int ensure_ctx(int device, DeviceCtx** out, WsUse use = WS_HOST, cudaStream_t user = nullptr, int* lane_out = nullptr) {
   if (device < 0 || device >= MAX_DEVICES) return fail(INNR_EINVAL, "device index out of range");
   DeviceCtx& c = g_ctx[device];
   if (!c.ready) {
@@ -186,35 +220,40 @@ int ensure_ctx(int device, DeviceCtx** out, bool dev_entry = false, cudaStream_t
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c.device = device;
-    c.ws.num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c.ev0));
     CU(cudaEventCreate(&c.ev1));
-    CU(cudaEventCreateWithFlags(&c.ws_event, cudaEventDisableTiming));
-    // per-CTA partial lists: up to 8 CTAs/SM x 8 queries x 32 keys, or 1 query x 128 keys
-    // (the same buffers hold several query groups of one launch when the grid is small: scan_f32.cu, grid.y)
-    c.ws.partials_cap = (size_t)c.ws.num_sms * 8 * 8 * 32 * 4;
-    CU(cudaMalloc(&c.ws.partials, c.ws.partials_cap * sizeof(uint64_t)));
-    c.ws.group_cap = (size_t)(c.ws.num_sms * 8 / 32 + 2) * 8 * 128 * 4;
-    CU(cudaMalloc(&c.ws.group_partials, c.ws.group_cap * sizeof(uint64_t)));
-    c.ws.tickets_cap = 16384;
-    CU(cudaMalloc(&c.ws.tickets, c.ws.tickets_cap * sizeof(unsigned)));
-    CU(cudaMemset(c.ws.tickets, 0, c.ws.tickets_cap * sizeof(unsigned)));
-    CU(cudaMalloc(&c.ws.shared_thr, 64 * sizeof(unsigned long long)));
-    CU(cudaMemset(c.ws.shared_thr, 0xFF, 64 * sizeof(unsigned long long)));
+    for (int l = 0; l < 2; ++l) CU(cudaEventCreateWithFlags(&c.ws_event[l], cudaEventDisableTiming));
+    int rc = alloc_workspace(c.ws, prop.multiProcessorCount);
+    if (rc == INNR_OK) rc = alloc_workspace(c.ws_alt, prop.multiProcessorCount);
+    if (rc) return rc;
     c.h_pin.pinned = true;
     c.h_counts.pinned = true;
     c.ready = true;
   } else {
     CU(cudaSetDevice(device));
   }
-  // order this call after the last `_dev` call that is still using the workspace on another stream
-  if (dev_entry) {
-    if (c.ws_pending && c.ws_stream != user) CU(cudaStreamWaitEvent(user, c.ws_event, 0));
-  } else if (c.ws_pending) {
-    CU(cudaStreamWaitEvent(c.stream, c.ws_event, 0));
-    c.ws_pending = false;  // host-facing entries synchronise c.stream before they return
+  // order this call after the last `_dev` call that is still using the same lane on another stream
+  int lane = 0;
+  if (use == WS_DEV_SCAN) {
+    for (int l = 0; l < 2; ++l)
+      if (c.ws_pending[l] && cudaEventQuery(c.ws_event[l]) == cudaSuccess) c.ws_pending[l] = false;
+    cudaGetLastError();  // cudaErrorNotReady from the queries above is not an error
+    if (c.ws_pending[0] && c.ws_stream[0] == user) lane = 0;        // stream order already covers it
+    else if (c.ws_pending[1] && c.ws_stream[1] == user) lane = 1;
+    else if (!c.ws_pending[0]) lane = 0;
+    else if (!c.ws_pending[1]) lane = 1;
+    else lane = c.ws_seq[0] <= c.ws_seq[1] ? 0 : 1;                // both busy elsewhere: queue behind the older one
   }
+  if (use == WS_HOST) {
+    if (c.ws_pending[0]) {
+      CU(cudaStreamWaitEvent(c.stream, c.ws_event[0], 0));
+      c.ws_pending[0] = false;  // host-facing entries synchronise c.stream before they return
+    }
+  } else if (use != WS_NONE) {
+    if (c.ws_pending[lane] && c.ws_stream[lane] != user) CU(cudaStreamWaitEvent(user, c.ws_event[lane], 0));
+  }
+  if (lane_out) *lane_out = lane;
   *out = &c;
   return INNR_OK;
 }
@@ -223,11 +262,13 @@ int ensure_ctx(int device, DeviceCtx** out, bool dev_entry = false, cudaStream_t
 struct DevRelease {
   DeviceCtx& c;
   cudaStream_t s;
-  DevRelease(DeviceCtx& ctx, cudaStream_t stream) : c(ctx), s(stream) {}
+  int lane;
+  DevRelease(DeviceCtx& ctx, cudaStream_t stream, int lane_ = 0) : c(ctx), s(stream), lane(lane_) {}
   ~DevRelease() {
-    if (cudaEventRecord(c.ws_event, s) == cudaSuccess) {
-      c.ws_pending = true;
-      c.ws_stream = s;
+    if (cudaEventRecord(c.ws_event[lane], s) == cudaSuccess) {
+      c.ws_pending[lane] = true;
+      c.ws_stream[lane] = s;
+      c.ws_seq[lane] = ++c.seq;
     } else {
       cudaGetLastError();
     }
@@ -237,7 +278,9 @@ struct DevRelease {
 int current_ctx(DeviceCtx** out) { return ensure_ctx(cur_dev(), out); }
 
 int ctx_for(const innr_cuda_corpus* c, DeviceCtx** out) { return ensure_ctx(c->device, out); }
-int ctx_for_dev(const innr_cuda_corpus* c, DeviceCtx** out, cudaStream_t user) { return ensure_ctx(c->device, out, true, user); }
+int ctx_for_dev(const innr_cuda_corpus* c, DeviceCtx** out, cudaStream_t user, bool scan_only = false, int* lane = nullptr) {
+  return ensure_ctx(c->device, out, scan_only ? WS_DEV_SCAN : WS_DEV, user, lane);
+}
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
@@ -357,13 +400,11 @@ int innr_cuda_shutdown(void) {
     cudaSetDevice(i);
     cudaStreamSynchronize(c.stream);
     c.d_query.release(); c.d_keys.release(); c.d_scores.release(); c.d_aux.release(); c.d_tcws.release(); c.h_pin.release(); c.h_counts.release();
-    cudaFree(c.ws.partials);
-    cudaFree(c.ws.group_partials);
-    cudaFree(c.ws.tickets);
-    cudaFree(c.ws.shared_thr);
+    free_workspace(c.ws);
+    free_workspace(c.ws_alt);
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
-    cudaEventDestroy(c.ws_event);
+    for (int l = 0; l < 2; ++l) cudaEventDestroy(c.ws_event[l]);
     cudaStreamDestroy(c.stream);
     c = DeviceCtx();
   }
@@ -685,8 +726,15 @@ static int big_k_from_scores(DeviceCtx* ctx, const void* dev_scores, int kind, s
 
 // Writes min(k, n) keys per query at row stride `k` (k <= 128: the fused lists are sentinel-initialised, so the rows come
 // out sentinel-padded to k by themselves; k > 128: the caller pre-fills dev_keys with sentinels when k > n).
+static bool knn_takes_tc_filter(const innr_cuda_corpus* c, const PdxView& v, int mode, size_t nq, size_t k) {
+  return g_opt.knn_tc && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries && knn_tc_supported(v, mode, nq, k);
+}
+// the plain fused scan (k <= 128, no tensor-core filter) needs a Workspace and nothing else: either lane will do
+static bool knn_is_scan_only(const innr_cuda_corpus* c, int mode, size_t nq, size_t k) {
+  return k <= MAX_FUSED_K && !knn_takes_tc_filter(c, pdx_view(c), mode, nq, k);
+}
 static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const float* dev_queries, size_t nq, size_t k,
-                        uint64_t* dev_keys, cudaStream_t s) {
+                        uint64_t* dev_keys, cudaStream_t s, int lane = 0) {
   PdxView v = pdx_view(c);
   if (k > MAX_FUSED_K) {
     const size_t kk = k < c->n ? k : c->n;
@@ -699,12 +747,12 @@ static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const flo
     }
     return INNR_OK;
   }
-  if (g_opt.knn_tc && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries && knn_tc_supported(v, mode, nq, k)) {
+  const bool tc = knn_takes_tc_filter(c, v, mode, nq, k);
+  if (tc) {
     int rc = knn_tc_prepare(c, ctx, v, s);
     if (rc) return rc;
   }
-  if (g_opt.knn_tc && c->tc_state == 1 && c->n >= g_opt.knn_tc_min_n && nq >= g_opt.knn_tc_min_queries &&
-      knn_tc_supported(v, mode, nq, k)) {
+  if (tc && c->tc_state == 1) {
     CU(ctx->d_tcws.reserve(knn_tc_workspace_bytes(c->n, c->d, nq, k)));
     CU(ctx->h_counts.reserve(nq * sizeof(unsigned)));
     std::vector<unsigned> overflow;
@@ -719,7 +767,7 @@ static int knn_keys_dev(innr_cuda_corpus* c, DeviceCtx* ctx, int mode, const flo
       CU(launch_pdx_knn(v, mode, dev_queries + (size_t)q * c->d, 1, k, dev_keys + (size_t)q * k, ctx->ws, s, &g_launches));
     return INNR_OK;
   }
-  CU(launch_pdx_knn(v, mode, dev_queries, nq, k, dev_keys, ctx->ws, s, &g_launches));
+  CU(launch_pdx_knn(v, mode, dev_queries, nq, k, dev_keys, ctx->lane_ws(tc ? 0 : lane), s, &g_launches));
   return INNR_OK;
 }
 
@@ -1139,14 +1187,15 @@ int innr_cuda_batch_knn_keys_dev(const innr_cuda_corpus* c, int metric, const fl
   EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   DeviceCtx* ctx;
-  rc = ctx_for_dev(c, &ctx, s);
+  int lane = 0;
+  rc = ctx_for_dev(c, &ctx, s, knn_is_scan_only(c, mode, n_queries, k), &lane);
   if (rc) return rc;
-  DevRelease rel(*ctx, s);
+  DevRelease rel(*ctx, s, lane);
   if (c->n == 0) {  // rows are n_queries x k, sentinel-padded (header contract)
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  return knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, dev_queries, n_queries, k, dev_keys, s);
+  return knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, dev_queries, n_queries, k, dev_keys, s, lane);
 }
 
 int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t n_queries, size_t k, int metric,
@@ -1160,10 +1209,17 @@ int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t
   EntryGuard lk(device);
   cudaStream_t us = (cudaStream_t)stream;
   DeviceCtx* ctx;
-  int rc = ensure_ctx(device, &ctx, true, us);
+  if (k <= MAX_FUSED_K) {  // one launch, no workspace and no scratch: nothing to order against
+    int rc = ensure_ctx(device, &ctx, WS_NONE, us);
+    if (rc) return rc;
+    CU(launch_merge_keys(dev_keys_in, n_lists, n_queries, k, metric != INNR_METRIC_L2, dev_keys_out, dev_idx, dev_score,
+                         us, &g_launches));
+    return INNR_OK;
+  }
+  int rc = ensure_ctx(device, &ctx, WS_DEV, us);
   if (rc) return rc;
   DevRelease rel(*ctx, us);
-  if (k > MAX_FUSED_K) {
+  {
     uint64_t* keys_out = dev_keys_out;
     if (!keys_out) {
       CU(ctx->d_tcws.reserve(n_queries * k * sizeof(uint64_t)));
@@ -1173,9 +1229,6 @@ int innr_cuda_merge_keys_dev(const uint64_t* dev_keys_in, size_t n_lists, size_t
                              ctx->ws, (cudaStream_t)stream, &g_launches));
     return INNR_OK;
   }
-  CU(launch_merge_keys(dev_keys_in, n_lists, n_queries, k, metric != INNR_METRIC_L2, dev_keys_out, dev_idx, dev_score,
-                       (cudaStream_t)stream, &g_launches));
-  return INNR_OK;
 }
 
 int innr_cuda_topk_from_distances(const float* distances, size_t n, size_t k, uint32_t* out_id, float* out_distance,
@@ -1443,9 +1496,9 @@ int innr_cuda_binary_topk(const innr_cuda_corpus* c, int op, const uint64_t* que
 }
 
 static int hamming_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const uint64_t* dev_query_words, size_t nq, size_t k,
-                        uint64_t* dev_keys, cudaStream_t s) {
+                        uint64_t* dev_keys, cudaStream_t s, int lane = 0) {
   if (k <= MAX_FUSED_K) {
-    CU(launch_hamming_topk(bin_view(c), dev_query_words, nq, k, dev_keys, ctx->ws, s, &g_launches));
+    CU(launch_hamming_topk(bin_view(c), dev_query_words, nq, k, dev_keys, ctx->lane_ws(lane), s, &g_launches));
     return INNR_OK;
   }
   const size_t kk = k < c->n ? k : c->n;  // rows stay k wide, sentinel-padded
@@ -1507,14 +1560,15 @@ int innr_cuda_hamming_topk_keys_dev(const innr_cuda_corpus* c, const uint64_t* d
   EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   DeviceCtx* ctx;
-  int rc = ctx_for_dev(c, &ctx, s);
+  int lane = 0;
+  int rc = ctx_for_dev(c, &ctx, s, k <= MAX_FUSED_K, &lane);
   if (rc) return rc;
-  DevRelease rel(*ctx, s);
+  DevRelease rel(*ctx, s, lane);
   if (c->n == 0 || c->words == 0) {
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  return hamming_keys(c, ctx, dev_query_words, n_queries, k, dev_keys, s);
+  return hamming_keys(c, ctx, dev_query_words, n_queries, k, dev_keys, s, lane);
 }
 
 int innr_cuda_encode_binary(const float* values, size_t n, float threshold, uint64_t* out_words) {
@@ -1678,9 +1732,9 @@ int innr_cuda_asymmetric_dot_u8_all(const innr_cuda_corpus* c, const float* quer
 }
 
 static int u8_keys(const innr_cuda_corpus* c, DeviceCtx* ctx, const float* dev_queries, size_t nq, size_t k,
-                   uint64_t* dev_keys, cudaStream_t s) {
+                   uint64_t* dev_keys, cudaStream_t s, int lane = 0) {
   if (k <= MAX_FUSED_K) {
-    CU(launch_u8_knn(u8_view(c), dev_queries, nq, k, dev_keys, ctx->ws, s, &g_launches));
+    CU(launch_u8_knn(u8_view(c), dev_queries, nq, k, dev_keys, ctx->lane_ws(lane), s, &g_launches));
     return INNR_OK;
   }
   const size_t kk = k < c->n ? k : c->n;  // rows stay k wide, sentinel-padded
@@ -1729,14 +1783,15 @@ int innr_cuda_batch_knn_u8_keys_dev(const innr_cuda_corpus* c, const float* dev_
   EntryGuard lk(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   DeviceCtx* ctx;
-  int rc = ctx_for_dev(c, &ctx, s);
+  int lane = 0;
+  int rc = ctx_for_dev(c, &ctx, s, k <= MAX_FUSED_K, &lane);
   if (rc) return rc;
-  DevRelease rel(*ctx, s);
+  DevRelease rel(*ctx, s, lane);
   if (c->n == 0 || c->d == 0) {
     CU(cudaMemsetAsync(dev_keys, 0xFF, n_queries * k * sizeof(uint64_t), s));
     return INNR_OK;
   }
-  return u8_keys(c, ctx, dev_queries, n_queries, k, dev_keys, s);
+  return u8_keys(c, ctx, dev_queries, n_queries, k, dev_keys, s, lane);
 }
 
 // ------------------------------------------------------------------------------------------ ternary codes
@@ -2263,7 +2318,7 @@ int innr_cuda_exchange_merge_dev(innr_cuda_exchange* x, const uint64_t* dev_loca
   if (!dev_local_keys) return fail(INNR_EINVAL, "null argument");
   EntryGuard lk(x->device);
   DeviceCtx* ctx;
-  int rc = ensure_ctx(x->device, &ctx, true, (cudaStream_t)stream);
+  int rc = ensure_ctx(x->device, &ctx, WS_NONE, (cudaStream_t)stream);  // mailboxes only: no workspace, no scratch
   if (rc) return rc;
   ++x->calls;
   CU(launch_exchange_merge(ex_view(x), dev_local_keys, n_queries, k, x->calls, publish_only, metric != INNR_METRIC_L2,

@@ -186,7 +186,7 @@ class ShardedKnn:
                None, C.c_void_p(b["idx"].data_ptr()), C.c_void_p(b["score"].data_ptr()), stream)
         return b["idx"].view(nq, k), b["score"].view(nq, k)
 
-    # ---- pipelined form: the exchange of query i runs on a side stream under the scan of query i + 1 ------------------
+    # ---- pipelined form: consecutive scans overlap, the exchange of query i runs under the scan of query i + 1 ---------
     def _keys(self, dev_queries, nq, k, local, stream):
         qp, lp = C.c_void_p(dev_queries.data_ptr()), C.c_void_p(local.data_ptr())
         if self.kind == "f32":
@@ -197,42 +197,66 @@ class ShardedKnn:
             L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
 
     def knn_dev_pipelined(self, dev_queries, nq: int, k: int):
-        """Throughput form of knn_dev for a stream of queries. The exchange is a barrier between the ranks: done on the
-        scan's stream it adds its own latency AND the ranks' per-step skew to every step. Here the shard scan of this
-        call is queued on torch's current stream and its exchange + merge on a high-priority side stream (one CTA; it
-        finds a free slot next to the next scan's CTAs), so consecutive calls overlap and a rank only ever waits for
-        data that is two calls old. Returns (idx, score, event): the tensors are valid once `event` has completed
+        """Throughput form of knn_dev for a stream of independent queries. Two things overlap here that knn_dev serialises:
+
+        * consecutive shard scans. They alternate between two scan streams (the library keeps two workspaces per device
+          for exactly this, api.cu `lane`), so the CTAs of scan i + 1 fill the SMs as the last CTAs of scan i retire and
+          while its merge runs: the ramp at both ends of a launch -- 4 % (f32) to 10 % (Hamming) of a 1/8-corpus shard
+          scan -- disappears;
+        * scan and exchange. The exchange is a barrier between the ranks: on the scan's stream it adds its latency AND
+          the ranks' per-step skew to every step. Here it is queued on a high-priority side stream (one CTA; it finds a
+          slot next to the next scan's CTAs), so a rank only ever waits for data that is two calls old.
+
+        The scan streams first wait for everything queued so far on torch's current stream (the queries may have been
+        produced there). Returns (idx, score, event): the tensors are valid once `event` has completed
         (`torch.cuda.current_stream().wait_event(event)` or `drain()`); they are reused by the call after next.
-        Falls back to knn_dev (event None) without a peer exchange or for requests that do not fit its mailboxes."""
+        Without a peer exchange at world > 1 (NCCL route), or for requests that do not fit the mailboxes, falls back to
+        knn_dev (event None)."""
         t = self.torch
-        if self.exchange is None or not self.exchange.fits(nq, k):
+        if (self.exchange is None and self.world > 1) or (self.exchange is not None and not self.exchange.fits(nq, k)) \
+                or k > 128:
             idx, sc = self.knn_dev(dev_queries, nq, k)
             return idx, sc, None
         key = ("pipe", nq, k)
         if key not in self._bufs:
             dev = dev_queries.device
             mk = lambda dt: t.empty(nq * k, dtype=dt, device=dev)  # noqa: E731
-            self._bufs[key] = {"slots": [dict(local=mk(t.int64), idx=mk(t.int64),
+            self._bufs[key] = {"slots": [dict(local=mk(t.int64), idx=mk(t.int64), keys=mk(t.int64),
                                               score=mk(t.float32 if self.kind != "binary" else t.int32),
-                                              scan_done=t.cuda.Event(), ex_done=t.cuda.Event(), used=False) for _ in range(2)],
+                                              scan_done=t.cuda.Event(), ex_done=t.cuda.Event(), ready=t.cuda.Event(),
+                                              used=False) for _ in range(2)],
                                "calls": 0}
             if getattr(self, "_ex_stream", None) is None:
                 self._ex_stream = t.cuda.Stream(device=dev, priority=-1)
+                self._scan_streams = [t.cuda.Stream(device=dev), t.cuda.Stream(device=dev)]
         st = self._bufs[key]
-        slot = st["slots"][st["calls"] & 1]
+        parity = st["calls"] & 1
+        slot = st["slots"][parity]
         st["calls"] += 1
-        main = t.cuda.current_stream()
+        scan = self._scan_streams[parity]
+        slot["ready"].record(t.cuda.current_stream())
+        scan.wait_event(slot["ready"])
         if slot["used"]:
-            main.wait_event(slot["ex_done"])   # the exchange of two calls ago has read `local` (long done)
-        self._keys(dev_queries, nq, k, slot["local"], C.c_void_p(main.cuda_stream))
-        slot["scan_done"].record(main)
+            scan.wait_event(slot["ex_done"])   # the exchange of two calls ago has read `local` (long done)
+        self._keys(dev_queries, nq, k, slot["local"], C.c_void_p(scan.cuda_stream))
+        m = L.METRIC_L2 if (self.kind == "binary" or (self.kind == "f32" and self.metric == "l2")) else L.METRIC_DOT
+        if self.exchange is None:  # one rank: decode the list behind the scan, on the scan's stream
+            L.call("innr_cuda_merge_keys_dev", C.c_void_p(slot["local"].data_ptr()), 1, nq, k, m,
+                   C.c_void_p(slot["keys"].data_ptr()), C.c_void_p(slot["idx"].data_ptr()),
+                   None if self.kind == "binary" else C.c_void_p(slot["score"].data_ptr()), C.c_void_p(scan.cuda_stream))
+            if self.kind == "binary":  # the distance is the high half of the key itself
+                with t.cuda.stream(scan):
+                    slot["score"].copy_(slot["keys"] >> 32)
+            slot["ex_done"].record(scan)
+            slot["used"] = True
+            return slot["idx"].view(nq, k), slot["score"].view(nq, k), slot["ex_done"]
+        slot["scan_done"].record(scan)
         ex = self._ex_stream
         ex.wait_event(slot["scan_done"])
         exs = C.c_void_p(ex.cuda_stream)
         if self.kind == "binary":
-            self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, L.METRIC_L2, exs, idx=slot["idx"], dist_out=slot["score"])
+            self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, m, exs, idx=slot["idx"], dist_out=slot["score"])
         else:
-            m = L.METRIC_L2 if (self.kind == "f32" and self.metric == "l2") else L.METRIC_DOT
             self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, m, exs, idx=slot["idx"], score=slot["score"])
         slot["ex_done"].record(ex)
         slot["used"] = True

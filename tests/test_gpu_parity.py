@@ -1077,6 +1077,106 @@ def test_dev_entries_on_different_streams_do_not_share_the_workspace_unordered(i
             assert (keys & np.uint64(0xFFFFFFFF)).tolist() == want[j][0][0].tolist(), (rep, j)
 
 
+def test_two_lanes_overlapping_scans_of_every_kind(ib, oracle):
+    """The fused k <= 128 scans of `_dev` entries may take either of the device's two workspaces (api.cu lanes), so
+    independent scans on two caller streams really run concurrently. Every overlapped result must equal the one the
+    same call gives alone -- whole 64-bit keys, every kind, 3 streams (more streams than lanes), a host-facing call and a
+    lane-0-only call (k > 128) in between."""
+    import ctypes as C
+    import torch
+    from innr_b200 import _lib as L
+    n, d = 400_000, 96
+    rows = rand_rows(n, d, 31)
+    qs = rand_rows(6, d, 32)
+    db = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    rng = np.random.default_rng(33)
+    codes = rng.integers(0, 2**63, size=(n, 4), dtype=np.int64).view(np.uint64)
+    bc = ib.BinaryCorpus.from_words(codes.reshape(-1), n, 256)
+    qw = rng.integers(0, 2**63, size=(6, 4), dtype=np.int64)
+    u8rows = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    uc = ib.U8Corpus.from_rows(u8rows, ib.QuantizationParams(0.01, -1.0))
+    dq, dqw = torch.from_numpy(qs).cuda(), torch.from_numpy(qw).cuda()
+
+    def f32(j, out, st, k=10):
+        L.call("innr_cuda_batch_knn_keys_dev", db.h, L.METRIC_COSINE, C.c_void_p(dq[j].data_ptr()), 1, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    def ham(j, out, st, k=100):
+        L.call("innr_cuda_hamming_topk_keys_dev", bc.h, C.c_void_p(dqw[j].data_ptr()), 1, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    def u8(j, out, st, k=10):
+        L.call("innr_cuda_batch_knn_u8_keys_dev", uc.h, C.c_void_p(dq[j].data_ptr()), 1, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    kinds = [(f32, 10), (ham, 100), (u8, 10)]
+    main = torch.cuda.current_stream()
+    alone = {}
+    for fn, k in kinds:
+        for j in range(6):
+            out = torch.empty(k, dtype=torch.int64, device="cuda")
+            fn(j, out, main)
+            torch.cuda.synchronize()
+            alone[(fn, j)] = out.cpu().numpy().copy()
+    big_alone = torch.empty(200, dtype=torch.int64, device="cuda")
+    f32(0, big_alone, main, k=200)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    for rep in range(15):
+        outs = []
+        for i in range(18):
+            fn, k = kinds[i % len(kinds)]
+            j = (i + rep) % 6
+            out = torch.empty(k, dtype=torch.int64, device="cuda")
+            fn(j, out, streams[i % 3])
+            outs.append((fn, j, out))
+            if i == 7:   # k > 128 takes the scores pass + selection: lane 0 and the scratch buffers
+                big = torch.empty(200, dtype=torch.int64, device="cuda")
+                f32(0, big, streams[1], k=200)
+            if i == 11:  # a host-facing call right in the middle
+                host = ib.batch_knn_many("cosine", qs[2], db, 10)
+        torch.cuda.synchronize()
+        for fn, j, out in outs:
+            assert np.array_equal(out.cpu().numpy(), alone[(fn, j)]), (rep, fn.__name__, j)
+        assert np.array_equal(big.cpu().numpy(), big_alone.cpu().numpy())
+        assert (alone[(f32, 2)].view(np.uint64) & np.uint64(0xFFFFFFFF)).tolist() == host[0][0].tolist()
+
+
+def test_pipelined_single_rank_matches_knn_dev(ib):
+    """ShardedKnn.knn_dev_pipelined on one rank (no exchange): scans alternate between two streams and the decode runs
+    behind each; a run of different queries gives what knn_dev gives for each."""
+    import torch
+    from innr_b200 import sharded
+    n, d = 300_000, 64
+    rows = rand_rows(n, d, 41)
+    qs = rand_rows(8, d, 42)
+    db = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    rng = np.random.default_rng(43)
+    bc = ib.BinaryCorpus.from_words(rng.integers(0, 2**63, size=n * 4, dtype=np.int64).view(np.uint64), n, 256)
+    qw = torch.from_numpy(rng.integers(0, 2**63, size=(8, 4), dtype=np.int64)).cuda()
+    dq = torch.from_numpy(qs).cuda()
+    for sk, q, k in ((sharded.ShardedKnn(db, "f32", "cosine"), dq, 10), (sharded.ShardedKnn(db, "f32", "l2"), dq, 10),
+                     (sharded.ShardedKnn(bc, "binary"), qw, 100)):
+        want = []
+        for j in range(8):
+            idx, sc = sk.knn_dev(q[j], 1, k)
+            want.append((idx.cpu().numpy().copy(), sc.cpu().numpy().copy()))
+        got = []
+        for j in range(8):
+            idx, sc, ev = sk.knn_dev_pipelined(q[j], 1, k)
+            assert ev is not None
+            ev.synchronize()   # results are reused by the call after next: read them now
+            got.append((idx.cpu().numpy().copy(), sc.cpu().numpy().copy()))
+        for j in range(8):
+            assert np.array_equal(got[j][0], want[j][0]) and np.array_equal(bits(got[j][1]), bits(want[j][1])), (sk.kind, j)
+        # and without reading in between (the steady state of a throughput loop): the last two results are intact
+        for j in range(8):
+            last = sk.knn_dev_pipelined(q[j], 1, k)
+        sk.drain()
+        torch.cuda.synchronize()
+        assert np.array_equal(last[0].cpu().numpy(), want[7][0])
+
+
 def test_entries_leave_the_current_device_alone(ib):
     import torch
     before = torch.cuda.current_device()
