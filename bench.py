@@ -387,7 +387,9 @@ class KnnF32(Workload):
         return ((x >> np.uint64(33)).astype(np.float32) / np.float32(2**31) * np.float32(2.0) - np.float32(1.0)).astype(np.float32)
 
     def step_dev(self, i):
-        return self.sk.knn_dev_pipelined(self.q_dev[i % self.q_dev.shape[0]], self.nq, self.k)
+        # C1's step is bound by the host's launch rate (one 30 us launch): keep its scans on one stream
+        return self.sk.knn_dev_pipelined(self.q_dev[i % self.q_dev.shape[0]], self.nq, self.k,
+                                         overlap_scans=self.workload != "batch_demo")
 
     def step_e2e(self, i):
         if self.world == 1:  # the C-ABI call with host buffers (pinned query; keys come back through pinned staging)
@@ -844,7 +846,7 @@ def measure(w, args, env):
         }
         if batch:
             entry["query_batch"] = batch
-        if getattr(w, "sk", None) is not None and w.workload != "knn_cosine_multi":
+        if getattr(w, "sk", None) is not None and w.workload not in ("knn_cosine_multi", "batch_demo"):
             entry["step_overlap"] = ("device-resident steps are independent queries: their scans alternate between two streams "
                                      "(two workspaces per device), so the head of scan i+1 fills the SMs under the tail and the "
                                      "merge of scan i; roofline.kernel_ms is the same launch back to back on ONE stream")

@@ -62,7 +62,8 @@ int innr_cuda_dense_backend(size_t len, int* out_is_cuda);
 /* Tuning knobs (process-wide). Names: "knn_tc" (1/0: tensor-core filter path for large dot/cosine query batches),
  * "knn_tc_min_n" (corpus size from which it is used, default 100000), "knn_tc_min_queries" (default 2; 1 sends single queries through the filter too),
  * "maxsim_tc" (1/0: tcgen05 MaxSim when dim <= 128 is a multiple of 4), "u8_scaled_chains" (1/0: PRMT + FFMA2
- * chains scaled by 2^-23 in the u8 scan when the query allows it). Results never depend on them. */
+ * chains scaled by 2^-23 in the u8 scan when the query allows it), "kernel_timing" (1/0, default 0: host-facing calls
+ * bracket their kernels with timed CUDA events for innr_cuda_last_kernel_ms). Results never depend on them. */
 int innr_cuda_set_option(const char* name, double value);
 /* Statistics of the most recent batch_knn call that went through the tensor-core filter (csrc/knn_tc.cu): time of the
  * whole-corpus filter pass and of the whole device-side call (CUDA events), flops issued by that pass, number of
@@ -322,8 +323,9 @@ int innr_cuda_hamming_topk_sharded(const innr_cuda_corpus* const* shards, size_t
 int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
                                    size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
                                    size_t* out_count);
-/* ---- timing hook for bench.py: average device time (ms) of the last call's dominant kernel, measured with
- *      CUDA events on the launching stream ---------------------------------------------------------- */
+/* ---- timing hook: device time (ms) of the last host-facing call's kernels, measured with CUDA events on the
+ *      launching stream. Off by default (the two timed event records cost a short call ~15 us): enable with
+ *      innr_cuda_set_option("kernel_timing", 1); 0 until then. ------------------------------------------------- */
 int innr_cuda_last_kernel_ms(float* out_ms);
 
 #ifdef __cplusplus

@@ -122,6 +122,7 @@ struct Options {
   size_t knn_tc_min_n = 100000;
   size_t knn_tc_min_queries = 2;  // measured at 10M x 768: filter call 2.6 ms for 2..64 queries, 8-query scan pass 6.3 ms
   bool maxsim_tc = true;
+  bool kernel_timing = false;
 } g_opt;
 
 // One mutex per device: calls on different GPUs run concurrently from different host threads (one stream + one
@@ -291,9 +292,11 @@ int check_index_range(size_t n, uint64_t index_base) {
 
 struct Timed {  // records the device time of the kernels launched in its scope
   DeviceCtx& c;
-  explicit Timed(DeviceCtx& ctx) : c(ctx) { cudaEventRecord(c.ev0, c.stream); }
-  void stop() { cudaEventRecord(c.ev1, c.stream); }
-  void finish() { cudaEventElapsedTime(&c.last_ms, c.ev0, c.ev1); }
+  // off unless innr_cuda_set_option("kernel_timing", 1): the two timed event records cost a 70 us call 15 us
+  bool on;
+  explicit Timed(DeviceCtx& ctx) : c(ctx), on(g_opt.kernel_timing) { if (on) cudaEventRecord(c.ev0, c.stream); }
+  void stop() { if (on) cudaEventRecord(c.ev1, c.stream); }
+  void finish() { if (on) cudaEventElapsedTime(&c.last_ms, c.ev0, c.ev1); }
 };
 
 // decode sorted composite keys on the host
@@ -358,9 +361,10 @@ TokView tok_view(const innr_cuda_corpus* c) {
 
 // Shared tail of every host-facing top-k call: keys device -> pinned -> decode.
 template <class Decode>
-int fetch_keys(DeviceCtx& ctx, size_t nq, size_t kk, Timed& tm, Decode decode) {
+int fetch_keys(DeviceCtx& ctx, size_t nq, size_t kk, Timed& tm, Decode decode, bool already_on_host = false) {
   CU(ctx.h_pin.reserve(nq * kk * sizeof(uint64_t)));
-  CU(cudaMemcpyAsync(ctx.h_pin.p, ctx.d_keys.p, nq * kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.stream));
+  if (!already_on_host)
+    CU(cudaMemcpyAsync(ctx.h_pin.p, ctx.d_keys.p, nq * kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx.stream));
   CU(cudaStreamSynchronize(ctx.stream));
   tm.finish();
   decode((const uint64_t*)ctx.h_pin.p);
@@ -427,6 +431,7 @@ int innr_cuda_set_option(const char* name, double value) {
   else if (n == "knn_tc_min_n") g_opt.knn_tc_min_n = (size_t)value;
   else if (n == "knn_tc_min_queries") g_opt.knn_tc_min_queries = (size_t)value;
   else if (n == "maxsim_tc") g_opt.maxsim_tc = value != 0;
+  else if (n == "kernel_timing") g_opt.kernel_timing = value != 0;
   else if (n == "u8_scaled_chains") u8_set_scaled_chains(value != 0);
   else return fail(INNR_EINVAL, "unknown option: " + n);
   return INNR_OK;
@@ -831,15 +836,19 @@ int innr_cuda_batch_knn(const innr_cuda_corpus* c, int metric, const float* quer
   CU(ctx->d_keys.reserve(n_queries * kk * sizeof(uint64_t)));
   if (c->d)
     CU(cudaMemcpyAsync(ctx->d_query.p, queries, n_queries * c->d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  // small results: the finishing CTA stores the keys straight into pinned host memory (mapped under UVA), which saves
+  // the device-to-host copy's own launch
+  const bool mapped = n_queries * kk * sizeof(uint64_t) <= (64u << 10) && knn_is_scan_only(c, mode, n_queries, kk);
+  if (mapped) CU(ctx->h_pin.reserve(n_queries * kk * sizeof(uint64_t)));
   Timed tm(*ctx);
   rc = knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, (const float*)ctx->d_query.p, n_queries, kk,
-                    (uint64_t*)ctx->d_keys.p, ctx->stream);
+                    (uint64_t*)(mapped ? ctx->h_pin.p : ctx->d_keys.p), ctx->stream);
   if (rc) return rc;
   tm.stop();
   rc = fetch_keys(*ctx, n_queries, kk, tm, [&](const uint64_t* keys) {
     for (size_t q = 0; q < n_queries; ++q)
       decode_keys_f32(keys + q * kk, kk, metric != INNR_METRIC_L2, out_idx + q * k, out_score + q * k);
-  });
+  }, mapped);
   if (rc) return rc;
   if (out_count) *out_count = kk;
   return INNR_OK;

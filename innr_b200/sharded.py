@@ -196,7 +196,7 @@ class ShardedKnn:
         else:
             L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
 
-    def knn_dev_pipelined(self, dev_queries, nq: int, k: int):
+    def knn_dev_pipelined(self, dev_queries, nq: int, k: int, overlap_scans: bool = True):
         """Throughput form of knn_dev for a stream of independent queries. Two things overlap here that knn_dev serialises:
 
         * consecutive shard scans. They alternate between two scan streams (the library keeps two workspaces per device
@@ -211,10 +211,12 @@ class ShardedKnn:
         produced there). Returns (idx, score, event): the tensors are valid once `event` has completed
         (`torch.cuda.current_stream().wait_event(event)` or `drain()`); they are reused by the call after next.
         Without a peer exchange at world > 1 (NCCL route), or for requests that do not fit the mailboxes, falls back to
-        knn_dev (event None)."""
+        knn_dev (event None). `overlap_scans=False` keeps the scans on torch's current stream (only the exchange moves
+        to the side stream): fewer host calls per step, the better choice when a scan is so short that the step is bound
+        by the host's launch rate (BASELINE C1: a 5 MB corpus)."""
         t = self.torch
-        if (self.exchange is None and self.world > 1) or (self.exchange is not None and not self.exchange.fits(nq, k)) \
-                or k > 128:
+        if (self.exchange is None and (self.world > 1 or not overlap_scans)) \
+                or (self.exchange is not None and not self.exchange.fits(nq, k)) or k > 128:
             idx, sc = self.knn_dev(dev_queries, nq, k)
             return idx, sc, None
         key = ("pipe", nq, k)
@@ -233,9 +235,12 @@ class ShardedKnn:
         parity = st["calls"] & 1
         slot = st["slots"][parity]
         st["calls"] += 1
-        scan = self._scan_streams[parity]
-        slot["ready"].record(t.cuda.current_stream())
-        scan.wait_event(slot["ready"])
+        if overlap_scans:
+            scan = self._scan_streams[parity]
+            slot["ready"].record(t.cuda.current_stream())
+            scan.wait_event(slot["ready"])
+        else:
+            scan = t.cuda.current_stream()
         if slot["used"]:
             scan.wait_event(slot["ex_done"])   # the exchange of two calls ago has read `local` (long done)
         self._keys(dev_queries, nq, k, slot["local"], C.c_void_p(scan.cuda_stream))
