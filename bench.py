@@ -395,10 +395,10 @@ class KnnF32(Workload):
         if self.world == 1:  # the C-ABI call with host buffers (pinned query; keys come back through pinned staging)
             import innr_b200 as ib
             return ib.batch_knn_many(self.metric, self.q_host[i % self.q_host.shape[0]], self.shard, self.k)
+        # N > 1: pinned query in, pinned result out, streamed (results one call late, one host sync per batch of calls)
         q = self.q_host_t[i % self.q_host_t.shape[0]]
-        dq = q.to(self.dev, non_blocking=True)
-        idx, sc = self.sk.knn_dev(dq, self.nq, self.k)
-        return self.fetch(idx, sc)
+        return self.sk.knn_dev_pipelined(None, self.nq, self.k, overlap_scans=self.workload != "batch_demo",
+                                         host_queries=q, host_out=True)
 
     def keys_entry(self, L, q, b, stream):
         L.call("innr_cuda_batch_knn_keys_dev", self.shard.h, self.sk._metric_id, C.c_void_p(q.data_ptr()), self.nq, self.k,
@@ -464,9 +464,7 @@ class Hamming(Workload):
         if self.world == 1:
             import innr_b200 as ib
             return ib.hamming_topk_many(self.q_host[i % 16].view(np.uint64).reshape(1, -1), self.shard, self.k)
-        dq = self.q_host_t[i % 16].to(self.dev, non_blocking=True)
-        idx, ds = self.sk.knn_dev(dq, 1, self.k)
-        return self.fetch(idx, ds)
+        return self.sk.knn_dev_pipelined(None, 1, self.k, host_queries=self.q_host_t[i % 16], host_out=True)
 
     def keys_entry(self, L, q, b, stream):
         L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, C.c_void_p(q.data_ptr()), self.nq, self.k,
@@ -533,9 +531,7 @@ class U8(Workload):
         if self.world == 1:
             import innr_b200 as ib
             return ib.batch_knn_u8_many(self.q_host[i % 16].reshape(1, -1), self.shard, self.k)
-        dq = self.q_host_t[i % 16].to(self.dev, non_blocking=True)
-        idx, sc = self.sk.knn_dev(dq, 1, self.k)
-        return self.fetch(idx, sc)
+        return self.sk.knn_dev_pipelined(None, 1, self.k, host_queries=self.q_host_t[i % 16], host_out=True)
 
     def keys_entry(self, L, q, b, stream):
         L.call("innr_cuda_batch_knn_u8_keys_dev", self.shard.h, C.c_void_p(q.data_ptr()), self.nq, self.k,
@@ -839,7 +835,10 @@ def measure(w, args, env):
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": dtype_of(w.workload), "data": "synthetic",
             "config": config_of(w.workload, args.scale, world, args.queries),
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
+                    "mode": ("one synchronous host-buffer C-ABI call per step" if world == 1 or getattr(w, "sk", None) is None
+                             else "streamed per rank: pinned query H2D -> shard scan -> peer exchange -> D2H into pinned "
+                                  "buffers, double-buffered, one host synchronisation after the last step")},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "clocks": clocks,

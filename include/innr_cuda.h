@@ -21,8 +21,15 @@
  *  - Indices: `index_base` is added to local row numbers so a row-sharded corpus reports global
  *    indices; global indices must be < 2^32 - 1 (the reference truncates ids to u32 at
  *    src/batch.rs:403).
- *  - Thread safety: a corpus handle is immutable after upload. Calls are serialised per device by an
- *    internal mutex (one stream + one workspace per device).
+ *  - Thread safety: a corpus handle is immutable after upload. The host side of every call is serialised per
+ *    device by an internal mutex; calls on different devices run concurrently from different threads.
+ *  - Stream ordering of `_dev` entries: they enqueue on the CALLER's stream and return while the work is in
+ *    flight. Each device has two internal workspaces. The fused k <= 128 scans (`*_keys_dev` without the
+ *    tensor-core filter) need only a workspace and may take either, so two such calls on two streams overlap
+ *    on the device; every other `_dev` call and every host-facing call uses the first workspace plus the
+ *    scratch buffers. The library orders users of the same workspace with events: a call never observes
+ *    another call's partial state, whatever streams the caller uses. Inputs and outputs follow the usual
+ *    CUDA rule: they belong to the stream they were passed with until that stream has run the call.
  */
 #ifndef INNR_CUDA_H
 #define INNR_CUDA_H

@@ -196,7 +196,8 @@ class ShardedKnn:
         else:
             L.call("innr_cuda_hamming_topk_keys_dev", self.shard.h, qp, nq, k, lp, stream)
 
-    def knn_dev_pipelined(self, dev_queries, nq: int, k: int, overlap_scans: bool = True):
+    def knn_dev_pipelined(self, dev_queries, nq: int, k: int, overlap_scans: bool = True, host_queries=None,
+                          host_out: bool = False):
         """Throughput form of knn_dev for a stream of independent queries. Two things overlap here that knn_dev serialises:
 
         * consecutive shard scans. They alternate between two scan streams (the library keeps two workspaces per device
@@ -213,15 +214,26 @@ class ShardedKnn:
         Without a peer exchange at world > 1 (NCCL route), or for requests that do not fit the mailboxes, falls back to
         knn_dev (event None). `overlap_scans=False` keeps the scans on torch's current stream (only the exchange moves
         to the side stream): fewer host calls per step, the better choice when a scan is so short that the step is bound
-        by the host's launch rate (BASELINE C1: a 5 MB corpus)."""
+        by the host's launch rate (BASELINE C1: a 5 MB corpus).
+
+        Host-buffer streaming: `host_queries` (a PINNED torch tensor; dev_queries is then ignored) is copied to the
+        device on torch's current stream in front of the scan, and with `host_out=True` the results are copied into
+        pinned host tensors behind the merge, on its stream -- the returned (idx, score) are then those HOST tensors,
+        complete when `event` is. One host synchronisation per batch of calls instead of one per call."""
         t = self.torch
+        if host_queries is not None and ((self.exchange is None and self.world > 1) or k > 128
+                                         or (self.exchange is not None and not self.exchange.fits(nq, k))):
+            dev_queries = host_queries.to(f"cuda:{t.cuda.current_device()}", non_blocking=True)
+            host_queries = None
         if (self.exchange is None and (self.world > 1 or not overlap_scans)) \
                 or (self.exchange is not None and not self.exchange.fits(nq, k)) or k > 128:
             idx, sc = self.knn_dev(dev_queries, nq, k)
+            if host_out:
+                idx, sc = idx.cpu(), sc.cpu()
             return idx, sc, None
         key = ("pipe", nq, k)
         if key not in self._bufs:
-            dev = dev_queries.device
+            dev = dev_queries.device if host_queries is None else t.device("cuda", t.cuda.current_device())
             mk = lambda dt: t.empty(nq * k, dtype=dt, device=dev)  # noqa: E731
             self._bufs[key] = {"slots": [dict(local=mk(t.int64), idx=mk(t.int64), keys=mk(t.int64),
                                               score=mk(t.float32 if self.kind != "binary" else t.int32),
@@ -235,12 +247,23 @@ class ShardedKnn:
         parity = st["calls"] & 1
         slot = st["slots"][parity]
         st["calls"] += 1
+        main = t.cuda.current_stream()
+        if host_queries is not None:
+            if "dq" not in slot:
+                slot["dq"] = t.empty(host_queries.shape, dtype=host_queries.dtype, device=slot["local"].device)
+            if slot["used"]:
+                main.wait_event(slot["scan_done"])   # the scan of two calls ago has read this slot's query copy
+            slot["dq"].copy_(host_queries, non_blocking=True)
+            dev_queries = slot["dq"]
+        if host_out and "h_idx" not in slot:
+            slot["h_idx"] = t.empty(nq * k, dtype=t.int64).pin_memory()
+            slot["h_score"] = t.empty(nq * k, dtype=slot["score"].dtype).pin_memory()
         if overlap_scans:
             scan = self._scan_streams[parity]
-            slot["ready"].record(t.cuda.current_stream())
+            slot["ready"].record(main)
             scan.wait_event(slot["ready"])
         else:
-            scan = t.cuda.current_stream()
+            scan = main
         if slot["used"]:
             scan.wait_event(slot["ex_done"])   # the exchange of two calls ago has read `local` (long done)
         self._keys(dev_queries, nq, k, slot["local"], C.c_void_p(scan.cuda_stream))
@@ -249,11 +272,18 @@ class ShardedKnn:
             L.call("innr_cuda_merge_keys_dev", C.c_void_p(slot["local"].data_ptr()), 1, nq, k, m,
                    C.c_void_p(slot["keys"].data_ptr()), C.c_void_p(slot["idx"].data_ptr()),
                    None if self.kind == "binary" else C.c_void_p(slot["score"].data_ptr()), C.c_void_p(scan.cuda_stream))
-            if self.kind == "binary":  # the distance is the high half of the key itself
+            slot["scan_done"].record(scan)
+            if self.kind == "binary" or host_out:
                 with t.cuda.stream(scan):
-                    slot["score"].copy_(slot["keys"] >> 32)
+                    if self.kind == "binary":  # the distance is the high half of the key itself
+                        slot["score"].copy_(slot["keys"] >> 32)
+                    if host_out:
+                        slot["h_idx"].copy_(slot["idx"], non_blocking=True)
+                        slot["h_score"].copy_(slot["score"], non_blocking=True)
             slot["ex_done"].record(scan)
             slot["used"] = True
+            if host_out:
+                return slot["h_idx"].view(nq, k), slot["h_score"].view(nq, k), slot["ex_done"]
             return slot["idx"].view(nq, k), slot["score"].view(nq, k), slot["ex_done"]
         slot["scan_done"].record(scan)
         ex = self._ex_stream
@@ -263,8 +293,14 @@ class ShardedKnn:
             self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, m, exs, idx=slot["idx"], dist_out=slot["score"])
         else:
             self.exchange.merge_dev(slot["local"].data_ptr(), nq, k, m, exs, idx=slot["idx"], score=slot["score"])
+        if host_out:
+            with t.cuda.stream(ex):
+                slot["h_idx"].copy_(slot["idx"], non_blocking=True)
+                slot["h_score"].copy_(slot["score"], non_blocking=True)
         slot["ex_done"].record(ex)
         slot["used"] = True
+        if host_out:
+            return slot["h_idx"].view(nq, k), slot["h_score"].view(nq, k), slot["ex_done"]
         return slot["idx"].view(nq, k), slot["score"].view(nq, k), slot["ex_done"]
 
     def drain(self):

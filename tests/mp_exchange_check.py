@@ -72,6 +72,21 @@ def main():
         torch.cuda.synchronize()
         if not same(got[i], want):
             failures.append(("pipelined", i))
+    # host-buffer streaming: pinned queries in, pinned results out, one event per call
+    hq = torch.from_numpy(qs).pin_memory()
+    got, pending = [], None
+    for i in range(9):
+        cur = peer.knn_dev_pipelined(None, 1, 10, host_queries=hq[i], host_out=True)
+        if pending is not None:
+            pending[2].synchronize()
+            got.append((pending[0].clone(), pending[1].clone()))
+        pending = cur
+    pending[2].synchronize()
+    got.append((pending[0].clone(), pending[1].clone()))
+    for i in range(9):
+        want = [t.cpu() for t in sync.knn_dev(dqs[i], 1, 10)]
+        if not (got[i][0].device.type == "cpu" and same(got[i], want)):
+            failures.append(("host-streaming", i))
     # Hamming (heavy ties) and u8
     nb = 200_000
     lo, hi = sharded.shard_range(nb, rank, world)
@@ -90,6 +105,24 @@ def main():
     torch.cuda.synchronize()
     if not same(a, b):
         failures.append(("u8",))
+    # the same two through the pipelined form (two scan streams, exchange on the side stream), several calls in flight
+    for kind, corpus, q, k in (("binary", codes, qc, 100), ("u8", u8, q8, 10)):
+        pk, sk = sharded.ShardedKnn(corpus, kind, exchange=ex), sharded.ShardedKnn(corpus, kind)
+        want = [t.clone() for t in sk.knn_dev(q, 1, k)]
+        outs = []
+        for i in range(6):
+            r = pk.knn_dev_pipelined(q, 1, k)
+            r[2].synchronize()
+            outs.append((r[0].clone(), r[1].clone()))
+        for i in range(4):
+            last = pk.knn_dev_pipelined(q, 1, k)
+        pk.drain()
+        torch.cuda.synchronize()
+        outs.append((last[0].clone(), last[1].clone()))
+        for o in outs:
+            if not (torch.equal(o[0], want[0]) and torch.equal(o[1].long() if kind == "binary" else o[1], want[1].long() if kind == "binary" else want[1])):
+                failures.append(("pipelined", kind))
+                break
     if ex.status() != 0:
         failures.append(("timeout",))
     bad = torch.tensor([len(failures)], device=dev)

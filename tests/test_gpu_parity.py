@@ -1175,6 +1175,19 @@ def test_pipelined_single_rank_matches_knn_dev(ib):
         sk.drain()
         torch.cuda.synchronize()
         assert np.array_equal(last[0].cpu().numpy(), want[7][0])
+        # host-buffer streaming: pinned queries in, pinned results out
+        hq = q.cpu().pin_memory()
+        pending, got = None, []
+        for j in range(8):
+            cur = sk.knn_dev_pipelined(None, 1, k, host_queries=hq[j], host_out=True)
+            if pending is not None:
+                pending[2].synchronize()
+                got.append((pending[0].numpy().copy(), pending[1].numpy().copy()))
+            pending = cur
+        pending[2].synchronize()
+        got.append((pending[0].numpy().copy(), pending[1].numpy().copy()))
+        for j in range(8):
+            assert np.array_equal(got[j][0], want[j][0]) and np.array_equal(bits(got[j][1]), bits(want[j][1])), (sk.kind, "host", j)
 
 
 def test_entries_leave_the_current_device_alone(ib):
