@@ -53,9 +53,6 @@ constexpr int LO_COL0 = 256;                // TMEM columns [256, 512): two Xlo 
 // KH = K halves per tile (token dimensions 129..256): a tile's 128 tokens arrive as KH stages of 128 columns each, and
 // both passes accumulate over the halves into the same TMEM columns (KH = 2 only with G = 1: the B operand of a 256-d
 // query group is 64 KB, a query pair's footprint).
-// TSA = both MMA passes take their A operand from TENSOR MEMORY: the converters write the TF32 part of X next to Xlo,
-// and the tensor core reads nothing but the (small) B operand from shared memory. Stages are then 64 columns wide
-// (P = 2, KH = ceil(dim / 64) <= 4) so that two operand buffers (X + Xlo, 128 columns each) fit beside the accumulators.
 template <int P, int G, int KH = 1>
 struct Shape {
   static constexpr int DIM = 32 * P;                    // columns per stage
@@ -84,7 +81,6 @@ struct TcArgs {
   unsigned n_docs, n_q;
   unsigned dim;  // token dimension (a multiple of 4, <= 32 P): the columns up to 32 P are zero-filled by TMA / the query staging
   const float* q;
-  int box_rows;    // debug_mode 1 only: rows per TMA box of ONE contiguous token stream (0 = the four-stream production order)
   int debug_mode;  // 0 normal; 1 = TMA streaming only; 2 = hi pass only; 4 = no epilogue math (profiling aids)
   int accumulate;  // 0: out[doc] = sum; 1: out[doc] += sum (second and later groups of 32 query tokens)
   float* out;
@@ -148,17 +144,14 @@ __device__ __forceinline__ void addmul2(float& x0, float& x1, float y0, float y1
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
 }
 
-template <bool COSINE, int P, int G, int KH = 1, bool TSA = false>
+template <bool COSINE, int P, int G, int KH = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_constant__ CUtensorMap tm_tokens,
                                                                    const TcArgs a) {
   using SH = Shape<P, G, KH>;
   constexpr int DIM = SH::DIM, STAGES = SH::STAGES, STAGE_BYTES = SH::STAGE_BYTES, QBYTES = SH::QBYTES,
                 UMMA_N = SH::UMMA_N, ACC = SH::ACC, QPANEL_BYTES = SH::QPANEL_BYTES, NQG = NQ * G, DIMT = DIM * KH;
   static_assert(STAGES >= 2, "ring too shallow");
-  static_assert(TSA || KH == 1 || (G == 1 && P == 4), "K halves: full 128-column stages, one query group");
-  static_assert(!TSA || (P <= 2 && KH <= 4), "A in tensor memory: stages of at most 64 columns");
-  constexpr int EMPTY_ARRIVES = TSA ? 4 : 5;  // converter warps (+ the hi MMAs' commit when they read the stage)
-  constexpr int OPW = TSA ? 2 * DIM : DIM;    // TMEM columns of one operand buffer: [X ;] Xlo
+  static_assert(KH == 1 || (G == 1 && P == 4), "K halves: full 128-column stages, one query group");
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_tok = smem;                                  // STAGES x (P x 16 KB)
   uint8_t* s_q = smem + STAGES * STAGE_BYTES;             // P x 8 KB
@@ -198,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&st->full[s], 1);
-      mbar_init(&st->empty[s], EMPTY_ARRIVES);  // hi MMAs done reading (1 commit) + 4 converter warps done reading (one elected
+      mbar_init(&st->empty[s], 5);  // hi MMAs done reading (1 commit) + 4 converter warps done reading (one elected
                                     // arrive per warp: 128 per-thread arrives on one mbarrier serialise in the LSU and
                                     // showed up as a quarter of the kernel's shared-memory wavefronts)
     }
@@ -270,16 +263,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
         mbar_wait_sleepy(&st->empty[s], ((i / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&st->full[s], STAGE_BYTES);
         uint8_t* dst = s_tok + s * STAGE_BYTES;
-        if (a.debug_mode == 1 && a.box_rows) {  // load-path experiment: one contiguous stream, boxes of box_rows rows
-          const long long base_row = (long long)st->s_tok[0] + (long long)(i / KH) * TILE_M;
-          for (int j = 0; j < TILE_M / a.box_rows; ++j) {
-            long long r0 = base_row + (long long)j * a.box_rows;
-            if (r0 > last_row) r0 = last_row;
-            for (int p = 0; p < P; ++p)
-              tma_load_2d(dst + p * PANEL_BYTES + j * a.box_rows * 128, &tm_tokens, &st->full[s], half * DIM + p * 32, (int)r0);
-          }
-          continue;
-        }
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           const int r0 = (int)(row[w] < (long long)st->s_tok[w + 1] ? row[w] : last_row);  // rows past the matrix end are zero-filled
@@ -313,48 +296,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // A = Xlo in tensor memory (128 lanes x 128 columns); B = the Qhi rows only (N = 32): Qlo.Xlo is below
     // 2^-22 of the product and is not worth a quarter of the tensor work (the kernel runs under the power cap).
     auto issue_lo = [&](int t, int b, int half) {
-      const uint32_t acc = tmem + t * UMMA_N, src = tmem + LO_COL0 + b * OPW + (TSA ? DIM : 0);
+      const uint32_t acc = tmem + t * UMMA_N, src = tmem + LO_COL0 + b * DIM;
       const uint64_t qd0 = desc_advance(q_desc, (uint32_t)half * P * QPANEL_BYTES);
 #pragma unroll
       for (int kk = 0; kk < DIM / 8; ++kk)
         umma_tf32_ts_c<true>(acc, src + kk * 8, desc_advance(qd0, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc_lo);
     };
-    // A = the TF32 part of X in tensor memory (TSA): same accumulator, N = [Qhi ; Qlo]
-    auto issue_hi_ts = [&](int t, int b, int half) {
-      const uint32_t acc = tmem + t * UMMA_N, src = tmem + LO_COL0 + b * OPW;
-      const uint64_t qd0 = desc_advance(q_desc, (uint32_t)half * P * QPANEL_BYTES);
-      if (half == 0) umma_tf32_ts_c<false>(acc, src, qd0, idesc);
-      else umma_tf32_ts_c<true>(acc, src, qd0, idesc);
-#pragma unroll
-      for (int kk = 1; kk < DIM / 8; ++kk)
-        umma_tf32_ts_c<true>(acc, src + kk * 8, desc_advance(qd0, (kk >> 2) * QPANEL_BYTES + (kk & 3) * 32), idesc);
-    };
     if (a.debug_mode == 1) {
       for (unsigned i = 0; i < n_it; ++i) {
         mbar_wait(&st->full[i % STAGES], (i / STAGES) & 1);
         if (lane == 0)
-          for (int r = 0; r < EMPTY_ARRIVES; ++r) mbar_arrive(&st->empty[i % STAGES]);
+          for (int r = 0; r < 5; ++r) mbar_arrive(&st->empty[i % STAGES]);
         __syncwarp();
       }
     }
-    if (TSA && a.debug_mode != 1) {
-      // both passes of stage i wait for ONE thing, the converters' operand buffer; they go out back to back
-      for (unsigned i = 0; i < n_it; ++i) {
-        const unsigned tile = i / KH;
-        const int half = (int)(i % KH), b = i & 1, t = tile % ACC;
-        mbar_wait_sleepy(&st->lo_ready[b], (i >> 1) & 1);
-        if (half == 0) mbar_wait_sleepy(&st->tmem_empty[t], ((tile / ACC) & 1) ^ 1);
-        tc_fence_after_sync();
-        if (elect_one_sync()) {
-          if (!(a.debug_mode & 128)) issue_hi_ts(t, b, half);  // (debug: timing experiments)
-          if (!(a.debug_mode & 256)) issue_lo(t, b, half);
-          if (half == KH - 1) umma_commit(&st->tmem_full[t]);  // accumulator complete for the epilogue
-          umma_commit(&st->lo_free[b]);                         // operand buffer may be overwritten
-        }
-        __syncwarp();
-      }
-    }
-    if (!TSA && a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
+    if (a.debug_mode == 2) {  // profiling aid: hi pass only (no Xlo), results are TF32-accurate only
       for (unsigned i = 0; i < n_it; ++i) {
         const unsigned tile = i / KH;
         const int s = i % STAGES, t = tile % ACC, half = (int)(i % KH);
@@ -372,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // hi(i) and lo(j) are issued in whatever order their inputs become ready (never block on one while the
     // other could run); lo(j) always follows hi(j) because both accumulate into the same TMEM columns.
     unsigned nh = 0, nl = 0;  // counted in stages (K halves of tiles)
-    while (!TSA && a.debug_mode != 1 && a.debug_mode != 2 && nl < n_it) {
+    while (a.debug_mode != 1 && a.debug_mode != 2 && nl < n_it) {
       bool progressed = false;
       if (nl < nh) {  // lo(nl): the converters have written Xlo of stage nl to TMEM buffer nl % 2
         const int b = nl & 1;
@@ -412,82 +368,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
     // One token row per thread = one TMEM lane per thread (warps 4-7 own lane quadrants 0-3). A panel row (8 chunks
     // of 16 B) is loaded at once, split, and written as 32 TMEM columns with one tcgen05.st.
     const int row = threadIdx.x - 128;
-    if (TSA && a.debug_mode != 1) {
-      // Both operands of a stage go to tensor memory. The row of stage i + 1 is read from shared memory while the
-      // tcgen05.st of stage i drain (the stores and the loads use different ports), and the stage is handed back to
-      // the TMA producer as soon as it is in registers.
-      ulonglong2 v[P][8];  // two packed f32 pairs per 16-byte chunk: the pairs stay in 64-bit registers end to end
-      auto load_row = [&](unsigned i) {
-        const uint8_t* base = s_tok + (i % STAGES) * STAGE_BYTES + row * 128;
-        if (!(a.debug_mode & 32)) {
-#pragma unroll
-          for (int p = 0; p < P; ++p)
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              v[p][c] = *reinterpret_cast<const ulonglong2*>(base + p * PANEL_BYTES + ((c ^ (row & 7)) << 4));
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st->empty[i % STAGES]);
-      };
-      if (n_it > 0) {
-        mbar_wait_sleepy(&st->full[0], 0);
-        load_row(0);
-      }
-      for (unsigned i = 0; i < n_it; ++i) {
-        const int b = i & 1;
-        mbar_wait_sleepy(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * OPW;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          uint32_t hi[32], lo[32];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {  // explicit truncation: the split must be exact
-            const uint64_t h01 = v[p][c].x & 0xFFFFE000FFFFE000ull, h23 = v[p][c].y & 0xFFFFE000FFFFE000ull;
-            const uint64_t l01 = sub2_rn(v[p][c].x, h01), l23 = sub2_rn(v[p][c].y, h23);
-            hi[4 * c + 0] = (uint32_t)h01;
-            hi[4 * c + 1] = (uint32_t)(h01 >> 32);
-            hi[4 * c + 2] = (uint32_t)h23;
-            hi[4 * c + 3] = (uint32_t)(h23 >> 32);
-            lo[4 * c + 0] = (uint32_t)l01;
-            lo[4 * c + 1] = (uint32_t)(l01 >> 32);
-            lo[4 * c + 2] = (uint32_t)l23;
-            lo[4 * c + 3] = (uint32_t)(l23 >> 32);
-          }
-          if (!(a.debug_mode & 8)) tmem_st_32x32b_x32(tdst + 32 * p, hi);        // (debug: timing experiments)
-          if (!(a.debug_mode & 16)) tmem_st_32x32b_x32(tdst + DIM + 32 * p, lo);
-        }
-        const unsigned nx = i + 1;
-        const bool early = nx < n_it && mbar_try_wait(&st->full[nx % STAGES], (nx / STAGES) & 1);
-        if (early) load_row(nx);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st->lo_ready[b]);
-        if (!early && nx < n_it) {
-          mbar_wait_sleepy(&st->full[nx % STAGES], (nx / STAGES) & 1);
-          load_row(nx);
-        }
-      }
-    }
-    for (unsigned i = 0; !TSA && a.debug_mode != 1 && i < n_it; ++i) {
+    for (unsigned i = 0; a.debug_mode != 1 && i < n_it; ++i) {
       const int s = i % STAGES, b = i & 1;
       mbar_wait_sleepy(&st->full[s], (i / STAGES) & 1);
-      if (!TSA && a.debug_mode == 2) {
+      if (a.debug_mode == 2) {
         if (lane == 0) mbar_arrive(&st->empty[s]);
         continue;
       }
       mbar_wait_sleepy(&st->lo_free[b], ((i >> 1) & 1) ^ 1);
       tc_fence_after_sync();
       const uint8_t* base = s_tok + s * STAGE_BYTES + row * 128;
-      const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * OPW;
+      const uint32_t tdst = tmem + ((uint32_t)((warp & 3) * 32) << 16) + LO_COL0 + b * DIM;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const uint8_t* pbase = base + p * PANEL_BYTES;
         ulonglong2 v[8];  // two packed f32 pairs per 16-byte chunk: the pairs stay in 64-bit registers end to end
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          v[c] = (a.debug_mode & 32) ? make_ulonglong2(i, p) : *reinterpret_cast<const ulonglong2*>(pbase + ((c ^ (row & 7)) << 4));
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const ulonglong2*>(pbase + ((c ^ (row & 7)) << 4));
         if (p == P - 1) {  // every lane of this warp has read its whole row: 1 of 5
           __syncwarp();
           if (lane == 0) mbar_arrive(&st->empty[s]);
@@ -502,7 +399,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
           lo[4 * c + 2] = (uint32_t)l23;
           lo[4 * c + 3] = (uint32_t)(l23 >> 32);
         }
-        if (!(a.debug_mode & 16)) tmem_st_32x32b_x32(tdst + 32 * p, lo);
+        tmem_st_32x32b_x32(tdst + 32 * p, lo);
       }
       tmem_st_wait();
       tc_fence_before_sync();
@@ -554,14 +451,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) maxsim_tc_kernel(const __grid_c
       for (int gq = 0; gq < G; ++gq) {
         uint32_t rh[32], rl[32];
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + t * UMMA_N + gq * NQ;
-        if (!(a.debug_mode & 64)) {
-          tmem_ld_32x32b_x32(taddr, rh);            // Xhi.Qhi + Xlo.Qhi
-          tmem_ld_32x32b_x32(taddr + NQ * G, rl);   // Xhi.Qlo
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rh[j] = rl[j] = i + j;
-        }
+        tmem_ld_32x32b_x32(taddr, rh);            // Xhi.Qhi + Xlo.Qhi
+        tmem_ld_32x32b_x32(taddr + NQ * G, rl);   // Xhi.Qlo
+        tmem_ld_wait();
         if (gq == G - 1) {  // the accumulator is in registers: the MMA warp may overwrite it
           tc_fence_before_sync();
           if (lane == 0) mbar_arrive(&st->tmem_empty[t]);
@@ -681,7 +573,7 @@ bool maxsim_tc_supported(const TokView& v, size_t n_q) {
 }
 
 namespace {
-template <bool COSINE, int P, int G, int KH = 1, bool TSA = false>
+template <bool COSINE, int P, int G, int KH = 1>
 cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
   using SH = Shape<P, G, KH>;
   constexpr size_t smem = (size_t)SH::STAGES * SH::STAGE_BYTES + SH::QBYTES + sizeof(SharedTail);
@@ -689,27 +581,15 @@ cudaError_t launch_shape(const CUtensorMap& tm, const TcArgs& a, unsigned grid, 
   static bool attr_set_dev[16] = {};
   bool& attr_set = attr_set_dev[current_device_slot()];
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P, G, KH, TSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(maxsim_tc_kernel<COSINE, P, G, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  maxsim_tc_kernel<COSINE, P, G, KH, TSA><<<grid, TC_THREADS, smem, s>>>(tm, a);
+  maxsim_tc_kernel<COSINE, P, G, KH><<<grid, TC_THREADS, smem, s>>>(tm, a);
   return cudaGetLastError();
-}
-bool maxsim_ts_enabled() {  // A/B switch: INNR_MAXSIM_TS=0 keeps the hi pass on the shared-memory stage
-  static const bool on = !(getenv("INNR_MAXSIM_TS") && atoi(getenv("INNR_MAXSIM_TS")) == 0);
-  return on;
 }
 template <bool COSINE, int G>
 cudaError_t launch_dim(size_t dim, const CUtensorMap& tm, const TcArgs& a, unsigned grid, cudaStream_t s) {
-  if (maxsim_ts_enabled()) {  // stages of 64 columns (32 for dim <= 32), A operands in tensor memory
-    if (dim <= 32) return launch_shape<COSINE, 1, G, 1, true>(tm, a, grid, s);
-    if (dim <= 64) return launch_shape<COSINE, 2, G, 1, true>(tm, a, grid, s);
-    if (dim <= 128) return launch_shape<COSINE, 2, G, 2, true>(tm, a, grid, s);
-    if (G != 1) return cudaErrorInvalidValue;
-    if (dim <= 192) return launch_shape<COSINE, 2, 1, 3, true>(tm, a, grid, s);
-    return launch_shape<COSINE, 2, 1, 4, true>(tm, a, grid, s);
-  }
   if (dim > 128) {  // 129..256 columns: two K halves of 128 columns per tile, one query group per pass
     if (G != 1) return cudaErrorInvalidValue;
     return launch_shape<COSINE, 4, 1, 2>(tm, a, grid, s);
@@ -739,14 +619,6 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
   a.out = dev_scores;
   static const int dbg = getenv("INNR_MAXSIM_DEBUG") ? atoi(getenv("INNR_MAXSIM_DEBUG")) : 0;
   a.debug_mode = dbg;
-  CUtensorMap tm_use = v.tmap;
-  if (dbg == 1 && (getenv("INNR_MAXSIM_BOXROWS") || getenv("INNR_MAXSIM_L2PROMO"))) {  // load-path experiments
-    const int rows = getenv("INNR_MAXSIM_BOXROWS") ? atoi(getenv("INNR_MAXSIM_BOXROWS")) : 0;
-    const int promo = getenv("INNR_MAXSIM_L2PROMO") ? atoi(getenv("INNR_MAXSIM_L2PROMO")) : 128;
-    a.box_rows = rows;
-    if (!make_tmap_f32_rows(&tm_use, v.tokens, v.total_tokens, v.dim, rows ? rows : CHUNK, 0, false, promo))
-      return cudaErrorInvalidValue;
-  }
   unsigned grid = (unsigned)num_sms;
   const unsigned long long tiles = (v.total_tokens + TILE_M - 1) / TILE_M;
   if (grid > tiles) grid = (unsigned)tiles;
@@ -761,8 +633,8 @@ cudaError_t launch_maxsim_tc(const TokView& v, const float* dev_q, size_t n_q, i
     a.n_q = (unsigned)take;
     a.q = dev_q + q0 * v.dim;
     a.accumulate = q0 > 0;
-    if (two) e = cosine ? launch_dim<true, 2>(v.dim, tm_use, a, grid, s) : launch_dim<false, 2>(v.dim, tm_use, a, grid, s);
-    else e = cosine ? launch_dim<true, 1>(v.dim, tm_use, a, grid, s) : launch_dim<false, 1>(v.dim, tm_use, a, grid, s);
+    if (two) e = cosine ? launch_dim<true, 2>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 2>(v.dim, v.tmap, a, grid, s);
+    else e = cosine ? launch_dim<true, 1>(v.dim, v.tmap, a, grid, s) : launch_dim<false, 1>(v.dim, v.tmap, a, grid, s);
     if (e != cudaSuccess) return e;
     ++*launches;
     q0 += take;

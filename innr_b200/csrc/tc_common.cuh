@@ -221,7 +221,7 @@ inline PFN_encodeTiled get_encode_tiled() {
 
 // pitch_floats: row pitch of the matrix in floats (>= cols; 0 = dense)
 inline bool make_tmap_f32_rows(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                               uint64_t pitch_floats = 0, bool atom32 = false, int l2_promotion = 128) {
+                               uint64_t pitch_floats = 0, bool atom32 = false) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t gdim[2] = {cols, rows};
@@ -230,9 +230,7 @@ inline bool make_tmap_f32_rows(CUtensorMap* m, const float* base, uint64_t rows,
   cuuint32_t estr[2] = {1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-             l2_promotion == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                 : (l2_promotion == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                                       : (l2_promotion == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B)),
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
