@@ -166,6 +166,7 @@ def launch_count() -> int:
 
 
 def last_kernel_ms() -> float:
+    """Device time of the last host-facing call's kernels; recorded only after set_option("kernel_timing", 1)."""
     v = C.c_float(0)
     call("innr_cuda_last_kernel_ms", C.byref(v))
     return float(v.value)

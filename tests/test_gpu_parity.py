@@ -1190,6 +1190,24 @@ def test_pipelined_single_rank_matches_knn_dev(ib):
             assert np.array_equal(got[j][0], want[j][0]) and np.array_equal(bits(got[j][1]), bits(want[j][1])), (sk.kind, "host", j)
 
 
+def test_kernel_timing_is_opt_in(ib):
+    """innr_cuda_last_kernel_ms reports only after set_option("kernel_timing", 1): the timed event records are kept out
+    of short calls by default (include/innr_cuda.h)."""
+    from innr_b200 import _lib as L
+    vb = ib.VerticalBatch.from_flat(rand_rows(2000, 32, 5).reshape(-1), 2000, 32)
+    q = rand_rows(1, 32, 6)[0]
+    L.set_option("kernel_timing", 0)
+    ib.batch_knn_dot(q, vb, 5)
+    before = ib.last_kernel_ms()
+    L.set_option("kernel_timing", 1)
+    try:
+        ib.batch_knn_dot(q, vb, 5)
+        assert ib.last_kernel_ms() > 0.0
+        assert ib.last_kernel_ms() != before or before > 0.0
+    finally:
+        L.set_option("kernel_timing", 0)
+
+
 def test_entries_leave_the_current_device_alone(ib):
     import torch
     before = torch.cuda.current_device()
