@@ -290,6 +290,17 @@ class Workload:
         self.torch.cuda.current_stream().synchronize()
         return self._h_idx, self._h_sc
 
+    _pending = None
+
+    def e2e_collect(self, ticket):
+        """Keeps one asynchronous call in flight behind the one just submitted; returns the previous call's result."""
+        prev, self._pending = self._pending, ticket
+        return prev.wait() if prev is not None else None
+
+    def e2e_drain(self):
+        prev, self._pending = self._pending, None
+        return prev.wait() if prev is not None else None
+
     def drain(self):
         """Queue a wait for everything step_dev left on side streams (the pipelined exchanges at N > 1)."""
         sk = getattr(self, "sk", None)
@@ -392,9 +403,10 @@ class KnnF32(Workload):
                                          overlap_scans=self.workload != "batch_demo")
 
     def step_e2e(self, i):
-        if self.world == 1:  # the C-ABI call with host buffers (pinned query; keys come back through pinned staging)
-            import innr_b200 as ib
-            return ib.batch_knn_many(self.metric, self.q_host[i % self.q_host.shape[0]], self.shard, self.k)
+        if self.world == 1:
+            # the C-ABI with host buffers, asynchronous form: submit call i, then collect call i - 1 (two in flight)
+            from innr_b200 import stream
+            return self.e2e_collect(stream.submit_knn(self.metric, self.q_host[i % self.q_host.shape[0]], self.shard, self.k))
         # N > 1: pinned query in, pinned result out, streamed (results one call late, one host sync per batch of calls)
         q = self.q_host_t[i % self.q_host_t.shape[0]]
         return self.sk.knn_dev_pipelined(None, self.nq, self.k, overlap_scans=self.workload != "batch_demo",
@@ -462,8 +474,8 @@ class Hamming(Workload):
 
     def step_e2e(self, i):
         if self.world == 1:
-            import innr_b200 as ib
-            return ib.hamming_topk_many(self.q_host[i % 16].view(np.uint64).reshape(1, -1), self.shard, self.k)
+            from innr_b200 import stream
+            return self.e2e_collect(stream.submit_hamming_topk(self.q_host[i % 16].view(np.uint64).reshape(1, -1), self.shard, self.k))
         return self.sk.knn_dev_pipelined(None, 1, self.k, host_queries=self.q_host_t[i % 16], host_out=True)
 
     def keys_entry(self, L, q, b, stream):
@@ -529,8 +541,8 @@ class U8(Workload):
 
     def step_e2e(self, i):
         if self.world == 1:
-            import innr_b200 as ib
-            return ib.batch_knn_u8_many(self.q_host[i % 16].reshape(1, -1), self.shard, self.k)
+            from innr_b200 import stream
+            return self.e2e_collect(stream.submit_knn_u8(self.q_host[i % 16].reshape(1, -1), self.shard, self.k))
         return self.sk.knn_dev_pipelined(None, 1, self.k, host_queries=self.q_host_t[i % 16], host_out=True)
 
     def keys_entry(self, L, q, b, stream):
@@ -786,10 +798,12 @@ def measure(w, args, env):
     # ---- end-to-end through the public API with host buffers ---------------------------------------------
     for i in range(min(warmup, 3)):
         w.step_e2e(i)
+    w.e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for i in range(steps):
         w.step_e2e(i)
+    w.e2e_drain()  # the last asynchronous call's result is read inside the timed region too
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -836,7 +850,9 @@ def measure(w, args, env):
             "dtype": dtype_of(w.workload), "data": "synthetic",
             "config": config_of(w.workload, args.scale, world, args.queries),
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": w.h2d, "d2h_bytes_per_step": w.d2h,
-                    "mode": ("one synchronous host-buffer C-ABI call per step" if world == 1 or getattr(w, "sk", None) is None
+                    "mode": ("host-buffer C-ABI calls, asynchronous form (innr_cuda_*_async + innr_cuda_ticket_wait): call i is "
+                             "submitted before the result of call i - 1 is collected" if world == 1 and getattr(w, "sk", None) is not None
+                             else "one synchronous host-buffer C-ABI call per step" if world == 1
                              else "streamed per rank: pinned query H2D -> shard scan -> peer exchange -> D2H into pinned "
                                   "buffers, double-buffered, one host synchronisation after the last step")},
             "gpu_launches": int(launches),

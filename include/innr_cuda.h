@@ -46,6 +46,7 @@ extern "C" {
 #define INNR_ECUDA 2        /* CUDA runtime failure or no device */
 #define INNR_ENOMEM 3       /* device or host allocation failed */
 #define INNR_EUNSUPPORTED 4 /* shape outside what the kernels cover (message says which) */
+#define INNR_EBUSY 5        /* both asynchronous slots of the device are in flight: wait for a ticket first */
 
 /* metric selector for the f32 PDX scans */
 #define INNR_METRIC_DOT 0    /* batch_dot / batch_knn_dot        src/batch.rs:270, :742 */
@@ -330,6 +331,25 @@ int innr_cuda_hamming_topk_sharded(const innr_cuda_corpus* const* shards, size_t
 int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
                                    size_t n_queries, size_t query_len, size_t k, uint64_t* out_idx, float* out_score,
                                    size_t* out_count);
+/* ---- asynchronous host-buffer top-k ------------------------------------------------------------------------
+ * The entries above synchronise before they return. These queue the same call -- same arguments, same checks, same
+ * results -- and hand back a ticket; innr_cuda_ticket_wait blocks until THAT call is complete, writes min(k, N)
+ * results per query at row stride k like the synchronous entry (f32 / u8 corpora: out_score, out_dist may be NULL;
+ * binary corpora: out_dist, out_score may be NULL) and releases the ticket. The queries are copied before the call
+ * returns (the caller may reuse its buffer at once). At most TWO tickets per device may be in flight (a third submit
+ * fails with INNR_EBUSY): submit(i + 1) before wait(i) keeps two shard scans overlapping on the device, which is what
+ * hides the ramp at both ends of a launch. Tickets belong to the library; a ticket is invalid
+ * after its wait. */
+typedef struct innr_cuda_ticket innr_cuda_ticket;
+int innr_cuda_batch_knn_async(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                              size_t query_len, size_t k, innr_cuda_ticket** out_ticket);
+int innr_cuda_hamming_topk_async(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
+                                 size_t query_dim_bits, size_t k, innr_cuda_ticket** out_ticket);
+int innr_cuda_batch_knn_u8_async(const innr_cuda_corpus* c, const float* queries, size_t n_queries, size_t query_len,
+                                 size_t k, innr_cuda_ticket** out_ticket);
+int innr_cuda_ticket_wait(innr_cuda_ticket* t, uint64_t* out_idx, float* out_score, uint32_t* out_dist,
+                          size_t* out_count);
+
 /* ---- timing hook: device time (ms) of the last host-facing call's kernels, measured with CUDA events on the
  *      launching stream. Off by default (the two timed event records cost a short call ~15 us): enable with
  *      innr_cuda_set_option("kernel_timing", 1); 0 until then. ------------------------------------------------- */

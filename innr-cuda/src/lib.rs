@@ -24,7 +24,7 @@ use sys::*;
 /// A non-zero status of the C-ABI with the library's thread-local message.
 #[derive(Debug, Clone, PartialEq, Eq)]
 pub struct Error {
-    /// `INNR_EINVAL` (1), `INNR_ECUDA` (2), `INNR_ENOMEM` (3) or `INNR_EUNSUPPORTED` (4).
+    /// `INNR_EINVAL` (1), `INNR_ECUDA` (2), `INNR_ENOMEM` (3), `INNR_EUNSUPPORTED` (4) or `INNR_EBUSY` (5).
     pub code: i32,
     /// `innr_cuda_last_error()` at the time of the failure.
     pub message: String,
@@ -239,6 +239,16 @@ impl F32Corpus {
         Ok(split_results(idx, sc, n_queries, k, count))
     }
 
+    /// Asynchronous `knn_many`: queues the call and returns at once; `Ticket::wait` blocks on this call only and gives
+    /// what `knn_many` gives. Two tickets per device may be in flight -- submitting call i + 1 before waiting for call i
+    /// keeps two scans overlapping on the device.
+    pub fn knn_submit(&self, metric: Metric, queries: &[f32], n_queries: usize, k: usize) -> Result<Ticket> {
+        assert_eq!(queries.len(), n_queries * self.d); // src/batch.rs:386 / :743 / :778, per query
+        let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+        check(unsafe { innr_cuda_batch_knn_async(self.h.0, metric.id(), queries.as_ptr(), n_queries, self.d, k, &mut t) })?;
+        Ok(Ticket { t, n_queries, k, binary: false })
+    }
+
     /// `batch_knn_filtered` (src/batch.rs:820-882). The closure is evaluated into a bitmask here (the reference builds
     /// `mask: Vec<bool>` itself, :839); rows of rejected vectors are never read on the device.
     pub fn knn_filtered<F: Fn(usize) -> bool>(&self, query: &[f32], k: usize, predicate: F) -> Result<(Vec<usize>, Vec<f32>)> {
@@ -445,6 +455,14 @@ impl BinaryCorpus {
         Ok(idx.into_iter().zip(dist).take(count).map(|(i, d)| (i as usize, d)).collect())
     }
 
+    /// Asynchronous `hamming_top_k` (see `F32Corpus::knn_submit`); `Ticket::wait_hamming` returns `(index, distance)`.
+    pub fn hamming_top_k_submit(&self, query_words: &[u64], query_dim_bits: usize, k: usize) -> Result<Ticket> {
+        self.check_query(query_words, query_dim_bits, "binary_hamming");
+        let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+        check(unsafe { innr_cuda_hamming_topk_async(self.h.0, query_words.as_ptr(), 1, query_dim_bits, k, &mut t) })?;
+        Ok(Ticket { t, n_queries: 1, k, binary: true })
+    }
+
     /// Top-k by `binary_dot` (`jaccard == false`) or `binary_jaccard` (`true`): descending, ties -> lower index.
     pub fn similarity_top_k(&self, jaccard: bool, query_words: &[u64], query_dim_bits: usize, k: usize) -> Result<Vec<(usize, f32)>> {
         self.check_query(query_words, query_dim_bits, if jaccard { "binary_jaccard" } else { "binary_dot" });
@@ -537,6 +555,61 @@ impl U8Corpus {
             innr_cuda_batch_knn_u8(self.h.0, query.as_ptr(), 1, query.len(), k, idx.as_mut_ptr(), sc.as_mut_ptr(), &mut count)
         })?;
         Ok(idx.into_iter().zip(sc).take(count).map(|(i, s)| (i as usize, s)).collect())
+    }
+}
+
+impl U8Corpus {
+    /// Asynchronous `knn` (see `F32Corpus::knn_submit`).
+    pub fn knn_submit(&self, query: &[f32], k: usize) -> Result<Ticket> {
+        if self.n != 0 && k != 0 {
+            assert_eq!(query.len(), self.d, "asymmetric_dot_u8_precomputed: dimension mismatch ({} vs {})", query.len(), self.d); // src/scalar.rs:290-296
+        }
+        let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+        check(unsafe { innr_cuda_batch_knn_u8_async(self.h.0, query.as_ptr(), 1, query.len(), k, &mut t) })?;
+        Ok(Ticket { t, n_queries: 1, k, binary: false })
+    }
+}
+
+/// One asynchronous top-k call in flight. The library owns the ticket; waiting consumes it. A ticket that is dropped
+/// without a wait is waited for in `drop` (its slot must be free before the device accepts a third call).
+pub struct Ticket {
+    t: *mut innr_cuda_ticket,
+    n_queries: usize,
+    k: usize,
+    binary: bool,
+}
+
+impl Ticket {
+    /// f32 and u8 corpora: per query `(indices, scores)`, exactly what the synchronous call returns.
+    pub fn wait(mut self) -> Result<Vec<(Vec<usize>, Vec<f32>)>> {
+        assert!(!self.binary, "a Hamming ticket is read with wait_hamming");
+        let (mut idx, mut sc) = knn_buffers(self.n_queries, self.k);
+        let mut count = 0usize;
+        let t = std::mem::replace(&mut self.t, std::ptr::null_mut());
+        check(unsafe { innr_cuda_ticket_wait(t, idx.as_mut_ptr(), sc.as_mut_ptr(), std::ptr::null_mut(), &mut count) })?;
+        Ok(split_results(idx, sc, self.n_queries, self.k, count))
+    }
+
+    /// Binary corpora: `(index, distance)` of the single query, ascending distance, ties -> lower index.
+    pub fn wait_hamming(mut self) -> Result<Vec<(usize, u32)>> {
+        assert!(self.binary, "not a Hamming ticket");
+        let kk = self.k.max(1) * self.n_queries.max(1);
+        let (mut idx, mut dist) = (vec![0u64; kk], vec![0u32; kk]);
+        let mut count = 0usize;
+        let t = std::mem::replace(&mut self.t, std::ptr::null_mut());
+        check(unsafe { innr_cuda_ticket_wait(t, idx.as_mut_ptr(), std::ptr::null_mut(), dist.as_mut_ptr(), &mut count) })?;
+        Ok(idx.into_iter().zip(dist).take(count).map(|(i, d)| (i as usize, d)).collect())
+    }
+}
+
+impl Drop for Ticket {
+    fn drop(&mut self) {
+        if !self.t.is_null() {
+            let kk = self.k.max(1) * self.n_queries.max(1);
+            let (mut idx, mut sc, mut dist) = (vec![0u64; kk], vec![0f32; kk], vec![0u32; kk]);
+            let mut count = 0usize;
+            let _ = unsafe { innr_cuda_ticket_wait(self.t, idx.as_mut_ptr(), sc.as_mut_ptr(), dist.as_mut_ptr(), &mut count) };
+        }
     }
 }
 

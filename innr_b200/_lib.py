@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libinnr_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "innr_cuda.h")
 
-INNR_OK, INNR_EINVAL, INNR_ECUDA, INNR_ENOMEM, INNR_EUNSUPPORTED = 0, 1, 2, 3, 4
+INNR_OK, INNR_EINVAL, INNR_ECUDA, INNR_ENOMEM, INNR_EUNSUPPORTED, INNR_EBUSY = 0, 1, 2, 3, 4, 5
 METRIC_DOT, METRIC_COSINE, METRIC_L2 = 0, 1, 2
 
 f32p = C.POINTER(C.c_float)
@@ -92,6 +92,10 @@ SIGNATURES = {
     "innr_cuda_batch_knn_sharded": [vp, sz, ci, f32p, sz, sz, sz, u64p, f32p, szp],
     "innr_cuda_hamming_topk_sharded": [vp, sz, u64p, sz, sz, sz, u64p, u32p, szp],
     "innr_cuda_batch_knn_u8_sharded": [vp, sz, f32p, sz, sz, sz, u64p, f32p, szp],
+    "innr_cuda_batch_knn_async": [vp, ci, f32p, sz, sz, sz, handle_p],
+    "innr_cuda_hamming_topk_async": [vp, u64p, sz, sz, sz, handle_p],
+    "innr_cuda_batch_knn_u8_async": [vp, f32p, sz, sz, sz, handle_p],
+    "innr_cuda_ticket_wait": [vp, u64p, f32p, u32p, szp],
     "innr_cuda_exchange_create": [ci, ci, sz, handle_p],
     "innr_cuda_exchange_ipc_handle": [vp, vp],
     "innr_cuda_exchange_connect_ipc": [vp, vp],

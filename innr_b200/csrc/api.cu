@@ -50,6 +50,20 @@ struct innr_cuda_corpus {
   uint32_t* dev_order = nullptr;
 };
 
+// One asynchronous host-buffer call in flight (innr_cuda_*_async -> innr_cuda_ticket_wait). A device owns two of
+// these, one per workspace lane: stream, event and staging buffers live as long as the device context.
+struct innr_cuda_ticket {
+  int device = -1;
+  bool in_flight = false;
+  int kind = 0;            // corpus kind of the call: 0 f32, 1 binary, 2 u8
+  int metric = 0;
+  size_t nq = 0, k = 0, kk = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  void *d_query = nullptr, *d_keys = nullptr, *h_in = nullptr, *h_out = nullptr;  // h_*: pinned
+  size_t d_query_cap = 0, d_keys_cap = 0, h_in_cap = 0, h_out_cap = 0;
+};
+
 // One rank's end of the peer-mapped key exchange (exchange.cu).
 struct innr_cuda_exchange {
   int device = 0, n_ranks = 1, rank = 0;
@@ -113,6 +127,8 @@ struct DeviceCtx {
   uint64_t seq = 0;
   Workspace ws, ws_alt;
   Workspace& lane_ws(int lane) { return lane ? ws_alt : ws; }
+  innr_cuda_ticket async_slot[2];  // asynchronous host-buffer calls in flight (at most one per lane)
+  unsigned async_next = 0;
   Buf d_query, d_keys, d_scores, d_aux, d_tcws, h_pin, h_counts;
   float last_ms = 0.0f;
 };
@@ -409,6 +425,15 @@ int innr_cuda_shutdown(void) {
     cudaEventDestroy(c.ev0);
     cudaEventDestroy(c.ev1);
     for (int l = 0; l < 2; ++l) cudaEventDestroy(c.ws_event[l]);
+    for (innr_cuda_ticket& t : c.async_slot) {
+      if (t.stream) cudaStreamSynchronize(t.stream);
+      if (t.d_query) cudaFree(t.d_query);
+      if (t.d_keys) cudaFree(t.d_keys);
+      if (t.h_in) cudaFreeHost(t.h_in);
+      if (t.h_out) cudaFreeHost(t.h_out);
+      if (t.done) cudaEventDestroy(t.done);
+      if (t.stream) cudaStreamDestroy(t.stream);
+    }
     cudaStreamDestroy(c.stream);
     c = DeviceCtx();
   }
@@ -2167,6 +2192,202 @@ int innr_cuda_maxsim_dev(const innr_cuda_corpus* c, const float* dev_q_tokens, s
   if (rc) return rc;
   DevRelease rel(*ctx, (cudaStream_t)stream);
   return maxsim_common(c, ctx, dev_q_tokens, n_q, cosine_flag, dev_scores, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------ asynchronous host-buffer calls
+// The host-facing top-k entries synchronise before they return, so a caller with one query per call pays the ramp at
+// both ends of every launch and leaves the GPU idle while it decodes. The _async forms queue the same work (query
+// staged through pinned memory, shard scan on one of the device's two lanes, keys back into pinned memory) on a stream
+// of their own and return a ticket; innr_cuda_ticket_wait blocks on that call only. Two tickets per device can be in
+// flight: submit(i + 1) before wait(i) keeps two scans overlapping on the device.
+static int grow(void** p, size_t* cap, size_t bytes, bool pinned) {
+  if (bytes <= *cap) return INNR_OK;
+  if (*p) {
+    if (pinned) cudaFreeHost(*p); else cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+  }
+  const size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+  CU(pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want));
+  *cap = want;
+  return INNR_OK;
+}
+// picks a free ticket of the corpus' device (the caller holds the device mutex) and sizes its buffers
+static int async_begin(const innr_cuda_corpus* c, DeviceCtx** ctx_out, innr_cuda_ticket** out, size_t query_bytes,
+                       size_t nq, size_t k, size_t kk) {
+  DeviceCtx* ctx;
+  int rc = ensure_ctx(c->device, &ctx, WS_NONE);
+  if (rc) return rc;
+  innr_cuda_ticket* t = nullptr;
+  for (unsigned j = 0; j < 2 && !t; ++j) {
+    innr_cuda_ticket& cand = ctx->async_slot[(ctx->async_next + j) & 1];
+    if (!cand.in_flight) t = &cand;
+  }
+  if (!t) return fail(INNR_EBUSY, "two asynchronous calls are already in flight on this device: wait for a ticket first");
+  ctx->async_next = (unsigned)((t - ctx->async_slot) + 1) & 1;
+  if (!t->stream) {
+    CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    // spin-wait unless asked otherwise: a blocking wait puts the host thread to sleep and adds its wake-up latency
+    // (tens of microseconds) to every short call
+    static const bool blocking = getenv("INNR_ASYNC_BLOCKING_WAIT") != nullptr;
+    CU(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0)));
+  }
+  t->device = c->device;
+  t->kind = c->kind;
+  t->nq = nq;
+  t->k = k;
+  t->kk = kk;
+  if ((rc = grow(&t->h_in, &t->h_in_cap, query_bytes, true))) return rc;
+  if ((rc = grow(&t->d_query, &t->d_query_cap, query_bytes + 16, false))) return rc;
+  if ((rc = grow(&t->d_keys, &t->d_keys_cap, nq * kk * sizeof(uint64_t), false))) return rc;
+  if ((rc = grow(&t->h_out, &t->h_out_cap, nq * kk * sizeof(uint64_t), true))) return rc;
+  *ctx_out = ctx;
+  *out = t;
+  return INNR_OK;
+}
+// keys -> pinned memory, completion event; the ticket is in flight from here on
+static int async_finish(innr_cuda_ticket* t) {
+  if (t->nq * t->kk)
+    CU(cudaMemcpyAsync(t->h_out, t->d_keys, t->nq * t->kk * sizeof(uint64_t), cudaMemcpyDeviceToHost, t->stream));
+  CU(cudaEventRecord(t->done, t->stream));
+  t->in_flight = true;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_async(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
+                              size_t query_len, size_t k, innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!c || c->kind != 0) return fail(INNR_EINVAL, "need an f32 PDX corpus");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  if (query_len != c->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");  // src/batch.rs:386,743,778
+  const bool empty = c->n == 0 || k == 0 || n_queries == 0;                            // src/batch.rs:388-393
+  if (!empty && !queries && c->d) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = empty ? 0 : (k < c->n ? k : c->n);
+  EntryGuard lk(c->device);
+  DeviceCtx* ctx;
+  innr_cuda_ticket* t;
+  const size_t qbytes = empty ? 0 : n_queries * c->d * sizeof(float);
+  rc = async_begin(c, &ctx, &t, qbytes, n_queries, k, kk);
+  if (rc) return rc;
+  t->metric = metric;
+  if (!empty) {
+    if (qbytes) {
+      std::memcpy(t->h_in, queries, qbytes);
+      CU(cudaMemcpyAsync(t->d_query, t->h_in, qbytes, cudaMemcpyHostToDevice, t->stream));
+    }
+    int lane = 0;
+    rc = ensure_ctx(c->device, &ctx, knn_is_scan_only(c, mode, n_queries, kk) ? WS_DEV_SCAN : WS_DEV, t->stream, &lane);
+    if (rc) return rc;
+    DevRelease rel(*ctx, t->stream, lane);
+    rc = knn_keys_dev(const_cast<innr_cuda_corpus*>(c), ctx, mode, (const float*)t->d_query, n_queries, kk,
+                      (uint64_t*)t->d_keys, t->stream, lane);
+    if (rc) return rc;
+  }
+  rc = async_finish(t);
+  if (rc) return rc;
+  *out_ticket = t;
+  return INNR_OK;
+}
+
+int innr_cuda_hamming_topk_async(const innr_cuda_corpus* c, const uint64_t* query_words, size_t n_queries,
+                                 size_t query_dim_bits, size_t k, innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!c || c->kind != 1) return fail(INNR_EINVAL, "need a binary corpus");
+  if (query_dim_bits != c->dim_bits) return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");
+  const bool empty = c->n == 0 || k == 0 || n_queries == 0;
+  if (!empty && c->words == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional codes: use innr_cuda_hamming_topk");
+  if (!empty && !query_words) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = empty ? 0 : (k < c->n ? k : c->n);
+  EntryGuard lk(c->device);
+  DeviceCtx* ctx;
+  innr_cuda_ticket* t;
+  const size_t qw = 2 * c->chunks;
+  const size_t qbytes = empty ? 0 : n_queries * qw * sizeof(uint64_t);
+  int rc = async_begin(c, &ctx, &t, qbytes, n_queries, k, kk);
+  if (rc) return rc;
+  if (!empty) {
+    uint64_t* h = (uint64_t*)t->h_in;
+    const size_t rem = c->dim_bits % 64;
+    for (size_t q = 0; q < n_queries; ++q)
+      for (size_t w = 0; w < qw; ++w) {
+        uint64_t x = w < c->words ? query_words[q * c->words + w] : 0;
+        if (w + 1 == c->words && rem) x &= (1ull << rem) - 1;  // PackedBinary::new masks padding
+        h[q * qw + w] = x;
+      }
+    CU(cudaMemcpyAsync(t->d_query, t->h_in, qbytes, cudaMemcpyHostToDevice, t->stream));
+    int lane = 0;
+    rc = ensure_ctx(c->device, &ctx, kk <= MAX_FUSED_K ? WS_DEV_SCAN : WS_DEV, t->stream, &lane);
+    if (rc) return rc;
+    DevRelease rel(*ctx, t->stream, lane);
+    rc = hamming_keys(c, ctx, (const uint64_t*)t->d_query, n_queries, kk, (uint64_t*)t->d_keys, t->stream, lane);
+    if (rc) return rc;
+  }
+  rc = async_finish(t);
+  if (rc) return rc;
+  *out_ticket = t;
+  return INNR_OK;
+}
+
+int innr_cuda_batch_knn_u8_async(const innr_cuda_corpus* c, const float* queries, size_t n_queries, size_t query_len,
+                                 size_t k, innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!c || c->kind != 2) return fail(INNR_EINVAL, "need a u8 corpus");
+  const bool empty = c->n == 0 || k == 0 || n_queries == 0;  // src/scalar.rs:376-378 (before any length check)
+  if (!empty && query_len != c->d) return fail(INNR_EINVAL, "asymmetric_dot_u8_precomputed: dimension mismatch");
+  if (!empty && c->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
+  if (!empty && !queries) return fail(INNR_EINVAL, "null argument");
+  const size_t kk = empty ? 0 : (k < c->n ? k : c->n);
+  EntryGuard lk(c->device);
+  DeviceCtx* ctx;
+  innr_cuda_ticket* t;
+  const size_t qbytes = empty ? 0 : n_queries * c->d * sizeof(float);
+  int rc = async_begin(c, &ctx, &t, qbytes, n_queries, k, kk);
+  if (rc) return rc;
+  if (!empty) {
+    std::memcpy(t->h_in, queries, qbytes);
+    CU(cudaMemcpyAsync(t->d_query, t->h_in, qbytes, cudaMemcpyHostToDevice, t->stream));
+    int lane = 0;
+    rc = ensure_ctx(c->device, &ctx, kk <= MAX_FUSED_K ? WS_DEV_SCAN : WS_DEV, t->stream, &lane);
+    if (rc) return rc;
+    DevRelease rel(*ctx, t->stream, lane);
+    rc = u8_keys(c, ctx, (const float*)t->d_query, n_queries, kk, (uint64_t*)t->d_keys, t->stream, lane);
+    if (rc) return rc;
+  }
+  rc = async_finish(t);
+  if (rc) return rc;
+  *out_ticket = t;
+  return INNR_OK;
+}
+
+int innr_cuda_ticket_wait(innr_cuda_ticket* t, uint64_t* out_idx, float* out_score, uint32_t* out_dist,
+                          size_t* out_count) {
+  if (out_count) *out_count = 0;
+  if (!t || !t->in_flight) return fail(INNR_EINVAL, "ticket is not in flight");
+  if (t->kk && (!out_idx || (t->kind == 1 ? !out_dist : !out_score))) return fail(INNR_EINVAL, "null argument");
+  // block on this call only, outside the device mutex: other threads keep submitting meanwhile
+  cudaError_t e = cudaEventSynchronize(t->done);
+  EntryGuard lk(t->device);
+  t->in_flight = false;
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(ticket)");
+  const uint64_t* keys = (const uint64_t*)t->h_out;
+  for (size_t q = 0; q < t->nq && t->kk; ++q) {
+    if (t->kind == 1) {
+      for (size_t j = 0; j < t->kk; ++j) {
+        out_idx[q * t->k + j] = keys[q * t->kk + j] & 0xFFFFFFFFull;
+        out_dist[q * t->k + j] = (uint32_t)(keys[q * t->kk + j] >> 32);
+      }
+    } else {
+      decode_keys_f32(keys + q * t->kk, t->kk, t->kind == 2 || t->metric != INNR_METRIC_L2, out_idx + q * t->k,
+                      out_score + q * t->k);
+    }
+  }
+  if (out_count) *out_count = t->kk;
+  return INNR_OK;
 }
 
 // ------------------------------------------------------------------------------------------ peer-mapped exchange

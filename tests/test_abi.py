@@ -138,7 +138,7 @@ def test_rust_shim_is_complete_source():
         r_params = re.search(rf"pub fn {name}\(([^)]*)\)", sys_text).group(1).strip()
         n_r = 0 if not r_params else r_params.count(",") + 1
         assert n_c == n_r, (name, n_c, n_r)
-    text, fns = _check_rust_source(os.path.join(shim, "src", "lib.rs"), extra_defined={"innr_cuda_corpus", "innr_cuda_exchange"})
+    text, fns = _check_rust_source(os.path.join(shim, "src", "lib.rs"), extra_defined={"innr_cuda_corpus", "innr_cuda_exchange", "innr_cuda_ticket"})
     called = set(re.findall(r"\b(innr_cuda_[a-z0-9_]+)\s*\(", text))
     assert called <= declared, sorted(called - declared)
     # one wrapper per reference function of the path
@@ -180,7 +180,7 @@ def test_integration_patch_applies_to_the_reference():
                      "get_or_upload", "device_available"):
             assert need in fns, f"src/cuda.rs lacks `{need}`"
         lib_methods = _check_rust_source(os.path.join(ROOT, "innr-cuda", "src", "lib.rs"),
-                                         extra_defined={"innr_cuda_corpus", "innr_cuda_exchange"})[1]
+                                         extra_defined={"innr_cuda_corpus", "innr_cuda_exchange", "innr_cuda_ticket"})[1]
         for m in set(re.findall(r"self\.inner\.([a-z_0-9]+)\(", text)):   # every call into innr-cuda exists there
             assert m in lib_methods, f"src/cuda.rs calls innr_cuda::*::{m}, which innr-cuda/src/lib.rs does not define"
         batch = open(os.path.join(tmp, "src", "batch.rs")).read()

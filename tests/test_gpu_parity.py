@@ -1190,6 +1190,64 @@ def test_pipelined_single_rank_matches_knn_dev(ib):
             assert np.array_equal(got[j][0], want[j][0]) and np.array_equal(bits(got[j][1]), bits(want[j][1])), (sk.kind, "host", j)
 
 
+def test_async_host_calls_match_the_synchronous_ones(ib):
+    """innr_cuda_*_async + innr_cuda_ticket_wait: two calls in flight per device, results bit-identical to the
+    synchronous entries for every corpus kind (fused scans, the k > 128 path and the tensor-core filter path), a third
+    submit is refused, empty results keep the reference's shape, a ticket is good for one wait."""
+    from innr_b200 import stream
+    n, d = 150_000, 64
+    rows = rand_rows(n, d, 51)
+    qs = rand_rows(6, d, 52)
+    db = ib.DeviceBatch.from_rows_flat(rows.reshape(-1), n, d)
+    rng = np.random.default_rng(53)
+    bc = ib.BinaryCorpus.from_words(rng.integers(0, 2**63, size=n * 4, dtype=np.int64).view(np.uint64), n, 256)
+    qw = rng.integers(0, 2**63, size=(6, 4), dtype=np.int64).view(np.uint64)
+    uc = ib.U8Corpus.from_rows(rng.integers(0, 256, size=(n, d), dtype=np.uint8), ib.QuantizationParams(0.01, -1.0))
+
+    def same(a, b):
+        return np.array_equal(a[0], b[0]) and a[1].tobytes() == b[1].tobytes()
+
+    calls = []
+    for j in range(6):
+        for metric in ("cosine", "dot", "l2"):
+            calls.append((lambda j=j, m=metric: stream.submit_knn(m, qs[j], db, 10), lambda j=j, m=metric: ib.batch_knn_many(m, qs[j], db, 10)))
+        calls.append((lambda j=j: stream.submit_hamming_topk(qw[j], bc, 100), lambda j=j: ib.hamming_topk_many(qw[j], bc, 100)))
+        calls.append((lambda j=j: stream.submit_knn_u8(qs[j], uc, 10), lambda j=j: ib.batch_knn_u8_many(qs[j], uc, 10)))
+    calls.append((lambda: stream.submit_knn("cosine", qs[0], db, 200), lambda: ib.batch_knn_many("cosine", qs[0], db, 200)))   # k > 128
+    calls.append((lambda: stream.submit_knn("dot", qs[:4], db, 10), lambda: ib.batch_knn_many("dot", qs[:4], db, 10)))        # filter path
+    calls.append((lambda: stream.submit_hamming_topk(qw[:2], bc, 100), lambda: ib.hamming_topk_many(qw[:2], bc, 100)))
+    want = [sync() for _, sync in calls]
+    pending, got = None, []
+    for submit, _ in calls:
+        t = submit()
+        if pending is not None:
+            got.append(pending.wait())
+        pending = t
+    got.append(pending.wait())
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert same(g, w), i
+    # two in flight, the third is refused until one of them has been collected
+    t1 = stream.submit_knn("cosine", qs[0], db, 10)
+    t2 = stream.submit_knn_u8(qs[1], uc, 10)
+    with pytest.raises(ib.InnrCudaError):
+        stream.submit_knn("cosine", qs[2], db, 10)
+    assert same(t2.wait(), ib.batch_knn_u8_many(qs[1], uc, 10))   # any order
+    t3 = stream.submit_knn("l2", qs[2], db, 10)
+    assert same(t1.wait(), ib.batch_knn_many("cosine", qs[0], db, 10))
+    assert same(t3.wait(), ib.batch_knn_many("l2", qs[2], db, 10))
+    with pytest.raises(ib.InnrCudaError):
+        t3.wait()
+    # k == 0 and an empty corpus: empty result, like the reference
+    idx, sc = stream.submit_knn("dot", qs[0], db, 0).wait()
+    assert idx.shape == (1, 0) and sc.shape == (1, 0)
+    empty = ib.DeviceBatch.from_rows_flat(np.zeros(0, np.float32), 0, d)
+    idx, sc = stream.submit_knn("dot", qs[0], empty, 5).wait()
+    assert idx.shape == (1, 0)
+    # a wrong query length is refused at submit, with the reference's message
+    with pytest.raises(AssertionError):
+        stream.submit_knn("dot", qs[0][:5], db, 3)
+
+
 def test_kernel_timing_is_opt_in(ib):
     """innr_cuda_last_kernel_ms reports only after set_option("kernel_timing", 1): the timed event records are kept out
     of short calls by default (include/innr_cuda.h)."""
