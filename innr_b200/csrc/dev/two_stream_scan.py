@@ -1,6 +1,6 @@
-"""dev: would overlapping consecutive shard scans (two streams, two workspaces) recover the ramp at both ends of a small-shard
-launch? Timing experiment on a 1/8 shard of C2a / C4: one stream vs two alternating streams. With INNR_UNSAFE_NO_WS_ORDER=1
-the library skips its workspace ordering so that the two streams really overlap (results are then NOT valid)."""
+"""dev: consecutive shard scans on ONE stream against TWO alternating streams, on a 1/8 shard of C2a / C4. The library
+keeps two workspaces per device (api.cu lanes), so the two-stream form really overlaps: the head of scan i + 1 fills the
+SMs under the tail of scan i. Measured: f32 0.5565 -> 0.5270 ms per scan, Hamming 0.3030 -> 0.2442 ms."""
 import sys, ctypes as C, torch
 sys.path.insert(0, ".")
 import innr_b200 as ib
