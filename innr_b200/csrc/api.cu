@@ -2723,6 +2723,9 @@ int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, s
       int rc = ctx_for(c, &ctx);
       if (rc) return rc;
       cudaStream_t s = ctx->stream;
+      // the non-root shards leave their work in flight on the device's stream: later host-facing calls are ordered behind
+      // it by that stream, `_dev` calls on caller streams by the lane-0 event this records
+      DevRelease rel(*ctx, s, 0);
       CU(g->pin_q[i].reserve(query_bytes));
       std::memcpy(g->pin_q[i].p, queries, query_bytes);
       CU(ctx->d_query.reserve(query_bytes + 16));
