@@ -339,7 +339,7 @@ int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t
  * returns (the caller may reuse its buffer at once). At most TWO tickets per device may be in flight (a third submit
  * fails with INNR_EBUSY): submit(i + 1) before wait(i) keeps two shard scans overlapping on the device, which is what
  * hides the ramp at both ends of a launch. Tickets belong to the library; a ticket is invalid
- * after its wait. */
+ * after its wait (and after innr_cuda_shutdown); the corpus must stay alive until the ticket has been waited for. */
 typedef struct innr_cuda_ticket innr_cuda_ticket;
 int innr_cuda_batch_knn_async(const innr_cuda_corpus* c, int metric, const float* queries, size_t n_queries,
                               size_t query_len, size_t k, innr_cuda_ticket** out_ticket);
