@@ -23,6 +23,14 @@ class Ticket:
     def __init__(self, handle, kind: str, nq: int, k: int):
         self._h, self.kind, self.nq, self.k = handle, kind, nq, k
 
+    def __del__(self):
+        # a ticket dropped without a wait still occupies one of the device's two slots: collect it
+        try:
+            if getattr(self, "_h", None) is not None:
+                self.wait()
+        except Exception:
+            pass
+
     def wait(self):
         """(idx[nq, min(k, N)], scores-or-distances[nq, min(k, N)]); a ticket can be waited for once."""
         if self._h is None:

@@ -1237,6 +1237,10 @@ def test_async_host_calls_match_the_synchronous_ones(ib):
     assert same(t3.wait(), ib.batch_knn_many("l2", qs[2], db, 10))
     with pytest.raises(ib.InnrCudaError):
         t3.wait()
+    # tickets dropped without a wait free their slots (two more submits go through)
+    stream.submit_knn("cosine", qs[0], db, 10)
+    stream.submit_knn("cosine", qs[1], db, 10)
+    assert same(stream.submit_knn("cosine", qs[3], db, 10).wait(), ib.batch_knn_many("cosine", qs[3], db, 10))
     # k == 0 and an empty corpus: empty result, like the reference
     idx, sc = stream.submit_knn("dot", qs[0], db, 0).wait()
     assert idx.shape == (1, 0) and sc.shape == (1, 0)
