@@ -140,12 +140,16 @@ class ShardedKnn:
         key = (nq, k)
         if key not in self._bufs:
             t = self.torch
-            self._bufs[key] = dict(
+            b = dict(
                 local=t.empty(nq * k, dtype=t.int64, device=device),
                 gathered=t.empty(self.world * nq * k, dtype=t.int64, device=device),
                 idx=t.empty(nq * k, dtype=t.int64, device=device),
                 score=t.empty(nq * k, dtype=t.float32 if self.kind != "binary" else t.int32, device=device),
                 keys=t.empty(nq * k, dtype=t.int64, device=device))
+            # the pointers never change: build the ctypes objects once (a step of a small corpus is host-bound)
+            b["p"] = {name: C.c_void_p(b[name].data_ptr()) for name in ("local", "gathered", "idx", "score", "keys")}
+            b["views"] = (b["idx"].view(nq, k), b["score"].view(nq, k))
+            self._bufs[key] = b
         return self._bufs[key]
 
     def knn_dev(self, dev_queries, nq: int, k: int):
@@ -156,7 +160,7 @@ class ShardedKnn:
         stream = C.c_void_p(t.cuda.current_stream().cuda_stream)
         b = self._buffers(nq, k, dev_queries.device)
         qp = C.c_void_p(dev_queries.data_ptr())
-        lp = C.c_void_p(b["local"].data_ptr())
+        lp = b["p"]["local"]
         if self.kind == "f32":
             L.call("innr_cuda_batch_knn_keys_dev", self.shard.h, self._metric_id, qp, nq, k, lp, stream)
         elif self.kind == "u8":
@@ -182,9 +186,9 @@ class ShardedKnn:
                    C.c_void_p(b["keys"].data_ptr()), C.c_void_p(b["idx"].data_ptr()), None, stream)
             return b["idx"].view(nq, k), (b["keys"] >> 32).view(nq, k)
         m = L.METRIC_L2 if (self.kind == "f32" and self.metric == "l2") else L.METRIC_DOT
-        L.call("innr_cuda_merge_keys_dev", C.c_void_p(src.data_ptr()), n_lists, nq, k, m,
-               None, C.c_void_p(b["idx"].data_ptr()), C.c_void_p(b["score"].data_ptr()), stream)
-        return b["idx"].view(nq, k), b["score"].view(nq, k)
+        L.call("innr_cuda_merge_keys_dev", b["p"]["gathered" if self.world > 1 else "local"], n_lists, nq, k, m,
+               None, b["p"]["idx"], b["p"]["score"], stream)
+        return b["views"]
 
     # ---- pipelined form: consecutive scans overlap, the exchange of query i runs under the scan of query i + 1 ---------
     def _keys(self, dev_queries, nq, k, local, stream):
