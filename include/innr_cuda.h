@@ -349,6 +349,21 @@ int innr_cuda_batch_knn_u8_async(const innr_cuda_corpus* c, const float* queries
                                  size_t k, innr_cuda_ticket** out_ticket);
 int innr_cuda_ticket_wait(innr_cuda_ticket* t, uint64_t* out_idx, float* out_score, uint32_t* out_dist,
                           size_t* out_count);
+/* The same for row shards on pairwise distinct devices (the peer-mapped exchange route of the *_sharded entries):
+ * every device queues its shard scan and its part of the exchange without any host synchronisation, the root's merged
+ * keys come back through pinned memory, and ONE ticket stands for the whole call. Two calls per device group may be in
+ * flight. *out_ticket stays NULL (status INNR_OK) when the result is empty (no rows, k == 0 or no queries).
+ * INNR_EUNSUPPORTED where the exchange route does not apply (shards sharing a device, no peer access, k > 128, a batch
+ * larger than the mailboxes): use the synchronous entry. While asynchronous sharded calls are in flight the synchronous
+ * sharded entries on the same devices return INNR_EBUSY. */
+int innr_cuda_batch_knn_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards, int metric,
+                                      const float* queries, size_t n_queries, size_t query_len, size_t k,
+                                      innr_cuda_ticket** out_ticket);
+int innr_cuda_hamming_topk_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards,
+                                         const uint64_t* query_words, size_t n_queries, size_t query_dim_bits,
+                                         size_t k, innr_cuda_ticket** out_ticket);
+int innr_cuda_batch_knn_u8_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
+                                         size_t n_queries, size_t query_len, size_t k, innr_cuda_ticket** out_ticket);
 
 /* ---- timing hook: device time (ms) of the last host-facing call's kernels, measured with CUDA events on the
  *      launching stream. Off by default (the two timed event records cost a short call ~15 us): enable with

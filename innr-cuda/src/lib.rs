@@ -781,6 +781,34 @@ pub fn hamming_top_k_sharded(shards: &[&BinaryCorpus], query_words: &[u64], quer
     Ok(idx.into_iter().zip(dist).take(count).map(|(i, d)| (i as usize, d)).collect())
 }
 
+/// Asynchronous `knn_sharded` (shards on pairwise distinct devices): one `Ticket` for the whole call, two calls in flight
+/// per device group, no device synchronised until the wait. `Ok(None)`: the result is empty (no rows, k == 0).
+pub fn knn_sharded_submit(shards: &[&F32Corpus], metric: Metric, query: &[f32], k: usize) -> Result<Option<Ticket>> {
+    assert!(!shards.is_empty(), "no shards");
+    let ptrs: Vec<*const innr_cuda_corpus> = shards.iter().map(|s| s.as_ptr()).collect();
+    let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+    check(unsafe { innr_cuda_batch_knn_sharded_async(ptrs.as_ptr(), ptrs.len(), metric.id(), query.as_ptr(), 1, query.len(), k, &mut t) })?;
+    Ok(if t.is_null() { None } else { Some(Ticket { t, n_queries: 1, k, binary: false }) })
+}
+
+/// Asynchronous `hamming_top_k_sharded`; read the ticket with `Ticket::wait_hamming`.
+pub fn hamming_top_k_sharded_submit(shards: &[&BinaryCorpus], query_words: &[u64], query_dim_bits: usize, k: usize) -> Result<Option<Ticket>> {
+    assert!(!shards.is_empty(), "no shards");
+    let ptrs: Vec<*const innr_cuda_corpus> = shards.iter().map(|s| s.as_ptr()).collect();
+    let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+    check(unsafe { innr_cuda_hamming_topk_sharded_async(ptrs.as_ptr(), ptrs.len(), query_words.as_ptr(), 1, query_dim_bits, k, &mut t) })?;
+    Ok(if t.is_null() { None } else { Some(Ticket { t, n_queries: 1, k, binary: true }) })
+}
+
+/// Asynchronous `knn_u8_sharded`.
+pub fn knn_u8_sharded_submit(shards: &[&U8Corpus], query: &[f32], k: usize) -> Result<Option<Ticket>> {
+    assert!(!shards.is_empty(), "no shards");
+    let ptrs: Vec<*const innr_cuda_corpus> = shards.iter().map(|s| s.as_ptr()).collect();
+    let mut t: *mut innr_cuda_ticket = std::ptr::null_mut();
+    check(unsafe { innr_cuda_batch_knn_u8_sharded_async(ptrs.as_ptr(), ptrs.len(), query.as_ptr(), 1, query.len(), k, &mut t) })?;
+    Ok(if t.is_null() { None } else { Some(Ticket { t, n_queries: 1, k, binary: false }) })
+}
+
 /// `batch_knn_u8` over row shards on different devices.
 pub fn knn_u8_sharded(shards: &[&U8Corpus], query: &[f32], k: usize) -> Result<Vec<(usize, f32)>> {
     assert!(!shards.is_empty(), "no shards");

@@ -96,6 +96,9 @@ SIGNATURES = {
     "innr_cuda_hamming_topk_async": [vp, u64p, sz, sz, sz, handle_p],
     "innr_cuda_batch_knn_u8_async": [vp, f32p, sz, sz, sz, handle_p],
     "innr_cuda_ticket_wait": [vp, u64p, f32p, u32p, szp],
+    "innr_cuda_batch_knn_sharded_async": [vp, sz, ci, f32p, sz, sz, sz, handle_p],
+    "innr_cuda_hamming_topk_sharded_async": [vp, sz, u64p, sz, sz, sz, handle_p],
+    "innr_cuda_batch_knn_u8_sharded_async": [vp, sz, f32p, sz, sz, sz, handle_p],
     "innr_cuda_exchange_create": [ci, ci, sz, handle_p],
     "innr_cuda_exchange_ipc_handle": [vp, vp],
     "innr_cuda_exchange_connect_ipc": [vp, vp],

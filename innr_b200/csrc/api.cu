@@ -50,6 +50,7 @@ struct innr_cuda_corpus {
   uint32_t* dev_order = nullptr;
 };
 
+constexpr int MAX_SHARD_DEVICES = 16;
 // One asynchronous host-buffer call in flight (innr_cuda_*_async -> innr_cuda_ticket_wait). A device owns two of
 // these, one per workspace lane: stream, event and staging buffers live as long as the device context.
 struct innr_cuda_ticket {
@@ -62,6 +63,16 @@ struct innr_cuda_ticket {
   cudaEvent_t done = nullptr;
   void *d_query = nullptr, *d_keys = nullptr, *h_in = nullptr, *h_out = nullptr;  // h_*: pinned
   size_t d_query_cap = 0, d_keys_cap = 0, h_in_cap = 0, h_out_cap = 0;
+  // a sharded call (innr_cuda_*_sharded_async): this is the root's ticket, `siblings` are the other devices' (released
+  // with it), the merged keys come out of the exchange launch into d_merged, rows are k wide, and the exchange's status
+  // word travels behind the keys
+  bool sharded = false;
+  size_t krow = 0;
+  void* d_merged = nullptr;
+  size_t d_merged_cap = 0;
+  innr_cuda_ticket* siblings[MAX_SHARD_DEVICES] = {};
+  int n_siblings = 0;
+  std::atomic<int>* group_busy = nullptr;  // the group's in-flight counter (decremented at the wait)
 };
 
 // One rank's end of the peer-mapped key exchange (exchange.cu).
@@ -431,6 +442,7 @@ int innr_cuda_shutdown(void) {
       if (t.d_keys) cudaFree(t.d_keys);
       if (t.h_in) cudaFreeHost(t.h_in);
       if (t.h_out) cudaFreeHost(t.h_out);
+      if (t.d_merged) cudaFree(t.d_merged);
       if (t.done) cudaEventDestroy(t.done);
       if (t.stream) cudaStreamDestroy(t.stream);
     }
@@ -2237,6 +2249,9 @@ static int async_begin(const innr_cuda_corpus* c, DeviceCtx** ctx_out, innr_cuda
   t->nq = nq;
   t->k = k;
   t->kk = kk;
+  t->sharded = false;  // the slot may have served a sharded call before
+  t->n_siblings = 0;
+  t->group_busy = nullptr;
   if ((rc = grow(&t->h_in, &t->h_in_cap, query_bytes, true))) return rc;
   if ((rc = grow(&t->d_query, &t->d_query_cap, query_bytes + 16, false))) return rc;
   if ((rc = grow(&t->d_keys, &t->d_keys_cap, nq * kk * sizeof(uint64_t), false))) return rc;
@@ -2371,18 +2386,30 @@ int innr_cuda_ticket_wait(innr_cuda_ticket* t, uint64_t* out_idx, float* out_sco
   if (t->kk && (!out_idx || (t->kind == 1 ? !out_dist : !out_score))) return fail(INNR_EINVAL, "null argument");
   // block on this call only, outside the device mutex: other threads keep submitting meanwhile
   cudaError_t e = cudaEventSynchronize(t->done);
+  for (int j = 0; j < t->n_siblings; ++j) {  // the other devices' parts of a sharded call: long finished, release them
+    innr_cuda_ticket* sib = t->siblings[j];
+    cudaError_t es = cudaEventSynchronize(sib->done);
+    if (e == cudaSuccess) e = es;
+    EntryGuard slk(sib->device);
+    sib->in_flight = false;
+  }
   EntryGuard lk(t->device);
   t->in_flight = false;
+  t->n_siblings = 0;
+  if (t->sharded && t->group_busy) t->group_busy->fetch_sub(1);
   if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(ticket)");
   const uint64_t* keys = (const uint64_t*)t->h_out;
+  const size_t row = t->sharded ? t->krow : t->kk;
+  if (t->sharded && t->kk && *(const unsigned*)(keys + t->nq * t->krow) != 0)
+    return fail(INNR_ECUDA, "sharded call: a shard did not publish its keys within the exchange timeout");
   for (size_t q = 0; q < t->nq && t->kk; ++q) {
     if (t->kind == 1) {
       for (size_t j = 0; j < t->kk; ++j) {
-        out_idx[q * t->k + j] = keys[q * t->kk + j] & 0xFFFFFFFFull;
-        out_dist[q * t->k + j] = (uint32_t)(keys[q * t->kk + j] >> 32);
+        out_idx[q * t->k + j] = keys[q * row + j] & 0xFFFFFFFFull;
+        out_dist[q * t->k + j] = (uint32_t)(keys[q * row + j] >> 32);
       }
     } else {
-      decode_keys_f32(keys + q * t->kk, t->kk, t->kind == 2 || t->metric != INNR_METRIC_L2, out_idx + q * t->k,
+      decode_keys_f32(keys + q * row, t->kk, t->kind == 2 || t->metric != INNR_METRIC_L2, out_idx + q * t->k,
                       out_score + q * t->k);
     }
   }
@@ -2640,6 +2667,10 @@ struct ShardGroup {  // one per distinct ordered device list
   std::vector<Buf> pin_q, pin_out;  // per shard pinned staging (queries in, root results out)
   std::vector<Buf> d_idx, d_score;  // root outputs
   std::mutex mu;                    // one sharded call at a time per group (the exchange numbers its calls)
+  // asynchronous calls: at most two in flight (one per mailbox parity); `consumed[p]` is recorded on the root's stream
+  // behind its merge of the call with parity p -- the other devices wait for it before they publish into that parity again
+  std::atomic<int> async_in_flight{0};
+  cudaEvent_t consumed[2] = {nullptr, nullptr};
 };
 std::mutex g_groups_mu;
 std::map<std::vector<int>, std::unique_ptr<ShardGroup>> g_groups;
@@ -2650,6 +2681,8 @@ void shard_groups_shutdown() {
     ShardGroup* g = kv.second.get();
     if (!g) continue;
     g->pool.reset();  // joins the workers
+    for (int p = 0; p < 2; ++p)
+      if (g->consumed[p]) cudaEventDestroy(g->consumed[p]);
     for (size_t i = 0; i < g->ex.size(); ++i) {
       cudaSetDevice(g->ex[i]->device);
       g->pin_q[i].release();
@@ -2710,6 +2743,7 @@ int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, s
                          uint64_t* out_idx, float* out_score, uint32_t* out_dist) {
   if (k > MAX_FUSED_K || nq * k > g->ex[0]->slot_keys) return INNR_EUNSUPPORTED;
   std::lock_guard<std::mutex> call_lk(g->mu);
+  if (g->async_in_flight.load()) return fail(INNR_EBUSY, "asynchronous sharded calls are in flight on these devices: wait for their tickets first");
   std::vector<int> rcs(n_shards, INNR_OK);
   std::vector<std::string> errs(n_shards);
   const size_t out_bytes = nq * k * (sizeof(uint64_t) + sizeof(uint32_t));
@@ -2763,6 +2797,133 @@ int sharded_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, s
   std::memcpy(out_idx, h, nq * k * sizeof(uint64_t));
   if (want_dist) std::memcpy(out_dist, h + nq * k * sizeof(uint64_t), nq * k * sizeof(uint32_t));
   else std::memcpy(out_score, h + nq * k * sizeof(uint64_t), nq * k * sizeof(float));
+  return INNR_OK;
+}
+
+// Asynchronous form of the exchange route: every device queues its part on the stream of one of its two asynchronous
+// slots (the slot = the mailbox parity of this call, so consecutive calls alternate and two can be in flight), the root
+// keeps the merged KEYS in device memory and copies them to pinned memory behind the merge; nothing synchronises. The
+// returned ticket is the root's; innr_cuda_ticket_wait releases the other devices' slots with it. `enqueue_keys(i, ctx,
+// dev_query, dev_keys, stream, lane)` queues shard i's local top-k.
+template <class ScanOnly, class EnqueueKeys>
+int sharded_async_via_exchange(ShardGroup* g, const innr_cuda_corpus* const* shards, size_t n_shards, const void* queries,
+                               size_t query_bytes, size_t nq, size_t k, size_t kk, int metric, ScanOnly scan_only,
+                               EnqueueKeys enqueue_keys, innr_cuda_ticket** out_ticket) {
+  if (k > MAX_FUSED_K || nq * k > g->ex[0]->slot_keys || n_shards > (size_t)MAX_SHARD_DEVICES)
+    return fail(INNR_EUNSUPPORTED, "asynchronous sharded call: k > 128 or the batch does not fit the mailboxes (use the synchronous entry)");
+  std::lock_guard<std::mutex> call_lk(g->mu);
+  if (g->async_in_flight.load() >= 2) return fail(INNR_EBUSY, "two asynchronous sharded calls are already in flight: wait for a ticket first");
+  const int p = (int)((g->ex[0]->calls + 1) & 1);  // slot = mailbox parity of this call
+  // reserve slot p on every device and make its stream wait until the root has consumed the previous call of this parity
+  std::vector<innr_cuda_ticket*> tk(n_shards, nullptr);
+  int rc = INNR_OK;
+  for (size_t i = 0; i < n_shards && rc == INNR_OK; ++i) {
+    EntryGuard lk(shards[i]->device);
+    DeviceCtx* ctx;
+    rc = ensure_ctx(shards[i]->device, &ctx, WS_NONE);
+    if (rc) break;
+    innr_cuda_ticket* t = &ctx->async_slot[p];
+    if (t->in_flight) {
+      rc = fail(INNR_EBUSY, "an asynchronous call is in flight in the slot this sharded call needs: wait for its ticket first");
+      break;
+    }
+    auto prepare = [&]() -> int {
+      if (!t->stream) {
+        static const bool blocking = getenv("INNR_ASYNC_BLOCKING_WAIT") != nullptr;
+        CU(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0)));
+      }
+      if (i == 0 && !g->consumed[p]) CU(cudaEventCreateWithFlags(&g->consumed[p], cudaEventDisableTiming));
+      return INNR_OK;
+    };
+    rc = prepare();
+    if (rc) break;
+    t->in_flight = true;  // reserved
+    tk[i] = t;
+  }
+  if (rc == INNR_OK)
+    for (size_t i = 1; i < n_shards && rc == INNR_OK; ++i) {
+      cudaError_t e = cudaStreamWaitEvent(tk[i]->stream, g->consumed[p], 0);  // a never-recorded event counts as complete
+      if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamWaitEvent(consumed)");
+    }
+  if (rc) {
+    for (size_t i = 0; i < n_shards; ++i)
+      if (tk[i]) {
+        EntryGuard lk(shards[i]->device);
+        tk[i]->in_flight = false;
+      }
+    return rc;
+  }
+  std::vector<int> rcs(n_shards, INNR_OK);
+  std::vector<std::string> errs(n_shards);
+  std::function<void(size_t)> job = [&](size_t i) {
+    auto body = [&]() -> int {
+      const innr_cuda_corpus* c = shards[i];
+      innr_cuda_exchange* x = g->ex[i];
+      innr_cuda_ticket* t = tk[i];
+      ++x->calls;  // first thing: a shard that fails below must not leave the ranks' call numbers out of step
+      EntryGuard lk(c->device);
+      DeviceCtx* ctx;
+      int r = ensure_ctx(c->device, &ctx, WS_NONE);
+      if (r) return r;
+      t->device = c->device;
+      t->kind = c->kind;
+      t->metric = metric;
+      t->nq = nq;
+      t->k = k;
+      t->kk = kk;
+      t->krow = k;
+      t->sharded = i == 0;
+      t->n_siblings = 0;
+      if ((r = grow(&t->h_in, &t->h_in_cap, query_bytes, true))) return r;
+      if ((r = grow(&t->d_query, &t->d_query_cap, query_bytes + 16, false))) return r;
+      if ((r = grow(&t->d_keys, &t->d_keys_cap, nq * k * sizeof(uint64_t), false))) return r;
+      std::memcpy(t->h_in, queries, query_bytes);
+      CU(cudaMemcpyAsync(t->d_query, t->h_in, query_bytes, cudaMemcpyHostToDevice, t->stream));
+      int lane = 0;
+      r = ensure_ctx(c->device, &ctx, scan_only(i) ? WS_DEV_SCAN : WS_DEV, t->stream, &lane);
+      if (r) return r;
+      {
+        DevRelease rel(*ctx, t->stream, lane);
+        r = enqueue_keys(i, ctx, t->d_query, (uint64_t*)t->d_keys, t->stream, lane);
+        if (r) return r;
+      }
+      if (i != 0) {
+        CU(launch_exchange_merge(ex_view(x), (const uint64_t*)t->d_keys, nq, k, x->calls, 1, 0, nullptr, nullptr, nullptr,
+                                 nullptr, t->stream, &g_launches));
+        CU(cudaEventRecord(t->done, t->stream));
+        return INNR_OK;
+      }
+      if ((r = grow(&t->d_merged, &t->d_merged_cap, nq * k * sizeof(uint64_t), false))) return r;
+      if ((r = grow(&t->h_out, &t->h_out_cap, nq * k * sizeof(uint64_t) + 16, true))) return r;
+      CU(launch_exchange_merge(ex_view(x), (const uint64_t*)t->d_keys, nq, k, x->calls, 0, metric != INNR_METRIC_L2,
+                               (uint64_t*)t->d_merged, nullptr, nullptr, nullptr, t->stream, &g_launches));
+      CU(cudaEventRecord(g->consumed[p], t->stream));
+      CU(cudaMemcpyAsync(t->h_out, t->d_merged, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, t->stream));
+      CU(cudaMemcpyAsync((char*)t->h_out + nq * k * sizeof(uint64_t), x->dev_status, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                         t->stream));
+      CU(cudaEventRecord(t->done, t->stream));
+      return INNR_OK;
+    };
+    rcs[i] = body();
+    if (rcs[i]) errs[i] = t_err;
+  };
+  g->pool->run(job);
+  for (size_t i = 0; i < n_shards; ++i)
+    if (rcs[i]) {
+      // what was queued stays queued; give the slots back once their streams have drained
+      for (size_t j = 0; j < n_shards; ++j) {
+        cudaStreamSynchronize(tk[j]->stream);
+        EntryGuard lk(shards[j]->device);
+        tk[j]->in_flight = false;
+      }
+      return fail(rcs[i], "shard " + std::to_string(i) + ": " + errs[i]);
+    }
+  innr_cuda_ticket* root = tk[0];
+  for (size_t i = 1; i < n_shards; ++i) root->siblings[root->n_siblings++] = tk[i];
+  root->group_busy = &g->async_in_flight;
+  g->async_in_flight.fetch_add(1);
+  *out_ticket = root;
   return INNR_OK;
 }
 
@@ -2969,6 +3130,111 @@ int innr_cuda_batch_knn_u8_sharded(const innr_cuda_corpus* const* shards, size_t
   }
   if (out_count) *out_count = kk;
   return INNR_OK;
+}
+
+// ---- asynchronous forms of the sharded entries (exchange route only: shards on pairwise distinct devices) ------------
+int innr_cuda_batch_knn_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards, int metric,
+                                      const float* queries, size_t n_queries, size_t query_len, size_t k,
+                                      innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 0) return fail(INNR_EINVAL, "need f32 PDX shards");
+    if (shards[i]->d != shards[0]->d) return fail(INNR_EINVAL, "shards differ in dimension");
+    n_total += shards[i]->n;
+  }
+  if (query_len != shards[0]->d) return fail(INNR_EINVAL, "query.len() != batch.dimension");
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;  // empty result: no ticket
+  if (!queries) return fail(INNR_EINVAL, "null argument");
+  int mode;
+  int rc = metric_to_mode(metric, &mode);
+  if (rc) return rc;
+  ShardGroup* g = shard_group_for(shards, n_shards);
+  if (!g) return fail(INNR_EUNSUPPORTED, "asynchronous sharded calls need two or more shards on pairwise distinct devices with peer access");
+  return sharded_async_via_exchange(
+      g, shards, n_shards, queries, n_queries * query_len * sizeof(float), n_queries, k, k < n_total ? k : n_total, metric,
+      [&](size_t i) { return shards[i]->n == 0 || knn_is_scan_only(shards[i], mode, n_queries, k); },
+      [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk, cudaStream_t s, int lane) -> int {
+        innr_cuda_corpus* c = const_cast<innr_cuda_corpus*>(shards[i]);
+        if (c->n == 0) {
+          CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), s));
+          return INNR_OK;
+        }
+        return knn_keys_dev(c, ctx, mode, (const float*)dq, n_queries, k, dk, s, lane);
+      },
+      out_ticket);
+}
+
+int innr_cuda_hamming_topk_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards, const uint64_t* query_words,
+                                         size_t n_queries, size_t query_dim_bits, size_t k, innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 1) return fail(INNR_EINVAL, "need binary shards");
+    if (shards[i]->dim_bits != query_dim_bits) return fail(INNR_EINVAL, "innr::binary_hamming: dimension mismatch");
+    n_total += shards[i]->n;
+  }
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;  // empty result: no ticket
+  if (!query_words) return fail(INNR_EINVAL, "null argument");
+  if (shards[0]->words == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional codes: use innr_cuda_hamming_topk_sharded");
+  ShardGroup* g = shard_group_for(shards, n_shards);
+  if (!g) return fail(INNR_EUNSUPPORTED, "asynchronous sharded calls need two or more shards on pairwise distinct devices with peer access");
+  const innr_cuda_corpus* c0 = shards[0];
+  const size_t qw = 2 * c0->chunks, rem = c0->dim_bits % 64;
+  std::vector<uint64_t> padded(n_queries * qw, 0);  // padded to whole 128-bit chunks, padding bits masked
+  for (size_t q = 0; q < n_queries; ++q)
+    for (size_t w = 0; w < c0->words; ++w) {
+      uint64_t x = query_words[q * c0->words + w];
+      if (w + 1 == c0->words && rem) x &= (1ull << rem) - 1;
+      padded[q * qw + w] = x;
+    }
+  return sharded_async_via_exchange(
+      g, shards, n_shards, padded.data(), padded.size() * sizeof(uint64_t), n_queries, k, k < n_total ? k : n_total,
+      INNR_METRIC_L2, [&](size_t) { return true; },
+      [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk, cudaStream_t s, int lane) -> int {
+        const innr_cuda_corpus* c = shards[i];
+        if (c->n == 0) {
+          CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), s));
+          return INNR_OK;
+        }
+        return hamming_keys(c, ctx, (const uint64_t*)dq, n_queries, k, dk, s, lane);
+      },
+      out_ticket);
+}
+
+int innr_cuda_batch_knn_u8_sharded_async(const innr_cuda_corpus* const* shards, size_t n_shards, const float* queries,
+                                         size_t n_queries, size_t query_len, size_t k, innr_cuda_ticket** out_ticket) {
+  if (!out_ticket) return fail(INNR_EINVAL, "null out_ticket");
+  *out_ticket = nullptr;
+  if (!shards || n_shards == 0) return fail(INNR_EINVAL, "no shards");
+  size_t n_total = 0;
+  for (size_t i = 0; i < n_shards; ++i) {
+    if (!shards[i] || shards[i]->kind != 2) return fail(INNR_EINVAL, "need u8 shards");
+    if (shards[i]->d != shards[0]->d) return fail(INNR_EINVAL, "shards differ in dimension");
+    n_total += shards[i]->n;
+  }
+  if (n_total == 0 || k == 0 || n_queries == 0) return INNR_OK;  // src/scalar.rs:376-378 (before any length check): no ticket
+  if (query_len != shards[0]->d) return fail(INNR_EINVAL, "asymmetric_dot_u8_precomputed: dimension mismatch");
+  if (!queries) return fail(INNR_EINVAL, "null argument");
+  if (shards[0]->d == 0) return fail(INNR_EUNSUPPORTED, "zero-dimensional u8 corpus");
+  ShardGroup* g = shard_group_for(shards, n_shards);
+  if (!g) return fail(INNR_EUNSUPPORTED, "asynchronous sharded calls need two or more shards on pairwise distinct devices with peer access");
+  return sharded_async_via_exchange(
+      g, shards, n_shards, queries, n_queries * query_len * sizeof(float), n_queries, k, k < n_total ? k : n_total,
+      INNR_METRIC_DOT, [&](size_t) { return true; },
+      [&](size_t i, DeviceCtx* ctx, void* dq, uint64_t* dk, cudaStream_t s, int lane) -> int {
+        const innr_cuda_corpus* c = shards[i];
+        if (c->n == 0) {
+          CU(cudaMemsetAsync(dk, 0xFF, n_queries * k * sizeof(uint64_t), s));
+          return INNR_OK;
+        }
+        return u8_keys(c, ctx, (const float*)dq, n_queries, k, dk, s, lane);
+      },
+      out_ticket);
 }
 
 }  // extern "C"

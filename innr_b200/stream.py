@@ -35,6 +35,10 @@ class Ticket:
         """(idx[nq, min(k, N)], scores-or-distances[nq, min(k, N)]); a ticket can be waited for once."""
         if self._h is None:
             raise L.InnrCudaError("ticket was already waited for")
+        if not self._h:  # the library hands out no ticket for an empty result (sharded forms)
+            self._h = None
+            return (np.zeros((self.nq, 0), np.uint64),
+                    np.zeros((self.nq, 0), np.uint32 if self.kind == "binary" else np.float32))
         kk = max(self.k, 1)
         idx = np.zeros((self.nq, kk), np.uint64)
         cnt = C.c_size_t(0)
@@ -80,4 +84,42 @@ def submit_knn_u8(queries, corpus, k: int) -> Ticket:
     nq, qlen = qs.shape
     h = C.c_void_p()
     L.call("innr_cuda_batch_knn_u8_async", corpus.h, qs.ctypes.data_as(L.f32p), nq, qlen, k, C.byref(h))
+    return Ticket(h, "u8", nq, k)
+
+
+# ---- row shards on different devices of this process (innr_cuda_*_sharded_async): one ticket per call ------------------
+def _shard_handles(shards):
+    return (C.c_void_p * len(shards))(*[sh.h for sh in shards])
+
+
+def submit_knn_sharded(metric: str, queries, shards, k: int) -> Ticket:
+    qs = np.ascontiguousarray(queries, dtype=np.float32)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq, qlen = qs.shape
+    m = {"dot": L.METRIC_DOT, "cosine": L.METRIC_COSINE, "l2": L.METRIC_L2}[metric]
+    h = C.c_void_p()
+    L.call("innr_cuda_batch_knn_sharded_async", _shard_handles(shards), len(shards), m, qs.ctypes.data_as(L.f32p), nq, qlen, k,
+           C.byref(h))
+    return Ticket(h, "f32", nq, k)
+
+
+def submit_hamming_topk_sharded(query_words, shards, k: int) -> Ticket:
+    qs = np.ascontiguousarray(query_words, dtype=np.uint64)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    h = C.c_void_p()
+    L.call("innr_cuda_hamming_topk_sharded_async", _shard_handles(shards), len(shards), qs.ctypes.data_as(L.u64p), qs.shape[0],
+           shards[0].dimension, k, C.byref(h))
+    return Ticket(h, "binary", qs.shape[0], k)
+
+
+def submit_knn_u8_sharded(queries, shards, k: int) -> Ticket:
+    qs = np.ascontiguousarray(queries, dtype=np.float32)
+    if qs.ndim == 1:
+        qs = qs.reshape(1, -1)
+    nq, qlen = qs.shape
+    h = C.c_void_p()
+    L.call("innr_cuda_batch_knn_u8_sharded_async", _shard_handles(shards), len(shards), qs.ctypes.data_as(L.f32p), nq, qlen, k,
+           C.byref(h))
     return Ticket(h, "u8", nq, k)

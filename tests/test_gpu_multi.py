@@ -113,3 +113,69 @@ def test_c_abi_sharded_entries_over_devices(oracle):
         ui, us = sharded.batch_knn_u8_sharded(q8, ush, 10)
         wi, ws = oracle.batch_knn_u8_many(q8, mat, op, 10, n_threads=2)
         assert np.array_equal(ui, wi) and us.tobytes() == ws.tobytes(), rep
+
+
+@needs2
+def test_c_abi_sharded_async_over_devices():
+    """innr_cuda_*_sharded_async: one ticket per call, two calls in flight, every device's part queued without a host
+    synchronisation. A run of calls with different queries -- f32 (three metrics), Hamming, u8, interleaved -- equals the
+    synchronous sharded entries bit for bit; a third submit and a synchronous sharded call are refused while two are in
+    flight; single-device asynchronous calls keep working next to it."""
+    import torch
+    import innr_b200 as ib
+    from innr_b200 import sharded, stream
+    n_dev = min(torch.cuda.device_count(), 4)
+    n, d = 120_001, 48
+    rng = np.random.default_rng(24)
+    rows = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    codes = rng.integers(0, 2**62, size=(n, 3), dtype=np.uint64)
+    mat = rng.integers(0, 256, size=(n, d), dtype=np.uint8)
+    gp = ib.QuantizationParams.from_range(-1.0, 1.0)
+    cuts = [n * r // n_dev for r in range(n_dev + 1)]
+    shards, bsh, ush = [], [], []
+    for dev, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        ib.init(dev)
+        shards.append(ib.DeviceBatch.from_rows_flat(rows[a:b].reshape(-1), b - a, d, index_base=a))
+        bsh.append(ib.BinaryCorpus.from_words(codes[a:b], b - a, 192, index_base=a))
+        ush.append(ib.U8Corpus.from_rows(mat[a:b], gp, index_base=a, dimension=d))
+    ib.init(0)
+    qs = rng.integers(-3, 4, size=(12, d)).astype(np.float32)
+    qc = rng.integers(0, 2**62, size=(12, 3), dtype=np.uint64)
+    q8 = rng.uniform(-1, 1, size=(12, d)).astype(np.float32)
+    calls = []
+    for j in range(12):
+        m = ("dot", "cosine", "l2")[j % 3]
+        calls.append((lambda j=j, m=m: stream.submit_knn_sharded(m, qs[j], shards, 10), lambda j=j, m=m: sharded.batch_knn_sharded(m, qs[j], shards, 10)))
+        calls.append((lambda j=j: stream.submit_hamming_topk_sharded(qc[j], bsh, 100), lambda j=j: sharded.hamming_topk_sharded(qc[j], bsh, 100)))
+        calls.append((lambda j=j: stream.submit_knn_u8_sharded(q8[j], ush, 10), lambda j=j: sharded.batch_knn_u8_sharded(q8[j], ush, 10)))
+    calls.append((lambda: stream.submit_knn_sharded("cosine", qs[:3], shards, 7), lambda: sharded.batch_knn_sharded("cosine", qs[:3], shards, 7)))
+    want = [sync() for _, sync in calls]
+    pending, got = None, []
+    for submit, _ in calls:
+        t = submit()
+        if pending is not None:
+            got.append(pending.wait())
+        pending = t
+    got.append(pending.wait())
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert np.array_equal(g[0], w[0]) and g[1].tobytes() == w[1].tobytes(), i
+    # two in flight: a third submit and a synchronous sharded call are refused, then everything drains
+    t1 = stream.submit_knn_sharded("dot", qs[0], shards, 10)
+    t2 = stream.submit_knn_sharded("dot", qs[1], shards, 10)
+    with pytest.raises(ib.InnrCudaError):
+        stream.submit_knn_sharded("dot", qs[2], shards, 10)
+    with pytest.raises(ib.InnrCudaError):
+        sharded.batch_knn_sharded("dot", qs[2], shards, 10)
+    a, b = t1.wait(), t2.wait()
+    assert np.array_equal(a[0], sharded.batch_knn_sharded("dot", qs[0], shards, 10)[0])
+    assert np.array_equal(b[0], sharded.batch_knn_sharded("dot", qs[1], shards, 10)[0])
+    # single-device asynchronous calls and sharded ones share the devices' two slots
+    t1 = stream.submit_knn_sharded("dot", qs[3], shards, 10)
+    t2 = stream.submit_knn("dot", qs[4], shards[0], 10)
+    assert np.array_equal(t2.wait()[0], ib.batch_knn_many("dot", qs[4], shards[0], 10)[0])
+    assert np.array_equal(t1.wait()[0], sharded.batch_knn_sharded("dot", qs[3], shards, 10)[0])
+    # empty result: no ticket inside, empty arrays out; k > 128 is the synchronous entry's business
+    idx, sc = stream.submit_knn_sharded("dot", qs[0], shards, 0).wait()
+    assert idx.shape == (1, 0) and sc.shape == (1, 0)
+    with pytest.raises(NotImplementedError):
+        stream.submit_knn_sharded("dot", qs[0], shards, 300)
