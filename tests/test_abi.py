@@ -54,6 +54,9 @@ def test_no_cpu_fallback_without_device():
         innr_b200.encode_binary([1.0, -1.0], 0.0)
     with pytest.raises(innr_b200.InnrCudaError):
         innr_b200.quantize_u8([0.5], innr_b200.QuantizationParams.from_range(0.0, 1.0))
+    from innr_b200 import stream
+    with pytest.raises(innr_b200.InnrCudaError):   # the asynchronous forms upload lazily like the synchronous ones
+        stream.submit_knn("dot", [1.0, 1.0], b, 1)
 
 
 def test_host_side_types_match_reference_contracts():
