@@ -1109,37 +1109,53 @@ def test_two_lanes_overlapping_scans_of_every_kind(ib, oracle):
         L.call("innr_cuda_batch_knn_u8_keys_dev", uc.h, C.c_void_p(dq[j].data_ptr()), 1, k,
                C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
 
-    kinds = [(f32, 10), (ham, 100), (u8, 10)]
-    main = torch.cuda.current_stream()
-    alone = {}
-    for fn, k in kinds:
-        for j in range(6):
-            out = torch.empty(k, dtype=torch.int64, device="cuda")
-            fn(j, out, main)
-            torch.cuda.synchronize()
-            alone[(fn, j)] = out.cpu().numpy().copy()
-    big_alone = torch.empty(200, dtype=torch.int64, device="cuda")
-    f32(0, big_alone, main, k=200)
-    torch.cuda.synchronize()
-    streams = [torch.cuda.Stream() for _ in range(3)]
-    for rep in range(15):
-        outs = []
-        for i in range(18):
-            fn, k = kinds[i % len(kinds)]
-            j = (i + rep) % 6
-            out = torch.empty(k, dtype=torch.int64, device="cuda")
-            fn(j, out, streams[i % 3])
-            outs.append((fn, j, out))
-            if i == 7:   # k > 128 takes the scores pass + selection: lane 0 and the scratch buffers
-                big = torch.empty(200, dtype=torch.int64, device="cuda")
-                f32(0, big, streams[1], k=200)
-            if i == 11:  # a host-facing call right in the middle
-                host = ib.batch_knn_many("cosine", qs[2], db, 10)
+    def f32_pair(j, out, st, k=10):   # two queries per call: the query-blocked scan / pair kernels on either lane
+        L.call("innr_cuda_batch_knn_keys_dev", db.h, L.METRIC_DOT, C.c_void_p(dq[j % 5].data_ptr()), 2, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    def ham_pair(j, out, st, k=100):
+        L.call("innr_cuda_hamming_topk_keys_dev", bc.h, C.c_void_p(dqw[j % 5].data_ptr()), 2, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    def u8_pair(j, out, st, k=10):
+        L.call("innr_cuda_batch_knn_u8_keys_dev", uc.h, C.c_void_p(dq[j % 5].data_ptr()), 2, k,
+               C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+
+    ib.set_option("knn_tc", 0)   # two f32 queries on 400 K rows would take the tensor-core filter (lane 0 only)
+    try:
+        kinds = [(f32, 10), (ham, 100), (u8, 10), (f32_pair, 20), (ham_pair, 200), (u8_pair, 20)]
+        main = torch.cuda.current_stream()
+        alone = {}
+        for fn, k in kinds:
+            for j in range(6):
+                out = torch.empty(k, dtype=torch.int64, device="cuda")
+                fn(j, out, main)
+                torch.cuda.synchronize()
+                alone[(fn, j)] = out.cpu().numpy().copy()
+        big_alone = torch.empty(200, dtype=torch.int64, device="cuda")
+        f32(0, big_alone, main, k=200)
         torch.cuda.synchronize()
-        for fn, j, out in outs:
-            assert np.array_equal(out.cpu().numpy(), alone[(fn, j)]), (rep, fn.__name__, j)
-        assert np.array_equal(big.cpu().numpy(), big_alone.cpu().numpy())
-        assert (alone[(f32, 2)].view(np.uint64) & np.uint64(0xFFFFFFFF)).tolist() == host[0][0].tolist()
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        for rep in range(15):
+            outs = []
+            for i in range(18):
+                fn, k = kinds[i % len(kinds)]
+                j = (i + rep) % 6
+                out = torch.empty(k, dtype=torch.int64, device="cuda")
+                fn(j, out, streams[i % 3])
+                outs.append((fn, j, out))
+                if i == 7:   # k > 128 takes the scores pass + selection: lane 0 and the scratch buffers
+                    big = torch.empty(200, dtype=torch.int64, device="cuda")
+                    f32(0, big, streams[1], k=200)
+                if i == 11:  # a host-facing call right in the middle
+                    host = ib.batch_knn_many("cosine", qs[2], db, 10)
+            torch.cuda.synchronize()
+            for fn, j, out in outs:
+                assert np.array_equal(out.cpu().numpy(), alone[(fn, j)]), (rep, fn.__name__, j)
+            assert np.array_equal(big.cpu().numpy(), big_alone.cpu().numpy())
+            assert (alone[(f32, 2)].view(np.uint64) & np.uint64(0xFFFFFFFF)).tolist() == host[0][0].tolist()
+    finally:
+        ib.set_option("knn_tc", 1)
 
 
 def test_pipelined_single_rank_matches_knn_dev(ib):
